@@ -1,0 +1,73 @@
+"""Shared helpers for the tests: golden loading, case definitions, tie-aware index comparison."""
+import os
+
+import numpy as np
+import torch
+
+from oracle import init_state as oinit
+from oracle import vqvae_oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+
+CASES = {
+    'cfg1': dict(S=64, B=8, ch=128, nrb=2, mult=(1, 2, 2, 4), K=256, D=256, seed=1234),
+    'tiny': dict(S=16, B=4, ch=32, nrb=1, mult=(1, 2), K=64, D=32, seed=4321),
+}
+Q_PARAMS = {
+    'standard': dict(type='standard', commitment_cost=0.25),
+    'ema': dict(type='ema', commitment_cost=0.25, decay=0.95, epsilon=1e-5),
+    'entropy': dict(type='entropy', ent_loss_ratio=0.1, ent_temperature=0.01, ent_loss_type='softmax',
+                    commitment_cost=0.25),
+    'gumbel': dict(type='gumbel', straight_through=False, temp=1.0, kl_cost=0.00859375),
+}
+
+
+def golden(name):
+    return np.load(os.path.join(GOLDEN, name + '.npz'))
+
+
+def seeded_inputs(case_name, qtype):
+    """Regenerate (state dict, images in [-1,1]) exactly as oracle/make_golden.py did."""
+    c = CASES[case_name]
+    sd = oinit.init_state(qtype, c['K'], c['D'], c['ch'], c['nrb'], c['mult'], seed=c['seed'])
+    x = torch.rand(c['B'], 3, c['S'], c['S']) * 2 - 1
+    return sd, x
+
+
+def oracle_cfg(case_name, qtype):
+    c = CASES[case_name]
+    return {'num_res_blocks': c['nrb'], 'channel_multipliers': c['mult'], 'quantizer': dict(Q_PARAMS[qtype])}
+
+
+def rel_err(a, b):
+    a = torch.as_tensor(a).detach().double().flatten().cpu()
+    b = torch.as_tensor(b).detach().double().flatten().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def max_rel(a, b, floor=None):
+    """max |a-b| / max(|b|, floor); floor defaults to 1e-3 * max|b| (elementwise rel. error is meaningless
+    near zero crossings)."""
+    a = torch.as_tensor(a).detach().double().cpu()
+    b = torch.as_tensor(b).detach().double().cpu()
+    if floor is None:
+        floor = 1e-3 * float(b.abs().max()) + 1e-30
+    return float(((a - b).abs() / torch.clamp(b.abs(), min=floor)).max())
+
+
+def tie_aware_index_check(idx, ref_idx, flat, codebook, order='standard', ulps=4):
+    """Indices must be bit-exact except where the reference's own fp32 distances are tied/near-tied
+    (SURVEY.md section 7 'argmin tie fragility').  Returns (n_exact, n_tie_class, n_bad)."""
+    idx = torch.as_tensor(idx).reshape(-1).long().cpu()
+    ref_idx = torch.as_tensor(ref_idx).reshape(-1).long().cpu()
+    mism = (idx != ref_idx).nonzero().flatten()
+    n_bad = 0
+    if mism.numel():
+        d = orc.l2_distances(flat[mism].cpu().float(), codebook.cpu().float(), order)
+        da = d.gather(1, idx[mism, None]).squeeze(1)
+        db = d.gather(1, ref_idx[mism, None]).squeeze(1)
+        scale = torch.maximum(da.abs(), db.abs()).clamp_min(1e-30)
+        tol = ulps * torch.finfo(torch.float32).eps * torch.maximum(scale, (flat[mism].cpu().float() ** 2).sum(1))
+        n_bad = int(((da - db).abs() > tol).sum())
+    return int(idx.numel() - mism.numel()), int(mism.numel() - n_bad), n_bad
