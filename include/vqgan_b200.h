@@ -1,0 +1,176 @@
+/*
+ * vqgan_b200.h -- C ABI of libvqgan_b200.so (hand-written sm_100a CUDA kernels for the VQ-VAE / VQGAN
+ * training step).
+ *
+ * Conventions:
+ *   - every entry point is extern "C", takes raw DEVICE pointers, plain integer sizes and the CUDA stream to
+ *     launch on (cudaStream_t passed as void*), and returns 0 on success or a negative vqb_status;
+ *     vqb_last_error() returns a thread-local human-readable message for the last failure;
+ *   - nothing is allocated inside the library: the caller owns inputs, outputs and workspaces;
+ *   - nothing synchronises: kernels are enqueued on `stream` and the call returns;
+ *   - activations are NHWC ("channels last") -- logical [N,C,H,W] tensors stored as [N][H][W][C];
+ *   - dtype arguments are vqb_dtype (VQB_F32 = fp32 storage, VQB_BF16 = bf16 storage; arithmetic is fp32 in
+ *     the SIMT kernels and bf16 x bf16 -> fp32 in the tcgen05 kernels);
+ *   - the reference interface each entry point replaces is cited as file:line relative to the reference repo
+ *     (SerezD/vqvae-vqgan-pytorch-lightning @ 277d909).
+ *
+ * The reference's own native boundary is the StyleGAN2 op loader (custom_ops.get_plugin,
+ * vqvae/modules/loss/stylegan2_discriminator/utils/custom_ops.py:49) with POD parameter structs launched on
+ * the current ATen stream (ops/bias_act.cpp:32-90, ops/upfirdn2d.cpp:16-92); this header generalises that
+ * pattern to the whole training step.  INTEGRATION.md shows the ctypes binding a maintainer adds.
+ */
+#ifndef VQGAN_B200_H
+#define VQGAN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum { VQB_OK = 0, VQB_ERR_ARG = -1, VQB_ERR_CUDA = -2, VQB_ERR_UNSUPPORTED = -3 } vqb_status;
+typedef enum { VQB_F32 = 0, VQB_BF16 = 1 } vqb_dtype;
+typedef enum { VQB_ACT_NONE = 0, VQB_ACT_TANH = 1, VQB_ACT_SILU = 2, VQB_ACT_LRELU = 3, VQB_ACT_RELU = 4 } vqb_act;
+
+const char* vqb_last_error(void);
+/* library / build identification: returns e.g. "vqgan_b200 0.1 sm_100a" */
+const char* vqb_version(void);
+/* 1 when the current device is compute capability 10.x (tcgen05 kernels usable), else 0 */
+int vqb_device_supports_tcgen05(void);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Layout plumbing
+ * ---------------------------------------------------------------------------------------------------- */
+/* NCHW fp32 -> NHWC (dtype out), optionally clamp to [lo,hi] then (x-shift)*scale: the image normalisation
+ * of BaseVQVAE.preprocess_batch (vqvae/modules/abstract_modules/base_autoencoder.py:41-50) without kornia
+ * augmentation.  do_clamp=0 skips the clamp. */
+int vqb_nchw_to_nhwc(const float* x, void* y, int out_dtype, int64_t N, int64_t C, int64_t H, int64_t W,
+                     int do_clamp, float lo, float hi, float shift, float scale, void* stream);
+/* NHWC (dtype in) -> NCHW fp32, y = x*scale + shift, optional clamp (base_autoencoder.py:52-61). */
+int vqb_nhwc_to_nchw(const void* x, int in_dtype, float* y, int64_t N, int64_t C, int64_t H, int64_t W,
+                     float scale, float shift, int do_clamp, float lo, float hi, void* stream);
+/* dtype conversion of a flat buffer */
+int vqb_convert(const void* x, int in_dtype, void* y, int out_dtype, int64_t n, void* stream);
+
+/* Conv2d weight [Co][Ci][KH][KW] fp32 (nn.Conv2d layout, vqvae/modules/autoencoder.py:55-61) ->
+ *   mode 0 (forward  GEMM-B): wp[(kh*KW+kw)*Ci+ci][co]
+ *   mode 1 (dgrad    GEMM-B): wp[((KH-1-kh)*KW+(KW-1-kw))*Co+co][ci]   (taps flipped, channels swapped)
+ *   mode 2 (tcgen05 forward, K-major): wp[co][(kh*KW+kw)*Ci+ci]
+ *   mode 3 (tcgen05 dgrad,   K-major): wp[ci][((KH-1-kh)*KW+(KW-1-kw))*Co+co]
+ * scale multiplies every weight (StyleGAN2 equalised-lr gain, discriminator.py:148,165). */
+int vqb_pack_conv_weight(const float* w, void* wp, int out_dtype, int mode, int Co, int Ci, int KH, int KW,
+                         float scale, void* stream);
+/* inverse of mode 0 for gradients: dw[co][ci][kh][kw] = scale * dwp[(kh*KW+kw)*Ci+ci][co] */
+int vqb_unpack_conv_wgrad(const float* dwp, float* dw, int Co, int Ci, int KH, int KW, float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Convolution as implicit GEMM (replaces F.conv2d behind nn.Conv2d: autoencoder.py:55-61,102,114,133,153,170)
+ *   y[n,oh,ow,co] = act( sum_{kh,kw,ci} x[n, oh*stride-pad+kh, ow*stride-pad+kw, ci] * w[co,ci,kh,kw]
+ *                        + bias[co] ) * gain + residual[n,oh,ow,co]
+ * impl 0 = fp32 SIMT (strict parity path), impl 1 = tcgen05/TMA bf16 (fast path; x,y bf16; Ci%64==0, Co%64==0).
+ * wp is the packed weight for that impl (mode 0 for impl 0, mode 2 for impl 1).  bias / residual may be NULL.
+ * dgrad is the same call on dy with the dgrad-packed weight (stride 1 only).
+ * ---------------------------------------------------------------------------------------------------- */
+int vqb_conv2d_fwd(int impl, const void* x, int x_dtype, const void* wp, const float* bias, const void* residual,
+                   void* y, int y_dtype, int N, int H, int W, int Ci, int Co, int KH, int KW, int pad, int stride,
+                   int act, float act_alpha, float gain, void* stream);
+/* weight gradient: dwp[(kh*KW+kw)*Ci+ci][co] (fp32, mode-0 packed layout) = sum_pix x_shift * dy.
+ * dwp must be zero-filled by the caller (split-K partial sums are accumulated with atomics). */
+int vqb_conv2d_wgrad(int impl, const void* x, int x_dtype, const void* dy, int dy_dtype, float* dwp,
+                     int N, int H, int W, int Ci, int Co, int KH, int KW, int pad, int stride, void* stream);
+/* column sums: out[c] (fp32, caller zero-fills) += sum_p a[p][c]; used for bias gradients */
+int vqb_colsum(const void* a, int a_dtype, float* out, int64_t P, int C, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * GroupNorm (custom, UNBIASED variance, eps 1e-6: autoencoder.py:25-39) fused with SiLU
+ * ---------------------------------------------------------------------------------------------------- */
+/* sums[b][g][2] (double, caller zero-fills) += (sum x, sum x^2) over the group's (C/G)*HW elements */
+int vqb_gn_stats(const void* x, int x_dtype, double* sums, int N, int HW, int C, int G, void* stream);
+/* stats[b][g] = (mean, 1/sqrt(var_unbiased + eps)) */
+int vqb_gn_finalize(const double* sums, float* stats, int N, int HW, int C, int G, float eps, void* stream);
+/* y = act( (x-mean)*rstd * gamma[c] + beta[c] ), act in {NONE, SILU} */
+int vqb_gn_apply(const void* x, int x_dtype, const float* stats, const float* gamma, const float* beta, void* y,
+                 int y_dtype, int N, int HW, int C, int G, int act, void* stream);
+/* backward pass 1: part[b][c][2] (double, caller zero-fills) += (sum_pix ds, sum_pix ds*xhat),
+ * ds = dy * act'(xhat*gamma+beta) */
+int vqb_gn_bwd_reduce(const void* x, int x_dtype, const void* dy, int dy_dtype, const float* stats,
+                      const float* gamma, const float* beta, double* part, int N, int HW, int C, int G, int act,
+                      void* stream);
+/* backward finalize: coef[b][g] = (sum_g/n, sum_g_xhat/(n-1)); dgamma[c], dbeta[c] (overwritten) */
+int vqb_gn_bwd_finalize(const double* part, const float* gamma, float* coef, float* dgamma, float* dbeta, int N,
+                        int HW, int C, int G, void* stream);
+/* backward pass 2: dx = rstd * (g - coef0 - xhat*coef1), g = ds*gamma */
+int vqb_gn_bwd_apply(const void* x, int x_dtype, const void* dy, int dy_dtype, const float* stats,
+                     const float* gamma, const float* beta, const float* coef, void* dx, int dx_dtype, int N, int HW,
+                     int C, int G, int act, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Resampling (Downsample = avg_pool2d(2,2) autoencoder.py:89-91; Upsample = nearest-exact x2 :103-106)
+ * ---------------------------------------------------------------------------------------------------- */
+/* y[n,h,w,c] = scale * sum_{i,j<2} x[n,2h+i,2w+j,c]   (x is [N,2H,2W,C]; avg-pool: scale=.25; upsample bwd: 1) */
+int vqb_down2(const void* x, void* y, int dtype, int N, int H, int W, int C, float scale, void* stream);
+/* y[n,h,w,c] = scale * x[n,h/2,w/2,c]                 (y is [N,2H,2W,C]; upsample: scale=1; avg-pool bwd: .25) */
+int vqb_up2(const void* x, void* y, int dtype, int N, int H, int W, int C, float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Elementwise / reductions used by the loss heads (vqvae/model.py:272-275, loss/loss.py:118-121)
+ * ---------------------------------------------------------------------------------------------------- */
+/* out[0] += sum (a-b)^2 ; out[1] += sum |a-b|   (double[2], caller zero-fills) */
+int vqb_diff_sums(const void* a, int a_dtype, const void* b, int b_dtype, double* out, int64_t n, void* stream);
+/* da = c2 * 2*(a-b) * up2 + c1 * sign(a-b) * up1, (up2, up1) = upstream ? (upstream[0], upstream[1]) : (1, 1)
+ * (device scalars: the upstream gradients of the L2 and L1 means); when y_tanh!=0 `a` is a tanh output and the
+ * result is additionally multiplied by (1-a^2) (grad wrt the pre-activation) */
+int vqb_diff_grad(const void* a, int a_dtype, const void* b, int b_dtype, void* da, int da_dtype, float c1, float c2,
+                  const float* upstream, int y_tanh, int64_t n, void* stream);
+/* dx = dy * act'(from the saved OUTPUT y): tanh -> 1-y^2 ; used after a conv with a fused tanh epilogue */
+int vqb_act_bwd_from_output(const void* y, int y_dtype, const void* dy, int dy_dtype, void* dx, int dx_dtype, int act,
+                            float alpha, float gain, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Vector quantisation (vqvae/modules/vector_quantizers.py)
+ * ---------------------------------------------------------------------------------------------------- */
+/* Fused pairwise-L2 distance -> argmin -> gather -> straight-through value -> loss partial -> code histogram
+ * (+ EMA cluster sums).  Replaces VectorQuantizer.forward :23-61, EMAVectorQuantizer.forward :128-180 (the
+ * part before the EMA update), EntropyVectorQuantizer.forward :337-349 (argmin/gather), vec_to_codes
+ * :63-84,182-203,358-381.
+ *   z        [N][D] fp32 (the NHWC latent, 'b c h w -> (b h w) c')
+ *   codebook [K][D] fp32
+ *   order    0: d = (|z|^2 + |e|^2) - 2 z.e   (:37-39,142-144)   1: d = (|z|^2 - 2 z.e) + |e|^2   (:337-340)
+ *   q_out    [N][D] fp32 or NULL: z + (e[idx] - z)  (forward value of the straight-through estimator :58,177)
+ *   idx_out  [N] int64 (first minimal index, torch.argmin semantics)
+ *   sse      double[1] or NULL, caller zero-fills: += sum (e[idx]-z)^2
+ *   counts   [K] float or NULL, caller zero-fills: += histogram of idx (= encodings.sum(0) :160; bincount model.py:290)
+ *   dw       [K][D] float or NULL, caller zero-fills: += sum_{i: idx_i=k} z_i  (= encodings.T @ flat_x :166)
+ * workspace: vqb_vq_workspace_bytes(N,K,D) bytes. */
+size_t vqb_vq_workspace_bytes(int64_t N, int K, int D);
+int vqb_vq_assign(const float* z, const float* codebook, int order, float* q_out, int64_t* idx_out, double* sse,
+                  float* counts, float* dw, int64_t N, int K, int D, void* workspace, size_t workspace_bytes,
+                  void* stream);
+/* EMA codebook update (vector_quantizers.py:158-169), in place:
+ *   c = decay*ema_count + (1-decay)*counts ; ema_count = (c+eps)/(b + K*eps)*b   (b = IMAGE batch: defect B7)
+ *   ema_weight = decay*ema_weight + (1-decay)*dw ; codebook = ema_weight / ema_count[:,None] */
+int vqb_vq_ema_update(float* ema_count, float* ema_weight, float* codebook, const float* counts, const float* dw,
+                      int K, int D, float decay, float eps, float batch, void* stream);
+/* Backward of the standard/EMA/entropy commitment + codebook MSE terms.  `q` holds the
+ * per-row quantised vectors e[idx_i] as produced by vqb_vq_assign (q_out), so the EMA path may already have
+ * overwritten the codebook (vector_quantizers.py:169 runs before backward):
+ *   dz[i]  = g_q[i] + (g_loss[0] * 2*beta/(N*D)) * (z[i]-q[i])             (g_q may be NULL -> 0)
+ *   dcb[k] += (g_loss[0] * 2*cb_scale/(N*D)) * sum_{i:idx_i=k} (q[i]-z[i])   (dcb NULL for EMA; caller zero-fills) */
+int vqb_vq_backward(const float* z, const float* q, const int64_t* idx, const float* g_q, const float* g_loss,
+                    float beta, float cb_scale, float* dz, float* dcb, int64_t N, int K, int D, void* stream);
+/* gather rows: out[i] = codebook[idx[i]] (BaseVectorQuantizer.codes_to_vec base_quantizer.py:53-61) */
+int vqb_vq_gather(const float* codebook, const int64_t* idx, float* out, int64_t N, int K, int D, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Optimizer (torch.optim.AdamW as configured by VQVAE.configure_optimizers, vqvae/model.py:411-438)
+ * ---------------------------------------------------------------------------------------------------- */
+/* One fused pass over a flat fp32 range: decoupled weight decay, bias-corrected Adam.  grad_scale multiplies
+ * the gradient first (1/world_size after a sum all-reduce). */
+int vqb_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+              float weight_decay, int step, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VQGAN_B200_H */

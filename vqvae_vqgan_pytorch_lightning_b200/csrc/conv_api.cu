@@ -1,0 +1,45 @@
+// C-ABI entry points for convolution: dispatch between the fp32 SIMT implicit GEMM (impl 0, conv_simt.cu) and
+// the tcgen05/TMA bf16 implicit GEMM (impl 1, conv_tc.cu).
+#include "common.cuh"
+
+int vqb_conv2d_fwd_simt(const void* x, int x_dtype, const float* wp, const float* bias, const void* residual, void* y,
+                        int y_dtype, int N, int H, int W, int Ci, int Co, int KH, int KW, int pad, int stride, int act,
+                        float alpha, float gain, cudaStream_t stream);
+int vqb_conv2d_wgrad_simt(const void* x, int x_dtype, const void* dy, int dy_dtype, float* dwp, int N, int H, int W, int Ci,
+                          int Co, int KH, int KW, int pad, int stride, cudaStream_t stream);
+int vqb_conv2d_fwd_tc(const void* x, const void* wp, const float* bias, const void* residual, void* y, int y_dtype, int N,
+                      int H, int W, int Ci, int Co, int KH, int KW, int pad, int act, float alpha, float gain,
+                      cudaStream_t stream);
+int vqb_conv2d_wgrad_tc(const void* x, const void* dy, float* dwp, int N, int H, int W, int Ci, int Co, int KH, int KW,
+                        int pad, cudaStream_t stream);
+
+extern "C" int vqb_conv2d_fwd(int impl, const void* x, int x_dtype, const void* wp, const float* bias, const void* residual,
+                              void* y, int y_dtype, int N, int H, int W, int Ci, int Co, int KH, int KW, int pad, int stride,
+                              int act, float act_alpha, float gain, void* stream) {
+    VQB_CHECK_ARG(x && wp && y, "conv2d_fwd: null pointer");
+    if (impl == 0)
+        return vqb_conv2d_fwd_simt(x, x_dtype, (const float*)wp, bias, residual, y, y_dtype, N, H, W, Ci, Co, KH, KW, pad,
+                                   stride, act, act_alpha, gain, as_stream(stream));
+    if (impl == 1) {
+        VQB_CHECK_ARG(x_dtype == VQB_BF16, "conv2d_fwd(tcgen05): x must be bf16");
+        VQB_CHECK_ARG(stride == 1, "conv2d_fwd(tcgen05): stride must be 1");
+        return vqb_conv2d_fwd_tc(x, wp, bias, residual, y, y_dtype, N, H, W, Ci, Co, KH, KW, pad, act, act_alpha, gain,
+                                 as_stream(stream));
+    }
+    vqb_set_error("conv2d_fwd: unknown impl %d", impl);
+    return VQB_ERR_ARG;
+}
+
+extern "C" int vqb_conv2d_wgrad(int impl, const void* x, int x_dtype, const void* dy, int dy_dtype, float* dwp, int N, int H,
+                                int W, int Ci, int Co, int KH, int KW, int pad, int stride, void* stream) {
+    VQB_CHECK_ARG(x && dy && dwp, "conv2d_wgrad: null pointer");
+    if (impl == 0)
+        return vqb_conv2d_wgrad_simt(x, x_dtype, dy, dy_dtype, dwp, N, H, W, Ci, Co, KH, KW, pad, stride, as_stream(stream));
+    if (impl == 1) {
+        VQB_CHECK_ARG(x_dtype == VQB_BF16 && dy_dtype == VQB_BF16, "conv2d_wgrad(tcgen05): x and dy must be bf16");
+        VQB_CHECK_ARG(stride == 1, "conv2d_wgrad(tcgen05): stride must be 1");
+        return vqb_conv2d_wgrad_tc(x, dy, dwp, N, H, W, Ci, Co, KH, KW, pad, as_stream(stream));
+    }
+    vqb_set_error("conv2d_wgrad: unknown impl %d", impl);
+    return VQB_ERR_ARG;
+}

@@ -1,0 +1,341 @@
+// fp32 SIMT implicit-GEMM convolution (strict-parity path; also serves the 3-channel edge layers of the bf16
+// path).  NHWC activations, packed weights wp[(kh,kw,ci)][co].
+//
+//   forward : C[m = (n,oh,ow)][co] = sum_k A[m][k = (kh,kw,ci)] * wp[k][co]      A gathered on the fly (no im2col)
+//   wgrad   : dwp[m = (kh,kw,ci)][co] = sum_p A'[m][p = (n,oh,ow)] * dy[p][co]    split over p, fp32 atomics
+//
+// Block tile 128 x 128 x 16, 256 threads, 8 x 8 register micro-tile per thread, register-staged double
+// buffering (global loads of tile t+1 are in flight while tile t is multiplied).  The tensor-core path for
+// the wide layers is conv_tc.cu; this kernel's roof is the fp32 FMA pipe (148 SMs x 128 FMA/clk).
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 16, PADM = 4;
+
+struct ConvGeom {
+    int N, H, W, Ci, Co, KH, KW, pad, stride, OH, OW;
+    int64_t M;   // N*OH*OW
+    int K;       // KH*KW*Ci
+};
+
+__device__ __forceinline__ float apply_act(float v, int act, float alpha) {
+    if (act == VQB_ACT_TANH) return tanhf(v);
+    if (act == VQB_ACT_SILU) return silu_f(v);
+    if (act == VQB_ACT_LRELU) return v > 0.f ? v : v * alpha;
+    if (act == VQB_ACT_RELU) return fmaxf(v, 0.f);
+    return v;
+}
+
+__device__ __forceinline__ void mma_tile(const float (*As)[BM + PADM], const float (*Bs)[BN], float (&acc)[8][8], int ty, int tx) {
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+        float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+        float4 a1 = *reinterpret_cast<const float4*>(&As[k][64 + ty * 4]);
+        float4 b0 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+        float4 b1 = *reinterpret_cast<const float4*>(&Bs[k][64 + tx * 4]);
+        float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------------
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(256, 2)
+conv_fwd_simt_kernel(const TIn* __restrict__ x, const float* __restrict__ wp, const float* __restrict__ bias,
+                     const TOut* __restrict__ residual, TOut* __restrict__ y, ConvGeom g, int act, float alpha, float gain) {
+    __shared__ __align__(16) float As[2][BK][BM + PADM];
+    __shared__ __align__(16) float Bs[2][BK][BN];
+    const int tid = threadIdx.x;
+    const int ty = tid >> 4, tx = tid & 15;
+    const int64_t m0 = (int64_t)blockIdx.x * BM;
+    const int n0 = blockIdx.y * BN;
+    const bool vecA = (g.Ci % 4 == 0);
+    const bool vecB = (g.Co % 4 == 0);
+
+    // A loader: rows ar, ar+64; k offset akc..akc+3
+    const int ar = tid >> 2, akc = (tid & 3) * 4;
+    int a_ih0[2], a_iw0[2];
+    int64_t a_base[2];
+    bool a_ok[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        int64_t m = m0 + ar + r * 64;
+        a_ok[r] = m < g.M;
+        int64_t mm = a_ok[r] ? m : 0;
+        int ow = (int)(mm % g.OW); int64_t t = mm / g.OW; int oh = (int)(t % g.OH); int n = (int)(t / g.OH);
+        a_ih0[r] = oh * g.stride - g.pad;
+        a_iw0[r] = ow * g.stride - g.pad;
+        a_base[r] = (int64_t)n * g.H * g.W * g.Ci;
+    }
+    // B loader: rows bk, bk+8; n offset bn..bn+3
+    const int bk = tid >> 5, bn = (tid & 31) * 4;
+
+    float a_reg[2][4], b_reg[2][4];
+    auto load_tiles = [&](int kt) {
+        const int k0 = kt * BK;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            int k = k0 + akc;
+            if (vecA) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (a_ok[r] && k < g.K) {
+                    int tap = k / g.Ci, ci = k - tap * g.Ci;
+                    int kh = tap / g.KW, kw = tap - kh * g.KW;
+                    int ih = a_ih0[r] + kh, iw = a_iw0[r] + kw;
+                    if (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W)
+                        v = ld4(x + a_base[r] + ((int64_t)ih * g.W + iw) * g.Ci + ci);
+                }
+                a_reg[r][0] = v.x; a_reg[r][1] = v.y; a_reg[r][2] = v.z; a_reg[r][3] = v.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float v = 0.f;
+                    int kk = k + j;
+                    if (a_ok[r] && kk < g.K) {
+                        int tap = kk / g.Ci, ci = kk - tap * g.Ci;
+                        int kh = tap / g.KW, kw = tap - kh * g.KW;
+                        int ih = a_ih0[r] + kh, iw = a_iw0[r] + kw;
+                        if (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W)
+                            v = ld1(x + a_base[r] + ((int64_t)ih * g.W + iw) * g.Ci + ci);
+                    }
+                    a_reg[r][j] = v;
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            int k = k0 + bk + r * 8;
+            int n = n0 + bn;
+            if (vecB) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (k < g.K && n < g.Co) v = *reinterpret_cast<const float4*>(wp + (int64_t)k * g.Co + n);
+                b_reg[r][0] = v.x; b_reg[r][1] = v.y; b_reg[r][2] = v.z; b_reg[r][3] = v.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) b_reg[r][j] = (k < g.K && n + j < g.Co) ? wp[(int64_t)k * g.Co + n + j] : 0.f;
+            }
+        }
+    };
+    auto store_tiles = [&](int buf) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) As[buf][akc + j][ar + r * 64] = a_reg[r][j];
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+            *reinterpret_cast<float4*>(&Bs[buf][bk + r * 8][bn]) = make_float4(b_reg[r][0], b_reg[r][1], b_reg[r][2], b_reg[r][3]);
+    };
+
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+    const int KT = (g.K + BK - 1) / BK;
+    load_tiles(0);
+    store_tiles(0);
+    __syncthreads();
+    for (int kt = 0; kt < KT; ++kt) {
+        const int cur = kt & 1;
+        if (kt + 1 < KT) load_tiles(kt + 1);
+        mma_tile(As[cur], Bs[cur], acc, ty, tx);
+        if (kt + 1 < KT) store_tiles(cur ^ 1);
+        __syncthreads();
+    }
+
+    // epilogue
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        int64_t m = m0 + ((i < 4) ? (ty * 4 + i) : (64 + ty * 4 + i - 4));
+        if (m >= g.M) continue;
+#pragma unroll
+        for (int jh = 0; jh < 2; ++jh) {
+            int n = n0 + jh * 64 + tx * 4;
+            if (n >= g.Co) continue;
+            float v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float t = acc[i][jh * 4 + j];
+                if (bias && n + j < g.Co) t += bias[n + j];
+                t = apply_act(t, act, alpha) * gain;
+                v[j] = t;
+            }
+            int64_t off = m * g.Co + n;
+            if (vecB) {
+                if (residual) { float4 r = ld4(residual + off); v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w; }
+                st4(y + off, make_float4(v[0], v[1], v[2], v[3]));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (n + j < g.Co) {
+                        float t = v[j];
+                        if (residual) t += ld1(residual + off + j);
+                        st1(y + off + j, t);
+                    }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// weight gradient
+// ---------------------------------------------------------------------------------------------------
+template <typename TIn, typename TG>
+__global__ void __launch_bounds__(256, 2)
+conv_wgrad_simt_kernel(const TIn* __restrict__ x, const TG* __restrict__ dy, float* __restrict__ dwp, ConvGeom g,
+                       int64_t p_chunk) {
+    __shared__ __align__(16) float As[2][BK][BM + PADM];
+    __shared__ __align__(16) float Bs[2][BK][BN];
+    const int tid = threadIdx.x;
+    const int ty = tid >> 4, tx = tid & 15;
+    const int m0 = blockIdx.x * BM;      // over K = (kh,kw,ci)
+    const int n0 = blockIdx.y * BN;      // over Co
+    const int64_t pbeg = (int64_t)blockIdx.z * p_chunk;
+    int64_t pend = pbeg + p_chunk; if (pend > g.M) pend = g.M;
+    const bool vecA = (g.Ci % 4 == 0);
+    const bool vecB = (g.Co % 4 == 0);
+
+    // loaders: p rows lk, lk+8 ; m / n offset lc..lc+3
+    const int lk = tid >> 5, lc = (tid & 31) * 4;
+    // per-thread decomposition of its A columns m = m0+lc+j -> (tap, ci)
+    int a_kh[4], a_kw[4], a_ci[4];
+    bool a_mok[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        int m = m0 + lc + j;
+        a_mok[j] = m < g.K;
+        int mm = a_mok[j] ? m : 0;
+        int tap = mm / g.Ci;
+        a_ci[j] = mm - tap * g.Ci;
+        a_kh[j] = tap / g.KW;
+        a_kw[j] = tap - a_kh[j] * g.KW;
+    }
+
+    float a_reg[2][4], b_reg[2][4];
+    auto load_tiles = [&](int64_t p0) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            int64_t p = p0 + lk + r * 8;
+            bool pok = p < pend;
+            int64_t pp = pok ? p : 0;
+            int ow = (int)(pp % g.OW); int64_t t = pp / g.OW; int oh = (int)(t % g.OH); int n = (int)(t / g.OH);
+            int ih0 = oh * g.stride - g.pad, iw0 = ow * g.stride - g.pad;
+            const TIn* xb = x + (int64_t)n * g.H * g.W * g.Ci;
+            if (vecA) {   // the 4 columns share one tap (Ci % 4 == 0)
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                int ih = ih0 + a_kh[0], iw = iw0 + a_kw[0];
+                if (pok && a_mok[0] && ih >= 0 && ih < g.H && iw >= 0 && iw < g.W)
+                    v = ld4(xb + ((int64_t)ih * g.W + iw) * g.Ci + a_ci[0]);
+                a_reg[r][0] = v.x; a_reg[r][1] = v.y; a_reg[r][2] = v.z; a_reg[r][3] = v.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float v = 0.f;
+                    int ih = ih0 + a_kh[j], iw = iw0 + a_kw[j];
+                    if (pok && a_mok[j] && ih >= 0 && ih < g.H && iw >= 0 && iw < g.W)
+                        v = ld1(xb + ((int64_t)ih * g.W + iw) * g.Ci + a_ci[j]);
+                    a_reg[r][j] = v;
+                }
+            }
+            int n_ = n0 + lc;
+            if (vecB) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (pok && n_ < g.Co) v = ld4(dy + p * g.Co + n_);
+                b_reg[r][0] = v.x; b_reg[r][1] = v.y; b_reg[r][2] = v.z; b_reg[r][3] = v.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) b_reg[r][j] = (pok && n_ + j < g.Co) ? ld1(dy + p * g.Co + n_ + j) : 0.f;
+            }
+        }
+    };
+    auto store_tiles = [&](int buf) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            *reinterpret_cast<float4*>(&As[buf][lk + r * 8][lc]) = make_float4(a_reg[r][0], a_reg[r][1], a_reg[r][2], a_reg[r][3]);
+            *reinterpret_cast<float4*>(&Bs[buf][lk + r * 8][lc]) = make_float4(b_reg[r][0], b_reg[r][1], b_reg[r][2], b_reg[r][3]);
+        }
+    };
+
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+    if (pbeg >= pend) return;
+    const int64_t PT = (pend - pbeg + BK - 1) / BK;
+    load_tiles(pbeg);
+    store_tiles(0);
+    __syncthreads();
+    for (int64_t pt = 0; pt < PT; ++pt) {
+        const int cur = (int)(pt & 1);
+        if (pt + 1 < PT) load_tiles(pbeg + (pt + 1) * BK);
+        mma_tile(As[cur], Bs[cur], acc, ty, tx);
+        if (pt + 1 < PT) store_tiles(cur ^ 1);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        int m = m0 + ((i < 4) ? (ty * 4 + i) : (64 + ty * 4 + i - 4));
+        if (m >= g.K) continue;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            int n = n0 + ((j < 4) ? (tx * 4 + j) : (64 + tx * 4 + j - 4));
+            if (n < g.Co) atomicAdd(dwp + (int64_t)m * g.Co + n, acc[i][j]);
+        }
+    }
+}
+
+inline int make_geom(ConvGeom& g, int N, int H, int W, int Ci, int Co, int KH, int KW, int pad, int stride) {
+    if (!(N > 0 && H > 0 && W > 0 && Ci > 0 && Co > 0 && KH > 0 && KW > 0 && pad >= 0 && stride >= 1)) {
+        vqb_set_error("conv2d: bad geometry N=%d H=%d W=%d Ci=%d Co=%d KH=%d KW=%d pad=%d stride=%d", N, H, W, Ci, Co, KH, KW, pad, stride);
+        return VQB_ERR_ARG;
+    }
+    g.N = N; g.H = H; g.W = W; g.Ci = Ci; g.Co = Co; g.KH = KH; g.KW = KW; g.pad = pad; g.stride = stride;
+    g.OH = (H + 2 * pad - KH) / stride + 1;
+    g.OW = (W + 2 * pad - KW) / stride + 1;
+    if (g.OH <= 0 || g.OW <= 0) { vqb_set_error("conv2d: empty output"); return VQB_ERR_ARG; }
+    g.M = (int64_t)N * g.OH * g.OW;
+    g.K = KH * KW * Ci;
+    return VQB_OK;
+}
+
+}  // namespace
+
+int vqb_conv2d_fwd_simt(const void* x, int x_dtype, const float* wp, const float* bias, const void* residual, void* y,
+                        int y_dtype, int N, int H, int W, int Ci, int Co, int KH, int KW, int pad, int stride, int act,
+                        float alpha, float gain, cudaStream_t stream) {
+    ConvGeom g;
+    int rc = make_geom(g, N, H, W, Ci, Co, KH, KW, pad, stride); if (rc) return rc;
+    dim3 grid((unsigned)ceil_div64(g.M, BM), (unsigned)((Co + BN - 1) / BN));
+    VQB_DISPATCH_1(x_dtype, TIn, VQB_DISPATCH_1(y_dtype, TOut,
+        (conv_fwd_simt_kernel<TIn, TOut><<<grid, 256, 0, stream>>>((const TIn*)x, wp, bias, (const TOut*)residual, (TOut*)y, g, act, alpha, gain));))
+    VQB_CHECK_LAUNCH("conv2d_fwd_simt");
+    return VQB_OK;
+}
+
+int vqb_conv2d_wgrad_simt(const void* x, int x_dtype, const void* dy, int dy_dtype, float* dwp, int N, int H, int W, int Ci,
+                          int Co, int KH, int KW, int pad, int stride, cudaStream_t stream) {
+    ConvGeom g;
+    int rc = make_geom(g, N, H, W, Ci, Co, KH, KW, pad, stride); if (rc) return rc;
+    int gm = (g.K + BM - 1) / BM, gn = (Co + BN - 1) / BN;
+    // split the pixel reduction so that the grid is ~4 waves of 148 SMs x 2 resident CTAs
+    int64_t want = (int64_t)148 * 2 * 4;
+    int64_t splits = want / ((int64_t)gm * gn); if (splits < 1) splits = 1;
+    int64_t max_splits = ceil_div64(g.M, 64); if (splits > max_splits) splits = max_splits;
+    int64_t chunk = ceil_div64(ceil_div64(g.M, splits), BK) * BK;
+    splits = ceil_div64(g.M, chunk);
+    dim3 grid(gm, gn, (unsigned)splits);
+    VQB_DISPATCH_1(x_dtype, TIn, VQB_DISPATCH_1(dy_dtype, TG,
+        (conv_wgrad_simt_kernel<TIn, TG><<<grid, 256, 0, stream>>>((const TIn*)x, (const TG*)dy, dwp, g, chunk));))
+    VQB_CHECK_LAUNCH("conv2d_wgrad_simt");
+    return VQB_OK;
+}

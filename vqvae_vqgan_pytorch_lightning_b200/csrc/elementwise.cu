@@ -1,0 +1,418 @@
+// HBM-bound plumbing kernels: layout changes, weight packing, 2x resampling, loss reductions, activation
+// backward, column sums, fused AdamW.  All are grid-stride, vectorised where alignment allows, and sized as
+// multiples of the SM count (148 on B200).
+#include "common.cuh"
+#include <stdarg.h>
+#include <string.h>
+
+static thread_local char g_err[512] = "";
+void vqb_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+extern "C" const char* vqb_last_error(void) { return g_err; }
+extern "C" const char* vqb_version(void) { return "vqgan_b200 0.1 sm_100a"; }
+extern "C" int vqb_device_supports_tcgen05(void) {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+    return major == 10;
+}
+
+static const int kSMs = 148;
+static inline int grid_for(int64_t work_items, int threads, int max_waves = 16) {
+    int64_t b = ceil_div64(work_items, threads);
+    int64_t cap = (int64_t)kSMs * max_waves;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// NCHW <-> NHWC
+// ---------------------------------------------------------------------------------------------------
+template <typename TO>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, TO* __restrict__ y, int64_t N, int64_t C, int64_t HW,
+                                    int do_clamp, float lo, float hi, float shift, float scale) {
+    // one thread per (n, p): reads C strided planes (coalesced across p), writes C contiguous values
+    int64_t total = N * HW;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t n = i / HW, p = i - n * HW;
+        const float* src = x + n * C * HW + p;
+        TO* dst = y + i * C;
+        for (int64_t c = 0; c < C; ++c) {
+            float v = src[c * HW];
+            if (do_clamp) v = fminf(fmaxf(v, lo), hi);
+            st1(dst + c, (v - shift) * scale);
+        }
+    }
+}
+
+template <typename TI>
+__global__ void nhwc_to_nchw_kernel(const TI* __restrict__ x, float* __restrict__ y, int64_t N, int64_t C, int64_t HW,
+                                    float scale, float shift, int do_clamp, float lo, float hi) {
+    int64_t total = N * HW;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t n = i / HW, p = i - n * HW;
+        const TI* src = x + i * C;
+        float* dst = y + n * C * HW + p;
+        for (int64_t c = 0; c < C; ++c) {
+            float v = ld1(src + c) * scale + shift;
+            if (do_clamp) v = fminf(fmaxf(v, lo), hi);
+            dst[c * HW] = v;
+        }
+    }
+}
+
+// tiled transpose for wide channel counts: [N][C][HW] <-> [N][HW][C]
+template <typename TI, typename TO>
+__global__ void transpose_tiled_kernel(const TI* __restrict__ x, TO* __restrict__ y, int R, int Cc, float scale,
+                                       float shift) {
+    // x: [batch][R][Cc] -> y: [batch][Cc][R]
+    __shared__ float tile[32][33];
+    int b = blockIdx.z;
+    const TI* xb = x + (int64_t)b * R * Cc;
+    TO* yb = y + (int64_t)b * R * Cc;
+    int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        int r = r0 + j, c = c0 + threadIdx.x;
+        if (r < R && c < Cc) tile[j][threadIdx.x] = ld1(xb + (int64_t)r * Cc + c);
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        int c = c0 + j, r = r0 + threadIdx.x;
+        if (r < R && c < Cc) st1(yb + (int64_t)c * R + r, tile[threadIdx.x][j] * scale + shift);
+    }
+}
+
+extern "C" int vqb_nchw_to_nhwc(const float* x, void* y, int out_dtype, int64_t N, int64_t C, int64_t H, int64_t W,
+                                int do_clamp, float lo, float hi, float shift, float scale, void* stream) {
+    VQB_CHECK_ARG(x && y && N > 0 && C > 0 && H > 0 && W > 0, "nchw_to_nhwc: bad arguments");
+    int64_t HW = H * W;
+    if (C <= 8 || do_clamp) {
+        int g = grid_for(N * HW, 256);
+        VQB_DISPATCH_1(out_dtype, TO, (nchw_to_nhwc_kernel<TO><<<g, 256, 0, as_stream(stream)>>>(
+                                          x, (TO*)y, N, C, HW, do_clamp, lo, hi, shift, scale));)
+    } else {
+        dim3 grid((unsigned)ceil_div64(HW, 32), (unsigned)ceil_div64(C, 32), (unsigned)N), block(32, 8);
+        // (v - shift) * scale == v*scale + (-shift*scale)
+        VQB_DISPATCH_1(out_dtype, TO, (transpose_tiled_kernel<float, TO><<<grid, block, 0, as_stream(stream)>>>(
+                                          x, (TO*)y, (int)C, (int)HW, scale, -shift * scale));)
+    }
+    VQB_CHECK_LAUNCH("nchw_to_nhwc");
+    return VQB_OK;
+}
+
+extern "C" int vqb_nhwc_to_nchw(const void* x, int in_dtype, float* y, int64_t N, int64_t C, int64_t H, int64_t W,
+                                float scale, float shift, int do_clamp, float lo, float hi, void* stream) {
+    VQB_CHECK_ARG(x && y && N > 0 && C > 0 && H > 0 && W > 0, "nhwc_to_nchw: bad arguments");
+    int64_t HW = H * W;
+    if (C <= 8 || do_clamp) {
+        int g = grid_for(N * HW, 256);
+        VQB_DISPATCH_1(in_dtype, TI, (nhwc_to_nchw_kernel<TI><<<g, 256, 0, as_stream(stream)>>>(
+                                         (const TI*)x, y, N, C, HW, scale, shift, do_clamp, lo, hi));)
+    } else {
+        dim3 grid((unsigned)ceil_div64(C, 32), (unsigned)ceil_div64(HW, 32), (unsigned)N), block(32, 8);
+        VQB_DISPATCH_1(in_dtype, TI, (transpose_tiled_kernel<TI, float><<<grid, block, 0, as_stream(stream)>>>(
+                                         (const TI*)x, y, (int)HW, (int)C, scale, shift));)
+    }
+    VQB_CHECK_LAUNCH("nhwc_to_nchw");
+    return VQB_OK;
+}
+
+template <typename TI, typename TO>
+__global__ void convert_kernel(const TI* __restrict__ x, TO* __restrict__ y, int64_t n) {
+    int64_t n4 = n >> 2;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x)
+        st4(y + i * 4, ld4(x + i * 4));
+    for (int64_t i = (n4 << 2) + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        st1(y + i, ld1(x + i));
+}
+
+extern "C" int vqb_convert(const void* x, int in_dtype, void* y, int out_dtype, int64_t n, void* stream) {
+    VQB_CHECK_ARG(x && y && n >= 0, "convert: bad arguments");
+    if (n == 0) return VQB_OK;
+    int g = grid_for(n / 4 + 1, 256);
+    VQB_DISPATCH_1(in_dtype, TI, VQB_DISPATCH_1(out_dtype, TO, (convert_kernel<TI, TO><<<g, 256, 0, as_stream(stream)>>>(
+                                                                   (const TI*)x, (TO*)y, n));))
+    VQB_CHECK_LAUNCH("convert");
+    return VQB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// weight packing
+// ---------------------------------------------------------------------------------------------------
+template <typename TO>
+__global__ void pack_weight_kernel(const float* __restrict__ w, TO* __restrict__ wp, int mode, int Co, int Ci, int KH,
+                                   int KW, float scale) {
+    int64_t total = (int64_t)Co * Ci * KH * KW;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        // i enumerates the OUTPUT layout so that writes are coalesced
+        int co, ci, kh, kw;
+        if (mode == 0) {  // [(kh,kw,ci)][co]
+            co = (int)(i % Co); int64_t r = i / Co; ci = (int)(r % Ci); r /= Ci; kw = (int)(r % KW); kh = (int)(r / KW);
+        } else if (mode == 1) {  // [(kh',kw',co)][ci], kh' = KH-1-kh
+            ci = (int)(i % Ci); int64_t r = i / Ci; co = (int)(r % Co); r /= Co; kw = KW - 1 - (int)(r % KW); kh = KH - 1 - (int)(r / KW);
+        } else if (mode == 2) {  // [co][(kh,kw,ci)]
+            ci = (int)(i % Ci); int64_t r = i / Ci; kw = (int)(r % KW); r /= KW; kh = (int)(r % KH); co = (int)(r / KH);
+        } else {  // mode 3: [ci][(kh',kw',co)]
+            co = (int)(i % Co); int64_t r = i / Co; kw = KW - 1 - (int)(r % KW); r /= KW; kh = KH - 1 - (int)(r % KH); ci = (int)(r / KH);
+        }
+        float v = w[(((int64_t)co * Ci + ci) * KH + kh) * KW + kw] * scale;
+        st1(wp + i, v);
+    }
+}
+
+extern "C" int vqb_pack_conv_weight(const float* w, void* wp, int out_dtype, int mode, int Co, int Ci, int KH, int KW,
+                                    float scale, void* stream) {
+    VQB_CHECK_ARG(w && wp && mode >= 0 && mode <= 3 && Co > 0 && Ci > 0 && KH > 0 && KW > 0, "pack_conv_weight: bad arguments");
+    int64_t total = (int64_t)Co * Ci * KH * KW;
+    int g = grid_for(total, 256);
+    VQB_DISPATCH_1(out_dtype, TO, (pack_weight_kernel<TO><<<g, 256, 0, as_stream(stream)>>>(w, (TO*)wp, mode, Co, Ci, KH, KW, scale));)
+    VQB_CHECK_LAUNCH("pack_conv_weight");
+    return VQB_OK;
+}
+
+__global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int Co, int Ci, int KH, int KW,
+                                    float scale) {
+    // tile-transpose between [(tap,ci)][co] and [co][ci][tap]: handle per tap a [Ci][Co] -> [Co][Ci] transpose
+    __shared__ float tile[32][33];
+    int tap = blockIdx.z;
+    int T = KH * KW;
+    int ci0 = blockIdx.y * 32, co0 = blockIdx.x * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        int ci = ci0 + j, co = co0 + threadIdx.x;
+        if (ci < Ci && co < Co) tile[j][threadIdx.x] = dwp[((int64_t)tap * Ci + ci) * Co + co];
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        int co = co0 + j, ci = ci0 + threadIdx.x;
+        if (ci < Ci && co < Co) dw[((int64_t)co * Ci + ci) * T + tap] = tile[threadIdx.x][j] * scale;
+    }
+}
+
+extern "C" int vqb_unpack_conv_wgrad(const float* dwp, float* dw, int Co, int Ci, int KH, int KW, float scale, void* stream) {
+    VQB_CHECK_ARG(dwp && dw && Co > 0 && Ci > 0 && KH > 0 && KW > 0, "unpack_conv_wgrad: bad arguments");
+    dim3 grid((Co + 31) / 32, (Ci + 31) / 32, KH * KW), block(32, 8);
+    unpack_wgrad_kernel<<<grid, block, 0, as_stream(stream)>>>(dwp, dw, Co, Ci, KH, KW, scale);
+    VQB_CHECK_LAUNCH("unpack_conv_wgrad");
+    return VQB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// 2x resampling
+// ---------------------------------------------------------------------------------------------------
+template <typename T, int VEC>
+__global__ void down2_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, float scale) {
+    // y [N,H,W,C], x [N,2H,2W,C]
+    int Cv = C / VEC;
+    int64_t total = (int64_t)N * H * W * Cv;
+    int64_t rowx = (int64_t)2 * W * C;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int cv = (int)(i % Cv); int64_t r = i / Cv; int w = (int)(r % W); r /= W; int h = (int)(r % H); int n = (int)(r / H);
+        const T* p = x + (((int64_t)n * 2 * H + 2 * h) * 2 * W + 2 * w) * C + cv * VEC;
+        if (VEC == 4) {
+            float4 a = ld4(p), b = ld4(p + C), c = ld4(p + rowx), d = ld4(p + rowx + C);
+            float4 o = make_float4((a.x + b.x + c.x + d.x) * scale, (a.y + b.y + c.y + d.y) * scale,
+                                   (a.z + b.z + c.z + d.z) * scale, (a.w + b.w + c.w + d.w) * scale);
+            st4(y + i * 4, o);
+        } else {
+            st1(y + i, (ld1(p) + ld1(p + C) + ld1(p + rowx) + ld1(p + rowx + C)) * scale);
+        }
+    }
+}
+
+template <typename T, int VEC>
+__global__ void up2_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, float scale) {
+    // x [N,H,W,C], y [N,2H,2W,C]; iterate over output
+    int Cv = C / VEC;
+    int H2 = 2 * H, W2 = 2 * W;
+    int64_t total = (int64_t)N * H2 * W2 * Cv;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int cv = (int)(i % Cv); int64_t r = i / Cv; int w = (int)(r % W2); r /= W2; int h = (int)(r % H2); int n = (int)(r / H2);
+        const T* p = x + (((int64_t)n * H + (h >> 1)) * W + (w >> 1)) * C + cv * VEC;
+        if (VEC == 4) {
+            float4 a = ld4(p);
+            st4(y + i * 4, make_float4(a.x * scale, a.y * scale, a.z * scale, a.w * scale));
+        } else {
+            st1(y + i, ld1(p) * scale);
+        }
+    }
+}
+
+extern "C" int vqb_down2(const void* x, void* y, int dtype, int N, int H, int W, int C, float scale, void* stream) {
+    VQB_CHECK_ARG(x && y && N > 0 && H > 0 && W > 0 && C > 0, "down2: bad arguments");
+    int64_t total = (int64_t)N * H * W * C;
+    if (C % 4 == 0) {
+        int g = grid_for(total / 4, 256);
+        VQB_DISPATCH_1(dtype, T, (down2_kernel<T, 4><<<g, 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, N, H, W, C, scale));)
+    } else {
+        int g = grid_for(total, 256);
+        VQB_DISPATCH_1(dtype, T, (down2_kernel<T, 1><<<g, 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, N, H, W, C, scale));)
+    }
+    VQB_CHECK_LAUNCH("down2");
+    return VQB_OK;
+}
+
+extern "C" int vqb_up2(const void* x, void* y, int dtype, int N, int H, int W, int C, float scale, void* stream) {
+    VQB_CHECK_ARG(x && y && N > 0 && H > 0 && W > 0 && C > 0, "up2: bad arguments");
+    int64_t total = (int64_t)N * 4 * H * W * C;
+    if (C % 4 == 0) {
+        int g = grid_for(total / 4, 256);
+        VQB_DISPATCH_1(dtype, T, (up2_kernel<T, 4><<<g, 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, N, H, W, C, scale));)
+    } else {
+        int g = grid_for(total, 256);
+        VQB_DISPATCH_1(dtype, T, (up2_kernel<T, 1><<<g, 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, N, H, W, C, scale));)
+    }
+    VQB_CHECK_LAUNCH("up2");
+    return VQB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// loss reductions and their gradients
+// ---------------------------------------------------------------------------------------------------
+template <typename TA, typename TB>
+__global__ void diff_sums_kernel(const TA* __restrict__ a, const TB* __restrict__ b, double* __restrict__ out, int64_t n) {
+    float s2 = 0.f, s1 = 0.f;
+    double d2 = 0.0, d1 = 0.0;
+    int cnt = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float d = ld1(a + i) - ld1(b + i);
+        s2 += d * d;
+        s1 += fabsf(d);
+        if (++cnt == 64) { d2 += s2; d1 += s1; s2 = s1 = 0.f; cnt = 0; }
+    }
+    d2 += s2; d1 += s1;
+    d2 = warp_sum(d2); d1 = warp_sum(d1);
+    __shared__ double sh[2][8];
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) { sh[0][wid] = d2; sh[1][wid] = d1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t2 = 0, t1 = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { t2 += sh[0][i]; t1 += sh[1][i]; }
+        atomicAdd(out, t2);
+        atomicAdd(out + 1, t1);
+    }
+}
+
+extern "C" int vqb_diff_sums(const void* a, int a_dtype, const void* b, int b_dtype, double* out, int64_t n, void* stream) {
+    VQB_CHECK_ARG(a && b && out && n > 0, "diff_sums: bad arguments");
+    int g = grid_for(n, 256, 4);
+    VQB_DISPATCH_1(a_dtype, TA, VQB_DISPATCH_1(b_dtype, TB, (diff_sums_kernel<TA, TB><<<g, 256, 0, as_stream(stream)>>>(
+                                                                (const TA*)a, (const TB*)b, out, n));))
+    VQB_CHECK_LAUNCH("diff_sums");
+    return VQB_OK;
+}
+
+template <typename TA, typename TB, typename TD>
+__global__ void diff_grad_kernel(const TA* __restrict__ a, const TB* __restrict__ b, TD* __restrict__ da, float c1, float c2,
+                                 const float* __restrict__ upstream, int y_tanh, int64_t n) {
+    const float up2 = upstream ? upstream[0] : 1.0f, up1 = upstream ? upstream[1] : 1.0f;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float av = ld1(a + i);
+        float d = av - ld1(b + i);
+        float sg = (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f);
+        float g = c2 * 2.0f * d * up2 + c1 * sg * up1;
+        if (y_tanh) g *= (1.0f - av * av);
+        st1(da + i, g);
+    }
+}
+
+extern "C" int vqb_diff_grad(const void* a, int a_dtype, const void* b, int b_dtype, void* da, int da_dtype, float c1,
+                             float c2, const float* upstream, int y_tanh, int64_t n, void* stream) {
+    VQB_CHECK_ARG(a && b && da && n > 0, "diff_grad: bad arguments");
+    int g = grid_for(n, 256);
+    VQB_DISPATCH_1(a_dtype, TA, VQB_DISPATCH_1(b_dtype, TB, VQB_DISPATCH_1(da_dtype, TD,
+        (diff_grad_kernel<TA, TB, TD><<<g, 256, 0, as_stream(stream)>>>((const TA*)a, (const TB*)b, (TD*)da, c1, c2, upstream, y_tanh, n));)))
+    VQB_CHECK_LAUNCH("diff_grad");
+    return VQB_OK;
+}
+
+template <typename TY, typename TG, typename TD>
+__global__ void act_bwd_out_kernel(const TY* __restrict__ y, const TG* __restrict__ dy, TD* __restrict__ dx, int act,
+                                   float alpha, float gain, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float yv = ld1(y + i), g = ld1(dy + i);
+        float d;
+        if (act == VQB_ACT_TANH) { float t = yv / gain; d = gain * (1.0f - t * t); }
+        else if (act == VQB_ACT_LRELU) d = (yv > 0.f) ? gain : gain * alpha;     // sign(y) == sign(pre-activation)
+        else if (act == VQB_ACT_RELU) d = (yv > 0.f) ? gain : 0.f;
+        else d = gain;
+        st1(dx + i, g * d);
+    }
+}
+
+extern "C" int vqb_act_bwd_from_output(const void* y, int y_dtype, const void* dy, int dy_dtype, void* dx, int dx_dtype,
+                                       int act, float alpha, float gain, int64_t n, void* stream) {
+    VQB_CHECK_ARG(y && dy && dx && n > 0, "act_bwd_from_output: bad arguments");
+    VQB_CHECK_ARG(act != VQB_ACT_SILU, "act_bwd_from_output: SiLU is not invertible from its output");
+    int g = grid_for(n, 256);
+    VQB_DISPATCH_1(y_dtype, TY, VQB_DISPATCH_1(dy_dtype, TG, VQB_DISPATCH_1(dx_dtype, TD,
+        (act_bwd_out_kernel<TY, TG, TD><<<g, 256, 0, as_stream(stream)>>>((const TY*)y, (const TG*)dy, (TD*)dx, act, alpha, gain, n));)))
+    VQB_CHECK_LAUNCH("act_bwd_from_output");
+    return VQB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// column sums (bias gradients): out[c] += sum_p a[p][c]
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ a, float* __restrict__ out, int64_t P, int C, int rows_per_block) {
+    // blockDim.x threads cover channels (strided), blockIdx.x covers a row chunk
+    int64_t p0 = (int64_t)blockIdx.x * rows_per_block;
+    int64_t p1 = p0 + rows_per_block; if (p1 > P) p1 = P;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = 0.f;
+        for (int64_t p = p0 + threadIdx.y; p < p1; p += blockDim.y) s += ld1(a + p * C + c);
+        atomicAdd(out + c, s);
+    }
+}
+
+extern "C" int vqb_colsum(const void* a, int a_dtype, float* out, int64_t P, int C, void* stream) {
+    VQB_CHECK_ARG(a && out && P > 0 && C > 0, "colsum: bad arguments");
+    int tx = C >= 128 ? 128 : (C >= 32 ? 32 : (C >= 8 ? 8 : 4));
+    int ty = 256 / tx;
+    int64_t want_blocks = (int64_t)kSMs * 8;
+    int rows = (int)ceil_div64(P, want_blocks);
+    if (rows < ty * 4) rows = ty * 4;
+    int g = (int)ceil_div64(P, rows);
+    dim3 block(tx, ty);
+    VQB_DISPATCH_1(a_dtype, T, (colsum_kernel<T><<<g, block, 0, as_stream(stream)>>>((const T*)a, out, P, C, rows));)
+    VQB_CHECK_LAUNCH("colsum");
+    return VQB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// fused AdamW over a flat range (torch.optim.AdamW semantics)
+// ---------------------------------------------------------------------------------------------------
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                             float* __restrict__ v, int64_t n, float lr, float beta1, float beta2, float eps,
+                             float wd, float bc1, float bc2_sqrt, float grad_scale) {
+    const float step_size = lr / bc1;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float gi = g[i] * grad_scale;
+        float pi = p[i] * (1.0f - lr * wd);
+        float mi = m[i] * beta1 + (1.0f - beta1) * gi;
+        float vi = v[i] * beta2 + (1.0f - beta2) * gi * gi;
+        float denom = sqrtf(vi) / bc2_sqrt + eps;
+        p[i] = pi - step_size * (mi / denom);
+        m[i] = mi;
+        v[i] = vi;
+    }
+}
+
+extern "C" int vqb_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                         float eps, float weight_decay, int step, float grad_scale, void* stream) {
+    VQB_CHECK_ARG(p && g && m && v && n >= 0 && step >= 1, "adamw: bad arguments");
+    if (n == 0) return VQB_OK;
+    double bc1 = 1.0 - pow((double)beta1, (double)step);
+    double bc2 = 1.0 - pow((double)beta2, (double)step);
+    int gsz = grid_for(n, 256);
+    adamw_kernel<<<gsz, 256, 0, as_stream(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, (float)bc1,
+                                                      (float)sqrt(bc2), grad_scale);
+    VQB_CHECK_LAUNCH("adamw");
+    return VQB_OK;
+}

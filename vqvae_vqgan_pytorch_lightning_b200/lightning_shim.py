@@ -1,0 +1,137 @@
+"""Minimal stand-in for the part of pytorch_lightning that the reference's VQVAE module touches
+(vqvae/model.py: self.log, self.optimizers(), self.manual_backward, self.trainer.{num_training_batches,optimizers},
+self.current_epoch, automatic_optimization and the fit-loop hooks), plus a one-process-per-GPU data-parallel
+Trainer.  pytorch_lightning is not installable in the build image; when it is importable the real
+`pl.LightningModule` is used as the base class instead and this Trainer remains available as the B200 fit loop.
+
+Data parallelism (reference: Lightning DDPStrategy, vqvae/train.py:128-131): the global batch is sharded across
+ranks; after backward the flat gradient buffer of each FusedAdamW is SUM-all-reduced with NCCL over NVLink in one
+call and scaled by 1/world inside the AdamW kernel; EMA cluster statistics are all-reduced by the quantizer.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, Iterable, List, Optional
+
+import torch
+import torch.distributed as dist
+from torch import nn
+
+try:                                    # pragma: no cover - not installed in the build image
+    import pytorch_lightning as _pl
+    _Base = _pl.LightningModule
+    HAVE_LIGHTNING = True
+except Exception:
+    _Base = nn.Module
+    HAVE_LIGHTNING = False
+
+
+class LightningModule(_Base):
+    """The subset of pl.LightningModule used by vqvae/model.py."""
+
+    if not HAVE_LIGHTNING:
+        def __init__(self):
+            super().__init__()
+            self.trainer: Optional['Trainer'] = None
+            self.current_epoch = 0
+            self.automatic_optimization = True
+            self.logged: Dict[str, Any] = {}
+
+        def log(self, name: str, value, **kwargs) -> None:
+            # values may be device tensors; nothing is synchronised here (the reference does 7 .item() syncs per step)
+            self.logged[name] = value
+
+        def optimizers(self):
+            opts = self.trainer.optimizers
+            return opts if len(opts) > 1 else opts[0]
+
+        def manual_backward(self, loss: torch.Tensor) -> None:
+            loss.backward()
+            if self.trainer is not None:
+                self.trainer.sync_gradients()
+
+        # hooks (overridden by the model)
+        def on_train_start(self): ...
+        def on_train_batch_start(self, batch, batch_index): ...
+        def on_train_epoch_end(self): ...
+        def on_train_end(self): ...
+
+
+class Trainer:
+    """One-process-per-GPU fit loop (rank / world from torch.distributed when initialised)."""
+
+    def __init__(self, max_epochs: int = 1, num_training_batches: Optional[int] = None):
+        self.max_epochs = max_epochs
+        self.num_training_batches = num_training_batches or 0
+        self.optimizers: List[torch.optim.Optimizer] = []
+        self.world_size = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank() if self.world_size > 1 else 0
+        self.model: Optional[LightningModule] = None
+
+    # ---- data parallel plumbing ---------------------------------------------------------------------
+    def attach(self, model: LightningModule) -> None:
+        self.model = model
+        model.trainer = self
+        opt = model.configure_optimizers()
+        if isinstance(opt, tuple):
+            opt = opt[0]
+        self.optimizers = list(opt) if isinstance(opt, (list, tuple)) else [opt]
+        for o in self.optimizers:
+            if hasattr(o, 'grad_scale'):
+                o.grad_scale = 1.0 / self.world_size
+        q = getattr(model, 'quantizer', None)
+        if q is not None and self.world_size > 1:
+            q.world_size = self.world_size
+            q.stats_allreduce = self._allreduce_stats
+
+    def _allreduce_stats(self, *tensors: torch.Tensor) -> None:
+        for t in tensors:
+            if t is not None:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+
+    def sync_gradients(self) -> None:
+        if self.world_size <= 1:
+            return
+        for o in self.optimizers:
+            flat = getattr(o, 'flat_grad', None)
+            if flat is not None:
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM)       # one NCCL call per optimizer; averaged in vqb_adamw
+            else:
+                for g in o.param_groups:
+                    for p in g['params']:
+                        if p.grad is not None:
+                            dist.all_reduce(p.grad, op=dist.ReduceOp.SUM)
+                            p.grad.div_(self.world_size)
+
+    # ---- one optimisation step (what Lightning's fit loop does around training_step) -------------------
+    def run_step(self, batch, batch_index: int):
+        m = self.model
+        m.on_train_batch_start(batch, batch_index)
+        if m.automatic_optimization:
+            opt = self.optimizers[0]
+            opt.zero_grad()
+            loss = m.training_step(batch, batch_index)
+            loss.backward()
+            self.sync_gradients()
+            opt.step()
+        else:
+            loss = m.training_step(batch, batch_index)
+        return loss
+
+    def fit(self, model: LightningModule, batches: Iterable, steps_per_epoch: Optional[int] = None):
+        if self.model is not model:
+            self.attach(model)
+        if steps_per_epoch is None:
+            steps_per_epoch = len(batches)
+        self.num_training_batches = steps_per_epoch
+        model.train()
+        model.on_train_start()
+        loss = None
+        for epoch in range(self.max_epochs):
+            model.current_epoch = epoch
+            for i, batch in enumerate(batches):
+                if i >= steps_per_epoch:
+                    break
+                loss = self.run_step(batch, i)
+            model.on_train_epoch_end()
+        model.on_train_end()
+        return loss

@@ -1,0 +1,243 @@
+"""VQVAE LightningModule surface (reference: vqvae/model.py) on top of the libvqgan_b200 kernels.
+
+Same constructor (`VQVAE(image_size, ae_conf, q_conf, l_conf, t_conf, init_cb, load_loss)`, model.py:25-26), same
+sub-module / parameter / buffer names, same construction order (quantizer -> encoder -> decoder -> criterion ->
+init_codebook, so seeded initialisation matches the reference), same YAML-derived dict schema, same hooks and
+inference API.  Reference defects are handled as stated in each method's docstring.
+"""
+from __future__ import annotations
+
+from typing import Any, Optional
+
+import torch
+from torch import nn
+
+from . import ops
+from .lightning_shim import LightningModule
+from .modules.abstract_modules.base_autoencoder import BaseVQVAE
+from .modules.autoencoder import Conv2d, Decoder, Encoder, GroupNorm
+from .modules.vector_quantizers import EMAVectorQuantizer, VectorQuantizer
+from .optim import FusedAdamW
+from .schedulers import CosineScheduler, LinearCosineScheduler, LinearScheduler
+
+try:
+    from .modules.vector_quantizers import EntropyVectorQuantizer, GumbelVectorQuantizer
+except ImportError:          # pragma: no cover
+    EntropyVectorQuantizer = GumbelVectorQuantizer = None
+
+
+class MSELoss(nn.Module):
+    """torch.nn.MSELoss() replacement used when l_conf is None (model.py:136-137): mean((a-b)^2) by vqb_diff_sums."""
+
+    def forward(self, recon: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        return ops.mse_l1(recon, target)[0]
+
+
+class VQVAE(BaseVQVAE, LightningModule):
+
+    def __init__(self, image_size: int, ae_conf: dict, q_conf: dict, l_conf: Optional[dict], t_conf: Optional[dict],
+                 init_cb: bool = True, load_loss: bool = True, fix_param_groups: bool = False):
+        """Arguments as in the reference (model.py:25-78).  `fix_param_groups=True` repairs defect B2 (53 encoder
+        tensors never reach the optimizer because of relative-name collisions); the default replicates it."""
+        LightningModule.__init__(self)
+        BaseVQVAE.__init__(self, image_size=image_size)
+        self.t_conf = t_conf
+        self.fix_param_groups = fix_param_groups
+
+        self.cb_size = q_conf['num_embeddings']
+        self.latent_dim = q_conf['embedding_dim']
+        self.reinit_every_n_epochs = q_conf.get('reinit_every_n_epochs')
+        qtype, qp = q_conf['type'], q_conf.get('params') or {}
+        self.kl_warmup_epochs = self.temp_decay_epochs = self.temp_final = None
+        if qtype == 'standard':
+            self.quantizer = VectorQuantizer(self.cb_size, self.latent_dim, float(qp['commitment_cost']))
+        elif qtype == 'ema':
+            self.quantizer = EMAVectorQuantizer(self.cb_size, self.latent_dim, float(qp['commitment_cost']),
+                                                float(qp['decay']), float(qp['epsilon']))
+        elif qtype == 'gumbel':
+            if GumbelVectorQuantizer is None:
+                raise NotImplementedError('gumbel quantizer kernels are not built yet')
+            self.quantizer = GumbelVectorQuantizer(self.cb_size, self.latent_dim, bool(qp['straight_through']),
+                                                   float(qp['temp']), float(qp['kl_cost']))
+            self.kl_warmup_epochs = qp.get('kl_warmup_epochs')
+            self.temp_decay_epochs = qp.get('temp_decay_epochs')
+            self.temp_final = qp.get('temp_final')
+        elif qtype == 'entropy':
+            if EntropyVectorQuantizer is None:
+                raise NotImplementedError('entropy quantizer kernels are not built yet')
+            self.quantizer = EntropyVectorQuantizer(self.cb_size, self.latent_dim, float(qp['ent_loss_ratio']),
+                                                    float(qp['ent_temperature']), str(qp['ent_loss_type']),
+                                                    float(qp['commitment_cost']))
+        else:
+            raise ValueError(f'unrecognized quantizer: {q_conf["type"]}')
+
+        channels = ae_conf['channels']
+        num_res_blocks = ae_conf['num_res_blocks']
+        channel_multipliers = tuple(ae_conf['channel_multipliers'])
+        final_conv_channels = self.cb_size if qtype == 'gumbel' else self.latent_dim
+        self.encoder = Encoder(channels, num_res_blocks, channel_multipliers, final_conv_channels)
+        self.decoder = Decoder(channels, num_res_blocks, channel_multipliers, self.latent_dim)
+
+        if load_loss:
+            if l_conf is None:
+                self.criterion = MSELoss()
+            else:
+                raise NotImplementedError('LPIPS / StyleGAN2-discriminator loss heads (loss/loss.py) are the next '
+                                          'rows of the hot-path table; only the MSE branch is built')
+        else:
+            self.criterion = None
+
+        if init_cb:
+            self.quantizer.init_codebook()
+
+    # ---------------------------------------------------------------------------------------------------
+    def forward(self, x: torch.Tensor):
+        """x [B,3,H,W] in [-1,1] -> (reconstructions [B,3,H,W], quantizer loss, used indices [B,S])  (model.py:151-161)"""
+        z = self.encoder(x)
+        quantized, used_indices, e_loss = self.quantizer(z)
+        x_recon = self.decoder(quantized)
+        return x_recon, e_loss, used_indices
+
+    # ---- schedules (model.py:163-230) --------------------------------------------------------------------
+    def on_train_start(self):
+        lr = float(self.t_conf['lr'])
+        nb = self.trainer.num_training_batches
+        wu, dc = self.t_conf.get('warmup_epochs'), self.t_conf.get('decay_epochs')
+        if wu is not None and dc is not None:
+            self.scheduler = LinearCosineScheduler(0, dc * nb, lr, lr / 2., wu * nb)
+        elif wu is not None:
+            self.scheduler = LinearScheduler(0, wu * nb, 1e-20, lr)
+        elif dc is not None:
+            self.scheduler = CosineScheduler(0, dc * nb, lr, lr / 2.)
+        if GumbelVectorQuantizer is not None and isinstance(self.quantizer, GumbelVectorQuantizer):
+            temp, kl = self.quantizer.get_consts()
+            if self.kl_warmup_epochs is not None:
+                self.quantizer.kl_warmup = CosineScheduler(0, int(self.kl_warmup_epochs * nb), 0.0, kl)
+            if self.temp_decay_epochs is not None and self.temp_final is not None:
+                self.quantizer.temp_decay = CosineScheduler(0, int(self.temp_decay_epochs * nb), temp, self.temp_final)
+
+    def on_train_batch_start(self, _: Any, batch_index: int):
+        current_step = (self.current_epoch * self.trainer.num_training_batches) + batch_index
+        step_lr = self.scheduler.step(current_step) if self.scheduler is not None else float(self.t_conf['lr'])
+        for optimizer in self.trainer.optimizers:
+            for g in optimizer.param_groups:
+                g['lr'] = step_lr
+        if GumbelVectorQuantizer is not None and isinstance(self.quantizer, GumbelVectorQuantizer):
+            this_temp, this_kl = self.quantizer.get_consts()
+            if self.quantizer.kl_warmup is not None:
+                this_kl = self.quantizer.kl_warmup.step(current_step)
+            if self.quantizer.temp_decay is not None:
+                this_temp = self.quantizer.temp_decay.step(current_step)
+            self.quantizer.set_consts(this_temp, this_kl)
+        else:
+            this_temp, this_kl = 0.0, 0.0
+        self.log('gumbel_quantizer/temperature', this_temp, sync_dist=True)
+        self.log('gumbel_quantizer/kl_constant', this_kl, sync_dist=True)
+
+    # ---- the hot loop body (model.py:232-295) ---------------------------------------------------------
+    def training_step(self, batch: Any, batch_index: int):
+        """Branch C (plain VQ-VAE, MSE).  Defect B1 (the reference returns an unbound `loss` here) is fixed by
+        returning ae_loss; logged scalars stay on the device (no per-step host syncs)."""
+        images = self.preprocess_batch(batch[0] if isinstance(batch, tuple) else batch, training=True)
+        x_recon, q_loss, used_indices = self.forward(images)
+        l2_loss = self.criterion(x_recon, images)
+        ae_loss = q_loss + l2_loss
+        self.log('train/loss', ae_loss.detach())
+        self.log('train/l2_loss', l2_loss.detach())
+        self.log('train/quant_loss', q_loss.detach())
+        # per-batch code usage (model.py:289-293; defect B3 -- only the last batch is kept -- replicated)
+        self.train_epoch_usage_count = torch.bincount(used_indices.view(-1), minlength=self.cb_size)
+        return ae_loss
+
+    def on_train_epoch_end(self):
+        if (self.reinit_every_n_epochs is not None and self.current_epoch % self.reinit_every_n_epochs == 0
+                and self.current_epoch > 0):
+            self.quantizer.reinit_unused_codes(self.quantizer.get_codebook_usage(self.train_epoch_usage_count.float())[0])
+        self.train_epoch_usage_count = None
+
+    def on_train_end(self):
+        if self.scheduler is not None:          # defect B10 guarded
+            self.scheduler.destroy()
+
+    @torch.no_grad()
+    def validation_step(self, batch: Any, batch_index: int):
+        """model.py:309-356 (MSE branch): returns the validation loss; usage counts kept for on_validation_epoch_end."""
+        images = self.preprocess_batch(batch[0] if isinstance(batch, tuple) else batch)
+        x_recon, q_loss, used_indices = self.forward(images)
+        l2_loss = self.criterion(x_recon, images)
+        loss = q_loss + l2_loss
+        self.log('validation/loss', loss)
+        self.log('validation/l2_loss', l2_loss)
+        self.log('validation/quant_loss', q_loss)
+        self.val_epoch_usage_count = torch.bincount(used_indices.view(-1), minlength=self.cb_size)
+        return loss
+
+    def on_validation_epoch_end(self):
+        if self.val_epoch_usage_count is not None:
+            _, perplexity, cb_usage = self.quantizer.get_codebook_usage(self.val_epoch_usage_count.float())
+            self.log('val_metrics/used_codebook', cb_usage)
+            self.log('val_metrics/perplexity', perplexity)
+        self.val_epoch_usage_count = None
+
+    # ---- optimizer (model.py:372-440) -----------------------------------------------------------------
+    def configure_optimizers(self):
+        """AdamW with two groups (Conv2d weights decay; biases, Embedding and GroupNorm weights do not), fused over flat
+        buffers.  Defect B2: the reference keys its parameter dict by names RELATIVE to encoder / decoder / quantizer, so
+        a decoder tensor silently replaces the encoder tensor of the same relative name; replicated unless
+        fix_param_groups=True."""
+        lr = float(self.t_conf['lr'])
+        betas = [float(b) for b in self.t_conf['betas']]
+        eps = float(self.t_conf['eps'])
+        weight_decay = float(self.t_conf['weight_decay'])
+
+        decay, no_decay, param_dict = set(), set(), {}
+        for prefix, sub in (('encoder', self.encoder), ('decoder', self.decoder), ('quantizer', self.quantizer)):
+            rename = (lambda n: f'{prefix}.{n}') if self.fix_param_groups else (lambda n: n)
+            for mn, m in sub.named_modules():
+                for pn, _ in m.named_parameters():
+                    fpn = rename('%s.%s' % (mn, pn) if mn else pn)
+                    if pn.endswith('bias'):
+                        no_decay.add(fpn)
+                    elif pn.endswith('weight') and isinstance(m, nn.Conv2d):
+                        decay.add(fpn)
+                    elif pn.endswith('weight') and isinstance(m, (nn.Embedding, GroupNorm)):
+                        no_decay.add(fpn)
+            for pn, p in sub.named_parameters():
+                param_dict[rename(pn)] = p          # later sub-modules overwrite equal relative names (B2)
+        assert len(decay & no_decay) == 0
+        assert len(param_dict.keys() - (decay | no_decay)) == 0
+        groups = [
+            {'params': [param_dict[pn] for pn in sorted(decay)], 'weight_decay': weight_decay},
+            {'params': [param_dict[pn] for pn in sorted(no_decay)], 'weight_decay': 0.0},
+        ]
+        return FusedAdamW(groups, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+
+    # ---- two-stage-model API (model.py:458-489) -------------------------------------------------------------
+    @torch.no_grad()
+    def get_tokens(self, images: torch.Tensor) -> torch.Tensor:
+        """images [B,3,H,W] in [0,1] -> codebook indices [B,S]"""
+        return self.quantizer.vec_to_codes(self.encoder(self.preprocess_batch(images)))
+
+    @torch.no_grad()
+    def quantize(self, images: torch.Tensor) -> torch.Tensor:
+        """images [B,3,H,W] in [0,1] -> quantized latents [B,S,D]"""
+        q = self.quantizer(self.encoder(self.preprocess_batch(images)))[0]          # [B,D,h,w], physically NHWC
+        b, d, h, w = q.shape
+        return q.permute(0, 2, 3, 1).reshape(b, h * w, d)
+
+    @torch.no_grad()
+    def reconstruct(self, images: torch.Tensor) -> torch.Tensor:
+        """images [B,3,H,W] in [0,1] -> reconstructions [B,3,H,W] in [0,1]"""
+        return self.preprocess_visualization(self(self.preprocess_batch(images))[0])
+
+    @torch.no_grad()
+    def reconstruct_from_tokens(self, tokens: torch.Tensor) -> torch.Tensor:
+        """tokens [B,S] -> images [B,3,H,W] in [0,1].  Defect B4 (the reference feeds [B,S,D] to a Conv2d decoder)
+        is fixed: S must be a square h*w and the vectors are laid out as a [B,D,h,w] latent."""
+        b, s = tokens.shape
+        h = int(round(s ** 0.5))
+        if h * h != s:
+            raise ValueError('token sequence length must be a perfect square')
+        vec = self.quantizer.codes_to_vec(tokens)                                     # [B,S,D]
+        latent = vec.reshape(b, h, h, self.latent_dim).permute(0, 3, 1, 2)          # logical NCHW, physical NHWC
+        return self.preprocess_visualization(self.decoder(latent))

@@ -1,0 +1,431 @@
+"""torch.autograd bindings of the libvqgan_b200 kernels.
+
+PyTorch is used here for device memory, streams and the autograd tape only; every arithmetic operation on the
+hot path is a call through the C ABI (lib.call).  Activations are channels-last tensors (logical [N,C,H,W],
+physical NHWC) so the module surface keeps the reference's shapes while the kernels see NHWC.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+
+from . import lib
+from .lib import ACT_NONE, ACT_SILU, ACT_TANH, BF16, F32, call, dt, ptr, stream
+
+CL = torch.channels_last
+
+
+@dataclass
+class Precision:
+    """Numeric mode of the convolution stacks.
+
+    strict: fp32 storage + fp32 SIMT implicit GEMM -- the parity path (<= 1e-4 rel. vs the fp32 oracle).
+    fast  : bf16 storage, tcgen05 bf16 x bf16 -> fp32 implicit GEMM wherever Ci and Co are multiples of 64
+            (the reference itself trains with precision='16-mixed', vqvae/train.py:129); fp32 master weights,
+            fp32 GroupNorm statistics, fp32 VQ, fp32 weight gradients.
+    """
+    name: str = 'strict'
+
+    @property
+    def act_dtype(self) -> torch.dtype:
+        return torch.float32 if self.name == 'strict' else torch.bfloat16
+
+    def conv_impl(self, ci: int, co: int, stride: int = 1) -> int:
+        if self.name == 'fast' and ci % 64 == 0 and co % 64 == 0 and stride == 1:
+            return 1
+        return 0
+
+
+_precision = Precision('strict')
+_weights_epoch = 0          # bumped whenever a kernel updates parameters behind autograd's back (optimizer step)
+
+
+def set_precision(name: str) -> None:
+    if name not in ('strict', 'fast'):
+        raise ValueError(f'unknown precision mode {name!r}')
+    _precision.name = name
+
+
+def get_precision() -> Precision:
+    return _precision
+
+
+def bump_weights_epoch() -> None:
+    global _weights_epoch
+    _weights_epoch += 1
+
+
+def empty_nhwc(n: int, c: int, h: int, w: int, dtype: torch.dtype, device) -> torch.Tensor:
+    return torch.empty((n, c, h, w), dtype=dtype, device=device, memory_format=CL)
+
+
+def as_nhwc(t: torch.Tensor, dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """Return `t` as a channels-last tensor of `dtype` (no copy when it already is one)."""
+    if not t.is_contiguous(memory_format=CL):
+        t = t.contiguous(memory_format=CL)          # layout plumbing only (grad tensors produced outside our ops)
+    if dtype is not None and t.dtype != dtype:
+        out = torch.empty_like(t, dtype=dtype, memory_format=torch.preserve_format)
+        call('vqb_convert', ptr(t), dt(t), ptr(out), dt(out), t.numel(), stream())
+        t = out
+    return t
+
+
+def images_to_nhwc(images: torch.Tensor, dtype: torch.dtype, normalize: bool = True) -> torch.Tensor:
+    """NCHW fp32 images -> channels-last; with `normalize` applies clamp[0,1] and (x-0.5)/0.5
+    (reference: BaseVQVAE.preprocess_batch, abstract_modules/base_autoencoder.py:41-50, augmentation excluded)."""
+    if images.dtype != torch.float32:
+        images = images.float()
+    images = images.contiguous()
+    n, c, h, w = images.shape
+    out = empty_nhwc(n, c, h, w, dtype, images.device)
+    if normalize:
+        call('vqb_nchw_to_nhwc', ptr(images), ptr(out), dt(out), n, c, h, w, 1, 0.0, 1.0, 0.5, 2.0, stream())
+    else:
+        call('vqb_nchw_to_nhwc', ptr(images), ptr(out), dt(out), n, c, h, w, 0, 0.0, 0.0, 0.0, 1.0, stream())
+    return out
+
+
+def nhwc_to_images(x: torch.Tensor, scale: float = 1.0, shift: float = 0.0, clamp: Optional[Tuple[float, float]] = None):
+    """channels-last (any dtype) -> NCHW-contiguous fp32, y = x*scale+shift (+clamp)
+    (reference: preprocess_visualization, base_autoencoder.py:52-61)."""
+    x = as_nhwc(x)
+    n, c, h, w = x.shape
+    out = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+    lo, hi = clamp if clamp is not None else (0.0, 0.0)
+    call('vqb_nhwc_to_nchw', ptr(x), dt(x), ptr(out), n, c, h, w, scale, shift, int(clamp is not None), lo, hi, stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------
+# convolution
+# ------------------------------------------------------------------------------------------------------
+def _packed_weight(weight: torch.Tensor, mode: int, dtype: torch.dtype, scale: float = 1.0) -> torch.Tensor:
+    """Cached kernel-layout copy of an nn.Conv2d weight (see vqb_pack_conv_weight for the modes)."""
+    key = (weight._version, _weights_epoch, weight.data_ptr(), scale)
+    cache = getattr(weight, '_vqb_pack', None)
+    if cache is None or cache.get('key') != key:
+        cache = {'key': key}
+        try:
+            weight._vqb_pack = cache
+        except Exception:
+            pass
+    tag = (mode, dtype)
+    if tag not in cache:
+        co, ci, kh, kw = weight.shape
+        wp = torch.empty(co * ci * kh * kw, dtype=dtype, device=weight.device)
+        call('vqb_pack_conv_weight', ptr(weight.detach()), ptr(wp), dt(wp), mode, co, ci, kh, kw, scale, stream())
+        cache[tag] = wp
+    return cache[tag]
+
+
+def _conv_fwd_raw(impl: int, x: torch.Tensor, wp: torch.Tensor, bias, residual, out_dtype, ci, co, kh, kw, pad, stride, act,
+                  alpha, gain) -> torch.Tensor:
+    n, _, h, w = x.shape
+    oh = (h + 2 * pad - kh) // stride + 1
+    ow = (w + 2 * pad - kw) // stride + 1
+    y = empty_nhwc(n, co, oh, ow, out_dtype, x.device)
+    call('vqb_conv2d_fwd', impl, ptr(x), dt(x), ptr(wp), ptr(bias), ptr(residual), ptr(y), dt(y), n, h, w, ci, co, kh, kw,
+         pad, stride, act, alpha, gain, stream())
+    return y
+
+
+class Conv2dFn(torch.autograd.Function):
+    """y = act(conv2d(x, w) + b) * gain + residual   (reference: nn.Conv2d in vqvae/modules/autoencoder.py:55-61,
+    102,114,133,153,170; fused epilogues replace the separate `x + h` of ResBlock.forward :77 and torch.tanh :180)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, pad, stride, act, alpha, gain, out_dtype, w_scale):
+        prec = get_precision()
+        co, ci, kh, kw = weight.shape
+        impl = prec.conv_impl(ci, co, stride)
+        in_dtype = x.dtype
+        if impl == 1:
+            cdt = torch.bfloat16
+        else:
+            cdt = x.dtype if x.dtype in (torch.float32, torch.bfloat16) else prec.act_dtype
+        x = as_nhwc(x, cdt)
+        out_dtype = out_dtype or prec.act_dtype
+        if residual is not None:
+            residual = as_nhwc(residual, out_dtype)
+        wp = _packed_weight(weight, 2 if impl == 1 else 0, torch.bfloat16 if impl == 1 else torch.float32, w_scale)
+        b = bias.detach().reshape(-1).float().contiguous() if bias is not None else None
+        y = _conv_fwd_raw(impl, x, wp, b, residual, out_dtype, ci, co, kh, kw, pad, stride, act, alpha, gain)
+        ctx.save_for_backward(x, weight, y if act != ACT_NONE else None)
+        ctx.cfg = (impl, pad, stride, act, alpha, gain, w_scale, bias is not None, residual is not None,
+                   residual.dtype if residual is not None else None, in_dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, y = ctx.saved_tensors
+        impl, pad, stride, act, alpha, gain, w_scale, has_bias, has_res, res_dtype, in_dtype = ctx.cfg
+        prec = get_precision()
+        co, ci, kh, kw = weight.shape
+        n, _, h, w = x.shape
+        gdt = prec.act_dtype                            # storage dtype of activation gradients
+        dy = as_nhwc(dy)
+        dres = None
+        if has_res:
+            dres = dy if dy.dtype == res_dtype else as_nhwc(dy, res_dtype)
+        if act != ACT_NONE:
+            dpre = torch.empty_like(dy, dtype=gdt, memory_format=torch.preserve_format)
+            call('vqb_act_bwd_from_output', ptr(y), dt(y), ptr(dy), dt(dy), ptr(dpre), dt(dpre), act, alpha, gain,
+                 dy.numel(), stream())
+            dy = dpre
+        elif gain != 1.0:
+            raise lib.VQBError('gain != 1 requires an activation epilogue')
+        _, _, oh, ow = dy.shape
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            if stride != 1:
+                raise lib.VQBError('dgrad for stride != 1 is not implemented')
+            dimpl = prec.conv_impl(co, ci, 1)
+            dyd = as_nhwc(dy, torch.bfloat16) if dimpl == 1 else dy
+            wd = _packed_weight(weight, 3 if dimpl == 1 else 1, torch.bfloat16 if dimpl == 1 else torch.float32, w_scale)
+            # dgrad = correlation of dy with the tap-flipped, channel-swapped weight; padding k-1-pad
+            ddt = in_dtype if (dimpl == 0 or in_dtype == torch.float32) else gdt
+            dx = _conv_fwd_raw(dimpl, dyd, wd, None, None, ddt, co, ci, kh, kw, kh - 1 - pad, 1, ACT_NONE, 0.0, 1.0)
+        if ctx.needs_input_grad[1]:
+            dyw = as_nhwc(dy, torch.bfloat16) if impl == 1 else dy
+            dwp = torch.zeros(kh * kw * ci * co, dtype=torch.float32, device=x.device)
+            call('vqb_conv2d_wgrad', impl, ptr(x), dt(x), ptr(dyw), dt(dyw), ptr(dwp), n, h, w, ci, co, kh, kw, pad, stride,
+                 stream())
+            dw = torch.empty_like(weight, dtype=torch.float32)
+            call('vqb_unpack_conv_wgrad', ptr(dwp), ptr(dw), co, ci, kh, kw, w_scale, stream())
+        if has_bias and ctx.needs_input_grad[2]:
+            db = torch.zeros(co, dtype=torch.float32, device=x.device)
+            call('vqb_colsum', ptr(dy), dt(dy), ptr(db), n * oh * ow, co, stream())
+        return dx, dw, db, dres, None, None, None, None, None, None, None
+
+
+def conv2d(x, weight, bias=None, residual=None, pad=0, stride=1, act=ACT_NONE, alpha=0.0, gain=1.0, out_dtype=None,
+           w_scale=1.0):
+    return Conv2dFn.apply(x, weight, bias, residual, pad, stride, act, alpha, gain, out_dtype, w_scale)
+
+
+# ------------------------------------------------------------------------------------------------------
+# GroupNorm (+SiLU)
+# ------------------------------------------------------------------------------------------------------
+class GroupNormActFn(torch.autograd.Function):
+    """act(GroupNorm(x)) with the reference's unbiased variance (vqvae/modules/autoencoder.py:25-39)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, groups, eps, act):
+        x = as_nhwc(x)
+        n, c, h, w = x.shape
+        ga = gamma.detach().reshape(-1).float().contiguous()
+        be = beta.detach().reshape(-1).float().contiguous()
+        sums = torch.zeros(n * groups * 2, dtype=torch.float64, device=x.device)
+        stats = torch.empty(n * groups * 2, dtype=torch.float32, device=x.device)
+        call('vqb_gn_stats', ptr(x), dt(x), ptr(sums), n, h * w, c, groups, stream())
+        call('vqb_gn_finalize', ptr(sums), ptr(stats), n, h * w, c, groups, eps, stream())
+        y = torch.empty_like(x, memory_format=torch.preserve_format)
+        call('vqb_gn_apply', ptr(x), dt(x), ptr(stats), ptr(ga), ptr(be), ptr(y), dt(y), n, h * w, c, groups, act, stream())
+        ctx.save_for_backward(x, stats, ga, be)
+        ctx.cfg = (groups, act, gamma.shape, beta.shape)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, stats, ga, be = ctx.saved_tensors
+        groups, act, gshape, bshape = ctx.cfg
+        n, c, h, w = x.shape
+        dy = as_nhwc(dy)
+        part = torch.zeros(n * c * 2, dtype=torch.float64, device=x.device)
+        call('vqb_gn_bwd_reduce', ptr(x), dt(x), ptr(dy), dt(dy), ptr(stats), ptr(ga), ptr(be), ptr(part), n, h * w, c, groups,
+             act, stream())
+        coef = torch.empty(n * groups * 2, dtype=torch.float32, device=x.device)
+        dgamma = torch.empty(c, dtype=torch.float32, device=x.device)
+        dbeta = torch.empty(c, dtype=torch.float32, device=x.device)
+        call('vqb_gn_bwd_finalize', ptr(part), ptr(ga), ptr(coef), ptr(dgamma), ptr(dbeta), n, h * w, c, groups, stream())
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x, memory_format=torch.preserve_format)
+            call('vqb_gn_bwd_apply', ptr(x), dt(x), ptr(dy), dt(dy), ptr(stats), ptr(ga), ptr(be), ptr(coef), ptr(dx), dt(dx),
+                 n, h * w, c, groups, act, stream())
+        return dx, dgamma.reshape(gshape), dbeta.reshape(bshape), None, None, None
+
+
+def group_norm_act(x, gamma, beta, groups=32, eps=1e-6, act=ACT_SILU):
+    return GroupNormActFn.apply(x, gamma, beta, groups, eps, act)
+
+
+# ------------------------------------------------------------------------------------------------------
+# 2x resampling
+# ------------------------------------------------------------------------------------------------------
+def _down2(x, scale):
+    n, c, h, w = x.shape
+    y = empty_nhwc(n, c, h // 2, w // 2, x.dtype, x.device)
+    call('vqb_down2', ptr(x), ptr(y), dt(x), n, h // 2, w // 2, c, scale, stream())
+    return y
+
+
+def _up2(x, scale):
+    n, c, h, w = x.shape
+    y = empty_nhwc(n, c, 2 * h, 2 * w, x.dtype, x.device)
+    call('vqb_up2', ptr(x), ptr(y), dt(x), n, h, w, c, scale, stream())
+    return y
+
+
+class AvgPool2Fn(torch.autograd.Function):
+    """F.avg_pool2d(x, 2, 2, 0)  (reference Downsample, autoencoder.py:89-91)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = as_nhwc(x)
+        if x.shape[2] % 2 or x.shape[3] % 2:
+            raise lib.VQBError('avg_pool2: odd spatial size')
+        return _down2(x, 0.25)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return _up2(as_nhwc(dy), 0.25)
+
+
+class Upsample2Fn(torch.autograd.Function):
+    """F.interpolate(x, scale_factor=2, mode='nearest-exact')  (reference Upsample, autoencoder.py:103-105)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return _up2(as_nhwc(x), 1.0)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return _down2(as_nhwc(dy), 1.0)
+
+
+avg_pool2 = AvgPool2Fn.apply
+upsample2 = Upsample2Fn.apply
+
+
+# ------------------------------------------------------------------------------------------------------
+# reconstruction losses
+# ------------------------------------------------------------------------------------------------------
+class DiffLossFn(torch.autograd.Function):
+    """Returns (mean((a-b)^2), mean(|a-b|)) -- F.mse_loss (vqvae/model.py:274) and the L1/L2 terms of
+    loss/loss.py:118-119.  `a_is_tanh` folds the tanh derivative of the producing conv epilogue into the gradient
+    when `a` is marked as a tanh output (then the producer must NOT apply it again)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        a = as_nhwc(a)
+        b = as_nhwc(b)
+        sums = torch.zeros(2, dtype=torch.float64, device=a.device)
+        call('vqb_diff_sums', ptr(a), dt(a), ptr(b), dt(b), ptr(sums), a.numel(), stream())
+        ctx.save_for_backward(a, b)
+        out = (sums / a.numel()).float()
+        return out[0], out[1]
+
+    @staticmethod
+    def backward(ctx, g2, g1):
+        a, b = ctx.saved_tensors
+        n = a.numel()
+        # the upstream scalars stay on the device (no host sync): up = [g_l2, g_l1]
+        up = torch.stack([g2.reshape(()), g1.reshape(())]).float().contiguous()
+        da = torch.empty_like(a, memory_format=torch.preserve_format)
+        call('vqb_diff_grad', ptr(a), dt(a), ptr(b), dt(b), ptr(da), dt(da), 1.0 / n, 1.0 / n, ptr(up), 0, n, stream())
+        return da, None
+
+
+def mse_l1(a, b):
+    return DiffLossFn.apply(a, b)
+
+
+# ------------------------------------------------------------------------------------------------------
+# vector quantisation
+# ------------------------------------------------------------------------------------------------------
+def vq_assign_raw(flat: torch.Tensor, codebook: torch.Tensor, order: int, want_q: bool = True, want_stats: bool = False):
+    """flat [N,D] fp32, codebook [K,D] fp32 -> (q or None, idx int64 [N], sse double[1], counts [K] or None, dw [K,D] or None)."""
+    n, d = flat.shape
+    k = codebook.shape[0]
+    dev = flat.device
+    q = torch.empty_like(flat) if want_q else None
+    idx = torch.empty(n, dtype=torch.int64, device=dev)
+    sse = torch.zeros(1, dtype=torch.float64, device=dev)
+    counts = torch.zeros(k, dtype=torch.float32, device=dev)
+    dw = torch.zeros(k, d, dtype=torch.float32, device=dev) if want_stats else None
+    ws_bytes = lib.load().vqb_vq_workspace_bytes(n, k, d)
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+    call('vqb_vq_assign', ptr(flat), ptr(codebook), order, ptr(q), ptr(idx), ptr(sse), ptr(counts), ptr(dw), n, k, d, ptr(ws),
+         ws_bytes, stream())
+    return q, idx, sse, counts, dw
+
+
+class VQFn(torch.autograd.Function):
+    """Fused nearest-code quantisation with straight-through estimator and the MSE latent losses.
+
+    forward(z [B,D,h,w] channels-last fp32, codebook [K,D]) ->
+        (quantized [B,D,h,w], idx [B,h*w] int64, loss = (beta + cb_scale) * mean((e[idx]-z)^2), counts [K], dw [K,D] | None)
+    reference: VectorQuantizer.forward vector_quantizers.py:23-61 (cb_scale=1), EMAVectorQuantizer.forward :128-180
+    (cb_scale=0; the EMA state update itself is vqb_vq_ema_update, called by the module), EntropyVectorQuantizer :337-349.
+    """
+
+    @staticmethod
+    def forward(ctx, z, codebook, order, beta, cb_scale, want_stats):
+        z = as_nhwc(z, torch.float32)
+        b, d, h, w = z.shape
+        flat = z.permute(0, 2, 3, 1).reshape(b * h * w, d)        # a view: channels-last memory is already (b h w) c
+        cb = codebook.detach().float().contiguous()
+        q, idx, sse, counts, dw = vq_assign_raw(flat, cb, order, True, want_stats)
+        loss = (sse[0] * ((beta + cb_scale) / flat.numel())).float()
+        ctx.save_for_backward(flat, q, idx)
+        ctx.cfg = (beta, cb_scale, codebook.shape, z.shape)
+        qz = q.reshape(b, h, w, d).permute(0, 3, 1, 2)             # logical NCHW, physical NHWC
+        ctx.mark_non_differentiable(idx, counts)
+        if dw is not None:
+            ctx.mark_non_differentiable(dw)
+        return qz, idx.reshape(b, h * w), loss, counts, dw
+
+    @staticmethod
+    def backward(ctx, g_q, _g_idx, g_loss, _g_counts, _g_dw):
+        flat, q, idx = ctx.saved_tensors
+        beta, cb_scale, cb_shape, zshape = ctx.cfg
+        n, d = flat.shape
+        k = cb_shape[0]
+        gq = as_nhwc(g_q, torch.float32) if g_q is not None else None
+        gl = g_loss.reshape(1).float().contiguous() if g_loss is not None else torch.zeros(1, device=flat.device)
+        dz = torch.empty_like(flat)
+        dcb = torch.zeros(cb_shape, dtype=torch.float32, device=flat.device) if (ctx.needs_input_grad[1] and cb_scale != 0.0) else None
+        call('vqb_vq_backward', ptr(flat), ptr(q), ptr(idx), ptr(gq), ptr(gl), beta, cb_scale, ptr(dz), ptr(dcb), n, k, d,
+             stream())
+        b, _, h, w = zshape
+        return dz.reshape(b, h, w, d).permute(0, 3, 1, 2), dcb, None, None, None, None
+
+
+def vq_quantize(z, codebook, order=0, beta=0.25, cb_scale=1.0, want_stats=False):
+    return VQFn.apply(z, codebook, order, beta, cb_scale, want_stats)
+
+
+def vq_codes(z, codebook, order=0):
+    """argmin only (vec_to_codes, vector_quantizers.py:63-84,182-203,358-381) -> idx [B, h*w] int64."""
+    z = as_nhwc(z.detach(), torch.float32)
+    b, d, h, w = z.shape
+    flat = z.permute(0, 2, 3, 1).reshape(b * h * w, d)
+    _, idx, _, _, _ = vq_assign_raw(flat, codebook.detach().float().contiguous(), order, False, False)
+    return idx.reshape(b, h * w)
+
+
+def vq_ema_update(ema_count, ema_weight, codebook, counts, dw, decay, eps, batch):
+    k, d = codebook.shape
+    call('vqb_vq_ema_update', ptr(ema_count), ptr(ema_weight), ptr(codebook), ptr(counts), ptr(dw), k, d, decay, eps,
+         float(batch), stream())
+
+
+def vq_gather(codebook, idx):
+    """codes_to_vec (abstract_modules/base_quantizer.py:53-61): idx [...,] int64 -> [..., D]."""
+    cb = codebook.detach().float().contiguous()
+    flat_idx = idx.reshape(-1).to(torch.int64).contiguous()
+    out = torch.empty(flat_idx.numel(), cb.shape[1], dtype=torch.float32, device=cb.device)
+    call('vqb_vq_gather', ptr(cb), ptr(flat_idx), ptr(out), flat_idx.numel(), cb.shape[0], cb.shape[1], stream())
+    return out.reshape(*idx.shape, cb.shape[1])
+
+
+# ------------------------------------------------------------------------------------------------------
+# optimizer
+# ------------------------------------------------------------------------------------------------------
+def adamw_flat(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
+    call('vqb_adamw', ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), lr, beta1, beta2, eps, weight_decay, step, grad_scale, stream())
+    bump_weights_epoch()

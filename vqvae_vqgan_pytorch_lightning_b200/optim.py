@@ -1,0 +1,75 @@
+"""Fused AdamW over flat parameter / gradient / moment buffers.
+
+Replaces torch.optim.AdamW as configured by VQVAE.configure_optimizers (reference vqvae/model.py:411-438): same
+update rule and param-group interface (`param_groups[i]['lr']` is what on_train_batch_start rewrites every step,
+model.py:216-218), but all tensors of a group live in ONE contiguous fp32 range so that the update is one kernel
+launch per group (vqb_adamw) and the data-parallel gradient all-reduce is one NCCL call on one buffer.
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional
+
+import torch
+
+from . import ops
+
+
+class FusedAdamW(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
+        defaults = dict(lr=float(lr), betas=tuple(float(b) for b in betas), eps=float(eps), weight_decay=float(weight_decay))
+        super().__init__(params, defaults)
+        self._ranges = []          # per group: (start, end) in the flat buffers
+        live: List[List[torch.nn.Parameter]] = []
+        total = 0
+        device = None
+        for g in self.param_groups:
+            ps = [p for p in g['params'] if p.requires_grad]
+            for p in ps:
+                if p.dtype != torch.float32:
+                    raise TypeError('FusedAdamW keeps fp32 master parameters')
+                device = device or p.device
+            live.append(ps)
+            n = sum(p.numel() for p in ps)
+            self._ranges.append((total, total + n))
+            total += n
+        if device is None or device.type != 'cuda':
+            raise RuntimeError('FusedAdamW needs CUDA parameters (no CPU fallback)')
+        self.flat_param = torch.empty(total, dtype=torch.float32, device=device)
+        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=device)
+        self.exp_avg = torch.zeros(total, dtype=torch.float32, device=device)
+        self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=device)
+        off = 0
+        with torch.no_grad():
+            for ps in live:
+                for p in ps:
+                    n = p.numel()
+                    view = self.flat_param[off:off + n].view(p.shape)
+                    view.copy_(p.data)
+                    p.data = view                                   # parameters become views of the flat buffer
+                    p.grad = self.flat_grad[off:off + n].view(p.shape)   # autograd accumulates in place into these views
+                    off += n
+        self._live = live
+        self.step_count = 0
+        self.grad_scale = 1.0       # set to 1/world_size by the data-parallel trainer (after a SUM all-reduce)
+        ops.bump_weights_epoch()
+
+    def zero_grad(self, set_to_none: bool = False) -> None:      # grads must stay views of flat_grad
+        self.flat_grad.zero_()
+        off = 0
+        for ps in self._live:
+            for p in ps:
+                n = p.numel()
+                if p.grad is None or p.grad.data_ptr() != self.flat_grad.data_ptr() + 4 * off:
+                    p.grad = self.flat_grad[off:off + n].view(p.shape)
+                off += n
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        self.step_count += 1
+        for g, (a, b) in zip(self.param_groups, self._ranges):
+            if b > a:
+                ops.adamw_flat(self.flat_param[a:b], self.flat_grad[a:b], self.exp_avg[a:b], self.exp_avg_sq[a:b],
+                               float(g['lr']), g['betas'][0], g['betas'][1], g['eps'], g['weight_decay'], self.step_count,
+                               self.grad_scale)
+        return loss
