@@ -96,11 +96,39 @@ def stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+class KernelTimer:
+    """Optional per-entry-point device timing (CUDA events on the launching stream, resolved after a sync).
+    bench.py uses it to measure the dominant kernel's average launch duration inside the timed region."""
+
+    def __init__(self, names):
+        self.names = set(names)
+        self.records = []          # (name, args, start_event, end_event)
+
+    def summary(self):
+        out = {}
+        for name, args, e0, e1 in self.records:
+            d = out.setdefault(name, {'calls': 0, 'ms': 0.0, 'args': []})
+            d['calls'] += 1
+            d['ms'] += e0.elapsed_time(e1)
+            d['args'].append(args)
+        return out
+
+
+timer: Optional[KernelTimer] = None
+
+
 def call(name: str, *args) -> None:
     """Invoke an int-returning entry point and raise on a non-zero status."""
     global launch_count
     lib = load()
-    rc = getattr(lib, name)(*args)
+    if timer is not None and name in timer.names:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args)
+        e1.record()
+        timer.records.append((name, args, e0, e1))
+    else:
+        rc = getattr(lib, name)(*args)
     launch_count += 1
     if rc != 0:
         raise VQBError(f'{name} failed ({rc}): {lib.vqb_last_error().decode()}')
