@@ -1,0 +1,77 @@
+"""GPU parity of the tcgen05/TMA implicit-GEMM convolution (bf16 operands, fp32 accumulate) against the CPU oracle.
+
+Inputs are pre-rounded to bf16 so that the oracle (fp32 F.conv2d on the same rounded values) differs only by
+accumulation order: fp32 outputs must agree to 1e-4 relative; bf16 outputs to bf16 rounding (4e-3)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests import common as C
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def V():
+    import vqvae_vqgan_pytorch_lightning_b200 as pkg
+    pkg.lib.load()
+    if not pkg.lib.load().vqb_device_supports_tcgen05():
+        pytest.skip('needs sm_100')
+    pkg.set_precision('fast')
+    yield pkg
+    pkg.set_precision('strict')
+
+
+def cl(t):
+    return t.cuda().contiguous(memory_format=torch.channels_last)
+
+
+def r16(t):
+    return t.bfloat16().float()
+
+
+CASES = [
+    # n, h, w, ci, co, k, bias, res, act
+    (2, 16, 16, 64, 64, 3, False, False, 0),
+    (1, 16, 16, 128, 128, 3, True, True, 0),
+    (3, 16, 16, 128, 256, 3, False, False, 0),
+    (2, 32, 32, 256, 128, 3, False, True, 0),
+    (2, 8, 8, 512, 256, 1, True, False, 0),
+    (5, 4, 4, 128, 128, 3, False, False, 0),        # spatial smaller than a tile: several images per TMA box, N not a multiple
+    (2, 12, 20, 64, 128, 3, False, False, 0),       # H, W not powers of two: partially out-of-bounds boxes
+    (1, 64, 64, 128, 128, 3, False, False, 0),
+    (2, 16, 16, 512, 512, 3, False, False, 0),      # two Co tiles, 72 k-steps (pipeline wrap-around)
+]
+
+
+@pytest.mark.parametrize('n,h,w,ci,co,k,bias,res,act', CASES)
+def test_conv_tc_forward_fp32_out(V, n, h, w, ci, co, k, bias, res, act):
+    torch.manual_seed(0)
+    x = r16(torch.randn(n, ci, h, w))
+    wt = r16(torch.randn(co, ci, k, k) / (ci * k * k) ** 0.5)
+    b = torch.randn(co) if bias else None
+    r = torch.randn(n, co, h, w) if res else None
+    y = F.conv2d(x, wt, b, padding=k // 2)
+    if res:
+        y = y + r
+    yg = V.ops.conv2d(cl(x).bfloat16(), wt.cuda(), b.cuda() if bias else None, cl(r) if res else None, pad=k // 2,
+                      out_dtype=torch.float32)
+    assert yg.dtype == torch.float32
+    assert C.rel_err(yg, y) < 1e-4
+    assert C.max_rel(yg, y) < 5e-3
+
+
+@pytest.mark.parametrize('n,h,w,ci,co,k,bias,res,act', CASES)
+def test_conv_tc_backward(V, n, h, w, ci, co, k, bias, res, act):
+    torch.manual_seed(1)
+    x = r16(torch.randn(n, ci, h, w))
+    wt = r16(torch.randn(co, ci, k, k) / (ci * k * k) ** 0.5)
+    go = r16(torch.randn(n, co, h, w))
+    xo, wo = x.clone().requires_grad_(), wt.clone().requires_grad_()
+    F.conv2d(xo, wo, None, padding=k // 2).backward(go)
+    xg, wg = cl(x).bfloat16().requires_grad_(), wt.cuda().requires_grad_()
+    yg = V.ops.conv2d(xg, wg, None, None, pad=k // 2)
+    assert yg.dtype == torch.bfloat16
+    yg.backward(cl(go).bfloat16())
+    assert C.rel_err(xg.grad.float(), xo.grad) < 4e-3          # dgrad output is stored as bf16
+    assert C.rel_err(wg.grad, wo.grad) < 1e-4                  # wgrad accumulates and stores fp32

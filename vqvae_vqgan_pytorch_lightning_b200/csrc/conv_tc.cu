@@ -1,11 +1,435 @@
-// placeholder until the tcgen05 path lands
+// tcgen05 / TMA implicit-GEMM convolution for sm_100a (bf16 operands, fp32 accumulation in TMEM).
+//
+// Forward / dgrad  (conv_fwd_tc_kernel, persistent, warp-specialised):
+//   D[128 pixels][BN co] += A[128 pixels][64 ci] * B[BN co][64 ci]^T   for every (tap, ci-chunk)
+//   * A is NOT materialised (no im2col): one 4-D TMA box {64 ch, tw, th, nb} of the NHWC activation at spatial offset
+//     (kh-pad, kw-pad) lands in shared memory as a K-major SWIZZLE_128B tile; out-of-image elements are zero-filled by
+//     the TMA unit, which IS the convolution's zero padding.
+//   * B is a 2-D TMA box of the packed weight [Co][(kh,kw,ci)].
+//   * warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread tcgen05.mma issuer, warps 2..5 = epilogue
+//     (tcgen05.ld -> bias / activation / residual -> NHWC global stores).  The fp32 accumulator is double-buffered in
+//     TMEM (2 x BN columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Weight gradient (conv_wgrad_tc_kernel):
+//   dW[tap][ci][co] = sum_pixels x_shift[pix][ci] * dy[pix][co]: the reduction runs over pixels, so both operands are
+//   MN-major SWIZZLE_128B tiles (rows = pixels, 128 B = 64 channels), again straight from 4-D TMA boxes.  M = 128 co
+//   (TMEM lanes), N = up to 256 ci (TMEM columns); the pixel range is split across CTAs and partial tiles are combined
+//   with fp32 red.global.add (coalesced across lanes).
+//
+// Roofline: tensor pipe (bf16 dense); see DESIGN.md for the per-layer FLOP table.
 #include "common.cuh"
-int vqb_conv2d_fwd_tc(const void*, const void*, const float*, const void*, void*, int, int, int, int, int, int, int, int, int,
-                      int, float, float, cudaStream_t) {
-    vqb_set_error("conv2d_fwd(tcgen05): not built");
-    return VQB_ERR_UNSUPPORTED;
+#include "ptx.cuh"
+#include <mutex>
+
+namespace {
+
+constexpr int BM = 128;          // UMMA M (pixels for fwd, co for wgrad)
+constexpr int BK = 64;           // K elements per pipeline stage (one 128-byte swizzle row of bf16)
+constexpr int UMMA_K = 16;
+constexpr int NTHREADS = 192;    // 6 warps: TMA, MMA, 4 x epilogue
+constexpr int SMEM_LIMIT = 227 * 1024;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
 }
-int vqb_conv2d_wgrad_tc(const void*, const void*, float*, int, int, int, int, int, int, int, int, cudaStream_t) {
-    vqb_set_error("conv2d_wgrad(tcgen05): not built");
-    return VQB_ERR_UNSUPPORTED;
+
+// NHWC bf16 activation as a 4-D tensor {C, W, H, N} with box {64, tw, th, nb}
+int make_act_map(CUtensorMap* m, const void* base, int N, int H, int W, int C, int tw, int th, int nb) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { vqb_set_error("cuTensorMapEncodeTiled unavailable"); return VQB_ERR_CUDA; }
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)nb};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { vqb_set_error("cuTensorMapEncodeTiled(activation) failed: %d", (int)r); return VQB_ERR_CUDA; }
+    return VQB_OK;
+}
+
+// packed weight [rows][K] bf16 as a 2-D tensor {K, rows} with box {64, box_rows}
+int make_weight_map(CUtensorMap* m, const void* base, int rows, int K, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { vqb_set_error("cuTensorMapEncodeTiled unavailable"); return VQB_ERR_CUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { vqb_set_error("cuTensorMapEncodeTiled(weight) failed: %d", (int)r); return VQB_ERR_CUDA; }
+    return VQB_OK;
+}
+
+inline int pow2_floor(int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; }
+
+// spatial tile of `pixels` (power of two) pixels: tw x th x nb
+inline void pick_tile(int pixels, int H, int W, int& tw, int& th, int& nb) {
+    tw = pow2_floor(W); if (tw > 16) tw = 16; if (tw > pixels) tw = pixels;
+    th = pow2_floor(H); if (th > pixels / tw) th = pixels / tw;
+    nb = pixels / (tw * th);
+}
+
+__device__ __forceinline__ float act_f(float v, int act, float alpha) {
+    if (act == VQB_ACT_TANH) return tanhf(v);
+    if (act == VQB_ACT_SILU) return silu_f(v);
+    if (act == VQB_ACT_LRELU) return v > 0.f ? v : v * alpha;
+    if (act == VQB_ACT_RELU) return fmaxf(v, 0.f);
+    return v;
+}
+
+struct FwdParams {
+    int N, H, W, Ci, Co, KH, KW, pad;
+    int tw, th, nb, tiles_w, tiles_h, tiles_n, co_tiles, BN, stages;
+    int num_tiles, ksteps, cchunks;
+    const float* bias;
+    const void* residual;
+    void* y;
+    int y_f32, act;
+    float alpha, gain;
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const FwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int a_bytes = BM * BK * 2;                 // 16 KB
+    const int b_bytes = p.BN * BK * 2;
+    const int stage_bytes = a_bytes + b_bytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+    uint64_t* empty = full + p.stages;
+    uint64_t* tfull = empty + p.stages;              // [2]
+    uint64_t* tempty = tfull + 2;                    // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmA);
+        ptx::prefetch_tmap(&tmB);
+        for (int i = 0; i < p.stages; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull[i], 1); ptx::mbar_init(&tempty[i], 4); }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                int ct = tile % p.co_tiles; int pt = tile / p.co_tiles;
+                int twi = pt % p.tiles_w; int t2 = pt / p.tiles_w; int thi = t2 % p.tiles_h; int tni = t2 / p.tiles_h;
+                int w0 = twi * p.tw, h0 = thi * p.th, n0 = tni * p.nb, co0 = ct * p.BN;
+                for (int tap = 0; tap < p.KH * p.KW; ++tap) {
+                    int kh = tap / p.KW, kw = tap - kh * p.KW;
+                    for (int cc = 0; cc < p.cchunks; ++cc) {
+                        ptx::mbar_wait(&empty[stage], phase ^ 1);
+                        uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                        ptx::mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
+                        ptx::tma_load_4d(sa, &tmA, &full[stage], cc * BK, w0 + kw - p.pad, h0 + kh - p.pad, n0);
+                        ptx::tma_load_2d(sa + a_bytes, &tmB, &full[stage], tap * p.Ci + cc * BK, co0);
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint32_t idesc = ptx::umma_idesc_bf16(BM, p.BN, 0, 0);
+            int stage = 0; uint32_t phase = 0;
+            int as = 0; uint32_t aphase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                ptx::mbar_wait(&tempty[as], aphase ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.BN);
+                for (int ks = 0; ks < p.ksteps; ++ks) {
+                    ptx::mbar_wait(&full[stage], phase);
+                    ptx::tc_fence_after();
+                    const uint32_t sa = ptx::smem_u32(smem + (size_t)stage * stage_bytes);
+                    const uint64_t adesc = ptx::umma_smem_desc(sa, 0, 1024);
+                    const uint64_t bdesc = ptx::umma_smem_desc(sa + a_bytes, 0, 1024);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k)
+                        ptx::umma_bf16(d_tmem, adesc + (uint64_t)(k * UMMA_K * 2 / 16), bdesc + (uint64_t)(k * UMMA_K * 2 / 16), idesc,
+                                       (ks | k) != 0 ? 1u : 0u);
+                    ptx::umma_commit(&empty[stage]);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+                ptx::umma_commit(&tfull[as]);
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+        }
+    } else {
+        // ================= epilogue (warps 2..5; TMEM lane quarter = warp % 4) =================
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        int as = 0; uint32_t aphase = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            int ct = tile % p.co_tiles; int pt = tile / p.co_tiles;
+            int twi = pt % p.tiles_w; int t2 = pt / p.tiles_w; int thi = t2 % p.tiles_h; int tni = t2 / p.tiles_h;
+            int wi = row % p.tw; int r2 = row / p.tw; int hi = r2 % p.th; int ni = r2 / p.th;
+            int w = twi * p.tw + wi, h = thi * p.th + hi, n = tni * p.nb + ni;
+            const bool valid = (w < p.W) && (h < p.H) && (n < p.N);
+            const int64_t pix = ((int64_t)n * p.H + h) * p.W + w;
+            const int co0 = ct * p.BN;
+            ptx::mbar_wait(&tfull[as], aphase);
+            ptx::tc_fence_after();
+            const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * p.BN);
+            for (int c = 0; c < p.BN; c += 32) {
+                uint32_t r[32];
+                ptx::tmem_ld32(t_addr + (uint32_t)c, r);
+                ptx::tmem_ld_wait();
+                if (valid) {
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float t = __uint_as_float(r[j]);
+                        if (p.bias) t += __ldg(p.bias + co0 + c + j);
+                        v[j] = act_f(t, p.act, p.alpha) * p.gain;
+                    }
+                    const int64_t off = pix * p.Co + co0 + c;
+                    if (p.y_f32) {
+                        float* yo = reinterpret_cast<float*>(p.y) + off;
+                        const float* ro = p.residual ? reinterpret_cast<const float*>(p.residual) + off : nullptr;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                            if (ro) { float4 q = *reinterpret_cast<const float4*>(ro + j); o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w; }
+                            *reinterpret_cast<float4*>(yo + j) = o;
+                        }
+                    } else {
+                        bf16* yo = reinterpret_cast<bf16*>(p.y) + off;
+                        const bf16* ro = p.residual ? reinterpret_cast<const bf16*>(p.residual) + off : nullptr;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            if (ro) {
+                                uint4 q = *reinterpret_cast<const uint4*>(ro + j);
+                                const __nv_bfloat162* qb = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) { float2 f = __bfloat1622float2(qb[u]); v[j + 2 * u] += f.x; v[j + 2 * u + 1] += f.y; }
+                            }
+                            uint4 o;
+                            __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) ob[u] = __floats2bfloat162_rn(v[j + 2 * u], v[j + 2 * u + 1]);
+                            *reinterpret_cast<uint4*>(yo + j) = o;
+                        }
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tempty[as]);
+            if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+struct WgradParams {
+    int N, H, W, Ci, Co, KH, KW, pad;
+    int tw, th, nb, tiles_w, tiles_h, tiles_n;
+    int CN, co_tiles, ci_tiles, stages;
+    int ptiles_total, ptiles_per_split;
+    float* dwp;
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX, const WgradParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int blk_bytes = BK * 128;                     // one [64 pixels][64 channels] bf16 box = 8 KB
+    const int a_bytes = (BM / 64) * blk_bytes;          // dy: 128 co
+    const int b_bytes = (p.CN / 64) * blk_bytes;        // x : CN ci
+    const int stage_bytes = a_bytes + b_bytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+    uint64_t* empty = full + p.stages;
+    uint64_t* tfull = empty + p.stages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // tile decode: blockIdx.x = ((tap * ci_tiles + cit) * co_tiles + cot), blockIdx.y = pixel split
+    int cot = blockIdx.x % p.co_tiles; int t1 = blockIdx.x / p.co_tiles; int cit = t1 % p.ci_tiles; int tap = t1 / p.ci_tiles;
+    const int kh = tap / p.KW, kw = tap - kh * p.KW;
+    const int co0 = cot * BM, ci0 = cit * p.CN;
+    const int pt_begin = blockIdx.y * p.ptiles_per_split;
+    int pt_end = pt_begin + p.ptiles_per_split; if (pt_end > p.ptiles_total) pt_end = p.ptiles_total;
+    const int nsteps = pt_end - pt_begin;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmDy);
+        ptx::prefetch_tmap(&tmX);
+        for (int i = 0; i < p.stages; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 1); }
+        ptx::mbar_init(tfull, 1);
+        ptx::fence_barrier_init();
+    }
+    uint32_t tcols = 32; while ((int)tcols < p.CN) tcols <<= 1;
+    if (warp == 1) ptx::tmem_alloc(tmem_slot, tcols);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (nsteps > 0) {
+        if (warp == 0) {
+            if (lane == 0) {
+                int stage = 0; uint32_t phase = 0;
+                for (int pt = pt_begin; pt < pt_end; ++pt) {
+                    int twi = pt % p.tiles_w; int t2 = pt / p.tiles_w; int thi = t2 % p.tiles_h; int tni = t2 / p.tiles_h;
+                    int w0 = twi * p.tw, h0 = thi * p.th, n0 = tni * p.nb;
+                    ptx::mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                    ptx::mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
+                    for (int j = 0; j < BM / 64; ++j)
+                        ptx::tma_load_4d(sa + j * blk_bytes, &tmDy, &full[stage], co0 + j * 64, w0, h0, n0);
+                    for (int j = 0; j < p.CN / 64; ++j)
+                        ptx::tma_load_4d(sa + a_bytes + j * blk_bytes, &tmX, &full[stage], ci0 + j * 64, w0 + kw - p.pad, h0 + kh - p.pad, n0);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        } else if (warp == 1) {
+            if (lane == 0) {
+                const uint32_t idesc = ptx::umma_idesc_bf16(BM, p.CN, 1, 1);
+                int stage = 0; uint32_t phase = 0;
+                for (int s = 0; s < nsteps; ++s) {
+                    ptx::mbar_wait(&full[stage], phase);
+                    ptx::tc_fence_after();
+                    const uint32_t sa = ptx::smem_u32(smem + (size_t)stage * stage_bytes);
+                    // MN-major: LBO = stride between 64-channel blocks (one 8 KB box), SBO = 1024 (8 pixel rows)
+                    const uint64_t adesc = ptx::umma_smem_desc(sa, (uint32_t)blk_bytes, 1024);
+                    const uint64_t bdesc = ptx::umma_smem_desc(sa + a_bytes, (uint32_t)blk_bytes, 1024);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k)      // 16 pixel rows = 2048 bytes per UMMA
+                        ptx::umma_bf16(tmem_base, adesc + (uint64_t)(k * UMMA_K * 128 / 16), bdesc + (uint64_t)(k * UMMA_K * 128 / 16),
+                                       idesc, (s | k) != 0 ? 1u : 0u);
+                    ptx::umma_commit(&empty[stage]);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+                ptx::umma_commit(tfull);
+            }
+        } else {
+            const int quarter = warp & 3;
+            const int co = co0 + quarter * 32 + lane;
+            ptx::mbar_wait(tfull, 0);
+            ptx::tc_fence_after();
+            const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+            float* out = p.dwp + ((int64_t)tap * p.Ci + ci0) * p.Co + co;
+            for (int c = 0; c < p.CN; c += 32) {
+                uint32_t r[32];
+                ptx::tmem_ld32(t_addr + (uint32_t)c, r);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) atomicAdd(out + (int64_t)(c + j) * p.Co, __uint_as_float(r[j]));
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, tcols);
+    }
+}
+
+int sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+}  // namespace
+
+int vqb_conv2d_fwd_tc(const void* x, const void* wp, const float* bias, const void* residual, void* y, int y_dtype, int N,
+                      int H, int W, int Ci, int Co, int KH, int KW, int pad, int act, float alpha, float gain,
+                      cudaStream_t stream) {
+    VQB_CHECK_ARG(N > 0 && H > 0 && W > 0 && KH > 0 && KW > 0 && pad >= 0, "conv2d_fwd(tcgen05): bad geometry");
+    VQB_CHECK_ARG(Ci % 64 == 0 && Co % 64 == 0, "conv2d_fwd(tcgen05): Ci and Co must be multiples of 64 (got %d, %d)", Ci, Co);
+    VQB_CHECK_ARG(H + 2 * pad - KH + 1 == H && W + 2 * pad - KW + 1 == W, "conv2d_fwd(tcgen05): only 'same' convolutions");
+    VQB_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)wp & 15) == 0 && ((uintptr_t)y & 15) == 0, "conv2d_fwd(tcgen05): unaligned pointer");
+    FwdParams p;
+    p.N = N; p.H = H; p.W = W; p.Ci = Ci; p.Co = Co; p.KH = KH; p.KW = KW; p.pad = pad;
+    pick_tile(BM, H, W, p.tw, p.th, p.nb);
+    p.tiles_w = (W + p.tw - 1) / p.tw; p.tiles_h = (H + p.th - 1) / p.th; p.tiles_n = (N + p.nb - 1) / p.nb;
+    p.BN = (Co % 256 == 0) ? 256 : ((Co % 128 == 0) ? 128 : 64);
+    p.co_tiles = Co / p.BN;
+    p.cchunks = Ci / BK;
+    p.ksteps = KH * KW * p.cchunks;
+    p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.co_tiles;
+    const int stage_bytes = BM * BK * 2 + p.BN * BK * 2;
+    p.stages = (SMEM_LIMIT - 2048) / stage_bytes; if (p.stages > 8) p.stages = 8;
+    p.bias = bias; p.residual = residual; p.y = y; p.y_f32 = (y_dtype == VQB_F32); p.act = act; p.alpha = alpha; p.gain = gain;
+    CUtensorMap tmA, tmB;
+    int rc = make_act_map(&tmA, x, N, H, W, Ci, p.tw, p.th, p.nb); if (rc) return rc;
+    rc = make_weight_map(&tmB, wp, Co, KH * KW * Ci, p.BN); if (rc) return rc;
+    size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256;
+    VQB_CUDA(cudaFuncSetAttribute(conv_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+    conv_fwd_tc_kernel<<<grid, NTHREADS, smem, stream>>>(tmA, tmB, p);
+    VQB_CHECK_LAUNCH("conv2d_fwd_tc");
+    return VQB_OK;
+}
+
+int vqb_conv2d_wgrad_tc(const void* x, const void* dy, float* dwp, int N, int H, int W, int Ci, int Co, int KH, int KW,
+                        int pad, cudaStream_t stream) {
+    VQB_CHECK_ARG(N > 0 && H > 0 && W > 0 && KH > 0 && KW > 0 && pad >= 0, "conv2d_wgrad(tcgen05): bad geometry");
+    VQB_CHECK_ARG(Ci % 64 == 0 && Co % 128 == 0, "conv2d_wgrad(tcgen05): need Ci %% 64 == 0 and Co %% 128 == 0 (got %d, %d)", Ci, Co);
+    VQB_CHECK_ARG(H + 2 * pad - KH + 1 == H && W + 2 * pad - KW + 1 == W, "conv2d_wgrad(tcgen05): only 'same' convolutions");
+    WgradParams p;
+    p.N = N; p.H = H; p.W = W; p.Ci = Ci; p.Co = Co; p.KH = KH; p.KW = KW; p.pad = pad;
+    pick_tile(BK, H, W, p.tw, p.th, p.nb);
+    p.tiles_w = (W + p.tw - 1) / p.tw; p.tiles_h = (H + p.th - 1) / p.th; p.tiles_n = (N + p.nb - 1) / p.nb;
+    p.CN = (Ci % 256 == 0) ? 256 : ((Ci % 128 == 0) ? 128 : 64);
+    p.co_tiles = Co / BM; p.ci_tiles = Ci / p.CN;
+    const int stage_bytes = (BM / 64 + p.CN / 64) * BK * 128;
+    p.stages = (SMEM_LIMIT - 2048) / stage_bytes; if (p.stages > 8) p.stages = 8;
+    p.ptiles_total = p.tiles_w * p.tiles_h * p.tiles_n;
+    const int out_tiles = KH * KW * p.ci_tiles * p.co_tiles;
+    int splits = (sm_count() * 2 + out_tiles - 1) / out_tiles;       // ~2 waves of CTAs
+    int max_splits = (p.ptiles_total + 7) / 8; if (max_splits < 1) max_splits = 1;   // >= 8 pixel tiles (512 pixels) per CTA
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    p.ptiles_per_split = (p.ptiles_total + splits - 1) / splits;
+    splits = (p.ptiles_total + p.ptiles_per_split - 1) / p.ptiles_per_split;
+    p.dwp = dwp;
+    CUtensorMap tmDy, tmX;
+    int rc = make_act_map(&tmDy, dy, N, H, W, Co, p.tw, p.th, p.nb); if (rc) return rc;
+    rc = make_act_map(&tmX, x, N, H, W, Ci, p.tw, p.th, p.nb); if (rc) return rc;
+    size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256;
+    VQB_CUDA(cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(out_tiles, splits);
+    conv_wgrad_tc_kernel<<<grid, NTHREADS, smem, stream>>>(tmDy, tmX, p);
+    VQB_CHECK_LAUNCH("conv2d_wgrad_tc");
+    return VQB_OK;
 }

@@ -34,7 +34,13 @@ class Precision:
         return torch.float32 if self.name == 'strict' else torch.bfloat16
 
     def conv_impl(self, ci: int, co: int, stride: int = 1) -> int:
+        """1 = tcgen05 implicit GEMM (forward, and dgrad with ci/co swapped), 0 = fp32 SIMT."""
         if self.name == 'fast' and ci % 64 == 0 and co % 64 == 0 and stride == 1:
+            return 1
+        return 0
+
+    def wgrad_impl(self, ci: int, co: int, stride: int = 1) -> int:
+        if self.name == 'fast' and ci % 64 == 0 and co % 128 == 0 and stride == 1:
             return 1
         return 0
 
@@ -189,9 +195,10 @@ class Conv2dFn(torch.autograd.Function):
             ddt = in_dtype if (dimpl == 0 or in_dtype == torch.float32) else gdt
             dx = _conv_fwd_raw(dimpl, dyd, wd, None, None, ddt, co, ci, kh, kw, kh - 1 - pad, 1, ACT_NONE, 0.0, 1.0)
         if ctx.needs_input_grad[1]:
-            dyw = as_nhwc(dy, torch.bfloat16) if impl == 1 else dy
+            wimpl = prec.wgrad_impl(ci, co, stride) if x.dtype == torch.bfloat16 else 0
+            dyw = as_nhwc(dy, torch.bfloat16) if wimpl == 1 else dy
             dwp = torch.zeros(kh * kw * ci * co, dtype=torch.float32, device=x.device)
-            call('vqb_conv2d_wgrad', impl, ptr(x), dt(x), ptr(dyw), dt(dyw), ptr(dwp), n, h, w, ci, co, kh, kw, pad, stride,
+            call('vqb_conv2d_wgrad', wimpl, ptr(x), dt(x), ptr(dyw), dt(dyw), ptr(dwp), n, h, w, ci, co, kh, kw, pad, stride,
                  stream())
             dw = torch.empty_like(weight, dtype=torch.float32)
             call('vqb_unpack_conv_wgrad', ptr(dwp), ptr(dw), co, ci, kh, kw, w_scale, stream())
