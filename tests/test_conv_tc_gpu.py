@@ -41,6 +41,7 @@ CASES = [
     (2, 12, 20, 64, 128, 3, False, False, 0),       # H, W not powers of two: partially out-of-bounds boxes
     (1, 64, 64, 128, 128, 3, False, False, 0),
     (2, 16, 16, 512, 512, 3, False, False, 0),      # two Co tiles, 72 k-steps (pipeline wrap-around)
+    (2, 32, 32, 128, 3, 3, True, False, 1),         # narrow head (decoder.conv_out): UMMA N=16, tanh epilogue
 ]
 
 
@@ -52,10 +53,12 @@ def test_conv_tc_forward_fp32_out(V, n, h, w, ci, co, k, bias, res, act):
     b = torch.randn(co) if bias else None
     r = torch.randn(n, co, h, w) if res else None
     y = F.conv2d(x, wt, b, padding=k // 2)
+    if act == 1:
+        y = torch.tanh(y)
     if res:
         y = y + r
     yg = V.ops.conv2d(cl(x).bfloat16(), wt.cuda(), b.cuda() if bias else None, cl(r) if res else None, pad=k // 2,
-                      out_dtype=torch.float32)
+                      act=act, out_dtype=torch.float32)
     assert yg.dtype == torch.float32
     assert C.rel_err(yg, y) < 1e-4
     assert C.max_rel(yg, y) < 5e-3

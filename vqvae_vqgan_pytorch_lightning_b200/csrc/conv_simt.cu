@@ -294,6 +294,68 @@ conv_wgrad_simt_kernel(const TIn* __restrict__ x, const TG* __restrict__ dy, flo
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// weight gradient of a narrow head (Co <= 4, stride 1, 3x3): decoder.conv_out 128 -> 3 at full resolution.
+// The GEMM view (N = 3) wastes a 128-wide tile; here thread <-> input channel keeps the 9 x Co partial sums in
+// registers, streams x once (coalesced over channels) and reads the 3x3 window of dy from a zero-padded
+// shared-memory copy of three dy rows (broadcast reads).  HBM-bound: x is read exactly once.
+// ---------------------------------------------------------------------------------------------------
+template <typename TIn, typename TG>
+__global__ void __launch_bounds__(128)
+conv_wgrad_narrow_kernel(const TIn* __restrict__ x, const TG* __restrict__ dy, float* __restrict__ dwp, int N, int H, int W,
+                         int Ci, int Co) {
+    extern __shared__ float4 dys[];                 // [3][W + 2] (co padded to 4), zero borders
+    const int ci = blockIdx.y * 128 + threadIdx.x;
+    const bool ci_ok = ci < Ci;
+    float acc[9][4];
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[t][c] = 0.f;
+    const int WP = W + 2;
+    for (int row = blockIdx.x; row < N * H; row += gridDim.x) {
+        const int n = row / H, h = row - n * H;
+        __syncthreads();
+        for (int i = threadIdx.x; i < 3 * WP; i += 128) {
+            int r = i / WP, wp = i - r * WP;
+            int hh = h + 1 - r;                      // tap kh pairs input row h with output row h - kh + 1  (kh = r)
+            int ww = wp - 1;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
+                const TG* src = dy + (((int64_t)n * H + hh) * W + ww) * Co;
+                v.x = ld1(src);
+                if (Co > 1) v.y = ld1(src + 1);
+                if (Co > 2) v.z = ld1(src + 2);
+                if (Co > 3) v.w = ld1(src + 3);
+            }
+            dys[i] = v;
+        }
+        __syncthreads();
+        if (ci_ok) {
+            const TIn* xr = x + (((int64_t)n * H + h) * W) * Ci + ci;
+            for (int w = 0; w < W; ++w) {
+                const float xv = ld1(xr + (int64_t)w * Ci);
+#pragma unroll
+                for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                    for (int kw = 0; kw < 3; ++kw) {
+                        // input pixel (h, w) meets output pixel (h - kh + 1, w - kw + 1): padded column index w - kw + 2
+                        const float4 g = dys[kh * WP + (w - kw + 2)];
+                        acc[kh * 3 + kw][0] = fmaf(xv, g.x, acc[kh * 3 + kw][0]);
+                        acc[kh * 3 + kw][1] = fmaf(xv, g.y, acc[kh * 3 + kw][1]);
+                        acc[kh * 3 + kw][2] = fmaf(xv, g.z, acc[kh * 3 + kw][2]);
+                        acc[kh * 3 + kw][3] = fmaf(xv, g.w, acc[kh * 3 + kw][3]);
+                    }
+            }
+        }
+    }
+    if (ci_ok) {
+#pragma unroll
+        for (int t = 0; t < 9; ++t)
+            for (int c = 0; c < Co; ++c) atomicAdd(dwp + ((int64_t)t * Ci + ci) * Co + c, acc[t][c]);
+    }
+}
+
 inline int make_geom(ConvGeom& g, int N, int H, int W, int Ci, int Co, int KH, int KW, int pad, int stride) {
     if (!(N > 0 && H > 0 && W > 0 && Ci > 0 && Co > 0 && KH > 0 && KW > 0 && pad >= 0 && stride >= 1)) {
         vqb_set_error("conv2d: bad geometry N=%d H=%d W=%d Ci=%d Co=%d KH=%d KW=%d pad=%d stride=%d", N, H, W, Ci, Co, KH, KW, pad, stride);
@@ -326,6 +388,15 @@ int vqb_conv2d_wgrad_simt(const void* x, int x_dtype, const void* dy, int dy_dty
                           int Co, int KH, int KW, int pad, int stride, cudaStream_t stream) {
     ConvGeom g;
     int rc = make_geom(g, N, H, W, Ci, Co, KH, KW, pad, stride); if (rc) return rc;
+    if (Co <= 4 && KH == 3 && KW == 3 && pad == 1 && stride == 1 && (size_t)3 * (W + 2) * 16 <= 48 * 1024) {
+        int rows = N * H;
+        dim3 grid(rows < 148 * 8 ? rows : 148 * 8, (Ci + 127) / 128);
+        size_t sm = (size_t)3 * (W + 2) * sizeof(float4);
+        VQB_DISPATCH_1(x_dtype, TIn, VQB_DISPATCH_1(dy_dtype, TG,
+            (conv_wgrad_narrow_kernel<TIn, TG><<<grid, 128, sm, stream>>>((const TIn*)x, (const TG*)dy, dwp, N, H, W, Ci, Co));))
+        VQB_CHECK_LAUNCH("conv2d_wgrad_narrow");
+        return VQB_OK;
+    }
     int gm = (g.K + BM - 1) / BM, gn = (Co + BN - 1) / BN;
     // split the pixel reduction so that the grid is ~4 waves of 148 SMs x 2 resident CTAs
     int64_t want = (int64_t)148 * 2 * 4;

@@ -95,12 +95,12 @@ __device__ __forceinline__ float act_f(float v, int act, float alpha) {
 
 struct FwdParams {
     int N, H, W, Ci, Co, KH, KW, pad;
-    int tw, th, nb, tiles_w, tiles_h, tiles_n, co_tiles, BN, stages;
+    int tw, th, nb, tiles_w, tiles_h, tiles_n, co_tiles, BN, stages, MT;
     int num_tiles, ksteps, cchunks;
     const float* bias;
     const void* residual;
     void* y;
-    int y_f32, act;
+    int y_f32, act, narrow;
     float alpha, gain;
 };
 
@@ -108,7 +108,8 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const FwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int a_bytes = BM * BK * 2;                 // 16 KB
+    const int a_tile = BM * BK * 2;                  // 16 KB per 128-pixel sub-tile
+    const int a_bytes = p.MT * a_tile;               // MT sub-tiles share one B tile (doubles FLOP per byte staged)
     const int b_bytes = p.BN * BK * 2;
     const int stage_bytes = a_bytes + b_bytes;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
@@ -138,15 +139,21 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 int ct = tile % p.co_tiles; int pt = tile / p.co_tiles;
-                int twi = pt % p.tiles_w; int t2 = pt / p.tiles_w; int thi = t2 % p.tiles_h; int tni = t2 / p.tiles_h;
-                int w0 = twi * p.tw, h0 = thi * p.th, n0 = tni * p.nb, co0 = ct * p.BN;
+                int w0[2], h0[2], n0[2];
+                for (int m = 0; m < p.MT; ++m) {          // sub-tiles past the end decode to n0 >= N: TMA zero-fills them
+                    int q = pt * p.MT + m;
+                    int twi = q % p.tiles_w; int t2 = q / p.tiles_w; int thi = t2 % p.tiles_h; int tni = t2 / p.tiles_h;
+                    w0[m] = twi * p.tw; h0[m] = thi * p.th; n0[m] = tni * p.nb;
+                }
+                const int co0 = ct * p.BN;
                 for (int tap = 0; tap < p.KH * p.KW; ++tap) {
                     int kh = tap / p.KW, kw = tap - kh * p.KW;
                     for (int cc = 0; cc < p.cchunks; ++cc) {
                         ptx::mbar_wait(&empty[stage], phase ^ 1);
                         uint8_t* sa = smem + (size_t)stage * stage_bytes;
                         ptx::mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
-                        ptx::tma_load_4d(sa, &tmA, &full[stage], cc * BK, w0 + kw - p.pad, h0 + kh - p.pad, n0);
+                        for (int m = 0; m < p.MT; ++m)
+                            ptx::tma_load_4d(sa + m * a_tile, &tmA, &full[stage], cc * BK, w0[m] + kw - p.pad, h0[m] + kh - p.pad, n0[m]);
                         ptx::tma_load_2d(sa + a_bytes, &tmB, &full[stage], tap * p.Ci + cc * BK, co0);
                         if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     }
@@ -162,17 +169,19 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 ptx::mbar_wait(&tempty[as], aphase ^ 1);
                 ptx::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.BN);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.MT * p.BN);
                 for (int ks = 0; ks < p.ksteps; ++ks) {
                     ptx::mbar_wait(&full[stage], phase);
                     ptx::tc_fence_after();
                     const uint32_t sa = ptx::smem_u32(smem + (size_t)stage * stage_bytes);
-                    const uint64_t adesc = ptx::umma_smem_desc(sa, 0, 1024);
                     const uint64_t bdesc = ptx::umma_smem_desc(sa + a_bytes, 0, 1024);
+                    for (int m = 0; m < p.MT; ++m) {
+                        const uint64_t adesc = ptx::umma_smem_desc(sa + m * a_tile, 0, 1024);
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k)
-                        ptx::umma_bf16(d_tmem, adesc + (uint64_t)(k * UMMA_K * 2 / 16), bdesc + (uint64_t)(k * UMMA_K * 2 / 16), idesc,
-                                       (ks | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < BK / UMMA_K; ++k)
+                            ptx::umma_bf16(d_tmem + (uint32_t)(m * p.BN), adesc + (uint64_t)(k * UMMA_K * 2 / 16),
+                                           bdesc + (uint64_t)(k * UMMA_K * 2 / 16), idesc, (ks | k) != 0 ? 1u : 0u);
+                    }
                     ptx::umma_commit(&empty[stage]);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
@@ -187,20 +196,40 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         int as = 0; uint32_t aphase = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             int ct = tile % p.co_tiles; int pt = tile / p.co_tiles;
-            int twi = pt % p.tiles_w; int t2 = pt / p.tiles_w; int thi = t2 % p.tiles_h; int tni = t2 / p.tiles_h;
+            const int co0 = ct * p.BN;
+            ptx::mbar_wait(&tfull[as], aphase);
+            ptx::tc_fence_after();
+            for (int m = 0; m < p.MT; ++m) {
+            int q = pt * p.MT + m;
+            int twi = q % p.tiles_w; int t2 = q / p.tiles_w; int thi = t2 % p.tiles_h; int tni = t2 / p.tiles_h;
             int wi = row % p.tw; int r2 = row / p.tw; int hi = r2 % p.th; int ni = r2 / p.th;
             int w = twi * p.tw + wi, h = thi * p.th + hi, n = tni * p.nb + ni;
             const bool valid = (w < p.W) && (h < p.H) && (n < p.N);
             const int64_t pix = ((int64_t)n * p.H + h) * p.W + w;
-            const int co0 = ct * p.BN;
-            ptx::mbar_wait(&tfull[as], aphase);
-            ptx::tc_fence_after();
-            const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * p.BN);
+            const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((as * p.MT + m) * p.BN);
             for (int c = 0; c < p.BN; c += 32) {
                 uint32_t r[32];
                 ptx::tmem_ld32(t_addr + (uint32_t)c, r);
                 ptx::tmem_ld_wait();
-                if (valid) {
+                if (valid && p.narrow) {
+                    // Co < BN (e.g. the 3-channel image head): scalar, masked stores
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {             // static register indices (narrow heads have BN = 16)
+                        if (co0 + c + j < p.Co) {
+                            float t = __uint_as_float(r[j]);
+                            if (p.bias) t += __ldg(p.bias + co0 + c + j);
+                            t = act_f(t, p.act, p.alpha) * p.gain;
+                            const int64_t off = pix * p.Co + co0 + c + j;
+                            if (p.y_f32) {
+                                if (p.residual) t += reinterpret_cast<const float*>(p.residual)[off];
+                                reinterpret_cast<float*>(p.y)[off] = t;
+                            } else {
+                                if (p.residual) t += __bfloat162float(reinterpret_cast<const bf16*>(p.residual)[off]);
+                                reinterpret_cast<bf16*>(p.y)[off] = __float2bfloat16_rn(t);
+                            }
+                        }
+                    }
+                } else if (valid) {
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
@@ -238,6 +267,7 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     }
                 }
             }
+            }   // m
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tempty[as]);
@@ -375,19 +405,23 @@ int vqb_conv2d_fwd_tc(const void* x, const void* wp, const float* bias, const vo
                       int H, int W, int Ci, int Co, int KH, int KW, int pad, int act, float alpha, float gain,
                       cudaStream_t stream) {
     VQB_CHECK_ARG(N > 0 && H > 0 && W > 0 && KH > 0 && KW > 0 && pad >= 0, "conv2d_fwd(tcgen05): bad geometry");
-    VQB_CHECK_ARG(Ci % 64 == 0 && Co % 64 == 0, "conv2d_fwd(tcgen05): Ci and Co must be multiples of 64 (got %d, %d)", Ci, Co);
+    VQB_CHECK_ARG(Ci % 64 == 0 && (Co % 64 == 0 || Co <= 16), "conv2d_fwd(tcgen05): need Ci %% 64 == 0 and (Co %% 64 == 0 or Co <= 16) (got %d, %d)", Ci, Co);
     VQB_CHECK_ARG(H + 2 * pad - KH + 1 == H && W + 2 * pad - KW + 1 == W, "conv2d_fwd(tcgen05): only 'same' convolutions");
     VQB_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)wp & 15) == 0 && ((uintptr_t)y & 15) == 0, "conv2d_fwd(tcgen05): unaligned pointer");
     FwdParams p;
     p.N = N; p.H = H; p.W = W; p.Ci = Ci; p.Co = Co; p.KH = KH; p.KW = KW; p.pad = pad;
     pick_tile(BM, H, W, p.tw, p.th, p.nb);
     p.tiles_w = (W + p.tw - 1) / p.tw; p.tiles_h = (H + p.th - 1) / p.th; p.tiles_n = (N + p.nb - 1) / p.nb;
-    p.BN = (Co % 256 == 0) ? 256 : ((Co % 128 == 0) ? 128 : 64);
-    p.co_tiles = Co / p.BN;
+    p.narrow = (Co % 64 != 0);
+    // narrow heads: UMMA N = 16, the weight box rows beyond Co are zero-filled by TMA
+    p.BN = p.narrow ? 16 : ((Co % 256 == 0) ? 256 : ((Co % 128 == 0) ? 128 : 64));
+    p.co_tiles = p.narrow ? 1 : Co / p.BN;
     p.cchunks = Ci / BK;
     p.ksteps = KH * KW * p.cchunks;
-    p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.co_tiles;
-    const int stage_bytes = BM * BK * 2 + p.BN * BK * 2;
+    const int ptiles = p.tiles_w * p.tiles_h * p.tiles_n;
+    p.MT = (p.BN <= 128 && ptiles >= 2 * sm_count()) ? 2 : 1;     // 2 x 128 pixels per CTA tile when the accumulators fit TMEM
+    p.num_tiles = ((ptiles + p.MT - 1) / p.MT) * p.co_tiles;
+    const int stage_bytes = p.MT * BM * BK * 2 + p.BN * BK * 2;
     p.stages = (SMEM_LIMIT - 2048) / stage_bytes; if (p.stages > 8) p.stages = 8;
     p.bias = bias; p.residual = residual; p.y = y; p.y_f32 = (y_dtype == VQB_F32); p.act = act; p.alpha = alpha; p.gain = gain;
     CUtensorMap tmA, tmB;

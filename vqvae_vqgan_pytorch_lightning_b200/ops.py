@@ -35,7 +35,7 @@ class Precision:
 
     def conv_impl(self, ci: int, co: int, stride: int = 1) -> int:
         """1 = tcgen05 implicit GEMM (forward, and dgrad with ci/co swapped), 0 = fp32 SIMT."""
-        if self.name == 'fast' and ci % 64 == 0 and co % 64 == 0 and stride == 1:
+        if self.name == 'fast' and ci % 64 == 0 and (co % 64 == 0 or co <= 16) and stride == 1:
             return 1
         return 0
 
