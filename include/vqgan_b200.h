@@ -79,6 +79,9 @@ int vqb_conv2d_fwd(int impl, const void* x, int x_dtype, const void* wp, const f
  * dwp must be zero-filled by the caller (split-K partial sums are accumulated with atomics). */
 int vqb_conv2d_wgrad(int impl, const void* x, int x_dtype, const void* dy, int dy_dtype, float* dwp,
                      int N, int H, int W, int Ci, int Co, int KH, int KW, int pad, int stride, void* stream);
+/* Test / tuning hook for the tcgen05 forward kernel: 0 = generic per-tap TMA loads only, 1 = 3x3 halo reuse (default),
+ * 2-4 = descriptor-semantics probes (see csrc/conv_tc.cu); -1 = follow the VQB_HALO_MODE environment variable. */
+void vqb_set_halo_mode(int mode);
 /* column sums: out[c] (fp32, caller zero-fills) += sum_p a[p][c]; used for bias gradients */
 int vqb_colsum(const void* a, int a_dtype, float* out, int64_t P, int C, void* stream);
 

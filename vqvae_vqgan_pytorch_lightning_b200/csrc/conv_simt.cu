@@ -352,7 +352,121 @@ conv_wgrad_narrow_kernel(const TIn* __restrict__ x, const TG* __restrict__ dy, f
     if (ci_ok) {
 #pragma unroll
         for (int t = 0; t < 9; ++t)
-            for (int c = 0; c < Co; ++c) atomicAdd(dwp + ((int64_t)t * Ci + ci) * Co + c, acc[t][c]);
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (c < Co) atomicAdd(dwp + ((int64_t)t * Ci + ci) * Co + c, acc[t][c]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// narrow INPUT (Ci <= 4, 3x3, stride 1): encoder.conv_in 3 -> 128 and the dgrad of decoder.conv_out.
+// thread <-> output channel; the 9 x Ci weights of that channel live in registers; three zero-padded input rows
+// are staged in shared memory and read as broadcasts.  HBM-bound: y is written once, x read once.
+// ---------------------------------------------------------------------------------------------------
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(128)
+conv_fwd_narrow_ci_kernel(const TIn* __restrict__ x, const float* __restrict__ wp, const float* __restrict__ bias,
+                          TOut* __restrict__ y, int N, int H, int W, int Ci, int Co) {
+    extern __shared__ float4 xs[];                  // [3][W + 2]
+    const int co = blockIdx.y * 128 + threadIdx.x;
+    const bool ok = co < Co;
+    float wr[9][4];
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) wr[t][c] = (ok && c < Ci) ? wp[((int64_t)t * Ci + c) * Co + co] : 0.f;
+    const float b = (ok && bias) ? bias[co] : 0.f;
+    const int WP = W + 2;
+    for (int row = blockIdx.x; row < N * H; row += gridDim.x) {
+        const int n = row / H, h = row - n * H;
+        __syncthreads();
+        for (int i = threadIdx.x; i < 3 * WP; i += 128) {
+            int r = i / WP, wp_ = i - r * WP;
+            int hh = h + r - 1, ww = wp_ - 1;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
+                const TIn* src = x + (((int64_t)n * H + hh) * W + ww) * Ci;
+                v.x = ld1(src);
+                if (Ci > 1) v.y = ld1(src + 1);
+                if (Ci > 2) v.z = ld1(src + 2);
+                if (Ci > 3) v.w = ld1(src + 3);
+            }
+            xs[i] = v;
+        }
+        __syncthreads();
+        if (ok) {
+            TOut* yr = y + (((int64_t)n * H + h) * W) * Co + co;
+            for (int w = 0; w < W; ++w) {
+                float acc = b;
+#pragma unroll
+                for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                    for (int kw = 0; kw < 3; ++kw) {
+                        const float4 v = xs[kh * WP + w + kw];
+                        acc = fmaf(v.x, wr[kh * 3 + kw][0], acc);
+                        acc = fmaf(v.y, wr[kh * 3 + kw][1], acc);
+                        acc = fmaf(v.z, wr[kh * 3 + kw][2], acc);
+                        acc = fmaf(v.w, wr[kh * 3 + kw][3], acc);
+                    }
+                st1(yr + (int64_t)w * Co, acc);
+            }
+        }
+    }
+}
+
+template <typename TIn, typename TG>
+__global__ void __launch_bounds__(128)
+conv_wgrad_narrow_ci_kernel(const TIn* __restrict__ x, const TG* __restrict__ dy, float* __restrict__ dwp, int N, int H, int W,
+                            int Ci, int Co) {
+    extern __shared__ float4 xs[];                  // [3][W + 2]
+    const int co = blockIdx.y * 128 + threadIdx.x;
+    const bool ok = co < Co;
+    float acc[9][4];
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[t][c] = 0.f;
+    const int WP = W + 2;
+    for (int row = blockIdx.x; row < N * H; row += gridDim.x) {
+        const int n = row / H, h = row - n * H;
+        __syncthreads();
+        for (int i = threadIdx.x; i < 3 * WP; i += 128) {
+            int r = i / WP, wp_ = i - r * WP;
+            int hh = h + r - 1, ww = wp_ - 1;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
+                const TIn* src = x + (((int64_t)n * H + hh) * W + ww) * Ci;
+                v.x = ld1(src);
+                if (Ci > 1) v.y = ld1(src + 1);
+                if (Ci > 2) v.z = ld1(src + 2);
+                if (Ci > 3) v.w = ld1(src + 3);
+            }
+            xs[i] = v;
+        }
+        __syncthreads();
+        if (ok) {
+            const TG* gr = dy + (((int64_t)n * H + h) * W) * Co + co;
+            for (int w = 0; w < W; ++w) {
+                const float g = ld1(gr + (int64_t)w * Co);
+#pragma unroll
+                for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                    for (int kw = 0; kw < 3; ++kw) {
+                        const float4 v = xs[kh * WP + w + kw];
+                        acc[kh * 3 + kw][0] = fmaf(v.x, g, acc[kh * 3 + kw][0]);
+                        acc[kh * 3 + kw][1] = fmaf(v.y, g, acc[kh * 3 + kw][1]);
+                        acc[kh * 3 + kw][2] = fmaf(v.z, g, acc[kh * 3 + kw][2]);
+                        acc[kh * 3 + kw][3] = fmaf(v.w, g, acc[kh * 3 + kw][3]);
+                    }
+            }
+        }
+    }
+    if (ok) {
+#pragma unroll
+        for (int t = 0; t < 9; ++t)
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (c < Ci) atomicAdd(dwp + ((int64_t)t * Ci + c) * Co + co, acc[t][c]);
     }
 }
 
@@ -377,6 +491,16 @@ int vqb_conv2d_fwd_simt(const void* x, int x_dtype, const float* wp, const float
                         float alpha, float gain, cudaStream_t stream) {
     ConvGeom g;
     int rc = make_geom(g, N, H, W, Ci, Co, KH, KW, pad, stride); if (rc) return rc;
+    if (Ci <= 4 && KH == 3 && KW == 3 && pad == 1 && stride == 1 && act == VQB_ACT_NONE && gain == 1.0f && !residual &&
+        (size_t)3 * (W + 2) * 16 <= 48 * 1024) {
+        int rows = N * H;
+        dim3 ngrid(rows < 148 * 8 ? rows : 148 * 8, (Co + 127) / 128);
+        size_t sm = (size_t)3 * (W + 2) * sizeof(float4);
+        VQB_DISPATCH_1(x_dtype, TIn, VQB_DISPATCH_1(y_dtype, TOut,
+            (conv_fwd_narrow_ci_kernel<TIn, TOut><<<ngrid, 128, sm, stream>>>((const TIn*)x, wp, bias, (TOut*)y, N, H, W, Ci, Co));))
+        VQB_CHECK_LAUNCH("conv2d_fwd_narrow_ci");
+        return VQB_OK;
+    }
     dim3 grid((unsigned)ceil_div64(g.M, BM), (unsigned)((Co + BN - 1) / BN));
     VQB_DISPATCH_1(x_dtype, TIn, VQB_DISPATCH_1(y_dtype, TOut,
         (conv_fwd_simt_kernel<TIn, TOut><<<grid, 256, 0, stream>>>((const TIn*)x, wp, bias, (const TOut*)residual, (TOut*)y, g, act, alpha, gain));))
@@ -395,6 +519,15 @@ int vqb_conv2d_wgrad_simt(const void* x, int x_dtype, const void* dy, int dy_dty
         VQB_DISPATCH_1(x_dtype, TIn, VQB_DISPATCH_1(dy_dtype, TG,
             (conv_wgrad_narrow_kernel<TIn, TG><<<grid, 128, sm, stream>>>((const TIn*)x, (const TG*)dy, dwp, N, H, W, Ci, Co));))
         VQB_CHECK_LAUNCH("conv2d_wgrad_narrow");
+        return VQB_OK;
+    }
+    if (Ci <= 4 && KH == 3 && KW == 3 && pad == 1 && stride == 1 && (size_t)3 * (W + 2) * 16 <= 48 * 1024) {
+        int rows = N * H;
+        dim3 grid(rows < 148 * 8 ? rows : 148 * 8, (Co + 127) / 128);
+        size_t sm = (size_t)3 * (W + 2) * sizeof(float4);
+        VQB_DISPATCH_1(x_dtype, TIn, VQB_DISPATCH_1(dy_dtype, TG,
+            (conv_wgrad_narrow_ci_kernel<TIn, TG><<<grid, 128, sm, stream>>>((const TIn*)x, (const TG*)dy, dwp, N, H, W, Ci, Co));))
+        VQB_CHECK_LAUNCH("conv2d_wgrad_narrow_ci");
         return VQB_OK;
     }
     int gm = (g.K + BM - 1) / BM, gn = (Co + BN - 1) / BN;

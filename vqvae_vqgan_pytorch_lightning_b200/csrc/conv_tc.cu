@@ -1,14 +1,18 @@
 // tcgen05 / TMA implicit-GEMM convolution for sm_100a (bf16 operands, fp32 accumulation in TMEM).
 //
-// Forward / dgrad  (conv_fwd_tc_kernel, persistent, warp-specialised):
-//   D[128 pixels][BN co] += A[128 pixels][64 ci] * B[BN co][64 ci]^T   for every (tap, ci-chunk)
-//   * A is NOT materialised (no im2col): one 4-D TMA box {64 ch, tw, th, nb} of the NHWC activation at spatial offset
-//     (kh-pad, kw-pad) lands in shared memory as a K-major SWIZZLE_128B tile; out-of-image elements are zero-filled by
-//     the TMA unit, which IS the convolution's zero padding.
-//   * B is a 2-D TMA box of the packed weight [Co][(kh,kw,ci)].
-//   * warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread tcgen05.mma issuer, warps 2..5 = epilogue
-//     (tcgen05.ld -> bias / activation / residual -> NHWC global stores).  The fp32 accumulator is double-buffered in
-//     TMEM (2 x BN columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Forward / dgrad, two kernels sharing one epilogue:
+//   conv_fwd_tc_kernel       generic (any KHxKW 'same' conv, any spatial size): per (tap, 64-channel chunk) one 4-D TMA box
+//                            {64 ch, tw, th, nb} of the NHWC activation at offset (kh-pad, kw-pad) is a K-major
+//                            SWIZZLE_128B A tile; out-of-image elements are zero-filled by TMA (= the conv padding).
+//   conv_fwd_tc_halo_kernel  3x3 convs on >= 16x8 images: ONE halo box {64 ch, 10, 18} per channel chunk serves all nine
+//                            taps -- the A operand of tap (kh,kw) is the same shared-memory tile addressed through a UMMA
+//                            descriptor whose start is shifted by (kh*pitch + kw) rows and whose 8-row-group stride (SBO)
+//                            is the halo pitch.  L2->SMEM traffic for A drops ~6x; profiling showed the generic kernel is
+//                            bound by exactly that traffic (profiles/).
+//   Both: D[128 pixels][BN co] (+)= A * B^T with B = packed weight [Co][(kh,kw,ci)] via 2-D TMA; persistent CTAs;
+//   warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread tcgen05.mma issuer, warps 2..5 = epilogue
+//   (tcgen05.ld -> bias / activation / residual -> NHWC stores); fp32 accumulators double-buffered in TMEM so the
+//   epilogue of tile i overlaps the MMAs of tile i+1; MT = 2 pixel sub-tiles share each B tile when BN <= 128.
 //
 // Weight gradient (conv_wgrad_tc_kernel):
 //   dW[tap][ci][co] = sum_pixels x_shift[pix][ci] * dy[pix][co]: the reduction runs over pixels, so both operands are
@@ -20,6 +24,7 @@
 #include "common.cuh"
 #include "ptx.cuh"
 #include <mutex>
+#include <stdlib.h>
 
 namespace {
 
@@ -46,13 +51,13 @@ EncodeTiledFn get_encode() {
     return fn;
 }
 
-// NHWC bf16 activation as a 4-D tensor {C, W, H, N} with box {64, tw, th, nb}
-int make_act_map(CUtensorMap* m, const void* base, int N, int H, int W, int C, int tw, int th, int nb) {
+// NHWC bf16 activation as a 4-D tensor {C, W, H, N} with box {64, bw, bh, bn}
+int make_act_map(CUtensorMap* m, const void* base, int N, int H, int W, int C, int bw, int bh, int bn) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { vqb_set_error("cuTensorMapEncodeTiled unavailable"); return VQB_ERR_CUDA; }
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)nb};
+    cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -97,6 +102,8 @@ struct FwdParams {
     int N, H, W, Ci, Co, KH, KW, pad;
     int tw, th, nb, tiles_w, tiles_h, tiles_n, co_tiles, BN, stages, MT;
     int num_tiles, ksteps, cchunks;
+    // halo kernel only
+    int pitch, bo_mode, a_tile_bytes, a_stages, b_stages;
     const float* bias;
     const void* residual;
     void* y;
@@ -104,6 +111,106 @@ struct FwdParams {
     float alpha, gain;
 };
 
+// ---- shared epilogue: 32 accumulator columns of one pixel row -> bias / act / residual -> NHWC store ---------------
+__device__ __forceinline__ void epilogue_chunk(const FwdParams& p, const uint32_t (&r)[32], bool valid, int64_t pix, int co0, int c) {
+    if (!valid) return;
+    if (p.narrow) {
+        // Co < BN (e.g. the 3-channel image head): scalar, masked stores; static register indices
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            if (co0 + c + j < p.Co) {
+                float t = __uint_as_float(r[j]);
+                if (p.bias) t += __ldg(p.bias + co0 + c + j);
+                t = act_f(t, p.act, p.alpha) * p.gain;
+                const int64_t off = pix * p.Co + co0 + c + j;
+                if (p.y_f32) {
+                    if (p.residual) t += reinterpret_cast<const float*>(p.residual)[off];
+                    reinterpret_cast<float*>(p.y)[off] = t;
+                } else {
+                    if (p.residual) t += __bfloat162float(reinterpret_cast<const bf16*>(p.residual)[off]);
+                    reinterpret_cast<bf16*>(p.y)[off] = __float2bfloat16_rn(t);
+                }
+            }
+        }
+        return;
+    }
+    float v[32];
+    if (p.bias || p.act != VQB_ACT_NONE || p.gain != 1.0f) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            float t = __uint_as_float(r[j]);
+            if (p.bias) t += __ldg(p.bias + co0 + c + j);
+            v[j] = act_f(t, p.act, p.alpha) * p.gain;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    }
+    const int64_t off = pix * p.Co + co0 + c;
+    if (p.y_f32) {
+        float* yo = reinterpret_cast<float*>(p.y) + off;
+        const float* ro = p.residual ? reinterpret_cast<const float*>(p.residual) + off : nullptr;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            if (ro) { float4 q = *reinterpret_cast<const float4*>(ro + j); o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w; }
+            *reinterpret_cast<float4*>(yo + j) = o;
+        }
+    } else {
+        bf16* yo = reinterpret_cast<bf16*>(p.y) + off;
+        const bf16* ro = p.residual ? reinterpret_cast<const bf16*>(p.residual) + off : nullptr;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+            if (ro) {
+                uint4 q = *reinterpret_cast<const uint4*>(ro + j);
+                const __nv_bfloat162* qb = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { float2 f = __bfloat1622float2(qb[u]); v[j + 2 * u] += f.x; v[j + 2 * u + 1] += f.y; }
+            }
+            uint4 o;
+            __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) ob[u] = __floats2bfloat162_rn(v[j + 2 * u], v[j + 2 * u + 1]);
+            *reinterpret_cast<uint4*>(yo + j) = o;
+        }
+    }
+}
+
+// epilogue warps of both forward kernels: drain the MT sub-tile accumulators of every tile this CTA owns
+__device__ __forceinline__ void epilogue_loop(const FwdParams& p, uint32_t tmem_base, uint64_t* tfull, uint64_t* tempty, int warp, int lane) {
+    const int quarter = warp & 3;                    // TMEM lane quarter this warp may read
+    const int row = quarter * 32 + lane;
+    const int wi = row % p.tw, r2 = row / p.tw, hi = r2 % p.th, ni = r2 / p.th;
+    int as = 0; uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int ct = tile % p.co_tiles, pt = tile / p.co_tiles;
+        const int co0 = ct * p.BN;
+        ptx::mbar_wait(&tfull[as], aphase);
+        ptx::tc_fence_after();
+        for (int m = 0; m < p.MT; ++m) {
+            const int q = pt * p.MT + m;
+            const int twi = q % p.tiles_w, t2 = q / p.tiles_w, thi = t2 % p.tiles_h, tni = t2 / p.tiles_h;
+            const int w = twi * p.tw + wi, h = thi * p.th + hi, n = tni * p.nb + ni;
+            const bool valid = (w < p.W) && (h < p.H) && (n < p.N);
+            const int64_t pix = ((int64_t)n * p.H + h) * p.W + w;
+            const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((as * p.MT + m) * p.BN);
+            for (int c = 0; c < p.BN; c += 32) {
+                uint32_t r[32];
+                ptx::tmem_ld32(t_addr + (uint32_t)c, r);
+                ptx::tmem_ld_wait();
+                epilogue_chunk(p, r, valid, pix, co0, c);
+            }
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tempty[as]);
+        if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// generic forward kernel
+// ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const FwdParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -190,89 +297,119 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             }
         }
     } else {
-        // ================= epilogue (warps 2..5; TMEM lane quarter = warp % 4) =================
-        const int quarter = warp & 3;
-        const int row = quarter * 32 + lane;
-        int as = 0; uint32_t aphase = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-            int ct = tile % p.co_tiles; int pt = tile / p.co_tiles;
-            const int co0 = ct * p.BN;
-            ptx::mbar_wait(&tfull[as], aphase);
-            ptx::tc_fence_after();
-            for (int m = 0; m < p.MT; ++m) {
-            int q = pt * p.MT + m;
-            int twi = q % p.tiles_w; int t2 = q / p.tiles_w; int thi = t2 % p.tiles_h; int tni = t2 / p.tiles_h;
-            int wi = row % p.tw; int r2 = row / p.tw; int hi = r2 % p.th; int ni = r2 / p.th;
-            int w = twi * p.tw + wi, h = thi * p.th + hi, n = tni * p.nb + ni;
-            const bool valid = (w < p.W) && (h < p.H) && (n < p.N);
-            const int64_t pix = ((int64_t)n * p.H + h) * p.W + w;
-            const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((as * p.MT + m) * p.BN);
-            for (int c = 0; c < p.BN; c += 32) {
-                uint32_t r[32];
-                ptx::tmem_ld32(t_addr + (uint32_t)c, r);
-                ptx::tmem_ld_wait();
-                if (valid && p.narrow) {
-                    // Co < BN (e.g. the 3-channel image head): scalar, masked stores
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {             // static register indices (narrow heads have BN = 16)
-                        if (co0 + c + j < p.Co) {
-                            float t = __uint_as_float(r[j]);
-                            if (p.bias) t += __ldg(p.bias + co0 + c + j);
-                            t = act_f(t, p.act, p.alpha) * p.gain;
-                            const int64_t off = pix * p.Co + co0 + c + j;
-                            if (p.y_f32) {
-                                if (p.residual) t += reinterpret_cast<const float*>(p.residual)[off];
-                                reinterpret_cast<float*>(p.y)[off] = t;
-                            } else {
-                                if (p.residual) t += __bfloat162float(reinterpret_cast<const bf16*>(p.residual)[off]);
-                                reinterpret_cast<bf16*>(p.y)[off] = __float2bfloat16_rn(t);
-                            }
-                        }
-                    }
-                } else if (valid) {
-                    float v[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float t = __uint_as_float(r[j]);
-                        if (p.bias) t += __ldg(p.bias + co0 + c + j);
-                        v[j] = act_f(t, p.act, p.alpha) * p.gain;
-                    }
-                    const int64_t off = pix * p.Co + co0 + c;
-                    if (p.y_f32) {
-                        float* yo = reinterpret_cast<float*>(p.y) + off;
-                        const float* ro = p.residual ? reinterpret_cast<const float*>(p.residual) + off : nullptr;
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                            if (ro) { float4 q = *reinterpret_cast<const float4*>(ro + j); o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w; }
-                            *reinterpret_cast<float4*>(yo + j) = o;
-                        }
-                    } else {
-                        bf16* yo = reinterpret_cast<bf16*>(p.y) + off;
-                        const bf16* ro = p.residual ? reinterpret_cast<const bf16*>(p.residual) + off : nullptr;
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            if (ro) {
-                                uint4 q = *reinterpret_cast<const uint4*>(ro + j);
-                                const __nv_bfloat162* qb = reinterpret_cast<const __nv_bfloat162*>(&q);
-#pragma unroll
-                                for (int u = 0; u < 4; ++u) { float2 f = __bfloat1622float2(qb[u]); v[j + 2 * u] += f.x; v[j + 2 * u + 1] += f.y; }
-                            }
-                            uint4 o;
-                            __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) ob[u] = __floats2bfloat162_rn(v[j + 2 * u], v[j + 2 * u + 1]);
-                            *reinterpret_cast<uint4*>(yo + j) = o;
-                        }
+        epilogue_loop(p, tmem_base, tfull, tempty, warp, lane);
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// 3x3 forward kernel with halo reuse (tw = 8, th = 16): one A load per channel chunk serves nine taps
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NTHREADS, 1)
+conv_fwd_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const FwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int a_tile = p.a_tile_bytes;                              // (th+2) x pitch rows of 128 B, rounded up to 1024
+    const int a_stage = p.MT * a_tile;
+    const int b_stage = p.BN * BK * 2;
+    uint8_t* smemA = smem;
+    uint8_t* smemB = smem + (size_t)p.a_stages * a_stage;
+    uint64_t* fullA = reinterpret_cast<uint64_t*>(smemB + (size_t)p.b_stages * b_stage);
+    uint64_t* emptyA = fullA + p.a_stages;
+    uint64_t* fullB = emptyA + p.a_stages;
+    uint64_t* emptyB = fullB + p.b_stages;
+    uint64_t* tfull = emptyB + p.b_stages;           // [2]
+    uint64_t* tempty = tfull + 2;                    // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t a_box_bytes = (uint32_t)((p.th + 2) * p.pitch * 128);
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmA);
+        ptx::prefetch_tmap(&tmB);
+        for (int i = 0; i < p.a_stages; ++i) { ptx::mbar_init(&fullA[i], 1); ptx::mbar_init(&emptyA[i], 1); }
+        for (int i = 0; i < p.b_stages; ++i) { ptx::mbar_init(&fullB[i], 1); ptx::mbar_init(&emptyB[i], 1); }
+        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull[i], 1); ptx::mbar_init(&tempty[i], 4); }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                int ct = tile % p.co_tiles; int pt = tile / p.co_tiles;
+                int w0[2], h0[2], n0[2];
+                for (int m = 0; m < p.MT; ++m) {
+                    int q = pt * p.MT + m;
+                    int twi = q % p.tiles_w; int t2 = q / p.tiles_w; int thi = t2 % p.tiles_h; int tni = t2 / p.tiles_h;
+                    w0[m] = twi * p.tw; h0[m] = thi * p.th; n0[m] = tni;
+                }
+                const int co0 = ct * p.BN;
+                for (int cc = 0; cc < p.cchunks; ++cc) {
+                    ptx::mbar_wait(&emptyA[sa], pa ^ 1);
+                    ptx::mbar_expect_tx(&fullA[sa], a_box_bytes * (uint32_t)p.MT);
+                    for (int m = 0; m < p.MT; ++m)
+                        ptx::tma_load_4d(smemA + (size_t)sa * a_stage + m * a_tile, &tmA, &fullA[sa], cc * BK, w0[m] - 1, h0[m] - 1, n0[m]);
+                    if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
+                    for (int tap = 0; tap < 9; ++tap) {
+                        ptx::mbar_wait(&emptyB[sb], pb ^ 1);
+                        ptx::mbar_expect_tx(&fullB[sb], (uint32_t)b_stage);
+                        ptx::tma_load_2d(smemB + (size_t)sb * b_stage, &tmB, &fullB[sb], tap * p.Ci + cc * BK, co0);
+                        if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
                     }
                 }
             }
-            }   // m
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&tempty[as]);
-            if (++as == 2) { as = 0; aphase ^= 1; }
         }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = ptx::umma_idesc_bf16(BM, p.BN, 0, 0);
+            const uint32_t sbo = (uint32_t)p.pitch * 128u;           // stride between 8-pixel row groups = one halo row
+            int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+            int as = 0; uint32_t aphase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                ptx::mbar_wait(&tempty[as], aphase ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.MT * p.BN);
+                for (int cc = 0; cc < p.cchunks; ++cc) {
+                    ptx::mbar_wait(&fullA[sa], pa);
+                    const uint32_t a_addr = ptx::smem_u32(smemA + (size_t)sa * a_stage);
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const int kh = tap / 3, kw = tap - kh * 3;
+                        ptx::mbar_wait(&fullB[sb], pb);
+                        ptx::tc_fence_after();
+                        const uint64_t bdesc = ptx::umma_smem_desc(ptx::smem_u32(smemB + (size_t)sb * b_stage), 0, 1024);
+                        const uint32_t row_off = (uint32_t)(kh * p.pitch + kw);
+                        for (int m = 0; m < p.MT; ++m) {
+                            uint64_t adesc = ptx::umma_smem_desc(a_addr + (uint32_t)(m * a_tile) + row_off * 128u, 0, sbo);
+                            if (p.bo_mode) adesc |= (uint64_t)(row_off & 7u) << 49;      // matrix base offset field
+#pragma unroll
+                            for (int k = 0; k < BK / UMMA_K; ++k)
+                                ptx::umma_bf16(d_tmem + (uint32_t)(m * p.BN), adesc + (uint64_t)(k * UMMA_K * 2 / 16),
+                                               bdesc + (uint64_t)(k * UMMA_K * 2 / 16), idesc, (cc | tap | k) != 0 ? 1u : 0u);
+                        }
+                        ptx::umma_commit(&emptyB[sb]);
+                        if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
+                    }
+                    ptx::umma_commit(&emptyA[sa]);
+                    if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
+                }
+                ptx::umma_commit(&tfull[as]);
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+        }
+    } else {
+        epilogue_loop(p, tmem_base, tfull, tempty, warp, lane);
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -388,6 +525,123 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_cons
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// 3x3 weight gradient with halo reuse: a CTA owns (128 co) x (CN ci) x (one kernel row kh = three taps) and a range
+// of 8x8-pixel tiles.  Per tile it loads dy [64 px][128 co] once and ONE x halo box {64 ch, 10, 8} per channel block;
+// the B operand of tap kw is that halo addressed with a start offset of kw rows and SBO = halo pitch (MN-major:
+// an 8-row K atom = 8 consecutive pixels along w).  Three accumulators (one per kw) live in TMEM.
+// ---------------------------------------------------------------------------------------------------
+struct WgradHaloParams {
+    int N, H, W, Ci, Co;
+    int tiles_w, tiles_h, CN, co_tiles, ci_tiles, stages;
+    int ptiles_total, ptiles_per_split;
+    float* dwp;
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+conv_wgrad_tc_halo_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX, const WgradHaloParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    constexpr int PITCH = 10;                           // halo row pitch in pixels (8 + 2)
+    constexpr int DY_BLK = 64 * 128;                    // [64 pixels][64 co] = 8 KB
+    constexpr int X_BLK = 8 * PITCH * 128;              // [8 rows][10 cols][64 ci] = 10 KB (multiple of 1024)
+    const int a_bytes = (BM / 64) * DY_BLK;
+    const int b_bytes = (p.CN / 64) * X_BLK;
+    const int stage_bytes = a_bytes + b_bytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+    uint64_t* empty = full + p.stages;
+    uint64_t* tfull = empty + p.stages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // blockIdx.x = ((kh * ci_tiles + cit) * co_tiles + cot), blockIdx.y = pixel split
+    int cot = blockIdx.x % p.co_tiles; int t1 = blockIdx.x / p.co_tiles; int cit = t1 % p.ci_tiles; int kh = t1 / p.ci_tiles;
+    const int co0 = cot * BM, ci0 = cit * p.CN;
+    const int pt_begin = blockIdx.y * p.ptiles_per_split;
+    int pt_end = pt_begin + p.ptiles_per_split; if (pt_end > p.ptiles_total) pt_end = p.ptiles_total;
+    const int nsteps = pt_end - pt_begin;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmDy);
+        ptx::prefetch_tmap(&tmX);
+        for (int i = 0; i < p.stages; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 1); }
+        ptx::mbar_init(tfull, 1);
+        ptx::fence_barrier_init();
+    }
+    uint32_t tcols = 32; while ((int)tcols < 3 * p.CN) tcols <<= 1;
+    if (warp == 1) ptx::tmem_alloc(tmem_slot, tcols);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (nsteps > 0) {
+        if (warp == 0) {
+            if (lane == 0) {
+                int stage = 0; uint32_t phase = 0;
+                for (int pt = pt_begin; pt < pt_end; ++pt) {
+                    int twi = pt % p.tiles_w; int t2 = pt / p.tiles_w; int thi = t2 % p.tiles_h; int n = t2 / p.tiles_h;
+                    int w0 = twi * 8, h0 = thi * 8;
+                    ptx::mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                    ptx::mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
+                    for (int j = 0; j < BM / 64; ++j)
+                        ptx::tma_load_4d(sa + j * DY_BLK, &tmDy, &full[stage], co0 + j * 64, w0, h0, n);
+                    for (int j = 0; j < p.CN / 64; ++j)
+                        ptx::tma_load_4d(sa + a_bytes + j * X_BLK, &tmX, &full[stage], ci0 + j * 64, w0 - 1, h0 + kh - 1, n);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        } else if (warp == 1) {
+            if (lane == 0) {
+                const uint32_t idesc = ptx::umma_idesc_bf16(BM, p.CN, 1, 1);
+                int stage = 0; uint32_t phase = 0;
+                for (int s = 0; s < nsteps; ++s) {
+                    ptx::mbar_wait(&full[stage], phase);
+                    ptx::tc_fence_after();
+                    const uint32_t sa = ptx::smem_u32(smem + (size_t)stage * stage_bytes);
+                    const uint64_t adesc = ptx::umma_smem_desc(sa, (uint32_t)DY_BLK, 1024);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {              // UMMA j: pixel rows 2j, 2j+1 of the 8x8 tile (16 K-rows)
+#pragma unroll
+                        for (int kw = 0; kw < 3; ++kw) {
+                            const uint64_t bdesc = ptx::umma_smem_desc(sa + a_bytes + (uint32_t)((2 * j * PITCH + kw) * 128),
+                                                                       (uint32_t)X_BLK, (uint32_t)(PITCH * 128));
+                            ptx::umma_bf16(tmem_base + (uint32_t)(kw * p.CN), adesc + (uint64_t)(j * 2048 / 16), bdesc, idesc,
+                                           (s | j) != 0 ? 1u : 0u);
+                        }
+                    }
+                    ptx::umma_commit(&empty[stage]);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+                ptx::umma_commit(tfull);
+            }
+        } else {
+            const int quarter = warp & 3;
+            const int co = co0 + quarter * 32 + lane;
+            ptx::mbar_wait(tfull, 0);
+            ptx::tc_fence_after();
+            for (int kw = 0; kw < 3; ++kw) {
+                const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(kw * p.CN);
+                float* out = p.dwp + ((int64_t)(kh * 3 + kw) * p.Ci + ci0) * p.Co + co;
+                for (int c = 0; c < p.CN; c += 32) {
+                    uint32_t r[32];
+                    ptx::tmem_ld32(t_addr + (uint32_t)c, r);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) atomicAdd(out + (int64_t)(c + j) * p.Co, __uint_as_float(r[j]));
+                }
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, tcols);
+    }
+}
+
 int sm_count() {
     static int n = 0;
     if (!n) {
@@ -399,7 +653,24 @@ int sm_count() {
     return n;
 }
 
+// VQB_HALO_MODE: 0 = generic kernel only; 1 = halo pitch 10 (default); 2 = pitch 16; 3 = pitch 16 + base-offset field;
+// 4 = pitch 10 + base-offset field.  (2-4 exist to pin down the descriptor semantics on hardware; see tests.)
+int halo_mode() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("VQB_HALO_MODE");
+        mode = e ? atoi(e) : 1;
+        if (mode < 0 || mode > 4) mode = 1;
+    }
+    return mode;
+}
+
 }  // namespace
+
+// test hook: override the halo mode at run time (-1 = re-read the environment)
+extern "C" void vqb_set_halo_mode(int mode);
+static int g_halo_override = -1;
+extern "C" void vqb_set_halo_mode(int mode) { g_halo_override = mode; }
 
 int vqb_conv2d_fwd_tc(const void* x, const void* wp, const float* bias, const void* residual, void* y, int y_dtype, int N,
                       int H, int W, int Ci, int Co, int KH, int KW, int pad, int act, float alpha, float gain,
@@ -410,23 +681,48 @@ int vqb_conv2d_fwd_tc(const void* x, const void* wp, const float* bias, const vo
     VQB_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)wp & 15) == 0 && ((uintptr_t)y & 15) == 0, "conv2d_fwd(tcgen05): unaligned pointer");
     FwdParams p;
     p.N = N; p.H = H; p.W = W; p.Ci = Ci; p.Co = Co; p.KH = KH; p.KW = KW; p.pad = pad;
-    pick_tile(BM, H, W, p.tw, p.th, p.nb);
-    p.tiles_w = (W + p.tw - 1) / p.tw; p.tiles_h = (H + p.th - 1) / p.th; p.tiles_n = (N + p.nb - 1) / p.nb;
     p.narrow = (Co % 64 != 0);
     // narrow heads: UMMA N = 16, the weight box rows beyond Co are zero-filled by TMA
     p.BN = p.narrow ? 16 : ((Co % 256 == 0) ? 256 : ((Co % 128 == 0) ? 128 : 64));
     p.co_tiles = p.narrow ? 1 : Co / p.BN;
     p.cchunks = Ci / BK;
     p.ksteps = KH * KW * p.cchunks;
+    p.bias = bias; p.residual = residual; p.y = y; p.y_f32 = (y_dtype == VQB_F32); p.act = act; p.alpha = alpha; p.gain = gain;
+    p.pitch = 0; p.bo_mode = 0; p.a_tile_bytes = 0; p.a_stages = 0; p.b_stages = 0;
+    const int mode = g_halo_override >= 0 ? g_halo_override : halo_mode();
+    const bool halo = mode != 0 && KH == 3 && KW == 3 && pad == 1 && H >= 16 && W >= 8;
+    CUtensorMap tmA, tmB;
+    int rc = make_weight_map(&tmB, wp, Co, KH * KW * Ci, p.BN); if (rc) return rc;
+    if (halo) {
+        p.tw = 8; p.th = 16; p.nb = 1;
+        p.tiles_w = (W + 7) / 8; p.tiles_h = (H + 15) / 16; p.tiles_n = N;
+        p.pitch = (mode == 2 || mode == 3) ? 16 : 10;
+        p.bo_mode = (mode == 3 || mode == 4) ? 1 : 0;
+        p.a_tile_bytes = (((p.th + 2) * p.pitch * 128) + 1023) / 1024 * 1024;
+        const int ptiles = p.tiles_w * p.tiles_h * p.tiles_n;
+        p.MT = (p.BN <= 128 && ptiles >= 2 * sm_count()) ? 2 : 1;
+        p.num_tiles = ((ptiles + p.MT - 1) / p.MT) * p.co_tiles;
+        const int a_stage = p.MT * p.a_tile_bytes, b_stage = p.BN * BK * 2;
+        p.a_stages = 2;
+        p.b_stages = (SMEM_LIMIT - 2048 - p.a_stages * a_stage) / b_stage; if (p.b_stages > 12) p.b_stages = 12;
+        VQB_CHECK_ARG(p.b_stages >= 2, "conv2d_fwd(tcgen05 halo): shared memory budget");
+        p.stages = 0;
+        rc = make_act_map(&tmA, x, N, H, W, Ci, p.pitch, p.th + 2, 1); if (rc) return rc;
+        size_t smem = (size_t)p.a_stages * a_stage + (size_t)p.b_stages * b_stage + 1024 + 512;
+        VQB_CUDA(cudaFuncSetAttribute(conv_fwd_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+        conv_fwd_tc_halo_kernel<<<grid, NTHREADS, smem, stream>>>(tmA, tmB, p);
+        VQB_CHECK_LAUNCH("conv2d_fwd_tc_halo");
+        return VQB_OK;
+    }
+    pick_tile(BM, H, W, p.tw, p.th, p.nb);
+    p.tiles_w = (W + p.tw - 1) / p.tw; p.tiles_h = (H + p.th - 1) / p.th; p.tiles_n = (N + p.nb - 1) / p.nb;
     const int ptiles = p.tiles_w * p.tiles_h * p.tiles_n;
     p.MT = (p.BN <= 128 && ptiles >= 2 * sm_count()) ? 2 : 1;     // 2 x 128 pixels per CTA tile when the accumulators fit TMEM
     p.num_tiles = ((ptiles + p.MT - 1) / p.MT) * p.co_tiles;
     const int stage_bytes = p.MT * BM * BK * 2 + p.BN * BK * 2;
     p.stages = (SMEM_LIMIT - 2048) / stage_bytes; if (p.stages > 8) p.stages = 8;
-    p.bias = bias; p.residual = residual; p.y = y; p.y_f32 = (y_dtype == VQB_F32); p.act = act; p.alpha = alpha; p.gain = gain;
-    CUtensorMap tmA, tmB;
-    int rc = make_act_map(&tmA, x, N, H, W, Ci, p.tw, p.th, p.nb); if (rc) return rc;
-    rc = make_weight_map(&tmB, wp, Co, KH * KW * Ci, p.BN); if (rc) return rc;
+    rc = make_act_map(&tmA, x, N, H, W, Ci, p.tw, p.th, p.nb); if (rc) return rc;
     size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256;
     VQB_CUDA(cudaFuncSetAttribute(conv_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
@@ -440,6 +736,34 @@ int vqb_conv2d_wgrad_tc(const void* x, const void* dy, float* dwp, int N, int H,
     VQB_CHECK_ARG(N > 0 && H > 0 && W > 0 && KH > 0 && KW > 0 && pad >= 0, "conv2d_wgrad(tcgen05): bad geometry");
     VQB_CHECK_ARG(Ci % 64 == 0 && Co % 128 == 0, "conv2d_wgrad(tcgen05): need Ci %% 64 == 0 and Co %% 128 == 0 (got %d, %d)", Ci, Co);
     VQB_CHECK_ARG(H + 2 * pad - KH + 1 == H && W + 2 * pad - KW + 1 == W, "conv2d_wgrad(tcgen05): only 'same' convolutions");
+    const int mode = g_halo_override >= 0 ? g_halo_override : halo_mode();
+    if (mode != 0 && KH == 3 && KW == 3 && pad == 1 && H >= 8 && W >= 8) {
+        WgradHaloParams h;
+        h.N = N; h.H = H; h.W = W; h.Ci = Ci; h.Co = Co;
+        h.tiles_w = (W + 7) / 8; h.tiles_h = (H + 7) / 8;
+        h.CN = (Ci % 128 == 0) ? 128 : 64;
+        h.co_tiles = Co / BM; h.ci_tiles = Ci / h.CN;
+        const int stage_bytes = (BM / 64) * 64 * 128 + (h.CN / 64) * 8 * 10 * 128;
+        h.stages = (SMEM_LIMIT - 2048) / stage_bytes; if (h.stages > 8) h.stages = 8;
+        h.ptiles_total = h.tiles_w * h.tiles_h * N;
+        const int out_tiles = 3 * h.ci_tiles * h.co_tiles;
+        int splits = (sm_count() * 2 + out_tiles - 1) / out_tiles;
+        int max_splits = (h.ptiles_total + 7) / 8; if (max_splits < 1) max_splits = 1;
+        if (splits > max_splits) splits = max_splits;
+        if (splits < 1) splits = 1;
+        h.ptiles_per_split = (h.ptiles_total + splits - 1) / splits;
+        splits = (h.ptiles_total + h.ptiles_per_split - 1) / h.ptiles_per_split;
+        h.dwp = dwp;
+        CUtensorMap tmDy, tmX;
+        int rc = make_act_map(&tmDy, dy, N, H, W, Co, 8, 8, 1); if (rc) return rc;
+        rc = make_act_map(&tmX, x, N, H, W, Ci, 10, 8, 1); if (rc) return rc;
+        size_t smem = (size_t)h.stages * stage_bytes + 1024 + 256;
+        VQB_CUDA(cudaFuncSetAttribute(conv_wgrad_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid(out_tiles, splits);
+        conv_wgrad_tc_halo_kernel<<<grid, NTHREADS, smem, stream>>>(tmDy, tmX, h);
+        VQB_CHECK_LAUNCH("conv2d_wgrad_tc_halo");
+        return VQB_OK;
+    }
     WgradParams p;
     p.N = N; p.H = H; p.W = W; p.Ci = Ci; p.Co = Co; p.KH = KH; p.KW = KW; p.pad = pad;
     pick_tile(BK, H, W, p.tw, p.th, p.nb);

@@ -31,6 +31,7 @@ SIGNATURES = {
     'vqb_unpack_conv_wgrad': (_i, [_p, _p, _i, _i, _i, _i, _f, _p]),
     'vqb_conv2d_fwd': (_i, [_i, _p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, _p]),
     'vqb_conv2d_wgrad': (_i, [_i, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    'vqb_set_halo_mode': (None, [_i]),
     'vqb_colsum': (_i, [_p, _i, _p, _i64, _i, _p]),
     'vqb_gn_stats': (_i, [_p, _i, _p, _i, _i, _i, _i, _p]),
     'vqb_gn_finalize': (_i, [_p, _p, _i, _i, _i, _i, _f, _p]),
