@@ -162,6 +162,38 @@ int vqb_vq_ema_update(float* ema_count, float* ema_weight, float* codebook, cons
  *   dcb[k] += (g_loss[0] * 2*cb_scale/(N*D)) * sum_{i:idx_i=k} (q[i]-z[i])   (dcb NULL for EMA; caller zero-fills) */
 int vqb_vq_backward(const float* z, const float* q, const int64_t* idx, const float* g_q, const float* g_loss,
                     float beta, float cb_scale, float* dz, float* dcb, int64_t N, int K, int D, void* stream);
+/* out[r] = sum_d a[r][d]^2  (|e_k|^2 of the codebook rows) */
+int vqb_row_sqnorm(const float* a, float* out, int64_t R, int D, void* stream);
+
+/* Entropy quantizer (EntropyVectorQuantizer.forward, vector_quantizers.py:290-356), organised around the N x K matrix
+ * that the implicit-GEMM kernel produces (dot = flat_x @ codebook^T as a 1x1 convolution):
+ *   entropy_rows : dot[N][K] is overwritten IN PLACE by logp = log_softmax(-d/T), d = (|z|^2 - 2 dot) + |e|^2 (:337-340);
+ *                  idx_out = argmin d (first index); *sample_entropy_sum (double, caller zero-fills) += -sum_k p log p per row
+ *   colsum_exp   : out[k] (caller zero-fills) += sum_rows exp(logp[row][k])           (N * avg_probs, :320)
+ *   finalize     : out[0] = ratio * (sample_entropy_sum/N - avg_entropy), out[1] = avg_entropy = -sum m log(m+1e-5) (:321-328)
+ *   bwd_rows     : logp[N][K] is overwritten IN PLACE by G = dLoss/dd; dz += -2 G E and
+ *                  dE += 2 E colsum(G) - 2 G^T Z are then 1x1-convolution dgrad/wgrad calls + combine_dcb */
+int vqb_vq_entropy_rows(float* dot_to_logp, const float* z, const float* codebook_sq, float temperature, int64_t* idx_out,
+                        double* sample_entropy_sum, int64_t N, int K, int D, void* stream);
+int vqb_vq_colsum_exp(const float* logp, float* out, int64_t N, int K, void* stream);
+int vqb_vq_entropy_finalize(const float* colsum_p, const double* sample_entropy_sum, float ratio, float* out, int64_t N, int K,
+                            void* stream);
+int vqb_vq_entropy_bwd_rows(float* logp_to_g, const float* colsum_p, const float* g_loss, float ratio, float temperature,
+                            int64_t N, int K, void* stream);
+int vqb_vq_entropy_combine_dcb(float* dcb, const float* codebook, const float* colsum_g, const float* gtz, int K, int D,
+                               void* stream);
+
+/* Gumbel-softmax quantizer rows (GumbelVectorQuantizer.forward, vector_quantizers.py:223-245; F.gumbel_softmax):
+ *   fwd: y[row] = softmax((logits - log(exp_noise)) / tau)  (hard != 0: one-hot of its argmax), idx = argmax,
+ *        *kl_sum (double, caller zero-fills) += sum_n qy log(qy K + 1e-10), qy = softmax(logits).
+ *        exp_noise holds the Exp(1) samples F.gumbel_softmax draws (explicit so CPU and GPU consume identical noise;
+ *        NULL = no noise).
+ *   bwd: dlogits = (1/tau) soft (dy - sum soft dy) + g_kl[0] * kl_scale * qy (f - sum qy f) */
+int vqb_gumbel_rows_fwd(const float* logits, const float* exp_noise, float tau, int hard, float* y, int64_t* idx_out,
+                        double* kl_sum, int64_t N, int K, void* stream);
+int vqb_gumbel_rows_bwd(const float* logits, const float* exp_noise, float tau, const float* dy, const float* g_kl,
+                        float kl_scale, float* dlogits, int64_t N, int K, void* stream);
+
 /* gather rows: out[i] = codebook[idx[i]] (BaseVectorQuantizer.codes_to_vec base_quantizer.py:53-61) */
 int vqb_vq_gather(const float* codebook, const int64_t* idx, float* out, int64_t N, int K, int D, void* stream);
 

@@ -188,6 +188,8 @@ def test_adamw(V):
 def _build_model(V, case, qtype, sd):
     c = C.CASES[case]
     qp = {k: v for k, v in C.Q_PARAMS[qtype].items() if k != 'type'}
+    if qtype == 'gumbel':
+        qp.update(kl_warmup_epochs=None, temp_decay_epochs=None, temp_final=None)
     model = V.VQVAE(c['S'], dict(channels=c['ch'], num_res_blocks=c['nrb'], channel_multipliers=list(c['mult'])),
                     dict(num_embeddings=c['K'], embedding_dim=c['D'], type=qtype, params=qp, reinit_every_n_epochs=None),
                     None, dict(lr=1e-4, betas=[0.0, 0.99], eps=1e-8, weight_decay=1e-4, warmup_epochs=None, decay_epochs=None))
@@ -228,3 +230,57 @@ def test_train_step_matches_reference_fixture(V, case, qtype):
             assert C.rel_err(model.quantizer.ema_weight, g['new_ema_weight']) < 1e-5
         else:
             assert C.rel_err(model.quantizer.codebook.weight.grad, g['grad_codebook']) < TOL
+
+
+@pytest.mark.parametrize('case', ['tiny', 'cfg1'])
+def test_entropy_train_step_matches_reference_fixture(V, case):
+    """Entropy quantizer (cfg3 family): forward + backward incl. the softmax-entropy regulariser and its codebook gradient."""
+    g = C.golden(f'{case}_entropy')
+    sd, x = C.seeded_inputs(case, 'entropy')
+    model = _build_model(V, case, 'entropy', sd)
+    xg = cl(x)
+    recon, q_loss, idx = model(xg)
+    l2 = model.criterion(recon, xg)
+    (q_loss + l2).backward()
+    c = C.CASES[case]
+    flat = torch.from_numpy(g['z']).permute(0, 2, 3, 1).reshape(-1, c['D'])
+    exact, ties, bad = C.tie_aware_index_check(idx, g['idx'], flat, sd['quantizer.codebook.weight'], order='entropy')
+    assert bad == 0 and ties <= max(1, idx.numel() // 100), (exact, ties, bad)
+    if ties == 0:
+        assert abs(float(q_loss) - float(g['q_loss'])) <= TOL * max(1.0, abs(float(g['q_loss'])))
+        assert C.rel_err(recon, g['recon']) < TOL
+        assert C.rel_err(model.quantizer.codebook.weight.grad, g['grad_codebook']) < 5 * TOL
+        assert C.rel_err(model.encoder.conv_in.weight.grad, g['grad_enc_conv_in']) < 5 * TOL
+        ref_norm = dict(zip(g['grad_names'].tolist(), g['grad_norms'].tolist()))
+        for n, p in model.named_parameters():
+            if p.grad is not None and n in ref_norm:
+                assert abs(float(p.grad.double().norm()) - ref_norm[n]) <= 5 * TOL * ref_norm[n] + 1e-7, n
+
+
+@pytest.mark.parametrize('case', ['tiny', 'cfg1'])
+def test_gumbel_train_step_matches_reference_fixture(V, case):
+    """Gumbel quantizer (cfg4 family) with the reference's own Exp(1) noise fed explicitly to the kernel."""
+    g = C.golden(f'{case}_gumbel')
+    sd, x = C.seeded_inputs(case, 'gumbel')
+    model = _build_model(V, case, 'gumbel', sd)
+    xg = cl(x)
+    noise = cl(torch.from_numpy(g['exp_noise']))
+    z = model.encoder(xg)
+    quant, idx, q_loss = model.quantizer(z, exp_noise=noise)
+    recon = model.decoder(quant)
+    l2 = model.criterion(recon, xg)
+    (q_loss + l2).backward()
+    assert tuple(idx.shape) == tuple(g['idx'].shape)                     # (B,H,W): defect B5 replicated
+    assert C.rel_err(z, g['z']) < TOL
+    mism = int((idx.cpu() != torch.from_numpy(g['idx'])).sum())
+    assert mism <= max(1, idx.numel() // 100)
+    assert abs(float(q_loss) - float(g['q_loss'])) <= TOL * max(1e-3, abs(float(g['q_loss'])))
+    assert C.rel_err(quant, g['quantized']) < TOL
+    assert C.rel_err(recon, g['recon']) < TOL
+    assert abs(float(l2) - float(g['l2'])) <= TOL
+    assert C.rel_err(model.quantizer.x_to_logits.weight.grad, g['grad_x_to_logits']) < 5 * TOL
+    assert C.rel_err(model.encoder.conv_in.weight.grad, g['grad_enc_conv_in']) < 5 * TOL
+    ref_norm = dict(zip(g['grad_names'].tolist(), g['grad_norms'].tolist()))
+    for n, p in model.named_parameters():
+        if p.grad is not None and n in ref_norm:
+            assert abs(float(p.grad.double().norm()) - ref_norm[n]) <= 5 * TOL * ref_norm[n] + 1e-7, n

@@ -49,6 +49,14 @@ SIGNATURES = {
     'vqb_vq_ema_update': (_i, [_p, _p, _p, _p, _p, _i, _i, _f, _f, _f, _p]),
     'vqb_vq_backward': (_i, [_p, _p, _p, _p, _p, _f, _f, _p, _p, _i64, _i, _i, _p]),
     'vqb_vq_gather': (_i, [_p, _p, _p, _i64, _i, _i, _p]),
+    'vqb_row_sqnorm': (_i, [_p, _p, _i64, _i, _p]),
+    'vqb_vq_entropy_rows': (_i, [_p, _p, _p, _f, _p, _p, _i64, _i, _i, _p]),
+    'vqb_vq_colsum_exp': (_i, [_p, _p, _i64, _i, _p]),
+    'vqb_vq_entropy_finalize': (_i, [_p, _p, _f, _p, _i64, _i, _p]),
+    'vqb_vq_entropy_bwd_rows': (_i, [_p, _p, _p, _f, _f, _i64, _i, _p]),
+    'vqb_vq_entropy_combine_dcb': (_i, [_p, _p, _p, _p, _i, _i, _p]),
+    'vqb_gumbel_rows_fwd': (_i, [_p, _p, _f, _i, _p, _p, _p, _i64, _i, _p]),
+    'vqb_gumbel_rows_bwd': (_i, [_p, _p, _f, _p, _p, _f, _p, _i64, _i, _p]),
     'vqb_adamw': (_i, [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _f, _i, _f, _p]),
 }
 

@@ -59,3 +59,71 @@ class EMAVectorQuantizer(BaseVectorQuantizer):
     @torch.no_grad()
     def vec_to_codes(self, x: torch.Tensor) -> torch.Tensor:
         return ops.vq_codes(x, self.codebook.weight, 0)
+
+
+class GumbelVectorQuantizer(BaseVectorQuantizer):
+    """Gumbel-softmax quantizer (vector_quantizers.py:206-274).  The encoder emits K channels; logits = 1x1 conv K->K
+    (implicit GEMM), y = gumbel_softmax(logits, tau) over channels (row kernel on the channels-last tensor), quantized =
+    einsum('b n h w, n d -> b d h w', y, codebook) = a second 1x1 conv with the transposed codebook as weight, plus the
+    KL-to-uniform term.  Defects replicated: noise is always added, even in eval mode (B6); indices are (B,H,W) (B5).
+    `exp_noise` (the Exp(1) samples F.gumbel_softmax draws) may be passed explicitly for parity runs."""
+
+    def __init__(self, num_embeddings: int, embedding_dim: int, straight_through: bool = False, temp: float = 1.0,
+                 kl_cost: float = 5e-4):
+        super().__init__(num_embeddings, embedding_dim)
+        from .autoencoder import Conv2d
+        self.x_to_logits = Conv2d(num_embeddings, num_embeddings, 1)
+        self.straight_through = straight_through
+        self.temp = temp
+        self.kl_cost = kl_cost
+
+    def forward(self, x: torch.Tensor, exp_noise: torch.Tensor = None):
+        hard = self.straight_through if self.training else True
+        logits = self.x_to_logits(x, out_dtype=torch.float32)
+        if exp_noise is None:
+            exp_noise = torch.empty_like(logits, memory_format=torch.preserve_format).exponential_()     # RNG plumbing
+        y, idx, kl_mean = ops.gumbel_rows(logits, exp_noise, float(self.temp), hard)
+        w = self.codebook.weight.t().reshape(self.embedding_dim, self.num_embeddings, 1, 1)
+        quantized = ops.conv2d(y, w, out_dtype=torch.float32)
+        self.last_counts = None
+        return quantized, idx, self.kl_cost * kl_mean
+
+    def get_consts(self):
+        return self.temp, self.kl_cost
+
+    def set_consts(self, temp: float = None, kl_cost: float = None) -> None:
+        if temp is not None:
+            self.temp = temp
+        if kl_cost is not None:
+            self.kl_cost = kl_cost
+
+    @torch.no_grad()
+    def vec_to_codes(self, x: torch.Tensor, exp_noise: torch.Tensor = None) -> torch.Tensor:
+        """gumbel_softmax(x, tau=1, hard=True).argmax(1) on the RAW encoder output (x_to_logits is skipped: B6)."""
+        x = ops.as_nhwc(x, torch.float32)
+        if exp_noise is None:
+            exp_noise = torch.empty_like(x, memory_format=torch.preserve_format).exponential_()
+        return ops.gumbel_rows(x, exp_noise, 1.0, True)[1]
+
+
+class EntropyVectorQuantizer(BaseVectorQuantizer):
+    """Entropy-regularised quantizer (vector_quantizers.py:277-381)."""
+
+    def __init__(self, num_embeddings: int, embedding_dim: int, ent_loss_ratio: float = 0.1, ent_temperature: float = 0.01,
+                 ent_loss_type: str = 'softmax', commitment_cost: float = 0.25):
+        super().__init__(num_embeddings, embedding_dim)
+        self.ent_loss_ratio = ent_loss_ratio
+        self.ent_temperature = ent_temperature
+        self.ent_loss_type = ent_loss_type
+        self.commitment_cost = commitment_cost
+
+    def forward(self, x: torch.Tensor):
+        if self.ent_loss_type != 'softmax':
+            if self.ent_loss_type == 'argmax':
+                raise NotImplementedError("ent_loss_type='argmax' (straight-through one-hot targets, :311-315) is not built yet")
+            raise ValueError('Entropy loss {} not supported'.format(self.ent_loss_type))
+        return ops.vq_entropy(x, self.codebook.weight, self.commitment_cost, self.ent_loss_ratio, self.ent_temperature)
+
+    @torch.no_grad()
+    def vec_to_codes(self, x: torch.Tensor) -> torch.Tensor:
+        return ops.vq_codes(x, self.codebook.weight, 1)

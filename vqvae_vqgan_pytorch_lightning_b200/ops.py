@@ -122,7 +122,10 @@ def _packed_weight(weight: torch.Tensor, mode: int, dtype: torch.dtype, scale: f
     if tag not in cache:
         co, ci, kh, kw = weight.shape
         wp = torch.empty(co * ci * kh * kw, dtype=dtype, device=weight.device)
-        call('vqb_pack_conv_weight', ptr(weight.detach()), ptr(wp), dt(wp), mode, co, ci, kh, kw, scale, stream())
+        src = weight.detach()
+        if not src.is_contiguous() or src.dtype != torch.float32:
+            src = src.float().contiguous()            # e.g. the transposed-codebook view used by the Gumbel einsum
+        call('vqb_pack_conv_weight', ptr(src), ptr(wp), dt(wp), mode, co, ci, kh, kw, scale, stream())
         cache[tag] = wp
     return cache[tag]
 
@@ -200,7 +203,7 @@ class Conv2dFn(torch.autograd.Function):
             dwp = torch.zeros(kh * kw * ci * co, dtype=torch.float32, device=x.device)
             call('vqb_conv2d_wgrad', wimpl, ptr(x), dt(x), ptr(dyw), dt(dyw), ptr(dwp), n, h, w, ci, co, kh, kw, pad, stride,
                  stream())
-            dw = torch.empty_like(weight, dtype=torch.float32)
+            dw = torch.empty(weight.shape, dtype=torch.float32, device=x.device)      # contiguous even if `weight` is a view
             call('vqb_unpack_conv_wgrad', ptr(dwp), ptr(dw), co, ci, kh, kw, w_scale, stream())
         if has_bias and ctx.needs_input_grad[2]:
             db = torch.zeros(co, dtype=torch.float32, device=x.device)
@@ -428,6 +431,114 @@ def vq_gather(codebook, idx):
     out = torch.empty(flat_idx.numel(), cb.shape[1], dtype=torch.float32, device=cb.device)
     call('vqb_vq_gather', ptr(cb), ptr(flat_idx), ptr(out), flat_idx.numel(), cb.shape[0], cb.shape[1], stream())
     return out.reshape(*idx.shape, cb.shape[1])
+
+
+def _gemm_nk(x2d: torch.Tensor, wp: torch.Tensor, k_in: int, k_out: int, residual=None, gain: float = 1.0) -> torch.Tensor:
+    """[N,k_in] fp32 @ wp[k_in][k_out] fp32 (+ residual) * gain as a 1x1 'convolution' on N single-pixel images (fp32 SIMT
+    implicit GEMM: the quantizers need fp32 distances / codebook gradients)."""
+    n = x2d.shape[0]
+    y = torch.empty(n, k_out, dtype=torch.float32, device=x2d.device)
+    call('vqb_conv2d_fwd', 0, ptr(x2d), F32, ptr(wp), None, ptr(residual), ptr(y), F32, n, 1, 1, k_in, k_out, 1, 1, 0, 1, ACT_NONE,
+         0.0, gain, stream())
+    return y
+
+
+class VQEntropyFn(torch.autograd.Function):
+    """EntropyVectorQuantizer.forward (vector_quantizers.py:290-356): nearest code on d = (|z|^2 - 2 z.e) + |e|^2, straight-through
+    output, (1+beta)-weighted MSE terms and the entropy regulariser ratio * (mean_i H(p_i) - H(mean_i p_i)), p = softmax(-d/T).
+    The N x K matrix exists once (fp32) and is transformed in place: dot -> log p (forward), log p -> dLoss/dd (backward)."""
+
+    @staticmethod
+    def forward(ctx, z, codebook, beta, ratio, temperature):
+        z = as_nhwc(z, torch.float32)
+        b, d, h, w = z.shape
+        flat = z.permute(0, 2, 3, 1).reshape(b * h * w, d)
+        cb = codebook.detach().float().contiguous()
+        n, k = flat.shape[0], cb.shape[0]
+        dev = flat.device
+        cbt = torch.empty(d * k, dtype=torch.float32, device=dev)                       # E^T as a packed 1x1 weight [D][K]
+        call('vqb_pack_conv_weight', ptr(cb), ptr(cbt), F32, 0, k, d, 1, 1, 1.0, stream())
+        m = _gemm_nk(flat, cbt, d, k)                                                    # dot products [N,K]
+        cb_sq = torch.empty(k, dtype=torch.float32, device=dev)
+        call('vqb_row_sqnorm', ptr(cb), ptr(cb_sq), k, d, stream())
+        idx = torch.empty(n, dtype=torch.int64, device=dev)
+        ent_sum = torch.zeros(1, dtype=torch.float64, device=dev)
+        call('vqb_vq_entropy_rows', ptr(m), ptr(flat), ptr(cb_sq), temperature, ptr(idx), ptr(ent_sum), n, k, d, stream())
+        colsum_p = torch.zeros(k, dtype=torch.float32, device=dev)
+        call('vqb_vq_colsum_exp', ptr(m), ptr(colsum_p), n, k, stream())
+        ent = torch.empty(2, dtype=torch.float32, device=dev)
+        call('vqb_vq_entropy_finalize', ptr(colsum_p), ptr(ent_sum), ratio, ptr(ent), n, k, stream())
+        q = torch.empty_like(flat)
+        call('vqb_vq_gather', ptr(cb), ptr(idx), ptr(q), n, k, d, stream())
+        sums = torch.zeros(2, dtype=torch.float64, device=dev)
+        call('vqb_diff_sums', ptr(q), F32, ptr(flat), F32, ptr(sums), flat.numel(), stream())
+        loss = (sums[0] * ((1.0 + beta) / flat.numel())).float() + ent[0]
+        ctx.save_for_backward(flat, q, idx, m, colsum_p, cb)
+        ctx.cfg = (beta, ratio, temperature, z.shape)
+        qz = q.reshape(b, h, w, d).permute(0, 3, 1, 2)
+        ctx.mark_non_differentiable(idx)
+        return qz, idx.reshape(b, h * w), loss
+
+    @staticmethod
+    def backward(ctx, g_q, _g_idx, g_loss):
+        flat, q, idx, m, colsum_p, cb = ctx.saved_tensors
+        beta, ratio, temperature, zshape = ctx.cfg
+        n, d = flat.shape
+        k = cb.shape[0]
+        dev = flat.device
+        gq = as_nhwc(g_q, torch.float32) if g_q is not None else None
+        gl = g_loss.reshape(1).float().contiguous() if g_loss is not None else torch.zeros(1, device=dev)
+        dz = torch.empty_like(flat)
+        dcb = torch.zeros(k, d, dtype=torch.float32, device=dev)
+        call('vqb_vq_backward', ptr(flat), ptr(q), ptr(idx), ptr(gq), ptr(gl), beta, 1.0, ptr(dz), ptr(dcb), n, k, d, stream())
+        g = m.clone()                                                                    # keep logp intact for a second backward call
+        call('vqb_vq_entropy_bwd_rows', ptr(g), ptr(colsum_p), ptr(gl), ratio, temperature, n, k, stream())
+        dz = _gemm_nk(g, cb, k, d, residual=dz, gain=-2.0)                               # dz += -2 G E   (wp[(k)][d] = E itself)
+        gtz = torch.zeros(k * d, dtype=torch.float32, device=dev)
+        call('vqb_conv2d_wgrad', 0, ptr(g), F32, ptr(flat), F32, ptr(gtz), n, 1, 1, k, d, 1, 1, 0, 1, stream())   # G^T Z
+        colsum_g = torch.zeros(k, dtype=torch.float32, device=dev)
+        call('vqb_colsum', ptr(g), F32, ptr(colsum_g), n, k, stream())
+        call('vqb_vq_entropy_combine_dcb', ptr(dcb), ptr(cb), ptr(colsum_g), ptr(gtz), k, d, stream())
+        b, _, h, w = zshape
+        return dz.reshape(b, h, w, d).permute(0, 3, 1, 2), dcb, None, None, None
+
+
+def vq_entropy(z, codebook, beta, ratio, temperature):
+    return VQEntropyFn.apply(z, codebook, beta, ratio, temperature)
+
+
+class GumbelRowsFn(torch.autograd.Function):
+    """Gumbel-softmax over the channel dimension of a channels-last [B,K,h,w] logits tensor + KL-to-uniform term
+    (F.gumbel_softmax + vector_quantizers.py:234-241).  Returns (y [B,K,h,w], idx [B,h,w] int64, kl_mean)."""
+
+    @staticmethod
+    def forward(ctx, logits, exp_noise, tau, hard):
+        logits = as_nhwc(logits, torch.float32)
+        b, k, h, w = logits.shape
+        n = b * h * w
+        noise = as_nhwc(exp_noise, torch.float32) if exp_noise is not None else None
+        y = torch.empty_like(logits, memory_format=torch.preserve_format)
+        idx = torch.empty(n, dtype=torch.int64, device=logits.device)
+        kl = torch.zeros(1, dtype=torch.float64, device=logits.device)
+        call('vqb_gumbel_rows_fwd', ptr(logits), ptr(noise), tau, int(hard), ptr(y), ptr(idx), ptr(kl), n, k, stream())
+        ctx.save_for_backward(logits, noise)
+        ctx.cfg = (tau, n, k)
+        ctx.mark_non_differentiable(idx)
+        return y, idx.reshape(b, h, w), (kl[0] / n).float()
+
+    @staticmethod
+    def backward(ctx, dy, _g_idx, g_kl):
+        logits, noise = ctx.saved_tensors
+        tau, n, k = ctx.cfg
+        dyc = as_nhwc(dy, torch.float32) if dy is not None else None
+        gk = g_kl.reshape(1).float().contiguous() if g_kl is not None else None
+        dl = torch.empty_like(logits, memory_format=torch.preserve_format)
+        call('vqb_gumbel_rows_bwd', ptr(logits), ptr(noise), tau, ptr(dyc), ptr(gk), 1.0 / n, ptr(dl), n, k, stream())
+        return dl, None, None, None
+
+
+def gumbel_rows(logits, exp_noise, tau, hard):
+    return GumbelRowsFn.apply(logits, exp_noise, tau, hard)
 
 
 # ------------------------------------------------------------------------------------------------------
