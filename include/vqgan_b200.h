@@ -79,6 +79,11 @@ int vqb_conv2d_fwd(int impl, const void* x, int x_dtype, const void* wp, const f
  * dwp must be zero-filled by the caller (split-K partial sums are accumulated with atomics). */
 int vqb_conv2d_wgrad(int impl, const void* x, int x_dtype, const void* dy, int dy_dtype, float* dwp,
                      int N, int H, int W, int Ci, int Co, int KH, int KW, int pad, int stride, void* stream);
+/* Input gradient of a STRIDED convolution (stride-1 dgrad is vqb_conv2d_fwd on dy with the mode-1/3 packed weight):
+ * dx[N,H,W,Ci] from dy[N,OH,OW,Co], OH = (H+2*pad-KH)/stride+1, wd = mode-1 packed weight (fp32 SIMT gather over the
+ * virtually zero-upsampled dy).  Used by the StyleGAN2 discriminator's down-sampling convs (conv2d_resample.py:119-122). */
+int vqb_conv2d_dgrad(const void* dy, int dy_dtype, const void* wd, void* dx, int dx_dtype, int N, int H, int W, int Ci, int Co,
+                     int KH, int KW, int pad, int stride, void* stream);
 /* Test / tuning hook for the tcgen05 forward kernel: 0 = generic per-tap TMA loads only, 1 = 3x3 halo reuse (default),
  * 2-4 = descriptor-semantics probes (see csrc/conv_tc.cu); -1 = follow the VQB_HALO_MODE environment variable. */
 void vqb_set_halo_mode(int mode);
@@ -129,6 +134,31 @@ int vqb_diff_grad(const void* a, int a_dtype, const void* b, int b_dtype, void* 
 /* dx = dy * act'(from the saved OUTPUT y): tanh -> 1-y^2 ; used after a conv with a fused tanh epilogue */
 int vqb_act_bwd_from_output(const void* y, int y_dtype, const void* dy, int dy_dtype, void* dx, int dx_dtype, int act,
                             float alpha, float gain, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * VQGAN loss heads: StyleGAN2 discriminator resampling, LPIPS, minibatch-stddev (vqvae/modules/loss/)
+ * ---------------------------------------------------------------------------------------------------- */
+/* depthwise 4x4 FIR [1,3,3,1]x[1,3,3,1]/64 on the zero-padded input, then keep every `down`-th sample:
+ * y[n,oh,ow,c] = sum_{a,b} f[a]f[b] x[n, oh*down-pad+a, ow*down-pad+b, c], OH = (H+2*pad-4)/down+1
+ * (upfirdn2d with up=1: ops/upfirdn2d.py:120-208, kernels upfirdn2d.cu:97-341).  bwd = its adjoint (dx is [N,H,W,C]). */
+int vqb_fir4_fwd(const void* x, void* y, int dtype, int N, int H, int W, int C, int pad, int down, void* stream);
+int vqb_fir4_bwd(const void* dy, void* dx, int dtype, int N, int H, int W, int C, int pad, int down, void* stream);
+/* 2x2 / stride-2 max-pool (torchvision VGG16 features): y is [N,H,W,C], x is [N,2H,2W,C]; backward routes the
+ * gradient to the first maximal element of each window (torch semantics) and writes all of dx */
+int vqb_maxpool2_fwd(const void* x, void* y, int dtype, int N, int H, int W, int C, void* stream);
+int vqb_maxpool2_bwd(const void* x, int x_dtype, const void* dy, void* dx, int g_dtype, int N, int H, int W, int C, void* stream);
+/* y[p][c] = x[p][c]*scale[c] + shift[c]  (BaseNet.z_score, lpips_pytorch/modules/networks.py:48-49) */
+int vqb_channel_affine(const void* x, int x_dtype, void* y, int y_dtype, const float* scale, const float* shift, int64_t P, int C,
+                       void* stream);
+/* LPIPS tap (lpips.py:31-38, utils.py:6-8): out[0] (double, caller zero-fills) += sum_pixels sum_c w[c] (u_c - v_c)^2 with
+ * u = fx/(|fx|_c + 1e-10), v = fy/(|fy|_c + 1e-10);  bwd: dfy = scale * upstream[0] * d(out)/d(fy) */
+int vqb_lpips_tap_fwd(const void* fx, const void* fy, int dtype, const float* w, double* out, int64_t P, int C, void* stream);
+int vqb_lpips_tap_bwd(const void* fx, const void* fy, int dtype, const float* w, const float* upstream, float scale, void* dfy,
+                      int g_dtype, int64_t P, int C, void* stream);
+/* MinibatchStdLayer (discriminator.py:277-293), num_channels=1: y [N][HW][C+1]; stat [N/G] scratch; sample s is in
+ * group s % (N/G) exactly as the reference's reshape(G, -1, ...) */
+int vqb_mbstd_fwd(const void* x, void* y, float* stat, int dtype, int N, int G, int HW, int C, void* stream);
+int vqb_mbstd_bwd(const void* x, int x_dtype, const void* dy, void* dx, int g_dtype, int N, int G, int HW, int C, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * Vector quantisation (vqvae/modules/vector_quantizers.py)

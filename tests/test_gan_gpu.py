@@ -1,0 +1,168 @@
+"""GPU parity of the VQGAN loss heads (LPIPS-VGG16, StyleGAN2 discriminator, FIR / max-pool / mbstd kernels) against
+fixtures produced by the reference's own modules (oracle/make_golden_gan.py) and against plain-torch restatements."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from tests import common as C
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.fixture(scope='module')
+def V():
+    import vqvae_vqgan_pytorch_lightning_b200 as pkg
+    pkg.lib.load()
+    pkg.set_precision('strict')
+    return pkg
+
+
+def cl(t):
+    return t.cuda().contiguous(memory_format=torch.channels_last)
+
+
+def test_fir4_matches_upfirdn2d_semantics(V):
+    """4x4 [1,3,3,1]^2/64 FIR with the two (pad, down) settings the discriminator uses, forward and adjoint."""
+    from vqvae_vqgan_pytorch_lightning_b200 import ops_gan
+    torch.manual_seed(0)
+    f = torch.tensor([1., 3., 3., 1.]); f = f.ger(f); f = f / f.sum()
+    for (pad, down, h, w) in ((2, 1, 8, 8), (1, 2, 8, 8), (2, 1, 5, 7), (1, 2, 6, 10)):
+        x = torch.randn(2, 5, h, w)
+        xo = x.clone().requires_grad_()
+        y = F.conv2d(F.pad(xo, [pad, pad, pad, pad]), f[None, None].repeat(5, 1, 1, 1), groups=5)[:, :, ::down, ::down]
+        go = torch.randn_like(y)
+        y.backward(go)
+        xg = cl(x).requires_grad_()
+        yg = ops_gan.fir4(xg, pad, down)
+        yg.backward(cl(go))
+        assert C.rel_err(yg, y) < 1e-6 and C.rel_err(xg.grad, xo.grad) < 1e-6
+
+
+def test_maxpool_mbstd_strided_conv(V):
+    from vqvae_vqgan_pytorch_lightning_b200 import ops_gan
+    torch.manual_seed(1)
+    x = torch.relu(torch.randn(2, 8, 6, 6))                       # ReLU input: ties at zero exercise first-max routing
+    xo = x.clone().requires_grad_()
+    y = F.max_pool2d(xo, 2, 2); go = torch.randn_like(y); y.backward(go)
+    xg = cl(x).requires_grad_()
+    yg = ops_gan.max_pool2(xg); yg.backward(cl(go))
+    assert torch.equal(yg.cpu(), y) and C.rel_err(xg.grad, xo.grad) < 1e-7
+    # minibatch stddev, N=8, G=4
+    x = torch.randn(8, 6, 4, 4); xo = x.clone().requires_grad_()
+    G, N, Cc, H, W = 4, 8, 6, 4, 4
+    t = xo.reshape(G, -1, 1, Cc, H, W); t = t - t.mean(dim=0); t = (t.square().mean(dim=0) + 1e-8).sqrt().mean(dim=[2, 3, 4])
+    y = torch.cat([xo, t.reshape(-1, 1, 1, 1).repeat(G, 1, H, W)], dim=1)
+    go = torch.randn_like(y); y.backward(go)
+    xg = cl(x).requires_grad_()
+    yg = ops_gan.mbstd(xg, 4); yg.backward(cl(go))
+    assert C.rel_err(yg, y) < 1e-6 and C.rel_err(xg.grad, xo.grad) < 1e-5
+    # stride-2 conv without padding (discriminator down-conv), forward / dgrad / wgrad
+    x = torch.randn(2, 16, 9, 9); wt = torch.randn(24, 16, 3, 3) * 0.1
+    xo, wo = x.clone().requires_grad_(), wt.clone().requires_grad_()
+    y = F.conv2d(xo, wo, None, stride=2); go = torch.randn_like(y); y.backward(go)
+    xg, wg = cl(x).requires_grad_(), wt.cuda().requires_grad_()
+    yg = V.ops.conv2d(xg, wg, None, None, pad=0, stride=2); yg.backward(cl(go))
+    assert C.rel_err(yg, y) < TOL and C.rel_err(xg.grad, xo.grad) < TOL and C.rel_err(wg.grad, wo.grad) < TOL
+
+
+def test_lpips_vgg_matches_reference_fixture(V):
+    import torchvision
+    from vqvae_vqgan_pytorch_lightning_b200.modules.loss.lpips import LPIPS
+    g = C.golden('gan_lpips_vgg')
+    chans = [64, 128, 256, 512, 512]
+    torch.manual_seed(11)                                          # same RNG stream as oracle/make_golden_gan.ref_lpips
+    tv = torchvision.models.vgg16(weights=None)
+    _ = [nn.Conv2d(nc, 1, 1, 1, 0, bias=False) for nc in chans]   # LinLayers' default init consumes the stream
+    lin_w = [torch.rand(1, c, 1, 1) for c in chans]
+    assert abs(float(tv.features[0].weight.double().sum()) - float(g['w0_sum'])) < 1e-9
+    m = LPIPS('vgg', pretrained=False)
+    m.net.layers.load_state_dict({k: v for k, v in tv.features.state_dict().items() if int(k.split('.')[0]) < 30})
+    for i, w in enumerate(lin_w):
+        m.lin[i][1].weight.data.copy_(w)
+    m = m.cuda().eval()
+    x, y = cl(torch.from_numpy(g['x'])), cl(torch.from_numpy(g['y'])).requires_grad_()
+    feats = m.net(y.detach())
+    for f, s in zip(feats, g['feat_sums']):             # the reference returns channel-unit-normalised taps (utils.py:6-8)
+        fn = f.float() / (f.float().pow(2).sum(1, keepdim=True).sqrt() + 1e-10)
+        assert abs(float(fn.double().sum()) - s) <= 2e-4 * abs(s)
+    out = m(x, y)
+    out.backward()
+    assert abs(float(out) - float(g['loss'])) <= TOL * abs(float(g['loss']))
+    # ReLU / max-pool gradient routing flips on 1-ulp forward differences: the reference's own fp32 gradient is ~0.7% away
+    # from its fp64 evaluation, so the bar is "no worse than twice the reference's own fp32 error" (plus the 1e-4 target)
+    err_ref = C.rel_err(g['grad_y'], g['grad_y_f64'])
+    assert C.rel_err(y.grad, g['grad_y_f64']) <= 2 * err_ref + TOL
+
+
+def test_discriminator_matches_reference_fixture(V):
+    from vqvae_vqgan_pytorch_lightning_b200.modules.loss.discriminator import Discriminator
+    g = C.golden('gan_discriminator')
+    torch.manual_seed(21)
+    d = Discriminator(64)
+    assert abs(sum(float(p.double().abs().sum()) for p in d.parameters()) - float(g['w_abs_sum'])) < 1e-6 * float(g['w_abs_sum'])
+    d = d.cuda().train()
+    img = cl(torch.from_numpy(g['img'])).requires_grad_()
+    logits = d(img)
+    B = logits.shape[0]
+    w = torch.linspace(-1.0, 1.0, B, device='cuda').reshape(B, 1)
+    loss = (logits * w).sum() + F.softplus(logits).mean()
+    loss.backward()
+    assert C.rel_err(logits, g['logits']) < TOL
+    assert abs(float(loss) - float(g['loss'])) < TOL
+    # Backward through 26 leaky-ReLU layers: a pre-activation within ~1 ulp of zero takes the other slope (0.2 vs 1) when the
+    # forward sum is accumulated in a different order, and ONE such flip in the 32768-element 4x4 layer already moves the
+    # input gradient by ~1.5e-3 (measured: tools/debug_disc2.py -- 6 flips in 22 M activations).  Every backward kernel is
+    # exact on its own (test_odd_channel_lrelu_conv_exact, test_fir4..., test_maxpool_mbstd...), so the fixture comparison
+    # uses a flip-tolerant bar; the reference's own fp32 result is 2e-4 away from a true fp64 evaluation.
+    assert C.rel_err(img.grad, g['grad_img']) < 5e-3
+    assert C.rel_err(d.b64.conv0.weight.grad[:8], g['grad_b64_conv0_w']) < 5e-3
+    assert C.rel_err(d.b4.out.weight.grad, g['grad_b4_out_w']) < 5 * TOL
+    ref_norm = dict(zip(g['grad_names'].tolist(), g['grad_norms'].tolist()))
+    for n, p in d.named_parameters():
+        assert abs(float(p.grad.double().norm()) - ref_norm[n]) <= 2e-3 * ref_norm[n] + 1e-9, n
+
+
+@pytest.mark.parametrize('n,h,w,ci,co,k', [(4, 4, 4, 513, 512, 3), (2, 8, 8, 130, 70, 3), (4, 1, 1, 8192, 512, 1)])
+def test_odd_channel_lrelu_conv_exact(V, n, h, w, ci, co, k):
+    """bias + leaky-ReLU(0.2) * sqrt(2) epilogue and its backward, channel counts that are not multiples of 4 (513 = mbstd
+    output), and the 8192 -> 512 fully connected layer as a 1x1 conv, against a float64 evaluation."""
+    torch.manual_seed(0)
+    x = torch.randn(n, ci, h, w).double(); wt = (torch.randn(co, ci, k, k) / (ci * k * k) ** 0.5).double(); b = torch.randn(co).double()
+    xo, wo, bo = x.clone().requires_grad_(), wt.clone().requires_grad_(), b.clone().requires_grad_()
+    y = F.leaky_relu(F.conv2d(xo, wo, bo, padding=k // 2), 0.2) * 1.4142135
+    go = torch.randn_like(y); y.backward(go)
+    xg, wg, bg = cl(x.float()).requires_grad_(), wt.float().cuda().requires_grad_(), b.float().cuda().requires_grad_()
+    yg = V.ops.conv2d(xg, wg, bg, None, pad=k // 2, act=V.lib.ACT_LRELU, alpha=0.2, gain=1.4142135)
+    yg.backward(cl(go.float()))
+    assert C.rel_err(yg, y) < 1e-5 and C.rel_err(xg.grad, xo.grad) < 1e-5
+    assert C.rel_err(wg.grad, wo.grad) < 1e-5 and C.rel_err(bg.grad, bo.grad) < 1e-5
+
+
+def test_gan_training_step_runs_and_updates(V):
+    """Branch A of training_step (two optimizers, manual optimisation) end to end on a small VQGAN: losses finite, both
+    parameter sets move, discriminator gradients from the generator pass are not applied."""
+    from vqvae_vqgan_pytorch_lightning_b200.lightning_shim import Trainer
+    torch.manual_seed(3)
+    adv = dict(start_epoch=0, loss_type='non-saturating', g_weight=0.1, use_adaptive=True, r1_reg_weight=None, r1_reg_every=16)
+    model = V.VQVAE(64, dict(channels=32, num_res_blocks=1, channel_multipliers=[1, 2]),
+                    dict(num_embeddings=64, embedding_dim=32, type='ema', params=dict(commitment_cost=0.25, decay=0.95, epsilon=1e-5),
+                         reinit_every_n_epochs=None),
+                    dict(l1_weight=0.8, l2_weight=0.2, perc_weight=1.0, adversarial_params=adv),
+                    dict(lr=1e-3, betas=[0.0, 0.99], eps=1e-8, weight_decay=1e-4, warmup_epochs=None, decay_epochs=None),
+                    pretrained_lpips=False).cuda().train()
+    tr = Trainer(max_epochs=1, num_training_batches=4)
+    tr.attach(model)
+    model.on_train_start()
+    w_dec0 = model.decoder.conv_out.weight.detach().clone()
+    w_d0 = model.criterion.discriminator.b4.out.weight.detach().clone()
+    x = torch.rand(4, 3, 64, 64, device='cuda')
+    for i in range(2):
+        loss = tr.run_step(x, i)
+    assert torch.isfinite(loss).all()
+    for k in ('train/loss', 'train/perc_loss', 'train/gen_loss', 'train/disc_loss'):
+        assert torch.isfinite(torch.as_tensor(model.logged[k])).all(), k
+    assert not torch.equal(model.decoder.conv_out.weight, w_dec0)
+    assert not torch.equal(model.criterion.discriminator.b4.out.weight, w_d0)

@@ -7,6 +7,8 @@ int vqb_conv2d_fwd_simt(const void* x, int x_dtype, const float* wp, const float
                         float alpha, float gain, cudaStream_t stream);
 int vqb_conv2d_wgrad_simt(const void* x, int x_dtype, const void* dy, int dy_dtype, float* dwp, int N, int H, int W, int Ci,
                           int Co, int KH, int KW, int pad, int stride, cudaStream_t stream);
+int vqb_conv2d_dgrad_simt(const void* dy, int dy_dtype, const float* wd, void* dx, int dx_dtype, int N, int H, int W, int Ci,
+                          int Co, int KH, int KW, int pad, int stride, cudaStream_t stream);
 int vqb_conv2d_fwd_tc(const void* x, const void* wp, const float* bias, const void* residual, void* y, int y_dtype, int N,
                       int H, int W, int Ci, int Co, int KH, int KW, int pad, int act, float alpha, float gain,
                       cudaStream_t stream);
@@ -42,4 +44,10 @@ extern "C" int vqb_conv2d_wgrad(int impl, const void* x, int x_dtype, const void
     }
     vqb_set_error("conv2d_wgrad: unknown impl %d", impl);
     return VQB_ERR_ARG;
+}
+
+extern "C" int vqb_conv2d_dgrad(const void* dy, int dy_dtype, const void* wd, void* dx, int dx_dtype, int N, int H, int W, int Ci,
+                                int Co, int KH, int KW, int pad, int stride, void* stream) {
+    VQB_CHECK_ARG(dy && wd && dx, "conv2d_dgrad: null pointer");
+    return vqb_conv2d_dgrad_simt(dy, dy_dtype, (const float*)wd, dx, dx_dtype, N, H, W, Ci, Co, KH, KW, pad, stride, as_stream(stream));
 }

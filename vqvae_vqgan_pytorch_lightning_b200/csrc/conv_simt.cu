@@ -15,6 +15,7 @@ constexpr int BM = 128, BN = 128, BK = 16, PADM = 4;
 
 struct ConvGeom {
     int N, H, W, Ci, Co, KH, KW, pad, stride, OH, OW;
+    int up;      // > 1: the input is (virtually) zero-upsampled by `up` -- transposed-conv gather for strided dgrad
     int64_t M;   // N*OH*OW
     int K;       // KH*KW*Ci
 };
@@ -89,7 +90,9 @@ conv_fwd_simt_kernel(const TIn* __restrict__ x, const float* __restrict__ wp, co
                     int tap = k / g.Ci, ci = k - tap * g.Ci;
                     int kh = tap / g.KW, kw = tap - kh * g.KW;
                     int ih = a_ih0[r] + kh, iw = a_iw0[r] + kw;
-                    if (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W)
+                    bool ok = ih >= 0 && iw >= 0;
+                    if (g.up > 1) { ok = ok && (ih % g.up == 0) && (iw % g.up == 0); ih /= g.up; iw /= g.up; }
+                    if (ok && ih < g.H && iw < g.W)
                         v = ld4(x + a_base[r] + ((int64_t)ih * g.W + iw) * g.Ci + ci);
                 }
                 a_reg[r][0] = v.x; a_reg[r][1] = v.y; a_reg[r][2] = v.z; a_reg[r][3] = v.w;
@@ -102,7 +105,9 @@ conv_fwd_simt_kernel(const TIn* __restrict__ x, const float* __restrict__ wp, co
                         int tap = kk / g.Ci, ci = kk - tap * g.Ci;
                         int kh = tap / g.KW, kw = tap - kh * g.KW;
                         int ih = a_ih0[r] + kh, iw = a_iw0[r] + kw;
-                        if (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W)
+                        bool ok = ih >= 0 && iw >= 0;
+                        if (g.up > 1) { ok = ok && (ih % g.up == 0) && (iw % g.up == 0); ih /= g.up; iw /= g.up; }
+                        if (ok && ih < g.H && iw < g.W)
                             v = ld1(x + a_base[r] + ((int64_t)ih * g.W + iw) * g.Ci + ci);
                     }
                     a_reg[r][j] = v;
@@ -475,7 +480,7 @@ inline int make_geom(ConvGeom& g, int N, int H, int W, int Ci, int Co, int KH, i
         vqb_set_error("conv2d: bad geometry N=%d H=%d W=%d Ci=%d Co=%d KH=%d KW=%d pad=%d stride=%d", N, H, W, Ci, Co, KH, KW, pad, stride);
         return VQB_ERR_ARG;
     }
-    g.N = N; g.H = H; g.W = W; g.Ci = Ci; g.Co = Co; g.KH = KH; g.KW = KW; g.pad = pad; g.stride = stride;
+    g.N = N; g.H = H; g.W = W; g.Ci = Ci; g.Co = Co; g.KH = KH; g.KW = KW; g.pad = pad; g.stride = stride; g.up = 1;
     g.OH = (H + 2 * pad - KH) / stride + 1;
     g.OW = (W + 2 * pad - KW) / stride + 1;
     if (g.OH <= 0 || g.OW <= 0) { vqb_set_error("conv2d: empty output"); return VQB_ERR_ARG; }
@@ -505,6 +510,24 @@ int vqb_conv2d_fwd_simt(const void* x, int x_dtype, const float* wp, const float
     VQB_DISPATCH_1(x_dtype, TIn, VQB_DISPATCH_1(y_dtype, TOut,
         (conv_fwd_simt_kernel<TIn, TOut><<<grid, 256, 0, stream>>>((const TIn*)x, wp, bias, (const TOut*)residual, (TOut*)y, g, act, alpha, gain));))
     VQB_CHECK_LAUNCH("conv2d_fwd_simt");
+    return VQB_OK;
+}
+
+// dgrad of a (possibly strided) convolution: dx[N,H,W,Ci] from dy[N,OH,OW,Co] and the dgrad-packed weight
+// wd[((KH-1-kh)*KW+(KW-1-kw))*Co+co][ci]; a stride-s forward conv becomes a gather over the zero-upsampled dy.
+int vqb_conv2d_dgrad_simt(const void* dy, int dy_dtype, const float* wd, void* dx, int dx_dtype, int N, int H, int W, int Ci,
+                          int Co, int KH, int KW, int pad, int stride, cudaStream_t stream) {
+    ConvGeom g;
+    const int OH = (H + 2 * pad - KH) / stride + 1, OW = (W + 2 * pad - KW) / stride + 1;
+    if (!(N > 0 && OH > 0 && OW > 0 && Ci > 0 && Co > 0)) { vqb_set_error("conv2d_dgrad: bad geometry"); return VQB_ERR_ARG; }
+    g.N = N; g.H = OH; g.W = OW; g.Ci = Co; g.Co = Ci; g.KH = KH; g.KW = KW;
+    g.pad = KH - 1 - pad; g.stride = 1; g.up = stride; g.OH = H; g.OW = W;
+    g.M = (int64_t)N * H * W; g.K = KH * KW * Co;
+    if (KH != KW) { vqb_set_error("conv2d_dgrad: square kernels only"); return VQB_ERR_UNSUPPORTED; }
+    dim3 grid((unsigned)ceil_div64(g.M, BM), (unsigned)((Ci + BN - 1) / BN));
+    VQB_DISPATCH_1(dy_dtype, TIn, VQB_DISPATCH_1(dx_dtype, TOut,
+        (conv_fwd_simt_kernel<TIn, TOut><<<grid, 256, 0, stream>>>((const TIn*)dy, wd, nullptr, (const TOut*)nullptr, (TOut*)dx, g, VQB_ACT_NONE, 0.f, 1.f));))
+    VQB_CHECK_LAUNCH("conv2d_dgrad_simt");
     return VQB_OK;
 }
 

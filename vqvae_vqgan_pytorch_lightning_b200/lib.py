@@ -32,6 +32,16 @@ SIGNATURES = {
     'vqb_conv2d_fwd': (_i, [_i, _p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, _p]),
     'vqb_conv2d_wgrad': (_i, [_i, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     'vqb_set_halo_mode': (None, [_i]),
+    'vqb_conv2d_dgrad': (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    'vqb_fir4_fwd': (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
+    'vqb_fir4_bwd': (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
+    'vqb_maxpool2_fwd': (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
+    'vqb_maxpool2_bwd': (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _i, _p]),
+    'vqb_channel_affine': (_i, [_p, _i, _p, _i, _p, _p, _i64, _i, _p]),
+    'vqb_lpips_tap_fwd': (_i, [_p, _p, _i, _p, _p, _i64, _i, _p]),
+    'vqb_lpips_tap_bwd': (_i, [_p, _p, _i, _p, _p, _f, _p, _i, _i64, _i, _p]),
+    'vqb_mbstd_fwd': (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    'vqb_mbstd_bwd': (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _i, _p]),
     'vqb_colsum': (_i, [_p, _i, _p, _i64, _i, _p]),
     'vqb_gn_stats': (_i, [_p, _i, _p, _i, _i, _i, _i, _p]),
     'vqb_gn_finalize': (_i, [_p, _p, _i, _i, _i, _i, _f, _p]),

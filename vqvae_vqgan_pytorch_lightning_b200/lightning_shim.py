@@ -44,10 +44,11 @@ class LightningModule(_Base):
             opts = self.trainer.optimizers
             return opts if len(opts) > 1 else opts[0]
 
-        def manual_backward(self, loss: torch.Tensor) -> None:
+        def manual_backward(self, loss: torch.Tensor, optimizer=None) -> None:
+            """backward + data-parallel all-reduce of `optimizer`'s gradients (all optimizers when None)"""
             loss.backward()
             if self.trainer is not None:
-                self.trainer.sync_gradients()
+                self.trainer.sync_gradients(optimizer)
 
         # hooks (overridden by the model)
         def on_train_start(self): ...
@@ -88,10 +89,10 @@ class Trainer:
             if t is not None:
                 dist.all_reduce(t, op=dist.ReduceOp.SUM)
 
-    def sync_gradients(self) -> None:
+    def sync_gradients(self, optimizer=None) -> None:
         if self.world_size <= 1:
             return
-        for o in self.optimizers:
+        for o in (self.optimizers if optimizer is None else [optimizer]):
             flat = getattr(o, 'flat_grad', None)
             if flat is not None:
                 dist.all_reduce(flat, op=dist.ReduceOp.SUM)       # one NCCL call per optimizer; averaged in vqb_adamw

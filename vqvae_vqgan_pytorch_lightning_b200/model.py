@@ -16,6 +16,7 @@ from . import ops
 from .lightning_shim import LightningModule
 from .modules.abstract_modules.base_autoencoder import BaseVQVAE
 from .modules.autoencoder import Conv2d, Decoder, Encoder, GroupNorm
+from .modules.loss.loss import VQLPIPS, VQLPIPSWithDiscriminator
 from .modules.vector_quantizers import EMAVectorQuantizer, VectorQuantizer
 from .optim import FusedAdamW
 from .schedulers import CosineScheduler, LinearCosineScheduler, LinearScheduler
@@ -36,9 +37,10 @@ class MSELoss(nn.Module):
 class VQVAE(BaseVQVAE, LightningModule):
 
     def __init__(self, image_size: int, ae_conf: dict, q_conf: dict, l_conf: Optional[dict], t_conf: Optional[dict],
-                 init_cb: bool = True, load_loss: bool = True, fix_param_groups: bool = False):
+                 init_cb: bool = True, load_loss: bool = True, fix_param_groups: bool = False, pretrained_lpips: bool = True):
         """Arguments as in the reference (model.py:25-78).  `fix_param_groups=True` repairs defect B2 (53 encoder
-        tensors never reach the optimizer because of relative-name collisions); the default replicates it."""
+        tensors never reach the optimizer because of relative-name collisions); the default replicates it.
+        `pretrained_lpips=False` keeps the seeded random LPIPS weights (offline parity / benchmark runs)."""
         LightningModule.__init__(self)
         BaseVQVAE.__init__(self, image_size=image_size)
         self.t_conf = t_conf
@@ -81,9 +83,13 @@ class VQVAE(BaseVQVAE, LightningModule):
         if load_loss:
             if l_conf is None:
                 self.criterion = MSELoss()
+            elif l_conf.get('adversarial_params') is None:
+                self.criterion = VQLPIPS(l_conf['l1_weight'], l_conf['l2_weight'], l_conf['perc_weight'],
+                                         net_type=l_conf.get('lpips_net', 'alex'), pretrained_lpips=pretrained_lpips)
             else:
-                raise NotImplementedError('LPIPS / StyleGAN2-discriminator loss heads (loss/loss.py) are the next '
-                                          'rows of the hot-path table; only the MSE branch is built')
+                self.criterion = VQLPIPSWithDiscriminator(image_size, l_conf['l1_weight'], l_conf['l2_weight'],
+                                                          l_conf['perc_weight'], l_conf['adversarial_params'],
+                                                          pretrained_lpips=pretrained_lpips)
         else:
             self.criterion = None
 
@@ -136,15 +142,42 @@ class VQVAE(BaseVQVAE, LightningModule):
 
     # ---- the hot loop body (model.py:232-295) ---------------------------------------------------------
     def training_step(self, batch: Any, batch_index: int):
-        """Branch C (plain VQ-VAE, MSE).  Defect B1 (the reference returns an unbound `loss` here) is fixed by
-        returning ae_loss; logged scalars stay on the device (no per-step host syncs)."""
+        """model.py:232-295.  Branch A = VQGAN (two optimizers, manual optimisation), B = LPIPS only, C = plain MSE.
+        Defect B1 (the reference returns an unbound `loss` outside branch A) is fixed by returning ae_loss; logged
+        scalars stay on the device (the reference does 7 .item() host syncs per step)."""
         images = self.preprocess_batch(batch[0] if isinstance(batch, tuple) else batch, training=True)
         x_recon, q_loss, used_indices = self.forward(images)
-        l2_loss = self.criterion(x_recon, images)
-        ae_loss = q_loss + l2_loss
+        zero = torch.zeros(1, device=images.device)
+        if isinstance(self.criterion, VQLPIPSWithDiscriminator):
+            ae_opt, disc_opt = self.optimizers()
+            ae_opt.zero_grad()
+            res = self.criterion.forward_autoencoder(q_loss, images, x_recon, self.current_epoch,
+                                                     last_layer=self.decoder.conv_out.weight)
+            ae_loss, l1_loss, l2_loss, p_loss, g_loss, g_weight = res
+            self.manual_backward(ae_loss, ae_opt)
+            ae_opt.step()
+            step = (self.current_epoch * self.trainer.num_training_batches) + batch_index
+            loss, d_loss, r1_penalty = self.criterion.forward_discriminator(images, x_recon, self.current_epoch, step)
+            if loss is not None:
+                disc_opt.zero_grad()
+                self.manual_backward(loss, disc_opt)
+                disc_opt.step()
+        elif isinstance(self.criterion, VQLPIPS):
+            ae_loss, l1_loss, l2_loss, p_loss = self.criterion(q_loss, images, x_recon)
+            g_loss, d_loss, g_weight, r1_penalty = zero, zero, 0., 0.
+        else:
+            l2_loss = self.criterion(x_recon, images)
+            l1_loss, g_loss, p_loss, d_loss, g_weight, r1_penalty = zero, zero, zero, zero, 0., 0.
+            ae_loss = q_loss + l2_loss
+        self.log('g_weight', g_weight)
+        self.log('r1_penalty', r1_penalty)
         self.log('train/loss', ae_loss.detach())
+        self.log('train/l1_loss', l1_loss.detach())
         self.log('train/l2_loss', l2_loss.detach())
         self.log('train/quant_loss', q_loss.detach())
+        self.log('train/perc_loss', p_loss.detach())
+        self.log('train/gen_loss', g_loss.detach())
+        self.log('train/disc_loss', d_loss.detach())
         # per-batch code usage (model.py:289-293; defect B3 -- only the last batch is kept -- replicated)
         self.train_epoch_usage_count = torch.bincount(used_indices.view(-1), minlength=self.cb_size)
         return ae_loss
@@ -210,7 +243,14 @@ class VQVAE(BaseVQVAE, LightningModule):
             {'params': [param_dict[pn] for pn in sorted(decay)], 'weight_decay': weight_decay},
             {'params': [param_dict[pn] for pn in sorted(no_decay)], 'weight_decay': 0.0},
         ]
-        return FusedAdamW(groups, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        ae_optimizer = FusedAdamW(groups, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        if isinstance(self.criterion, VQLPIPSWithDiscriminator):
+            # every discriminator tensor decays (model.py:431-433); manual optimisation with two optimizers (:436-438)
+            disc_optimizer = FusedAdamW(list(self.criterion.discriminator.parameters()), lr=lr, betas=betas, eps=eps,
+                                        weight_decay=weight_decay)
+            self.automatic_optimization = False
+            return [ae_optimizer, disc_optimizer], []
+        return ae_optimizer
 
     # ---- two-stage-model API (model.py:458-489) -------------------------------------------------------------
     @torch.no_grad()

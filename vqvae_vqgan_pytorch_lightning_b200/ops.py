@@ -149,7 +149,7 @@ class Conv2dFn(torch.autograd.Function):
     def forward(ctx, x, weight, bias, residual, pad, stride, act, alpha, gain, out_dtype, w_scale):
         prec = get_precision()
         co, ci, kh, kw = weight.shape
-        impl = prec.conv_impl(ci, co, stride)
+        impl = prec.conv_impl(ci, co, stride) if (pad == kh // 2 and kh == kw) else 0
         in_dtype = x.dtype
         if impl == 1:
             cdt = torch.bfloat16
@@ -158,6 +158,9 @@ class Conv2dFn(torch.autograd.Function):
         x = as_nhwc(x, cdt)
         out_dtype = out_dtype or prec.act_dtype
         if residual is not None:
+            if act != ACT_NONE:
+                # the activation derivative is recovered from the saved OUTPUT, which a fused residual would contaminate
+                raise lib.VQBError('conv2d: a fused residual cannot be combined with an activation epilogue')
             residual = as_nhwc(residual, out_dtype)
         wp = _packed_weight(weight, 2 if impl == 1 else 0, torch.bfloat16 if impl == 1 else torch.float32, w_scale)
         b = bias.detach().reshape(-1).float().contiguous() if bias is not None else None
@@ -190,13 +193,17 @@ class Conv2dFn(torch.autograd.Function):
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             if stride != 1:
-                raise lib.VQBError('dgrad for stride != 1 is not implemented')
-            dimpl = prec.conv_impl(co, ci, 1)
-            dyd = as_nhwc(dy, torch.bfloat16) if dimpl == 1 else dy
-            wd = _packed_weight(weight, 3 if dimpl == 1 else 1, torch.bfloat16 if dimpl == 1 else torch.float32, w_scale)
-            # dgrad = correlation of dy with the tap-flipped, channel-swapped weight; padding k-1-pad
-            ddt = in_dtype if (dimpl == 0 or in_dtype == torch.float32) else gdt
-            dx = _conv_fwd_raw(dimpl, dyd, wd, None, None, ddt, co, ci, kh, kw, kh - 1 - pad, 1, ACT_NONE, 0.0, 1.0)
+                # strided forward conv: transposed-conv gather over the (virtually) zero-upsampled dy, fp32 SIMT
+                wd = _packed_weight(weight, 1, torch.float32, w_scale)
+                dx = empty_nhwc(n, ci, h, w, in_dtype if in_dtype in (torch.float32, torch.bfloat16) else gdt, x.device)
+                call('vqb_conv2d_dgrad', ptr(dy), dt(dy), ptr(wd), ptr(dx), dt(dx), n, h, w, ci, co, kh, kw, pad, stride, stream())
+            else:
+                dimpl = prec.conv_impl(co, ci, 1) if kh - 1 - pad == kh // 2 else 0       # tcgen05 path needs a 'same' dgrad
+                dyd = as_nhwc(dy, torch.bfloat16) if dimpl == 1 else dy
+                wd = _packed_weight(weight, 3 if dimpl == 1 else 1, torch.bfloat16 if dimpl == 1 else torch.float32, w_scale)
+                # dgrad = correlation of dy with the tap-flipped, channel-swapped weight; padding k-1-pad
+                ddt = in_dtype if (dimpl == 0 or in_dtype == torch.float32) else gdt
+                dx = _conv_fwd_raw(dimpl, dyd, wd, None, None, ddt, co, ci, kh, kw, kh - 1 - pad, 1, ACT_NONE, 0.0, 1.0)
         if ctx.needs_input_grad[1]:
             wimpl = prec.wgrad_impl(ci, co, stride) if x.dtype == torch.bfloat16 else 0
             dyw = as_nhwc(dy, torch.bfloat16) if wimpl == 1 else dy

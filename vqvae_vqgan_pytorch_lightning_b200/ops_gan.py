@@ -1,0 +1,175 @@
+"""autograd bindings of the loss-head kernels (csrc/gan_ops.cu): FIR resampling, max-pool, z-score, LPIPS taps,
+minibatch stddev, NHWC->flat-NCHW for the discriminator's fully connected layers."""
+from __future__ import annotations
+
+import torch
+
+from . import lib
+from .lib import call, dt, ptr, stream
+from .ops import as_nhwc, empty_nhwc
+
+
+class Fir4Fn(torch.autograd.Function):
+    """upfirdn2d(x, f=[1,3,3,1]^2/64, up=1, down=down, padding=pad)  (ops/upfirdn2d.py:120-208)."""
+
+    @staticmethod
+    def forward(ctx, x, pad, down):
+        x = as_nhwc(x)
+        n, c, h, w = x.shape
+        oh, ow = (h + 2 * pad - 4) // down + 1, (w + 2 * pad - 4) // down + 1
+        y = empty_nhwc(n, c, oh, ow, x.dtype, x.device)
+        call('vqb_fir4_fwd', ptr(x), ptr(y), dt(x), n, h, w, c, pad, down, stream())
+        ctx.cfg = (n, c, h, w, pad, down, x.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        n, c, h, w, pad, down, dtype = ctx.cfg
+        dy = as_nhwc(dy, dtype)
+        dx = empty_nhwc(n, c, h, w, dtype, dy.device)
+        call('vqb_fir4_bwd', ptr(dy), ptr(dx), dt(dy), n, h, w, c, pad, down, stream())
+        return dx, None, None
+
+
+def fir4(x, pad, down=1):
+    return Fir4Fn.apply(x, pad, down)
+
+
+class MaxPool2Fn(torch.autograd.Function):
+    """nn.MaxPool2d(2, 2) of torchvision's VGG16 features."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = as_nhwc(x)
+        n, c, h, w = x.shape
+        y = empty_nhwc(n, c, h // 2, w // 2, x.dtype, x.device)
+        call('vqb_maxpool2_fwd', ptr(x), ptr(y), dt(x), n, h // 2, w // 2, c, stream())
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        n, c, h, w = x.shape
+        dy = as_nhwc(dy)
+        dx = torch.zeros_like(x, dtype=dy.dtype, memory_format=torch.preserve_format) if (h % 2 or w % 2) else \
+            torch.empty_like(x, dtype=dy.dtype, memory_format=torch.preserve_format)
+        call('vqb_maxpool2_bwd', ptr(x), dt(x), ptr(dy), ptr(dx), dt(dy), n, h // 2, w // 2, c, stream())
+        return dx
+
+
+max_pool2 = MaxPool2Fn.apply
+
+
+class ChannelAffineFn(torch.autograd.Function):
+    """y = x * scale[c] + shift[c] (BaseNet.z_score with scale = 1/std, shift = -mean/std)."""
+
+    @staticmethod
+    def forward(ctx, x, scale, shift, out_dtype):
+        x = as_nhwc(x)
+        n, c, h, w = x.shape
+        y = empty_nhwc(n, c, h, w, out_dtype or x.dtype, x.device)
+        call('vqb_channel_affine', ptr(x), dt(x), ptr(y), dt(y), ptr(scale), ptr(shift), n * h * w, c, stream())
+        ctx.save_for_backward(scale)
+        ctx.in_dtype = x.dtype
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (scale,) = ctx.saved_tensors
+        dy = as_nhwc(dy)
+        n, c, h, w = dy.shape
+        dx = empty_nhwc(n, c, h, w, ctx.in_dtype, dy.device)
+        zero = torch.zeros_like(scale)
+        call('vqb_channel_affine', ptr(dy), dt(dy), ptr(dx), dt(dx), ptr(scale), ptr(zero), n * h * w, c, stream())
+        return dx, None, None, None
+
+
+def channel_affine(x, scale, shift, out_dtype=None):
+    return ChannelAffineFn.apply(x, scale, shift, out_dtype)
+
+
+class LpipsTapFn(torch.autograd.Function):
+    """mean over batch of the spatial mean of lin((normalize(fx) - normalize(fy))^2)  (lpips.py:33-37) for ONE tap;
+    differentiable w.r.t. fy (the reconstruction branch) only."""
+
+    @staticmethod
+    def forward(ctx, fx, fy, w):
+        fx, fy = as_nhwc(fx), as_nhwc(fy)
+        if fx.dtype != fy.dtype:
+            fx = as_nhwc(fx, fy.dtype)
+        n, c, h, wd = fy.shape
+        out = torch.zeros(1, dtype=torch.float64, device=fy.device)
+        wv = w.detach().reshape(-1).float().contiguous()
+        call('vqb_lpips_tap_fwd', ptr(fx), ptr(fy), dt(fy), ptr(wv), ptr(out), n * h * wd, c, stream())
+        ctx.save_for_backward(fx, fy, wv)
+        return (out[0] / (n * h * wd)).float()
+
+    @staticmethod
+    def backward(ctx, g):
+        fx, fy, wv = ctx.saved_tensors
+        n, c, h, wd = fy.shape
+        up = g.reshape(1).float().contiguous()
+        dfy = torch.empty_like(fy, memory_format=torch.preserve_format)
+        call('vqb_lpips_tap_bwd', ptr(fx), ptr(fy), dt(fy), ptr(wv), ptr(up), 1.0 / (n * h * wd), ptr(dfy), dt(dfy), n * h * wd, c,
+             stream())
+        return None, dfy, None
+
+
+lpips_tap = LpipsTapFn.apply
+
+
+class MbstdFn(torch.autograd.Function):
+    """MinibatchStdLayer(group_size, num_channels=1)  (discriminator.py:277-293)."""
+
+    @staticmethod
+    def forward(ctx, x, group_size):
+        x = as_nhwc(x)
+        n, c, h, w = x.shape
+        g = min(group_size, n) if group_size is not None else n
+        if n % g:
+            raise lib.VQBError(f'minibatch-stddev needs the batch ({n}) to be a multiple of the group size ({g})')
+        y = empty_nhwc(n, c + 1, h, w, x.dtype, x.device)
+        stat = torch.empty(n // g, dtype=torch.float32, device=x.device)
+        call('vqb_mbstd_fwd', ptr(x), ptr(y), ptr(stat), dt(x), n, g, h * w, c, stream())
+        ctx.save_for_backward(x)
+        ctx.g = g
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        n, c, h, w = x.shape
+        dy = as_nhwc(dy)
+        dx = torch.empty_like(x, dtype=dy.dtype, memory_format=torch.preserve_format)
+        call('vqb_mbstd_bwd', ptr(x), dt(x), ptr(dy), ptr(dx), dt(dy), n, ctx.g, h * w, c, stream())
+        return dx, None
+
+
+def mbstd(x, group_size=4):
+    return MbstdFn.apply(x, group_size)
+
+
+class FlattenNCHWFn(torch.autograd.Function):
+    """x.flatten(1) of an NCHW tensor (discriminator.py:347) for a channels-last input: NHWC -> [N, C*H*W] in (c,h,w) order,
+    returned as a channels-last [N, C*H*W, 1, 1] fp32 tensor so that the FC layer is a 1x1 implicit GEMM."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = as_nhwc(x)
+        n, c, h, w = x.shape
+        out = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+        call('vqb_nhwc_to_nchw', ptr(x), dt(x), ptr(out), n, c, h, w, 1.0, 0.0, 0, 0.0, 0.0, stream())
+        ctx.cfg = (n, c, h, w, x.dtype)
+        return out.reshape(n, c * h * w, 1, 1)
+
+    @staticmethod
+    def backward(ctx, dy):
+        n, c, h, w, dtype = ctx.cfg
+        g = dy.reshape(n, c, h, w).float().contiguous()
+        dx = empty_nhwc(n, c, h, w, dtype, dy.device)
+        call('vqb_nchw_to_nhwc', ptr(g), ptr(dx), dt(dx), n, c, h, w, 0, 0.0, 0.0, 0.0, 1.0, stream())
+        return dx
+
+
+flatten_nchw = FlattenNCHWFn.apply
