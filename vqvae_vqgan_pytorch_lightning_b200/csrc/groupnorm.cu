@@ -3,26 +3,39 @@
 // HBM-bound.  Forward = one statistics pass (read x) + one apply pass (read x, write y).  Backward = one
 // reduction pass (read x, dy) + one apply pass (read x, dy, write dx).  Thread mapping: threadIdx.x owns VEC
 // consecutive channels (fixed for the whole kernel, so per-channel parameters live in registers and global
-// loads of one pixel row are fully coalesced), threadIdx.y strides over pixels.  Partial sums are fp32 over
-// <= 32 pixels per thread, then promoted to double for the block / grid combine (E[x^2]-mu^2 is evaluated in
-// double, so there is no catastrophic cancellation at n = 4*65536 elements per group).
+// loads of one pixel row are fully coalesced 16-byte accesses: VEC = 8 for bf16 / wide layers), threadIdx.y strides
+// over pixels with a 2-deep unrolled loop (two independent 16-byte loads in flight per thread).  Partial sums are
+// fp32 over <= 32 pixels per thread, then promoted to double for the block / grid combine (E[x^2]-mu^2 is
+// evaluated in double, so there is no catastrophic cancellation at n = 4*65536 elements per group).
 #include "common.cuh"
 
 namespace {
+
+// sigmoid via MUFU ex2 + fast reciprocal: ~1e-6 relative error, a fraction of the instruction count of expf + IEEE division
+__device__ __forceinline__ float fast_sigmoid(float t) { return __fdividef(1.0f, 1.0f + __expf(-t)); }
+__device__ __forceinline__ float fast_silu(float t) { return t * fast_sigmoid(t); }
+__device__ __forceinline__ float fast_silu_grad(float t) { float s = fast_sigmoid(t); return s * fmaf(t, 1.0f - s, 1.0f); }
 
 struct GnLaunch {
     dim3 grid, block;
     int vec, ppb;
 };
 
-inline GnLaunch gn_launch(int N, int HW, int C, int G) {
+inline int gn_vec(int C, int G) {
+    const int cg = C / G;
+    if (C % 8 == 0 && cg % 4 == 0 && C / 8 <= 1024) return 8;   // each 4-channel half stays inside one group
+    if (C % 4 == 0 && cg % 4 == 0 && C / 4 >= G) return 4;
+    return 1;
+}
+
+inline GnLaunch gn_launch(int N, int HW, int C, int G, int pix_per_thread = 32) {
     GnLaunch L;
-    L.vec = (C % 4 == 0 && (C / G) % 4 == 0 && C / 4 >= G) ? 4 : 1;   // VEC=4 keeps a float4 inside one group
+    L.vec = gn_vec(C, G);
     int tx = C / L.vec;
     int ty = 256 / tx; if (ty < 1) ty = 1;
     if (ty > 32) ty = 32;
     L.block = dim3(tx, ty);
-    L.ppb = ty * 32;                   // pixels per block: 32 per thread row
+    L.ppb = ty * pix_per_thread;       // pixels per block (reductions use more: fewer double atomics per byte read)
     if (L.ppb > HW) L.ppb = ((HW + ty - 1) / ty) * ty;
     L.grid = dim3((HW + L.ppb - 1) / L.ppb, N);
     return L;
@@ -30,49 +43,82 @@ inline GnLaunch gn_launch(int N, int HW, int C, int G) {
 
 template <typename T, int VEC>
 __device__ __forceinline__ void ldv(const T* p, float (&v)[VEC]) {
-    if (VEC == 4) { float4 t = ld4(p); v[0] = t.x; v[1 % VEC] = t.y; v[2 % VEC] = t.z; v[3 % VEC] = t.w; }
-    else v[0] = ld1(p);
+    if constexpr (VEC == 8) {
+        if constexpr (sizeof(T) == 2) {
+            uint4 u = *reinterpret_cast<const uint4*>(p);
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+        } else {
+            float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        }
+    } else if constexpr (VEC == 4) {
+        float4 t = ld4(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+        v[0] = ld1(p);
+    }
 }
 template <typename T, int VEC>
 __device__ __forceinline__ void stv(T* p, const float (&v)[VEC]) {
-    if (VEC == 4) st4(p, make_float4(v[0], v[1 % VEC], v[2 % VEC], v[3 % VEC]));
-    else st1(p, v[0]);
+    if constexpr (VEC == 8) {
+        if constexpr (sizeof(T) == 2) {
+            uint4 u;
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            *reinterpret_cast<uint4*>(p) = u;
+        } else {
+            *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        }
+    } else if constexpr (VEC == 4) {
+        st4(p, make_float4(v[0], v[1], v[2], v[3]));
+    } else {
+        st1(p, v[0]);
+    }
 }
 
 // ---- forward statistics ---------------------------------------------------------------------------
+// accumulation unit = UNIT consecutive channels (4 when VEC >= 4, else 1); a group is C/G/UNIT units
 template <typename T, int VEC>
 __global__ void gn_stats_kernel(const T* __restrict__ x, double* __restrict__ sums, int HW, int C, int G, int ppb) {
-    extern __shared__ double sh[];   // [2][blockDim.y][blockDim.x]
+    constexpr int UNIT = (VEC >= 4) ? 4 : 1;
+    constexpr int NU = VEC / UNIT;
+    extern __shared__ double sh[];   // [2][blockDim.y][blockDim.x * NU]
     const int b = blockIdx.y;
     const int c0 = threadIdx.x * VEC;
     const int p0 = blockIdx.x * ppb;
     int p1 = p0 + ppb; if (p1 > HW) p1 = HW;
-    float s = 0.f, ss = 0.f;
+    float s[NU], ss[NU];
+#pragma unroll
+    for (int u = 0; u < NU; ++u) { s[u] = 0.f; ss[u] = 0.f; }
     const T* xb = x + (int64_t)b * HW * C + c0;
+#pragma unroll 2
     for (int p = p0 + threadIdx.y; p < p1; p += blockDim.y) {
         float v[VEC];
         ldv<T, VEC>(xb + (int64_t)p * C, v);
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) { s += v[j]; ss += v[j] * v[j]; }
+        for (int j = 0; j < VEC; ++j) { s[j / UNIT] += v[j]; ss[j / UNIT] = fmaf(v[j], v[j], ss[j / UNIT]); }
     }
-    const int tx = blockDim.x, ty = blockDim.y;
-    sh[threadIdx.y * tx + threadIdx.x] = (double)s;
-    sh[(ty + threadIdx.y) * tx + threadIdx.x] = (double)ss;
+    const int tx = blockDim.x, ty = blockDim.y, row = tx * NU;
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+        sh[threadIdx.y * row + threadIdx.x * NU + u] = (double)s[u];
+        sh[(ty + threadIdx.y) * row + threadIdx.x * NU + u] = (double)ss[u];
+    }
     __syncthreads();
     const int tid = threadIdx.y * tx + threadIdx.x;
-    const int cg = C / G;                         // channels per group
-    const int tpg = (cg >= VEC) ? cg / VEC : 1;   // threads (in x) per group
-    const int gpt = (cg >= VEC) ? 1 : VEC / cg;   // groups per thread (only when VEC=1 -> 1)
-    (void)gpt;
-    if (tid < G) {
+    const int upg = (C / G) / UNIT;               // units per group
+    for (int g = tid; g < G; g += tx * ty) {
         double a = 0.0, q = 0.0;
         for (int y = 0; y < ty; ++y)
-            for (int t = 0; t < tpg; ++t) {
-                a += sh[y * tx + tid * tpg + t];
-                q += sh[(ty + y) * tx + tid * tpg + t];
+            for (int t = 0; t < upg; ++t) {
+                a += sh[y * row + g * upg + t];
+                q += sh[(ty + y) * row + g * upg + t];
             }
-        atomicAdd(&sums[((int64_t)b * G + tid) * 2 + 0], a);
-        atomicAdd(&sums[((int64_t)b * G + tid) * 2 + 1], q);
+        atomicAdd(&sums[((int64_t)b * G + g) * 2 + 0], a);
+        atomicAdd(&sums[((int64_t)b * G + g) * 2 + 1], q);
     }
 }
 
@@ -94,25 +140,26 @@ __global__ void gn_apply_kernel(const TI* __restrict__ x, const float* __restric
     const int b = blockIdx.y;
     const int c0 = threadIdx.x * VEC;
     const int cg = C / G;
-    float mean[VEC], rstd[VEC], ga[VEC], be[VEC];
+    float sc[VEC], sh_[VEC];          // y = x * sc + sh_  with sc = rstd*gamma, sh_ = beta - mean*rstd*gamma
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
         int g = (c0 + j) / cg;
-        mean[j] = stats[((int64_t)b * G + g) * 2];
-        rstd[j] = stats[((int64_t)b * G + g) * 2 + 1];
-        ga[j] = gamma[c0 + j];
-        be[j] = beta[c0 + j];
+        float mean = stats[((int64_t)b * G + g) * 2];
+        float rstd = stats[((int64_t)b * G + g) * 2 + 1];
+        sc[j] = rstd * gamma[c0 + j];
+        sh_[j] = beta[c0 + j] - mean * sc[j];
     }
     const int p0 = blockIdx.x * ppb;
     int p1 = p0 + ppb; if (p1 > HW) p1 = HW;
     const int64_t base = (int64_t)b * HW * C + c0;
+#pragma unroll 2
     for (int p = p0 + threadIdx.y; p < p1; p += blockDim.y) {
         float v[VEC], o[VEC];
         ldv<TI, VEC>(x + base + (int64_t)p * C, v);
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
-            float t = (v[j] - mean[j]) * rstd[j] * ga[j] + be[j];
-            o[j] = (act == VQB_ACT_SILU) ? silu_f(t) : t;
+            float t = fmaf(v[j], sc[j], sh_[j]);
+            o[j] = (act == VQB_ACT_SILU) ? fast_silu(t) : t;
         }
         stv<TO, VEC>(y + base + (int64_t)p * C, o);
     }
@@ -127,32 +174,34 @@ __global__ void gn_bwd_reduce_kernel(const TI* __restrict__ x, const TG* __restr
     const int b = blockIdx.y;
     const int c0 = threadIdx.x * VEC;
     const int cg = C / G;
-    float mean[VEC], rstd[VEC], ga[VEC], be[VEC], a[VEC], q[VEC];
+    float mean[VEC], rstd[VEC], sc[VEC], sf[VEC], a[VEC], q[VEC];      // t = x*sc + sf is the pre-activation
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
         int g = (c0 + j) / cg;
         mean[j] = stats[((int64_t)b * G + g) * 2];
         rstd[j] = stats[((int64_t)b * G + g) * 2 + 1];
-        ga[j] = gamma[c0 + j];
-        be[j] = beta[c0 + j];
+        sc[j] = rstd[j] * gamma[c0 + j];
+        sf[j] = beta[c0 + j] - mean[j] * sc[j];
         a[j] = 0.f; q[j] = 0.f;
     }
     const int p0 = blockIdx.x * ppb;
     int p1 = p0 + ppb; if (p1 > HW) p1 = HW;
     const int64_t base = (int64_t)b * HW * C + c0;
+#pragma unroll 2
     for (int p = p0 + threadIdx.y; p < p1; p += blockDim.y) {
         float v[VEC], g[VEC];
         ldv<TI, VEC>(x + base + (int64_t)p * C, v);
         ldv<TG, VEC>(dy + base + (int64_t)p * C, g);
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
-            float xh = (v[j] - mean[j]) * rstd[j];
             float ds = g[j];
-            if (act == VQB_ACT_SILU) ds *= silu_grad_f(xh * ga[j] + be[j]);
+            if (act == VQB_ACT_SILU) ds *= fast_silu_grad(fmaf(v[j], sc[j], sf[j]));
             a[j] += ds;
-            q[j] += ds * xh;
+            q[j] = fmaf(ds, v[j], q[j]);             // sum ds*x; converted to sum ds*xhat below
         }
     }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) q[j] = rstd[j] * (q[j] - mean[j] * a[j]);
     const int tx = blockDim.x, ty = blockDim.y, row = tx * VEC;
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
@@ -205,30 +254,33 @@ __global__ void gn_bwd_apply_kernel(const TI* __restrict__ x, const TG* __restri
     const int b = blockIdx.y;
     const int c0 = threadIdx.x * VEC;
     const int cg = C / G;
-    float mean[VEC], rstd[VEC], ga[VEC], be[VEC], k1[VEC], k2[VEC];
+    float sc[VEC], sf[VEC], ca[VEC], cb[VEC], cc[VEC];       // dx = ds*ca + x*cb + cc
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
         int g = (c0 + j) / cg;
-        mean[j] = stats[((int64_t)b * G + g) * 2];
-        rstd[j] = stats[((int64_t)b * G + g) * 2 + 1];
-        k1[j] = coef[((int64_t)b * G + g) * 2];
-        k2[j] = coef[((int64_t)b * G + g) * 2 + 1];
-        ga[j] = gamma[c0 + j];
-        be[j] = beta[c0 + j];
+        const float mean = stats[((int64_t)b * G + g) * 2];
+        const float rstd = stats[((int64_t)b * G + g) * 2 + 1];
+        const float k1 = coef[((int64_t)b * G + g) * 2];
+        const float k2 = coef[((int64_t)b * G + g) * 2 + 1];
+        sc[j] = rstd * gamma[c0 + j];
+        sf[j] = beta[c0 + j] - mean * sc[j];
+        ca[j] = sc[j];                                    // rstd * gamma
+        cb[j] = -rstd * rstd * k2;                        // -(x-mean)*rstd^2*k2
+        cc[j] = -rstd * k1 - mean * cb[j];
     }
     const int p0 = blockIdx.x * ppb;
     int p1 = p0 + ppb; if (p1 > HW) p1 = HW;
     const int64_t base = (int64_t)b * HW * C + c0;
+#pragma unroll 2
     for (int p = p0 + threadIdx.y; p < p1; p += blockDim.y) {
         float v[VEC], g[VEC], o[VEC];
         ldv<TI, VEC>(x + base + (int64_t)p * C, v);
         ldv<TG, VEC>(dy + base + (int64_t)p * C, g);
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
-            float xh = (v[j] - mean[j]) * rstd[j];
             float ds = g[j];
-            if (act == VQB_ACT_SILU) ds *= silu_grad_f(xh * ga[j] + be[j]);
-            o[j] = rstd[j] * (ds * ga[j] - k1[j] - xh * k2[j]);
+            if (act == VQB_ACT_SILU) ds *= fast_silu_grad(fmaf(v[j], sc[j], sf[j]));
+            o[j] = fmaf(ds, ca[j], fmaf(v[j], cb[j], cc[j]));
         }
         stv<TO, VEC>(dx + base + (int64_t)p * C, o);
     }
@@ -239,23 +291,24 @@ inline int gn_check(const char* name, int N, int HW, int C, int G) {
         vqb_set_error("%s: bad shape N=%d HW=%d C=%d G=%d", name, N, HW, C, G);
         return VQB_ERR_ARG;
     }
-    { int vec = (C % 4 == 0 && (C / G) % 4 == 0 && C / 4 >= G) ? 4 : 1;
-      if (C / vec > 1024) { vqb_set_error("%s: C=%d too large", name, C); return VQB_ERR_UNSUPPORTED; } }
+    if (C / gn_vec(C, G) > 1024) { vqb_set_error("%s: C=%d too large", name, C); return VQB_ERR_UNSUPPORTED; }
     if ((double)(C / G) * HW < 2.0) { vqb_set_error("%s: unbiased variance needs >= 2 elements per group", name); return VQB_ERR_ARG; }
     return VQB_OK;
 }
 
 }  // namespace
 
-#define GN_VEC_DISPATCH(L, ...) \
-    if ((L).vec == 4) { constexpr int VEC = 4; __VA_ARGS__ } else { constexpr int VEC = 1; __VA_ARGS__ }
+#define GN_VEC_DISPATCH(L, ...)                                     \
+    if ((L).vec == 8) { constexpr int VEC = 8; __VA_ARGS__ }        \
+    else if ((L).vec == 4) { constexpr int VEC = 4; __VA_ARGS__ }   \
+    else { constexpr int VEC = 1; __VA_ARGS__ }
 
 extern "C" int vqb_gn_stats(const void* x, int x_dtype, double* sums, int N, int HW, int C, int G, void* stream) {
     int rc = gn_check("gn_stats", N, HW, C, G); if (rc) return rc;
     VQB_CHECK_ARG(x && sums, "gn_stats: null pointer");
-    GnLaunch L = gn_launch(N, HW, C, G);
-    VQB_CHECK_ARG((int)(L.block.x * L.block.y) >= G, "gn_stats: block smaller than group count");
-    size_t sm = 2 * sizeof(double) * L.block.x * L.block.y;
+    GnLaunch L = gn_launch(N, HW, C, G, 128);
+    const int nu = (L.vec >= 4) ? L.vec / 4 : 1;
+    size_t sm = 2 * sizeof(double) * L.block.x * L.block.y * nu;
     GN_VEC_DISPATCH(L, VQB_DISPATCH_1(x_dtype, T, (gn_stats_kernel<T, VEC><<<L.grid, L.block, sm, as_stream(stream)>>>(
                                                       (const T*)x, sums, HW, C, G, L.ppb));))
     VQB_CHECK_LAUNCH("gn_stats");
@@ -288,7 +341,7 @@ extern "C" int vqb_gn_bwd_reduce(const void* x, int x_dtype, const void* dy, int
                                  void* stream) {
     int rc = gn_check("gn_bwd_reduce", N, HW, C, G); if (rc) return rc;
     VQB_CHECK_ARG(x && dy && stats && gamma && beta && part, "gn_bwd_reduce: null pointer");
-    GnLaunch L = gn_launch(N, HW, C, G);
+    GnLaunch L = gn_launch(N, HW, C, G, 128);
     size_t sm = 2 * sizeof(double) * L.block.x * L.block.y * L.vec;
     GN_VEC_DISPATCH(L, VQB_DISPATCH_1(x_dtype, TI, VQB_DISPATCH_1(dy_dtype, TG,
         (gn_bwd_reduce_kernel<TI, TG, VEC><<<L.grid, L.block, sm, as_stream(stream)>>>((const TI*)x, (const TG*)dy, stats, gamma, beta, part, HW, C, G, L.ppb, act));)))
