@@ -28,9 +28,10 @@ inline int gn_vec(int C, int G) {
     return 1;
 }
 
-inline GnLaunch gn_launch(int N, int HW, int C, int G, int pix_per_thread = 32) {
+inline GnLaunch gn_launch(int N, int HW, int C, int G, int pix_per_thread = 32, int max_vec = 8) {
     GnLaunch L;
     L.vec = gn_vec(C, G);
+    if (L.vec > max_vec) L.vec = max_vec;     // cg % 4 == 0 holds whenever gn_vec returned 8, so 4 is valid too
     int tx = C / L.vec;
     int ty = 256 / tx; if (ty < 1) ty = 1;
     if (ty > 32) ty = 32;
@@ -174,20 +175,20 @@ __global__ void gn_bwd_reduce_kernel(const TI* __restrict__ x, const TG* __restr
     const int b = blockIdx.y;
     const int c0 = threadIdx.x * VEC;
     const int cg = C / G;
-    float mean[VEC], rstd[VEC], sc[VEC], sf[VEC], a[VEC], q[VEC];      // t = x*sc + sf is the pre-activation
+    float sc[VEC], sf[VEC], a[VEC], q[VEC];      // t = x*sc + sf is the pre-activation
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
         int g = (c0 + j) / cg;
-        mean[j] = stats[((int64_t)b * G + g) * 2];
-        rstd[j] = stats[((int64_t)b * G + g) * 2 + 1];
-        sc[j] = rstd[j] * gamma[c0 + j];
-        sf[j] = beta[c0 + j] - mean[j] * sc[j];
+        const float mean = stats[((int64_t)b * G + g) * 2];
+        const float rstd = stats[((int64_t)b * G + g) * 2 + 1];
+        sc[j] = rstd * gamma[c0 + j];
+        sf[j] = beta[c0 + j] - mean * sc[j];
         a[j] = 0.f; q[j] = 0.f;
     }
     const int p0 = blockIdx.x * ppb;
     int p1 = p0 + ppb; if (p1 > HW) p1 = HW;
     const int64_t base = (int64_t)b * HW * C + c0;
-#pragma unroll 2
+#pragma unroll 4
     for (int p = p0 + threadIdx.y; p < p1; p += blockDim.y) {
         float v[VEC], g[VEC];
         ldv<TI, VEC>(x + base + (int64_t)p * C, v);
@@ -201,7 +202,12 @@ __global__ void gn_bwd_reduce_kernel(const TI* __restrict__ x, const TG* __restr
         }
     }
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) q[j] = rstd[j] * (q[j] - mean[j] * a[j]);
+    for (int j = 0; j < VEC; ++j) {
+        int g = (c0 + j) / cg;
+        const float mean = stats[((int64_t)b * G + g) * 2];
+        const float rstd = stats[((int64_t)b * G + g) * 2 + 1];
+        q[j] = rstd * (q[j] - mean * a[j]);
+    }
     const int tx = blockDim.x, ty = blockDim.y, row = tx * VEC;
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
@@ -306,7 +312,7 @@ inline int gn_check(const char* name, int N, int HW, int C, int G) {
 extern "C" int vqb_gn_stats(const void* x, int x_dtype, double* sums, int N, int HW, int C, int G, void* stream) {
     int rc = gn_check("gn_stats", N, HW, C, G); if (rc) return rc;
     VQB_CHECK_ARG(x && sums, "gn_stats: null pointer");
-    GnLaunch L = gn_launch(N, HW, C, G, 128);
+    GnLaunch L = gn_launch(N, HW, C, G, 32);
     const int nu = (L.vec >= 4) ? L.vec / 4 : 1;
     size_t sm = 2 * sizeof(double) * L.block.x * L.block.y * nu;
     GN_VEC_DISPATCH(L, VQB_DISPATCH_1(x_dtype, T, (gn_stats_kernel<T, VEC><<<L.grid, L.block, sm, as_stream(stream)>>>(
@@ -341,7 +347,7 @@ extern "C" int vqb_gn_bwd_reduce(const void* x, int x_dtype, const void* dy, int
                                  void* stream) {
     int rc = gn_check("gn_bwd_reduce", N, HW, C, G); if (rc) return rc;
     VQB_CHECK_ARG(x && dy && stats && gamma && beta && part, "gn_bwd_reduce: null pointer");
-    GnLaunch L = gn_launch(N, HW, C, G, 128);
+    GnLaunch L = gn_launch(N, HW, C, G, 32, 4);      // 4 channels per thread: fewer live registers -> more warps to hide latency
     size_t sm = 2 * sizeof(double) * L.block.x * L.block.y * L.vec;
     GN_VEC_DISPATCH(L, VQB_DISPATCH_1(x_dtype, TI, VQB_DISPATCH_1(dy_dtype, TG,
         (gn_bwd_reduce_kernel<TI, TG, VEC><<<L.grid, L.block, sm, as_stream(stream)>>>((const TI*)x, (const TG*)dy, stats, gamma, beta, part, HW, C, G, L.ppb, act));)))
