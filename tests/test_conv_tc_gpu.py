@@ -41,6 +41,8 @@ CASES = [
     (2, 12, 20, 64, 128, 3, False, False, 0),       # H, W not powers of two: partially out-of-bounds boxes
     (1, 64, 64, 128, 128, 3, False, False, 0),
     (2, 16, 16, 512, 512, 3, False, False, 0),      # two Co tiles, 72 k-steps (pipeline wrap-around)
+    (2, 40, 20, 128, 128, 3, True, True, 0),        # swapped-operand kernel (M = co, N = 256 pixels), ragged 32x8 tiles
+    (1, 33, 9, 256, 128, 3, False, True, 0),
     (2, 32, 32, 128, 3, 3, True, False, 1),         # narrow head (decoder.conv_out): UMMA N=16, tanh epilogue
 ]
 

@@ -47,3 +47,12 @@ print(f'step {total:.2f} ms; sum of timed calls {sum(r[1] for _, r in rows) / a.
 for k, (cnt, ms, fl) in rows[:a.top]:
     tf = fl / (ms / 1e3) / 1e12 if fl else 0
     print(f'{ms / a.steps:9.3f} ms  {cnt // a.steps:4d} calls  {tf:7.1f} TF/s  {k}')
+# ---- CPU enqueue time per step (no device sync inside) ----
+import time
+pkg.lib.timer = None
+torch.cuda.synchronize()
+ts = []
+for i in range(3):
+    t0 = time.perf_counter(); tr.run_step(x, 10 + i); t1 = time.perf_counter(); torch.cuda.synchronize(); t2 = time.perf_counter()
+    ts.append(((t1 - t0) * 1e3, (t2 - t0) * 1e3))
+print('CPU enqueue ms / total ms per step:', ['%.1f / %.1f' % t for t in ts], 'launches/step', pkg.lib.launch_count // (2 + a.steps + 3))

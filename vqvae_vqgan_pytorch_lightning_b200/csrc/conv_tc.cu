@@ -31,7 +31,9 @@ namespace {
 constexpr int BM = 128;          // UMMA M (pixels for fwd, co for wgrad)
 constexpr int BK = 64;           // K elements per pipeline stage (one 128-byte swizzle row of bf16)
 constexpr int UMMA_K = 16;
-constexpr int NTHREADS = 192;    // 6 warps: TMA, MMA, 4 x epilogue
+constexpr int NTHREADS = 192;      // wgrad kernels: 6 warps (TMA, MMA, 4 x epilogue)
+constexpr int NTHREADS_FWD = 320;  // forward kernels: 10 warps (TMA, MMA, 8 x epilogue -- two warps per TMEM lane quarter,
+                                   // alternating 32-column chunks; the epilogue paces the 128-channel layers)
 constexpr int SMEM_LIMIT = 227 * 1024;
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -179,6 +181,7 @@ __device__ __forceinline__ void epilogue_chunk(const FwdParams& p, const uint32_
 // epilogue warps of both forward kernels: drain the MT sub-tile accumulators of every tile this CTA owns
 __device__ __forceinline__ void epilogue_loop(const FwdParams& p, uint32_t tmem_base, uint64_t* tfull, uint64_t* tempty, int warp, int lane) {
     const int quarter = warp & 3;                    // TMEM lane quarter this warp may read
+    const int half = (warp - 2) >> 2;                // two warps per quarter take alternating 32-column chunks
     const int row = quarter * 32 + lane;
     const int wi = row % p.tw, r2 = row / p.tw, hi = r2 % p.th, ni = r2 / p.th;
     int as = 0; uint32_t aphase = 0;
@@ -194,7 +197,7 @@ __device__ __forceinline__ void epilogue_loop(const FwdParams& p, uint32_t tmem_
             const bool valid = (w < p.W) && (h < p.H) && (n < p.N);
             const int64_t pix = ((int64_t)n * p.H + h) * p.W + w;
             const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((as * p.MT + m) * p.BN);
-            for (int c = 0; c < p.BN; c += 32) {
+            for (int c = half * 32; c < p.BN; c += 64) {
                 uint32_t r[32];
                 ptx::tmem_ld32(t_addr + (uint32_t)c, r);
                 ptx::tmem_ld_wait();
@@ -211,7 +214,7 @@ __device__ __forceinline__ void epilogue_loop(const FwdParams& p, uint32_t tmem_
 // ---------------------------------------------------------------------------------------------------
 // generic forward kernel
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(NTHREADS_FWD, 1)
 conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const FwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -231,7 +234,7 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         ptx::prefetch_tmap(&tmA);
         ptx::prefetch_tmap(&tmB);
         for (int i = 0; i < p.stages; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull[i], 1); ptx::mbar_init(&tempty[i], 4); }
+        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull[i], 1); ptx::mbar_init(&tempty[i], 8); }
         ptx::fence_barrier_init();
     }
     if (warp == 1) ptx::tmem_alloc(tmem_slot, 512);
@@ -310,7 +313,7 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 // ---------------------------------------------------------------------------------------------------
 // 3x3 forward kernel with halo reuse (tw = 8, th = 16): one A load per channel chunk serves nine taps
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(NTHREADS_FWD, 1)
 conv_fwd_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const FwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -335,7 +338,7 @@ conv_fwd_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         ptx::prefetch_tmap(&tmB);
         for (int i = 0; i < p.a_stages; ++i) { ptx::mbar_init(&fullA[i], 1); ptx::mbar_init(&emptyA[i], 1); }
         for (int i = 0; i < p.b_stages; ++i) { ptx::mbar_init(&fullB[i], 1); ptx::mbar_init(&emptyB[i], 1); }
-        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull[i], 1); ptx::mbar_init(&tempty[i], 4); }
+        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull[i], 1); ptx::mbar_init(&tempty[i], 8); }
         ptx::fence_barrier_init();
     }
     if (warp == 1) ptx::tmem_alloc(tmem_slot, 512);
@@ -410,6 +413,181 @@ conv_fwd_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         }
     } else {
         epilogue_loop(p, tmem_base, tfull, tempty, warp, lane);
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// 3x3 forward kernel for Co tiles of 128 with the operand roles swapped: M = 128 output channels (the packed weight tile is
+// the A operand), N = 256 pixels (a 32 x 8 pixel tile; ONE halo box {64 ch, 10, 34} per channel chunk is the B operand of
+// all nine taps).  With N = 128 the UMMA reads 8 KB of shared memory per 64 cycles -- exactly the 128 B/clk SMEM port, so
+// the 128-channel layers were SMEM-bandwidth-bound at ~800 TFLOP/s; N = 256 needs 12 KB per 128 cycles.  The accumulator
+// is D^T [co lanes][pixel columns]; the epilogue writes one pixel per instruction with the warp's 32 lanes covering 32
+// consecutive channels (64-byte coalesced segments).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NTHREADS_FWD, 1)
+conv_fwd_tc_halo_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const FwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    constexpr int TH = 32, TW = 8, PITCH = 10, NPIX = 256;
+    const int x_stage = p.a_tile_bytes;               // (TH+2) x PITCH rows of 128 B, rounded up to 1024
+    const int w_stage = BM * BK * 2;                  // 16 KB weight tile (128 co x 64 ci)
+    uint8_t* smemX = smem;
+    uint8_t* smemW = smem + (size_t)p.a_stages * x_stage;
+    uint64_t* fullX = reinterpret_cast<uint64_t*>(smemW + (size_t)p.b_stages * w_stage);
+    uint64_t* emptyX = fullX + p.a_stages;
+    uint64_t* fullW = emptyX + p.a_stages;
+    uint64_t* emptyW = fullW + p.b_stages;
+    uint64_t* tfull = emptyW + p.b_stages;           // [2]
+    uint64_t* tempty = tfull + 2;                    // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t x_box_bytes = (uint32_t)((TH + 2) * PITCH * 128);
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmX);
+        ptx::prefetch_tmap(&tmW);
+        for (int i = 0; i < p.a_stages; ++i) { ptx::mbar_init(&fullX[i], 1); ptx::mbar_init(&emptyX[i], 1); }
+        for (int i = 0; i < p.b_stages; ++i) { ptx::mbar_init(&fullW[i], 1); ptx::mbar_init(&emptyW[i], 1); }
+        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull[i], 1); ptx::mbar_init(&tempty[i], 8); }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int sx = 0, sw = 0; uint32_t px = 0, pw = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int ct = tile % p.co_tiles, pt = tile / p.co_tiles;
+                const int twi = pt % p.tiles_w, t2 = pt / p.tiles_w, thi = t2 % p.tiles_h, n = t2 / p.tiles_h;
+                const int w0 = twi * TW, h0 = thi * TH, co0 = ct * BM;
+                for (int cc = 0; cc < p.cchunks; ++cc) {
+                    ptx::mbar_wait(&emptyX[sx], px ^ 1);
+                    ptx::mbar_expect_tx(&fullX[sx], x_box_bytes);
+                    ptx::tma_load_4d(smemX + (size_t)sx * x_stage, &tmX, &fullX[sx], cc * BK, w0 - 1, h0 - 1, n);
+                    if (++sx == p.a_stages) { sx = 0; px ^= 1; }
+                    for (int tap = 0; tap < 9; ++tap) {
+                        ptx::mbar_wait(&emptyW[sw], pw ^ 1);
+                        ptx::mbar_expect_tx(&fullW[sw], (uint32_t)w_stage);
+                        ptx::tma_load_2d(smemW + (size_t)sw * w_stage, &tmW, &fullW[sw], tap * p.Ci + cc * BK, co0);
+                        if (++sw == p.b_stages) { sw = 0; pw ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = ptx::umma_idesc_bf16(BM, NPIX, 0, 0);
+            int sx = 0, sw = 0; uint32_t px = 0, pw = 0;
+            int as = 0; uint32_t aphase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                ptx::mbar_wait(&tempty[as], aphase ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * NPIX);
+                for (int cc = 0; cc < p.cchunks; ++cc) {
+                    ptx::mbar_wait(&fullX[sx], px);
+                    const uint32_t x_addr = ptx::smem_u32(smemX + (size_t)sx * x_stage);
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const int kh = tap / 3, kw = tap - kh * 3;
+                        ptx::mbar_wait(&fullW[sw], pw);
+                        ptx::tc_fence_after();
+                        const uint64_t adesc = ptx::umma_smem_desc(ptx::smem_u32(smemW + (size_t)sw * w_stage), 0, 1024);
+                        const uint64_t bdesc = ptx::umma_smem_desc(x_addr + (uint32_t)((kh * PITCH + kw) * 128), 0, (uint32_t)(PITCH * 128));
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k)
+                            ptx::umma_bf16(d_tmem, adesc + (uint64_t)(k * UMMA_K * 2 / 16), bdesc + (uint64_t)(k * UMMA_K * 2 / 16), idesc,
+                                           (cc | tap | k) != 0 ? 1u : 0u);
+                        ptx::umma_commit(&emptyW[sw]);
+                        if (++sw == p.b_stages) { sw = 0; pw ^= 1; }
+                    }
+                    ptx::umma_commit(&emptyX[sx]);
+                    if (++sx == p.a_stages) { sx = 0; px ^= 1; }
+                }
+                ptx::umma_commit(&tfull[as]);
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+        }
+    } else {
+        // ---- transposed epilogue: lane = output channel, TMEM column = pixel of the 32 x 8 tile.  Each 32x32 block is
+        // transposed through a padded per-warp shared-memory tile so that global stores are 16-byte vectors along channels.
+        const int quarter = warp & 3;
+        const int half = (warp - 2) >> 2;                    // two warps per quarter take alternating 32-column chunks
+        float* tsm = reinterpret_cast<float*>(tmem_slot + 4) + (size_t)(warp - 2) * (32 * 36);   // [32 pixels][36] fp32
+        const int grp = lane & 3, prow = lane >> 2;          // phase 2: lane -> (pixel row within 8, group of 8 channels)
+        int as = 0; uint32_t aphase = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const int ct = tile % p.co_tiles, pt = tile / p.co_tiles;
+            const int twi = pt % p.tiles_w, t2 = pt / p.tiles_w, thi = t2 % p.tiles_h, n = t2 / p.tiles_h;
+            const int w0 = twi * TW, h0 = thi * TH;
+            const int co8 = ct * BM + quarter * 32 + grp * 8;
+            float bv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) bv[u] = p.bias ? __ldg(p.bias + co8 + u) : 0.f;
+            ptx::mbar_wait(&tfull[as], aphase);
+            ptx::tc_fence_after();
+            const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * NPIX);
+            for (int c = half * 32; c < NPIX; c += 64) {
+                uint32_t r[32];
+                ptx::tmem_ld32(t_addr + (uint32_t)c, r);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) tsm[j * 36 + lane] = __uint_as_float(r[j]);
+                __syncwarp();
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                    const int pl = it * 8 + prow;                       // pixel within this 32-column chunk
+                    const int h = h0 + (c >> 3) + (pl >> 3), w = w0 + (pl & 7);
+                    const float4 v0 = *reinterpret_cast<const float4*>(tsm + pl * 36 + grp * 8);
+                    const float4 v1 = *reinterpret_cast<const float4*>(tsm + pl * 36 + grp * 8 + 4);
+                    if (h < p.H && w < p.W) {
+                        float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                        if (p.bias || p.act != VQB_ACT_NONE || p.gain != 1.0f) {
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) v[u] = act_f(v[u] + bv[u], p.act, p.alpha) * p.gain;
+                        }
+                        const int64_t off = (((int64_t)n * p.H + h) * p.W + w) * p.Co + co8;
+                        if (p.y_f32) {
+                            float* yo = reinterpret_cast<float*>(p.y) + off;
+                            if (p.residual) {
+                                const float* ro = reinterpret_cast<const float*>(p.residual) + off;
+                                float4 q0 = *reinterpret_cast<const float4*>(ro), q1 = *reinterpret_cast<const float4*>(ro + 4);
+                                v[0] += q0.x; v[1] += q0.y; v[2] += q0.z; v[3] += q0.w; v[4] += q1.x; v[5] += q1.y; v[6] += q1.z; v[7] += q1.w;
+                            }
+                            *reinterpret_cast<float4*>(yo) = make_float4(v[0], v[1], v[2], v[3]);
+                            *reinterpret_cast<float4*>(yo + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                        } else {
+                            bf16* yo = reinterpret_cast<bf16*>(p.y) + off;
+                            if (p.residual) {
+                                uint4 q = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.residual) + off);
+                                const __nv_bfloat162* qb = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) { float2 f = __bfloat1622float2(qb[u]); v[2 * u] += f.x; v[2 * u + 1] += f.y; }
+                            }
+                            uint4 o;
+                            __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) ob[u] = __floats2bfloat162_rn(v[2 * u], v[2 * u + 1]);
+                            *reinterpret_cast<uint4*>(yo) = o;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tempty[as]);
+            if (++as == 2) { as = 0; aphase ^= 1; }
+        }
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -693,6 +871,25 @@ int vqb_conv2d_fwd_tc(const void* x, const void* wp, const float* bias, const vo
     const bool halo = mode != 0 && KH == 3 && KW == 3 && pad == 1 && H >= 16 && W >= 8;
     CUtensorMap tmA, tmB;
     int rc = make_weight_map(&tmB, wp, Co, KH * KW * Ci, p.BN); if (rc) return rc;
+    if (halo && mode == 1 && p.BN == 128 && !p.narrow && H >= 32) {
+        // Co tiles of 128: swapped operand roles (M = co, N = 256 pixels), see conv_fwd_tc_halo_t_kernel
+        p.tw = 8; p.th = 32; p.nb = 1; p.MT = 1; p.pitch = 10; p.bo_mode = 0; p.stages = 0;
+        p.tiles_w = (W + 7) / 8; p.tiles_h = (H + 31) / 32; p.tiles_n = N;
+        p.co_tiles = Co / BM;
+        p.num_tiles = p.tiles_w * p.tiles_h * N * p.co_tiles;
+        p.a_tile_bytes = ((34 * 10 * 128) + 1023) / 1024 * 1024;
+        const int w_stage = BM * BK * 2;
+        p.a_stages = 2;
+        const int tr_bytes = 8 * 32 * 36 * 4;                       // epilogue transpose tiles (8 warps)
+        p.b_stages = (SMEM_LIMIT - 2048 - tr_bytes - p.a_stages * p.a_tile_bytes) / w_stage; if (p.b_stages > 12) p.b_stages = 12;
+        rc = make_act_map(&tmA, x, N, H, W, Ci, 10, 34, 1); if (rc) return rc;
+        size_t smem = (size_t)p.a_stages * p.a_tile_bytes + (size_t)p.b_stages * w_stage + 1024 + 512 + tr_bytes;
+        VQB_CUDA(cudaFuncSetAttribute(conv_fwd_tc_halo_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+        conv_fwd_tc_halo_t_kernel<<<grid, NTHREADS_FWD, smem, stream>>>(tmA, tmB, p);
+        VQB_CHECK_LAUNCH("conv2d_fwd_tc_halo_t");
+        return VQB_OK;
+    }
     if (halo) {
         p.tw = 8; p.th = 16; p.nb = 1;
         p.tiles_w = (W + 7) / 8; p.tiles_h = (H + 15) / 16; p.tiles_n = N;
@@ -711,7 +908,7 @@ int vqb_conv2d_fwd_tc(const void* x, const void* wp, const float* bias, const vo
         size_t smem = (size_t)p.a_stages * a_stage + (size_t)p.b_stages * b_stage + 1024 + 512;
         VQB_CUDA(cudaFuncSetAttribute(conv_fwd_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-        conv_fwd_tc_halo_kernel<<<grid, NTHREADS, smem, stream>>>(tmA, tmB, p);
+        conv_fwd_tc_halo_kernel<<<grid, NTHREADS_FWD, smem, stream>>>(tmA, tmB, p);
         VQB_CHECK_LAUNCH("conv2d_fwd_tc_halo");
         return VQB_OK;
     }
@@ -726,7 +923,7 @@ int vqb_conv2d_fwd_tc(const void* x, const void* wp, const float* bias, const vo
     size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256;
     VQB_CUDA(cudaFuncSetAttribute(conv_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-    conv_fwd_tc_kernel<<<grid, NTHREADS, smem, stream>>>(tmA, tmB, p);
+    conv_fwd_tc_kernel<<<grid, NTHREADS_FWD, smem, stream>>>(tmA, tmB, p);
     VQB_CHECK_LAUNCH("conv2d_fwd_tc");
     return VQB_OK;
 }
