@@ -108,10 +108,11 @@ int vqb_gn_bwd_reduce(const void* x, int x_dtype, const void* dy, int dy_dtype, 
 /* backward finalize: coef[b][g] = (sum_g/n, sum_g_xhat/(n-1)); dgamma[c], dbeta[c] (overwritten) */
 int vqb_gn_bwd_finalize(const double* part, const float* gamma, float* coef, float* dgamma, float* dbeta, int N,
                         int HW, int C, int G, void* stream);
-/* backward pass 2: dx = rstd * (g - coef0 - xhat*coef1), g = ds*gamma */
+/* backward pass 2: dx = rstd * (g - coef0 - xhat*coef1) [+ add], g = ds*gamma.  `add` (dtype of dx, may be NULL) fuses the
+ * accumulation of a second gradient of x -- the ResBlock skip connection (autoencoder.py:77) -- into this pass. */
 int vqb_gn_bwd_apply(const void* x, int x_dtype, const void* dy, int dy_dtype, const float* stats,
-                     const float* gamma, const float* beta, const float* coef, void* dx, int dx_dtype, int N, int HW,
-                     int C, int G, int act, void* stream);
+                     const float* gamma, const float* beta, const float* coef, const void* add, void* dx, int dx_dtype,
+                     int N, int HW, int C, int G, int act, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * Resampling (Downsample = avg_pool2d(2,2) autoencoder.py:89-91; Upsample = nearest-exact x2 :103-106)

@@ -255,8 +255,8 @@ __global__ void gn_bwd_finalize_kernel(const double* __restrict__ part, const fl
 template <typename TI, typename TG, typename TO, int VEC>
 __global__ void gn_bwd_apply_kernel(const TI* __restrict__ x, const TG* __restrict__ dy, const float* __restrict__ stats,
                                     const float* __restrict__ gamma, const float* __restrict__ beta,
-                                    const float* __restrict__ coef, TO* __restrict__ dx, int HW, int C, int G, int ppb,
-                                    int act) {
+                                    const float* __restrict__ coef, const TO* __restrict__ add, TO* __restrict__ dx, int HW,
+                                    int C, int G, int ppb, int act) {
     const int b = blockIdx.y;
     const int c0 = threadIdx.x * VEC;
     const int cg = C / G;
@@ -287,6 +287,12 @@ __global__ void gn_bwd_apply_kernel(const TI* __restrict__ x, const TG* __restri
             float ds = g[j];
             if (act == VQB_ACT_SILU) ds *= fast_silu_grad(fmaf(v[j], sc[j], sf[j]));
             o[j] = fmaf(ds, ca[j], fmaf(v[j], cb[j], cc[j]));
+        }
+        if (add) {                                    // fused accumulation of the skip-connection gradient
+            float r[VEC];
+            ldv<TO, VEC>(add + base + (int64_t)p * C, r);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) o[j] += r[j];
         }
         stv<TO, VEC>(dx + base + (int64_t)p * C, o);
     }
@@ -367,13 +373,13 @@ extern "C" int vqb_gn_bwd_finalize(const double* part, const float* gamma, float
 }
 
 extern "C" int vqb_gn_bwd_apply(const void* x, int x_dtype, const void* dy, int dy_dtype, const float* stats,
-                                const float* gamma, const float* beta, const float* coef, void* dx, int dx_dtype, int N,
-                                int HW, int C, int G, int act, void* stream) {
+                                const float* gamma, const float* beta, const float* coef, const void* add, void* dx,
+                                int dx_dtype, int N, int HW, int C, int G, int act, void* stream) {
     int rc = gn_check("gn_bwd_apply", N, HW, C, G); if (rc) return rc;
     VQB_CHECK_ARG(x && dy && stats && gamma && beta && coef && dx, "gn_bwd_apply: null pointer");
     GnLaunch L = gn_launch(N, HW, C, G);
     GN_VEC_DISPATCH(L, VQB_DISPATCH_1(x_dtype, TI, VQB_DISPATCH_1(dy_dtype, TG, VQB_DISPATCH_1(dx_dtype, TO,
-        (gn_bwd_apply_kernel<TI, TG, TO, VEC><<<L.grid, L.block, 0, as_stream(stream)>>>((const TI*)x, (const TG*)dy, stats, gamma, beta, coef, (TO*)dx, HW, C, G, L.ppb, act));))))
+        (gn_bwd_apply_kernel<TI, TG, TO, VEC><<<L.grid, L.block, 0, as_stream(stream)>>>((const TI*)x, (const TG*)dy, stats, gamma, beta, coef, (const TO*)add, (TO*)dx, HW, C, G, L.ppb, act));))))
     VQB_CHECK_LAUNCH("gn_bwd_apply");
     return VQB_OK;
 }

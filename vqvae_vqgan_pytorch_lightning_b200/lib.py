@@ -48,7 +48,7 @@ SIGNATURES = {
     'vqb_gn_apply': (_i, [_p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     'vqb_gn_bwd_reduce': (_i, [_p, _i, _p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     'vqb_gn_bwd_finalize': (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
-    'vqb_gn_bwd_apply': (_i, [_p, _i, _p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    'vqb_gn_bwd_apply': (_i, [_p, _i, _p, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     'vqb_down2': (_i, [_p, _p, _i, _i, _i, _i, _i, _f, _p]),
     'vqb_up2': (_i, [_p, _p, _i, _i, _i, _i, _i, _f, _p]),
     'vqb_diff_sums': (_i, [_p, _i, _p, _i, _p, _i64, _p]),

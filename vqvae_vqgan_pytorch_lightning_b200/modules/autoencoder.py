@@ -38,8 +38,8 @@ class GroupNorm(nn.Module):
         self.weight = nn.Parameter(torch.ones(1, num_channels, 1, 1))
         self.bias = nn.Parameter(torch.zeros(1, num_channels, 1, 1))
 
-    def forward(self, x: torch.Tensor, act: int = ACT_NONE) -> torch.Tensor:
-        return ops.group_norm_act(x, self.weight, self.bias, self.num_groups, self.eps, act)
+    def forward(self, x: torch.Tensor, act: int = ACT_NONE, want_skip: bool = False):
+        return ops.group_norm_act(x, self.weight, self.bias, self.num_groups, self.eps, act, want_skip)
 
 
 class ResBlock(nn.Module):
@@ -57,11 +57,14 @@ class ResBlock(nn.Module):
         self.conv2 = Conv2d(self.out_channels, self.out_channels, kernel_size=3, stride=1, padding='same', bias=False)
 
     def forward(self, x):
-        h = self.norm1(x, act=ACT_SILU)
+        if self.in_channels != self.out_channels:
+            h = self.norm1(x, act=ACT_SILU)
+            x = self.conv_shortcut(x)
+        else:
+            # the skip connection goes through norm1's identity output: its gradient is added inside the GN backward kernel
+            h, x = self.norm1(x, act=ACT_SILU, want_skip=True)
         h = self.conv1(h)
         h = self.norm2(h, act=ACT_SILU)
-        if self.in_channels != self.out_channels:
-            x = self.conv_shortcut(x)
         return self.conv2(h, residual=x)
 
 

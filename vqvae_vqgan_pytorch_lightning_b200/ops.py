@@ -227,10 +227,14 @@ def conv2d(x, weight, bias=None, residual=None, pad=0, stride=1, act=ACT_NONE, a
 # GroupNorm (+SiLU)
 # ------------------------------------------------------------------------------------------------------
 class GroupNormActFn(torch.autograd.Function):
-    """act(GroupNorm(x)) with the reference's unbiased variance (vqvae/modules/autoencoder.py:25-39)."""
+    """act(GroupNorm(x)) with the reference's unbiased variance (vqvae/modules/autoencoder.py:25-39).
+
+    With `want_skip` the input is also returned (as an identity output) for the ResBlock skip connection (`x + h`,
+    autoencoder.py:77): the gradient arriving on that second output is then added inside the backward kernel instead of by
+    a separate elementwise pass over the activation."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, groups, eps, act):
+    def forward(ctx, x, gamma, beta, groups, eps, act, want_skip):
         x = as_nhwc(x)
         n, c, h, w = x.shape
         ga = gamma.detach().reshape(-1).float().contiguous()
@@ -243,10 +247,12 @@ class GroupNormActFn(torch.autograd.Function):
         call('vqb_gn_apply', ptr(x), dt(x), ptr(stats), ptr(ga), ptr(be), ptr(y), dt(y), n, h * w, c, groups, act, stream())
         ctx.save_for_backward(x, stats, ga, be)
         ctx.cfg = (groups, act, gamma.shape, beta.shape)
+        if want_skip:
+            return y, x.view_as(x)
         return y
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, dskip=None):
         x, stats, ga, be = ctx.saved_tensors
         groups, act, gshape, bshape = ctx.cfg
         n, c, h, w = x.shape
@@ -261,13 +267,14 @@ class GroupNormActFn(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x, memory_format=torch.preserve_format)
-            call('vqb_gn_bwd_apply', ptr(x), dt(x), ptr(dy), dt(dy), ptr(stats), ptr(ga), ptr(be), ptr(coef), ptr(dx), dt(dx),
-                 n, h * w, c, groups, act, stream())
-        return dx, dgamma.reshape(gshape), dbeta.reshape(bshape), None, None, None
+            add = as_nhwc(dskip, dx.dtype) if dskip is not None else None
+            call('vqb_gn_bwd_apply', ptr(x), dt(x), ptr(dy), dt(dy), ptr(stats), ptr(ga), ptr(be), ptr(coef), ptr(add), ptr(dx),
+                 dt(dx), n, h * w, c, groups, act, stream())
+        return dx, dgamma.reshape(gshape), dbeta.reshape(bshape), None, None, None, None
 
 
-def group_norm_act(x, gamma, beta, groups=32, eps=1e-6, act=ACT_SILU):
-    return GroupNormActFn.apply(x, gamma, beta, groups, eps, act)
+def group_norm_act(x, gamma, beta, groups=32, eps=1e-6, act=ACT_SILU, want_skip=False):
+    return GroupNormActFn.apply(x, gamma, beta, groups, eps, act, want_skip)
 
 
 # ------------------------------------------------------------------------------------------------------
