@@ -58,9 +58,14 @@ int vqb_convert(const void* x, int in_dtype, void* y, int out_dtype, int64_t n, 
  *   mode 1 (dgrad    GEMM-B): wp[((KH-1-kh)*KW+(KW-1-kw))*Co+co][ci]   (taps flipped, channels swapped)
  *   mode 2 (tcgen05 forward, K-major): wp[co][(kh*KW+kw)*Ci+ci]
  *   mode 3 (tcgen05 dgrad,   K-major): wp[ci][((KH-1-kh)*KW+(KW-1-kw))*Co+co]
+ *   mode 4 / 5: modes 2 / 3 with the reduction dimension zero-padded to 64 (KH*KW*C <= 64): wp[co][64] / wp[ci][64]
  * scale multiplies every weight (StyleGAN2 equalised-lr gain, discriminator.py:148,165). */
 int vqb_pack_conv_weight(const float* w, void* wp, int out_dtype, int mode, int Co, int Ci, int KH, int KW,
                          float scale, void* stream);
+/* Narrow-input 3x3 / pad-1 convolutions (the RGB heads: encoder.conv_in 3->128, and everything that touches the 3-channel
+ * side of decoder.conv_out) run on tensor cores as a 64-channel 1x1 implicit GEMM over this im2col tensor:
+ * P[n,h,w,j] = x[n,h+kh-1,w+kw-1,c] for j = (kh*3+kw)*C+c < 9*C, zero otherwise (C <= 7). */
+int vqb_im2col3x3_narrow(const void* x, int x_dtype, void* P, int p_dtype, int N, int H, int W, int C, void* stream);
 /* inverse of mode 0 for gradients: dw[co][ci][kh][kw] = scale * dwp[(kh*KW+kw)*Ci+ci][co] */
 int vqb_unpack_conv_wgrad(const float* dwp, float* dw, int Co, int Ci, int KH, int KW, float scale, void* stream);
 

@@ -80,3 +80,30 @@ def test_conv_tc_backward(V, n, h, w, ci, co, k, bias, res, act):
     yg.backward(cl(go).bfloat16())
     assert C.rel_err(xg.grad.float(), xo.grad) < 4e-3          # dgrad output is stored as bf16
     assert C.rel_err(wg.grad, wo.grad) < 1e-4                  # wgrad accumulates and stores fp32
+
+
+def test_rgb_heads_on_tensor_cores(V):
+    """encoder.conv_in (3 -> 128) and decoder.conv_out (128 -> 3, tanh): forward / dgrad / wgrad through the im2col-64
+    1x1 tcgen05 route, against fp32 torch on the same bf16-rounded operands."""
+    torch.manual_seed(2)
+    n, h, w = 2, 40, 24
+    # --- narrow input
+    x = r16(torch.rand(n, 3, h, w) * 2 - 1); wt = r16(torch.randn(128, 3, 3, 3) * 0.2); go = r16(torch.randn(n, 128, h, w))
+    wo = wt.clone().requires_grad_()
+    yo = F.conv2d(x, wo, None, padding=1); yo.backward(go)
+    wg = wt.cuda().requires_grad_()
+    yg = V.ops.conv2d(cl(x), wg, None, None, pad=1)                    # fp32 image input, bf16 output
+    yg.backward(cl(go).bfloat16())
+    assert yg.dtype == torch.bfloat16
+    assert C.rel_err(yg.float(), yo) < 4e-3 and C.rel_err(wg.grad, wo.grad) < 1e-4
+    # --- narrow output with bias + tanh
+    x = r16(torch.randn(n, 128, h, w)); wt = r16(torch.randn(3, 128, 3, 3) * 0.03); b = torch.randn(3) * 0.1
+    go = torch.randn(n, 3, h, w)
+    xo, wo, bo = x.clone().requires_grad_(), wt.clone().requires_grad_(), b.clone().requires_grad_()
+    yo = torch.tanh(F.conv2d(xo, wo, bo, padding=1)); yo.backward(go)
+    xg, wg, bg = cl(x).bfloat16().requires_grad_(), wt.cuda().requires_grad_(), b.cuda().requires_grad_()
+    yg = V.ops.conv2d(xg, wg, bg, None, pad=1, act=V.lib.ACT_TANH, out_dtype=torch.float32)
+    yg.backward(cl(go))
+    assert C.rel_err(yg, yo) < 1e-4
+    assert C.rel_err(xg.grad.float(), xo.grad) < 8e-3              # dpre and dx are stored as bf16
+    assert C.rel_err(wg.grad, wo.grad) < 5e-3 and C.rel_err(bg.grad, bo.grad) < 5e-3

@@ -165,13 +165,78 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, TO* __restrict__
     }
 }
 
+// modes 4 / 5: the K-major layouts of modes 2 / 3 with the reduction dimension zero-padded to 64 (narrow 3x3 heads run as
+// a 64-channel 1x1 implicit GEMM on the im2col tensor of vqb_im2col3x3_narrow)
+template <typename TO>
+__global__ void pack_weight_pad64_kernel(const float* __restrict__ w, TO* __restrict__ wp, int mode, int Co, int Ci, int KH,
+                                         int KW, float scale) {
+    const int rows = (mode == 4) ? Co : Ci, inner = (mode == 4) ? Ci : Co, kreal = KH * KW * inner;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (int64_t)rows * 64; i += (int64_t)gridDim.x * blockDim.x) {
+        int j = (int)(i % 64), r = (int)(i / 64);
+        float v = 0.f;
+        if (j < kreal) {
+            int c = j % inner, tap = j / inner, kw = tap % KW, kh = tap / KW;
+            if (mode == 4) v = w[(((int64_t)r * Ci + c) * KH + kh) * KW + kw];                                 // [co][(kh,kw,ci)]
+            else v = w[(((int64_t)c * Ci + r) * KH + (KH - 1 - kh)) * KW + (KW - 1 - kw)];                     // [ci][(kh',kw',co)]
+        }
+        st1(wp + i, v * scale);
+    }
+}
+
 extern "C" int vqb_pack_conv_weight(const float* w, void* wp, int out_dtype, int mode, int Co, int Ci, int KH, int KW,
                                     float scale, void* stream) {
-    VQB_CHECK_ARG(w && wp && mode >= 0 && mode <= 3 && Co > 0 && Ci > 0 && KH > 0 && KW > 0, "pack_conv_weight: bad arguments");
+    VQB_CHECK_ARG(w && wp && mode >= 0 && mode <= 5 && Co > 0 && Ci > 0 && KH > 0 && KW > 0, "pack_conv_weight: bad arguments");
+    if (mode >= 4) {
+        VQB_CHECK_ARG(KH * KW * ((mode == 4) ? Ci : Co) <= 64, "pack_conv_weight: padded modes need KH*KW*C <= 64");
+        int gp = grid_for((int64_t)((mode == 4) ? Co : Ci) * 64, 256);
+        VQB_DISPATCH_1(out_dtype, TO, (pack_weight_pad64_kernel<TO><<<gp, 256, 0, as_stream(stream)>>>(w, (TO*)wp, mode, Co, Ci, KH, KW, scale));)
+        VQB_CHECK_LAUNCH("pack_conv_weight(pad64)");
+        return VQB_OK;
+    }
     int64_t total = (int64_t)Co * Ci * KH * KW;
     int g = grid_for(total, 256);
     VQB_DISPATCH_1(out_dtype, TO, (pack_weight_kernel<TO><<<g, 256, 0, as_stream(stream)>>>(w, (TO*)wp, mode, Co, Ci, KH, KW, scale));)
     VQB_CHECK_LAUNCH("pack_conv_weight");
+    return VQB_OK;
+}
+
+// P[n,h,w, j] (64 channels, TO) = x[n, h+kh-1, w+kw-1, c] for j = (kh*3+kw)*C + c < 9*C, else 0   (3x3, pad 1, C <= 7)
+template <typename TI, typename TO, int CT>
+__global__ void im2col3x3_narrow_kernel(const TI* __restrict__ x, TO* __restrict__ P, int N, int H, int W, int Crt) {
+    const int C = (CT > 0) ? CT : Crt;                        // compile-time channel count (3 = RGB) avoids runtime div/mod
+    const int64_t total = (int64_t)N * H * W * 8;            // one thread per (pixel, group of 8 output columns)
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int grp = (int)(i & 7); int64_t pix = i >> 3;
+        int w = (int)(pix % W); int64_t r = pix / W; int h = (int)(r % H); int n = (int)(r / H);
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            int j = grp * 8 + u;
+            float val = 0.f;
+            if (j < 9 * C) {
+                int tap = j / C, c = j - tap * C, kh = tap / 3, kw = tap - kh * 3;
+                int ih = h + kh - 1, iw = w + kw - 1;
+                if (ih >= 0 && ih < H && iw >= 0 && iw < W) val = ld1(x + (((int64_t)n * H + ih) * W + iw) * C + c);
+            }
+            v[u] = val;
+        }
+        TO* dst = P + pix * 64 + grp * 8;
+        st4(dst, make_float4(v[0], v[1], v[2], v[3]));
+        st4(dst + 4, make_float4(v[4], v[5], v[6], v[7]));
+    }
+}
+
+extern "C" int vqb_im2col3x3_narrow(const void* x, int x_dtype, void* P, int p_dtype, int N, int H, int W, int C, void* stream) {
+    VQB_CHECK_ARG(x && P && N > 0 && H > 0 && W > 0 && C > 0 && 9 * C <= 64, "im2col3x3_narrow: bad arguments (need 9*C <= 64)");
+    int g = grid_for((int64_t)N * H * W * 8, 256);
+    if (C == 3) {
+        VQB_DISPATCH_1(x_dtype, TI, VQB_DISPATCH_1(p_dtype, TO, (im2col3x3_narrow_kernel<TI, TO, 3><<<g, 256, 0, as_stream(stream)>>>(
+                                                                    (const TI*)x, (TO*)P, N, H, W, C));))
+    } else {
+        VQB_DISPATCH_1(x_dtype, TI, VQB_DISPATCH_1(p_dtype, TO, (im2col3x3_narrow_kernel<TI, TO, 0><<<g, 256, 0, as_stream(stream)>>>(
+                                                                    (const TI*)x, (TO*)P, N, H, W, C));))
+    }
+    VQB_CHECK_LAUNCH("im2col3x3_narrow");
     return VQB_OK;
 }
 

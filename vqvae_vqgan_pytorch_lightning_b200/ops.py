@@ -121,7 +121,8 @@ def _packed_weight(weight: torch.Tensor, mode: int, dtype: torch.dtype, scale: f
     tag = (mode, dtype)
     if tag not in cache:
         co, ci, kh, kw = weight.shape
-        wp = torch.empty(co * ci * kh * kw, dtype=dtype, device=weight.device)
+        numel = co * ci * kh * kw if mode < 4 else 64 * (co if mode == 4 else ci)      # modes 4/5 pad K to 64
+        wp = torch.empty(numel, dtype=dtype, device=weight.device)
         src = weight.detach()
         if not src.is_contiguous() or src.dtype != torch.float32:
             src = src.float().contiguous()            # e.g. the transposed-codebook view used by the Gumbel einsum
@@ -139,6 +140,26 @@ def _conv_fwd_raw(impl: int, x: torch.Tensor, wp: torch.Tensor, bias, residual, 
     call('vqb_conv2d_fwd', impl, ptr(x), dt(x), ptr(wp), ptr(bias), ptr(residual), ptr(y), dt(y), n, h, w, ci, co, kh, kw,
          pad, stride, act, alpha, gain, stream())
     return y
+
+
+def _narrow_route(prec: Precision, ci: int, co: int, kh: int, kw: int, pad: int, stride: int) -> Optional[str]:
+    """fast mode: the RGB heads (3x3, pad 1) ride the tensor cores as a 64-channel 1x1 implicit GEMM over an im2col tensor
+    ('in': narrow input, e.g. encoder.conv_in 3->128; 'out': narrow output, e.g. decoder.conv_out 128->3, whose dgrad and
+    wgrad are narrow-INPUT problems on dy)."""
+    if prec.name != 'fast' or (kh, kw, pad, stride) != (3, 3, 1, 1):
+        return None
+    if ci <= 7 and co % 128 == 0:
+        return 'in'
+    if co <= 7 and ci % 128 == 0:
+        return 'out'
+    return None
+
+
+def _im2col64(x: torch.Tensor) -> torch.Tensor:
+    n, c, h, w = x.shape
+    p = empty_nhwc(n, 64, h, w, torch.bfloat16, x.device)
+    call('vqb_im2col3x3_narrow', ptr(x), dt(x), ptr(p), BF16, n, h, w, c, stream())
+    return p
 
 
 class Conv2dFn(torch.autograd.Function):
@@ -162,9 +183,14 @@ class Conv2dFn(torch.autograd.Function):
                 # the activation derivative is recovered from the saved OUTPUT, which a fused residual would contaminate
                 raise lib.VQBError('conv2d: a fused residual cannot be combined with an activation epilogue')
             residual = as_nhwc(residual, out_dtype)
-        wp = _packed_weight(weight, 2 if impl == 1 else 0, torch.bfloat16 if impl == 1 else torch.float32, w_scale)
         b = bias.detach().reshape(-1).float().contiguous() if bias is not None else None
-        y = _conv_fwd_raw(impl, x, wp, b, residual, out_dtype, ci, co, kh, kw, pad, stride, act, alpha, gain)
+        route = _narrow_route(prec, ci, co, kh, kw, pad, stride)
+        if route == 'in':
+            wp = _packed_weight(weight, 4, torch.bfloat16, w_scale)                  # [co][64], K zero-padded
+            y = _conv_fwd_raw(1, _im2col64(x), wp, b, residual, out_dtype, 64, co, 1, 1, 0, 1, act, alpha, gain)
+        else:
+            wp = _packed_weight(weight, 2 if impl == 1 else 0, torch.bfloat16 if impl == 1 else torch.float32, w_scale)
+            y = _conv_fwd_raw(impl, x, wp, b, residual, out_dtype, ci, co, kh, kw, pad, stride, act, alpha, gain)
         ctx.save_for_backward(x, weight, y if act != ACT_NONE else None)
         ctx.cfg = (impl, pad, stride, act, alpha, gain, w_scale, bias is not None, residual is not None,
                    residual.dtype if residual is not None else None, in_dtype)
@@ -191,6 +217,35 @@ class Conv2dFn(torch.autograd.Function):
             raise lib.VQBError('gain != 1 requires an activation epilogue')
         _, _, oh, ow = dy.shape
         dx = dw = db = None
+        route = _narrow_route(prec, ci, co, kh, kw, pad, stride)
+        if route == 'in' and ctx.needs_input_grad[1] and not ctx.needs_input_grad[0]:
+            # dW[(tap,ci)][co] = im2col(x)^T dy : 1x1 tcgen05 wgrad with 64 (zero-padded) input channels
+            dwp = torch.zeros(64 * co, dtype=torch.float32, device=x.device)
+            dyw = as_nhwc(dy, torch.bfloat16)
+            call('vqb_conv2d_wgrad', 1, ptr(_im2col64(x)), BF16, ptr(dyw), BF16, ptr(dwp), n, h, w, 64, co, 1, 1, 0, 1, stream())
+            dw = torch.empty(weight.shape, dtype=torch.float32, device=x.device)
+            call('vqb_unpack_conv_wgrad', ptr(dwp), ptr(dw), co, ci, kh, kw, w_scale, stream())
+            if has_bias and ctx.needs_input_grad[2]:
+                db = torch.zeros(co, dtype=torch.float32, device=x.device)
+                call('vqb_colsum', ptr(dy), dt(dy), ptr(db), n * oh * ow, co, stream())
+            return None, dw, db, dres, None, None, None, None, None, None, None
+        if route == 'out' and x.dtype == torch.bfloat16:
+            pd = _im2col64(dy)                                                        # im2col of the 3-channel gradient
+            if ctx.needs_input_grad[0]:
+                wd = _packed_weight(weight, 5, torch.bfloat16, w_scale)               # [ci][64]: flipped taps, K zero-padded
+                ddt = in_dtype if in_dtype in (torch.float32, torch.bfloat16) else gdt
+                dx = _conv_fwd_raw(1, pd, wd, None, None, ddt, 64, ci, 1, 1, 0, 1, ACT_NONE, 0.0, 1.0)
+            if ctx.needs_input_grad[1]:
+                # R[(kh',kw',co)][ci] = im2col(dy)^T x ; dW[co][ci][kh][kw] = R[(2-kh, 2-kw, co)][ci]
+                r = torch.zeros(64 * ci, dtype=torch.float32, device=x.device)
+                call('vqb_conv2d_wgrad', 1, ptr(pd), BF16, ptr(x), BF16, ptr(r), n, h, w, 64, ci, 1, 1, 0, 1, stream())
+                dw = r[:9 * co * ci].view(3, 3, co, ci).flip(0, 1).permute(2, 3, 0, 1).contiguous()      # 10 KB reorder
+                if w_scale != 1.0:
+                    dw = dw * w_scale
+            if has_bias and ctx.needs_input_grad[2]:
+                db = torch.zeros(co, dtype=torch.float32, device=x.device)
+                call('vqb_colsum', ptr(dy), dt(dy), ptr(db), n * oh * ow, co, stream())
+            return dx, dw, db, dres, None, None, None, None, None, None, None
         if ctx.needs_input_grad[0]:
             if stride != 1:
                 # strided forward conv: transposed-conv gather over the (virtually) zero-upsampled dy, fp32 SIMT
