@@ -220,7 +220,7 @@ def main():
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    pkg.lib.timer = pkg.lib.KernelTimer(['vqb_conv2d_fwd', 'vqb_conv2d_wgrad', 'vqb_vq_assign'])
+    pkg.lib.timer = pkg.lib.KernelTimer(['vqb_conv2d_fwd', 'vqb_conv2d_wgrad', 'vqb_vq_assign', 'vqb_vq_assign_tc'])
     launches0 = pkg.lib.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -263,13 +263,14 @@ def main():
         roofline = {'bound': 'tensor', 'kernel': 'implicit-GEMM conv (fwd+dgrad+wgrad launches)', 'achieved': achieved, 'peak': peak,
                     'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': None, 'peak_source': f'{pk_kind} (sustained bf16)',
                     'launches_timed': conv_calls, 'share_of_step': conv_ms / ms, 'flop_per_step': conv_fl / args.steps}
-        vq = ksum.get('vqb_vq_assign')
+        vq = ksum.get('vqb_vq_assign_tc') or ksum.get('vqb_vq_assign')
+        vq_kernel = 'vq_assign_tc (bf16 hi/lo tcgen05 search + exact fp32 re-rank + finish)' if 'vqb_vq_assign_tc' in ksum else 'vq_assign (fp32 SIMT)'
         n_lat = bs * (image_size // 16) ** 2
         vq_bytes = 4 * n_lat * 256 * 2 + 4 * args.codebook * 256 + 8 * n_lat + 8 * args.codebook + 12 * args.codebook * 256
         vq_roof = None
         if vq:
             vq_ms = vq['ms'] / vq['calls']
-            vq_roof = {'bound': 'hbm', 'kernel': 'vq_assign (+sqnorm)', 'achieved': vq_bytes / (vq_ms / 1e3) / 1e9, 'peak': pk['hbm_gbs'],
+            vq_roof = {'bound': 'hbm', 'kernel': vq_kernel, 'achieved': vq_bytes / (vq_ms / 1e3) / 1e9, 'peak': pk['hbm_gbs'],
                        'unit': 'GB/s', 'frac': vq_bytes / (vq_ms / 1e3) / 1e9 / pk['hbm_gbs'], 'traffic': None, 'us_per_launch': vq_ms * 1e3}
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,

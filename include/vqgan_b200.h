@@ -186,6 +186,15 @@ size_t vqb_vq_workspace_bytes(int64_t N, int K, int D);
 int vqb_vq_assign(const float* z, const float* codebook, int order, float* q_out, int64_t* idx_out, double* sse,
                   float* counts, float* dw, int64_t N, int K, int D, void* workspace, size_t workspace_bytes,
                   void* stream);
+/* The same contract as vqb_vq_assign (identical indices: first-index fp32 argmin in the reference's operation order), with
+ * the distance GEMM on the tensor cores: bf16 hi+lo split operands, three tcgen05 UMMAs per k-step, per-row best / second
+ * best in the epilogue; rows whose gap exceeds a rigorous error bound are decided there, the rest (genuine near-ties) are
+ * re-evaluated by the exact fp32 kernel.  Needs D % 64 == 0, D <= 256, K % 8 == 0.  undecided_rows_out (device int, may be
+ * NULL) receives the number of rows that took the exact path.  workspace: vqb_vq_tc_workspace_bytes(N,K,D). */
+size_t vqb_vq_tc_workspace_bytes(int64_t N, int K, int D);
+int vqb_vq_assign_tc(const float* z, const float* codebook, int order, float* q_out, int64_t* idx_out, double* sse,
+                     float* counts, float* dw, int64_t N, int K, int D, void* workspace, size_t workspace_bytes,
+                     int* undecided_rows_out, void* stream);
 /* EMA codebook update (vector_quantizers.py:158-169), in place:
  *   c = decay*ema_count + (1-decay)*counts ; ema_count = (c+eps)/(b + K*eps)*b   (b = IMAGE batch: defect B7)
  *   ema_weight = decay*ema_weight + (1-decay)*dw ; codebook = ema_weight / ema_count[:,None] */

@@ -1,0 +1,38 @@
+"""VQ kernel micro-benchmark: z ~ N(0,1) [N,256]; codebook U(+-1/K) (reference init, tie-heavy) and N(0,1)
+(tie-free); exact fp32 SIMT kernel vs tensor-core search + exact re-evaluation.  Reports us/launch, algorithmic GB/s
+(4ND + 4KD + 4ND + 8N + 8K + 12KD bytes, EMA statistics included) against the HBM peak, and the undecided-row count."""
+import json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
+import torch
+import vqvae_vqgan_pytorch_lightning_b200 as pkg
+pkg.lib.load()
+PEAK = 6555.8
+try:
+    PEAK = float(json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs'])
+except Exception:
+    pass
+flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device='cuda')
+def timeit(fn, iters=20):
+    for _ in range(3): fn()
+    ts = []
+    for _ in range(iters):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3)
+    ts.sort(); return ts[len(ts) // 2]
+rows = []
+for (N, K) in ((16384, 1024), (8192, 8192)):
+    D = 256
+    for init in ('uniform', 'normal'):
+        torch.manual_seed(0)
+        z = torch.randn(N, D, device='cuda')
+        cb = (torch.empty(K, D).uniform_(-1 / K, 1 / K) if init == 'uniform' else torch.randn(K, D)).cuda()
+        nbytes = 4 * N * D * 2 + 4 * K * D + 8 * N + 8 * K + 12 * K * D
+        for tc in (False, True):
+            us = timeit(lambda: pkg.ops.vq_assign_raw(z, cb, 0, True, True, use_tc=tc))
+            und = int(pkg.ops.vq_assign_raw.last_undecided) if tc else N
+            r = dict(N=N, K=K, init=init, kernel='tcgen05+exact-rerank' if tc else 'fp32-simt', us=round(us, 1),
+                     gbs=round(nbytes / us / 1e3, 1), frac_hbm=round(nbytes / us / 1e3 / PEAK, 4), undecided_rows=und,
+                     tflops=round(2.0 * N * K * D * (3 if tc else 1) / us / 1e6, 1))
+            rows.append(r); print(json.dumps(r), flush=True)

@@ -30,10 +30,12 @@ __global__ void row_sqnorm_kernel(const float* __restrict__ a, float* __restrict
     if (lane == 0) out[row] = s;
 }
 
-__global__ void __launch_bounds__(256)
-vq_assign_kernel(const float* __restrict__ z, const float* __restrict__ cb, const float* __restrict__ cb_sq, int order,
+__device__ __forceinline__ void
+vq_assign_tile(const int64_t tile_idx, const float* __restrict__ z, const float* __restrict__ cb, const float* __restrict__ cb_sq, int order,
                  float* __restrict__ q_out, int64_t* __restrict__ idx_out, double* __restrict__ sse,
-                 float* __restrict__ counts, float* __restrict__ dw, int64_t N, int K, int D) {
+                 float* __restrict__ counts, float* __restrict__ dw, int64_t N, int K, int D,
+                 const int* __restrict__ row_list, const int* __restrict__ n_rows_dev) {
+    // list mode (row_list != NULL): the CTA re-evaluates rows row_list[64*blockIdx.x ...] exactly and only writes idx_out
     extern __shared__ __align__(16) float smem[];
     float (*zs)[VM + VPAD] = reinterpret_cast<float (*)[VM + VPAD]>(smem);                        // [D][VM+PAD]
     float (*Bs)[VK][VN + VPAD] = reinterpret_cast<float (*)[VK][VN + VPAD]>(smem + (size_t)D * (VM + VPAD));   // [2][VK][VN+PAD]
@@ -42,13 +44,18 @@ vq_assign_kernel(const float* __restrict__ z, const float* __restrict__ cb, cons
 
     const int tid = threadIdx.x;
     const int ty = tid >> 4, tx = tid & 15;
-    const int64_t r0 = (int64_t)blockIdx.x * VM;
+    const int64_t r0 = tile_idx * VM;
+    const int64_t n_valid = row_list ? (int64_t)n_rows_dev[0] : N;
+    if (r0 >= n_valid) return;
+    __shared__ int64_t grow_s[VM];
+    if (tid < VM) grow_s[tid] = (r0 + tid < n_valid) ? (row_list ? (int64_t)row_list[r0 + tid] : r0 + tid) : -1;
+    __syncthreads();
 
     // ---- stage the z rows (transposed) and their squared norms
     for (int i = tid; i < VM * (D / 4); i += 256) {
         int row = i / (D / 4), d4 = (i - row * (D / 4)) * 4;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r0 + row < N) v = *reinterpret_cast<const float4*>(z + (r0 + row) * D + d4);
+        if (grow_s[row] >= 0) v = *reinterpret_cast<const float4*>(z + grow_s[row] * D + d4);
         zs[d4 + 0][row] = v.x; zs[d4 + 1][row] = v.y; zs[d4 + 2][row] = v.z; zs[d4 + 3][row] = v.w;
     }
     __syncthreads();
@@ -74,10 +81,15 @@ vq_assign_kernel(const float* __restrict__ z, const float* __restrict__ cb, cons
     const int lr = tid >> 2, lkc = (tid & 3) * 4;   // codebook loader: codes lr, lr+64; dims lkc..lkc+3
     const int DK = D / VK + ((D % VK) ? 1 : 0);
     const int CT = (K + VN - 1) / VN;
-    const int total = CT * DK;
+    // list mode: blockIdx.y selects a slice of the code tiles (partial minima are merged with a 64-bit atomicMin)
+    const int ct_per = (CT + gridDim.y - 1) / gridDim.y;
+    const int ct_begin = blockIdx.y * ct_per;
+    const int ct_end = (ct_begin + ct_per < CT) ? ct_begin + ct_per : CT;
+    const int total = (ct_end > ct_begin ? ct_end - ct_begin : 0) * DK;
+    if (total == 0) return;
     float b_reg[2][4];
     auto load_b = [&](int it) {
-        int ct = it / DK, dk = it - ct * DK;
+        int ct = ct_begin + it / DK, dk = it % DK;
         int d = dk * VK + lkc;
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
@@ -105,7 +117,7 @@ vq_assign_kernel(const float* __restrict__ z, const float* __restrict__ cb, cons
     __syncthreads();
     for (int it = 0; it < total; ++it) {
         const int cur = it & 1;
-        const int ct = it / DK, dk = it - ct * DK;
+        const int ct = ct_begin + it / DK, dk = it % DK;
         if (it + 1 < total) load_b(it + 1);
         const int dbase = dk * VK;
         const int klim = (D - dbase < VK) ? (D - dbase) : VK;
@@ -155,10 +167,19 @@ vq_assign_kernel(const float* __restrict__ z, const float* __restrict__ cb, cons
             int oi = __shfl_xor_sync(0xffffffffu, best_i[i], o);
             if (ov < best_v[i] || (ov == best_v[i] && oi < best_i[i])) { best_v[i] = ov; best_i[i] = oi; }
         }
-        if (tx == 0) best_idx_s[ty * 4 + i] = best_i[i];
+        if (tx == 0) {
+            best_idx_s[ty * 4 + i] = best_i[i];
+            if (row_list && grow_s[ty * 4 + i] >= 0) {
+                // order-preserving float -> uint map, code in the low word: atomicMin == (smallest distance, then smallest index)
+                uint32_t u = __float_as_uint(best_v[i]);
+                u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+                unsigned long long key = ((unsigned long long)u << 32) | (uint32_t)best_i[i];
+                atomicMin(reinterpret_cast<unsigned long long*>(idx_out) + grow_s[ty * 4 + i], key);
+            }
+        }
     }
     __syncthreads();
-
+    if (row_list) return;
     // ---- phase 2: gather, straight-through value, loss, histogram, EMA cluster sums
     const int warp = tid >> 5, lane = tid & 31;
     float sse_local = 0.f;
@@ -184,6 +205,59 @@ vq_assign_kernel(const float* __restrict__ z, const float* __restrict__ cb, cons
     if (sse) {
         sse_local = warp_sum(sse_local);
         if (lane == 0) atomicAdd(sse, (double)sse_local);
+    }
+}
+
+// phase D of the tensor-core path: one warp per row -- gather, straight-through value, loss, histogram, EMA cluster sums
+__global__ void vq_finish_kernel(const float* __restrict__ z, const float* __restrict__ cb, const int64_t* __restrict__ idx,
+                                 float* __restrict__ q_out, double* __restrict__ sse, float* __restrict__ counts,
+                                 float* __restrict__ dw, int64_t N, int K, int D) {
+    int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    float sse_local = 0.f;
+    if (row < N) {
+        int64_t code = idx[row];
+        if (code < 0 || code >= K) code = 0;
+        if (lane == 0 && counts) atomicAdd(counts + code, 1.0f);
+        const float* e = cb + code * D;
+        for (int d = lane; d < D; d += 32) {
+            float zv = z[row * D + d];
+            float diff = e[d] - zv;
+            sse_local = fmaf(diff, diff, sse_local);
+            if (q_out) q_out[row * D + d] = zv + diff;
+            if (dw) atomicAdd(dw + code * D + d, zv);
+        }
+    }
+    if (sse) {
+        sse_local = warp_sum(sse_local);
+        __shared__ float sh[8];
+        if (lane == 0) sh[threadIdx.x >> 5] = sse_local;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sh[i];
+            atomicAdd(sse, t);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+vq_assign_kernel(const float* __restrict__ z, const float* __restrict__ cb, const float* __restrict__ cb_sq, int order,
+                 float* __restrict__ q_out, int64_t* __restrict__ idx_out, double* __restrict__ sse,
+                 float* __restrict__ counts, float* __restrict__ dw, int64_t N, int K, int D) {
+    vq_assign_tile(blockIdx.x, z, cb, cb_sq, order, q_out, idx_out, sse, counts, dw, N, K, D, nullptr, nullptr);
+}
+
+// list mode: a fixed, small grid walks the (device-side counted) undecided rows, so a handful of rows costs a handful of
+// CTAs instead of a worst-case grid of early-exit launches
+__global__ void __launch_bounds__(256)
+vq_assign_rows_kernel(const float* __restrict__ z, const float* __restrict__ cb, const float* __restrict__ cb_sq, int order,
+                      int64_t* __restrict__ idx_out, int64_t N, int K, int D, const int* __restrict__ row_list,
+                      const int* __restrict__ n_rows_dev) {
+    const int64_t n = n_rows_dev[0];
+    for (int64_t tile = blockIdx.x; tile * VM < n; tile += gridDim.x) {
+        vq_assign_tile(tile, z, cb, cb_sq, order, nullptr, idx_out, nullptr, nullptr, nullptr, N, K, D, row_list, n_rows_dev);
+        __syncthreads();
     }
 }
 
@@ -259,6 +333,47 @@ extern "C" int vqb_vq_assign(const float* z, const float* codebook, int order, f
     VQB_CUDA(cudaFuncSetAttribute(vq_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     vq_assign_kernel<<<(unsigned)ceil_div64(N, VM), 256, smem, st>>>(z, codebook, cb_sq, order, q_out, idx_out, sse, counts, dw, N, K, D);
     VQB_CHECK_LAUNCH("vq_assign");
+    return VQB_OK;
+}
+
+namespace {
+__global__ void vq_keys_init_kernel(const int* __restrict__ row_list, const int* __restrict__ n_rows, int64_t* __restrict__ idx_out, int64_t N) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n_rows[0]) reinterpret_cast<unsigned long long*>(idx_out)[row_list[i]] = ~0ull;
+}
+__global__ void vq_keys_resolve_kernel(const int* __restrict__ row_list, const int* __restrict__ n_rows, int64_t* __restrict__ idx_out, int K) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n_rows[0]) {
+        unsigned long long key = reinterpret_cast<unsigned long long*>(idx_out)[row_list[i]];
+        uint32_t code = (uint32_t)(key & 0xffffffffull);
+        idx_out[row_list[i]] = (int64_t)((code < (uint32_t)K) ? code : 0);
+    }
+}
+}  // namespace
+
+int vqb_vq_exact_rows(const float* z, const float* codebook, const float* cb_sq, int order, const int* row_list,
+                      const int* n_rows_dev, int64_t* idx_out, int64_t N, int K, int D, cudaStream_t st) {
+    size_t smem = ((size_t)D * (VM + VPAD) + 2 * (size_t)VK * (VN + VPAD)) * sizeof(float);
+    if (smem > 227 * 1024 || D % 4 != 0) { vqb_set_error("vq_exact_rows: unsupported embedding_dim %d", D); return VQB_ERR_UNSUPPORTED; }
+    VQB_CUDA(cudaFuncSetAttribute(vq_assign_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // idx_out doubles as the 64-bit (distance, code) key array of the undecided rows; the grid covers the worst case
+    // (every row undecided), CTAs beyond the device-side count exit immediately; code tiles are split 8 ways so that a
+    // handful of undecided rows still spreads over many SMs
+    const int CT = (K + VN - 1) / VN;
+    const int ysplit = CT < 8 ? CT : 8;
+    vq_keys_init_kernel<<<(unsigned)ceil_div64(N, 256), 256, 0, st>>>(row_list, n_rows_dev, idx_out, N);
+    int64_t gx = ceil_div64(N, VM); if (gx > 2 * 148 / ysplit + 1) gx = 2 * 148 / ysplit + 1;     // ~2 CTAs per SM in total
+    dim3 grid((unsigned)gx, ysplit);
+    vq_assign_rows_kernel<<<grid, 256, smem, st>>>(z, codebook, cb_sq, order, idx_out, N, K, D, row_list, n_rows_dev);
+    vq_keys_resolve_kernel<<<(unsigned)ceil_div64(N, 256), 256, 0, st>>>(row_list, n_rows_dev, idx_out, K);
+    VQB_CHECK_LAUNCH("vq_exact_rows");
+    return VQB_OK;
+}
+
+int vqb_vq_finish(const float* z, const float* codebook, const int64_t* idx, float* q_out, double* sse, float* counts, float* dw,
+                  int64_t N, int K, int D, cudaStream_t st) {
+    vq_finish_kernel<<<(unsigned)ceil_div64(N * 32, 256), 256, 0, st>>>(z, codebook, idx, q_out, sse, counts, dw, N, K, D);
+    VQB_CHECK_LAUNCH("vq_finish");
     return VQB_OK;
 }
 

@@ -416,7 +416,8 @@ def mse_l1(a, b):
 # ------------------------------------------------------------------------------------------------------
 # vector quantisation
 # ------------------------------------------------------------------------------------------------------
-def vq_assign_raw(flat: torch.Tensor, codebook: torch.Tensor, order: int, want_q: bool = True, want_stats: bool = False):
+def vq_assign_raw(flat: torch.Tensor, codebook: torch.Tensor, order: int, want_q: bool = True, want_stats: bool = False,
+                  use_tc: Optional[bool] = None):
     """flat [N,D] fp32, codebook [K,D] fp32 -> (q or None, idx int64 [N], sse double[1], counts [K] or None, dw [K,D] or None)."""
     n, d = flat.shape
     k = codebook.shape[0]
@@ -426,6 +427,17 @@ def vq_assign_raw(flat: torch.Tensor, codebook: torch.Tensor, order: int, want_q
     sse = torch.zeros(1, dtype=torch.float64, device=dev)
     counts = torch.zeros(k, dtype=torch.float32, device=dev)
     dw = torch.zeros(k, d, dtype=torch.float32, device=dev) if want_stats else None
+    if use_tc is None:
+        use_tc = get_precision().name == 'fast'
+    if use_tc and d % 64 == 0 and d <= 256 and k % 8 == 0 and k <= 8192:
+        # tensor-core search with exact fp32 re-evaluation of near-ties: same indices as the exact kernel
+        ws_bytes = lib.load().vqb_vq_tc_workspace_bytes(n, k, d)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        und = torch.zeros(1, dtype=torch.int32, device=dev)
+        call('vqb_vq_assign_tc', ptr(flat), ptr(codebook), order, ptr(q), ptr(idx), ptr(sse), ptr(counts), ptr(dw), n, k, d, ptr(ws),
+             ws_bytes, ptr(und), stream())
+        vq_assign_raw.last_undecided = und
+        return q, idx, sse, counts, dw
     ws_bytes = lib.load().vqb_vq_workspace_bytes(n, k, d)
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
     call('vqb_vq_assign', ptr(flat), ptr(codebook), order, ptr(q), ptr(idx), ptr(sse), ptr(counts), ptr(dw), n, k, d, ptr(ws),
