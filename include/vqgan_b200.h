@@ -149,6 +149,11 @@ int vqb_act_bwd_from_output(const void* y, int y_dtype, const void* dy, int dy_d
  * (upfirdn2d with up=1: ops/upfirdn2d.py:120-208, kernels upfirdn2d.cu:97-341).  bwd = its adjoint (dx is [N,H,W,C]). */
 int vqb_fir4_fwd(const void* x, void* y, int dtype, int N, int H, int W, int C, int pad, int down, void* stream);
 int vqb_fir4_bwd(const void* dy, void* dx, int dtype, int N, int H, int W, int C, int pad, int down, void* stream);
+/* y[n,oh,ow,:] = x[n,2*oh+off,2*ow+off,:] and its adjoint (zero_upsample2 writes all of x).  A stride-2 3x3 convolution of the
+ * discriminator (conv2d_resample.py:119-122) runs in the bf16 fast mode as the stride-1 tcgen05 convolution at full
+ * resolution + decimate2(off=1); its backward is zero_upsample2 + the stride-1 dgrad / wgrad kernels. */
+int vqb_decimate2(const void* x, void* y, int dtype, int N, int H, int W, int C, int OH, int OW, int off, void* stream);
+int vqb_zero_upsample2(const void* y, void* x, int dtype, int N, int H, int W, int C, int OH, int OW, int off, void* stream);
 /* 2x2 / stride-2 max-pool (torchvision VGG16 features): y is [N,H,W,C], x is [N,2H,2W,C]; backward routes the
  * gradient to the first maximal element of each window (torch semantics) and writes all of dx */
 int vqb_maxpool2_fwd(const void* x, void* y, int dtype, int N, int H, int W, int C, void* stream);

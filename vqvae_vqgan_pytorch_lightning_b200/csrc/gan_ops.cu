@@ -239,10 +239,15 @@ inline int ew_grid(int64_t n) { int64_t b = (n + 255) / 256; if (b > 148 * 16) b
 
 }  // namespace
 
+int vqb_fir4_fwd_vec(const void* x, void* y, int dtype, int N, int H, int W, int C, int OH, int OW, int pad, int down, cudaStream_t st);
+int vqb_fir4_bwd_vec(const void* dy, void* dx, int dtype, int N, int H, int W, int C, int OH, int OW, int pad, int down, cudaStream_t st);
+
 extern "C" int vqb_fir4_fwd(const void* x, void* y, int dtype, int N, int H, int W, int C, int pad, int down, void* stream) {
     VQB_CHECK_ARG(x && y && N > 0 && H > 0 && W > 0 && C > 0 && pad >= 0 && down >= 1, "fir4_fwd: bad arguments");
     int OH = (H + 2 * pad - 4) / down + 1, OW = (W + 2 * pad - 4) / down + 1;
     VQB_CHECK_ARG(OH > 0 && OW > 0, "fir4_fwd: empty output");
+    if (C % ((dtype == VQB_BF16) ? 8 : 4) == 0 && (dtype == VQB_BF16 || dtype == VQB_F32) && down <= 2)
+        return vqb_fir4_fwd_vec(x, y, dtype, N, H, W, C, OH, OW, pad, down, as_stream(stream));
     VQB_DISPATCH_1(dtype, T, (fir4_fwd_kernel<T><<<ew_grid((int64_t)N * OH * OW * C), 256, 0, as_stream(stream)>>>(
                                  (const T*)x, (T*)y, N, H, W, C, OH, OW, pad, down));)
     VQB_CHECK_LAUNCH("fir4_fwd");
@@ -252,6 +257,8 @@ extern "C" int vqb_fir4_fwd(const void* x, void* y, int dtype, int N, int H, int
 extern "C" int vqb_fir4_bwd(const void* dy, void* dx, int dtype, int N, int H, int W, int C, int pad, int down, void* stream) {
     VQB_CHECK_ARG(dy && dx && N > 0 && H > 0 && W > 0 && C > 0 && pad >= 0 && down >= 1, "fir4_bwd: bad arguments");
     int OH = (H + 2 * pad - 4) / down + 1, OW = (W + 2 * pad - 4) / down + 1;
+    if (C % ((dtype == VQB_BF16) ? 8 : 4) == 0 && (dtype == VQB_BF16 || dtype == VQB_F32) && down <= 2)
+        return vqb_fir4_bwd_vec(dy, dx, dtype, N, H, W, C, OH, OW, pad, down, as_stream(stream));
     VQB_DISPATCH_1(dtype, T, (fir4_bwd_kernel<T><<<ew_grid((int64_t)N * H * W * C), 256, 0, as_stream(stream)>>>(
                                  (const T*)dy, (T*)dx, N, H, W, C, OH, OW, pad, down));)
     VQB_CHECK_LAUNCH("fir4_bwd");

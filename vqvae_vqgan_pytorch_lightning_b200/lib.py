@@ -36,6 +36,8 @@ SIGNATURES = {
     'vqb_conv2d_dgrad': (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     'vqb_fir4_fwd': (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     'vqb_fir4_bwd': (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
+    'vqb_decimate2': (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    'vqb_zero_upsample2': (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     'vqb_maxpool2_fwd': (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     'vqb_maxpool2_bwd': (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _i, _p]),
     'vqb_channel_affine': (_i, [_p, _i, _p, _i, _p, _p, _i64, _i, _p]),

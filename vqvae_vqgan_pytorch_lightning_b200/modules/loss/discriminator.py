@@ -87,6 +87,13 @@ class Conv2dLayer(nn.Module):
             return ops.conv2d(x, self.weight, self.bias, residual, pad=0, w_scale=w_scale, **kw)
         # conv2d_resample.py:119-122: pad k//2 + 1 each side, FIR, then a stride-2 conv without padding
         x = ops_gan.fir4(x, self.padding + 1, 1)
+        co, ci = self.weight.shape[0], self.weight.shape[1]
+        if (ops.get_precision().name == 'fast' and self.kernel_size == 3 and residual is None and ci % 64 == 0 and co % 128 == 0
+                and x.shape[2] >= 17 and x.shape[3] >= 9):
+            # tensor-core route: the same convolution at stride 1 ('same' padding, full resolution) keeps every 2nd output:
+            # valid_out[i] = same_out[i+1], strided_out[o] = valid_out[2o] = same_out[2o+1]
+            full = ops.conv2d(x, self.weight, self.bias, None, pad=1, stride=1, w_scale=w_scale, **kw)
+            return ops_gan.decimate2(full, (x.shape[2] - 3) // 2 + 1, (x.shape[3] - 3) // 2 + 1, 1)
         return ops.conv2d(x, self.weight, self.bias, residual, pad=0, stride=2, w_scale=w_scale, **kw)
 
 

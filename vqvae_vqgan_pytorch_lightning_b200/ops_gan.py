@@ -173,3 +173,29 @@ class FlattenNCHWFn(torch.autograd.Function):
 
 
 flatten_nchw = FlattenNCHWFn.apply
+
+
+class Decimate2Fn(torch.autograd.Function):
+    """y[..., oh, ow] = x[..., 2*oh+off, 2*ow+off]; backward = zero-insertion.  Together with a stride-1 'same' convolution at
+    full resolution this reproduces the discriminator's unpadded stride-2 3x3 convolution (conv2d_resample.py:119-122)."""
+
+    @staticmethod
+    def forward(ctx, x, oh, ow, off):
+        x = as_nhwc(x)
+        n, c, h, w = x.shape
+        y = empty_nhwc(n, c, oh, ow, x.dtype, x.device)
+        call('vqb_decimate2', ptr(x), ptr(y), dt(x), n, h, w, c, oh, ow, off, stream())
+        ctx.cfg = (n, c, h, w, oh, ow, off, x.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        n, c, h, w, oh, ow, off, dtype = ctx.cfg
+        dy = as_nhwc(dy, dtype)
+        dx = empty_nhwc(n, c, h, w, dtype, dy.device)
+        call('vqb_zero_upsample2', ptr(dy), ptr(dx), dt(dy), n, h, w, c, oh, ow, off, stream())
+        return dx, None, None, None
+
+
+def decimate2(x, oh, ow, off):
+    return Decimate2Fn.apply(x, oh, ow, off)
