@@ -196,6 +196,11 @@ def main():
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    t_start = time.time()
+
+    def stamp(what):                              # progress on stderr (the JSON line is the only thing on stdout)
+        if os.environ.get('VQB_BENCH_VERBOSE'):
+            print(f'[bench rank {rank} +{time.time() - t_start:6.1f}s] {what}', file=sys.stderr, flush=True)
 
     if args.impl == 'reference':
         run_reference(args, rank, world)
@@ -209,6 +214,7 @@ def main():
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=dev)
 
+    stamp('process group up')
     import vqvae_vqgan_pytorch_lightning_b200 as pkg
     from vqvae_vqgan_pytorch_lightning_b200.lightning_shim import Trainer
     pkg.lib.load()
@@ -245,9 +251,11 @@ def main():
         loss = trainer.run_step(x, step_idx[0]); step_idx[0] += 1
         return float(loss.detach().cpu())                                        # D2H read of the step's loss
 
+    stamp('model and inputs ready')
     for i in range(args.warmup):
         step_resident(i)
     barrier()
+    stamp('warm-up done')
 
     # ---- timed region 1: inputs resident in HBM (value, ms_per_step, roofline) ---------------------------------
     clocks = ClockSampler(local_rank)
@@ -276,6 +284,7 @@ def main():
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
+    stamp('timed regions done')
     clk = clocks.stop() if rank == 0 else None
 
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
