@@ -79,6 +79,50 @@ def disc_case(seed=21, B=4, S=64):
             'w_abs_sum': np.float64(sum(float(p.double().abs().sum()) for p in d.parameters()))}
 
 
+def disc_r1_case(seed=21, B=4, S=64, cost=10.0):
+    """loss.py:98-112,144-164 on the reference discriminator: non-saturating d_loss on (real, fake) + R1 penalty."""
+    from vqvae.modules.loss.stylegan2_discriminator.discriminator import Discriminator
+    from vqvae.modules.loss.loss import discriminator_loss
+    torch.manual_seed(seed)
+    d = Discriminator(S).train()
+    real = (torch.rand(B, 3, S, S) * 2 - 1)
+    fake = (torch.rand(B, 3, S, S) * 2 - 1)
+
+    def run(disc, real, fake):
+        real = real.clone().requires_grad_(True)
+        lr = disc(real)
+        lf = disc(fake)
+        d_loss = discriminator_loss(lr, lf, loss_type='non-saturating')
+        (g,) = torch.autograd.grad(outputs=lr.sum(), inputs=real, create_graph=True)
+        r1 = cost * g.pow(2).view(g.shape[0], -1).sum(1).mean()
+        (d_loss + r1).backward()
+        return lr, d_loss, r1, g
+
+    lr, d_loss, r1, g = run(d, real, fake)
+    names = [n for n, _ in d.named_parameters()]
+    norms = [float(p.grad.double().norm()) for _, p in d.named_parameters()]
+    # R1-only gradients (d_loss excluded) isolate the second-order path
+    d.zero_grad()
+    real2 = real.clone().requires_grad_(True)
+    (g2,) = torch.autograd.grad(outputs=d(real2).sum(), inputs=real2, create_graph=True)
+    (cost * g2.pow(2).view(B, -1).sum(1).mean()).backward()
+    norms_r1 = [float(p.grad.double().norm()) if p.grad is not None else 0.0 for _, p in d.named_parameters()]
+    r1_b64_conv0 = d.b64.conv0.weight.grad.numpy()[:8].copy()
+    r1_b4_fc_b = d.b4.fc.bias.grad.numpy().copy()
+    dd = Discriminator(S).train().double()
+    dd.load_state_dict({k: v.double() for k, v in d.state_dict().items()})
+    for mod in dd.modules():
+        if hasattr(mod, 'resample_filter'):
+            mod.resample_filter = mod.resample_filter.float()
+    _, d_loss64, r164, g64 = run(dd, real.double(), fake.double())
+    norms64 = [float(p.grad.norm()) for _, p in dd.named_parameters()]
+    return {'real': real.numpy(), 'fake': fake.numpy(), 'logits_real': lr.detach().numpy(), 'd_loss': np.float32(d_loss.item()),
+            'r1': np.float32(r1.item()), 'r1_f64': np.float64(r164.item()), 'grad_real': g.detach().numpy(),
+            'grad_real_f64': g64.detach().numpy(), 'grad_names': np.array(names), 'grad_norms': np.array(norms),
+            'grad_norms_f64': np.array(norms64), 'grad_norms_r1_only': np.array(norms_r1),
+            'r1_only_grad_b64_conv0_w': r1_b64_conv0, 'r1_only_grad_b4_fc_b': r1_b4_fc_b, 'cost': np.float32(cost)}
+
+
 def main():
     sys.path.insert(0, REF)
     sys.dont_write_bytecode = True
@@ -89,6 +133,9 @@ def main():
     res = disc_case()
     np.savez_compressed(os.path.join(OUT, 'gan_discriminator.npz'), **res)
     print('disc', res['logits'].ravel(), res['loss'])
+    res = disc_r1_case()
+    np.savez_compressed(os.path.join(OUT, 'gan_discriminator_r1.npz'), **res)
+    print('disc r1', res['d_loss'], res['r1'], res['r1_f64'], res['grad_norms'][:4], res['grad_norms_r1_only'][:4])
 
 
 if __name__ == '__main__':

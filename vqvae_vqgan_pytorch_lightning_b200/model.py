@@ -170,7 +170,7 @@ class VQVAE(BaseVQVAE, LightningModule):
             l1_loss, g_loss, p_loss, d_loss, g_weight, r1_penalty = zero, zero, zero, zero, 0., 0.
             ae_loss = q_loss + l2_loss
         self.log('g_weight', g_weight)
-        self.log('r1_penalty', r1_penalty)
+        self.log('r1_penalty', r1_penalty.detach() if torch.is_tensor(r1_penalty) else r1_penalty)
         self.log('train/loss', ae_loss.detach())
         self.log('train/l1_loss', l1_loss.detach())
         self.log('train/l2_loss', l2_loss.detach())

@@ -62,11 +62,13 @@ class VQLPIPSWithDiscriminator(nn.Module):
         return adaptive_weight * self.generator_weight
 
     def calculate_r1_regularization_term(self, logits_real, images, compute_r1: bool):
-        """loss.py:98-112.  R1 needs the gradient of a gradient through every discriminator kernel (double backward); those
-        second-order kernels are not built yet, so the term is refused loudly instead of being silently dropped."""
+        """loss.py:98-112: cost * mean_b sum (d sum(logits_real) / d images)^2, with the graph of that backward pass recorded
+        so that the penalty itself is differentiable in the discriminator weights.  Every discriminator op is twice
+        differentiable on the kernels (ops.ConvDgradFn / ActBwdFn and the adjoint pairs in ops_gan)."""
         if compute_r1:
-            raise NotImplementedError('R1 regularisation (double backward through the discriminator) is not built yet: set '
-                                      'adversarial_params.r1_reg_weight to null')
+            with ops.no_weight_gradients():
+                (gradients,) = torch.autograd.grad(outputs=logits_real.sum(), inputs=images, create_graph=True)
+            return self.r1_regularization_cost * gradients.pow(2).reshape(gradients.shape[0], -1).sum(1).mean()
         return 0.
 
     def forward_autoencoder(self, quantizer_loss, images, reconstructions, current_epoch: int, last_layer):
@@ -100,6 +102,8 @@ class VQLPIPSWithDiscriminator(nn.Module):
         if current_epoch >= self.adversarial_start_epoch:
             compute_r1 = (self.training and current_step % self.r1_regularization_every == 0 and
                           self.r1_regularization_cost is not None)
+            if compute_r1:
+                images = images.detach().requires_grad_(True)
             logits_real = self.discriminator(images)
             logits_fake = self.discriminator(reconstructions.detach())
             d_loss = discriminator_loss(logits_real, logits_fake, loss_type=self.adversarial_loss_type)

@@ -6,6 +6,7 @@ physical NHWC) so the module surface keeps the reference's shapes while the kern
 """
 from __future__ import annotations
 
+import contextlib
 import math
 from dataclasses import dataclass
 from typing import Optional, Tuple
@@ -13,7 +14,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import lib
-from .lib import ACT_NONE, ACT_SILU, ACT_TANH, BF16, F32, call, dt, ptr, stream
+from .lib import ACT_LRELU, ACT_NONE, ACT_RELU, ACT_SILU, ACT_TANH, BF16, F32, call, dt, ptr, stream
 
 CL = torch.channels_last
 
@@ -162,6 +163,29 @@ def _im2col64(x: torch.Tensor) -> torch.Tensor:
     return p
 
 
+class ActBwdFn(torch.autograd.Function):
+    """dpre = dy * act'(pre) * gain with act' recovered from the saved OUTPUT y (bias_act.py:143-210 with its `yref`).  Linear in
+    dy, and for the piecewise-linear activations of the discriminator (lrelu) act'' = 0, so the backward of this function is
+    the function itself; for the smooth activations only first order is built."""
+
+    @staticmethod
+    def forward(ctx, dy, y, act, alpha, gain, out_dtype):
+        dy = as_nhwc(dy) if dy.dim() == 4 else dy.contiguous()
+        dpre = torch.empty_like(dy, dtype=out_dtype, memory_format=torch.preserve_format)
+        call('vqb_act_bwd_from_output', ptr(y), dt(y), ptr(dy), dt(dy), ptr(dpre), dt(dpre), act, alpha, gain, dy.numel(), stream())
+        ctx.save_for_backward(y)
+        ctx.cfg = (act, alpha, gain, dy.dtype)
+        return dpre
+
+    @staticmethod
+    def backward(ctx, g):
+        (y,) = ctx.saved_tensors
+        act, alpha, gain, dy_dtype = ctx.cfg
+        if act not in (ACT_LRELU, ACT_RELU):
+            raise lib.VQBError('second-order backward is only built for piecewise-linear activations')
+        return ActBwdFn.apply(g, y, act, alpha, gain, dy_dtype), None, None, None, None, None
+
+
 class Conv2dFn(torch.autograd.Function):
     """y = act(conv2d(x, w) + b) * gain + residual   (reference: nn.Conv2d in vqvae/modules/autoencoder.py:55-61,
     102,114,133,153,170; fused epilogues replace the separate `x + h` of ResBlock.forward :77 and torch.tanh :180)."""
@@ -209,15 +233,14 @@ class Conv2dFn(torch.autograd.Function):
         if has_res:
             dres = dy if dy.dtype == res_dtype else as_nhwc(dy, res_dtype)
         if act != ACT_NONE:
-            dpre = torch.empty_like(dy, dtype=gdt, memory_format=torch.preserve_format)
-            call('vqb_act_bwd_from_output', ptr(y), dt(y), ptr(dy), dt(dy), ptr(dpre), dt(dpre), act, alpha, gain,
-                 dy.numel(), stream())
-            dy = dpre
+            dy = ActBwdFn.apply(dy, y.detach(), act, alpha, gain, gdt)
         elif gain != 1.0:
             raise lib.VQBError('gain != 1 requires an activation epilogue')
         _, _, oh, ow = dy.shape
         dx = dw = db = None
         route = _narrow_route(prec, ci, co, kh, kw, pad, stride)
+        if route is not None and torch.is_grad_enabled():
+            raise lib.VQBError('conv2d: the RGB-head im2col routes are not twice differentiable')
         if route == 'in' and ctx.needs_input_grad[1] and not ctx.needs_input_grad[0]:
             # dW[(tap,ci)][co] = im2col(x)^T dy : 1x1 tcgen05 wgrad with 64 (zero-padded) input channels
             dwp = torch.zeros(64 * co, dtype=torch.float32, device=x.device)
@@ -246,31 +269,97 @@ class Conv2dFn(torch.autograd.Function):
                 db = torch.zeros(co, dtype=torch.float32, device=x.device)
                 call('vqb_colsum', ptr(dy), dt(dy), ptr(db), n * oh * ow, co, stream())
             return dx, dw, db, dres, None, None, None, None, None, None, None
+        if torch.is_grad_enabled():
+            # the graph of this backward pass is being recorded (autograd.grad(..., create_graph=True): the R1 penalty,
+            # loss.py:98-112): produce dx through ConvDgradFn, itself differentiable in dy and in the weight
+            if (ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2])) and not _no_weight_grad:
+                raise lib.VQBError('conv2d: the weight / bias gradients are not twice differentiable; record the backward graph under '
+                                   'ops.no_weight_gradients() (as the reference does with conv2d_gradfix.no_weight_gradients)')
+            if ctx.needs_input_grad[0]:
+                ddt = in_dtype if in_dtype in (torch.float32, torch.bfloat16) else gdt
+                dx = ConvDgradFn.apply(dy, weight, h, w, pad, stride, w_scale, ddt)
+            return dx, None, None, dres, None, None, None, None, None, None, None
         if ctx.needs_input_grad[0]:
-            if stride != 1:
-                # strided forward conv: transposed-conv gather over the (virtually) zero-upsampled dy, fp32 SIMT
-                wd = _packed_weight(weight, 1, torch.float32, w_scale)
-                dx = empty_nhwc(n, ci, h, w, in_dtype if in_dtype in (torch.float32, torch.bfloat16) else gdt, x.device)
-                call('vqb_conv2d_dgrad', ptr(dy), dt(dy), ptr(wd), ptr(dx), dt(dx), n, h, w, ci, co, kh, kw, pad, stride, stream())
-            else:
-                dimpl = prec.conv_impl(co, ci, 1) if kh - 1 - pad == kh // 2 else 0       # tcgen05 path needs a 'same' dgrad
-                dyd = as_nhwc(dy, torch.bfloat16) if dimpl == 1 else dy
-                wd = _packed_weight(weight, 3 if dimpl == 1 else 1, torch.bfloat16 if dimpl == 1 else torch.float32, w_scale)
-                # dgrad = correlation of dy with the tap-flipped, channel-swapped weight; padding k-1-pad
-                ddt = in_dtype if (dimpl == 0 or in_dtype == torch.float32) else gdt
-                dx = _conv_fwd_raw(dimpl, dyd, wd, None, None, ddt, co, ci, kh, kw, kh - 1 - pad, 1, ACT_NONE, 0.0, 1.0)
-        if ctx.needs_input_grad[1]:
-            wimpl = prec.wgrad_impl(ci, co, stride) if x.dtype == torch.bfloat16 else 0
-            dyw = as_nhwc(dy, torch.bfloat16) if wimpl == 1 else dy
-            dwp = torch.zeros(kh * kw * ci * co, dtype=torch.float32, device=x.device)
-            call('vqb_conv2d_wgrad', wimpl, ptr(x), dt(x), ptr(dyw), dt(dyw), ptr(dwp), n, h, w, ci, co, kh, kw, pad, stride,
-                 stream())
-            dw = torch.empty(weight.shape, dtype=torch.float32, device=x.device)      # contiguous even if `weight` is a view
-            call('vqb_unpack_conv_wgrad', ptr(dwp), ptr(dw), co, ci, kh, kw, w_scale, stream())
-        if has_bias and ctx.needs_input_grad[2]:
+            dx = _dgrad_raw(dy, weight, h, w, pad, stride, w_scale, in_dtype if in_dtype in (torch.float32, torch.bfloat16) else gdt)
+        if ctx.needs_input_grad[1] and not _no_weight_grad:
+            dw = _wgrad_raw(x, dy, weight.shape, pad, stride, w_scale)
+        if has_bias and ctx.needs_input_grad[2] and not _no_weight_grad:
             db = torch.zeros(co, dtype=torch.float32, device=x.device)
             call('vqb_colsum', ptr(dy), dt(dy), ptr(db), n * oh * ow, co, stream())
         return dx, dw, db, dres, None, None, None, None, None, None, None
+
+
+def _dgrad_raw(dy: torch.Tensor, weight: torch.Tensor, h: int, w: int, pad: int, stride: int, w_scale: float, out_dtype):
+    """dx [n, ci, h, w] of y = conv2d(x, weight * w_scale, pad, stride) given dy (channels-last)."""
+    prec = get_precision()
+    co, ci, kh, kw = weight.shape
+    n = dy.shape[0]
+    if stride != 1:
+        # strided forward conv: transposed-conv gather over the (virtually) zero-upsampled dy, fp32 SIMT
+        wd = _packed_weight(weight, 1, torch.float32, w_scale)
+        dx = empty_nhwc(n, ci, h, w, out_dtype, dy.device)
+        call('vqb_conv2d_dgrad', ptr(dy), dt(dy), ptr(wd), ptr(dx), dt(dx), n, h, w, ci, co, kh, kw, pad, stride, stream())
+        return dx
+    dimpl = prec.conv_impl(co, ci, 1) if kh - 1 - pad == kh // 2 else 0       # tcgen05 path needs a 'same' dgrad
+    dyd = as_nhwc(dy, torch.bfloat16) if dimpl == 1 else dy
+    wd = _packed_weight(weight, 3 if dimpl == 1 else 1, torch.bfloat16 if dimpl == 1 else torch.float32, w_scale)
+    # dgrad = correlation of dy with the tap-flipped, channel-swapped weight; padding k-1-pad
+    ddt = out_dtype if (dimpl == 0 or out_dtype == torch.float32) else prec.act_dtype
+    return _conv_fwd_raw(dimpl, dyd, wd, None, None, ddt, co, ci, kh, kw, kh - 1 - pad, 1, ACT_NONE, 0.0, 1.0)
+
+
+def _wgrad_raw(x: torch.Tensor, dy: torch.Tensor, wshape, pad: int, stride: int, w_scale: float) -> torch.Tensor:
+    """dW [co, ci, kh, kw] fp32 of y = conv2d(x, W * w_scale, pad, stride) given x and dy (channels-last)."""
+    prec = get_precision()
+    co, ci, kh, kw = wshape
+    n, _, h, w = x.shape
+    wimpl = prec.wgrad_impl(ci, co, stride) if x.dtype == torch.bfloat16 else 0
+    dyw = as_nhwc(dy, torch.bfloat16) if wimpl == 1 else dy
+    dwp = torch.zeros(kh * kw * ci * co, dtype=torch.float32, device=x.device)
+    call('vqb_conv2d_wgrad', wimpl, ptr(x), dt(x), ptr(dyw), dt(dyw), ptr(dwp), n, h, w, ci, co, kh, kw, pad, stride, stream())
+    dw = torch.empty(tuple(wshape), dtype=torch.float32, device=x.device)         # contiguous even if the weight is a view
+    call('vqb_unpack_conv_wgrad', ptr(dwp), ptr(dw), co, ci, kh, kw, w_scale, stream())
+    return dw
+
+
+_no_weight_grad = False
+
+
+@contextlib.contextmanager
+def no_weight_gradients():
+    """conv2d_gradfix.no_weight_gradients (stylegan2_discriminator/ops/conv2d_gradfix.py): inside, conv backward passes
+    produce input gradients only (used while the R1 penalty records the graph of a backward pass)."""
+    global _no_weight_grad
+    old, _no_weight_grad = _no_weight_grad, True
+    try:
+        yield
+    finally:
+        _no_weight_grad = old
+
+
+class ConvDgradFn(torch.autograd.Function):
+    """dx = d conv2d(x, w * w_scale) / dx applied to dy: bilinear in (dy, w).  Only instantiated while the graph of a backward
+    pass is recorded; its own backward is a forward convolution (w.r.t. dy) and a weight-gradient kernel with the incoming
+    second-order signal in the role of the layer input (w.r.t. w)."""
+
+    @staticmethod
+    def forward(ctx, dy, weight, h, w, pad, stride, w_scale, out_dtype):
+        dy = as_nhwc(dy)
+        ctx.save_for_backward(dy, weight)
+        ctx.cfg = (pad, stride, w_scale)
+        return _dgrad_raw(dy, weight, h, w, pad, stride, w_scale, out_dtype)
+
+    @staticmethod
+    def backward(ctx, ddx):
+        dy, weight = ctx.saved_tensors
+        pad, stride, w_scale = ctx.cfg
+        g_dy = g_w = None
+        cdt = get_precision().act_dtype
+        if ctx.needs_input_grad[0]:
+            g_dy = Conv2dFn.apply(ddx, weight, None, None, pad, stride, ACT_NONE, 0.0, 1.0, dy.dtype, w_scale)
+        if ctx.needs_input_grad[1] and not _no_weight_grad:
+            g_w = _wgrad_raw(as_nhwc(ddx.detach(), cdt), dy.detach(), weight.shape, pad, stride, w_scale)
+        return g_dy, g_w, None, None, None, None, None, None
 
 
 def conv2d(x, weight, bias=None, residual=None, pad=0, stride=1, act=ACT_NONE, alpha=0.0, gain=1.0, out_dtype=None,

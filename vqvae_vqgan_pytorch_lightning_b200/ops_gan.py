@@ -25,10 +25,26 @@ class Fir4Fn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         n, c, h, w, pad, down, dtype = ctx.cfg
+        return Fir4AdjointFn.apply(dy, h, w, pad, down, dtype), None, None
+
+
+class Fir4AdjointFn(torch.autograd.Function):
+    """adjoint of Fir4Fn (a linear map), itself an autograd function so that the graph of a backward pass can be recorded
+    (R1 penalty): its backward is Fir4Fn again."""
+
+    @staticmethod
+    def forward(ctx, dy, h, w, pad, down, dtype):
         dy = as_nhwc(dy, dtype)
+        n, c = dy.shape[0], dy.shape[1]
         dx = empty_nhwc(n, c, h, w, dtype, dy.device)
         call('vqb_fir4_bwd', ptr(dy), ptr(dx), dt(dy), n, h, w, c, pad, down, stream())
-        return dx, None, None
+        ctx.cfg = (pad, down)
+        return dx
+
+    @staticmethod
+    def backward(ctx, ddx):
+        pad, down = ctx.cfg
+        return Fir4Fn.apply(ddx, pad, down), None, None, None, None, None
 
 
 def fir4(x, pad, down=1):
@@ -140,10 +156,30 @@ class MbstdFn(torch.autograd.Function):
     def backward(ctx, dy):
         (x,) = ctx.saved_tensors
         n, c, h, w = x.shape
+        if torch.is_grad_enabled():
+            # the graph of this backward pass is recorded (R1 penalty): the group standard deviation is the one non-linear,
+            # non-piecewise-linear op of the discriminator, so its backward depends on x itself.  The tensor is tiny
+            # (N x 512 x 4 x 4): restate the statistic with differentiable tensor ops and let the tape differentiate it.
+            with torch.enable_grad():
+                if not x.requires_grad:
+                    raise lib.VQBError('minibatch-stddev: the saved input lost its autograd history (layout/dtype copy in forward)')
+                y = _mbstd_composite(x.float(), ctx.g)
+                (dx,) = torch.autograd.grad(y, x, dy.float(), create_graph=True)
+            return dx.to(dy.dtype), None
         dy = as_nhwc(dy)
         dx = torch.empty_like(x, dtype=dy.dtype, memory_format=torch.preserve_format)
         call('vqb_mbstd_bwd', ptr(x), dt(x), ptr(dy), ptr(dx), dt(dy), n, ctx.g, h * w, c, stream())
         return dx, None
+
+
+def _mbstd_composite(x, g):
+    """discriminator.py:277-293 in tensor ops (fp32): used only for the second-order term of the R1 penalty."""
+    n, c, h, w = x.shape
+    y = x.reshape(g, n // g, c, h, w)
+    y = y - y.mean(dim=0)
+    y = (y.square().mean(dim=0) + 1e-8).sqrt()
+    y = y.mean(dim=[1, 2, 3]).reshape(-1, 1, 1, 1).repeat(g, 1, h, w)
+    return torch.cat([x, y], dim=1)
 
 
 def mbstd(x, group_size=4):
@@ -166,10 +202,23 @@ class FlattenNCHWFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         n, c, h, w, dtype = ctx.cfg
+        return UnflattenNCHWFn.apply(dy, c, h, w, dtype)
+
+
+class UnflattenNCHWFn(torch.autograd.Function):
+    """inverse (= adjoint) of FlattenNCHWFn: flat (c,h,w)-ordered [N, C*H*W, 1, 1] -> channels-last [N, C, H, W]."""
+
+    @staticmethod
+    def forward(ctx, dy, c, h, w, dtype):
+        n = dy.shape[0]
         g = dy.reshape(n, c, h, w).float().contiguous()
         dx = empty_nhwc(n, c, h, w, dtype, dy.device)
         call('vqb_nchw_to_nhwc', ptr(g), ptr(dx), dt(dx), n, c, h, w, 0, 0.0, 0.0, 0.0, 1.0, stream())
         return dx
+
+    @staticmethod
+    def backward(ctx, ddx):
+        return FlattenNCHWFn.apply(ddx), None, None, None, None
 
 
 flatten_nchw = FlattenNCHWFn.apply
@@ -191,10 +240,25 @@ class Decimate2Fn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         n, c, h, w, oh, ow, off, dtype = ctx.cfg
+        return ZeroUpsample2Fn.apply(dy, h, w, off, dtype), None, None, None
+
+
+class ZeroUpsample2Fn(torch.autograd.Function):
+    """adjoint of Decimate2Fn; its backward is Decimate2Fn (needed when the graph of a backward pass is recorded)."""
+
+    @staticmethod
+    def forward(ctx, dy, h, w, off, dtype):
         dy = as_nhwc(dy, dtype)
+        n, c, oh, ow = dy.shape
         dx = empty_nhwc(n, c, h, w, dtype, dy.device)
         call('vqb_zero_upsample2', ptr(dy), ptr(dx), dt(dy), n, h, w, c, oh, ow, off, stream())
-        return dx, None, None, None
+        ctx.cfg = (oh, ow, off)
+        return dx
+
+    @staticmethod
+    def backward(ctx, ddx):
+        oh, ow, off = ctx.cfg
+        return Decimate2Fn.apply(ddx, oh, ow, off), None, None, None, None
 
 
 def decimate2(x, oh, ow, off):
