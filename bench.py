@@ -230,6 +230,7 @@ def main():
     trainer = Trainer(max_epochs=1, num_training_batches=args.steps + args.warmup)
     trainer.attach(model)
     model.on_train_start()
+    model.training_augmentations = None           # the metric is quoted with augmentation off
 
     torch.manual_seed(1234 + rank)
     nbuf = 2

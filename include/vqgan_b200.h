@@ -47,6 +47,16 @@ int vqb_device_supports_tcgen05(void);
  * augmentation.  do_clamp=0 skips the clamp. */
 int vqb_nchw_to_nhwc(const float* x, void* y, int out_dtype, int64_t N, int64_t C, int64_t H, int64_t W,
                      int do_clamp, float lo, float hi, float shift, float scale, void* stream);
+
+/* Training-time input pipeline in one kernel (BaseVQVAE.preprocess_batch with training=True,
+ * vqvae/modules/abstract_modules/base_autoencoder.py:17-50): clamp[0,1] -> random resized crop (bilinear,
+ * align_corners=True; box[n] = {x0,y0,x1,y1} = source coordinates of the first / last crop pixel centre) -> optional
+ * horizontal flip (flip[n] != 0; flip may be NULL) -> (x - mean) / std.  images: NCHW, in_dtype 0 = fp32 in [0,1],
+ * 1 = fp16 in [0,1], 2 = uint8 in [0,255] (the three formats of the reference loaders, common_utils.py:60-71);
+ * out: NHWC [N][OH][OW][C] of out_dtype. */
+int vqb_crop_flip_normalize(const void* images, int in_dtype, void* out, int out_dtype, const float* boxes,
+                            const uint8_t* flip, int N, int C, int H, int W, int OH, int OW, float mean, float std,
+                            void* stream);
 /* NHWC (dtype in) -> NCHW fp32, y = x*scale + shift, optional clamp (base_autoencoder.py:52-61). */
 int vqb_nhwc_to_nchw(const void* x, int in_dtype, float* y, int64_t N, int64_t C, int64_t H, int64_t W,
                      float scale, float shift, int do_clamp, float lo, float hi, void* stream);
@@ -224,12 +234,12 @@ int vqb_row_sqnorm(const float* a, float* out, int64_t R, int D, void* stream);
  *   bwd_rows     : logp[N][K] is overwritten IN PLACE by G = dLoss/dd; dz += -2 G E and
  *                  dE += 2 E colsum(G) - 2 G^T Z are then 1x1-convolution dgrad/wgrad calls + combine_dcb */
 int vqb_vq_entropy_rows(float* dot_to_logp, const float* z, const float* codebook_sq, float temperature, int64_t* idx_out,
-                        double* sample_entropy_sum, int64_t N, int K, int D, void* stream);
+                        double* sample_entropy_sum, int64_t N, int K, int D, int argmax_target, void* stream);
 int vqb_vq_colsum_exp(const float* logp, float* out, int64_t N, int K, void* stream);
 int vqb_vq_entropy_finalize(const float* colsum_p, const double* sample_entropy_sum, float ratio, float* out, int64_t N, int K,
                             void* stream);
 int vqb_vq_entropy_bwd_rows(float* logp_to_g, const float* colsum_p, const float* g_loss, float ratio, float temperature,
-                            int64_t N, int K, void* stream);
+                            int64_t N, int K, const int64_t* argmax_idx, void* stream);
 int vqb_vq_entropy_combine_dcb(float* dcb, const float* codebook, const float* colsum_g, const float* gtz, int K, int D,
                                void* stream);
 

@@ -194,6 +194,7 @@ def _build_model(V, case, qtype, sd):
                     dict(num_embeddings=c['K'], embedding_dim=c['D'], type=qtype, params=qp, reinit_every_n_epochs=None),
                     None, dict(lr=1e-4, betas=[0.0, 0.99], eps=1e-8, weight_decay=1e-4, warmup_epochs=None, decay_epochs=None))
     model.load_state_dict(sd)
+    model.training_augmentations = None                    # the fixtures were produced without augmentation
     return model.cuda().train()
 
 
@@ -284,3 +285,23 @@ def test_gumbel_train_step_matches_reference_fixture(V, case):
     for n, p in model.named_parameters():
         if p.grad is not None and n in ref_norm:
             assert abs(float(p.grad.double().norm()) - ref_norm[n]) <= 5 * TOL * ref_norm[n] + 1e-7, n
+
+
+@pytest.mark.parametrize('loss_type', ['softmax', 'argmax'])
+def test_entropy_quantizer_matches_reference_module_fixture(V, loss_type):
+    """EntropyVectorQuantizer forward + backward, both target types (vector_quantizers.py:296-328: softmax targets, and
+    straight-through one-hot 'argmax' targets), against the reference module run on the same inputs."""
+    from vqvae_vqgan_pytorch_lightning_b200.modules.vector_quantizers import EntropyVectorQuantizer
+    g = C.golden(f'quantizer_entropy_{loss_type}')
+    K, D = g['codebook'].shape
+    q = EntropyVectorQuantizer(K, D, ent_loss_ratio=0.1, ent_temperature=0.01, ent_loss_type=loss_type, commitment_cost=0.25).cuda()
+    with torch.no_grad():
+        q.codebook.weight.copy_(torch.from_numpy(g['codebook']))
+    z = torch.from_numpy(g['z']).cuda().contiguous(memory_format=torch.channels_last).requires_grad_()
+    out, idx, loss = q(z)
+    (loss * 1.5 + (out * torch.from_numpy(g['g_q']).cuda()).sum()).backward()
+    assert torch.equal(idx.cpu(), torch.from_numpy(g['idx']))
+    assert C.rel_err(out, g['q']) < 1e-6
+    assert abs(float(loss) - float(g['loss'])) < 1e-5 * max(1.0, abs(float(g['loss'])))
+    assert C.rel_err(z.grad, g['dz']) < 1e-4
+    assert C.rel_err(q.codebook.weight.grad, g['dcb']) < 1e-4

@@ -1,4 +1,6 @@
 """CPU: pin the oracle (oracle/vqvae_oracle.py) against fixtures produced by the reference's own modules."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -97,3 +99,19 @@ def test_adamw_groups_collision():
     assert len(set(decay2) | set(no_decay2)) == len(enc) + len(dec) + 1
     assert 'quantizer.codebook.weight' in no_decay2 and 'encoder.conv_in.weight' in decay2
     assert 'encoder.norm.weight' in no_decay2 and 'decoder.blocks.2.conv.bias' in no_decay2
+
+
+@pytest.mark.parametrize('loss_type', ['softmax', 'argmax'])
+def test_oracle_entropy_quantizer_matches_reference_module(loss_type):
+    """oracle.vq_entropy (both target types of vector_quantizers.py:296-328) against the reference module's forward+backward."""
+    import numpy as np
+    import torch
+    from oracle import vqvae_oracle as O
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', f'quantizer_entropy_{loss_type}.npz'))
+    z = torch.from_numpy(g['z']).requires_grad_(); cb = torch.from_numpy(g['codebook']).requires_grad_()
+    q, idx, loss = O.vq_entropy(z, cb, 0.25, 0.1, 0.01, loss_type)
+    (loss * 1.5 + (q * torch.from_numpy(g['g_q'])).sum()).backward()
+    assert np.array_equal(idx.numpy(), g['idx'])
+    assert abs(float(loss) - float(g['loss'])) < 1e-6
+    assert np.allclose(z.grad.numpy(), g['dz'], atol=2e-5 * np.abs(g['dz']).max())
+    assert np.allclose(cb.grad.numpy(), g['dcb'], atol=2e-5 * np.abs(g['dcb']).max())

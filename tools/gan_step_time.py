@@ -16,7 +16,7 @@ if l is not None and l.get('adversarial_params'):
     l = dict(l); l['adversarial_params'] = dict(l['adversarial_params'], start_epoch=0, r1_reg_weight=(10. if a.r1 else None), r1_reg_every=1)
 torch.manual_seed(1234)
 model = pkg.VQVAE(image_size, ae, q, l, t, pretrained_lpips=False).cuda().train()
-tr = Trainer(); tr.attach(model); model.on_train_start()
+tr = Trainer(); tr.attach(model); model.on_train_start(); model.training_augmentations = None
 x = torch.rand(bs, 3, image_size, image_size, device='cuda')
 for i in range(2): tr.run_step(x, i)
 torch.cuda.synchronize()

@@ -16,7 +16,7 @@ conf = get_model_conf(os.path.join(ROOT, 'example_confs', 'ema_vqvae.yaml'))
 image_size, ae, q, l, t, bs = derive_confs(conf, 1, {'num_embeddings': 1024, 'cumulative_bs': a.batch})
 torch.manual_seed(1234)
 model = pkg.VQVAE(image_size, ae, q, l, t).cuda().train()
-tr = Trainer(); tr.attach(model); model.on_train_start()
+tr = Trainer(); tr.attach(model); model.on_train_start(); model.training_augmentations = None
 x = torch.rand(bs, 3, image_size, image_size, device='cuda')
 for i in range(2):
     tr.run_step(x, i)

@@ -28,7 +28,7 @@ __global__ void sqnorm_kernel(const float* __restrict__ a, float* __restrict__ o
 // in : m[row][k] = z_row . e_k ; out: m[row][k] = log softmax_k(-d/T), d = (|z|^2 - 2 dot) + |e_k|^2  (:337-340)
 __global__ void entropy_rows_kernel(float* __restrict__ m, const float* __restrict__ z, const float* __restrict__ cb_sq,
                                     float inv_t, int64_t* __restrict__ idx_out, double* __restrict__ ent_sum, int64_t N,
-                                    int K, int D) {
+                                    int K, int D, int argmax_target) {
     int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (row >= N) return;
@@ -61,8 +61,8 @@ __global__ void entropy_rows_kernel(float* __restrict__ m, const float* __restri
     }
     s = warp_sum(s); sa = warp_sum(sa);
     const float lse = amax + logf(s);
-    // sum_k p_k log p_k = sum_k p_k (a_k - lse) = sa/s - log(s)
-    if (lane == 0) atomicAdd(ent_sum, (double)(-(sa / s - logf(s))));
+    // softmax targets: -sum_k p_k log p_k = -(sa/s - log(s));  argmax targets (:311-315): -log p at the arg-max = log(s)
+    if (lane == 0) atomicAdd(ent_sum, argmax_target ? (double)logf(s) : (double)(-(sa / s - logf(s))));
     // pass 3: log-probabilities in place
     for (int k = lane; k < K; k += 32) mr[k] = -mr[k] * inv_t - lse;
 }
@@ -98,8 +98,10 @@ __global__ void entropy_finalize_kernel(const float* __restrict__ colsum_p, cons
 }
 
 // in: m = logp; out: m = G = dLoss/dd = -(1/T) p (g - sum_k p g),  g = c (-(logp+1) + log(mbar+eps) + mbar/(mbar+eps))
+// argmax targets (idx != null; colsum_p holds the code histogram): the straight-through one-hot t carries the softmax
+// Jacobian, and log p is differentiated with t as its weights:  G = -(1/T) [ p (g - sum_k p g) + c (p - t) ]
 __global__ void entropy_bwd_rows_kernel(float* __restrict__ m, const float* __restrict__ colsum_p, const float* __restrict__ g_loss,
-                                        float ratio, float inv_t, int64_t N, int K) {
+                                        float ratio, float inv_t, int64_t N, int K, const int64_t* __restrict__ idx) {
     int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (row >= N) return;
@@ -118,7 +120,9 @@ __global__ void entropy_bwd_rows_kernel(float* __restrict__ m, const float* __re
         float lp = mr[k], p = expf(lp);
         float mb = colsum_p[k] * invn;
         float g = c * (-(lp + 1.0f) + logf(mb + 1e-5f) + mb / (mb + 1e-5f));
-        mr[k] = -inv_t * p * (g - r);
+        float v = p * (g - r);
+        if (idx) v += c * (p - (idx[row] == k ? 1.0f : 0.0f));
+        mr[k] = -inv_t * v;
     }
 }
 
@@ -240,11 +244,12 @@ extern "C" int vqb_row_sqnorm(const float* a, float* out, int64_t R, int D, void
 }
 
 extern "C" int vqb_vq_entropy_rows(float* dot_to_logp, const float* z, const float* codebook_sq, float temperature,
-                                   int64_t* idx_out, double* sample_entropy_sum, int64_t N, int K, int D, void* stream) {
+                                   int64_t* idx_out, double* sample_entropy_sum, int64_t N, int K, int D, int argmax_target,
+                                   void* stream) {
     VQB_CHECK_ARG(dot_to_logp && z && codebook_sq && idx_out && sample_entropy_sum && N > 0 && K > 0 && D > 0 && temperature > 0.f,
                   "vq_entropy_rows: bad arguments");
     entropy_rows_kernel<<<(unsigned)ceil_div64(N * 32, 256), 256, 0, as_stream(stream)>>>(dot_to_logp, z, codebook_sq, 1.0f / temperature,
-                                                                                           idx_out, sample_entropy_sum, N, K, D);
+                                                                                           idx_out, sample_entropy_sum, N, K, D, argmax_target);
     VQB_CHECK_LAUNCH("vq_entropy_rows");
     return VQB_OK;
 }
@@ -268,10 +273,10 @@ extern "C" int vqb_vq_entropy_finalize(const float* colsum_p, const double* samp
 }
 
 extern "C" int vqb_vq_entropy_bwd_rows(float* logp_to_g, const float* colsum_p, const float* g_loss, float ratio, float temperature,
-                                       int64_t N, int K, void* stream) {
+                                       int64_t N, int K, const int64_t* argmax_idx, void* stream) {
     VQB_CHECK_ARG(logp_to_g && colsum_p && N > 0 && K > 0 && temperature > 0.f, "vq_entropy_bwd_rows: bad arguments");
     entropy_bwd_rows_kernel<<<(unsigned)ceil_div64(N * 32, 256), 256, 0, as_stream(stream)>>>(logp_to_g, colsum_p, g_loss, ratio,
-                                                                                               1.0f / temperature, N, K);
+                                                                                               1.0f / temperature, N, K, argmax_idx);
     VQB_CHECK_LAUNCH("vq_entropy_bwd_rows");
     return VQB_OK;
 }

@@ -25,6 +25,7 @@ SIGNATURES = {
     'vqb_version': (C.c_char_p, []),
     'vqb_device_supports_tcgen05': (_i, []),
     'vqb_nchw_to_nhwc': (_i, [_p, _p, _i, _i64, _i64, _i64, _i64, _i, _f, _f, _f, _f, _p]),
+    'vqb_crop_flip_normalize': (_i, [_p, _i, _p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _f, _f, _p]),
     'vqb_nhwc_to_nchw': (_i, [_p, _i, _p, _i64, _i64, _i64, _i64, _f, _f, _i, _f, _f, _p]),
     'vqb_convert': (_i, [_p, _i, _p, _i, _i64, _p]),
     'vqb_pack_conv_weight': (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _f, _p]),
@@ -65,10 +66,10 @@ SIGNATURES = {
     'vqb_vq_backward': (_i, [_p, _p, _p, _p, _p, _f, _f, _p, _p, _i64, _i, _i, _p]),
     'vqb_vq_gather': (_i, [_p, _p, _p, _i64, _i, _i, _p]),
     'vqb_row_sqnorm': (_i, [_p, _p, _i64, _i, _p]),
-    'vqb_vq_entropy_rows': (_i, [_p, _p, _p, _f, _p, _p, _i64, _i, _i, _p]),
+    'vqb_vq_entropy_rows': (_i, [_p, _p, _p, _f, _p, _p, _i64, _i, _i, _i, _p]),
     'vqb_vq_colsum_exp': (_i, [_p, _p, _i64, _i, _p]),
     'vqb_vq_entropy_finalize': (_i, [_p, _p, _f, _p, _i64, _i, _p]),
-    'vqb_vq_entropy_bwd_rows': (_i, [_p, _p, _p, _f, _f, _i64, _i, _p]),
+    'vqb_vq_entropy_bwd_rows': (_i, [_p, _p, _p, _f, _f, _i64, _i, _p, _p]),
     'vqb_vq_entropy_combine_dcb': (_i, [_p, _p, _p, _p, _i, _i, _p]),
     'vqb_gumbel_rows_fwd': (_i, [_p, _p, _f, _i, _p, _p, _p, _i64, _i, _p]),
     'vqb_gumbel_rows_bwd': (_i, [_p, _p, _f, _p, _p, _f, _p, _i64, _i, _p]),

@@ -7,6 +7,7 @@ from abc import ABC, abstractmethod
 import torch
 
 from ... import ops
+from ...augment import RandomResizedCropFlip
 
 
 class BaseVQVAE(ABC):
@@ -14,19 +15,25 @@ class BaseVQVAE(ABC):
     def __init__(self, image_size: int):
         self.image_size = image_size
         # the reference applies kornia RandomResizedCrop(0.7-1, ratio 1) + RandomHorizontalFlip when training
-        # (base_autoencoder.py:17-22,45-46).  kornia is un-pinned and absent here (PARITY UNPINNED); augmentation is
-        # the "next" row 8f-3 of the scope table and is off unless a callable is installed here.
-        self.training_augmentations = None
+        # (base_autoencoder.py:17-22,45-46): here one fused kernel (augment.py; random parameter stream PARITY UNPINNED,
+        # kornia is absent).  Set to None to train without augmentation (parity fixtures, bench), or to any callable
+        # images -> images.
+        self.training_augmentations = RandomResizedCropFlip(image_size)
         self.scheduler = None
         self.train_epoch_usage_count = None
         self.val_epoch_usage_count = None
 
     @torch.no_grad()
     def preprocess_batch(self, images: torch.Tensor, training: bool = False) -> torch.Tensor:
-        """images [B,C,H,W] fp32 in [0,1] -> clamp, (optional augmentation), (x-0.5)/0.5; returned channels-last fp32.
-        One fused kernel (vqb_nchw_to_nhwc) instead of clamp + Normalize (base_autoencoder.py:41-50)."""
+        """images [B,C,H,W] in [0,1] (fp32 / fp16) or uint8 -> clamp, (training: augmentation), (x-0.5)/0.5; returned
+        channels-last fp32.  One fused kernel either way (vqb_crop_flip_normalize / vqb_nchw_to_nhwc) instead of clamp +
+        kornia + Normalize (base_autoencoder.py:41-50)."""
         if training and self.training_augmentations is not None:
+            if getattr(self.training_augmentations, 'fused', False):
+                return self.training_augmentations(images, torch.float32)
             images = self.training_augmentations(images)
+        if images.dtype == torch.uint8:
+            images = images.float() / 255.0
         return ops.images_to_nhwc(images, torch.float32, normalize=True)
 
     @torch.no_grad()

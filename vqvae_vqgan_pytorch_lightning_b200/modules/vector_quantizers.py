@@ -118,11 +118,10 @@ class EntropyVectorQuantizer(BaseVectorQuantizer):
         self.commitment_cost = commitment_cost
 
     def forward(self, x: torch.Tensor):
-        if self.ent_loss_type != 'softmax':
-            if self.ent_loss_type == 'argmax':
-                raise NotImplementedError("ent_loss_type='argmax' (straight-through one-hot targets, :311-315) is not built yet")
+        if self.ent_loss_type not in ('softmax', 'argmax'):
             raise ValueError('Entropy loss {} not supported'.format(self.ent_loss_type))
-        return ops.vq_entropy(x, self.codebook.weight, self.commitment_cost, self.ent_loss_ratio, self.ent_temperature)
+        return ops.vq_entropy(x, self.codebook.weight, self.commitment_cost, self.ent_loss_ratio, self.ent_temperature,
+                              argmax_target=(self.ent_loss_type == 'argmax'))
 
     @torch.no_grad()
     def vec_to_codes(self, x: torch.Tensor) -> torch.Tensor:

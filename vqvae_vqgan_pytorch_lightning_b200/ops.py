@@ -619,7 +619,7 @@ class VQEntropyFn(torch.autograd.Function):
     The N x K matrix exists once (fp32) and is transformed in place: dot -> log p (forward), log p -> dLoss/dd (backward)."""
 
     @staticmethod
-    def forward(ctx, z, codebook, beta, ratio, temperature):
+    def forward(ctx, z, codebook, beta, ratio, temperature, argmax_target=False):
         z = as_nhwc(z, torch.float32)
         b, d, h, w = z.shape
         flat = z.permute(0, 2, 3, 1).reshape(b * h * w, d)
@@ -633,9 +633,14 @@ class VQEntropyFn(torch.autograd.Function):
         call('vqb_row_sqnorm', ptr(cb), ptr(cb_sq), k, d, stream())
         idx = torch.empty(n, dtype=torch.int64, device=dev)
         ent_sum = torch.zeros(1, dtype=torch.float64, device=dev)
-        call('vqb_vq_entropy_rows', ptr(m), ptr(flat), ptr(cb_sq), temperature, ptr(idx), ptr(ent_sum), n, k, d, stream())
-        colsum_p = torch.zeros(k, dtype=torch.float32, device=dev)
-        call('vqb_vq_colsum_exp', ptr(m), ptr(colsum_p), n, k, stream())
+        call('vqb_vq_entropy_rows', ptr(m), ptr(flat), ptr(cb_sq), temperature, ptr(idx), ptr(ent_sum), n, k, d, int(argmax_target),
+             stream())
+        if argmax_target:
+            # straight-through one-hot targets (:311-315): the batch-mean distribution is the code histogram
+            colsum_p = torch.bincount(idx, minlength=k).float()
+        else:
+            colsum_p = torch.zeros(k, dtype=torch.float32, device=dev)
+            call('vqb_vq_colsum_exp', ptr(m), ptr(colsum_p), n, k, stream())
         ent = torch.empty(2, dtype=torch.float32, device=dev)
         call('vqb_vq_entropy_finalize', ptr(colsum_p), ptr(ent_sum), ratio, ptr(ent), n, k, stream())
         q = torch.empty_like(flat)
@@ -644,7 +649,7 @@ class VQEntropyFn(torch.autograd.Function):
         call('vqb_diff_sums', ptr(q), F32, ptr(flat), F32, ptr(sums), flat.numel(), stream())
         loss = (sums[0] * ((1.0 + beta) / flat.numel())).float() + ent[0]
         ctx.save_for_backward(flat, q, idx, m, colsum_p, cb)
-        ctx.cfg = (beta, ratio, temperature, z.shape)
+        ctx.cfg = (beta, ratio, temperature, z.shape, bool(argmax_target))
         qz = q.reshape(b, h, w, d).permute(0, 3, 1, 2)
         ctx.mark_non_differentiable(idx)
         return qz, idx.reshape(b, h * w), loss
@@ -652,7 +657,7 @@ class VQEntropyFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_q, _g_idx, g_loss):
         flat, q, idx, m, colsum_p, cb = ctx.saved_tensors
-        beta, ratio, temperature, zshape = ctx.cfg
+        beta, ratio, temperature, zshape, argmax_target = ctx.cfg
         n, d = flat.shape
         k = cb.shape[0]
         dev = flat.device
@@ -662,7 +667,8 @@ class VQEntropyFn(torch.autograd.Function):
         dcb = torch.zeros(k, d, dtype=torch.float32, device=dev)
         call('vqb_vq_backward', ptr(flat), ptr(q), ptr(idx), ptr(gq), ptr(gl), beta, 1.0, ptr(dz), ptr(dcb), n, k, d, stream())
         g = m.clone()                                                                    # keep logp intact for a second backward call
-        call('vqb_vq_entropy_bwd_rows', ptr(g), ptr(colsum_p), ptr(gl), ratio, temperature, n, k, stream())
+        call('vqb_vq_entropy_bwd_rows', ptr(g), ptr(colsum_p), ptr(gl), ratio, temperature, n, k, ptr(idx) if argmax_target else None,
+             stream())
         dz = _gemm_nk(g, cb, k, d, residual=dz, gain=-2.0)                               # dz += -2 G E   (wp[(k)][d] = E itself)
         gtz = torch.zeros(k * d, dtype=torch.float32, device=dev)
         call('vqb_conv2d_wgrad', 0, ptr(g), F32, ptr(flat), F32, ptr(gtz), n, 1, 1, k, d, 1, 1, 0, 1, stream())   # G^T Z
@@ -670,11 +676,11 @@ class VQEntropyFn(torch.autograd.Function):
         call('vqb_colsum', ptr(g), F32, ptr(colsum_g), n, k, stream())
         call('vqb_vq_entropy_combine_dcb', ptr(dcb), ptr(cb), ptr(colsum_g), ptr(gtz), k, d, stream())
         b, _, h, w = zshape
-        return dz.reshape(b, h, w, d).permute(0, 3, 1, 2), dcb, None, None, None
+        return dz.reshape(b, h, w, d).permute(0, 3, 1, 2), dcb, None, None, None, None
 
 
-def vq_entropy(z, codebook, beta, ratio, temperature):
-    return VQEntropyFn.apply(z, codebook, beta, ratio, temperature)
+def vq_entropy(z, codebook, beta, ratio, temperature, argmax_target=False):
+    return VQEntropyFn.apply(z, codebook, beta, ratio, temperature, argmax_target)
 
 
 class GumbelRowsFn(torch.autograd.Function):
