@@ -191,6 +191,8 @@ def main():
     ap.add_argument('--cpu-batch', type=int, default=2)
     ap.add_argument('--cpu-steps', type=int, default=2)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--ncu-step', action='store_true', help='after the warm-up run ONE step between cudaProfilerStart/Stop and exit '
+                    '(for `ncu --profile-from-start off`; prints no bench line)')
     args = ap.parse_args()
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -258,6 +260,12 @@ def main():
         step_resident(i)
     barrier()
     stamp('warm-up done')
+    if args.ncu_step:
+        torch.cuda.profiler.start()
+        step_resident(0)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
 
     # ---- timed region 1: inputs resident in HBM (value, ms_per_step, roofline) ---------------------------------
     clocks = ClockSampler(local_rank)

@@ -12,9 +12,26 @@
 namespace {
 
 // sigmoid via MUFU ex2 + fast reciprocal: ~1e-6 relative error, a fraction of the instruction count of expf + IEEE division
-__device__ __forceinline__ float fast_sigmoid(float t) { return __fdividef(1.0f, 1.0f + __expf(-t)); }
-__device__ __forceinline__ float fast_silu(float t) { return t * fast_sigmoid(t); }
-__device__ __forceinline__ float fast_silu_grad(float t) { float s = fast_sigmoid(t); return s * fmaf(t, 1.0f - s, 1.0f); }
+// (two MUFU ops per element).  At full HBM rate these kernels process ~6 elements / clk / SM, i.e. ~12 of the 16 MUFU
+// issue slots per clock -- the SFU pipe, not HBM, paces them.  For bf16 activations (APPROX) the sigmoid is ONE MUFU op,
+// 0.5 * tanh.approx(0.5 t) + 0.5 (max abs error ~2.5e-4, an order of magnitude below bf16 rounding of the result).
+__device__ __forceinline__ float tanh_approx(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+template <bool APPROX>
+__device__ __forceinline__ float fast_sigmoid(float t) {
+    if constexpr (APPROX) return fmaf(0.5f, tanh_approx(0.5f * t), 0.5f);
+    else return __fdividef(1.0f, 1.0f + __expf(-t));
+}
+template <bool APPROX> __device__ __forceinline__ float fast_silu(float t) { return t * fast_sigmoid<APPROX>(t); }
+// the same two functions of u = t/2 (the halving is folded into the per-channel scale/shift by the callers):
+//   silu(t) = u (1 + tanh u);   2 silu'(t) = (1 + tanh u)(1 + u (1 - tanh u))      -- 3 and 5 instructions incl. the MUFU
+__device__ __forceinline__ float silu_of_half(float u) { return fmaf(u, tanh_approx(u), u); }
+__device__ __forceinline__ float silu_grad2_of_half(float u) {
+    const float th = tanh_approx(u);
+    const float k = 1.0f + fmaf(-u, th, u);
+    return fmaf(th, k, k);
+}
+template <bool APPROX>
+__device__ __forceinline__ float fast_silu_grad(float t) { float s = fast_sigmoid<APPROX>(t); return s * fmaf(t, 1.0f - s, 1.0f); }
 
 struct GnLaunch {
     dim3 grid, block;
@@ -123,6 +140,10 @@ __global__ void gn_stats_kernel(const T* __restrict__ x, double* __restrict__ su
     }
 }
 
+// bf16 / VEC = 8 statistics with the cp.async ring of gn_bwd_reduce_async_kernel (declared below): same sums
+template <int D>
+__global__ void gn_stats_async_kernel(const bf16* __restrict__ x, double* __restrict__ sums, int HW, int C, int G, int ppb);
+
 __global__ void gn_finalize_kernel(const double* __restrict__ sums, float* __restrict__ stats, int total, double n, double eps) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
@@ -150,6 +171,12 @@ __global__ void gn_apply_kernel(const TI* __restrict__ x, const float* __restric
         sc[j] = rstd * gamma[c0 + j];
         sh_[j] = beta[c0 + j] - mean * sc[j];
     }
+    constexpr bool APPROX = (sizeof(TI) == 2 && sizeof(TO) == 2);      // bf16 in and out: single-MUFU SiLU on u = t/2
+    const bool half_arg = APPROX && act == VQB_ACT_SILU;
+    if (half_arg) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) { sc[j] *= 0.5f; sh_[j] *= 0.5f; }
+    }
     const int p0 = blockIdx.x * ppb;
     int p1 = p0 + ppb; if (p1 > HW) p1 = HW;
     const int64_t base = (int64_t)b * HW * C + c0;
@@ -160,14 +187,15 @@ __global__ void gn_apply_kernel(const TI* __restrict__ x, const float* __restric
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
             float t = fmaf(v[j], sc[j], sh_[j]);
-            o[j] = (act == VQB_ACT_SILU) ? fast_silu(t) : t;
+            if constexpr (APPROX) o[j] = (act == VQB_ACT_SILU) ? silu_of_half(t) : t;
+            else o[j] = (act == VQB_ACT_SILU) ? fast_silu<false>(t) : t;
         }
         stv<TO, VEC>(y + base + (int64_t)p * C, o);
     }
 }
 
 // ---- backward reduce ---------------------------------------------------------------------------------
-template <typename TI, typename TG, int VEC>
+template <typename TI, typename TG, int VEC, int UNR>
 __global__ void gn_bwd_reduce_kernel(const TI* __restrict__ x, const TG* __restrict__ dy, const float* __restrict__ stats,
                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                      double* __restrict__ part, int HW, int C, int G, int ppb, int act) {
@@ -185,10 +213,16 @@ __global__ void gn_bwd_reduce_kernel(const TI* __restrict__ x, const TG* __restr
         sf[j] = beta[c0 + j] - mean * sc[j];
         a[j] = 0.f; q[j] = 0.f;
     }
+    constexpr bool APPROX = (sizeof(TI) == 2 && sizeof(TG) == 2);
+    const bool half_arg = APPROX && act == VQB_ACT_SILU;               // accumulate 2 ds, halve the sums once at the end
+    if (half_arg) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) { sc[j] *= 0.5f; sf[j] *= 0.5f; }
+    }
     const int p0 = blockIdx.x * ppb;
     int p1 = p0 + ppb; if (p1 > HW) p1 = HW;
     const int64_t base = (int64_t)b * HW * C + c0;
-#pragma unroll 4
+#pragma unroll UNR
     for (int p = p0 + threadIdx.y; p < p1; p += blockDim.y) {
         float v[VEC], g[VEC];
         ldv<TI, VEC>(x + base + (int64_t)p * C, v);
@@ -196,10 +230,15 @@ __global__ void gn_bwd_reduce_kernel(const TI* __restrict__ x, const TG* __restr
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
             float ds = g[j];
-            if (act == VQB_ACT_SILU) ds *= fast_silu_grad(fmaf(v[j], sc[j], sf[j]));
+            if constexpr (APPROX) { if (act == VQB_ACT_SILU) ds *= silu_grad2_of_half(fmaf(v[j], sc[j], sf[j])); }
+            else { if (act == VQB_ACT_SILU) ds *= fast_silu_grad<false>(fmaf(v[j], sc[j], sf[j])); }
             a[j] += ds;
             q[j] = fmaf(ds, v[j], q[j]);             // sum ds*x; converted to sum ds*xhat below
         }
+    }
+    if (half_arg) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) { a[j] *= 0.5f; q[j] *= 0.5f; }
     }
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
@@ -222,6 +261,225 @@ __global__ void gn_bwd_reduce_kernel(const TI* __restrict__ x, const TG* __restr
         atomicAdd(&part[((int64_t)b * C + c) * 2 + 0], sa);
         atomicAdd(&part[((int64_t)b * C + c) * 2 + 1], sq);
     }
+}
+
+// ---- backward reduce, bf16, asynchronous-copy pipeline -----------------------------------------------------
+// Same result as gn_bwd_reduce_kernel<bf16, bf16, 8>.  The plain-load version is latency-bound (ncu: >80 % of the stall
+// samples on the first use of a loaded register, 3.5 TB/s): the loads a thread keeps in flight are limited by registers.
+// Here every thread streams ITS OWN 16-byte pieces of x and dy through a private DEPTH-deep ring in shared memory with
+// cp.async (LDGSTS, no registers held while in flight, no inter-thread synchronisation -- only cp.async.wait_group):
+// bytes in flight per SM = DEPTH * 32 B * resident threads.
+constexpr int GN_ASYNC_DEPTH = 12;
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+
+template <int D>
+__global__ void gn_bwd_reduce_async_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, const float* __restrict__ stats,
+                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                           double* __restrict__ part, int HW, int C, int G, int ppb, int act) {
+    constexpr int VEC = 8;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint4* ring = reinterpret_cast<uint4*>(smem_raw);            // [D][2][nthreads]
+    double* sh = reinterpret_cast<double*>(smem_raw);            // reused after the loop: [2][ty][tx*VEC]
+    const int b = blockIdx.y;
+    const int c0 = threadIdx.x * VEC;
+    const int cg = C / G;
+    const int tx = blockDim.x, ty = blockDim.y, nthr = tx * ty;
+    const int tid = threadIdx.y * tx + threadIdx.x;
+    float sc[VEC], sf[VEC], a[VEC], q[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+        int g = (c0 + j) / cg;
+        const float mean = stats[((int64_t)b * G + g) * 2];
+        const float rstd = stats[((int64_t)b * G + g) * 2 + 1];
+        sc[j] = rstd * gamma[c0 + j];
+        sf[j] = beta[c0 + j] - mean * sc[j];
+        a[j] = 0.f; q[j] = 0.f;
+    }
+    const bool silu = (act == VQB_ACT_SILU);
+    if (silu) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) { sc[j] *= 0.5f; sf[j] *= 0.5f; }
+    }
+    const int p0 = blockIdx.x * ppb;
+    int p1 = p0 + ppb; if (p1 > HW) p1 = HW;
+    const int64_t base = (int64_t)b * HW * C + c0;
+    const int first = p0 + threadIdx.y;
+    const int niter = first < p1 ? (p1 - first + ty - 1) / ty : 0;
+#pragma unroll
+    for (int s = 0; s < D; ++s) {
+        if (s < niter) {
+            const int64_t off = base + (int64_t)(first + s * ty) * C;
+            cp_async16(&ring[(s * 2 + 0) * nthr + tid], x + off);
+            cp_async16(&ring[(s * 2 + 1) * nthr + tid], dy + off);
+        }
+        cp_async_commit();
+    }
+    int slot = 0;
+    for (int it = 0; it < niter; ++it) {
+        cp_async_wait<D - 1>();                                   // the group of iteration `it` has landed
+        const uint4 ux = ring[(slot * 2 + 0) * nthr + tid];
+        const uint4 ug = ring[(slot * 2 + 1) * nthr + tid];
+        float v[VEC], g[VEC];
+        unpack8(ux, v); unpack8(ug, g);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            float ds = g[j];
+            if (silu) ds *= silu_grad2_of_half(fmaf(v[j], sc[j], sf[j]));
+            a[j] += ds;
+            q[j] = fmaf(ds, v[j], q[j]);
+        }
+        if (it + D < niter) {                                     // refill the slot just consumed (its values are in registers)
+            const int64_t off = base + (int64_t)(first + (it + D) * ty) * C;
+            cp_async16(&ring[(slot * 2 + 0) * nthr + tid], x + off);
+            cp_async16(&ring[(slot * 2 + 1) * nthr + tid], dy + off);
+        }
+        cp_async_commit();
+        slot = (slot + 1 == D) ? 0 : slot + 1;
+    }
+    cp_async_wait<0>();
+    if (silu) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) { a[j] *= 0.5f; q[j] *= 0.5f; }
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+        int g = (c0 + j) / cg;
+        const float mean = stats[((int64_t)b * G + g) * 2];
+        const float rstd = stats[((int64_t)b * G + g) * 2 + 1];
+        q[j] = rstd * (q[j] - mean * a[j]);
+    }
+    __syncthreads();                                              // every thread is done with its ring before the reuse
+    const int row = tx * VEC;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+        sh[threadIdx.y * row + c0 + j] = (double)a[j];
+        sh[(ty + threadIdx.y) * row + c0 + j] = (double)q[j];
+    }
+    __syncthreads();
+    for (int c = tid; c < C; c += nthr) {
+        double sa = 0.0, sq = 0.0;
+        for (int y = 0; y < ty; ++y) { sa += sh[y * row + c]; sq += sh[(ty + y) * row + c]; }
+        atomicAdd(&part[((int64_t)b * C + c) * 2 + 0], sa);
+        atomicAdd(&part[((int64_t)b * C + c) * 2 + 1], sq);
+    }
+}
+
+template <int D>
+__global__ void gn_stats_async_kernel(const bf16* __restrict__ x, double* __restrict__ sums, int HW, int C, int G, int ppb) {
+    constexpr int VEC = 8, NU = 2;                               // accumulation unit = 4 consecutive channels
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint4* ring = reinterpret_cast<uint4*>(smem_raw);            // [D][nthreads]
+    double* sh = reinterpret_cast<double*>(smem_raw);            // reused after the loop: [2][ty][tx*NU]
+    const int b = blockIdx.y;
+    const int c0 = threadIdx.x * VEC;
+    const int tx = blockDim.x, ty = blockDim.y, nthr = tx * ty;
+    const int tid = threadIdx.y * tx + threadIdx.x;
+    const int p0 = blockIdx.x * ppb;
+    int p1 = p0 + ppb; if (p1 > HW) p1 = HW;
+    const int64_t base = (int64_t)b * HW * C + c0;
+    const int first = p0 + threadIdx.y;
+    const int niter = first < p1 ? (p1 - first + ty - 1) / ty : 0;
+    float s[NU] = {0.f, 0.f}, ss[NU] = {0.f, 0.f};
+#pragma unroll
+    for (int st = 0; st < D; ++st) {
+        if (st < niter) cp_async16(&ring[st * nthr + tid], x + base + (int64_t)(first + st * ty) * C);
+        cp_async_commit();
+    }
+    int slot = 0;
+    for (int it = 0; it < niter; ++it) {
+        cp_async_wait<D - 1>();
+        const uint4 ux = ring[slot * nthr + tid];
+        float v[VEC];
+        unpack8(ux, v);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) { s[j / 4] += v[j]; ss[j / 4] = fmaf(v[j], v[j], ss[j / 4]); }
+        if (it + D < niter) cp_async16(&ring[slot * nthr + tid], x + base + (int64_t)(first + (it + D) * ty) * C);
+        cp_async_commit();
+        slot = (slot + 1 == D) ? 0 : slot + 1;
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    const int row = tx * NU;
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+        sh[threadIdx.y * row + threadIdx.x * NU + u] = (double)s[u];
+        sh[(ty + threadIdx.y) * row + threadIdx.x * NU + u] = (double)ss[u];
+    }
+    __syncthreads();
+    const int upg = (C / G) / 4;
+    for (int g = tid; g < G; g += nthr) {
+        double a = 0.0, q = 0.0;
+        for (int y = 0; y < ty; ++y)
+            for (int t = 0; t < upg; ++t) {
+                a += sh[y * row + g * upg + t];
+                q += sh[(ty + y) * row + g * upg + t];
+            }
+        atomicAdd(&sums[((int64_t)b * G + g) * 2 + 0], a);
+        atomicAdd(&sums[((int64_t)b * G + g) * 2 + 1], q);
+    }
+}
+
+// forward apply, bf16 -> bf16, VEC = 8: x through the cp.async ring, y stored directly (stores are fire-and-forget)
+template <int D>
+__global__ void gn_apply_async_kernel(const bf16* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
+                                      const float* __restrict__ beta, bf16* __restrict__ y, int HW, int C, int G, int ppb, int act) {
+    constexpr int VEC = 8;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint4* ring = reinterpret_cast<uint4*>(smem_raw);            // [D][nthreads]
+    const int b = blockIdx.y;
+    const int c0 = threadIdx.x * VEC;
+    const int cg = C / G;
+    const int tx = blockDim.x, ty = blockDim.y, nthr = tx * ty;
+    const int tid = threadIdx.y * tx + threadIdx.x;
+    const bool silu = (act == VQB_ACT_SILU);
+    float sc[VEC], sh_[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+        int g = (c0 + j) / cg;
+        float mean = stats[((int64_t)b * G + g) * 2];
+        float rstd = stats[((int64_t)b * G + g) * 2 + 1];
+        sc[j] = rstd * gamma[c0 + j];
+        sh_[j] = beta[c0 + j] - mean * sc[j];
+        if (silu) { sc[j] *= 0.5f; sh_[j] *= 0.5f; }
+    }
+    const int p0 = blockIdx.x * ppb;
+    int p1 = p0 + ppb; if (p1 > HW) p1 = HW;
+    const int64_t base = (int64_t)b * HW * C + c0;
+    const int first = p0 + threadIdx.y;
+    const int niter = first < p1 ? (p1 - first + ty - 1) / ty : 0;
+#pragma unroll
+    for (int st = 0; st < D; ++st) {
+        if (st < niter) cp_async16(&ring[st * nthr + tid], x + base + (int64_t)(first + st * ty) * C);
+        cp_async_commit();
+    }
+    int slot = 0;
+    for (int it = 0; it < niter; ++it) {
+        cp_async_wait<D - 1>();
+        const uint4 ux = ring[slot * nthr + tid];
+        float v[VEC], o[VEC];
+        unpack8(ux, v);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            float t = fmaf(v[j], sc[j], sh_[j]);
+            o[j] = silu ? silu_of_half(t) : t;
+        }
+        stv<bf16, VEC>(y + base + (int64_t)(first + it * ty) * C, o);
+        if (it + D < niter) cp_async16(&ring[slot * nthr + tid], x + base + (int64_t)(first + (it + D) * ty) * C);
+        cp_async_commit();
+        slot = (slot + 1 == D) ? 0 : slot + 1;
+    }
+    cp_async_wait<0>();
 }
 
 // coef[b][g] and parameter grads
@@ -274,6 +532,11 @@ __global__ void gn_bwd_apply_kernel(const TI* __restrict__ x, const TG* __restri
         cb[j] = -rstd * rstd * k2;                        // -(x-mean)*rstd^2*k2
         cc[j] = -rstd * k1 - mean * cb[j];
     }
+    constexpr bool APPROX = (sizeof(TI) == 2 && sizeof(TG) == 2);
+    if (APPROX && act == VQB_ACT_SILU) {                  // ds arrives doubled (silu_grad2_of_half of u = t/2)
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) { sc[j] *= 0.5f; sf[j] *= 0.5f; ca[j] *= 0.5f; }
+    }
     const int p0 = blockIdx.x * ppb;
     int p1 = p0 + ppb; if (p1 > HW) p1 = HW;
     const int64_t base = (int64_t)b * HW * C + c0;
@@ -285,7 +548,8 @@ __global__ void gn_bwd_apply_kernel(const TI* __restrict__ x, const TG* __restri
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
             float ds = g[j];
-            if (act == VQB_ACT_SILU) ds *= fast_silu_grad(fmaf(v[j], sc[j], sf[j]));
+            if constexpr (APPROX) { if (act == VQB_ACT_SILU) ds *= silu_grad2_of_half(fmaf(v[j], sc[j], sf[j])); }
+            else { if (act == VQB_ACT_SILU) ds *= fast_silu_grad<false>(fmaf(v[j], sc[j], sf[j])); }
             o[j] = fmaf(ds, ca[j], fmaf(v[j], cb[j], cc[j]));
         }
         if (add) {                                    // fused accumulation of the skip-connection gradient
@@ -318,6 +582,16 @@ inline int gn_check(const char* name, int N, int HW, int C, int G) {
 extern "C" int vqb_gn_stats(const void* x, int x_dtype, double* sums, int N, int HW, int C, int G, void* stream) {
     int rc = gn_check("gn_stats", N, HW, C, G); if (rc) return rc;
     VQB_CHECK_ARG(x && sums, "gn_stats: null pointer");
+    static int use_async = getenv("VQB_GN_ASYNC") ? atoi(getenv("VQB_GN_ASYNC")) : 1;
+    if (use_async && x_dtype == VQB_BF16 && gn_vec(C, G) == 8) {
+        static int ppt = getenv("VQB_GN_SPPT") ? atoi(getenv("VQB_GN_SPPT")) : 128;
+        GnLaunch La = gn_launch(N, HW, C, G, ppt, 8);
+        const size_t nthr = (size_t)La.block.x * La.block.y;
+        size_t ring = (size_t)8 * nthr * 16, red = 2 * sizeof(double) * nthr * 2;
+        gn_stats_async_kernel<8><<<La.grid, La.block, ring > red ? ring : red, as_stream(stream)>>>((const bf16*)x, sums, HW, C, G, La.ppb);
+        VQB_CHECK_LAUNCH("gn_stats_async");
+        return VQB_OK;
+    }
     GnLaunch L = gn_launch(N, HW, C, G, 32);
     const int nu = (L.vec >= 4) ? L.vec / 4 : 1;
     size_t sm = 2 * sizeof(double) * L.block.x * L.block.y * nu;
@@ -341,6 +615,15 @@ extern "C" int vqb_gn_apply(const void* x, int x_dtype, const float* stats, cons
     int rc = gn_check("gn_apply", N, HW, C, G); if (rc) return rc;
     VQB_CHECK_ARG(x && stats && gamma && beta && y, "gn_apply: null pointer");
     VQB_CHECK_ARG(act == VQB_ACT_NONE || act == VQB_ACT_SILU, "gn_apply: act must be NONE or SILU");
+    static int use_async = getenv("VQB_GN_ASYNC") ? atoi(getenv("VQB_GN_ASYNC")) : 1;
+    if (use_async && x_dtype == VQB_BF16 && y_dtype == VQB_BF16 && gn_vec(C, G) == 8) {
+        static int ppt = getenv("VQB_GN_APPT") ? atoi(getenv("VQB_GN_APPT")) : 32;
+        GnLaunch La = gn_launch(N, HW, C, G, ppt, 8);
+        const size_t nthr = (size_t)La.block.x * La.block.y;
+        gn_apply_async_kernel<8><<<La.grid, La.block, (size_t)8 * nthr * 16, as_stream(stream)>>>((const bf16*)x, stats, gamma, beta, (bf16*)y, HW, C, G, La.ppb, act);
+        VQB_CHECK_LAUNCH("gn_apply_async");
+        return VQB_OK;
+    }
     GnLaunch L = gn_launch(N, HW, C, G);
     GN_VEC_DISPATCH(L, VQB_DISPATCH_1(x_dtype, TI, VQB_DISPATCH_1(y_dtype, TO,
         (gn_apply_kernel<TI, TO, VEC><<<L.grid, L.block, 0, as_stream(stream)>>>((const TI*)x, stats, gamma, beta, (TO*)y, HW, C, G, L.ppb, act));)))
@@ -353,10 +636,43 @@ extern "C" int vqb_gn_bwd_reduce(const void* x, int x_dtype, const void* dy, int
                                  void* stream) {
     int rc = gn_check("gn_bwd_reduce", N, HW, C, G); if (rc) return rc;
     VQB_CHECK_ARG(x && dy && stats && gamma && beta && part, "gn_bwd_reduce: null pointer");
-    GnLaunch L = gn_launch(N, HW, C, G, 32, 4);      // 4 channels per thread: fewer live registers -> more warps to hide latency
+    static int use_async = getenv("VQB_GN_ASYNC") ? atoi(getenv("VQB_GN_ASYNC")) : 1;
+    if (use_async && x_dtype == VQB_BF16 && dy_dtype == VQB_BF16 && gn_vec(C, G) == 8 && (act == VQB_ACT_NONE || act == VQB_ACT_SILU)) {
+        static int ppt = getenv("VQB_GN_RPPT") ? atoi(getenv("VQB_GN_RPPT")) : 128;
+        GnLaunch L = gn_launch(N, HW, C, G, ppt, 8);
+        const size_t nthr = (size_t)L.block.x * L.block.y;
+        static int depth = getenv("VQB_GN_DEPTH") ? atoi(getenv("VQB_GN_DEPTH")) : GN_ASYNC_DEPTH;
+        size_t ring = (size_t)depth * 2 * nthr * 16, red = 2 * sizeof(double) * nthr * 8;
+        size_t sm = ring > red ? ring : red;
+        static bool attr_set = false;
+        if (!attr_set) {
+            VQB_CUDA(cudaFuncSetAttribute(gn_bwd_reduce_async_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            VQB_CUDA(cudaFuncSetAttribute(gn_bwd_reduce_async_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            VQB_CUDA(cudaFuncSetAttribute(gn_bwd_reduce_async_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            VQB_CUDA(cudaFuncSetAttribute(gn_bwd_reduce_async_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            attr_set = true;
+        }
+#define GN_RED_ASYNC(DD) gn_bwd_reduce_async_kernel<DD><<<L.grid, L.block, sm, as_stream(stream)>>>((const bf16*)x, (const bf16*)dy, stats, gamma, beta, part, HW, C, G, L.ppb, act)
+        if (depth == 4) GN_RED_ASYNC(4); else if (depth == 8) GN_RED_ASYNC(8); else if (depth == 12) GN_RED_ASYNC(12); else GN_RED_ASYNC(6);
+#undef GN_RED_ASYNC
+        VQB_CHECK_LAUNCH("gn_bwd_reduce_async");
+        return VQB_OK;
+    }
+    static int exp_vec = getenv("VQB_GN_RVEC") ? atoi(getenv("VQB_GN_RVEC")) : 8;
+    static int exp_unr = getenv("VQB_GN_RUNR") ? atoi(getenv("VQB_GN_RUNR")) : 4;
+    static int exp_ppt = getenv("VQB_GN_RPPT") ? atoi(getenv("VQB_GN_RPPT")) : 128;
+    GnLaunch L = gn_launch(N, HW, C, G, exp_ppt, exp_vec);
     size_t sm = 2 * sizeof(double) * L.block.x * L.block.y * L.vec;
+    if (exp_unr == 2) {
     GN_VEC_DISPATCH(L, VQB_DISPATCH_1(x_dtype, TI, VQB_DISPATCH_1(dy_dtype, TG,
-        (gn_bwd_reduce_kernel<TI, TG, VEC><<<L.grid, L.block, sm, as_stream(stream)>>>((const TI*)x, (const TG*)dy, stats, gamma, beta, part, HW, C, G, L.ppb, act));)))
+        (gn_bwd_reduce_kernel<TI, TG, VEC, 2><<<L.grid, L.block, sm, as_stream(stream)>>>((const TI*)x, (const TG*)dy, stats, gamma, beta, part, HW, C, G, L.ppb, act));)))
+    } else if (exp_unr == 8) {
+    GN_VEC_DISPATCH(L, VQB_DISPATCH_1(x_dtype, TI, VQB_DISPATCH_1(dy_dtype, TG,
+        (gn_bwd_reduce_kernel<TI, TG, VEC, 8><<<L.grid, L.block, sm, as_stream(stream)>>>((const TI*)x, (const TG*)dy, stats, gamma, beta, part, HW, C, G, L.ppb, act));)))
+    } else {
+    GN_VEC_DISPATCH(L, VQB_DISPATCH_1(x_dtype, TI, VQB_DISPATCH_1(dy_dtype, TG,
+        (gn_bwd_reduce_kernel<TI, TG, VEC, 4><<<L.grid, L.block, sm, as_stream(stream)>>>((const TI*)x, (const TG*)dy, stats, gamma, beta, part, HW, C, G, L.ppb, act));)))
+    }
     VQB_CHECK_LAUNCH("gn_bwd_reduce");
     return VQB_OK;
 }
