@@ -482,6 +482,78 @@ __global__ void gn_apply_async_kernel(const bf16* __restrict__ x, const float* _
     cp_async_wait<0>();
 }
 
+// backward apply, all-bf16, VEC = 8: x, dy (and the skip gradient `add`) through the cp.async ring
+template <int D, bool HAS_ADD>
+__global__ void gn_bwd_apply_async_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, const float* __restrict__ stats,
+                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                          const float* __restrict__ coef, const bf16* __restrict__ add, bf16* __restrict__ dx,
+                                          int HW, int C, int G, int ppb, int act) {
+    constexpr int VEC = 8, NT = HAS_ADD ? 3 : 2;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint4* ring = reinterpret_cast<uint4*>(smem_raw);            // [D][NT][nthreads]
+    const int b = blockIdx.y;
+    const int c0 = threadIdx.x * VEC;
+    const int cg = C / G;
+    const int tx = blockDim.x, ty = blockDim.y, nthr = tx * ty;
+    const int tid = threadIdx.y * tx + threadIdx.x;
+    const bool silu = (act == VQB_ACT_SILU);
+    float sc[VEC], sf[VEC], ca[VEC], cb[VEC], cc[VEC];       // dx = ds*ca + x*cb + cc
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+        int g = (c0 + j) / cg;
+        const float mean = stats[((int64_t)b * G + g) * 2];
+        const float rstd = stats[((int64_t)b * G + g) * 2 + 1];
+        const float k1 = coef[((int64_t)b * G + g) * 2];
+        const float k2 = coef[((int64_t)b * G + g) * 2 + 1];
+        sc[j] = rstd * gamma[c0 + j];
+        sf[j] = beta[c0 + j] - mean * sc[j];
+        ca[j] = sc[j];
+        cb[j] = -rstd * rstd * k2;
+        cc[j] = -rstd * k1 - mean * cb[j];
+        if (silu) { sc[j] *= 0.5f; sf[j] *= 0.5f; ca[j] *= 0.5f; }
+    }
+    const int p0 = blockIdx.x * ppb;
+    int p1 = p0 + ppb; if (p1 > HW) p1 = HW;
+    const int64_t base = (int64_t)b * HW * C + c0;
+    const int first = p0 + threadIdx.y;
+    const int niter = first < p1 ? (p1 - first + ty - 1) / ty : 0;
+    auto issue = [&](int slot, int it) {
+        const int64_t off = base + (int64_t)(first + it * ty) * C;
+        cp_async16(&ring[(slot * NT + 0) * nthr + tid], x + off);
+        cp_async16(&ring[(slot * NT + 1) * nthr + tid], dy + off);
+        if constexpr (HAS_ADD) cp_async16(&ring[(slot * NT + 2) * nthr + tid], add + off);
+    };
+#pragma unroll
+    for (int st = 0; st < D; ++st) {
+        if (st < niter) issue(st, st);
+        cp_async_commit();
+    }
+    int slot = 0;
+    for (int it = 0; it < niter; ++it) {
+        cp_async_wait<D - 1>();
+        float v[VEC], g[VEC], o[VEC];
+        unpack8(ring[(slot * NT + 0) * nthr + tid], v);
+        unpack8(ring[(slot * NT + 1) * nthr + tid], g);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            float ds = g[j];
+            if (silu) ds *= silu_grad2_of_half(fmaf(v[j], sc[j], sf[j]));
+            o[j] = fmaf(ds, ca[j], fmaf(v[j], cb[j], cc[j]));
+        }
+        if constexpr (HAS_ADD) {
+            float r[VEC];
+            unpack8(ring[(slot * NT + 2) * nthr + tid], r);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) o[j] += r[j];
+        }
+        stv<bf16, VEC>(dx + base + (int64_t)(first + it * ty) * C, o);
+        if (it + D < niter) issue(slot, it + D);
+        cp_async_commit();
+        slot = (slot + 1 == D) ? 0 : slot + 1;
+    }
+    cp_async_wait<0>();
+}
+
 // coef[b][g] and parameter grads
 __global__ void gn_bwd_finalize_kernel(const double* __restrict__ part, const float* __restrict__ gamma,
                                        float* __restrict__ coef, float* __restrict__ dgamma, float* __restrict__ dbeta,
@@ -693,6 +765,28 @@ extern "C" int vqb_gn_bwd_apply(const void* x, int x_dtype, const void* dy, int 
                                 int dx_dtype, int N, int HW, int C, int G, int act, void* stream) {
     int rc = gn_check("gn_bwd_apply", N, HW, C, G); if (rc) return rc;
     VQB_CHECK_ARG(x && dy && stats && gamma && beta && coef && dx, "gn_bwd_apply: null pointer");
+    static int use_async = getenv("VQB_GN_ASYNC") ? atoi(getenv("VQB_GN_ASYNC")) : 1;
+    if (use_async && x_dtype == VQB_BF16 && dy_dtype == VQB_BF16 && dx_dtype == VQB_BF16 && gn_vec(C, G) == 8 &&
+        (act == VQB_ACT_NONE || act == VQB_ACT_SILU)) {
+        static int ppt = getenv("VQB_GN_BPPT") ? atoi(getenv("VQB_GN_BPPT")) : 16;
+        GnLaunch La = gn_launch(N, HW, C, G, ppt, 8);
+        const size_t nthr = (size_t)La.block.x * La.block.y;
+        constexpr int DB = 6;
+        static bool attr_set = false;
+        if (!attr_set) {
+            VQB_CUDA(cudaFuncSetAttribute(gn_bwd_apply_async_kernel<DB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            VQB_CUDA(cudaFuncSetAttribute(gn_bwd_apply_async_kernel<DB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            attr_set = true;
+        }
+        if (add)
+            gn_bwd_apply_async_kernel<DB, true><<<La.grid, La.block, (size_t)DB * 3 * nthr * 16, as_stream(stream)>>>(
+                (const bf16*)x, (const bf16*)dy, stats, gamma, beta, coef, (const bf16*)add, (bf16*)dx, HW, C, G, La.ppb, act);
+        else
+            gn_bwd_apply_async_kernel<DB, false><<<La.grid, La.block, (size_t)DB * 2 * nthr * 16, as_stream(stream)>>>(
+                (const bf16*)x, (const bf16*)dy, stats, gamma, beta, coef, nullptr, (bf16*)dx, HW, C, G, La.ppb, act);
+        VQB_CHECK_LAUNCH("gn_bwd_apply_async");
+        return VQB_OK;
+    }
     GnLaunch L = gn_launch(N, HW, C, G);
     GN_VEC_DISPATCH(L, VQB_DISPATCH_1(x_dtype, TI, VQB_DISPATCH_1(dy_dtype, TG, VQB_DISPATCH_1(dx_dtype, TO,
         (gn_bwd_apply_kernel<TI, TG, TO, VEC><<<L.grid, L.block, 0, as_stream(stream)>>>((const TI*)x, (const TG*)dy, stats, gamma, beta, coef, (const TO*)add, (TO*)dx, HW, C, G, L.ppb, act));))))
