@@ -200,6 +200,33 @@ extern "C" int vqb_pack_conv_weight(const float* w, void* wp, int out_dtype, int
     return VQB_OK;
 }
 
+// 16-byte vector access: 8 bf16 or 4 fp32 per thread
+template <typename T> struct V16 { static constexpr int N = 16 / sizeof(T); };
+template <typename T>
+__device__ __forceinline__ void ld16(const T* p, float* v) {
+    if constexpr (sizeof(T) == 2) {
+        uint4 u = *reinterpret_cast<const uint4*>(p);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+    } else {
+        float4 a = *reinterpret_cast<const float4*>(p);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    }
+}
+template <typename T>
+__device__ __forceinline__ void st16(T* p, const float* v) {
+    if constexpr (sizeof(T) == 2) {
+        uint4 u;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        *reinterpret_cast<uint4*>(p) = u;
+    } else {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
 // P[n,h,w, j] (64 channels, TO) = x[n, h+kh-1, w+kw-1, c] for j = (kh*3+kw)*C + c < 9*C, else 0   (3x3, pad 1, C <= 7)
 template <typename TI, typename TO, int CT>
 __global__ void im2col3x3_narrow_kernel(const TI* __restrict__ x, TO* __restrict__ P, int N, int H, int W, int Crt) {
@@ -221,8 +248,12 @@ __global__ void im2col3x3_narrow_kernel(const TI* __restrict__ x, TO* __restrict
             v[u] = val;
         }
         TO* dst = P + pix * 64 + grp * 8;
-        st4(dst, make_float4(v[0], v[1], v[2], v[3]));
-        st4(dst + 4, make_float4(v[4], v[5], v[6], v[7]));
+        if constexpr (sizeof(TO) == 2) {
+            st16<TO>(dst, v);                                    // one 16-byte store per thread
+        } else {
+            st4(dst, make_float4(v[0], v[1], v[2], v[3]));
+            st4(dst + 4, make_float4(v[4], v[5], v[6], v[7]));
+        }
     }
 }
 
@@ -269,20 +300,24 @@ extern "C" int vqb_unpack_conv_wgrad(const float* dwp, float* dw, int Co, int Ci
 // ---------------------------------------------------------------------------------------------------
 // 2x resampling
 // ---------------------------------------------------------------------------------------------------
+// VEC = 0: 16-byte vectors (C % V16<T>::N == 0), iterating over the LOW-resolution grid: four 16-byte loads -> one store
+// (down2) or one load -> four stores (up2); VEC = 1: scalar fallback for odd channel counts
 template <typename T, int VEC>
 __global__ void down2_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, float scale) {
     // y [N,H,W,C], x [N,2H,2W,C]
-    int Cv = C / VEC;
+    constexpr int V = (VEC == 0) ? V16<T>::N : 1;
+    int Cv = C / V;
     int64_t total = (int64_t)N * H * W * Cv;
     int64_t rowx = (int64_t)2 * W * C;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int cv = (int)(i % Cv); int64_t r = i / Cv; int w = (int)(r % W); r /= W; int h = (int)(r % H); int n = (int)(r / H);
-        const T* p = x + (((int64_t)n * 2 * H + 2 * h) * 2 * W + 2 * w) * C + cv * VEC;
-        if (VEC == 4) {
-            float4 a = ld4(p), b = ld4(p + C), c = ld4(p + rowx), d = ld4(p + rowx + C);
-            float4 o = make_float4((a.x + b.x + c.x + d.x) * scale, (a.y + b.y + c.y + d.y) * scale,
-                                   (a.z + b.z + c.z + d.z) * scale, (a.w + b.w + c.w + d.w) * scale);
-            st4(y + i * 4, o);
+        const T* p = x + (((int64_t)n * 2 * H + 2 * h) * 2 * W + 2 * w) * C + cv * V;
+        if constexpr (VEC == 0) {
+            float a[V], b[V], c[V], d[V], o[V];
+            ld16<T>(p, a); ld16<T>(p + C, b); ld16<T>(p + rowx, c); ld16<T>(p + rowx + C, d);
+#pragma unroll
+            for (int j = 0; j < V; ++j) o[j] = (a[j] + b[j] + c[j] + d[j]) * scale;
+            st16<T>(y + i * V, o);
         } else {
             st1(y + i, (ld1(p) + ld1(p + C) + ld1(p + rowx) + ld1(p + rowx + C)) * scale);
         }
@@ -291,18 +326,23 @@ __global__ void down2_kernel(const T* __restrict__ x, T* __restrict__ y, int N, 
 
 template <typename T, int VEC>
 __global__ void up2_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, float scale) {
-    // x [N,H,W,C], y [N,2H,2W,C]; iterate over output
-    int Cv = C / VEC;
-    int H2 = 2 * H, W2 = 2 * W;
-    int64_t total = (int64_t)N * H2 * W2 * Cv;
+    // x [N,H,W,C], y [N,2H,2W,C]; iterate over the input
+    constexpr int V = (VEC == 0) ? V16<T>::N : 1;
+    int Cv = C / V;
+    int64_t total = (int64_t)N * H * W * Cv;
+    int64_t rowy = (int64_t)2 * W * C;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        int cv = (int)(i % Cv); int64_t r = i / Cv; int w = (int)(r % W2); r /= W2; int h = (int)(r % H2); int n = (int)(r / H2);
-        const T* p = x + (((int64_t)n * H + (h >> 1)) * W + (w >> 1)) * C + cv * VEC;
-        if (VEC == 4) {
-            float4 a = ld4(p);
-            st4(y + i * 4, make_float4(a.x * scale, a.y * scale, a.z * scale, a.w * scale));
+        int cv = (int)(i % Cv); int64_t r = i / Cv; int w = (int)(r % W); r /= W; int h = (int)(r % H); int n = (int)(r / H);
+        T* q = y + (((int64_t)n * 2 * H + 2 * h) * 2 * W + 2 * w) * C + cv * V;
+        if constexpr (VEC == 0) {
+            float a[V];
+            ld16<T>(x + i * V, a);
+#pragma unroll
+            for (int j = 0; j < V; ++j) a[j] *= scale;
+            st16<T>(q, a); st16<T>(q + C, a); st16<T>(q + rowy, a); st16<T>(q + rowy + C, a);
         } else {
-            st1(y + i, ld1(p) * scale);
+            float a = ld1(x + i) * scale;
+            st1(q, a); st1(q + C, a); st1(q + rowy, a); st1(q + rowy + C, a);
         }
     }
 }
@@ -310,9 +350,10 @@ __global__ void up2_kernel(const T* __restrict__ x, T* __restrict__ y, int N, in
 extern "C" int vqb_down2(const void* x, void* y, int dtype, int N, int H, int W, int C, float scale, void* stream) {
     VQB_CHECK_ARG(x && y && N > 0 && H > 0 && W > 0 && C > 0, "down2: bad arguments");
     int64_t total = (int64_t)N * H * W * C;
-    if (C % 4 == 0) {
-        int g = grid_for(total / 4, 256);
-        VQB_DISPATCH_1(dtype, T, (down2_kernel<T, 4><<<g, 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, N, H, W, C, scale));)
+    const int vw = (dtype == VQB_BF16) ? 8 : 4;
+    if (C % vw == 0) {
+        int g = grid_for(total / vw, 256);
+        VQB_DISPATCH_1(dtype, T, (down2_kernel<T, 0><<<g, 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, N, H, W, C, scale));)
     } else {
         int g = grid_for(total, 256);
         VQB_DISPATCH_1(dtype, T, (down2_kernel<T, 1><<<g, 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, N, H, W, C, scale));)
@@ -323,10 +364,11 @@ extern "C" int vqb_down2(const void* x, void* y, int dtype, int N, int H, int W,
 
 extern "C" int vqb_up2(const void* x, void* y, int dtype, int N, int H, int W, int C, float scale, void* stream) {
     VQB_CHECK_ARG(x && y && N > 0 && H > 0 && W > 0 && C > 0, "up2: bad arguments");
-    int64_t total = (int64_t)N * 4 * H * W * C;
-    if (C % 4 == 0) {
-        int g = grid_for(total / 4, 256);
-        VQB_DISPATCH_1(dtype, T, (up2_kernel<T, 4><<<g, 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, N, H, W, C, scale));)
+    int64_t total = (int64_t)N * H * W * C;                    // threads iterate over the input grid
+    const int vw = (dtype == VQB_BF16) ? 8 : 4;
+    if (C % vw == 0) {
+        int g = grid_for(total / vw, 256);
+        VQB_DISPATCH_1(dtype, T, (up2_kernel<T, 0><<<g, 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, N, H, W, C, scale));)
     } else {
         int g = grid_for(total, 256);
         VQB_DISPATCH_1(dtype, T, (up2_kernel<T, 1><<<g, 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, N, H, W, C, scale));)
@@ -436,8 +478,52 @@ __global__ void colsum_kernel(const T* __restrict__ a, float* __restrict__ out, 
     }
 }
 
+// 16-byte vector form: threadIdx.x owns V consecutive channels, threadIdx.y strides over rows (8 independent loads in flight
+// per thread), block partials combined in shared memory, one atomicAdd per channel per block
+template <typename T>
+__global__ void colsum_vec_kernel(const T* __restrict__ a, float* __restrict__ out, int64_t P, int C, int rows_per_block) {
+    constexpr int V = V16<T>::N;
+    extern __shared__ float shc[];                               // [ty][C]
+    const int64_t p0 = (int64_t)blockIdx.x * rows_per_block;
+    int64_t p1 = p0 + rows_per_block; if (p1 > P) p1 = P;
+    const int c0 = threadIdx.x * V;
+    float acc[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[j] = 0.f;
+#pragma unroll 8
+    for (int64_t p = p0 + threadIdx.y; p < p1; p += blockDim.y) {
+        float v[V];
+        ld16<T>(a + p * C + c0, v);
+#pragma unroll
+        for (int j = 0; j < V; ++j) acc[j] += v[j];
+    }
+#pragma unroll
+    for (int j = 0; j < V; ++j) shc[threadIdx.y * C + c0 + j] = acc[j];
+    __syncthreads();
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    for (int c = tid; c < C; c += blockDim.x * blockDim.y) {
+        float t = 0.f;
+        for (int y = 0; y < (int)blockDim.y; ++y) t += shc[y * C + c];
+        atomicAdd(out + c, t);
+    }
+}
+
 extern "C" int vqb_colsum(const void* a, int a_dtype, float* out, int64_t P, int C, void* stream) {
     VQB_CHECK_ARG(a && out && P > 0 && C > 0, "colsum: bad arguments");
+    {
+        const int vw = (a_dtype == VQB_BF16) ? 8 : 4;
+        if (C % vw == 0 && C / vw <= 256 && P >= 4096) {
+            int tx = C / vw, ty = 256 / tx; if (ty < 1) ty = 1;
+            int rows = (int)ceil_div64(P, (int64_t)kSMs * 8);
+            if (rows < ty * 16) rows = ty * 16;
+            int g = (int)ceil_div64(P, rows);
+            dim3 block(tx, ty);
+            size_t sm = sizeof(float) * ty * C;
+            VQB_DISPATCH_1(a_dtype, T, (colsum_vec_kernel<T><<<g, block, sm, as_stream(stream)>>>((const T*)a, out, P, C, rows));)
+            VQB_CHECK_LAUNCH("colsum_vec");
+            return VQB_OK;
+        }
+    }
     int tx = C >= 128 ? 128 : (C >= 32 ? 32 : (C >= 8 ? 8 : 4));
     int ty = 256 / tx;
     int64_t want_blocks = (int64_t)kSMs * 8;
