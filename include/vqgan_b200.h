@@ -151,6 +151,12 @@ int vqb_diff_grad(const void* a, int a_dtype, const void* b, int b_dtype, void* 
 int vqb_act_bwd_from_output(const void* y, int y_dtype, const void* dy, int dy_dtype, void* dx, int dx_dtype, int act,
                             float alpha, float gain, int64_t n, void* stream);
 
+/* The same derivative for NHWC tensors [P][C] of ONE dtype with 16-byte vectors, fused with the bias gradient
+ * db[c] += sum_p dx[p][c] (db may be NULL; it must be zero-initialised by the caller): bias_act's backward
+ * (stylegan2_discriminator/ops/bias_act.py:143-210) in one pass.  C must be a multiple of 8 (bf16) / 4 (fp32). */
+int vqb_act_bwd_bias(const void* y, const void* dy, void* dx, int dtype, int act, float alpha, float gain, int64_t P, int C,
+                     float* db, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------
  * VQGAN loss heads: StyleGAN2 discriminator resampling, LPIPS, minibatch-stddev (vqvae/modules/loss/)
  * ---------------------------------------------------------------------------------------------------- */

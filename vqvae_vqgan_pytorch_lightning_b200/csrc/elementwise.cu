@@ -537,6 +537,70 @@ extern "C" int vqb_colsum(const void* a, int a_dtype, float* out, int64_t P, int
 }
 
 // ---------------------------------------------------------------------------------------------------
+// activation backward from the saved output + bias gradient in ONE pass (bias_act.py:143-210: dx = dy * act'(y) * gain,
+// db = sum over pixels of dx).  16-byte vectors; threadIdx.x owns V consecutive channels, threadIdx.y strides over pixels.
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void act_bwd_bias_kernel(const T* __restrict__ y, const T* __restrict__ dy, T* __restrict__ dx, int act, float alpha,
+                                    float gain, int64_t P, int C, int rows_per_block, float* __restrict__ db) {
+    constexpr int V = V16<T>::N;
+    extern __shared__ float shc[];                               // [ty][C] (only when db != null)
+    const int64_t p0 = (int64_t)blockIdx.x * rows_per_block;
+    int64_t p1 = p0 + rows_per_block; if (p1 > P) p1 = P;
+    const int c0 = threadIdx.x * V;
+    const float neg = (act == VQB_ACT_LRELU) ? gain * alpha : ((act == VQB_ACT_RELU) ? 0.f : gain);
+    const float inv_gain = 1.0f / gain;
+    float acc[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[j] = 0.f;
+#pragma unroll 4
+    for (int64_t p = p0 + threadIdx.y; p < p1; p += blockDim.y) {
+        float yv[V], g[V], o[V];
+        ld16<T>(y + p * C + c0, yv);
+        ld16<T>(dy + p * C + c0, g);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            float d;
+            if (act == VQB_ACT_TANH) { float t = yv[j] * inv_gain; d = gain * (1.0f - t * t); }
+            else d = (yv[j] > 0.f) ? gain : neg;
+            o[j] = g[j] * d;
+            if constexpr (sizeof(T) == 2) o[j] = __bfloat162float(__float2bfloat16_rn(o[j]));   // db sums what is stored
+            acc[j] += o[j];
+        }
+        st16<T>(dx + p * C + c0, o);
+    }
+    if (db == nullptr) return;
+#pragma unroll
+    for (int j = 0; j < V; ++j) shc[threadIdx.y * C + c0 + j] = acc[j];
+    __syncthreads();
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    for (int c = tid; c < C; c += blockDim.x * blockDim.y) {
+        float t = 0.f;
+        for (int yy = 0; yy < (int)blockDim.y; ++yy) t += shc[yy * C + c];
+        atomicAdd(db + c, t);
+    }
+}
+
+extern "C" int vqb_act_bwd_bias(const void* y, const void* dy, void* dx, int dtype, int act, float alpha, float gain, int64_t P,
+                                int C, float* db, void* stream) {
+    VQB_CHECK_ARG(y && dy && dx && P > 0 && C > 0 && gain != 0.f, "act_bwd_bias: bad arguments");
+    VQB_CHECK_ARG(act == VQB_ACT_NONE || act == VQB_ACT_TANH || act == VQB_ACT_LRELU || act == VQB_ACT_RELU,
+                  "act_bwd_bias: activation must be recoverable from its output");
+    const int vw = (dtype == VQB_BF16) ? 8 : 4;
+    VQB_CHECK_ARG(C % vw == 0 && C / vw <= 256, "act_bwd_bias: C must be a multiple of the 16-byte vector width and <= 256 vectors");
+    int tx = C / vw, ty = 256 / tx; if (ty < 1) ty = 1;
+    int rows = (int)ceil_div64(P, (int64_t)kSMs * 16);
+    if (rows < ty * 8) rows = ty * 8;
+    int g = (int)ceil_div64(P, rows);
+    dim3 block(tx, ty);
+    size_t sm = db ? sizeof(float) * ty * C : 0;
+    VQB_DISPATCH_1(dtype, T, (act_bwd_bias_kernel<T><<<g, block, sm, as_stream(stream)>>>((const T*)y, (const T*)dy, (T*)dx, act, alpha,
+                                                                                         gain, P, C, rows, db));)
+    VQB_CHECK_LAUNCH("act_bwd_bias");
+    return VQB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // fused AdamW over a flat range (torch.optim.AdamW semantics)
 // ---------------------------------------------------------------------------------------------------
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,

@@ -58,6 +58,7 @@ SIGNATURES = {
     'vqb_diff_sums': (_i, [_p, _i, _p, _i, _p, _i64, _p]),
     'vqb_diff_grad': (_i, [_p, _i, _p, _i, _p, _i, _f, _f, _p, _i, _i64, _p]),
     'vqb_act_bwd_from_output': (_i, [_p, _i, _p, _i, _p, _i, _i, _f, _f, _i64, _p]),
+    'vqb_act_bwd_bias': (_i, [_p, _p, _p, _i, _i, _f, _f, _i64, _i, _p, _p]),
     'vqb_vq_workspace_bytes': (_sz, [_i64, _i, _i]),
     'vqb_vq_assign': (_i, [_p, _p, _i, _p, _p, _p, _p, _p, _i64, _i, _i, _p, _sz, _p]),
     'vqb_vq_tc_workspace_bytes': (_sz, [_i64, _i, _i]),

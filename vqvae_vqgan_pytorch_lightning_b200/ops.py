@@ -169,10 +169,20 @@ class ActBwdFn(torch.autograd.Function):
     the function itself; for the smooth activations only first order is built."""
 
     @staticmethod
-    def forward(ctx, dy, y, act, alpha, gain, out_dtype):
+    def forward(ctx, dy, y, act, alpha, gain, out_dtype, db=None):
+        """`db` (optional, zero-initialised fp32 [C]) receives the bias gradient sum_p dpre[p, c] as a side effect when the
+        fused single-pass kernel applies (one dtype throughout, C a multiple of the 16-byte vector); returns dpre."""
         dy = as_nhwc(dy) if dy.dim() == 4 else dy.contiguous()
         dpre = torch.empty_like(dy, dtype=out_dtype, memory_format=torch.preserve_format)
-        call('vqb_act_bwd_from_output', ptr(y), dt(y), ptr(dy), dt(dy), ptr(dpre), dt(dpre), act, alpha, gain, dy.numel(), stream())
+        c = dy.shape[1] if dy.dim() == 4 else 0
+        vw = 8 if dy.dtype == torch.bfloat16 else 4
+        ctx.db_done = False
+        if dy.dim() == 4 and y.dtype == dy.dtype == out_dtype and c % vw == 0 and c // vw <= 256:
+            call('vqb_act_bwd_bias', ptr(y), ptr(dy), ptr(dpre), dt(dy), act, alpha, gain, dy.numel() // c, c, ptr(db), stream())
+            ctx.db_done = db is not None
+        else:
+            call('vqb_act_bwd_from_output', ptr(y), dt(y), ptr(dy), dt(dy), ptr(dpre), dt(dpre), act, alpha, gain, dy.numel(), stream())
+        ActBwdFn.last_db_done = ctx.db_done
         ctx.save_for_backward(y)
         ctx.cfg = (act, alpha, gain, dy.dtype)
         return dpre
@@ -183,7 +193,7 @@ class ActBwdFn(torch.autograd.Function):
         act, alpha, gain, dy_dtype = ctx.cfg
         if act not in (ACT_LRELU, ACT_RELU):
             raise lib.VQBError('second-order backward is only built for piecewise-linear activations')
-        return ActBwdFn.apply(g, y, act, alpha, gain, dy_dtype), None, None, None, None, None
+        return ActBwdFn.apply(g, y, act, alpha, gain, dy_dtype), None, None, None, None, None, None
 
 
 class Conv2dFn(torch.autograd.Function):
@@ -232,8 +242,13 @@ class Conv2dFn(torch.autograd.Function):
         dres = None
         if has_res:
             dres = dy if dy.dtype == res_dtype else as_nhwc(dy, res_dtype)
+        db_fused = None
         if act != ACT_NONE:
-            dy = ActBwdFn.apply(dy, y.detach(), act, alpha, gain, gdt)
+            want_db = has_bias and ctx.needs_input_grad[2] and not _no_weight_grad and not torch.is_grad_enabled()
+            db_buf = torch.zeros(co, dtype=torch.float32, device=x.device) if want_db else None
+            dy = ActBwdFn.apply(dy, y.detach(), act, alpha, gain, gdt, db_buf)
+            if want_db and ActBwdFn.last_db_done:
+                db_fused = db_buf                        # bias gradient produced by the same pass
         elif gain != 1.0:
             raise lib.VQBError('gain != 1 requires an activation epilogue')
         _, _, oh, ow = dy.shape
@@ -249,8 +264,7 @@ class Conv2dFn(torch.autograd.Function):
             dw = torch.empty(weight.shape, dtype=torch.float32, device=x.device)
             call('vqb_unpack_conv_wgrad', ptr(dwp), ptr(dw), co, ci, kh, kw, w_scale, stream())
             if has_bias and ctx.needs_input_grad[2]:
-                db = torch.zeros(co, dtype=torch.float32, device=x.device)
-                call('vqb_colsum', ptr(dy), dt(dy), ptr(db), n * oh * ow, co, stream())
+                db = db_fused if db_fused is not None else _colsum(dy, n * oh * ow, co)
             return None, dw, db, dres, None, None, None, None, None, None, None
         if route == 'out' and x.dtype == torch.bfloat16:
             pd = _im2col64(dy)                                                        # im2col of the 3-channel gradient
@@ -266,8 +280,7 @@ class Conv2dFn(torch.autograd.Function):
                 if w_scale != 1.0:
                     dw = dw * w_scale
             if has_bias and ctx.needs_input_grad[2]:
-                db = torch.zeros(co, dtype=torch.float32, device=x.device)
-                call('vqb_colsum', ptr(dy), dt(dy), ptr(db), n * oh * ow, co, stream())
+                db = db_fused if db_fused is not None else _colsum(dy, n * oh * ow, co)
             return dx, dw, db, dres, None, None, None, None, None, None, None
         if torch.is_grad_enabled():
             # the graph of this backward pass is being recorded (autograd.grad(..., create_graph=True): the R1 penalty,
@@ -284,9 +297,14 @@ class Conv2dFn(torch.autograd.Function):
         if ctx.needs_input_grad[1] and not _no_weight_grad:
             dw = _wgrad_raw(x, dy, weight.shape, pad, stride, w_scale)
         if has_bias and ctx.needs_input_grad[2] and not _no_weight_grad:
-            db = torch.zeros(co, dtype=torch.float32, device=x.device)
-            call('vqb_colsum', ptr(dy), dt(dy), ptr(db), n * oh * ow, co, stream())
+            db = db_fused if db_fused is not None else _colsum(dy, n * oh * ow, co)
         return dx, dw, db, dres, None, None, None, None, None, None, None
+
+
+def _colsum(dy: torch.Tensor, rows: int, co: int) -> torch.Tensor:
+    db = torch.zeros(co, dtype=torch.float32, device=dy.device)
+    call('vqb_colsum', ptr(dy), dt(dy), ptr(db), rows, co, stream())
+    return db
 
 
 def _dgrad_raw(dy: torch.Tensor, weight: torch.Tensor, h: int, w: int, pad: int, stride: int, w_scale: float, out_dtype):
