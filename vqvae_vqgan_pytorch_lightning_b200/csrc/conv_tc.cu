@@ -109,12 +109,13 @@ struct FwdParams {
     const float* bias;
     const void* residual;
     void* y;
-    int y_f32, act, narrow;
+    int y_f32, act, narrow, res_prefetch;
     float alpha, gain;
 };
 
 // ---- shared epilogue: 32 accumulator columns of one pixel row -> bias / act / residual -> NHWC store ---------------
-__device__ __forceinline__ void epilogue_chunk(const FwdParams& p, const uint32_t (&r)[32], bool valid, int64_t pix, int co0, int c) {
+__device__ __forceinline__ void epilogue_chunk(const FwdParams& p, const uint32_t (&r)[32], bool valid, int64_t pix, int co0, int c,
+                                               const uint4* qpre = nullptr) {
     if (!valid) return;
     if (p.narrow) {
         // Co < BN (e.g. the 3-channel image head): scalar, masked stores; static register indices
@@ -164,7 +165,8 @@ __device__ __forceinline__ void epilogue_chunk(const FwdParams& p, const uint32_
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
             if (ro) {
-                uint4 q = *reinterpret_cast<const uint4*>(ro + j);
+                // qpre: the residual of this chunk was requested before the accumulator was awaited (its latency is hidden)
+                uint4 q = qpre ? qpre[j >> 3] : *reinterpret_cast<const uint4*>(ro + j);
                 const __nv_bfloat162* qb = reinterpret_cast<const __nv_bfloat162*>(&q);
 #pragma unroll
                 for (int u = 0; u < 4; ++u) { float2 f = __bfloat1622float2(qb[u]); v[j + 2 * u] += f.x; v[j + 2 * u + 1] += f.y; }
@@ -178,31 +180,56 @@ __device__ __forceinline__ void epilogue_chunk(const FwdParams& p, const uint32_
     }
 }
 
-// epilogue warps of both forward kernels: drain the MT sub-tile accumulators of every tile this CTA owns
+// epilogue warps of both forward kernels: drain the MT sub-tile accumulators of every tile this CTA owns.
+// A fused bf16 residual is PREFETCHED one 32-column chunk ahead (the first chunk of a tile before the accumulator barrier is
+// awaited): issued at the point of use, these 16-byte loads were latency-exposed and made residual convolutions 1.6x slower
+// than plain ones (ncu: long-scoreboard stalls 9.6 vs 1.7 per issue, tensor pipe 43 % vs 91 % busy).
 __device__ __forceinline__ void epilogue_loop(const FwdParams& p, uint32_t tmem_base, uint64_t* tfull, uint64_t* tempty, int warp, int lane) {
     const int quarter = warp & 3;                    // TMEM lane quarter this warp may read
     const int half = (warp - 2) >> 2;                // two warps per quarter take alternating 32-column chunks
     const int row = quarter * 32 + lane;
     const int wi = row % p.tw, r2 = row / p.tw, hi = r2 % p.th, ni = r2 / p.th;
+    const bool pre = p.residual && !p.y_f32 && !p.narrow && p.res_prefetch;
+    const int nch = (p.BN - half * 32 + 63) / 64;    // chunks of one sub-tile handled by this warp
     int as = 0; uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int ct = tile % p.co_tiles, pt = tile / p.co_tiles;
         const int co0 = ct * p.BN;
-        ptx::mbar_wait(&tfull[as], aphase);
-        ptx::tc_fence_after();
-        for (int m = 0; m < p.MT; ++m) {
+        auto locate = [&](int m, bool& valid, int64_t& pix) {
             const int q = pt * p.MT + m;
             const int twi = q % p.tiles_w, t2 = q / p.tiles_w, thi = t2 % p.tiles_h, tni = t2 / p.tiles_h;
             const int w = twi * p.tw + wi, h = thi * p.th + hi, n = tni * p.nb + ni;
-            const bool valid = (w < p.W) && (h < p.H) && (n < p.N);
-            const int64_t pix = ((int64_t)n * p.H + h) * p.W + w;
-            const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((as * p.MT + m) * p.BN);
-            for (int c = half * 32; c < p.BN; c += 64) {
-                uint32_t r[32];
-                ptx::tmem_ld32(t_addr + (uint32_t)c, r);
-                ptx::tmem_ld_wait();
-                epilogue_chunk(p, r, valid, pix, co0, c);
+            valid = (w < p.W) && (h < p.H) && (n < p.N);
+            pix = ((int64_t)n * p.H + h) * p.W + w;
+        };
+        auto fetch = [&](int s, uint4 (&q)[4]) {       // s = m * nch + chunk index
+            bool valid; int64_t pix;
+            locate(s / nch, valid, pix);
+            const int c = half * 32 + (s % nch) * 64;
+            if (valid) {
+                const uint4* ro = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.residual) + pix * p.Co + co0 + c);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) q[i] = ro[i];
             }
+        };
+        const int total = p.MT * nch;
+        uint4 qn[4] = {};
+        if (pre && total > 0) fetch(0, qn);
+        ptx::mbar_wait(&tfull[as], aphase);
+        ptx::tc_fence_after();
+        for (int s = 0; s < total; ++s) {
+            const int m = s / nch, c = half * 32 + (s % nch) * 64;
+            bool valid; int64_t pix;
+            locate(m, valid, pix);
+            uint4 qc[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) qc[i] = qn[i];
+            if (pre && s + 1 < total) fetch(s + 1, qn);
+            const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((as * p.MT + m) * p.BN);
+            uint32_t r[32];
+            ptx::tmem_ld32(t_addr + (uint32_t)c, r);
+            ptx::tmem_ld_wait();
+            epilogue_chunk(p, r, valid, pix, co0, c, pre ? qc : nullptr);
         }
         ptx::tc_fence_before();
         __syncwarp();
@@ -533,10 +560,28 @@ conv_fwd_tc_halo_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
             float bv[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) bv[u] = p.bias ? __ldg(p.bias + co8 + u) : 0.f;
+            // bf16 residual of the NEXT 32-column chunk is requested one chunk ahead (see epilogue_loop)
+            const bool pre = p.residual && !p.y_f32 && p.res_prefetch;
+            auto fetch = [&](int c, uint4 (&q)[4]) {
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                    const int pl = it * 8 + prow;
+                    const int h = h0 + (c >> 3) + (pl >> 3), w = w0 + (pl & 7);
+                    if (h < p.H && w < p.W)
+                        q[it] = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.residual) +
+                                                                (((int64_t)n * p.H + h) * p.W + w) * p.Co + co8);
+                }
+            };
+            uint4 qn[4] = {};
+            if (pre) fetch(half * 32, qn);
             ptx::mbar_wait(&tfull[as], aphase);
             ptx::tc_fence_after();
             const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * NPIX);
             for (int c = half * 32; c < NPIX; c += 64) {
+                uint4 qc[4];
+#pragma unroll
+                for (int it = 0; it < 4; ++it) qc[it] = qn[it];
+                if (pre && c + 64 < NPIX) fetch(c + 64, qn);
                 uint32_t r[32];
                 ptx::tmem_ld32(t_addr + (uint32_t)c, r);
                 ptx::tmem_ld_wait();
@@ -568,7 +613,7 @@ conv_fwd_tc_halo_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
                         } else {
                             bf16* yo = reinterpret_cast<bf16*>(p.y) + off;
                             if (p.residual) {
-                                uint4 q = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.residual) + off);
+                                const uint4 q = pre ? qc[it] : *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.residual) + off);
                                 const __nv_bfloat162* qb = reinterpret_cast<const __nv_bfloat162*>(&q);
 #pragma unroll
                                 for (int u = 0; u < 4; ++u) { float2 f = __bfloat1622float2(qb[u]); v[2 * u] += f.x; v[2 * u + 1] += f.y; }
@@ -866,6 +911,8 @@ int vqb_conv2d_fwd_tc(const void* x, const void* wp, const float* bias, const vo
     p.cchunks = Ci / BK;
     p.ksteps = KH * KW * p.cchunks;
     p.bias = bias; p.residual = residual; p.y = y; p.y_f32 = (y_dtype == VQB_F32); p.act = act; p.alpha = alpha; p.gain = gain;
+    static const int res_prefetch = getenv("VQB_RES_PREFETCH") ? atoi(getenv("VQB_RES_PREFETCH")) : 1;
+    p.res_prefetch = res_prefetch;
     p.pitch = 0; p.bo_mode = 0; p.a_tile_bytes = 0; p.a_stages = 0; p.b_stages = 0;
     const int mode = g_halo_override >= 0 ? g_halo_override : halo_mode();
     const bool halo = mode != 0 && KH == 3 && KW == 3 && pad == 1 && H >= 16 && W >= 8;
