@@ -22,3 +22,19 @@ for ci, co, h in shapes:
                 if it >= 3: ts.append(e0.elapsed_time(e1))
         ms = sorted(ts)[len(ts) // 2]
         print(f'{ci:4d}->{co:4d} @{h:3d}^2 {name:9s} {ms * 1e3:8.1f} us  {fl / ms / 1e9:8.1f} TFLOP/s')
+
+# weight gradients of the same shapes
+for ci, co, h in shapes:
+    x = torch.randn(B, ci, h, h, device='cuda').bfloat16().contiguous(memory_format=cl).requires_grad_(False)
+    w = (torch.randn(co, ci, 3, 3, device='cuda') / (ci * 9) ** 0.5).requires_grad_()
+    dy = torch.randn(B, co, h, h, device='cuda').bfloat16().contiguous(memory_format=cl)
+    fl = 2.0 * B * h * h * ci * co * 9
+    pkg.lib.timer = pkg.lib.KernelTimer(['vqb_conv2d_wgrad'])
+    for it in range(8):
+        y = pkg.ops.conv2d(x, w, None, None, pad=1)
+        y.backward(dy)
+    torch.cuda.synchronize()
+    ts = sorted(s_.elapsed_time(e_) for _, _, s_, e_ in pkg.lib.timer.records[3:])
+    pkg.lib.timer = None
+    ms = ts[len(ts) // 2]
+    print(f'{ci:4d}->{co:4d} @{h:3d}^2 wgrad     {ms * 1e3:8.1f} us  {fl / ms / 1e9:8.1f} TFLOP/s')

@@ -991,7 +991,11 @@ int vqb_conv2d_wgrad_tc(const void* x, const void* dy, float* dwp, int N, int H,
         h.stages = (SMEM_LIMIT - 2048) / stage_bytes; if (h.stages > 8) h.stages = 8;
         h.ptiles_total = h.tiles_w * h.tiles_h * N;
         const int out_tiles = 3 * h.ci_tiles * h.co_tiles;
-        int splits = (sm_count() * 2 + out_tiles - 1) / out_tiles;
+        // ONE wave: TMEM (3 x 128 accumulator columns) admits one CTA per SM, so out_tiles * splits must not exceed the SM count
+        // -- ceil(2 * SMs / out_tiles) gave 297 CTAs for the 128-channel layers: two waves plus ONE straggler CTA (ncu: SMs
+        // active 57 % of the launch) and twice the atomic-combine traffic.
+        static const int waves = getenv("VQB_WGRAD_WAVES") ? atoi(getenv("VQB_WGRAD_WAVES")) : 1;
+        int splits = waves == 2 ? (sm_count() * 2 + out_tiles - 1) / out_tiles : (out_tiles <= sm_count() ? sm_count() / out_tiles : 1);
         int max_splits = (h.ptiles_total + 7) / 8; if (max_splits < 1) max_splits = 1;
         if (splits > max_splits) splits = max_splits;
         if (splits < 1) splits = 1;
@@ -1018,7 +1022,7 @@ int vqb_conv2d_wgrad_tc(const void* x, const void* dy, float* dwp, int N, int H,
     p.stages = (SMEM_LIMIT - 2048) / stage_bytes; if (p.stages > 8) p.stages = 8;
     p.ptiles_total = p.tiles_w * p.tiles_h * p.tiles_n;
     const int out_tiles = KH * KW * p.ci_tiles * p.co_tiles;
-    int splits = (sm_count() * 2 + out_tiles - 1) / out_tiles;       // ~2 waves of CTAs
+    int splits = out_tiles <= sm_count() ? sm_count() / out_tiles : 1;       // one wave of CTAs (see the halo launcher)
     int max_splits = (p.ptiles_total + 7) / 8; if (max_splits < 1) max_splits = 1;   // >= 8 pixel tiles (512 pixels) per CTA
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
