@@ -174,6 +174,10 @@ int vqb_zero_upsample2(const void* y, void* x, int dtype, int N, int H, int W, i
  * gradient to the first maximal element of each window (torch semantics) and writes all of dx */
 int vqb_maxpool2_fwd(const void* x, void* y, int dtype, int N, int H, int W, int C, void* stream);
 int vqb_maxpool2_bwd(const void* x, int x_dtype, const void* dy, void* dx, int g_dtype, int N, int H, int W, int C, void* stream);
+/* 3x3 / stride-2 max-pool without padding (torchvision AlexNet features, the LPIPS 'alex' trunk of loss.py:182):
+ * x [N,H,W,C] -> y [N,(H-3)/2+1,(W-3)/2+1,C]; overlapping windows, backward in gather form with torch's first-argmax rule */
+int vqb_maxpool3s2_fwd(const void* x, void* y, int dtype, int N, int H, int W, int C, void* stream);
+int vqb_maxpool3s2_bwd(const void* x, int x_dtype, const void* dy, void* dx, int g_dtype, int N, int H, int W, int C, void* stream);
 /* y[p][c] = x[p][c]*scale[c] + shift[c]  (BaseNet.z_score, lpips_pytorch/modules/networks.py:48-49) */
 int vqb_channel_affine(const void* x, int x_dtype, void* y, int y_dtype, const float* scale, const float* shift, int64_t P, int C,
                        void* stream);

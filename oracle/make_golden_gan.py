@@ -20,20 +20,27 @@ OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'tests', 'g
 LPIPS_CH = [64, 128, 256, 512, 512]
 
 
-def ref_lpips(seed: int):
+LPIPS_CH_ALEX = [64, 192, 384, 256, 256]
+
+
+def ref_lpips(seed: int, net_type: str = 'vgg'):
     import torchvision
     import vqvae.modules.loss.lpips_pytorch.modules.networks as nets
     import vqvae.modules.loss.lpips_pytorch.modules.lpips as lp
-    _vgg = torchvision.models.vgg16
+    if not hasattr(ref_lpips, '_tv'):
+        ref_lpips._tv = (torchvision.models.vgg16, torchvision.models.alexnet)
+    _vgg, _alex = ref_lpips._tv
     nets.models.vgg16 = lambda weights=None, **kw: _vgg(weights=None)
+    nets.models.alexnet = lambda *a, **kw: _alex(weights=None)            # the reference calls alexnet(True): no network here
+    chans = LPIPS_CH if net_type == 'vgg' else LPIPS_CH_ALEX
     lp.get_state_dict = lambda net_type='alex', version='0.1': OrderedDict(
-        (f'{i}.1.weight', torch.rand(1, c, 1, 1)) for i, c in enumerate(LPIPS_CH))
+        (f'{i}.1.weight', torch.rand(1, c, 1, 1)) for i, c in enumerate(chans))
     torch.manual_seed(seed)
-    return lp.LPIPS('vgg')
+    return lp.LPIPS(net_type)
 
 
-def lpips_case(seed=11, B=2, S=64):
-    m = ref_lpips(seed).eval()
+def lpips_case(seed=11, B=2, S=64, net_type='vgg'):
+    m = ref_lpips(seed, net_type).eval()
     x = torch.rand(B, 3, S, S) * 2 - 1
     y = (torch.rand(B, 3, S, S) * 2 - 1).requires_grad_()
     out = m(x, y)
@@ -41,7 +48,7 @@ def lpips_case(seed=11, B=2, S=64):
     feats = m.net(y.detach())
     # the same computation in float64: ReLU / max-pool routing makes the fp32 gradient fragile at random init (the reference's
     # own fp32 result is ~0.7% away from fp64), so the tests bound the kernel's error by the reference's own fp32 error
-    md = ref_lpips(seed).eval().double()
+    md = ref_lpips(seed, net_type).eval().double()
     yd = y.detach().double().requires_grad_()
     md(x.double(), yd).backward()
     return {'grad_y_f64': yd.grad.numpy(),'loss': np.float32(out.item()), 'grad_y': y.grad.numpy(), 'x': x.numpy(), 'y': y.detach().numpy(),
@@ -130,6 +137,9 @@ def main():
     res = lpips_case()
     np.savez_compressed(os.path.join(OUT, 'gan_lpips_vgg.npz'), **res)
     print('lpips', res['loss'], res['feat_sums'])
+    res = lpips_case(seed=13, B=2, S=96, net_type='alex')
+    np.savez_compressed(os.path.join(OUT, 'gan_lpips_alex.npz'), **res)
+    print('lpips alex', res['loss'], res['feat_sums'])
     res = disc_case()
     np.savez_compressed(os.path.join(OUT, 'gan_discriminator.npz'), **res)
     print('disc', res['logits'].ravel(), res['loss'])

@@ -43,6 +43,11 @@ def main():
     out['quantizer.entropy(32,16)'] = describe(vq.EntropyVectorQuantizer(32, 16, 0.1, 0.01, 'softmax', 0.25))
     out['discriminator(64)'] = describe(Discriminator(64))
     out['lpips(vgg)'] = describe(lp.LPIPS('vgg'))
+    _alex = torchvision.models.alexnet
+    nets.models.alexnet = lambda *a, **kw: _alex(weights=None)
+    lp.get_state_dict = lambda net_type='alex', version='0.1': OrderedDict(
+        (f'{i}.1.weight', torch.rand(1, c, 1, 1)) for i, c in enumerate([64, 192, 384, 256, 256]))
+    out['lpips(alex)'] = describe(lp.LPIPS('alex'))
     with open(OUT, 'w') as f:
         json.dump(out, f, indent=0)
     print({k: len(v) for k, v in out.items()})

@@ -93,3 +93,25 @@ def test_vqgan_step_fast_mode(V):
     assert torch.isfinite(loss).all()
     for k in ('train/perc_loss', 'train/gen_loss', 'train/disc_loss', 'train/quant_loss'):
         assert torch.isfinite(torch.as_tensor(model.logged[k])).all(), k
+
+
+def test_lpips_only_step_fast_mode_alexnet(V):
+    """branch B of training_step (VQLPIPS, AlexNet trunk as in loss.py:182) in the bf16 fast mode."""
+    from vqvae_vqgan_pytorch_lightning_b200.lightning_shim import Trainer
+    torch.manual_seed(4)
+    model = V.VQVAE(96, dict(channels=128, num_res_blocks=1, channel_multipliers=[1, 2]),
+                    dict(num_embeddings=128, embedding_dim=64, type='ema', params=dict(commitment_cost=0.25, decay=0.95, epsilon=1e-5),
+                         reinit_every_n_epochs=None),
+                    dict(l1_weight=0.8, l2_weight=0.2, perc_weight=1.0, adversarial_params=None),
+                    dict(lr=1e-4, betas=[0.9, 0.99], eps=1e-8, weight_decay=1e-4, warmup_epochs=None, decay_epochs=None),
+                    pretrained_lpips=False).cuda().train()
+    from vqvae_vqgan_pytorch_lightning_b200.modules.loss.lpips import AlexNet
+    assert isinstance(model.criterion.perceptual_loss.net, AlexNet)
+    tr = Trainer(max_epochs=1, num_training_batches=4)
+    tr.attach(model); model.on_train_start()
+    x = torch.rand(4, 3, 96, 96, device='cuda')
+    w0 = model.decoder.conv_out.weight.detach().clone()
+    for i in range(2):
+        loss = tr.run_step(x, i)
+    assert torch.isfinite(loss).all() and torch.isfinite(torch.as_tensor(model.logged['train/perc_loss'])).all()
+    assert float(model.logged['train/perc_loss']) > 0 and not torch.equal(model.decoder.conv_out.weight, w0)

@@ -97,6 +97,48 @@ def test_lpips_vgg_matches_reference_fixture(V):
     assert C.rel_err(y.grad, g['grad_y_f64']) <= 2 * err_ref + TOL
 
 
+def test_lpips_alex_matches_reference_fixture(V):
+    """the AlexNet trunk of the VQLPIPS ablation loss (loss.py:182): 11x11 / stride-4 conv, overlapping 3x3 / stride-2
+    max-pools, 5x5 conv, 192 / 384-channel layers."""
+    import torchvision
+    from vqvae_vqgan_pytorch_lightning_b200.modules.loss.lpips import LPIPS
+    g = C.golden('gan_lpips_alex')
+    chans = [64, 192, 384, 256, 256]
+    torch.manual_seed(13)                                          # same RNG stream as oracle/make_golden_gan.ref_lpips
+    tv = torchvision.models.alexnet(weights=None)
+    _ = [nn.Conv2d(nc, 1, 1, 1, 0, bias=False) for nc in chans]
+    lin_w = [torch.rand(1, c, 1, 1) for c in chans]
+    assert abs(float(tv.features[0].weight.double().sum()) - float(g['w0_sum'])) < 1e-9
+    m = LPIPS('alex', pretrained=False)
+    m.net.layers.load_state_dict(tv.features.state_dict())
+    for i, w in enumerate(lin_w):
+        m.lin[i][1].weight.data.copy_(w)
+    m = m.cuda().eval()
+    x, y = cl(torch.from_numpy(g['x'])), cl(torch.from_numpy(g['y'])).requires_grad_()
+    feats = m.net(y.detach())
+    assert [f.shape[1] for f in feats] == chans
+    for f, s in zip(feats, g['feat_sums']):
+        fn = f.float() / (f.float().pow(2).sum(1, keepdim=True).sqrt() + 1e-10)
+        assert abs(float(fn.double().sum()) - s) <= 2e-4 * abs(s)
+    out = m(x, y)
+    out.backward()
+    assert abs(float(out) - float(g['loss'])) <= TOL * abs(float(g['loss']))
+    err_ref = C.rel_err(g['grad_y'], g['grad_y_f64'])
+    assert C.rel_err(y.grad, g['grad_y_f64']) <= 2 * err_ref + 2 * TOL
+
+
+def test_maxpool3s2_matches_torch(V):
+    from vqvae_vqgan_pytorch_lightning_b200 import ops_gan
+    torch.manual_seed(6)
+    for (n, c, h, w) in ((2, 8, 15, 15), (1, 5, 7, 10), (2, 16, 8, 9)):
+        x = torch.randn(n, c, h, w).round(decimals=1)               # coarse values: ties inside windows are exercised
+        xo = x.clone().requires_grad_()
+        y = F.max_pool2d(xo, 3, 2); go = torch.randn_like(y); y.backward(go)
+        xg = cl(x).requires_grad_()
+        yg = ops_gan.max_pool3s2(xg); yg.backward(cl(go))
+        assert torch.equal(yg.cpu(), y) and C.rel_err(xg.grad, xo.grad) < 1e-6
+
+
 def test_discriminator_matches_reference_fixture(V):
     from vqvae_vqgan_pytorch_lightning_b200.modules.loss.discriminator import Discriminator
     g = C.golden('gan_discriminator')

@@ -34,12 +34,13 @@ def build(name):
         'quantizer.entropy(32,16)': lambda: vq.EntropyVectorQuantizer(32, 16, 0.1, 0.01, 'softmax', 0.25),
         'discriminator(64)': lambda: Discriminator(64),
         'lpips(vgg)': lambda: LPIPS('vgg', pretrained=False),
+        'lpips(alex)': lambda: LPIPS('alex', pretrained=False),
     }[name]()
 
 
 @pytest.mark.parametrize('name', ['encoder(128,2,[1,2],64)', 'decoder(128,2,[1,2],64)', 'quantizer.standard(32,16)',
                                   'quantizer.ema(32,16)', 'quantizer.gumbel(32,16)', 'quantizer.entropy(32,16)',
-                                  'discriminator(64)', 'lpips(vgg)'])
+                                  'discriminator(64)', 'lpips(vgg)', 'lpips(alex)'])
 def test_state_dict_layout_matches_reference(keys, name):
     ref = keys[name]
     got = describe(build(name))

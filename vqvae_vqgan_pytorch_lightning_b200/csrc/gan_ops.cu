@@ -97,6 +97,54 @@ __global__ void maxpool2_bwd_kernel(const T* __restrict__ x, const TG* __restric
     }
 }
 
+// 3x3 / stride-2 max-pool without padding (torchvision AlexNet features): y [N,OH,OW,C], OH = (H-3)/2+1
+template <typename T>
+__global__ void maxpool3s2_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int OH, int OW) {
+    int64_t total = (int64_t)N * OH * OW * C;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(i % C); int64_t r = i / C; int ow = (int)(r % OW); r /= OW; int oh = (int)(r % OH); int n = (int)(r / OH);
+        const T* p = x + (((int64_t)n * H + 2 * oh) * W + 2 * ow) * C + c;
+        float m = -INFINITY;
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) m = fmaxf(m, ld1(p + ((int64_t)a * W + b) * C));
+        st1(y + i, m);
+    }
+}
+
+// overlapping windows: gather form.  Each input element belongs to <= 4 windows; it receives a window's gradient iff it is
+// the FIRST maximal element of that window in scan order (torch max_pool2d argmax semantics).
+template <typename T, typename TG>
+__global__ void maxpool3s2_bwd_kernel(const T* __restrict__ x, const TG* __restrict__ dy, TG* __restrict__ dx, int N, int H, int W,
+                                      int C, int OH, int OW) {
+    int64_t total = (int64_t)N * H * W * C;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(i % C); int64_t r = i / C; int w = (int)(r % W); r /= W; int h = (int)(r % H); int n = (int)(r / H);
+        const float xv = ld1(x + i);
+        float acc = 0.f;
+        // windows covering row h: 2*oh <= h <= 2*oh + 2  ->  oh in [ceil((h-2)/2), floor(h/2)], clipped to the output grid
+        const int oh_lo = h > 0 ? (h - 1) / 2 : 0, oh_hi = min(h / 2, OH - 1);
+        const int ow_lo = w > 0 ? (w - 1) / 2 : 0, ow_hi = min(w / 2, OW - 1);
+        for (int oh = oh_lo; oh <= oh_hi; ++oh) {
+            for (int ow = ow_lo; ow <= ow_hi; ++ow) {
+                const T* p = x + (((int64_t)n * H + 2 * oh) * W + 2 * ow) * C + c;
+                const int mine = (h - 2 * oh) * 3 + (w - 2 * ow);
+                float m = -INFINITY; int arg = 0;
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) {
+                        float v = ld1(p + ((int64_t)a * W + b) * C);
+                        if (v > m) { m = v; arg = a * 3 + b; }
+                    }
+                if (arg == mine && m == xv) acc += ld1(dy + (((int64_t)n * OH + oh) * OW + ow) * C + c);
+            }
+        }
+        st1(dx + i, acc);
+    }
+}
+
 template <typename TI, typename TO>
 __global__ void channel_affine_kernel(const TI* __restrict__ x, TO* __restrict__ y, const float* __restrict__ scale,
                                       const float* __restrict__ shift, int64_t P, int C) {
@@ -277,6 +325,23 @@ extern "C" int vqb_maxpool2_bwd(const void* x, int x_dtype, const void* dy, void
     VQB_DISPATCH_1(x_dtype, T, VQB_DISPATCH_1(g_dtype, TG, (maxpool2_bwd_kernel<T, TG><<<ew_grid((int64_t)N * H * W * C), 256, 0, as_stream(stream)>>>(
                                                                (const T*)x, (const TG*)dy, (TG*)dx, N, H, W, C));))
     VQB_CHECK_LAUNCH("maxpool2_bwd");
+    return VQB_OK;
+}
+
+extern "C" int vqb_maxpool3s2_fwd(const void* x, void* y, int dtype, int N, int H, int W, int C, void* stream) {
+    VQB_CHECK_ARG(x && y && N > 0 && H >= 3 && W >= 3 && C > 0, "maxpool3s2_fwd: bad arguments (needs H, W >= 3)");
+    const int OH = (H - 3) / 2 + 1, OW = (W - 3) / 2 + 1;
+    VQB_DISPATCH_1(dtype, T, (maxpool3s2_fwd_kernel<T><<<ew_grid((int64_t)N * OH * OW * C), 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, N, H, W, C, OH, OW));)
+    VQB_CHECK_LAUNCH("maxpool3s2_fwd");
+    return VQB_OK;
+}
+
+extern "C" int vqb_maxpool3s2_bwd(const void* x, int x_dtype, const void* dy, void* dx, int g_dtype, int N, int H, int W, int C, void* stream) {
+    VQB_CHECK_ARG(x && dy && dx && N > 0 && H >= 3 && W >= 3 && C > 0, "maxpool3s2_bwd: bad arguments (needs H, W >= 3)");
+    const int OH = (H - 3) / 2 + 1, OW = (W - 3) / 2 + 1;
+    VQB_DISPATCH_1(x_dtype, T, VQB_DISPATCH_1(g_dtype, TG, (maxpool3s2_bwd_kernel<T, TG><<<ew_grid((int64_t)N * H * W * C), 256, 0, as_stream(stream)>>>(
+        (const T*)x, (const TG*)dy, (TG*)dx, N, H, W, C, OH, OW));))
+    VQB_CHECK_LAUNCH("maxpool3s2_bwd");
     return VQB_OK;
 }
 

@@ -41,6 +41,8 @@ SIGNATURES = {
     'vqb_zero_upsample2': (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     'vqb_maxpool2_fwd': (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     'vqb_maxpool2_bwd': (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _i, _p]),
+    'vqb_maxpool3s2_fwd': (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
+    'vqb_maxpool3s2_bwd': (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _i, _p]),
     'vqb_channel_affine': (_i, [_p, _i, _p, _i, _p, _p, _i64, _i, _p]),
     'vqb_lpips_tap_fwd': (_i, [_p, _p, _i, _p, _p, _i64, _i, _p]),
     'vqb_lpips_tap_bwd': (_i, [_p, _p, _i, _p, _p, _f, _p, _i, _i64, _i, _p]),

@@ -117,8 +117,7 @@ class VQLPIPSWithDiscriminator(nn.Module):
 
 
 class VQLPIPS(nn.Module):
-    """loss.py:167-199 (ablation: LPIPS without discriminator).  The reference uses the AlexNet trunk here; only VGG is built,
-    so `net_type='vgg'` must be requested explicitly."""
+    """loss.py:167-199 (ablation: LPIPS without discriminator), AlexNet trunk as in the reference (`net_type='alex'`)."""
 
     def __init__(self, l1_weight: float, l2_weight: float, perc_weight: float, net_type: str = 'alex', pretrained_lpips: bool = True):
         super().__init__()

@@ -26,6 +26,11 @@ class _MaxPool(nn.Module):
         return ops_gan.max_pool2(x)
 
 
+class _MaxPool3s2(nn.Module):
+    def forward(self, x):
+        return ops_gan.max_pool3s2(x)
+
+
 class LinLayers(nn.ModuleList):
     """networks.py:24-34 -- frozen 1x1 convs (nc -> 1, no bias); applied inside the fused tap kernel"""
 
@@ -70,6 +75,50 @@ class VGG16(nn.Module):
         return out
 
 
+class _BaseNet(nn.Module):
+    """networks.py:37-64: z-score with the LPIPS constants, then the trunk with normalised taps after `target_layers`."""
+
+    def __init__(self):
+        super().__init__()
+        self.register_buffer('mean', torch.Tensor([-.030, -.088, -.188])[None, :, None, None])
+        self.register_buffer('std', torch.Tensor([.458, .448, .450])[None, :, None, None])
+
+    def forward(self, x: torch.Tensor):
+        scale = (1.0 / self.std).reshape(-1).float().contiguous()
+        shift = (-self.mean / self.std).reshape(-1).float().contiguous()
+        x = ops_gan.channel_affine(x, scale, shift, torch.float32)
+        out = []
+        for i, layer in enumerate(self.layers, 1):
+            if isinstance(layer, Conv2d):
+                x = layer(x, act=ACT_RELU)
+            elif isinstance(layer, (_MaxPool, _MaxPool3s2)):
+                x = layer(x)
+            if i in self.target_layers:
+                out.append(x)
+            if len(out) == len(self.target_layers):
+                break
+        return out
+
+
+class AlexNet(_BaseNet):
+    """networks.py:78-86: torchvision alexnet.features (conv 11x11/4, pool 3/2, conv 5x5, pool 3/2, three 3x3 convs) with taps
+    after every ReLU (layers 2, 5, 8, 10, 12; 64, 192, 384, 256, 256 channels) -- the trunk of the VQLPIPS ablation loss
+    (loss.py:182).  Same layer numbering, hence the same state_dict keys, as torchvision."""
+
+    def __init__(self):
+        super().__init__()
+        self.layers = nn.Sequential(
+            Conv2d(3, 64, kernel_size=11, stride=4, padding=2), _FusedReLU(), _MaxPool3s2(),
+            Conv2d(64, 192, kernel_size=5, padding=2), _FusedReLU(), _MaxPool3s2(),
+            Conv2d(192, 384, kernel_size=3, padding=1), _FusedReLU(),
+            Conv2d(384, 256, kernel_size=3, padding=1), _FusedReLU(),
+            Conv2d(256, 256, kernel_size=3, padding=1), _FusedReLU(), _MaxPool3s2())
+        self.target_layers = [2, 5, 8, 10, 12]
+        self.n_channels_list = [64, 192, 384, 256, 256]
+        for p in self.parameters():
+            p.requires_grad = False
+
+
 class LPIPS(nn.Module):
     """LPIPS(net_type)(x, y) -> scalar (lpips.py:18-38).  `pretrained=True` loads torchvision's VGG16 weights and the
     LPIPS v0.1 lin weights exactly as the reference does (both need a network connection or a populated torch hub cache)
@@ -78,17 +127,24 @@ class LPIPS(nn.Module):
     def __init__(self, net_type: str = 'alex', version: str = '0.1', pretrained: bool = True):
         assert version in ['0.1'], 'v0.1 is only supported now'
         super().__init__()
-        if net_type != 'vgg':
-            raise NotImplementedError("only the 'vgg' trunk used by the VQGAN loss is built (AlexNet is the ablation row L4)")
-        self.net = VGG16()
+        if net_type == 'vgg':
+            self.net = VGG16()
+        elif net_type == 'alex':
+            self.net = AlexNet()
+        else:
+            raise NotImplementedError("choose net_type from [alex, vgg] (the reference's 'squeeze' trunk is used nowhere in it)")
         self.lin = LinLayers(self.net.n_channels_list)
         if pretrained:
             self._load_pretrained(net_type, version)
 
     def _load_pretrained(self, net_type: str, version: str) -> None:
         from torchvision import models
-        tv = models.vgg16(weights=models.VGG16_Weights.DEFAULT).features            # networks.py:93
-        self.net.layers.load_state_dict({k: v for k, v in tv.state_dict().items() if int(k.split('.')[0]) < 30})
+        if net_type == 'vgg':
+            tv = models.vgg16(weights=models.VGG16_Weights.DEFAULT).features        # networks.py:93
+            self.net.layers.load_state_dict({k: v for k, v in tv.state_dict().items() if int(k.split('.')[0]) < 30})
+        else:
+            tv = models.alexnet(weights=models.AlexNet_Weights.DEFAULT).features    # networks.py:82 (alexnet(True))
+            self.net.layers.load_state_dict(tv.state_dict())
         url = ('https://raw.githubusercontent.com/richzhang/PerceptualSimilarity/' + f'master/lpips/weights/v{version}/{net_type}.pth')
         sd = torch.hub.load_state_dict_from_url(url, progress=False, map_location='cpu')          # utils.py:11-20
         self.lin.load_state_dict({k.replace('lin', '').replace('model.', ''): v for k, v in sd.items()})

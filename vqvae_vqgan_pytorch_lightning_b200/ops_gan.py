@@ -77,6 +77,31 @@ class MaxPool2Fn(torch.autograd.Function):
 max_pool2 = MaxPool2Fn.apply
 
 
+class MaxPool3s2Fn(torch.autograd.Function):
+    """nn.MaxPool2d(kernel_size=3, stride=2) of torchvision's AlexNet features (overlapping windows)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = as_nhwc(x)
+        n, c, h, w = x.shape
+        y = empty_nhwc(n, c, (h - 3) // 2 + 1, (w - 3) // 2 + 1, x.dtype, x.device)
+        call('vqb_maxpool3s2_fwd', ptr(x), ptr(y), dt(x), n, h, w, c, stream())
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        n, c, h, w = x.shape
+        dy = as_nhwc(dy)
+        dx = torch.empty_like(x, dtype=dy.dtype, memory_format=torch.preserve_format)
+        call('vqb_maxpool3s2_bwd', ptr(x), dt(x), ptr(dy), ptr(dx), dt(dy), n, h, w, c, stream())
+        return dx
+
+
+max_pool3s2 = MaxPool3s2Fn.apply
+
+
 class ChannelAffineFn(torch.autograd.Function):
     """y = x * scale[c] + shift[c] (BaseNet.z_score with scale = 1/std, shift = -mean/std)."""
 
