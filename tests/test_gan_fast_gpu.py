@@ -115,3 +115,29 @@ def test_lpips_only_step_fast_mode_alexnet(V):
         loss = tr.run_step(x, i)
     assert torch.isfinite(loss).all() and torch.isfinite(torch.as_tensor(model.logged['train/perc_loss'])).all()
     assert float(model.logged['train/perc_loss']) > 0 and not torch.equal(model.decoder.conv_out.weight, w0)
+
+
+def test_down_conv_small_resolution_tensor_core_route(V):
+    """the 8 -> 4 discriminator block: FIR output 9 x 9, full-resolution tcgen05 conv on a sub-tile-sized image + decimation."""
+    from vqvae_vqgan_pytorch_lightning_b200.modules.loss.discriminator import Conv2dLayer, setup_filter
+    torch.manual_seed(7)
+    n, ci, co, h = 4, 128, 128, 8
+    layer = Conv2dLayer(ci, co, kernel_size=3, activation='lrelu', down=2)
+    with torch.no_grad():
+        layer.weight.copy_(r16(layer.weight)); layer.bias.copy_(torch.randn(co) * 0.1)
+    x = r16(torch.randn(n, ci, h, h)); go = r16(torch.randn(n, co, h // 2, h // 2))
+    f = setup_filter()
+    xo = x.clone().requires_grad_(); wo = layer.weight.detach().clone().requires_grad_(); bo = layer.bias.detach().clone().requires_grad_()
+    xb = F.conv2d(F.pad(xo, [2, 2, 2, 2]), f[None, None].repeat(ci, 1, 1, 1), groups=ci)
+    xb = xb + (r16(xb) - xb).detach()
+    wq = wo * layer.weight_gain
+    wq = wq + (r16(wq) - wq).detach()
+    yo = F.leaky_relu(F.conv2d(xb, wq, bo, stride=2), 0.2) * np.sqrt(2)
+    yo.backward(go)
+    layer = layer.cuda()
+    xg = cl(x).bfloat16().requires_grad_()
+    yg = layer(xg)
+    assert yg.shape == yo.shape
+    yg.backward(cl(go).bfloat16())
+    assert C.rel_err(yg.float(), yo) < 5e-3 and C.rel_err(xg.grad.float(), xo.grad) < 1e-2
+    assert C.rel_err(layer.weight.grad, wo.grad) < 1e-2 and C.rel_err(layer.bias.grad, bo.grad) < 1e-2

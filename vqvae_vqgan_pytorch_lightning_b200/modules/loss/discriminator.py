@@ -89,7 +89,7 @@ class Conv2dLayer(nn.Module):
         x = ops_gan.fir4(x, self.padding + 1, 1)
         co, ci = self.weight.shape[0], self.weight.shape[1]
         if (ops.get_precision().name == 'fast' and self.kernel_size == 3 and residual is None and ci % 64 == 0 and co % 128 == 0
-                and x.shape[2] >= 17 and x.shape[3] >= 9):
+                and x.shape[2] >= 9 and x.shape[3] >= 9):
             # tensor-core route: the same convolution at stride 1 ('same' padding, full resolution) keeps every 2nd output:
             # valid_out[i] = same_out[i+1], strided_out[o] = valid_out[2o] = same_out[2o+1]
             full = ops.conv2d(x, self.weight, self.bias, None, pad=1, stride=1, w_scale=w_scale, **kw)
