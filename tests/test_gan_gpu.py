@@ -208,3 +208,20 @@ def test_gan_training_step_runs_and_updates(V):
         assert torch.isfinite(torch.as_tensor(model.logged[k])).all(), k
     assert not torch.equal(model.decoder.conv_out.weight, w_dec0)
     assert not torch.equal(model.criterion.discriminator.b4.out.weight, w_d0)
+
+
+@pytest.mark.parametrize('ci,co', [(3, 128), (1, 64), (4, 256)])
+def test_pointwise_narrow_input_conv_exact(V, ci, co):
+    """the discriminator's fromrgb layer (1x1, 3 -> 128, bias + lrelu * sqrt(2)) on the dedicated pointwise kernels: forward,
+    weight and bias gradients against float64 torch (no input gradient: the image is a leaf without grad in the D step)."""
+    torch.manual_seed(8)
+    n, h = 2, 64
+    x = torch.randn(n, ci, h, h).double(); wt = (torch.randn(co, ci, 1, 1) / ci ** 0.5).double(); b = torch.randn(co).double()
+    wo, bo = wt.clone().requires_grad_(), b.clone().requires_grad_()
+    y = F.leaky_relu(F.conv2d(x, wo, bo), 0.2) * 1.4142135
+    go = torch.randn_like(y); y.backward(go)
+    xg, wg, bg = cl(x.float()), wt.float().cuda().requires_grad_(), b.float().cuda().requires_grad_()
+    yg = V.ops.conv2d(xg, wg, bg, None, pad=0, act=V.lib.ACT_LRELU, alpha=0.2, gain=1.4142135)
+    yg.backward(cl(go.float()))
+    assert C.rel_err(yg, y) < 1e-5
+    assert C.rel_err(wg.grad, wo.grad) < 1e-5 and C.rel_err(bg.grad, bo.grad) < 1e-5

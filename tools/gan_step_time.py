@@ -36,3 +36,17 @@ print(f'{a.conf} B={bs} {a.precision} r1={a.r1}: {ms:.1f} ms/step = {bs / ms * 1
       f'peak mem {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB; launches/step {len(pkg.lib.timer.records) // a.steps}')
 for k, (n, t_) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:14]:
     print(f'{t_ / a.steps:9.2f} ms {n // a.steps:5d} calls  {k}')
+# fp32 SIMT convolutions still on the path (impl 0): shape and time per call
+seen = {}
+for name, args, s, e in pkg.lib.timer.records:
+    if name == 'vqb_conv2d_fwd' and args[0] == 0:
+        key = ('fwd', args[9:17])            # N, H, W, Ci, Co, KH, KW, pad  (+ stride at 17)
+    elif name == 'vqb_conv2d_wgrad' and args[0] == 0:
+        key = ('wgrad', args[7:15])
+    elif name == 'vqb_conv2d_dgrad':
+        key = ('dgrad', args[5:14])
+    else:
+        continue
+    d = seen.setdefault(key, [0, 0.0]); d[0] += 1; d[1] += s.elapsed_time(e)
+for k, (n, t_) in sorted(seen.items(), key=lambda kv: -kv[1][1]):
+    print(f'{t_ / a.steps:8.2f} ms {n // a.steps:3d} calls  {k}')

@@ -475,6 +475,98 @@ conv_wgrad_narrow_ci_kernel(const TIn* __restrict__ x, const TG* __restrict__ dy
     }
 }
 
+// ---- pointwise (1x1) convolution with a narrow input (Ci <= 4): the discriminator's fromrgb layer 3 -> 128 at full
+// resolution.  HBM-bound (write y once / read dy once): threadIdx.x owns 8 consecutive output channels (its Ci x 8 weights
+// live in registers), threadIdx.y / blockIdx.x stride over pixels; 16-byte stores / loads along channels.
+template <typename T> __device__ __forceinline__ void pw_store8(T* p, const float* v);
+template <> __device__ __forceinline__ void pw_store8<float>(float* p, const float* v) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <> __device__ __forceinline__ void pw_store8<bf16>(bf16* p, const float* v) {
+    uint4 u;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = u;
+}
+template <typename T> __device__ __forceinline__ void pw_load8(const T* p, float* v);
+template <> __device__ __forceinline__ void pw_load8<float>(const float* p, float* v) {
+    float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <> __device__ __forceinline__ void pw_load8<bf16>(const bf16* p, float* v) {
+    uint4 u = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+
+template <typename TIn, typename TOut>
+__global__ void pw_narrow_ci_fwd_kernel(const TIn* __restrict__ x, const float* __restrict__ wp, const float* __restrict__ bias,
+                                        TOut* __restrict__ y, int64_t P, int Ci, int Co, int act, float alpha, float gain) {
+    const int c0 = threadIdx.x * 8;
+    float wr[4][8], bv[8];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int u = 0; u < 8; ++u) wr[c][u] = (c < Ci) ? wp[(int64_t)c * Co + c0 + u] : 0.f;      // wp = [(ci)][co]
+#pragma unroll
+    for (int u = 0; u < 8; ++u) bv[u] = bias ? bias[c0 + u] : 0.f;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; p < P; p += (int64_t)gridDim.x * blockDim.y) {
+        float xv[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) if (c < Ci) xv[c] = ld1(x + p * Ci + c);
+        float o[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            float t = bv[u];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) t = fmaf(xv[c], wr[c][u], t);
+            o[u] = apply_act(t, act, alpha) * gain;
+        }
+        pw_store8<TOut>(y + p * Co + c0, o);
+    }
+}
+
+// dwp[(ci)][co] += sum_p x[p][ci] * dy[p][co]
+template <typename TIn, typename TG>
+__global__ void pw_narrow_ci_wgrad_kernel(const TIn* __restrict__ x, const TG* __restrict__ dy, float* __restrict__ dwp, int64_t P,
+                                          int Ci, int Co, int rows_per_block) {
+    extern __shared__ float shw[];                               // [ty][4][Co]
+    const int c0 = threadIdx.x * 8;
+    float acc[4][8];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc[c][u] = 0.f;
+    const int64_t p0 = (int64_t)blockIdx.x * rows_per_block;
+    int64_t p1 = p0 + rows_per_block; if (p1 > P) p1 = P;
+#pragma unroll 4
+    for (int64_t p = p0 + threadIdx.y; p < p1; p += blockDim.y) {
+        float g[8], xv[4] = {0.f, 0.f, 0.f, 0.f};
+        pw_load8<TG>(dy + p * Co + c0, g);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) if (c < Ci) xv[c] = ld1(x + p * Ci + c);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc[c][u] = fmaf(xv[c], g[u], acc[c][u]);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int u = 0; u < 8; ++u) shw[((size_t)threadIdx.y * 4 + c) * Co + c0 + u] = acc[c][u];
+    __syncthreads();
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    for (int i = tid; i < Ci * Co; i += blockDim.x * blockDim.y) {
+        const int c = i / Co, co = i - c * Co;
+        float t = 0.f;
+        for (int yy = 0; yy < (int)blockDim.y; ++yy) t += shw[((size_t)yy * 4 + c) * Co + co];
+        atomicAdd(dwp + (int64_t)c * Co + co, t);
+    }
+}
+
 inline int make_geom(ConvGeom& g, int N, int H, int W, int Ci, int Co, int KH, int KW, int pad, int stride) {
     if (!(N > 0 && H > 0 && W > 0 && Ci > 0 && Co > 0 && KH > 0 && KW > 0 && pad >= 0 && stride >= 1)) {
         vqb_set_error("conv2d: bad geometry N=%d H=%d W=%d Ci=%d Co=%d KH=%d KW=%d pad=%d stride=%d", N, H, W, Ci, Co, KH, KW, pad, stride);
@@ -504,6 +596,16 @@ int vqb_conv2d_fwd_simt(const void* x, int x_dtype, const float* wp, const float
         VQB_DISPATCH_1(x_dtype, TIn, VQB_DISPATCH_1(y_dtype, TOut,
             (conv_fwd_narrow_ci_kernel<TIn, TOut><<<ngrid, 128, sm, stream>>>((const TIn*)x, wp, bias, (TOut*)y, N, H, W, Ci, Co));))
         VQB_CHECK_LAUNCH("conv2d_fwd_narrow_ci");
+        return VQB_OK;
+    }
+    if (Ci <= 4 && KH == 1 && KW == 1 && pad == 0 && stride == 1 && !residual && Co % 8 == 0 && Co / 8 <= 256 &&
+        (int64_t)N * H * W >= 4096) {
+        const int tx = Co / 8, ty = 256 / tx > 0 ? 256 / tx : 1;
+        const int64_t P = (int64_t)N * H * W;
+        int64_t blocks = ceil_div64(P, ty); if (blocks > 148 * 16) blocks = 148 * 16;
+        VQB_DISPATCH_1(x_dtype, TIn, VQB_DISPATCH_1(y_dtype, TOut,
+            (pw_narrow_ci_fwd_kernel<TIn, TOut><<<(unsigned)blocks, dim3(tx, ty), 0, stream>>>((const TIn*)x, wp, bias, (TOut*)y, P, Ci, Co, act, alpha, gain));))
+        VQB_CHECK_LAUNCH("conv2d_fwd_pw_narrow_ci");
         return VQB_OK;
     }
     dim3 grid((unsigned)ceil_div64(g.M, BM), (unsigned)((Co + BN - 1) / BN));
@@ -551,6 +653,17 @@ int vqb_conv2d_wgrad_simt(const void* x, int x_dtype, const void* dy, int dy_dty
         VQB_DISPATCH_1(x_dtype, TIn, VQB_DISPATCH_1(dy_dtype, TG,
             (conv_wgrad_narrow_ci_kernel<TIn, TG><<<grid, 128, sm, stream>>>((const TIn*)x, (const TG*)dy, dwp, N, H, W, Ci, Co));))
         VQB_CHECK_LAUNCH("conv2d_wgrad_narrow_ci");
+        return VQB_OK;
+    }
+    if (Ci <= 4 && KH == 1 && KW == 1 && pad == 0 && stride == 1 && Co % 8 == 0 && Co / 8 <= 256 && (int64_t)N * H * W >= 4096) {
+        const int tx = Co / 8, ty = 256 / tx > 0 ? 256 / tx : 1;
+        const int64_t P = (int64_t)N * H * W;
+        int rows = (int)ceil_div64(P, (int64_t)148 * 8); if (rows < ty * 16) rows = ty * 16;
+        const unsigned blocks = (unsigned)ceil_div64(P, rows);
+        const size_t sm = sizeof(float) * ty * 4 * Co;
+        VQB_DISPATCH_1(x_dtype, TIn, VQB_DISPATCH_1(dy_dtype, TG,
+            (pw_narrow_ci_wgrad_kernel<TIn, TG><<<blocks, dim3(tx, ty), sm, stream>>>((const TIn*)x, (const TG*)dy, dwp, P, Ci, Co, rows));))
+        VQB_CHECK_LAUNCH("conv2d_wgrad_pw_narrow_ci");
         return VQB_OK;
     }
     int gm = (g.K + BM - 1) / BM, gn = (Co + BN - 1) / BN;

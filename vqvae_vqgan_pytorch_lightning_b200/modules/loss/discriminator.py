@@ -78,6 +78,15 @@ class Conv2dLayer(nn.Module):
         else:
             raise NotImplementedError(self.activation)
         if self.down == 1:
+            co, ci = self.weight.shape[0], self.weight.shape[1]
+            if ops.get_precision().name == 'fast' and ci > 64 and ci % 64 != 0 and co % 128 == 0 and x.shape[1] == ci:
+                # the epilogue's 513 -> 512 conv (512 + the minibatch-stddev channel): zero-pad the input channels to the next
+                # multiple of 64 so that forward, dgrad and wgrad ride the tensor cores (tiny tensors: N x 576 x 4 x 4 and a
+                # 10 MB weight copy; the padding ops are layout plumbing and autograd slices the gradients back)
+                cpad = (ci + 63) // 64 * 64 - ci
+                xp = torch.nn.functional.pad(x, (0, 0, 0, 0, 0, cpad)).contiguous(memory_format=torch.channels_last)
+                wp = torch.nn.functional.pad(self.weight, (0, 0, 0, 0, 0, cpad))
+                return ops.conv2d(xp, wp, self.bias, residual, pad=self.padding, w_scale=w_scale, **kw)
             return ops.conv2d(x, self.weight, self.bias, residual, pad=self.padding, w_scale=w_scale, **kw)
         if self.down != 2:
             raise NotImplementedError('down must be 1 or 2')

@@ -143,13 +143,13 @@ def _conv_fwd_raw(impl: int, x: torch.Tensor, wp: torch.Tensor, bias, residual, 
     return y
 
 
-def _narrow_route(prec: Precision, ci: int, co: int, kh: int, kw: int, pad: int, stride: int) -> Optional[str]:
+def _narrow_route(prec: Precision, ci: int, co: int, kh: int, kw: int, pad: int, stride: int, frozen: bool = False) -> Optional[str]:
     """fast mode: the RGB heads (3x3, pad 1) ride the tensor cores as a 64-channel 1x1 implicit GEMM over an im2col tensor
     ('in': narrow input, e.g. encoder.conv_in 3->128; 'out': narrow output, e.g. decoder.conv_out 128->3, whose dgrad and
     wgrad are narrow-INPUT problems on dy)."""
     if prec.name != 'fast' or (kh, kw, pad, stride) != (3, 3, 1, 1):
         return None
-    if ci <= 7 and co % 128 == 0:
+    if ci <= 7 and (co % 128 == 0 or (frozen and co % 64 == 0)):       # the tcgen05 wgrad needs 128-wide Co tiles
         return 'in'
     if co <= 7 and ci % 128 == 0:
         return 'out'
@@ -218,7 +218,7 @@ class Conv2dFn(torch.autograd.Function):
                 raise lib.VQBError('conv2d: a fused residual cannot be combined with an activation epilogue')
             residual = as_nhwc(residual, out_dtype)
         b = bias.detach().reshape(-1).float().contiguous() if bias is not None else None
-        route = _narrow_route(prec, ci, co, kh, kw, pad, stride)
+        route = _narrow_route(prec, ci, co, kh, kw, pad, stride, frozen=not weight.requires_grad)
         if route == 'in':
             wp = _packed_weight(weight, 4, torch.bfloat16, w_scale)                  # [co][64], K zero-padded
             y = _conv_fwd_raw(1, _im2col64(x), wp, b, residual, out_dtype, 64, co, 1, 1, 0, 1, act, alpha, gain)
@@ -253,7 +253,7 @@ class Conv2dFn(torch.autograd.Function):
             raise lib.VQBError('gain != 1 requires an activation epilogue')
         _, _, oh, ow = dy.shape
         dx = dw = db = None
-        route = _narrow_route(prec, ci, co, kh, kw, pad, stride)
+        route = _narrow_route(prec, ci, co, kh, kw, pad, stride, frozen=not weight.requires_grad)
         if route is not None and torch.is_grad_enabled():
             raise lib.VQBError('conv2d: the RGB-head im2col routes are not twice differentiable')
         if route == 'in' and ctx.needs_input_grad[1] and not ctx.needs_input_grad[0]:
