@@ -100,6 +100,76 @@ __global__ void fir4_bwd_vec_kernel(const T* __restrict__ dy, T* __restrict__ dx
     }
 }
 
+// Separable, register-tiled form: one thread produces a 2 x 2 patch of outputs for V channels.  The DOWN + 4 input rows the
+// patch needs are streamed one at a time: DOWN + 4 vector loads per row, two horizontal 4-tap sums, then the vertical taps
+// accumulate them into the two output rows -- (DOWN+4)^2 loads per 4 outputs (6.25 / 9 per output instead of 16) and one
+// pass of FMAs less.  y[o] = sum_a f[a] x[o*DOWN - pad + a] per axis, zero outside the input; OH / OW are free parameters, so
+// the adjoint of the down = 1 filter is this kernel too (symmetric taps): dx = FIR(dy, pad' = 3 - pad) with OH = H.
+template <typename T, int DOWN>
+__global__ void fir4_patch_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int OH, int OW, int pad) {
+    constexpr int V = Vec<T>::N, R = DOWN + 4;
+    const int Cv = C / V, PH = (OH + 1) / 2, PW = (OW + 1) / 2;
+    const int64_t total = (int64_t)N * PH * PW * Cv;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int cv = (int)(i % Cv); int64_t r_ = i / Cv; int pw = (int)(r_ % PW); r_ /= PW; int ph = (int)(r_ % PH); int n = (int)(r_ / PH);
+        const int oh0 = 2 * ph, ow0 = 2 * pw;
+        const int ih0 = oh0 * DOWN - pad, iw0 = ow0 * DOWN - pad;
+        float acc[2][2][V];
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b)
+#pragma unroll
+                for (int u = 0; u < V; ++u) acc[a][b][u] = 0.f;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int ih = ih0 + r;
+            if (ih < 0 || ih >= H) continue;
+            float v[R][V];
+#pragma unroll
+            for (int c = 0; c < R; ++c) {
+                const int iw = iw0 + c;
+                if (iw >= 0 && iw < W) ldvec<T>(x + (((int64_t)n * H + ih) * W + iw) * C + cv * V, v[c]);
+                else {
+#pragma unroll
+                    for (int u = 0; u < V; ++u) v[c][u] = 0.f;
+                }
+            }
+            float h0[V], h1[V];
+#pragma unroll
+            for (int u = 0; u < V; ++u) {
+                h0[u] = fmaf(0.375f, v[1][u] + v[2][u], 0.125f * (v[0][u] + v[3][u]));
+                h1[u] = fmaf(0.375f, v[DOWN + 1][u] + v[DOWN + 2][u], 0.125f * (v[DOWN][u] + v[DOWN + 3][u]));
+            }
+            if (r <= 3) {                                         // output row oh0: vertical tap a = r
+                const float f = tap(r);
+#pragma unroll
+                for (int u = 0; u < V; ++u) { acc[0][0][u] = fmaf(f, h0[u], acc[0][0][u]); acc[0][1][u] = fmaf(f, h1[u], acc[0][1][u]); }
+            }
+            if (r >= DOWN) {                                      // output row oh0 + 1: vertical tap a = r - DOWN
+                const float f = tap(r - DOWN);
+#pragma unroll
+                for (int u = 0; u < V; ++u) { acc[1][0][u] = fmaf(f, h0[u], acc[1][0][u]); acc[1][1][u] = fmaf(f, h1[u], acc[1][1][u]); }
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b)
+                if (oh0 + a < OH && ow0 + b < OW) stvec<T>(y + (((int64_t)n * OH + oh0 + a) * OW + ow0 + b) * C + cv * V, acc[a][b]);
+    }
+}
+
+template <typename T>
+int launch_fir4_patch(const void* x, void* y, int N, int H, int W, int C, int OH, int OW, int pad, int down, cudaStream_t st) {
+    const int64_t total = (int64_t)N * ((OH + 1) / 2) * ((OW + 1) / 2) * (C / Vec<T>::N);
+    int64_t blocks = (total + 255) / 256; if (blocks > 148 * 32) blocks = 148 * 32; if (blocks < 1) blocks = 1;
+    const unsigned grid = (unsigned)blocks;
+    if (down == 1) fir4_patch_kernel<T, 1><<<grid, 256, 0, st>>>((const T*)x, (T*)y, N, H, W, C, OH, OW, pad);
+    else fir4_patch_kernel<T, 2><<<grid, 256, 0, st>>>((const T*)x, (T*)y, N, H, W, C, OH, OW, pad);
+    return 0;
+}
+
 // y[n,oh,ow,:] = x[n, 2*oh+off, 2*ow+off, :]
 template <typename T>
 __global__ void decimate2_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int OH, int OW, int off) {
@@ -138,12 +208,27 @@ inline int ew_grid(int64_t n) { int64_t b = (n + 255) / 256; if (b > 148 * 32) b
 
 // vectorised entry points used by vqb_fir4_fwd / vqb_fir4_bwd when C is a multiple of the vector width
 int vqb_fir4_fwd_vec(const void* x, void* y, int dtype, int N, int H, int W, int C, int OH, int OW, int pad, int down, cudaStream_t st) {
+    static const int use_patch = getenv("VQB_FIR_PATCH") ? atoi(getenv("VQB_FIR_PATCH")) : 1;
+    if (use_patch && (down == 1 || down == 2)) {
+        if (dtype == VQB_BF16) launch_fir4_patch<bf16>(x, y, N, H, W, C, OH, OW, pad, down, st);
+        else launch_fir4_patch<float>(x, y, N, H, W, C, OH, OW, pad, down, st);
+        VQB_CHECK_LAUNCH("fir4_patch");
+        return VQB_OK;
+    }
     if (dtype == VQB_BF16) fir4_fwd_vec_kernel<bf16><<<ew_grid((int64_t)N * OH * OW * C / 8), 256, 0, st>>>((const bf16*)x, (bf16*)y, N, H, W, C, OH, OW, pad, down);
     else fir4_fwd_vec_kernel<float><<<ew_grid((int64_t)N * OH * OW * C / 4), 256, 0, st>>>((const float*)x, (float*)y, N, H, W, C, OH, OW, pad, down);
     VQB_CHECK_LAUNCH("fir4_fwd_vec");
     return VQB_OK;
 }
 int vqb_fir4_bwd_vec(const void* dy, void* dx, int dtype, int N, int H, int W, int C, int OH, int OW, int pad, int down, cudaStream_t st) {
+    static const int use_patch = getenv("VQB_FIR_PATCH") ? atoi(getenv("VQB_FIR_PATCH")) : 1;
+    if (use_patch && down == 1 && pad <= 3) {
+        // adjoint of the symmetric down = 1 filter = the same filter with pad' = 3 - pad, applied to dy [OH, OW] -> dx [H, W]
+        if (dtype == VQB_BF16) launch_fir4_patch<bf16>(dy, dx, N, OH, OW, C, H, W, 3 - pad, 1, st);
+        else launch_fir4_patch<float>(dy, dx, N, OH, OW, C, H, W, 3 - pad, 1, st);
+        VQB_CHECK_LAUNCH("fir4_patch(adjoint)");
+        return VQB_OK;
+    }
     if (dtype == VQB_BF16) fir4_bwd_vec_kernel<bf16><<<ew_grid((int64_t)N * H * W * C / 8), 256, 0, st>>>((const bf16*)dy, (bf16*)dx, N, H, W, C, OH, OW, pad, down);
     else fir4_bwd_vec_kernel<float><<<ew_grid((int64_t)N * H * W * C / 4), 256, 0, st>>>((const float*)dy, (float*)dx, N, H, W, C, OH, OW, pad, down);
     VQB_CHECK_LAUNCH("fir4_bwd_vec");

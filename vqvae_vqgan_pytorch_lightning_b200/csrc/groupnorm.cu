@@ -656,7 +656,7 @@ extern "C" int vqb_gn_stats(const void* x, int x_dtype, double* sums, int N, int
     VQB_CHECK_ARG(x && sums, "gn_stats: null pointer");
     static int use_async = getenv("VQB_GN_ASYNC") ? atoi(getenv("VQB_GN_ASYNC")) : 1;
     if (use_async && x_dtype == VQB_BF16 && gn_vec(C, G) == 8) {
-        static int ppt = getenv("VQB_GN_SPPT") ? atoi(getenv("VQB_GN_SPPT")) : 128;
+        const int ppt = 128;                          // pixels per thread (tools/gn_probe.py sweep)
         GnLaunch La = gn_launch(N, HW, C, G, ppt, 8);
         const size_t nthr = (size_t)La.block.x * La.block.y;
         size_t ring = (size_t)8 * nthr * 16, red = 2 * sizeof(double) * nthr * 2;
@@ -689,7 +689,7 @@ extern "C" int vqb_gn_apply(const void* x, int x_dtype, const float* stats, cons
     VQB_CHECK_ARG(act == VQB_ACT_NONE || act == VQB_ACT_SILU, "gn_apply: act must be NONE or SILU");
     static int use_async = getenv("VQB_GN_ASYNC") ? atoi(getenv("VQB_GN_ASYNC")) : 1;
     if (use_async && x_dtype == VQB_BF16 && y_dtype == VQB_BF16 && gn_vec(C, G) == 8) {
-        static int ppt = getenv("VQB_GN_APPT") ? atoi(getenv("VQB_GN_APPT")) : 32;
+        const int ppt = 32;
         GnLaunch La = gn_launch(N, HW, C, G, ppt, 8);
         const size_t nthr = (size_t)La.block.x * La.block.y;
         gn_apply_async_kernel<8><<<La.grid, La.block, (size_t)8 * nthr * 16, as_stream(stream)>>>((const bf16*)x, stats, gamma, beta, (bf16*)y, HW, C, G, La.ppb, act);
@@ -710,41 +710,26 @@ extern "C" int vqb_gn_bwd_reduce(const void* x, int x_dtype, const void* dy, int
     VQB_CHECK_ARG(x && dy && stats && gamma && beta && part, "gn_bwd_reduce: null pointer");
     static int use_async = getenv("VQB_GN_ASYNC") ? atoi(getenv("VQB_GN_ASYNC")) : 1;
     if (use_async && x_dtype == VQB_BF16 && dy_dtype == VQB_BF16 && gn_vec(C, G) == 8 && (act == VQB_ACT_NONE || act == VQB_ACT_SILU)) {
-        static int ppt = getenv("VQB_GN_RPPT") ? atoi(getenv("VQB_GN_RPPT")) : 128;
+        const int ppt = 128;
         GnLaunch L = gn_launch(N, HW, C, G, ppt, 8);
         const size_t nthr = (size_t)L.block.x * L.block.y;
-        static int depth = getenv("VQB_GN_DEPTH") ? atoi(getenv("VQB_GN_DEPTH")) : GN_ASYNC_DEPTH;
+        const int depth = GN_ASYNC_DEPTH;
         size_t ring = (size_t)depth * 2 * nthr * 16, red = 2 * sizeof(double) * nthr * 8;
         size_t sm = ring > red ? ring : red;
         static bool attr_set = false;
         if (!attr_set) {
-            VQB_CUDA(cudaFuncSetAttribute(gn_bwd_reduce_async_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-            VQB_CUDA(cudaFuncSetAttribute(gn_bwd_reduce_async_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-            VQB_CUDA(cudaFuncSetAttribute(gn_bwd_reduce_async_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-            VQB_CUDA(cudaFuncSetAttribute(gn_bwd_reduce_async_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            VQB_CUDA(cudaFuncSetAttribute(gn_bwd_reduce_async_kernel<GN_ASYNC_DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
             attr_set = true;
         }
-#define GN_RED_ASYNC(DD) gn_bwd_reduce_async_kernel<DD><<<L.grid, L.block, sm, as_stream(stream)>>>((const bf16*)x, (const bf16*)dy, stats, gamma, beta, part, HW, C, G, L.ppb, act)
-        if (depth == 4) GN_RED_ASYNC(4); else if (depth == 8) GN_RED_ASYNC(8); else if (depth == 12) GN_RED_ASYNC(12); else GN_RED_ASYNC(6);
-#undef GN_RED_ASYNC
+        gn_bwd_reduce_async_kernel<GN_ASYNC_DEPTH><<<L.grid, L.block, sm, as_stream(stream)>>>((const bf16*)x, (const bf16*)dy, stats, gamma, beta,
+                                                                                             part, HW, C, G, L.ppb, act);
         VQB_CHECK_LAUNCH("gn_bwd_reduce_async");
         return VQB_OK;
     }
-    static int exp_vec = getenv("VQB_GN_RVEC") ? atoi(getenv("VQB_GN_RVEC")) : 8;
-    static int exp_unr = getenv("VQB_GN_RUNR") ? atoi(getenv("VQB_GN_RUNR")) : 4;
-    static int exp_ppt = getenv("VQB_GN_RPPT") ? atoi(getenv("VQB_GN_RPPT")) : 128;
-    GnLaunch L = gn_launch(N, HW, C, G, exp_ppt, exp_vec);
+    GnLaunch L = gn_launch(N, HW, C, G, 128, 8);
     size_t sm = 2 * sizeof(double) * L.block.x * L.block.y * L.vec;
-    if (exp_unr == 2) {
-    GN_VEC_DISPATCH(L, VQB_DISPATCH_1(x_dtype, TI, VQB_DISPATCH_1(dy_dtype, TG,
-        (gn_bwd_reduce_kernel<TI, TG, VEC, 2><<<L.grid, L.block, sm, as_stream(stream)>>>((const TI*)x, (const TG*)dy, stats, gamma, beta, part, HW, C, G, L.ppb, act));)))
-    } else if (exp_unr == 8) {
-    GN_VEC_DISPATCH(L, VQB_DISPATCH_1(x_dtype, TI, VQB_DISPATCH_1(dy_dtype, TG,
-        (gn_bwd_reduce_kernel<TI, TG, VEC, 8><<<L.grid, L.block, sm, as_stream(stream)>>>((const TI*)x, (const TG*)dy, stats, gamma, beta, part, HW, C, G, L.ppb, act));)))
-    } else {
     GN_VEC_DISPATCH(L, VQB_DISPATCH_1(x_dtype, TI, VQB_DISPATCH_1(dy_dtype, TG,
         (gn_bwd_reduce_kernel<TI, TG, VEC, 4><<<L.grid, L.block, sm, as_stream(stream)>>>((const TI*)x, (const TG*)dy, stats, gamma, beta, part, HW, C, G, L.ppb, act));)))
-    }
     VQB_CHECK_LAUNCH("gn_bwd_reduce");
     return VQB_OK;
 }
@@ -768,7 +753,7 @@ extern "C" int vqb_gn_bwd_apply(const void* x, int x_dtype, const void* dy, int 
     static int use_async = getenv("VQB_GN_ASYNC") ? atoi(getenv("VQB_GN_ASYNC")) : 1;
     if (use_async && x_dtype == VQB_BF16 && dy_dtype == VQB_BF16 && dx_dtype == VQB_BF16 && gn_vec(C, G) == 8 &&
         (act == VQB_ACT_NONE || act == VQB_ACT_SILU)) {
-        static int ppt = getenv("VQB_GN_BPPT") ? atoi(getenv("VQB_GN_BPPT")) : 16;
+        const int ppt = 16;
         GnLaunch La = gn_launch(N, HW, C, G, ppt, 8);
         const size_t nthr = (size_t)La.block.x * La.block.y;
         constexpr int DB = 6;
