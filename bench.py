@@ -157,7 +157,7 @@ def cpu_reference_step(batch: int, image_size: int, codebook: int, steps: int, w
     return batch / sec, sec
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, out=sys.stdout):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
@@ -174,7 +174,7 @@ def run_reference(args, rank, world):
         'e2e': {'value': ips, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line), flush=True)
+    out.write(json.dumps(line) + '\n'); out.flush()
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -199,13 +199,17 @@ def main():
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     t_start = time.time()
+    # stdout carries exactly ONE JSON line: everything libraries print to fd 1 (NCCL's version banner, ...) goes to stderr
+    sys.stdout.flush()
+    out = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
 
     def stamp(what):                              # progress on stderr (the JSON line is the only thing on stdout)
         if os.environ.get('VQB_BENCH_VERBOSE'):
             print(f'[bench rank {rank} +{time.time() - t_start:6.1f}s] {what}', file=sys.stderr, flush=True)
 
     if args.impl == 'reference':
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, out)
         return
 
     if not torch.cuda.is_available():
@@ -214,7 +218,6 @@ def main():
     dev = torch.device('cuda', local_rank)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')       # keep NCCL's version banner off stdout (one JSON line only)
         dist.init_process_group('nccl', device_id=dev)
 
     stamp('process group up')
@@ -336,7 +339,7 @@ def main():
             line['cpu_baseline'] = {'value': ips, 'unit': UNIT, 'cores': threads, 'kind': 'port',
                                     'sample': f'{args.cpu_steps} steps x {args.cpu_batch} images ({sec:.1f} s/step), oracle port of the '
                                               f'reference modules, fp32 torch CPU'}
-        print(json.dumps(line), flush=True)
+        out.write(json.dumps(line) + '\n'); out.flush()
     if world > 1:
         dist.destroy_process_group()
 
