@@ -316,7 +316,12 @@ def main():
         achieved = conv_fl / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
         peak = pk['bf16_tflops_sustained']
         roofline = {'bound': 'tensor', 'kernel': 'implicit-GEMM conv (fwd+dgrad+wgrad launches)', 'achieved': achieved, 'peak': peak,
-                    'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': None, 'peak_source': f'{pk_kind} (sustained bf16)',
+                    'unit': 'TFLOP/s', 'frac': achieved / peak,
+                    # DRAM bytes of ONE launch of the largest layer (128->128 3x3 @256^2, B=64; algorithmic 2.147e9 B = x + y) from the
+                    # committed `ncu --set full` capture -- not measured live (a profiler cannot run inside the timed region)
+                    'traffic': 2.114e9 if (image_size, bs) == (256, 64) else None,
+                    'traffic_source': 'profiles/r01_ncu_full_top_kernels.txt: conv_fwd_tc_halo_t_kernel launch 0, dram read 1.084 GB + write 1.030 GB',
+                    'peak_source': f'{pk_kind} (sustained bf16)',
                     'launches_timed': conv_calls, 'share_of_step': conv_ms / ms, 'flop_per_step': conv_fl / args.steps}
         vq_roof = vq_microbench(pkg, dev, bs * (image_size // 16) ** 2, args.codebook, precision == 'fast', pk['hbm_gbs'])
         vq_step = ksum.get('vqb_vq_assign_tc') or ksum.get('vqb_vq_assign')
