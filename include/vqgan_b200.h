@@ -74,8 +74,10 @@ int vqb_pack_conv_weight(const float* w, void* wp, int out_dtype, int mode, int 
                          float scale, void* stream);
 /* Narrow-input 3x3 / pad-1 convolutions (the RGB heads: encoder.conv_in 3->128, and everything that touches the 3-channel
  * side of decoder.conv_out) run on tensor cores as a 64-channel 1x1 implicit GEMM over this im2col tensor:
- * P[n,h,w,j] = x[n,h+kh-1,w+kw-1,c] for j = (kh*3+kw)*C+c < 9*C, zero otherwise (C <= 7). */
-int vqb_im2col3x3_narrow(const void* x, int x_dtype, void* P, int p_dtype, int N, int H, int W, int C, void* stream);
+ * P[n,h,w,j] = x[n,h+kh-1,w+kw-1,c] for j = (kh*3+kw)*C+c < 9*C, zero otherwise (C <= 7).  write_all = 0 writes only the
+ * first ceil(9C/8)*8 columns: for a P buffer whose remaining columns the caller keeps at zero across calls. */
+int vqb_im2col3x3_narrow(const void* x, int x_dtype, void* P, int p_dtype, int N, int H, int W, int C, int write_all,
+                         void* stream);
 /* inverse of mode 0 for gradients: dw[co][ci][kh][kw] = scale * dwp[(kh*KW+kw)*Ci+ci][co] */
 int vqb_unpack_conv_wgrad(const float* dwp, float* dw, int Co, int Ci, int KH, int KW, float scale, void* stream);
 

@@ -229,11 +229,11 @@ __device__ __forceinline__ void st16(T* p, const float* v) {
 
 // P[n,h,w, j] (64 channels, TO) = x[n, h+kh-1, w+kw-1, c] for j = (kh*3+kw)*C + c < 9*C, else 0   (3x3, pad 1, C <= 7)
 template <typename TI, typename TO, int CT>
-__global__ void im2col3x3_narrow_kernel(const TI* __restrict__ x, TO* __restrict__ P, int N, int H, int W, int Crt) {
+__global__ void im2col3x3_narrow_kernel(const TI* __restrict__ x, TO* __restrict__ P, int N, int H, int W, int Crt, int G) {
     const int C = (CT > 0) ? CT : Crt;                        // compile-time channel count (3 = RGB) avoids runtime div/mod
-    const int64_t total = (int64_t)N * H * W * 8;            // one thread per (pixel, group of 8 output columns)
+    const int64_t total = (int64_t)N * H * W * G;            // one thread per (pixel, group of 8 output columns); G groups written
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        int grp = (int)(i & 7); int64_t pix = i >> 3;
+        int grp = (int)(i % G); int64_t pix = i / G;
         int w = (int)(pix % W); int64_t r = pix / W; int h = (int)(r % H); int n = (int)(r / H);
         float v[8];
 #pragma unroll
@@ -257,15 +257,17 @@ __global__ void im2col3x3_narrow_kernel(const TI* __restrict__ x, TO* __restrict
     }
 }
 
-extern "C" int vqb_im2col3x3_narrow(const void* x, int x_dtype, void* P, int p_dtype, int N, int H, int W, int C, void* stream) {
+extern "C" int vqb_im2col3x3_narrow(const void* x, int x_dtype, void* P, int p_dtype, int N, int H, int W, int C, int write_all,
+                                    void* stream) {
     VQB_CHECK_ARG(x && P && N > 0 && H > 0 && W > 0 && C > 0 && 9 * C <= 64, "im2col3x3_narrow: bad arguments (need 9*C <= 64)");
-    int g = grid_for((int64_t)N * H * W * 8, 256);
+    const int G = write_all ? 8 : (9 * C + 7) / 8;
+    int g = grid_for((int64_t)N * H * W * G, 256);
     if (C == 3) {
         VQB_DISPATCH_1(x_dtype, TI, VQB_DISPATCH_1(p_dtype, TO, (im2col3x3_narrow_kernel<TI, TO, 3><<<g, 256, 0, as_stream(stream)>>>(
-                                                                    (const TI*)x, (TO*)P, N, H, W, C));))
+                                                                    (const TI*)x, (TO*)P, N, H, W, C, G));))
     } else {
         VQB_DISPATCH_1(x_dtype, TI, VQB_DISPATCH_1(p_dtype, TO, (im2col3x3_narrow_kernel<TI, TO, 0><<<g, 256, 0, as_stream(stream)>>>(
-                                                                    (const TI*)x, (TO*)P, N, H, W, C));))
+                                                                    (const TI*)x, (TO*)P, N, H, W, C, G));))
     }
     VQB_CHECK_LAUNCH("im2col3x3_narrow");
     return VQB_OK;

@@ -156,10 +156,22 @@ def _narrow_route(prec: Precision, ci: int, co: int, kh: int, kw: int, pad: int,
     return None
 
 
+_im2col_scratch = {}
+
+
 def _im2col64(x: torch.Tensor) -> torch.Tensor:
+    """64-channel im2col tensor of a narrow (C <= 7) input.  The tensor is consumed by the kernel launched right after it on
+    the same stream and never saved for backward, so ONE zero-initialised scratch buffer per shape is reused and only the
+    first ceil(9C/8)*8 columns are rewritten (the zero padding up to 64 is 58 % of the bytes for RGB)."""
     n, c, h, w = x.shape
-    p = empty_nhwc(n, 64, h, w, torch.bfloat16, x.device)
-    call('vqb_im2col3x3_narrow', ptr(x), dt(x), ptr(p), BF16, n, h, w, c, stream())
+    key = (n, h, w, c, x.device)
+    p = _im2col_scratch.get(key)
+    if p is None:
+        if len(_im2col_scratch) >= 4:
+            _im2col_scratch.clear()
+        p = empty_nhwc(n, 64, h, w, torch.bfloat16, x.device).zero_()
+        _im2col_scratch[key] = p
+    call('vqb_im2col3x3_narrow', ptr(x), dt(x), ptr(p), BF16, n, h, w, c, 0, stream())
     return p
 
 
