@@ -450,6 +450,165 @@ conv_fwd_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 }
 
 // ---------------------------------------------------------------------------------------------------
+// CTA-pair (tcgen05 cta_group::2) halo kernel: M = 256 pixels (128 per CTA of a 2-CTA cluster), N = BN output channels.
+// Each CTA loads the halo tile of ITS pixel tile and HALF of the weight tile (BN/2 rows); the leader's single MMA thread issues
+// M = 256 UMMAs that read both CTAs' shared memory, so each SM feeds 128 x 16 of A and only BN/2 x 16 of B per instruction
+// (ncu on the one-CTA kernels: the SMEM -> tensor operand path, sm__mem_tensor_cycles_active, is 91 % busy at 72 % tensor-pipe
+// activity).  Barrier protocol (tools/probes/umma2_probe.cu): operand bytes of both CTAs complete on the LEADER's full
+// barriers; empty / accumulator-full barriers are arrived by multicast commits in both CTAs; the epilogue warps of both CTAs
+// arrive on the leader's accumulator-empty barrier.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS_FWD, 1)
+conv_fwd_tc_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const FwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int a_stage = p.a_tile_bytes;                             // one halo tile per CTA and stage
+    const int b_stage = (p.BN / 2) * BK * 2;                        // this CTA's half of the weight tile
+    uint8_t* smemA = smem;
+    uint8_t* smemB = smem + (size_t)p.a_stages * a_stage;
+    uint64_t* fullA = reinterpret_cast<uint64_t*>(smemB + (size_t)p.b_stages * b_stage);
+    uint64_t* emptyA = fullA + p.a_stages;
+    uint64_t* fullB = emptyA + p.a_stages;
+    uint64_t* emptyB = fullB + p.b_stages;
+    uint64_t* tfull = emptyB + p.b_stages;           // [2]
+    uint64_t* tempty = tfull + 2;                    // [2] (the leader's are used)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = ptx::cluster_ctarank();
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+    const uint32_t a_box_bytes = (uint32_t)((p.th + 2) * p.pitch * 128);
+    const int ptiles = p.tiles_w * p.tiles_h * p.tiles_n;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmA);
+        ptx::prefetch_tmap(&tmB);
+        for (int i = 0; i < p.a_stages; ++i) { ptx::mbar_init(&fullA[i], 1); ptx::mbar_init(&emptyA[i], 1); }
+        for (int i = 0; i < p.b_stages; ++i) { ptx::mbar_init(&fullB[i], 1); ptx::mbar_init(&emptyB[i], 1); }
+        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull[i], 1); ptx::mbar_init(&tempty[i], 16); }   // 8 epilogue warps x 2 CTAs
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) ptx::tmem_alloc2(tmem_slot, 512);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync();                             // barriers and TMEM of BOTH CTAs exist before any remote signal
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+            for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
+                const int ct = tile % p.co_tiles, pt = tile / p.co_tiles;
+                const int q = pt * 2 + (int)rank;                   // this CTA's pixel tile (may be one past the end)
+                const int twi = q % p.tiles_w, t2 = q / p.tiles_w, thi = t2 % p.tiles_h;
+                const int w0 = twi * p.tw, h0 = thi * p.th, n0 = (q < ptiles) ? t2 / p.tiles_h : p.N;   // n = N: TMA zero-fill
+                const int co0 = ct * p.BN + (int)rank * (p.BN / 2);
+                for (int cc = 0; cc < p.cchunks; ++cc) {
+                    ptx::mbar_wait(&emptyA[sa], pa ^ 1);
+                    if (rank == 0) ptx::mbar_expect_tx(&fullA[sa], 2u * a_box_bytes);
+                    ptx::tma_load_4d_2sm(smemA + (size_t)sa * a_stage, &tmA, ptx::mapa_rank(ptx::smem_u32(&fullA[sa]), 0), cc * BK, w0 - 1,
+                                         h0 - 1, n0);
+                    if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
+                    for (int tap = 0; tap < 9; ++tap) {
+                        ptx::mbar_wait(&emptyB[sb], pb ^ 1);
+                        if (rank == 0) ptx::mbar_expect_tx(&fullB[sb], 2u * (uint32_t)b_stage);
+                        ptx::tma_load_2d_2sm(smemB + (size_t)sb * b_stage, &tmB, ptx::mapa_rank(ptx::smem_u32(&fullB[sb]), 0),
+                                             tap * p.Ci + cc * BK, co0);
+                        if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            const uint32_t idesc = ptx::umma_idesc_bf16(2 * BM, p.BN, 0, 0);
+            const uint32_t sbo = (uint32_t)p.pitch * 128u;
+            int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+            int as = 0; uint32_t aphase = 0;
+            for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
+                ptx::mbar_wait(&tempty[as], aphase ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.BN);
+                for (int cc = 0; cc < p.cchunks; ++cc) {
+                    ptx::mbar_wait(&fullA[sa], pa);
+                    const uint32_t a_addr = ptx::smem_u32(smemA + (size_t)sa * a_stage);
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const int kh = tap / 3, kw = tap - kh * 3;
+                        ptx::mbar_wait(&fullB[sb], pb);
+                        ptx::tc_fence_after();
+                        const uint64_t bdesc = ptx::umma_smem_desc(ptx::smem_u32(smemB + (size_t)sb * b_stage), 0, 1024);
+                        const uint64_t adesc = ptx::umma_smem_desc(a_addr + (uint32_t)(kh * p.pitch + kw) * 128u, 0, sbo);
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k)
+                            ptx::umma2_bf16(d_tmem, adesc + (uint64_t)(k * UMMA_K * 2 / 16), bdesc + (uint64_t)(k * UMMA_K * 2 / 16), idesc,
+                                            (cc | tap | k) != 0 ? 1u : 0u);
+                        ptx::umma2_commit(&emptyB[sb]);
+                        if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
+                    }
+                    ptx::umma2_commit(&emptyA[sa]);
+                    if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
+                }
+                ptx::umma2_commit(&tfull[as]);
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+        }
+    } else {
+        // epilogue: this CTA's 128 pixel rows x BN channels
+        const int quarter = warp & 3, half = (warp - 2) >> 2;
+        const int row = quarter * 32 + lane;
+        const int wi = row % p.tw, hi = row / p.tw;
+        const bool pre = p.residual && !p.y_f32 && p.res_prefetch;
+        const int nch = (p.BN - half * 32 + 63) / 64;
+        int as = 0; uint32_t aphase = 0;
+        for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
+            const int ct = tile % p.co_tiles, pt = tile / p.co_tiles;
+            const int co0 = ct * p.BN;
+            const int q = pt * 2 + (int)rank;
+            const int twi = q % p.tiles_w, t2 = q / p.tiles_w, thi = t2 % p.tiles_h, n = t2 / p.tiles_h;
+            const int w = twi * p.tw + wi, h = thi * p.th + hi;
+            const bool valid = (q < ptiles) && (w < p.W) && (h < p.H) && (n < p.N);
+            const int64_t pix = ((int64_t)n * p.H + h) * p.W + w;
+            auto fetch = [&](int s_, uint4 (&qv)[4]) {
+                if (valid) {
+                    const int c = half * 32 + s_ * 64;
+                    const uint4* ro = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.residual) + pix * p.Co + co0 + c);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) qv[i] = ro[i];
+                }
+            };
+            uint4 qn[4] = {};
+            if (pre) fetch(0, qn);
+            ptx::mbar_wait(&tfull[as], aphase);
+            ptx::tc_fence_after();
+            const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * p.BN);
+            for (int s_ = 0; s_ < nch; ++s_) {
+                const int c = half * 32 + s_ * 64;
+                uint4 qc[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) qc[i] = qn[i];
+                if (pre && s_ + 1 < nch) fetch(s_ + 1, qn);
+                uint32_t r[32];
+                ptx::tmem_ld32(t_addr + (uint32_t)c, r);
+                ptx::tmem_ld_wait();
+                epilogue_chunk(p, r, valid, pix, co0, c, pre ? qc : nullptr);
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa_rank(ptx::smem_u32(&tempty[as]), 0));
+            if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync();                             // the peer may still be reading this CTA's shared memory / TMEM until here
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc2(tmem_base, 512);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // 3x3 forward kernel for Co tiles of 128 with the operand roles swapped: M = 128 output channels (the packed weight tile is
 // the A operand), N = 256 pixels (a 32 x 8 pixel tile; ONE halo box {64 ch, 10, 34} per channel chunk is the B operand of
 // all nine taps).  With N = 128 the UMMA reads 8 KB of shared memory per 64 cycles -- exactly the 128 B/clk SMEM port, so
@@ -918,6 +1077,28 @@ int vqb_conv2d_fwd_tc(const void* x, const void* wp, const float* bias, const vo
     const bool halo = mode != 0 && KH == 3 && KW == 3 && pad == 1 && H >= 16 && W >= 8;
     CUtensorMap tmA, tmB;
     int rc = make_weight_map(&tmB, wp, Co, KH * KW * Ci, p.BN); if (rc) return rc;
+    // VQB_CONV_2CTA: 0 = never, 1 (default) = 256-channel output tiles, 2 = also 128-channel tiles (slower than the swapped-operand
+    // kernel below: with N = 128 a CTA pair still feeds 128 x 16 of A per 64 cycles -- measured 1.08 vs 1.42 PFLOP/s)
+    static const int use_2cta = getenv("VQB_CONV_2CTA") ? atoi(getenv("VQB_CONV_2CTA")) : 1;
+    if (halo && mode == 1 && use_2cta && !p.narrow && (p.BN == 256 || (use_2cta == 2 && p.BN == 128))) {
+        // CTA pairs: 2 x 128 pixels x BN channels per cluster tile (see conv_fwd_tc_halo2_kernel)
+        p.tw = 8; p.th = 16; p.nb = 1; p.MT = 1; p.pitch = 10; p.bo_mode = 0; p.stages = 0;
+        p.tiles_w = (W + 7) / 8; p.tiles_h = (H + 15) / 16; p.tiles_n = N;
+        const int ptiles = p.tiles_w * p.tiles_h * p.tiles_n;
+        p.num_tiles = ((ptiles + 1) / 2) * p.co_tiles;             // cluster tiles
+        p.a_tile_bytes = (((p.th + 2) * p.pitch * 128) + 1023) / 1024 * 1024;
+        const int b_stage = (p.BN / 2) * BK * 2;
+        p.a_stages = 3;
+        p.b_stages = (SMEM_LIMIT - 2048 - p.a_stages * p.a_tile_bytes) / b_stage; if (p.b_stages > 12) p.b_stages = 12;
+        rc = make_weight_map(&tmB, wp, Co, KH * KW * Ci, p.BN / 2); if (rc) return rc;
+        rc = make_act_map(&tmA, x, N, H, W, Ci, p.pitch, p.th + 2, 1); if (rc) return rc;
+        size_t smem = (size_t)p.a_stages * p.a_tile_bytes + (size_t)p.b_stages * b_stage + 1024 + 512;
+        VQB_CUDA(cudaFuncSetAttribute(conv_fwd_tc_halo2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int clusters = p.num_tiles < sm_count() / 2 ? p.num_tiles : sm_count() / 2;
+        conv_fwd_tc_halo2_kernel<<<2 * clusters, NTHREADS_FWD, smem, stream>>>(tmA, tmB, p);
+        VQB_CHECK_LAUNCH("conv2d_fwd_tc_halo2");
+        return VQB_OK;
+    }
     if (halo && mode == 1 && p.BN == 128 && !p.narrow && H >= 32) {
         // Co tiles of 128: swapped operand roles (M = co, N = 256 pixels), see conv_fwd_tc_halo_t_kernel
         p.tw = 8; p.th = 32; p.nb = 1; p.MT = 1; p.pitch = 10; p.bo_mode = 0; p.stages = 0;
