@@ -23,6 +23,18 @@ for ci, co, h in shapes:
         ms = sorted(ts)[len(ts) // 2]
         print(f'{ci:4d}->{co:4d} @{h:3d}^2 {name:9s} {ms * 1e3:8.1f} us  {fl / ms / 1e9:8.1f} TFLOP/s')
 
+# the narrow output head (decoder.conv_out 128 -> 3 + tanh)
+x = torch.randn(B, 128, 256, 256, device='cuda').bfloat16().contiguous(memory_format=cl)
+w = torch.randn(3, 128, 3, 3, device='cuda') * 0.03; b3 = torch.zeros(3, device='cuda')
+ts = []
+with torch.no_grad():
+    for it in range(10):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); y = pkg.ops.conv2d(x, w, b3, None, pad=1, act=pkg.lib.ACT_TANH, out_dtype=torch.float32); e1.record(); torch.cuda.synchronize()
+        if it >= 3: ts.append(e0.elapsed_time(e1))
+ms = sorted(ts)[len(ts) // 2]
+print(f' 128->   3 @256^2 head      {ms * 1e3:8.1f} us  {x.numel() * 2 / ms / 1e9:8.2f} TB/s of x')
+
 # weight gradients of the same shapes
 for ci, co, h in shapes:
     x = torch.randn(B, ci, h, h, device='cuda').bfloat16().contiguous(memory_format=cl).requires_grad_(False)
