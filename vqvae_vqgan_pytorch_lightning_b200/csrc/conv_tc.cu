@@ -1,20 +1,21 @@
 // tcgen05 / TMA implicit-GEMM convolution for sm_100a (bf16 operands, fp32 accumulation in TMEM).
 //
-// Forward / dgrad, two kernels sharing one epilogue:
-//   conv_fwd_tc_kernel       generic (any KHxKW 'same' conv, any spatial size): per (tap, 64-channel chunk) one 4-D TMA box
-//                            {64 ch, tw, th, nb} of the NHWC activation at offset (kh-pad, kw-pad) is a K-major
-//                            SWIZZLE_128B A tile; out-of-image elements are zero-filled by TMA (= the conv padding).
-//   conv_fwd_tc_halo_kernel  3x3 convs on >= 16x8 images: ONE halo box {64 ch, 10, 18} per channel chunk serves all nine
-//                            taps -- the A operand of tap (kh,kw) is the same shared-memory tile addressed through a UMMA
-//                            descriptor whose start is shifted by (kh*pitch + kw) rows and whose 8-row-group stride (SBO)
-//                            is the halo pitch.  L2->SMEM traffic for A drops ~6x; profiling showed the generic kernel is
-//                            bound by exactly that traffic (profiles/).
-//   Both: D[128 pixels][BN co] (+)= A * B^T with B = packed weight [Co][(kh,kw,ci)] via 2-D TMA; persistent CTAs;
-//   warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread tcgen05.mma issuer, warps 2..5 = epilogue
-//   (tcgen05.ld -> bias / activation / residual -> NHWC stores); fp32 accumulators double-buffered in TMEM so the
-//   epilogue of tile i overlaps the MMAs of tile i+1; MT = 2 pixel sub-tiles share each B tile when BN <= 128.
+// Forward / dgrad, four kernels sharing one epilogue (dispatch in vqb_conv2d_fwd_tc):
+//   conv_fwd_tc_kernel         generic (any KHxKW 'same' conv, any spatial size): per (tap, 64-channel chunk) one 4-D TMA box
+//                              {64 ch, tw, th, nb} of the NHWC activation at offset (kh-pad, kw-pad) is a K-major
+//                              SWIZZLE_128B A tile; out-of-image elements are zero-filled by TMA (= the conv padding).
+//   conv_fwd_tc_halo_kernel    3x3 convs on >= 16x8 images: ONE halo box {64 ch, 10, 18} per channel chunk serves all nine
+//                              taps -- the A operand of tap (kh,kw) is the same shared-memory tile addressed through a UMMA
+//                              descriptor whose start is shifted by (kh*pitch + kw) rows and whose 8-row-group stride (SBO)
+//                              is the halo pitch.  L2->SMEM traffic for A drops ~6x.  Now only the narrow heads (Co <= 16) and
+//                              64-channel tiles take this kernel.
+//   conv_fwd_tc_halo_t_kernel  Co tiles of 128: operand roles swapped (M = 128 co, N = 256 pixels), smem-transposed epilogue.
+//   conv_fwd_tc_halo2_kernel   Co tiles of 256: CTA pairs (tcgen05 cta_group::2), M = 256 pixels, half the weight tile per SM.
+//   All: B = packed weight [Co][(kh,kw,ci)] via 2-D TMA; persistent CTAs; warp 0 = TMA producer, warp 1 = TMEM allocator +
+//   single-thread tcgen05.mma issuer, warps 2..9 = epilogue (tcgen05.ld -> bias / activation / prefetched residual -> NHWC
+//   stores); fp32 accumulators double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
 //
-// Weight gradient (conv_wgrad_tc_kernel):
+// Weight gradient (conv_wgrad_tc_kernel; conv_wgrad_tc_halo_kernel = 3 taps per CTA on one x halo, ONE wave of CTAs):
 //   dW[tap][ci][co] = sum_pixels x_shift[pix][ci] * dy[pix][co]: the reduction runs over pixels, so both operands are
 //   MN-major SWIZZLE_128B tiles (rows = pixels, 128 B = 64 channels), again straight from 4-D TMA boxes.  M = 128 co
 //   (TMEM lanes), N = up to 256 ci (TMEM columns); the pixel range is split across CTAs and partial tiles are combined
