@@ -305,3 +305,26 @@ def test_entropy_quantizer_matches_reference_module_fixture(V, loss_type):
     assert abs(float(loss) - float(g['loss'])) < 1e-5 * max(1.0, abs(float(g['loss'])))
     assert C.rel_err(z.grad, g['dz']) < 1e-4
     assert C.rel_err(q.codebook.weight.grad, g['dcb']) < 1e-4
+
+
+def test_test_step_metrics_match_definitions(V):
+    """test_step / on_test_epoch_end (model.py:491-562): MSE, PSNR (torchmetrics definitions) and accumulated codebook usage
+    against a direct torch evaluation of the same reconstructions."""
+    import math
+    torch.manual_seed(9)
+    model = V.VQVAE(32, dict(channels=32, num_res_blocks=1, channel_multipliers=[1, 2]),
+                    dict(num_embeddings=32, embedding_dim=32, type='standard', params=dict(commitment_cost=0.25), reinit_every_n_epochs=None),
+                    None, dict(lr=1e-4, betas=[0.9, 0.99], eps=1e-8, weight_decay=0.0, warmup_epochs=None, decay_epochs=None)).cuda().eval()
+    batches = [torch.rand(4, 3, 32, 32, device='cuda') * 0.8 + 0.1 for _ in range(3)]
+    model.on_test_epoch_start()
+    for b in batches:
+        model.test_step(b, 0)
+    model.on_test_epoch_end()
+    rec = torch.cat([model.reconstruct(b) for b in batches]); tgt = torch.cat(batches)
+    mse = float(((rec - tgt).double() ** 2).mean())
+    rng = float(tgt.max() - tgt.min())
+    assert abs(float(model.logged['mse']) - mse) < 1e-6 * max(mse, 1e-6) + 1e-9
+    assert abs(float(model.logged['psnr']) - 10 * math.log10(rng * rng / mse)) < 1e-3
+    usage = sum(torch.bincount(model.get_tokens(b).view(-1), minlength=32) for b in batches)
+    assert torch.equal(model.test_usage_count, usage) and int(usage.sum()) == 12 * 64
+    assert 0 < float(model.logged['perplexity']) <= 32

@@ -212,6 +212,64 @@ class VQVAE(BaseVQVAE, LightningModule):
             self.log('val_metrics/perplexity', perplexity)
         self.val_epoch_usage_count = None
 
+    # ---- test-time evaluation (model.py:491-562) --------------------------------------------------------------
+    def on_test_epoch_start(self):
+        """MSE and PSNR are accumulated with the library's own reduction kernel (vqb_diff_sums, fp64 sums), following
+        torchmetrics' definitions (MeanSquaredError: sum of squared errors / elements; PeakSignalNoiseRatio with
+        data_range=None: 10 log10((max - min of all targets)^2 / MSE)).  SSIM and rFID are delegated to torchmetrics exactly as
+        in the reference when that package is installed (un-pinned third-party arithmetic, off the hot path); otherwise they are
+        not logged.  Codebook usage ACCUMULATES over the epoch (the reference's `else + used_indices` keeps the last batch only)."""
+        dev = next(self.parameters()).device
+        self._test_sse = torch.zeros((), dtype=torch.float64, device=dev)
+        self._test_elems = 0
+        self._test_min = torch.full((), float('inf'), device=dev)
+        self._test_max = torch.full((), float('-inf'), device=dev)
+        self.test_usage_count = None
+        self.test_ssim = self.test_rfid = None
+        try:
+            from torchmetrics.image import StructuralSimilarityIndexMeasure
+            self.test_ssim = StructuralSimilarityIndexMeasure().to(dev)
+            from torchmetrics.image.fid import FrechetInceptionDistance
+            self.test_rfid = FrechetInceptionDistance().to(dev)
+        except Exception:                # not installed (or its Inception weights are not downloadable): MSE / PSNR / usage only
+            pass
+
+    @torch.no_grad()
+    def test_step(self, images: Any, _: int = 0):
+        images = images[0] if isinstance(images, tuple) else images
+        reconstructions, _q, used_indices = self.forward(self.preprocess_batch(images))
+        reconstructions = self.preprocess_visualization(reconstructions)              # NCHW fp32 in [0,1]
+        target = images.float() / 255.0 if images.dtype == torch.uint8 else images.float()
+        target = target.contiguous()
+        counts = torch.bincount(used_indices.view(-1), minlength=self.cb_size)
+        self.test_usage_count = counts if self.test_usage_count is None else self.test_usage_count + counts
+        mse, _l1 = ops.mse_l1(reconstructions, target)
+        self._test_sse += mse.double() * target.numel()
+        self._test_elems += target.numel()
+        lo, hi = torch.aminmax(target)
+        self._test_min = torch.minimum(self._test_min, lo)
+        self._test_max = torch.maximum(self._test_max, hi)
+        if self.test_ssim is not None:
+            self.test_ssim.update(reconstructions, target)
+        if self.test_rfid is not None:
+            to_u8 = lambda t: (t.clamp(0, 1) * 255).to(torch.uint8)
+            self.test_rfid.update(to_u8(reconstructions), real=False)
+            self.test_rfid.update(to_u8(target), real=True)
+
+    def on_test_epoch_end(self):
+        mse = (self._test_sse / max(self._test_elems, 1)).float()
+        self.log('mse', mse)
+        data_range = (self._test_max - self._test_min).double()
+        self.log('psnr', (10.0 * torch.log10(data_range * data_range / self._test_sse * max(self._test_elems, 1))).float())
+        if self.test_ssim is not None:
+            self.log('ssim', self.test_ssim.compute())
+        if self.test_rfid is not None:
+            self.log('rfid', self.test_rfid.compute())
+        if self.test_usage_count is not None:
+            _, perplexity, cb_usage = self.quantizer.get_codebook_usage(self.test_usage_count.float())
+            self.log('used_codebook', cb_usage)
+            self.log('perplexity', perplexity)
+
     # ---- optimizer (model.py:372-440) -----------------------------------------------------------------
     def configure_optimizers(self):
         """AdamW with two groups (Conv2d weights decay; biases, Embedding and GroupNorm weights do not), fused over flat
