@@ -71,3 +71,40 @@ def tie_aware_index_check(idx, ref_idx, flat, codebook, order='standard', ulps=4
         tol = ulps * torch.finfo(torch.float32).eps * torch.maximum(scale, (flat[mism].cpu().float() ** 2).sum(1))
         n_bad = int(((da - db).abs() > tol).sum())
     return int(idx.numel() - mism.numel()), int(mism.numel() - n_bad), n_bad
+
+
+# ---- two-step optimisation fixtures (tests/golden/step_*.npz, oracle/make_golden_step.py) -------------------------------
+# a conv bias that feeds a GroupNorm whose groups hold ONE channel (ch = 32) is cancelled by the mean subtraction: its
+# gradient is mathematically zero, numerically ~1e-8 noise, and AdamW turns that noise into +-lr steps
+DEGENERATE = ('decoder.blocks.3.conv.bias',)
+HEAD = 512
+
+
+def step_state_errors(get, g, i, init):
+    """Compare the state after step `i` with the fixture.  get(name) -> current tensor, init[name] -> initial tensor.
+    Returns (aggregate rel. L2 error of the weight CHANGES over the stored leading elements of every tensor,
+             worst per-tensor error of the same [only tensors that moved], worst rel. error of the per-tensor change norms)."""
+    names = g['state_names'].tolist()
+    dn_ref = dict(zip(names, g[f'dnorm_{i}'].tolist()))
+    num = den = 0.0
+    worst, worst_dn = (0.0, None), (0.0, None)
+    for n in names:
+        if n in DEGENERATE:
+            continue
+        cur = torch.as_tensor(get(n)).detach().double().cpu().reshape(-1)
+        ini = torch.as_tensor(init[n]).detach().double().cpu().reshape(-1)
+        d = (cur - ini)[:HEAD]
+        dref = torch.from_numpy(g[f'w{i}/{n}']).double() - ini[:HEAD]
+        num += float((d - dref).pow(2).sum())
+        den += float(dref.pow(2).sum())
+        if float(dref.norm()) > 0:
+            e = float((d - dref).norm() / dref.norm())
+            if e > worst[0]:
+                worst = (e, n)
+        if dn_ref[n] > 0:
+            e = abs(float((cur - ini).norm()) - dn_ref[n]) / dn_ref[n]
+            if e > worst_dn[0]:
+                worst_dn = (e, n)
+        else:
+            assert float((cur - ini).norm()) == 0.0, f'{n} must not move (the reference leaves it untouched)'
+    return (num / max(den, 1e-300)) ** 0.5, worst, worst_dn
