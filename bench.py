@@ -1,17 +1,25 @@
 #!/usr/bin/env python
-"""bench.py -- images/sec of one full VQ-VAE train step (forward + backward + AdamW) at 256x256.
+"""bench.py -- images/sec of one full VQ-VAE / VQGAN train step (forward + backward + AdamW [+ discriminator step]) at 256x256.
 
     python bench.py --gpus N --steps K --warmup W          # our arm (one rank per GPU under torchrun for N>1)
     python bench.py --impl reference --gpus N ...          # the reference's CPU arithmetic (oracle port) on host cores
 
-Workload (BASELINE.json configs[1]): example_confs/ema_vqvae.yaml with codebook 1024, 256x256 synthetic RGB,
-batch 64 per GPU (weak scaling), random-init weights in the reference's construction order, augmentation off.
-Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definition of every field.
+Headline workload (BASELINE.json configs[1], `--config cfg2`): example_confs/ema_vqvae.yaml with codebook 1024, 256x256
+synthetic RGB, batch 64 per GPU (weak scaling), random-init weights in the reference's construction order, augmentation
+off.  The same JSON line carries one sub-record per other north_star configuration under "configs" (each measured the same
+way: device-resident value, end-to-end e2e, conv roofline, loss check):
+    cfg3  entropy_vqvae.yaml, K=1024, B=64/GPU
+    cfg4  gumbel_vqgan.yaml (Gumbel K=1024 + LPIPS-VGG16 + StyleGAN2 discriminator ACTIVE, R1 every 16th step), B=32/GPU
+    cfg5  EMA VQGAN: gumbel_vqgan.yaml's loss / autoencoder with the EMA quantizer at K=8192, B=32/GPU
+and "strict" = cfg2 in the fp32-parity numeric mode.  `--config X` makes X the headline and skips the sub-records;
+`--only-headline` skips them for cfg2.  Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
 """
 from __future__ import annotations
 
 import argparse
+import gc
 import json
+import math
 import os
 import subprocess
 import sys
@@ -25,9 +33,25 @@ if ROOT not in sys.path:
 import torch
 import torch.distributed as dist
 
-METRIC = 'images/sec VQ-VAE train step 256x256 (ema_vqvae, K=1024)'
 UNIT = 'images/s'
 FALLBACK_PEAKS = {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0}
+
+WORKLOADS = {
+    'cfg2': dict(yaml='ema_vqvae', codebook=1024, batch=64, quantizer=None, gan=False,
+                 metric='images/sec VQ-VAE train step 256x256 (ema_vqvae, K=1024)',
+                 label='ema_vqvae {S}x{S} K={K} B={B}/GPU (BASELINE configs[1]), fwd+bwd+AdamW, augmentation off'),
+    'cfg3': dict(yaml='entropy_vqvae', codebook=1024, batch=64, quantizer=None, gan=False,
+                 metric='images/sec VQ-VAE train step 256x256 (entropy_vqvae, K=1024)',
+                 label='entropy_vqvae {S}x{S} K={K} B={B}/GPU (BASELINE configs[2]), fwd+bwd+AdamW, augmentation off'),
+    'cfg4': dict(yaml='gumbel_vqgan', codebook=1024, batch=32, quantizer=None, gan=True,
+                 metric='images/sec VQGAN train step 256x256 (gumbel_vqgan: Gumbel K=1024 + LPIPS-VGG16 + StyleGAN2 D)',
+                 label='gumbel_vqgan {S}x{S} K={K} B={B}/GPU (BASELINE configs[3]): AE fwd+bwd+AdamW with L1/L2/LPIPS/generator '
+                       'loss, then D fwd x2 + bwd + AdamW, R1 every 16th step, discriminator active (start_epoch 0), augmentation off'),
+    'cfg5': dict(yaml='gumbel_vqgan', codebook=8192, batch=32, quantizer='ema', gan=True,
+                 metric='images/sec VQGAN train step 256x256 (EMA VQGAN K=8192 + LPIPS-VGG16 + StyleGAN2 D)',
+                 label='EMA VQGAN {S}x{S} K={K} B={B}/GPU (BASELINE configs[4]): gumbel_vqgan.yaml loss heads with the EMA quantizer '
+                       'of ema_vqvae.yaml, same step as cfg4'),
+}
 
 
 def peaks():
@@ -43,11 +67,33 @@ def peaks():
     return dict(FALLBACK_PEAKS), 'fallback'
 
 
-def model_confs(args, world):
+def measured_traffic():
+    """DRAM bytes per launch of the dominant conv kernel, parsed from THIS round's `ncu --set full` capture by
+    tools/ncu_traffic.py into profiles/r02_conv_traffic.json (a profiler cannot run inside the timed region)."""
+    path = os.path.join(ROOT, 'profiles', 'r02_conv_traffic.json')
+    if os.path.exists(path):
+        try:
+            return json.load(open(path))
+        except Exception:
+            return None
+    return None
+
+
+def model_confs(name, args, world):
     from vqvae_vqgan_pytorch_lightning_b200.common_utils import derive_confs, get_model_conf
-    conf = get_model_conf(os.path.join(ROOT, 'example_confs', 'ema_vqvae.yaml'))
-    return derive_confs(conf, world, {'num_embeddings': args.codebook, 'image_size': args.image_size,
-                                      'cumulative_bs': args.batch * world})
+    wl = WORKLOADS[name]
+    conf = get_model_conf(os.path.join(ROOT, 'example_confs', wl['yaml'] + '.yaml'))
+    if wl['quantizer'] == 'ema':
+        ema = get_model_conf(os.path.join(ROOT, 'example_confs', 'ema_vqvae.yaml'))['quantizer']
+        conf['quantizer'] = dict(ema, embedding_dim=conf['quantizer']['embedding_dim'])
+    batch = args.batch or wl['batch']
+    codebook = args.codebook or wl['codebook']
+    image_size, ae_conf, q_conf, l_conf, t_conf, bs = derive_confs(
+        conf, world, {'num_embeddings': codebook, 'image_size': args.image_size, 'cumulative_bs': batch * world})
+    if wl['gan']:
+        l_conf = dict(l_conf)
+        l_conf['adversarial_params'] = dict(l_conf['adversarial_params'], start_epoch=0)      # SURVEY.md 8d: D active
+    return image_size, ae_conf, q_conf, l_conf, t_conf, bs, codebook
 
 
 class ClockSampler:
@@ -92,14 +138,16 @@ def conv_flops(name, a):
 
 
 # ------------------------------------------------------------------------------------------------------
-def vq_microbench(pkg, dev, n_lat, k, use_tc, hbm_peak, iters=15):
-    """The fused VQ kernel in isolation on the workload's latent shape: z ~ N(0,1) [N,256]; codebook N(0,1)
+def vq_microbench(pkg, dev, n_lat, k, use_tc, pk, iters=15):
+    """The fused VQ op in isolation on a workload's latent shape: z ~ N(0,1) [N,256]; codebook N(0,1)
     (tie-free, what a trained codebook looks like to the search) and U(+-1/K) (the reference's initial codebook: thousands of
-    codes within 1e-5 of each other, so the exact fp32 path takes over).  L2 is flushed between launches; algorithmic bytes =
-    4ND (z) + 4KD (codebook) + 4ND (q) + 8N (idx) + 8K + 12KD (EMA statistics)."""
+    codes within 1e-5 of each other, so the exact fp32 path takes over).  L2 is flushed between launches.  Both roofs:
+    algorithmic bytes = 4ND (z) + 4KD (codebook) + 4ND (q) + 8N (idx) + 8K + 12KD (EMA statistics) against the HBM peak, and
+    the distance contraction 2NKD (x3 for the bf16 hi/lo split that keeps the indices exact) against the bf16 tensor peak."""
     d = 256
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     nbytes = 4 * n_lat * d * 2 + 4 * k * d + 8 * n_lat + 8 * k + 12 * k * d
+    flop = 2.0 * n_lat * k * d
     cases = []
     for init in ('normal', 'uniform'):
         torch.manual_seed(0)
@@ -116,40 +164,41 @@ def vq_microbench(pkg, dev, n_lat, k, use_tc, hbm_peak, iters=15):
             ts.append(e0.elapsed_time(e1) * 1e3)
         us = sorted(ts)[len(ts) // 2]
         und = int(pkg.ops.vq_assign_raw.last_undecided) if use_tc else None
-        cases.append({'codebook': init, 'us_per_launch': us, 'gbs': nbytes / us / 1e3, 'frac': nbytes / us / 1e3 / hbm_peak,
-                      'rows_on_exact_path': und})
+        cases.append({'codebook': init, 'us_per_launch': us, 'gbs': nbytes / us / 1e3, 'frac': nbytes / us / 1e3 / pk['hbm_gbs'],
+                      'tensor_tflops_algorithmic': flop / us / 1e6, 'tensor_frac_algorithmic': flop / us / 1e6 / pk['bf16_tflops'],
+                      'tensor_frac_issued_3x_split': 3 * flop / us / 1e6 / pk['bf16_tflops'], 'rows_on_exact_path': und})
     c0 = cases[0]
-    return {'bound': 'hbm', 'kernel': 'vq_assign_tc: bf16 hi/lo tcgen05 search + exact fp32 re-rank + gather/EMA scatter' if use_tc
-            else 'vq_assign: fused fp32 SIMT', 'achieved': c0['gbs'], 'peak': hbm_peak, 'unit': 'GB/s', 'frac': c0['frac'],
-            'traffic': None, 'algorithmic_bytes': nbytes, 'shape': {'N': n_lat, 'K': k, 'D': d}, 'cases': cases,
-            'note': 'exact-argmin contract: the distance GEMM (2NKD x3 bf16-split FLOP) keeps this kernel tensor/latency-bound, not HBM-bound'}
+    return {'bound': 'hbm', 'kernel': 'vq_assign_tc' if use_tc else 'vq_assign (fp32 SIMT)', 'achieved': c0['gbs'], 'peak': pk['hbm_gbs'],
+            'unit': 'GB/s', 'frac': c0['frac'], 'traffic': None, 'algorithmic_bytes': nbytes, 'algorithmic_flop': flop,
+            'shape': {'N': n_lat, 'K': k, 'D': d}, 'cases': cases}
 
 
-def cpu_reference_step(batch: int, image_size: int, codebook: int, steps: int, warmup: int, threads: int):
-    """The reference's arithmetic on host cores: oracle port of forward + backward + AdamW (fp32, oneDNN/MKL).
-    Returns (images_per_sec, seconds_per_step)."""
+def cpu_reference_step(name: str, batch: int, image_size: int, codebook: int, steps: int, warmup: int, threads: int):
+    """The reference's arithmetic on host cores: oracle port of on_train_batch_start + training_step + AdamW (fp32 torch CPU,
+    oneDNN / MKL) for workload `name`.  Returns (images_per_sec, seconds_per_step)."""
+    from oracle import gan_oracle as G
     from oracle import init_state as oinit
-    from oracle import vqvae_oracle as orc
+    from vqvae_vqgan_pytorch_lightning_b200.common_utils import derive_confs, get_model_conf
     torch.set_num_threads(threads)
-    sd = oinit.init_state('ema', codebook, 256, 128, 2, (1, 2, 2, 4), seed=1234)
-    sd = oinit.make_leaf(sd, 'ema')
-    cfg = {'num_res_blocks': 2, 'channel_multipliers': (1, 2, 2, 4),
-           'quantizer': dict(type='ema', commitment_cost=0.25, decay=0.95, epsilon=1e-5)}
-    mom = {n: (torch.zeros_like(t), torch.zeros_like(t)) for n, t in sd.items() if t.requires_grad}
-    x = orc.normalize_images(torch.rand(batch, 3, image_size, image_size))
+
+    class A:
+        pass
+    a = A(); a.batch, a.codebook, a.image_size = batch, codebook, image_size
+    image_size, ae_conf, q_conf, l_conf, t_conf, bs, codebook = model_confs(name, a, 1)
+    qtype = q_conf['type']
+    crit = None if l_conf is None else 'gan'
+    sd = oinit.init_state(qtype, codebook, q_conf['embedding_dim'], ae_conf['channels'], ae_conf['num_res_blocks'],
+                          tuple(ae_conf['channel_multipliers']), seed=1234, criterion=crit, image_size=image_size)
+    sd = oinit.make_leaf(sd, qtype)
+    cfg = {'num_res_blocks': ae_conf['num_res_blocks'], 'channel_multipliers': tuple(ae_conf['channel_multipliers']),
+           'quantizer': dict(q_conf.get('params') or {}, type=qtype)}
+    opts = G.configure_optimizers(sd, t_conf, gan=(crit == 'gan'))
+    x = torch.rand(batch, 3, image_size, image_size)
     times = []
     for it in range(warmup + steps):
+        noise = torch.empty(batch, codebook, image_size // 16, image_size // 16).exponential_() if qtype == 'gumbel' else None
         t0 = time.perf_counter()
-        for t in sd.values():
-            t.grad = None
-        out = orc.train_step_mse(sd, x, cfg)
-        with torch.no_grad():
-            sd['quantizer.codebook.weight'].copy_(out['new_codebook'])
-            sd['quantizer.ema_count'].copy_(out['new_ema_count'])
-            sd['quantizer.ema_weight'].copy_(out['new_ema_weight'])
-            for n, t in sd.items():
-                if t.requires_grad and t.grad is not None:
-                    orc.adamw_step(t, t.grad, mom[n][0], mom[n][1], it + 1, 1e-4, 0.0, 0.99, 1e-8, 1e-4)
+        G.train_step(sd, opts, x, cfg, l_conf, t_conf, 0, it, warmup + steps, exp_noise=noise)
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
@@ -160,15 +209,18 @@ def cpu_reference_step(batch: int, image_size: int, codebook: int, steps: int, w
 def run_reference(args, rank, world, out=sys.stdout):
     if rank != 0:
         return
+    name = args.config
+    wl = WORKLOADS[name]
     threads = os.cpu_count() or 1
     b = args.cpu_batch
-    ips, sec = cpu_reference_step(b, args.image_size, args.codebook, args.steps, min(args.warmup, 1), threads)
+    codebook = args.codebook or wl['codebook']
+    ips, sec = cpu_reference_step(name, b, args.image_size, codebook, args.steps, min(args.warmup, 1), threads)
     line = {
-        'impl': 'reference', 'metric': METRIC, 'value': ips, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+        'impl': 'reference', 'metric': wl['metric'], 'value': ips, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': min(args.warmup, 1), 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': f'ema_vqvae {args.image_size}x{args.image_size} K={args.codebook}: bounded sample of the '
-                               f'B={args.batch} step at micro-batch {b} (img/s is batch-insensitive on CPU)'},
+        'config': {'workload': wl['label'].format(S=args.image_size, K=codebook, B=args.batch or wl['batch']) +
+                               f' -- bounded sample at micro-batch {b} (img/s is batch-insensitive on CPU)'},
         'cpu_baseline': {'value': ips, 'unit': UNIT, 'cores': threads, 'kind': 'port',
                          'sample': f'{args.steps} steps x {b} images, oracle port of the reference modules (fp32, torch CPU)'},
         'e2e': {'value': ips, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -178,16 +230,154 @@ def run_reference(args, rank, world, out=sys.stdout):
 
 
 # ------------------------------------------------------------------------------------------------------
+def run_workload(name, args, pkg, dev, rank, world, precision, steps, warmup, stamp, sample_clocks=False, ncu_step=False):
+    """Build workload `name`, run `warmup` + `steps` device-resident steps and `steps` end-to-end steps through
+    Trainer.run_step; returns the record (rank 0; other ranks return None)."""
+    from vqvae_vqgan_pytorch_lightning_b200.lightning_shim import Trainer
+    pkg.set_precision(precision)
+    image_size, ae_conf, q_conf, l_conf, t_conf, bs, codebook = model_confs(name, args, world)
+    torch.manual_seed(1234)                       # same weights on every rank (reference construction order)
+    model = pkg.VQVAE(image_size, ae_conf, q_conf, l_conf, t_conf, pretrained_lpips=False).to(dev).train()
+    trainer = Trainer(max_epochs=1, num_training_batches=steps * 2 + warmup)
+    trainer.attach(model)
+    model.on_train_start()
+    model.training_augmentations = None           # SURVEY.md 8d: the metric is quoted with augmentation off
+
+    torch.manual_seed(1234 + rank)
+    nbuf = 2
+    host = [torch.rand(bs, 3, image_size, image_size).pin_memory() for _ in range(nbuf)]
+    resident = [h.to(dev) for h in host]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    step_idx = [0]
+    l2_log = []                                    # device scalars, read after the timed region
+
+    def step_resident(i):
+        loss = trainer.run_step(resident[i % nbuf], step_idx[0]); step_idx[0] += 1
+        l2_log.append((loss.detach(), torch.as_tensor(model.logged['train/l2_loss']).detach()))
+        return loss
+
+    def step_e2e(i):
+        x = host[i % nbuf].to(dev, non_blocking=True)                            # H2D from pinned memory, every step
+        loss = trainer.run_step(x, step_idx[0]); step_idx[0] += 1
+        l2_log.append((loss.detach(), torch.as_tensor(model.logged['train/l2_loss']).detach()))
+        return float(loss.detach().cpu())                                        # D2H read of the step's loss
+
+    stamp(f'{name}/{precision}: model and inputs ready')
+    for i in range(warmup):
+        step_resident(i)
+    barrier()
+    if ncu_step:
+        torch.cuda.profiler.start()
+        step_resident(0)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return None
+
+    # ---- timed region 1: inputs resident in HBM (value, ms_per_step, roofline) ---------------------------------
+    clocks = ClockSampler(dev.index or 0)
+    if rank == 0 and sample_clocks:
+        clocks.start()
+    pkg.lib.timer = pkg.lib.KernelTimer(['vqb_conv2d_fwd', 'vqb_conv2d_wgrad', 'vqb_vq_assign', 'vqb_vq_assign_tc', 'vqb_vq_fused'])
+    launches0 = pkg.lib.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(steps):
+        step_resident(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = pkg.lib.launch_count - launches0
+    ksum = pkg.lib.timer.summary()
+    pkg.lib.timer = None
+
+    # ---- timed region 2: end to end through the public API with host buffers ---------------------------------------
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    f0.record()
+    for i in range(steps):
+        step_e2e(i)
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    clk = clocks.stop() if (rank == 0 and sample_clocks) else None
+    stamp(f'{name}/{precision}: timed regions done')
+
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+
+    # ---- the step must be a real optimisation step: every loss finite, reconstruction error not increasing ----------
+    losses = torch.stack([a.float().reshape(()) for a, _ in l2_log]).cpu().tolist()
+    l2s = torch.stack([b.float().reshape(()) for _, b in l2_log]).cpu().tolist()
+    if not all(math.isfinite(v) for v in losses + l2s):
+        raise SystemExit(f'bench.py: non-finite loss in {name}/{precision}: {losses}')
+    head, tail = sum(l2s[:nbuf]) / nbuf, sum(l2s[-nbuf:]) / nbuf          # the same nbuf batches at the start and at the end
+    if tail > head * 1.001:
+        raise SystemExit(f'bench.py: reconstruction loss increased in {name}/{precision}: {head} -> {tail}')
+    peak_mem = torch.cuda.max_memory_allocated() / 2 ** 30
+    del model, trainer, resident, host
+    gc.collect()
+    torch.cuda.empty_cache()
+    torch.cuda.reset_peak_memory_stats()
+    if rank != 0:
+        return None
+
+    pk, pk_kind = peaks()
+    total_images = bs * world * steps
+    conv_ms = sum(ksum[k]['ms'] for k in ('vqb_conv2d_fwd', 'vqb_conv2d_wgrad') if k in ksum)
+    conv_fl = sum(conv_flops(k, a) for k in ('vqb_conv2d_fwd', 'vqb_conv2d_wgrad') if k in ksum for a in ksum[k]['args'])
+    conv_calls = sum(ksum[k]['calls'] for k in ('vqb_conv2d_fwd', 'vqb_conv2d_wgrad') if k in ksum)
+    achieved = conv_fl / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
+    fast = precision != 'strict'
+    peak = pk['bf16_tflops_sustained']
+    tr = measured_traffic() if (name == 'cfg2' and fast and (image_size, bs) == (256, 64)) else None
+    roofline = {'bound': 'tensor', 'kernel': 'implicit-GEMM conv (fwd+dgrad+wgrad launches)' + ('' if fast else ' -- fp32 SIMT kernels against the bf16 roof'),
+                'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
+                'traffic': tr['dram_bytes_per_launch'] if tr else None, 'traffic_source': tr.get('source') if tr else None,
+                'traffic_algorithmic_bytes': tr.get('algorithmic_bytes') if tr else None,
+                'peak_source': f'{pk_kind} (sustained bf16)', 'launches_timed': conv_calls, 'share_of_step': conv_ms / ms,
+                'flop_per_step': conv_fl / steps, 'whole_step_tflops': conv_fl / (ms / 1e3) / 1e12,
+                'whole_step_frac': conv_fl / (ms / 1e3) / 1e12 / peak}
+    rec = {
+        'metric': WORKLOADS[name]['metric'], 'value': total_images / (ms / 1e3), 'unit': UNIT, 'ms_per_step': ms / steps,
+        'steps': steps, 'warmup': warmup, 'dtype': 'bf16' if fast else 'f32',
+        'config': {'workload': WORKLOADS[name]['label'].format(S=image_size, K=codebook, B=bs), 'precision': precision,
+                   'global_batch': bs * world, 'parallelism': f'dp{world}',
+                   'l2_policy': 'working set per step (inputs + activations > 5 GB) exceeds the 126 MB L2'},
+        'e2e': {'value': total_images / (ms_e2e / 1e3), 'unit': UNIT, 'h2d_bytes_per_step': bs * 3 * image_size * image_size * 4,
+                'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e / steps},
+        'gpu_launches': launches, 'roofline': roofline,
+        'loss': {'first': losses[0], 'last': losses[-1], 'l2_first': head, 'l2_last': tail, 'all_finite': True,
+                 'steps_observed': len(losses)},
+        'peak_mem_gib': peak_mem,
+    }
+    vq_step = ksum.get('vqb_vq_fused') or ksum.get('vqb_vq_assign_tc') or ksum.get('vqb_vq_assign')
+    if vq_step:
+        rec['vq_in_step_us_per_launch'] = vq_step['ms'] / vq_step['calls'] * 1e3
+    if clk is not None:
+        rec['clocks'] = clk
+    return rec
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--config', default='cfg2', choices=list(WORKLOADS))
+    ap.add_argument('--only-headline', action='store_true', help='skip the cfg3 / cfg4 / cfg5 / strict sub-records')
     ap.add_argument('--precision', default=os.environ.get('VQB_PRECISION', 'fast'), choices=['strict', 'fast'])
-    ap.add_argument('--batch', type=int, default=64, help='images per GPU per step')
+    ap.add_argument('--batch', type=int, default=0, help='images per GPU per step (default: the workload\'s)')
     ap.add_argument('--image-size', type=int, default=256)
-    ap.add_argument('--codebook', type=int, default=1024)
+    ap.add_argument('--codebook', type=int, default=0)
     ap.add_argument('--cpu-batch', type=int, default=2)
     ap.add_argument('--cpu-steps', type=int, default=2)
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -222,125 +412,56 @@ def main():
 
     stamp('process group up')
     import vqvae_vqgan_pytorch_lightning_b200 as pkg
-    from vqvae_vqgan_pytorch_lightning_b200.lightning_shim import Trainer
     pkg.lib.load()
     precision = args.precision
-    if precision == 'fast' and not pkg.lib.load().vqb_device_supports_tcgen05():
-        raise SystemExit('bench.py: fast precision needs an sm_100 device')
-    pkg.set_precision(precision)
+    if not pkg.lib.load().vqb_device_supports_tcgen05():
+        raise SystemExit('bench.py: needs an sm_100 device')
 
-    image_size, ae_conf, q_conf, l_conf, t_conf, bs = model_confs(args, world)
-    torch.manual_seed(1234)                       # same weights on every rank (reference construction order)
-    model = pkg.VQVAE(image_size, ae_conf, q_conf, l_conf, t_conf).to(dev).train()
-    trainer = Trainer(max_epochs=1, num_training_batches=args.steps + args.warmup)
-    trainer.attach(model)
-    model.on_train_start()
-    model.training_augmentations = None           # the metric is quoted with augmentation off
-
-    torch.manual_seed(1234 + rank)
-    nbuf = 2
-    host = [torch.rand(bs, 3, image_size, image_size).pin_memory() for _ in range(nbuf)]
-    resident = [h.to(dev) for h in host]
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    step_idx = [0]
-
-    def step_resident(i):
-        loss = trainer.run_step(resident[i % nbuf], step_idx[0]); step_idx[0] += 1
-        return loss
-
-    def step_e2e(i):
-        x = host[i % nbuf].to(dev, non_blocking=True)                            # H2D from pinned memory, every step
-        loss = trainer.run_step(x, step_idx[0]); step_idx[0] += 1
-        return float(loss.detach().cpu())                                        # D2H read of the step's loss
-
-    stamp('model and inputs ready')
-    for i in range(args.warmup):
-        step_resident(i)
-    barrier()
-    stamp('warm-up done')
     if args.ncu_step:
-        torch.cuda.profiler.start()
-        step_resident(0)
-        torch.cuda.synchronize()
-        torch.cuda.profiler.stop()
+        run_workload(args.config, args, pkg, dev, rank, world, precision, args.steps, args.warmup, stamp, ncu_step=True)
         return
+    head = run_workload(args.config, args, pkg, dev, rank, world, precision, args.steps, args.warmup, stamp, sample_clocks=True)
 
-    # ---- timed region 1: inputs resident in HBM (value, ms_per_step, roofline) ---------------------------------
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
-    pkg.lib.timer = pkg.lib.KernelTimer(['vqb_conv2d_fwd', 'vqb_conv2d_wgrad', 'vqb_vq_assign', 'vqb_vq_assign_tc'])
-    launches0 = pkg.lib.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for i in range(args.steps):
-        step_resident(i)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    launches = pkg.lib.launch_count - launches0
-    ksum = pkg.lib.timer.summary()
-    pkg.lib.timer = None
-
-    # ---- timed region 2: end to end through the public API with host buffers ---------------------------------------
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    f0.record()
-    for i in range(args.steps):
-        step_e2e(i)
-    f1.record()
-    barrier()
-    ms_e2e = f0.elapsed_time(f1)
-    stamp('timed regions done')
-    clk = clocks.stop() if rank == 0 else None
-
-    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = float(t[0]), float(t[1])
+    subs = {}
+    strict = None
+    if args.config == 'cfg2' and not args.only_headline and not args.batch and not args.codebook and args.image_size == 256:
+        for name in ('cfg3', 'cfg4', 'cfg5'):
+            subs[name] = run_workload(name, args, pkg, dev, rank, world, precision, args.steps, args.warmup, stamp)
+        if precision == 'fast':
+            strict = run_workload('cfg2', args, pkg, dev, rank, world, 'strict', min(args.steps, 3), 3, stamp)
 
     if rank == 0:
         pk, pk_kind = peaks()
-        total_images = bs * world * args.steps
-        value = total_images / (ms / 1e3)
-        e2e = total_images / (ms_e2e / 1e3)
-        conv_ms = sum(ksum[k]['ms'] for k in ('vqb_conv2d_fwd', 'vqb_conv2d_wgrad') if k in ksum)
-        conv_fl = sum(conv_flops(k, a) for k in ('vqb_conv2d_fwd', 'vqb_conv2d_wgrad') if k in ksum for a in ksum[k]['args'])
-        conv_calls = sum(ksum[k]['calls'] for k in ('vqb_conv2d_fwd', 'vqb_conv2d_wgrad') if k in ksum)
-        achieved = conv_fl / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
-        peak = pk['bf16_tflops_sustained']
-        roofline = {'bound': 'tensor', 'kernel': 'implicit-GEMM conv (fwd+dgrad+wgrad launches)', 'achieved': achieved, 'peak': peak,
-                    'unit': 'TFLOP/s', 'frac': achieved / peak,
-                    # DRAM bytes of ONE launch of the largest layer (128->128 3x3 @256^2, B=64; algorithmic 2.147e9 B = x + y) from the
-                    # committed `ncu --set full` capture -- not measured live (a profiler cannot run inside the timed region)
-                    'traffic': 2.114e9 if (image_size, bs) == (256, 64) else None,
-                    'traffic_source': 'profiles/r01_ncu_full_top_kernels.txt: conv_fwd_tc_halo_t_kernel launch 0, dram read 1.084 GB + write 1.030 GB',
-                    'peak_source': f'{pk_kind} (sustained bf16)',
-                    'launches_timed': conv_calls, 'share_of_step': conv_ms / ms, 'flop_per_step': conv_fl / args.steps}
-        vq_roof = vq_microbench(pkg, dev, bs * (image_size // 16) ** 2, args.codebook, precision == 'fast', pk['hbm_gbs'])
-        vq_step = ksum.get('vqb_vq_assign_tc') or ksum.get('vqb_vq_assign')
-        if vq_step:
-            vq_roof['in_step_us_per_launch'] = vq_step['ms'] / vq_step['calls'] * 1e3      # init-time codebook: tie-heavy
+        bs = head['config']['global_batch'] // world
         line = {
-            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'bf16' if precision == 'fast' else 'f32', 'data': 'synthetic',
-            'config': {'workload': f'ema_vqvae {image_size}x{image_size} K={args.codebook} B={bs}/GPU (BASELINE configs[1]), '
-                                   f'fwd+bwd+AdamW, augmentation off', 'precision': precision, 'global_batch': bs * world,
-                       'parallelism': f'dp{world}', 'l2_policy': 'working set per step (inputs 50 MB + activations > 10 GB) exceeds the 126 MB L2'},
-            'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': bs * 3 * image_size * image_size * 4, 'd2h_bytes_per_step': 4,
-                    'ms_per_step': ms_e2e / args.steps},
-            'gpu_launches': launches, 'clocks': clk, 'roofline': roofline, 'vq_roofline': vq_roof,
+            'metric': head['metric'], 'value': head['value'], 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': head['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': head['dtype'], 'data': 'synthetic', 'config': head['config'], 'e2e': head['e2e'],
+            'gpu_launches': head['gpu_launches'], 'clocks': head.get('clocks'), 'roofline': head['roofline'], 'loss': head['loss'],
         }
+        if world == 1:
+            vq = {}
+            for tag, (n_lat, k) in {'cfg2': (64 * 256, 1024), 'cfg5': (32 * 256, 8192)}.items():
+                vq[tag] = vq_microbench(pkg, dev, n_lat, k, precision == 'fast', pk)
+            line['vq_roofline'] = vq['cfg2']
+            line['vq_roofline']['in_step_us_per_launch'] = head.get('vq_in_step_us_per_launch')
+            line['vq_roofline_k8192'] = vq['cfg5']
+            tr = os.path.join(ROOT, 'profiles', 'r02_vq_traffic.json')
+            if os.path.exists(tr):
+                try:
+                    t = json.load(open(tr))
+                    line['vq_roofline']['traffic'] = t.get('dram_bytes_per_launch')
+                    line['vq_roofline']['traffic_source'] = t.get('source')
+                except Exception:
+                    pass
+        if subs:
+            line['configs'] = subs
+        if strict is not None:
+            line['strict'] = strict
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            ips, sec = cpu_reference_step(args.cpu_batch, image_size, args.codebook, args.cpu_steps, 1, threads)
+            codebook = args.codebook or WORKLOADS[args.config]['codebook']
+            ips, sec = cpu_reference_step(args.config, args.cpu_batch, args.image_size, codebook, args.cpu_steps, 1, threads)
             line['cpu_baseline'] = {'value': ips, 'unit': UNIT, 'cores': threads, 'kind': 'port',
                                     'sample': f'{args.cpu_steps} steps x {args.cpu_batch} images ({sec:.1f} s/step), oracle port of the '
                                               f'reference modules, fp32 torch CPU'}

@@ -1,0 +1,140 @@
+"""GPU parity AT THE SHAPES bench.py RUNS (BASELINE configs 2-5: 256x256 images, B = 64 / 32 per GPU).
+
+* every tcgen05 kernel family at its dominant bench launch (128->128 @256^2 B=64 on the swapped-operand kernel, 256->256 @128^2
+  on the CTA-pair kernel, 512->512 @16^2, the 1x1 shortcut, the one-wave weight gradient) against the fp32 SIMT kernel of the
+  strict path on the SAME bf16-rounded operands, fp32 outputs: only the accumulation order differs -> 1e-4;
+* the VQ search at N=16384 / K=1024 and N=8192 / K=8192 (normal and the reference's tie-heavy uniform initial codebook)
+  against the exact kernel (identical indices) and, tie-aware, against the CPU oracle's distance matrix;
+* the whole cfg2 model (ema_vqvae.yaml, 256x256, K=1024) forward + backward in the fast mode against the strict mode,
+  with the per-tensor tolerance of bf16 activation storage stated below."""
+import pytest
+import torch
+
+from oracle import vqvae_oracle as orc
+from tests import common as C
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def V():
+    import vqvae_vqgan_pytorch_lightning_b200 as pkg
+    pkg.lib.load()
+    if not pkg.lib.load().vqb_device_supports_tcgen05():
+        pytest.skip('needs sm_100')
+    yield pkg
+    pkg.set_precision('strict')
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / b.norm())
+
+
+BENCH_LAYERS = [
+    # n, hw, ci, co, k, residual       (per-GPU bench launches: cfg2 B=64; cfg4/5 B=32 run the same kernels on half the grid)
+    (64, 256, 128, 128, 3, True),      # encoder level 0 / decoder top: conv_fwd_tc_halo_t_kernel (+ fused residual), 19.3 GF/img
+    (64, 128, 256, 256, 3, False),     # conv_fwd_tc_halo2_kernel (CTA pair)
+    (64, 128, 128, 256, 3, False),     # level transition
+    (64, 128, 128, 256, 1, False),     # 1x1 shortcut: conv_fwd_tc_kernel
+    (64, 64, 256, 256, 3, True),
+    (64, 32, 512, 512, 3, False),
+    (64, 16, 512, 512, 3, True),
+    (64, 16, 256, 512, 3, False),      # decoder.conv_in
+]
+
+
+@pytest.mark.parametrize('n,hw,ci,co,k,res', BENCH_LAYERS)
+def test_tcgen05_conv_equals_simt_at_bench_shapes(V, n, hw, ci, co, k, res):
+    ops = V.ops
+    torch.manual_seed(3)
+    dev = 'cuda'
+    x16 = torch.randn(n, ci, hw, hw, device=dev).contiguous(memory_format=torch.channels_last).bfloat16()
+    w = (torch.randn(co, ci, k, k, device=dev) / (ci * k * k) ** 0.5).bfloat16().float()
+    r = torch.randn(n, co, hw, hw, device=dev).contiguous(memory_format=torch.channels_last) if res else None
+    dy16 = torch.randn(n, co, hw, hw, device=dev).contiguous(memory_format=torch.channels_last).bfloat16()
+    pad = k // 2
+    # forward
+    V.set_precision('fast')
+    y_tc = ops.conv2d(x16, w, None, r, pad=pad, out_dtype=torch.float32)
+    dx_tc = ops._dgrad_raw(dy16, w, hw, hw, pad, 1, 1.0, torch.float32)
+    dw_tc = ops._wgrad_raw(x16, dy16, w.shape, pad, 1, 1.0)
+    V.set_precision('strict')
+    x32 = x16.float()
+    y_s = ops.conv2d(x32, w, None, r, pad=pad, out_dtype=torch.float32)
+    e = rel(y_tc, y_s)
+    del y_tc, y_s
+    dy32 = dy16.float()
+    dx_s = ops._dgrad_raw(dy32, w, hw, hw, pad, 1, 1.0, torch.float32)
+    e_dx = rel(dx_tc, dx_s)
+    del dx_tc, dx_s
+    dw_s = ops._wgrad_raw(x32, dy32, w.shape, pad, 1, 1.0)
+    e_dw = rel(dw_tc, dw_s)
+    # the weight gradient sums n*hw*hw (up to 4.2 M) products per element: both kernels carry fp32 accumulation error of that
+    # order, so each is also measured against a float64 evaluation of an 8x8-channel sub-block
+    xs, dys = x32[:, :8].double().contiguous(), dy32[:, :8].double().contiguous()
+    wsub = torch.zeros(8, 8, k, k, dtype=torch.float64, device=dev, requires_grad=True)
+    torch.nn.functional.conv2d(xs, wsub, padding=pad).backward(dys)
+    t_tc, t_s = rel(dw_tc[:8, :8], wsub.grad), rel(dw_s[:8, :8], wsub.grad)
+    assert e < 1e-4 and e_dx < 1e-4, (e, e_dx)
+    assert e_dw < 3e-4 and t_tc < max(1e-4, 2 * t_s), (e_dw, t_tc, t_s)
+
+
+@pytest.mark.parametrize('N,K,init', [(16384, 1024, 'normal'), (16384, 1024, 'uniform'), (8192, 8192, 'normal'),
+                                      (8192, 8192, 'uniform'), (8192, 1024, 'normal')])
+def test_vq_at_bench_shapes(V, N, K, init):
+    """cfg2/3: N = 64*256, K = 1024; cfg5: N = 32*256, K = 8192; cfg4's shape with a standard codebook."""
+    D = 256
+    torch.manual_seed(5)
+    z = torch.randn(N, D).cuda()
+    cb = (torch.empty(K, D).uniform_(-1 / K, 1 / K) if init == 'uniform' else torch.randn(K, D)).cuda()
+    q0, i0, s0, c0, w0 = V.ops.vq_assign_raw(z, cb, 0, True, True, use_tc=False)
+    q1, i1, s1, c1, w1 = V.ops.vq_assign_raw(z, cb, 0, True, True, use_tc=True)
+    assert torch.equal(i0, i1), int((i0 != i1).sum())
+    assert torch.equal(q0, q1) and torch.equal(c0, c1)
+    assert abs(float(s0) - float(s1)) <= 1e-6 * abs(float(s0)) and C.rel_err(w1, w0) < 1e-5
+    ref = torch.argmin(orc.l2_distances(z.cpu(), cb.cpu()), dim=1)
+    exact, ties, bad = C.tie_aware_index_check(i1, ref, z.cpu(), cb.cpu())
+    assert bad == 0, (exact, ties, bad)
+    if init == 'normal':
+        assert ties == 0 and exact == N                          # tie-free: bit-exact against the reference arithmetic
+
+
+def test_cfg2_fast_against_strict_at_256(V):
+    """ema_vqvae.yaml (cfg2 architecture: 128 channels, (1,2,2,4), K=1024, 256x256), B=8: the benchmarked fast path against the
+    parity (strict) path on the same weights and images.  Stated tolerance of bf16 activation storage through 48 convolutions
+    and 42 GroupNorms: latents 3e-2 rel. L2, reconstruction 1e-1, losses 2e-2, every parameter-gradient norm within 10 %
+    (aggregate gradient 5 %), >= 90 % identical code indices at the tie-heavy initial codebook."""
+    import os
+    from vqvae_vqgan_pytorch_lightning_b200.common_utils import derive_confs, get_model_conf
+    conf = get_model_conf(os.path.join(C.ROOT, 'example_confs', 'ema_vqvae.yaml'))
+    image_size, ae_conf, q_conf, l_conf, t_conf, _ = derive_confs(conf, 1, {'num_embeddings': 1024, 'image_size': 256, 'cumulative_bs': 8})
+    res = {}
+    for mode in ('strict', 'fast'):
+        V.set_precision(mode)
+        torch.manual_seed(1234)
+        model = V.VQVAE(image_size, ae_conf, q_conf, l_conf, t_conf).cuda().train()
+        model.training_augmentations = None
+        torch.manual_seed(99)
+        x = torch.rand(8, 3, 256, 256, device='cuda')
+        images = model.preprocess_batch(x, training=True)
+        recon, q_loss, idx = model(images)
+        l2 = model.criterion(recon, images)
+        (q_loss + l2).backward()
+        z = model.encoder(images).detach().float()
+        res[mode] = dict(z=z, recon=recon.detach().float(), idx=idx, l2=float(l2.detach()), q=float(q_loss.detach()),
+                         grads={n: p.grad.detach().double() for n, p in model.named_parameters() if p.grad is not None})
+        del model
+    s, f = res['strict'], res['fast']
+    num = sum(float((f['grads'][n] - g).pow(2).sum()) for n, g in s['grads'].items())
+    den = sum(float(g.pow(2).sum()) for g in s['grads'].values())
+    worst = max(abs(float(f['grads'][n].norm()) - float(g.norm())) / float(g.norm()) for n, g in s['grads'].items() if float(g.norm()) > 1e-7)
+    print(f'cfg2@256 fast vs strict: z {rel(f["z"], s["z"]):.2e} recon {rel(f["recon"], s["recon"]):.2e} grad aggregate '
+          f'{(num / den) ** 0.5:.2e} worst norm {worst:.2e} idx equal {float((f["idx"] == s["idx"]).float().mean()):.4f}')
+    print(f'   l2 {f["l2"]:.6f} vs {s["l2"]:.6f}  q {f["q"]:.6f} vs {s["q"]:.6f}')
+    # the reconstruction also carries the code flips of the tie-heavy initial codebook (U(+-1/K): thousands of codes within
+    # 1e-5 of each other), hence the wider bar than on the latents
+    assert rel(f['z'], s['z']) < 3e-2 and rel(f['recon'], s['recon']) < 1e-1
+    assert abs(f['l2'] - s['l2']) <= 2e-2 * s['l2'] and abs(f['q'] - s['q']) <= 5e-2 * abs(s['q']) + 1e-4
+    assert float((f['idx'] == s['idx']).float().mean()) >= 0.90
+    assert (num / den) ** 0.5 < 5e-2 and worst < 0.10
