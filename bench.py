@@ -190,8 +190,13 @@ def cpu_reference_step(name: str, batch: int, image_size: int, codebook: int, st
     sd = oinit.init_state(qtype, codebook, q_conf['embedding_dim'], ae_conf['channels'], ae_conf['num_res_blocks'],
                           tuple(ae_conf['channel_multipliers']), seed=1234, criterion=crit, image_size=image_size)
     sd = oinit.make_leaf(sd, qtype)
+    def num(v):                                    # PyYAML reads '1e-5' (no dot) as a string; the model casts with float() too
+        try:
+            return float(v) if isinstance(v, str) else v
+        except ValueError:
+            return v
     cfg = {'num_res_blocks': ae_conf['num_res_blocks'], 'channel_multipliers': tuple(ae_conf['channel_multipliers']),
-           'quantizer': dict(q_conf.get('params') or {}, type=qtype)}
+           'quantizer': dict({k: num(v) for k, v in (q_conf.get('params') or {}).items()}, type=qtype)}
     opts = G.configure_optimizers(sd, t_conf, gan=(crit == 'gan'))
     x = torch.rand(batch, 3, image_size, image_size)
     times = []
@@ -425,10 +430,15 @@ def main():
     subs = {}
     strict = None
     if args.config == 'cfg2' and not args.only_headline and not args.batch and not args.codebook and args.image_size == 256:
+        def guarded(*a):                           # a failing sub-record must not take the headline line with it
+            try:
+                return run_workload(*a)
+            except BaseException as e:                # incl. SystemExit from the loss check
+                return {'error': f'{type(e).__name__}: {e}'[:400]}
         for name in ('cfg3', 'cfg4', 'cfg5'):
-            subs[name] = run_workload(name, args, pkg, dev, rank, world, precision, args.steps, args.warmup, stamp)
+            subs[name] = guarded(name, args, pkg, dev, rank, world, precision, args.steps, args.warmup, stamp)
         if precision == 'fast':
-            strict = run_workload('cfg2', args, pkg, dev, rank, world, 'strict', min(args.steps, 3), 3, stamp)
+            strict = guarded('cfg2', args, pkg, dev, rank, world, 'strict', min(args.steps, 3), 3, stamp)
 
     if rank == 0:
         pk, pk_kind = peaks()
@@ -461,10 +471,13 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             codebook = args.codebook or WORKLOADS[args.config]['codebook']
-            ips, sec = cpu_reference_step(args.config, args.cpu_batch, args.image_size, codebook, args.cpu_steps, 1, threads)
-            line['cpu_baseline'] = {'value': ips, 'unit': UNIT, 'cores': threads, 'kind': 'port',
-                                    'sample': f'{args.cpu_steps} steps x {args.cpu_batch} images ({sec:.1f} s/step), oracle port of the '
-                                              f'reference modules, fp32 torch CPU'}
+            try:
+                ips, sec = cpu_reference_step(args.config, args.cpu_batch, args.image_size, codebook, args.cpu_steps, 1, threads)
+                line['cpu_baseline'] = {'value': ips, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                                        'sample': f'{args.cpu_steps} steps x {args.cpu_batch} images ({sec:.1f} s/step), oracle port of the '
+                                                  f'reference modules, fp32 torch CPU'}
+            except Exception as e:
+                line['cpu_baseline'] = {'value': None, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'error': str(e)[:300]}
         out.write(json.dumps(line) + '\n'); out.flush()
     if world > 1:
         dist.destroy_process_group()
