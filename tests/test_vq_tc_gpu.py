@@ -1,6 +1,7 @@
 """GPU: the tensor-core nearest-code search (bf16 hi/lo split + exact fp32 re-evaluation of near-ties) must return the
-same indices as the exact fp32 kernel -- bit-exact for tie-free codebooks, and via the exact fallback for the reference's
-tie-heavy U(+-1/K) initial codebook."""
+same indices as the exact fp32 kernel -- bit-exact for tie-free codebooks, and via the exact re-rank for the reference's
+tie-heavy U(+-1/K) initial codebook.  Both tensor-core forms are covered: the one-launch fused kernel (vqb_vq_fused, the
+product path) and the round-1 multi-launch path (vqb_vq_assign_tc, kept for A/B measurements)."""
 import pytest
 import torch
 
@@ -19,9 +20,11 @@ def V():
     return pkg
 
 
+@pytest.mark.parametrize('mode', ['fused', 'legacy'])
 @pytest.mark.parametrize('N,K,D,init', [(4096, 1024, 256, 'normal'), (4096, 1024, 256, 'uniform'), (1000, 512, 64, 'normal'),
-                                        (16384, 1024, 256, 'normal'), (2048, 8192, 256, 'normal'), (300, 264, 128, 'trained')])
-def test_tc_search_equals_exact_kernel(V, N, K, D, init):
+                                        (16384, 1024, 256, 'normal'), (2048, 8192, 256, 'normal'), (300, 264, 128, 'trained'),
+                                        (129, 8, 192, 'normal'), (257, 40, 64, 'uniform')])
+def test_tc_search_equals_exact_kernel(V, N, K, D, init, mode):
     torch.manual_seed(9)
     z = torch.randn(N, D).cuda()
     if init == 'uniform':
@@ -31,7 +34,7 @@ def test_tc_search_equals_exact_kernel(V, N, K, D, init):
     else:
         cb = torch.randn(K, D).cuda()
     q0, i0, s0, c0, w0 = V.ops.vq_assign_raw(z, cb, 0, True, True, use_tc=False)
-    q1, i1, s1, c1, w1 = V.ops.vq_assign_raw(z, cb, 0, True, True, use_tc=True)
+    q1, i1, s1, c1, w1 = V.ops.vq_assign_raw(z, cb, 0, True, True, use_tc=mode)
     und = int(V.ops.vq_assign_raw.last_undecided)
     assert torch.equal(i0, i1), (int((i0 != i1).sum()), und)
     assert torch.equal(q0, q1)
@@ -56,6 +59,56 @@ def test_tc_search_entropy_order_and_fixture(V):
     cb.uniform_(-1 / K, 1 / K); cb.normal_()
     z = torch.randn(N // 256, D, 16, 16)
     flat = z.permute(0, 2, 3, 1).reshape(N, D).contiguous().cuda()
-    for order in (0, 1):
-        _, idx, _, _, _ = V.ops.vq_assign_raw(flat, cb.cuda(), order, False, False, use_tc=True)
-        assert torch.equal(idx.cpu().int(), torch.from_numpy(g['idx']).int())       # bit-exact vs the reference module's indices
+    for mode in ('fused', 'legacy'):
+        for order in (0, 1):
+            _, idx, _, _, _ = V.ops.vq_assign_raw(flat, cb.cuda(), order, False, False, use_tc=mode)
+            assert torch.equal(idx.cpu().int(), torch.from_numpy(g['idx']).int())   # bit-exact vs the reference module's indices
+
+
+def test_fused_duplicate_codes_take_first_index(V):
+    """degenerate codebook: every code duplicated 40 times -> far more exact ties than the candidate list holds (overflow ->
+    exact scan of the whole codebook): first-index semantics of torch.argmin, identical to the strict kernel"""
+    torch.manual_seed(4)
+    N, K, D = 600, 320, 128
+    base = torch.randn(8, D)
+    cb = base.repeat_interleave(40, dim=0).cuda()
+    z = torch.randn(N, D).cuda()
+    q0, i0, s0, c0, w0 = V.ops.vq_assign_raw(z, cb, 0, True, True, use_tc=False)
+    q1, i1, s1, c1, w1 = V.ops.vq_assign_raw(z, cb, 0, True, True, use_tc='fused')
+    assert torch.equal(i0, i1) and torch.equal(q0, q1) and torch.equal(c0, c1)
+    assert int((i1 % 40 != 0).sum()) == 0                       # always the first of the 40 identical codes
+    assert int(V.ops.vq_assign_raw.last_undecided) == N
+
+
+def test_fused_prep_cache_follows_the_codebook(V):
+    """the quantizer modules cache the bf16 split of their codebook: an in-place change (optimizer step, EMA update, re-init)
+    must invalidate it"""
+    from vqvae_vqgan_pytorch_lightning_b200.modules.vector_quantizers import EMAVectorQuantizer, VectorQuantizer
+    V.set_precision('fast')
+    try:
+        torch.manual_seed(5)
+        x = torch.randn(4, 64, 8, 8).cuda().contiguous(memory_format=torch.channels_last)
+        for cls in (VectorQuantizer, EMAVectorQuantizer):
+            q = cls(128, 64).cuda().train()
+            with torch.no_grad():
+                q.codebook.weight.normal_()
+                if cls is EMAVectorQuantizer:
+                    q.ema_weight.copy_(q.codebook.weight); q.ema_count.fill_(1.0)
+            for _ in range(3):
+                _, idx, _ = q(x)
+                ref = V.ops.vq_assign_raw(x.permute(0, 2, 3, 1).reshape(-1, 64), q.codebook.weight.detach().clone(), 0, False, False,
+                                          use_tc=False)[1] if cls is VectorQuantizer else None
+                if ref is not None:
+                    assert torch.equal(idx.reshape(-1), ref)
+                with torch.no_grad():
+                    q.codebook.weight.add_(0.3 * torch.randn_like(q.codebook.weight))      # bumps the autograd version
+            # EMA: the update kernel rewrites the codebook behind autograd's back and refreshes the cached split itself
+            if cls is EMAVectorQuantizer:
+                _, idx1, _ = q(x)                                 # runs an EMA update -> new codebook
+                cb_now = q.codebook.weight.detach().clone()
+                q.eval()
+                _, idx2, _ = q(x)
+                ref = V.ops.vq_assign_raw(x.permute(0, 2, 3, 1).reshape(-1, 64), cb_now, 0, False, False, use_tc=False)[1]
+                assert torch.equal(idx2.reshape(-1), ref)
+    finally:
+        V.set_precision('strict')

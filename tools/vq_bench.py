@@ -29,10 +29,16 @@ for (N, K) in ((16384, 1024), (8192, 8192)):
         z = torch.randn(N, D, device='cuda')
         cb = (torch.empty(K, D).uniform_(-1 / K, 1 / K) if init == 'uniform' else torch.randn(K, D)).cuda()
         nbytes = 4 * N * D * 2 + 4 * K * D + 8 * N + 8 * K + 12 * K * D
-        for tc in (False, True):
-            us = timeit(lambda: pkg.ops.vq_assign_raw(z, cb, 0, True, True, use_tc=tc))
+        prep = pkg.ops.CodebookPrep(); prep.get(cb)                        # cached split, as the quantizer modules hold it
+        for tc in (False, 'legacy', 'fused', 'fused+prep'):
+            if tc == 'fused+prep':
+                us = timeit(lambda: pkg.ops.vq_assign_raw(z, cb, 0, True, True, use_tc='fused'))          # split launch included
+            else:
+                us = timeit(lambda: pkg.ops.vq_assign_raw(z, cb, 0, True, True, use_tc=tc, prep=prep if tc == 'fused' else None))
             und = int(pkg.ops.vq_assign_raw.last_undecided) if tc else N
-            r = dict(N=N, K=K, init=init, kernel='tcgen05+exact-rerank' if tc else 'fp32-simt', us=round(us, 1),
+            r = dict(N=N, K=K, init=init, kernel={False: 'fp32-simt', 'legacy': 'r01 tcgen05 search + exact rows (8 launches)',
+                                                  'fused': 'vq_fused (1 launch, cached codebook split)',
+                                                  'fused+prep': 'vq_fused + codebook split (2 launches)'}[tc], us=round(us, 1),
                      gbs=round(nbytes / us / 1e3, 1), frac_hbm=round(nbytes / us / 1e3 / PEAK, 4), undecided_rows=und,
                      tflops=round(2.0 * N * K * D * (3 if tc else 1) / us / 1e6, 1))
             rows.append(r); print(json.dumps(r), flush=True)

@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libvqgan_b200.so')
-SOURCES = ['elementwise.cu', 'groupnorm.cu', 'conv_simt.cu', 'conv_tc.cu', 'conv_api.cu', 'vq.cu', 'vq_tc.cu', 'vq_entropy.cu', 'gan_ops.cu', 'gan_resample.cu', 'augment.cu']
+SOURCES = ['elementwise.cu', 'groupnorm.cu', 'conv_simt.cu', 'conv_tc.cu', 'conv_api.cu', 'vq.cu', 'vq_tc.cu', 'vq_fused.cu', 'vq_entropy.cu', 'gan_ops.cu', 'gan_resample.cu', 'augment.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '--use_fast_math=false',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-O2']
 

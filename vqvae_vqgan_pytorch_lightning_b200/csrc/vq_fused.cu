@@ -1,0 +1,528 @@
+// ONE-launch vector quantisation (reference: VectorQuantizer.forward / EMAVectorQuantizer.forward,
+// vqvae/modules/vector_quantizers.py:23-61, 128-180; EntropyVectorQuantizer's argmin part :337-343):
+//   pairwise L2 distance of N latents against the K x D codebook -> argmin -> gather -> straight-through value -> sum (e-z)^2
+//   -> code histogram -> EMA cluster sums, with the exact-index contract of the strict kernel (vq.cu: fp32 distances in the
+//   reference's operation order, first-index ties).
+//
+// Structure (cluster of 2 CTAs = 256 latent rows, tcgen05 cta_group::2, 10 warps per CTA):
+//   prologue   warps 2-9 read this CTA's 128 z rows ONCE from HBM (fp32, coalesced), split every value into bf16 hi + lo
+//              (16 mantissa bits together) and write both straight into the UMMA K-major SWIZZLE_128B layout in shared
+//              memory, where they stay for the whole kernel (A operand, 2 x 64 KB at D = 256); |z|^2 comes from the same pass.
+//   warp 0     streams the pre-split codebook (hi / lo bf16, prepared once per codebook version by vq_prep_codebook or by the
+//              EMA update itself) through a 4-stage TMA ring; each CTA stages only HALF of every 256-code tile (16 KB).
+//   warp 1     (leader CTA) issues M = 256, N = 256 UMMAs: dot = zh.eh + zl.eh + zh.el in fp32 TMEM accumulators, double
+//              buffered (2 x 256 columns); three bf16 products give the dot products to ~2^-16 relative.
+//   warps 2-9  scan each accumulator tile: d~ = |e|^2 - 2 dot, running minimum, and an online CANDIDATE LIST per row: every
+//              code whose d~ is within a rigorous error bound of the running minimum (a superset of the codes within the
+//              bound of the final minimum).  After the last tile a row with a single surviving candidate is decided; for the
+//              others (true fp32 near-ties, e.g. the reference's U(+-1/K) initial codebook) the survivors -- and only
+//              they -- are re-evaluated EXACTLY (sequential fp32 FMA chain, (|z|^2 + |e|^2) - 2 dot, the strict kernel's
+//              arithmetic bit for bit), so the indices equal the strict kernel's in every case.
+//   finish     same warps, same launch: idx (int64), q = z + (e - z), sum (e-z)^2, histogram and EMA cluster sums
+//              (vector red.global.add), z re-read from L2.
+//
+// Roofline: algorithmic bytes 4ND + 4KD + 4ND + 8N (+8K + 12KD); tensor work 3 x 2NKD FLOP.  At K = 1024 the
+// op sits at the bf16 ridge; the exact-index contract (three bf16 products) makes it tensor-bound, not HBM-bound.
+#include "common.cuh"
+#include "ptx.cuh"
+#include <mutex>
+
+namespace {
+
+constexpr int TM = 128;          // latent rows per CTA (256 per cluster)
+constexpr int TN = 256;          // codes per accumulator tile (128 staged per CTA)
+constexpr int TK = 64;           // k elements per shared-memory tile row (128 bytes)
+constexpr int NTH = 320;         // warp 0 TMA, warp 1 MMA, warps 2-9 prologue / scan / exact / finish
+constexpr int ESTAGES = 4;
+constexpr int CAP = 16;          // candidate-list entries per (row, column half)
+constexpr int Z_TILE = TM * TK * 2;          // 16 KB
+constexpr int E_TILE = (TN / 2) * TK * 2;    // 16 KB (this CTA's half)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode3() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+int make_code_map(CUtensorMap* m, const void* base, int64_t rows, int cols, int box_rows) {
+    EncodeTiledFn enc = get_encode3();
+    if (!enc) { vqb_set_error("cuTensorMapEncodeTiled unavailable"); return VQB_ERR_CUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { vqb_set_error("cuTensorMapEncodeTiled(vq_fused) failed: %d", (int)r); return VQB_ERR_CUDA; }
+    return VQB_OK;
+}
+
+// codebook fp32 [K][D] -> hi, lo bf16 [K][D] and sq[k] = |e_k|^2 with EXACTLY the summation of row_sqnorm_kernel (vq.cu):
+// lane-strided fp32 FMA chains, then the xor butterfly -- the strict kernel and the exact re-rank below read the same values.
+__device__ __forceinline__ void split_row(const float* __restrict__ x, bf16* __restrict__ hi, bf16* __restrict__ lo,
+                                          float* __restrict__ sq, int64_t row, int D, int lane) {
+    float s = 0.f;
+    for (int d = lane; d < D; d += 32) {
+        const float v = x[row * D + d];
+        const bf16 h = __float2bfloat16_rn(v);
+        hi[row * D + d] = h;
+        lo[row * D + d] = __float2bfloat16_rn(v - __bfloat162float(h));
+        s = fmaf(v, v, s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) sq[row] = s;
+}
+
+__global__ void vq_prep_codebook_kernel(const float* __restrict__ cb, bf16* __restrict__ hi, bf16* __restrict__ lo,
+                                        float* __restrict__ sq, int K, int D) {
+    const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (row < K) split_row(cb, hi, lo, sq, row, D, threadIdx.x & 31);
+}
+
+// EMA state update (vector_quantizers.py:158-169, same arithmetic as vq_ema_update_kernel in vq.cu) that also leaves the
+// NEW codebook split for the next step's search: no separate preparation launch on the EMA path.
+__global__ void vq_ema_update_prep_kernel(float* __restrict__ ema_count, float* __restrict__ ema_weight, float* __restrict__ cb,
+                                          const float* __restrict__ counts, const float* __restrict__ dw, bf16* __restrict__ hi,
+                                          bf16* __restrict__ lo, float* __restrict__ sq, int K, int D, float decay, float eps, float batch) {
+    const int code = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (code >= K) return;
+    const float c = ema_count[code] * decay + (1.0f - decay) * counts[code];
+    const float cnt = (c + eps) / (batch + (float)K * eps) * batch;
+    float s = 0.f;
+    for (int d = lane; d < D; d += 32) {
+        const int64_t o = (int64_t)code * D + d;
+        const float w = ema_weight[o] * decay + (1.0f - decay) * dw[o];
+        ema_weight[o] = w;
+        const float v = w / cnt;
+        cb[o] = v;
+        const bf16 h = __float2bfloat16_rn(v);
+        hi[o] = h;
+        lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
+        s = fmaf(v, v, s);
+    }
+    s = warp_sum(s);
+    __syncwarp();
+    if (lane == 0) { ema_count[code] = cnt; sq[code] = s; }
+}
+
+struct FusedParams {
+    int64_t N;
+    int K, D, kchunks, ctiles, order;
+    const float* z;              // [N][D] fp32
+    const float* cb;             // [K][D] fp32
+    const float* cb_sq;          // [K]
+    float* q_out;                // [N][D] or NULL
+    int64_t* idx_out;            // [N]
+    double* sse;                 // [1] or NULL
+    float* counts;               // [K] or NULL
+    float* dw;                   // [K][D] or NULL
+    int* undecided;              // [1] or NULL: rows that took the exact path
+};
+
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "WAITC_%=:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONEC_%=;\n\t"
+        "bra WAITC_%=;\n\t"
+        "DONEC_%=:\n\t}" ::"r"(ptx::smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// exact fp32 distance of one (row, code) pair with the strict kernel's arithmetic (vq.cu: vq_assign_tile): |z|^2 from four
+// interleaved FMA chains combined as (s0+s1)+(s2+s3), the dot product as ONE sequential FMA chain over d, then the
+// reference's operation order.  z_sq does not depend on the code; it is recomputed here so that every lane holds it.
+__device__ __forceinline__ float exact_distance(const float* __restrict__ zrow, const float* __restrict__ erow, float e2, int D, int order) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, acc = 0.f;
+    for (int d = 0; d < D; d += 4) {
+        const float4 zv = *reinterpret_cast<const float4*>(zrow + d);
+        const float4 ev = __ldg(reinterpret_cast<const float4*>(erow + d));
+        s0 = __fmaf_rn(zv.x, zv.x, s0); s1 = __fmaf_rn(zv.y, zv.y, s1); s2 = __fmaf_rn(zv.z, zv.z, s2); s3 = __fmaf_rn(zv.w, zv.w, s3);
+        acc = __fmaf_rn(zv.x, ev.x, acc); acc = __fmaf_rn(zv.y, ev.y, acc); acc = __fmaf_rn(zv.z, ev.z, acc); acc = __fmaf_rn(zv.w, ev.w, acc);
+    }
+    const float zsq = __fadd_rn(__fadd_rn(s0, s1), __fadd_rn(s2, s3));
+    const float two_dot = __fmul_rn(2.0f, acc);
+    return (order == 0) ? __fsub_rn(__fadd_rn(zsq, e2), two_dot) : __fadd_rn(__fsub_rn(zsq, two_dot), e2);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTH, 1)
+vq_fused_kernel(const __grid_constant__ CUtensorMap tmEh, const __grid_constant__ CUtensorMap tmEl, const FusedParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smemZ = smem;                                               // [2 (hi, lo)][kchunks] tiles of [128 rows][64 k] bf16
+    uint8_t* smemE = smemZ + (size_t)2 * p.kchunks * Z_TILE;             // [ESTAGES] tiles of [128 codes][64 k] bf16
+    float* cand_d = reinterpret_cast<float*>(smemE + (size_t)ESTAGES * E_TILE);      // [CAP][256]
+    uint16_t* cand_c = reinterpret_cast<uint16_t*>(cand_d + CAP * 256);              // [CAP][256]
+    float* e2_s = reinterpret_cast<float*>(cand_c + CAP * 256);                       // [2][256] code norms of the tile in flight
+    float* zsq_s = e2_s + 2 * TN;                                        // [128] |z|^2 (approximate order; threshold only)
+    float* rbest = zsq_s + TM;                                           // [2][128] running minimum per (half, row)
+    int* rcode = reinterpret_cast<int*>(rbest + 2 * TM);                 // [128] final code per row (second half unused)
+    int* rcnt = rcode + 2 * TM;                                          // [2][128] list length, bit 31 = overflow
+    float* red_s = reinterpret_cast<float*>(rcnt + 2 * TM);              // [8] per-warp partial sums, [8] emax
+    uint64_t* zfull = reinterpret_cast<uint64_t*>(red_s + 16);
+    uint64_t* efull = zfull + 1;                                          // [ESTAGES] (the leader's are used)
+    uint64_t* eempty = efull + ESTAGES;                                   // [ESTAGES]
+    uint64_t* tfull = eempty + ESTAGES;                                   // [2]
+    uint64_t* tempty = tfull + 2;                                         // [2] (the leader's are used)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = ptx::cluster_ctarank();
+    const int64_t r0 = (int64_t)blockIdx.x * TM;                          // blockIdx.x = 2 * cluster + rank
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmEh); ptx::prefetch_tmap(&tmEl);
+        ptx::mbar_init(zfull, 2);                                          // one arrival per CTA of the pair
+        for (int i = 0; i < ESTAGES; ++i) { ptx::mbar_init(&efull[i], 1); ptx::mbar_init(&eempty[i], 1); }
+        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull[i], 1); ptx::mbar_init(&tempty[i], 16); }      // 8 scan warps x 2 CTAs
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) ptx::tmem_alloc2(tmem_slot, 512);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync();                              // barriers and TMEM of BOTH CTAs exist before any remote signal
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ---- codebook stream: this CTA's 128-code half of every (tile j, k chunk c, hi | lo) stage ----------------------
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (int j = 0; j < p.ctiles; ++j)
+                for (int c = 0; c < p.kchunks; ++c)
+                    for (int hl = 0; hl < 2; ++hl) {
+                        ptx::mbar_wait(&eempty[s], ph ^ 1);
+                        if (rank == 0) ptx::mbar_expect_tx(&efull[s], 2u * (uint32_t)E_TILE);
+                        ptx::tma_load_2d_2sm(smemE + (size_t)s * E_TILE, hl ? &tmEl : &tmEh, ptx::mapa_rank(ptx::smem_u32(&efull[s]), 0),
+                                             c * TK, j * TN + (int)rank * (TN / 2));
+                        if (++s == ESTAGES) { s = 0; ph ^= 1; }
+                    }
+        }
+    } else if (warp == 1) {
+        // ---- MMA issue (leader CTA only): M = 256 rows (128 per CTA), N = 256 codes (128 staged per CTA) -----------------
+        if (lane == 0 && rank == 0) {
+            const uint32_t idesc = ptx::umma_idesc_bf16(2 * TM, TN, 0, 0);
+            mbar_wait_cluster(zfull, 0);
+            ptx::tc_fence_after();
+            int s = 0; uint32_t ph = 0;
+            int as = 0; uint32_t aph = 0;
+            for (int j = 0; j < p.ctiles; ++j) {
+                ptx::mbar_wait(&tempty[as], aph ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * TN);
+                uint32_t first = 1;
+                for (int c = 0; c < p.kchunks; ++c)
+                    for (int hl = 0; hl < 2; ++hl) {
+                        ptx::mbar_wait(&efull[s], ph);
+                        ptx::tc_fence_after();
+                        const uint64_t bdesc = ptx::umma_smem_desc(ptx::smem_u32(smemE + (size_t)s * E_TILE), 0, 1024);
+                        const uint64_t zh = ptx::umma_smem_desc(ptx::smem_u32(smemZ + (size_t)c * Z_TILE), 0, 1024);
+                        const uint64_t zl = ptx::umma_smem_desc(ptx::smem_u32(smemZ + (size_t)(p.kchunks + c) * Z_TILE), 0, 1024);
+#pragma unroll
+                        for (int k = 0; k < TK / 16; ++k) {
+                            ptx::umma2_bf16(d_tmem, zh + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, first ? 0u : 1u);   // zh.eh | zh.el
+                            first = 0;
+                            if (hl == 0) ptx::umma2_bf16(d_tmem, zl + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, 1u);    // zl.eh
+                        }
+                        ptx::umma2_commit(&eempty[s]);
+                        if (++s == ESTAGES) { s = 0; ph ^= 1; }
+                    }
+                ptx::umma2_commit(&tfull[as]);
+                if (++as == 2) { as = 0; aph ^= 1; }
+            }
+        }
+    } else {
+        const int ew = warp - 2;                                            // 0..7
+        const int et = ew * 32 + lane;                                      // 0..255
+        // ---- prologue: z rows -> bf16 hi / lo in the UMMA K-major SWIZZLE_128B layout (resident), |z|^2 ------------------
+        // one warp per row and iteration: lane L owns k = 8L .. 8L+7 (one 16-byte chunk of the hi and of the lo tile)
+        {
+            const int cidx = lane >> 3, j16 = lane & 7;
+            for (int rr = 0; rr < TM / 8; rr += 4) {
+                float4 v[4][2];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int row = ew * (TM / 8) + rr + u;
+                    const int64_t g = r0 + row;
+                    v[u][0] = v[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (g < p.N && lane * 8 < p.D) {
+                        const float4* src = reinterpret_cast<const float4*>(p.z + g * p.D + lane * 8);
+                        v[u][0] = src[0]; v[u][1] = src[1];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int row = ew * (TM / 8) + rr + u;
+                    const float f[8] = {v[u][0].x, v[u][0].y, v[u][0].z, v[u][0].w, v[u][1].x, v[u][1].y, v[u][1].z, v[u][1].w};
+                    uint32_t hw[4], lw[4];
+                    float s = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const bf16 h0 = __float2bfloat16_rn(f[2 * i]), h1 = __float2bfloat16_rn(f[2 * i + 1]);
+                        const bf16 l0 = __float2bfloat16_rn(f[2 * i] - __bfloat162float(h0));
+                        const bf16 l1 = __float2bfloat16_rn(f[2 * i + 1] - __bfloat162float(h1));
+                        hw[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                        lw[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                        s = fmaf(f[2 * i], f[2 * i], s); s = fmaf(f[2 * i + 1], f[2 * i + 1], s);
+                    }
+                    if (lane * 8 < p.D) {
+                        const uint32_t off = (uint32_t)row * 128u + (uint32_t)((j16 ^ (row & 7)) << 4);
+                        *reinterpret_cast<uint4*>(smemZ + (size_t)cidx * Z_TILE + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                        *reinterpret_cast<uint4*>(smemZ + (size_t)(p.kchunks + cidx) * Z_TILE + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                    }
+                    s = warp_sum(s);
+                    if (lane == 0) zsq_s[row] = s;
+                }
+            }
+            // largest code norm (threshold only): every CTA scans the K norms once (L2-resident, 4 KB at K = 1024)
+            float m = 0.f;
+            for (int k = et; k < p.K; k += 256) m = fmaxf(m, p.cb_sq[k]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            if (lane == 0) red_s[8 + ew] = m;
+            fence_proxy_async_smem();                                       // generic-proxy stores -> visible to the UMMA (async proxy)
+            epi_sync();
+            if (et == 0) ptx::mbar_arrive_cluster(ptx::mapa_rank(ptx::smem_u32(zfull), 0));
+        }
+        float emax = red_s[8];
+#pragma unroll
+        for (int i = 1; i < 8; ++i) emax = fmaxf(emax, red_s[8 + i]);
+
+        // ---- scan: running minimum + online candidate list per (row, column half) -----------------------------------------
+        const int quarter = warp & 3, half = ew >> 2;
+        const int row = quarter * 32 + lane;
+        const int slot = half * TM + row;
+        const float zs = zsq_s[row];
+        // |d~ - d| <= 2 (3 * 2^-18 + 2^-16) |z||e| on the distance; 4x safety factor, plus the fp32 evaluation's own rounding
+        // band so that genuine fp32 near-ties always reach the exact re-rank (same threshold as vq_tc_decide_kernel)
+        const float thr = 4.8828125e-4f * sqrtf(zs * emax) + 1e-5f * (zs + emax);
+        float b1 = INFINITY; int bi = 0x7fffffff;
+        int cnt = 0, ovf = 0;
+        int as = 0; uint32_t aph = 0;
+        for (int j = 0; j < p.ctiles; ++j) {
+            {   // code norms of this tile (the previous use of e2_s[as] finished before tempty[as] was arrived two tiles ago)
+                const int code = j * TN + et;
+                e2_s[as * TN + et] = (code < p.K) ? p.cb_sq[code] : INFINITY;
+            }
+            epi_sync();
+            ptx::mbar_wait(&tfull[as], aph);
+            ptx::tc_fence_after();
+            const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * TN);
+            for (int c = half * 32; c < TN; c += 64) {
+                uint32_t r[32];
+                ptx::tmem_ld32(t_addr + (uint32_t)c, r);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int u = 0; u < 32; ++u) {
+                    const float d = fmaf(-2.0f, __uint_as_float(r[u]), e2_s[as * TN + c + u]);
+                    if (d <= b1 + thr) {                                     // rare: a new minimum or a near-tie of the running one
+                        const int code = j * TN + c + u;
+                        if (d < b1) { b1 = d; bi = code; }
+                        if (cnt == CAP) {                                    // compact against the current bound before giving up
+                            int m = 0;
+                            for (int i = 0; i < CAP; ++i) {
+                                const float di = cand_d[i * 256 + slot];
+                                if (di <= b1 + thr) { cand_d[m * 256 + slot] = di; cand_c[m * 256 + slot] = cand_c[i * 256 + slot]; ++m; }
+                            }
+                            cnt = m;
+                        }
+                        if (cnt < CAP) { cand_d[cnt * 256 + slot] = d; cand_c[cnt * 256 + slot] = (uint16_t)code; ++cnt; }
+                        else ovf = 1;
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa_rank(ptx::smem_u32(&tempty[as]), 0));
+            if (++as == 2) { as = 0; aph ^= 1; }
+        }
+        rbest[slot] = b1; rcnt[slot] = cnt | (ovf << 31);
+        (void)bi;
+        epi_sync();
+
+        // ---- decide / exact re-rank / finish: one warp per row ------------------------------------------------------------
+        float sse_local = 0.f;
+        int undecided_local = 0;
+        for (int rr = 0; rr < TM / 8; ++rr) {
+            const int rw = ew * (TM / 8) + rr;
+            const int64_t g = r0 + rw;
+            if (g >= p.N) break;
+            const float* zrow = p.z + g * p.D;
+            const float ba = rbest[rw], bb = rbest[TM + rw];
+            const float best = fminf(ba, bb);
+            const float zr = zsq_s[rw];
+            const float bound = best + (4.8828125e-4f * sqrtf(zr * emax) + 1e-5f * (zr + emax));
+            const int na = rcnt[rw] & 0x7fffffff, nb = rcnt[TM + rw] & 0x7fffffff;
+            const bool overflow = ((rcnt[rw] | rcnt[TM + rw]) >> 31) != 0;
+            int code;
+            if (!overflow) {
+                float dme = INFINITY; int cme = 0x7fffffff;
+                if (lane < na) { dme = cand_d[lane * 256 + rw]; cme = cand_c[lane * 256 + rw]; }
+                else if (lane < na + nb) { dme = cand_d[(lane - na) * 256 + TM + rw]; cme = cand_c[(lane - na) * 256 + TM + rw]; }
+                const bool keep = dme <= bound;
+                const unsigned mask = __ballot_sync(0xffffffffu, keep);
+                if (__popc(mask) == 1) {
+                    code = __shfl_sync(0xffffffffu, cme, __ffs(mask) - 1);
+                } else {
+                    ++undecided_local;
+                    float dist = INFINITY;
+                    if (keep) dist = exact_distance(zrow, p.cb + (int64_t)cme * p.D, p.cb_sq[cme], p.D, p.order);
+                    int c2 = keep ? cme : 0x7fffffff;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const float od = __shfl_xor_sync(0xffffffffu, dist, o);
+                        const int oc = __shfl_xor_sync(0xffffffffu, c2, o);
+                        if (od < dist || (od == dist && oc < c2)) { dist = od; c2 = oc; }
+                    }
+                    code = c2;
+                }
+            } else {
+                // more near-ties than the list holds (degenerate codebooks: duplicated codes): exact scan of every code
+                ++undecided_local;
+                float dist = INFINITY; int c2 = 0x7fffffff;
+                for (int k = lane; k < p.K; k += 32) {
+                    const float dk = exact_distance(zrow, p.cb + (int64_t)k * p.D, p.cb_sq[k], p.D, p.order);
+                    if (dk < dist || (dk == dist && k < c2)) { dist = dk; c2 = k; }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float od = __shfl_xor_sync(0xffffffffu, dist, o);
+                    const int oc = __shfl_xor_sync(0xffffffffu, c2, o);
+                    if (od < dist || (od == dist && oc < c2)) { dist = od; c2 = oc; }
+                }
+                code = c2;
+            }
+            if (code < 0 || code >= p.K) code = 0;        // NaN rows: keep memory-safe (torch.argmin would return the NaN position)
+            if (lane == 0) {
+                rcode[rw] = code;
+                p.idx_out[g] = (int64_t)code;
+                if (p.counts) atomicAdd(p.counts + code, 1.0f);
+            }
+        }
+        __syncwarp();
+        // finish, four rows in flight per warp: q = z + (e - z), sum (e - z)^2, EMA cluster sums
+        for (int rr = 0; rr < TM / 8; rr += 4) {
+            float4 zv[4][2], ev[4][2];
+            int codes[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int rw = ew * (TM / 8) + rr + u;
+                const int64_t g = r0 + rw;
+                codes[u] = (g < p.N) ? rcode[rw] : -1;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int d = lane * 4 + h * 128;
+                    zv[u][h] = ev[u][h] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (codes[u] >= 0 && d < p.D) {
+                        zv[u][h] = *reinterpret_cast<const float4*>(p.z + g * p.D + d);
+                        ev[u][h] = __ldg(reinterpret_cast<const float4*>(p.cb + (int64_t)codes[u] * p.D + d));
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t g = r0 + ew * (TM / 8) + rr + u;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int d = lane * 4 + h * 128;
+                    if (codes[u] >= 0 && d < p.D) {
+                        const float4 z4 = zv[u][h], e4 = ev[u][h];
+                        const float4 df = make_float4(e4.x - z4.x, e4.y - z4.y, e4.z - z4.z, e4.w - z4.w);
+                        sse_local = fmaf(df.x, df.x, sse_local); sse_local = fmaf(df.y, df.y, sse_local);
+                        sse_local = fmaf(df.z, df.z, sse_local); sse_local = fmaf(df.w, df.w, sse_local);
+                        if (p.q_out)                                          // flat_x + (quantized - flat_x).detach()
+                            *reinterpret_cast<float4*>(p.q_out + g * p.D + d) = make_float4(z4.x + df.x, z4.y + df.y, z4.z + df.z, z4.w + df.w);
+                        if (p.dw) red_add_v4(p.dw + (int64_t)codes[u] * p.D + d, z4.x, z4.y, z4.z, z4.w);
+                    }
+                }
+            }
+        }
+        sse_local = warp_sum(sse_local);
+        if (lane == 0) red_s[ew] = sse_local;
+        undecided_local = __shfl_sync(0xffffffffu, undecided_local, 0);
+        epi_sync();
+        if (et == 0 && p.sse) {
+            double t = 0.0;
+            for (int i = 0; i < 8; ++i) t += (double)red_s[i];
+            atomicAdd(p.sse, t);
+        }
+        if (lane == 0 && p.undecided && undecided_local) atomicAdd(p.undecided, undecided_local);
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync();                              // the peer may still be reading this CTA's shared memory / TMEM until here
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc2(tmem_base, 512);
+    }
+}
+
+size_t fused_smem_bytes(int D) {
+    const int kchunks = D / TK;
+    return (size_t)2 * kchunks * Z_TILE + (size_t)ESTAGES * E_TILE + (size_t)CAP * 256 * 6 + (size_t)2 * TN * 4 + TM * 4 + 2 * TM * 4 * 3 +
+           16 * 4 + (1 + 2 * ESTAGES + 4) * 8 + 16 + 1024 + 64;
+}
+
+}  // namespace
+
+extern "C" int vqb_vq_prep_codebook(const float* codebook, void* cb_hi, void* cb_lo, float* cb_sq, int K, int D, void* stream) {
+    VQB_CHECK_ARG(codebook && cb_hi && cb_lo && cb_sq && K > 0 && D > 0, "vq_prep_codebook: bad arguments");
+    vq_prep_codebook_kernel<<<(unsigned)ceil_div64((int64_t)K * 32, 256), 256, 0, as_stream(stream)>>>(codebook, (bf16*)cb_hi, (bf16*)cb_lo,
+                                                                                                        cb_sq, K, D);
+    VQB_CHECK_LAUNCH("vq_prep_codebook");
+    return VQB_OK;
+}
+
+extern "C" int vqb_vq_ema_update_prep(float* ema_count, float* ema_weight, float* codebook, const float* counts, const float* dw,
+                                      void* cb_hi, void* cb_lo, float* cb_sq, int K, int D, float decay, float eps, float batch,
+                                      void* stream) {
+    VQB_CHECK_ARG(ema_count && ema_weight && codebook && counts && dw && cb_hi && cb_lo && cb_sq && K > 0 && D > 0,
+                  "vq_ema_update_prep: bad arguments");
+    vq_ema_update_prep_kernel<<<(unsigned)ceil_div64((int64_t)K * 32, 256), 256, 0, as_stream(stream)>>>(
+        ema_count, ema_weight, codebook, counts, dw, (bf16*)cb_hi, (bf16*)cb_lo, cb_sq, K, D, decay, eps, batch);
+    VQB_CHECK_LAUNCH("vq_ema_update_prep");
+    return VQB_OK;
+}
+
+extern "C" int vqb_vq_fused(const float* z, const float* codebook, const void* cb_hi, const void* cb_lo, const float* cb_sq,
+                            int order, float* q_out, int64_t* idx_out, double* sse, float* counts, float* dw, int64_t N, int K, int D,
+                            int* undecided_rows_out, void* stream) {
+    VQB_CHECK_ARG(z && codebook && cb_hi && cb_lo && cb_sq && idx_out, "vq_fused: null pointer");
+    VQB_CHECK_ARG(N > 0 && K > 0 && D > 0 && (order == 0 || order == 1), "vq_fused: bad arguments");
+    VQB_CHECK_ARG(D % 64 == 0 && D <= 256 && K % 8 == 0 && K <= 65528, "vq_fused: needs D %% 64 == 0, D <= 256, K %% 8 == 0, K <= 65528 (got D=%d K=%d)", D, K);
+    VQB_CHECK_ARG(N < (int64_t)1 << 31, "vq_fused: N too large");
+    cudaStream_t st = as_stream(stream);
+    CUtensorMap tmEh, tmEl;
+    int rc;
+    if ((rc = make_code_map(&tmEh, cb_hi, K, D, TN / 2))) return rc;
+    if ((rc = make_code_map(&tmEl, cb_lo, K, D, TN / 2))) return rc;
+    FusedParams fp;
+    fp.N = N; fp.K = K; fp.D = D; fp.kchunks = D / TK; fp.ctiles = (K + TN - 1) / TN; fp.order = order;
+    fp.z = z; fp.cb = codebook; fp.cb_sq = cb_sq; fp.q_out = q_out; fp.idx_out = idx_out; fp.sse = sse; fp.counts = counts; fp.dw = dw;
+    fp.undecided = undecided_rows_out;
+    const size_t smem = fused_smem_bytes(D);
+    if (smem > 227 * 1024) { vqb_set_error("vq_fused: D=%d does not fit the shared-memory budget (%zu B)", D, smem); return VQB_ERR_UNSUPPORTED; }
+    static std::once_flag attr_once;
+    std::call_once(attr_once, [] { cudaFuncSetAttribute(vq_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
+    const unsigned ctas = (unsigned)(2 * ceil_div64(N, 2 * TM));             // whole clusters (a cluster covers 256 rows)
+    vq_fused_kernel<<<ctas, NTH, smem, st>>>(tmEh, tmEl, fp);
+    VQB_CHECK_LAUNCH("vq_fused");
+    return VQB_OK;
+}

@@ -23,6 +23,7 @@ class BaseVectorQuantizer(ABC, nn.Module):
         # number of ranks (so that Laplace smoothing sees the GLOBAL image batch)
         self.stats_allreduce = None
         self.world_size = 1
+        self._prep = ops.CodebookPrep()           # cached bf16 split of the codebook for the fused search kernel
 
     def init_codebook(self) -> None:
         """uniform U(-1/K, 1/K) (base_quantizer.py:27-31)"""

@@ -17,12 +17,12 @@ class VectorQuantizer(BaseVectorQuantizer):
         self.commitment_cost = commitment_cost
 
     def forward(self, x: torch.Tensor):
-        q, idx, loss, _, _ = ops.vq_quantize(x, self.codebook.weight, 0, self.commitment_cost, 1.0, False)
+        q, idx, loss, _ = ops.vq_quantize(x, self.codebook.weight, 0, self.commitment_cost, 1.0, False, self._prep)
         return q, idx, loss
 
     @torch.no_grad()
     def vec_to_codes(self, x: torch.Tensor) -> torch.Tensor:
-        return ops.vq_codes(x, self.codebook.weight, 0)
+        return ops.vq_codes(x, self.codebook.weight, 0, self._prep)
 
 
 class EMAVectorQuantizer(BaseVectorQuantizer):
@@ -44,21 +44,23 @@ class EMAVectorQuantizer(BaseVectorQuantizer):
         self.epsilon = epsilon
 
     def forward(self, x: torch.Tensor):
-        q, idx, loss, counts, dw = ops.vq_quantize(x, self.codebook.weight, 0, self.commitment_cost, 0.0, self.training)
+        q, idx, loss, stats = ops.vq_quantize(x, self.codebook.weight, 0, self.commitment_cost, 0.0, self.training, self._prep)
         if self.training:
             with torch.no_grad():
                 batch = x.shape[0]
                 if self.stats_allreduce is not None:
-                    self.stats_allreduce(counts, dw)
+                    self.stats_allreduce(stats)             # ONE buffer [counts | dw]: a single all-reduce
                     batch = batch * self.world_size
+                k = self.num_embeddings
+                counts, dw = stats[:k], stats[k:].view(k, self.embedding_dim)
                 ops.vq_ema_update(self.ema_count, self.ema_weight.data, self.codebook.weight.data, counts, dw, self.decay,
-                                  self.epsilon, batch)
+                                  self.epsilon, batch, prep=self._prep)
                 ops.bump_weights_epoch()
         return q, idx, loss
 
     @torch.no_grad()
     def vec_to_codes(self, x: torch.Tensor) -> torch.Tensor:
-        return ops.vq_codes(x, self.codebook.weight, 0)
+        return ops.vq_codes(x, self.codebook.weight, 0, self._prep)
 
 
 class GumbelVectorQuantizer(BaseVectorQuantizer):
@@ -125,4 +127,4 @@ class EntropyVectorQuantizer(BaseVectorQuantizer):
 
     @torch.no_grad()
     def vec_to_codes(self, x: torch.Tensor) -> torch.Tensor:
-        return ops.vq_codes(x, self.codebook.weight, 1)
+        return ops.vq_codes(x, self.codebook.weight, 1, self._prep)

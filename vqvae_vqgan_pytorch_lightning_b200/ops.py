@@ -535,31 +535,90 @@ def mse_l1(a, b):
 # ------------------------------------------------------------------------------------------------------
 # vector quantisation
 # ------------------------------------------------------------------------------------------------------
+class CodebookPrep:
+    """bf16 hi / lo split and row norms of a codebook for the fused search (vqb_vq_fused), owned by a quantizer module and
+    refreshed only when the codebook changed: the key holds the parameter's autograd version, its address and -- for codebooks
+    an optimizer may rewrite behind autograd's back -- the global weights epoch.  The EMA update kernel refreshes the split
+    itself (vq_ema_update), so the EMA path never runs a separate preparation launch."""
+
+    def __init__(self):
+        self.key = None
+        self.hi = self.lo = self.sq = None
+
+    def _key(self, codebook: torch.Tensor):
+        return (codebook._version, codebook.data_ptr(), tuple(codebook.shape), _weights_epoch if codebook.requires_grad else -1)
+
+    def _alloc(self, codebook: torch.Tensor):
+        k, d = codebook.shape
+        if self.hi is None or self.hi.shape != (k, d) or self.hi.device != codebook.device:
+            self.hi = torch.empty(k, d, dtype=torch.bfloat16, device=codebook.device)
+            self.lo = torch.empty(k, d, dtype=torch.bfloat16, device=codebook.device)
+            self.sq = torch.empty(k, dtype=torch.float32, device=codebook.device)
+
+    def get(self, codebook: torch.Tensor):
+        key = self._key(codebook)
+        if key != self.key:
+            self._alloc(codebook)
+            cb = codebook.detach()
+            k, d = cb.shape
+            call('vqb_vq_prep_codebook', ptr(cb), ptr(self.hi), ptr(self.lo), ptr(self.sq), k, d, stream())
+            self.key = key
+        return self.hi, self.lo, self.sq
+
+    def mark_fresh(self, codebook: torch.Tensor):
+        self.key = self._key(codebook)
+
+
+def _fused_vq_ok(flat: torch.Tensor, k: int, d: int) -> bool:
+    return d % 64 == 0 and d <= 256 and k % 8 == 0 and k <= 65528
+
+
+def vq_stat_buffers(k: int, d: int, want_stats: bool, device):
+    """ONE zero-filled fp32 buffer [counts (K) | dw (K*D)] (a single fill launch, and a single all-reduce for the EMA
+    statistics under data parallelism) + the views into it."""
+    buf = torch.zeros(k + (k * d if want_stats else 0), dtype=torch.float32, device=device)
+    counts = buf[:k]
+    dw = buf[k:].view(k, d) if want_stats else None
+    return buf, counts, dw
+
+
 def vq_assign_raw(flat: torch.Tensor, codebook: torch.Tensor, order: int, want_q: bool = True, want_stats: bool = False,
-                  use_tc: Optional[bool] = None):
-    """flat [N,D] fp32, codebook [K,D] fp32 -> (q or None, idx int64 [N], sse double[1], counts [K] or None, dw [K,D] or None)."""
+                  use_tc=None, prep: Optional[CodebookPrep] = None):
+    """flat [N,D] fp32, codebook [K,D] fp32 -> (q or None, idx int64 [N], sse double[1], counts [K], dw [K,D] or None).
+    use_tc: None = by precision mode (fast -> the one-launch fused kernel), True / 'fused' = fused kernel, 'legacy' = the round-1
+    multi-launch tensor-core path (kept for A/B measurements), False = exact fp32 SIMT kernel (strict mode)."""
     n, d = flat.shape
     k = codebook.shape[0]
     dev = flat.device
     q = torch.empty_like(flat) if want_q else None
     idx = torch.empty(n, dtype=torch.int64, device=dev)
-    sse = torch.zeros(1, dtype=torch.float64, device=dev)
-    counts = torch.zeros(k, dtype=torch.float32, device=dev)
-    dw = torch.zeros(k, d, dtype=torch.float32, device=dev) if want_stats else None
+    stat_buf, counts, dw = vq_stat_buffers(k, d, want_stats, dev)
+    vq_assign_raw.last_stat_buffer = stat_buf
     if use_tc is None:
         use_tc = get_precision().name == 'fast'
+    if use_tc and use_tc != 'legacy' and _fused_vq_ok(flat, k, d):
+        scal = torch.zeros(2, dtype=torch.float64, device=dev)           # [sse | undecided-row counter (int32 in the low word)]
+        sse, und = scal[:1], scal[1:].view(torch.int32)[:1]
+        hi, lo, sq = (prep or CodebookPrep()).get(codebook)
+        cb = codebook.detach()
+        call('vqb_vq_fused', ptr(flat), ptr(cb), ptr(hi), ptr(lo), ptr(sq), order, ptr(q), ptr(idx), ptr(sse), ptr(counts), ptr(dw),
+             n, k, d, ptr(und), stream())
+        vq_assign_raw.last_undecided = und
+        return q, idx, sse, counts, dw
+    sse = torch.zeros(1, dtype=torch.float64, device=dev)
+    cb = codebook.detach()
     if use_tc and d % 64 == 0 and d <= 256 and k % 8 == 0 and k <= 8192:
-        # tensor-core search with exact fp32 re-evaluation of near-ties: same indices as the exact kernel
+        # round-1 path: tensor-core search + exact fp32 re-evaluation of near-tied rows over the whole code range (8 launches)
         ws_bytes = lib.load().vqb_vq_tc_workspace_bytes(n, k, d)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         und = torch.zeros(1, dtype=torch.int32, device=dev)
-        call('vqb_vq_assign_tc', ptr(flat), ptr(codebook), order, ptr(q), ptr(idx), ptr(sse), ptr(counts), ptr(dw), n, k, d, ptr(ws),
+        call('vqb_vq_assign_tc', ptr(flat), ptr(cb), order, ptr(q), ptr(idx), ptr(sse), ptr(counts), ptr(dw), n, k, d, ptr(ws),
              ws_bytes, ptr(und), stream())
         vq_assign_raw.last_undecided = und
         return q, idx, sse, counts, dw
     ws_bytes = lib.load().vqb_vq_workspace_bytes(n, k, d)
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
-    call('vqb_vq_assign', ptr(flat), ptr(codebook), order, ptr(q), ptr(idx), ptr(sse), ptr(counts), ptr(dw), n, k, d, ptr(ws),
+    call('vqb_vq_assign', ptr(flat), ptr(cb), order, ptr(q), ptr(idx), ptr(sse), ptr(counts), ptr(dw), n, k, d, ptr(ws),
          ws_bytes, stream())
     return q, idx, sse, counts, dw
 
@@ -568,29 +627,30 @@ class VQFn(torch.autograd.Function):
     """Fused nearest-code quantisation with straight-through estimator and the MSE latent losses.
 
     forward(z [B,D,h,w] channels-last fp32, codebook [K,D]) ->
-        (quantized [B,D,h,w], idx [B,h*w] int64, loss = (beta + cb_scale) * mean((e[idx]-z)^2), counts [K], dw [K,D] | None)
+        (quantized [B,D,h,w], idx [B,h*w] int64, loss = (beta + cb_scale) * mean((e[idx]-z)^2),
+         stats = ONE fp32 buffer [counts (K) | dw (K*D, only with want_stats)])
     reference: VectorQuantizer.forward vector_quantizers.py:23-61 (cb_scale=1), EMAVectorQuantizer.forward :128-180
     (cb_scale=0; the EMA state update itself is vqb_vq_ema_update, called by the module), EntropyVectorQuantizer :337-349.
     """
 
     @staticmethod
-    def forward(ctx, z, codebook, order, beta, cb_scale, want_stats):
+    def forward(ctx, z, codebook, order, beta, cb_scale, want_stats, prep=None):
         z = as_nhwc(z, torch.float32)
         b, d, h, w = z.shape
         flat = z.permute(0, 2, 3, 1).reshape(b * h * w, d)        # a view: channels-last memory is already (b h w) c
-        cb = codebook.detach().float().contiguous()
-        q, idx, sse, counts, dw = vq_assign_raw(flat, cb, order, True, want_stats)
+        if codebook.dtype != torch.float32 or not codebook.is_contiguous():
+            raise lib.VQBError('the codebook must be a contiguous fp32 tensor')
+        q, idx, sse, counts, dw = vq_assign_raw(flat, codebook, order, True, want_stats, prep=prep)
+        stats = vq_assign_raw.last_stat_buffer
         loss = (sse[0] * ((beta + cb_scale) / flat.numel())).float()
         ctx.save_for_backward(flat, q, idx)
         ctx.cfg = (beta, cb_scale, codebook.shape, z.shape)
         qz = q.reshape(b, h, w, d).permute(0, 3, 1, 2)             # logical NCHW, physical NHWC
-        ctx.mark_non_differentiable(idx, counts)
-        if dw is not None:
-            ctx.mark_non_differentiable(dw)
-        return qz, idx.reshape(b, h * w), loss, counts, dw
+        ctx.mark_non_differentiable(idx, stats)
+        return qz, idx.reshape(b, h * w), loss, stats
 
     @staticmethod
-    def backward(ctx, g_q, _g_idx, g_loss, _g_counts, _g_dw):
+    def backward(ctx, g_q, _g_idx, g_loss, _g_stats):
         flat, q, idx = ctx.saved_tensors
         beta, cb_scale, cb_shape, zshape = ctx.cfg
         n, d = flat.shape
@@ -602,24 +662,31 @@ class VQFn(torch.autograd.Function):
         call('vqb_vq_backward', ptr(flat), ptr(q), ptr(idx), ptr(gq), ptr(gl), beta, cb_scale, ptr(dz), ptr(dcb), n, k, d,
              stream())
         b, _, h, w = zshape
-        return dz.reshape(b, h, w, d).permute(0, 3, 1, 2), dcb, None, None, None, None
+        return dz.reshape(b, h, w, d).permute(0, 3, 1, 2), dcb, None, None, None, None, None
 
 
-def vq_quantize(z, codebook, order=0, beta=0.25, cb_scale=1.0, want_stats=False):
-    return VQFn.apply(z, codebook, order, beta, cb_scale, want_stats)
+def vq_quantize(z, codebook, order=0, beta=0.25, cb_scale=1.0, want_stats=False, prep=None):
+    return VQFn.apply(z, codebook, order, beta, cb_scale, want_stats, prep)
 
 
-def vq_codes(z, codebook, order=0):
+def vq_codes(z, codebook, order=0, prep=None):
     """argmin only (vec_to_codes, vector_quantizers.py:63-84,182-203,358-381) -> idx [B, h*w] int64."""
     z = as_nhwc(z.detach(), torch.float32)
     b, d, h, w = z.shape
     flat = z.permute(0, 2, 3, 1).reshape(b * h * w, d)
-    _, idx, _, _, _ = vq_assign_raw(flat, codebook.detach().float().contiguous(), order, False, False)
+    _, idx, _, _, _ = vq_assign_raw(flat, codebook, order, False, False, prep=prep)
     return idx.reshape(b, h * w)
 
 
-def vq_ema_update(ema_count, ema_weight, codebook, counts, dw, decay, eps, batch):
+def vq_ema_update(ema_count, ema_weight, codebook, counts, dw, decay, eps, batch, prep: Optional[CodebookPrep] = None):
+    """EMA state update; with `prep` (fast mode) the same launch leaves the bf16 split / norms of the NEW codebook in it."""
     k, d = codebook.shape
+    if prep is not None and get_precision().name == 'fast' and _fused_vq_ok(None, k, d):
+        prep._alloc(codebook)
+        call('vqb_vq_ema_update_prep', ptr(ema_count), ptr(ema_weight), ptr(codebook), ptr(counts), ptr(dw), ptr(prep.hi), ptr(prep.lo),
+             ptr(prep.sq), k, d, decay, eps, float(batch), stream())
+        prep.mark_fresh(codebook)
+        return
     call('vqb_vq_ema_update', ptr(ema_count), ptr(ema_weight), ptr(codebook), ptr(counts), ptr(dw), k, d, decay, eps,
          float(batch), stream())
 
