@@ -146,6 +146,20 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// Width of the band around the smallest APPROXIMATE distance inside which a code may still be the fp32 argmin.  With
+// d~ = |e|^2 - 2 (zh.eh + zl.eh + zh.el) from the tensor cores and d = the strict kernel's fp32 value (same |z|^2 and |e|^2
+// operands for every code of a row, so they cancel in comparisons):
+//   * split error: z = zh + zl and e = eh + el hold 16 mantissa bits each, the zl.el product is dropped: <= 3 * 2^-18 |z||e|
+//     on the dot product; TMEM accumulation over 48 k-steps x 3 products (not round-to-nearest): <= 2^-16 |z||e|;
+//     on the distance (x2) and for two codes (x2): 2^-14 * 1.75 |z||e|  -> covered 4x by 2^-11 |z||e|;
+//   * the fp32 evaluation itself: one rounding of (|z|^2 + |e|^2) and one of the subtraction, each <= 1 ulp of a value
+//     <= (|z|+|e|)^2 <= 2 (|z|^2+|e|^2), i.e. <= 2^-22 (|z|^2+|e|^2) per code, and the sequential 256-term FMA chain of the
+//     dot product, <= 256 * 2^-24 |z||e| (x2 on the distance); for two codes: 2^-21 (|z|^2+|e|^2) + 2^-14 |z||e|.
+// A code outside the band cannot have the smallest fp32 distance, hence cannot be the strict kernel's first-index argmin.
+__device__ __forceinline__ float tie_threshold(float zs, float emax) {
+    return (4.8828125e-4f + 6.103515625e-5f) * sqrtf(zs * emax) + 4.76837158203125e-7f * (zs + emax);
+}
+
 // exact fp32 distance of one (row, code) pair with the strict kernel's arithmetic (vq.cu: vq_assign_tile): |z|^2 from four
 // interleaved FMA chains combined as (s0+s1)+(s2+s3), the dot product as ONE sequential FMA chain over d, then the
 // reference's operation order.  z_sq does not depend on the code; it is recomputed here so that every lane holds it.
@@ -160,6 +174,26 @@ __device__ __forceinline__ float exact_distance(const float* __restrict__ zrow, 
     const float zsq = __fadd_rn(__fadd_rn(s0, s1), __fadd_rn(s2, s3));
     const float two_dot = __fmul_rn(2.0f, acc);
     return (order == 0) ? __fsub_rn(__fadd_rn(zsq, e2), two_dot) : __fadd_rn(__fsub_rn(zsq, two_dot), e2);
+}
+
+// Append (d, code) to the candidate list of `slot` (shared memory, [CAP][256]).  `cnt` = length | overflow << 31.  When the list
+// is full it is first compacted against the current bound (entries that fell out of the band of the running minimum are
+// dropped); only if CAP genuine near-ties remain does the row fall back to the exact scan of the whole codebook.
+// Deliberately NOT inlined: the scan loop is unrolled 32x and an inlined copy per element made the loop body ~100 KB of
+// code (ncu: the scan warps stalled on instruction fetch); a thread gets here ~ln K times per row half.
+__device__ __noinline__ int cand_push(float d, int code, float bound, int cnt, int slot, float* cand_d, uint16_t* cand_c) {
+    if (!(d < INFINITY)) return cnt;                                        // padding codes (|e|^2 = inf) and NaN never qualify
+    int n = cnt & 0x7fffffff;
+    if (n == CAP) {
+        int m = 0;
+        for (int i = 0; i < CAP; ++i) {
+            const float di = cand_d[i * 256 + slot];
+            if (di <= bound) { cand_d[m * 256 + slot] = di; cand_c[m * 256 + slot] = cand_c[i * 256 + slot]; ++m; }
+        }
+        n = m;
+    }
+    if (n < CAP) { cand_d[n * 256 + slot] = d; cand_c[n * 256 + slot] = (uint16_t)code; return (cnt & 0x80000000) | (n + 1); }
+    return (int)0x80000000 | n;
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTH, 1)
@@ -255,10 +289,10 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmEh, const __grid_constant_
         // one warp per row and iteration: lane L owns k = 8L .. 8L+7 (one 16-byte chunk of the hi and of the lo tile)
         {
             const int cidx = lane >> 3, j16 = lane & 7;
-            for (int rr = 0; rr < TM / 8; rr += 4) {
-                float4 v[4][2];
+            for (int rr = 0; rr < TM / 8; rr += 8) {
+                float4 v[8][2];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < 8; ++u) {
                     const int row = ew * (TM / 8) + rr + u;
                     const int64_t g = r0 + row;
                     v[u][0] = v[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -268,7 +302,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmEh, const __grid_constant_
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < 8; ++u) {
                     const int row = ew * (TM / 8) + rr + u;
                     const float f[8] = {v[u][0].x, v[u][0].y, v[u][0].z, v[u][0].w, v[u][1].x, v[u][1].y, v[u][1].z, v[u][1].w};
                     uint32_t hw[4], lw[4];
@@ -309,19 +343,18 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmEh, const __grid_constant_
         const int quarter = warp & 3, half = ew >> 2;
         const int row = quarter * 32 + lane;
         const int slot = half * TM + row;
-        const float zs = zsq_s[row];
-        // |d~ - d| <= 2 (3 * 2^-18 + 2^-16) |z||e| on the distance; 4x safety factor, plus the fp32 evaluation's own rounding
-        // band so that genuine fp32 near-ties always reach the exact re-rank (same threshold as vq_tc_decide_kernel)
-        const float thr = 4.8828125e-4f * sqrtf(zs * emax) + 1e-5f * (zs + emax);
-        float b1 = INFINITY; int bi = 0x7fffffff;
-        int cnt = 0, ovf = 0;
+        const float thr = tie_threshold(zsq_s[row], emax);
+        float b1 = INFINITY;
+        int cnt = 0;                                                        // list length, bit 31 = overflow
         int as = 0; uint32_t aph = 0;
+        {
+            e2_s[et] = (et < p.K) ? p.cb_sq[et] : INFINITY;                // code norms of tile 0
+        }
         for (int j = 0; j < p.ctiles; ++j) {
-            {   // code norms of this tile (the previous use of e2_s[as] finished before tempty[as] was arrived two tiles ago)
-                const int code = j * TN + et;
-                e2_s[as * TN + et] = (code < p.K) ? p.cb_sq[code] : INFINITY;
-            }
-            epi_sync();
+            epi_sync();                                                     // e2_s[as] written; every warp has left tile j-1
+            // norms of the NEXT tile: loaded now, stored after this tile's scan (buffer as^1 was tile j-1's, free since the sync)
+            const int ncode = (j + 1) * TN + et;
+            const float e2_next = (j + 1 < p.ctiles && ncode < p.K) ? p.cb_sq[ncode] : INFINITY;
             ptx::mbar_wait(&tfull[as], aph);
             ptx::tc_fence_after();
             const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * TN);
@@ -329,22 +362,43 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmEh, const __grid_constant_
                 uint32_t r[32];
                 ptx::tmem_ld32(t_addr + (uint32_t)c, r);
                 ptx::tmem_ld_wait();
+                const float* e2c = e2_s + as * TN + c;
+                // all 32 distances first (independent FMAs) and their minimum by a tree.  Only if the chunk minimum m lies within
+                // the band of the running minimum does the chunk hold candidates at all; then m itself is appended, and -- rare,
+                // genuine near-ties inside one chunk -- every other code within the band of m.  (A code within the band of the
+                // FINAL minimum is either its chunk's minimum, appended because final <= running, or within the band of it.)
+                float d[32];
 #pragma unroll
-                for (int u = 0; u < 32; ++u) {
-                    const float d = fmaf(-2.0f, __uint_as_float(r[u]), e2_s[as * TN + c + u]);
-                    if (d <= b1 + thr) {                                     // rare: a new minimum or a near-tie of the running one
-                        const int code = j * TN + c + u;
-                        if (d < b1) { b1 = d; bi = code; }
-                        if (cnt == CAP) {                                    // compact against the current bound before giving up
-                            int m = 0;
-                            for (int i = 0; i < CAP; ++i) {
-                                const float di = cand_d[i * 256 + slot];
-                                if (di <= b1 + thr) { cand_d[m * 256 + slot] = di; cand_c[m * 256 + slot] = cand_c[i * 256 + slot]; ++m; }
+                for (int u = 0; u < 32; ++u) d[u] = fmaf(-2.0f, __uint_as_float(r[u]), e2c[u]);
+                float m[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) m[u] = fminf(d[u], d[u + 16]);
+#pragma unroll
+                for (int w2 = 8; w2 > 0; w2 >>= 1)
+#pragma unroll
+                    for (int u = 0; u < w2; ++u) m[u] = fminf(m[u], m[u + w2]);
+                const float mn = m[0];
+                if (mn <= b1 + thr && mn < INFINITY) {
+                    b1 = fminf(b1, mn);
+                    const float band = mn + thr;
+                    unsigned near = 0;
+#pragma unroll
+                    for (int u = 0; u < 32; ++u) near |= (d[u] <= band) ? (1u << u) : 0u;
+                    if (__popc(near) == 1) {                                 // the usual case: the chunk minimum alone
+                        const int code = j * TN + c + (__ffs(near) - 1);
+                        const int n = cnt & 0x7fffffff;
+                        if (n < CAP) { cand_d[n * 256 + slot] = mn; cand_c[n * 256 + slot] = (uint16_t)code; ++cnt; }
+                        else cnt = cand_push(mn, code, b1 + thr, cnt, slot, cand_d, cand_c);
+                    } else {
+#pragma unroll 1
+                        for (int u = 0; u < 32; ++u)
+                            if ((near >> u) & 1u) {
+                                // the value of element u without a dynamically indexed register array: a select chain
+                                float du = d[0];
+#pragma unroll
+                                for (int t = 1; t < 32; ++t) du = (u == t) ? d[t] : du;
+                                cnt = cand_push(du, j * TN + c + u, b1 + thr, cnt, slot, cand_d, cand_c);
                             }
-                            cnt = m;
-                        }
-                        if (cnt < CAP) { cand_d[cnt * 256 + slot] = d; cand_c[cnt * 256 + slot] = (uint16_t)code; ++cnt; }
-                        else ovf = 1;
                     }
                 }
             }
@@ -352,54 +406,49 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmEh, const __grid_constant_
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa_rank(ptx::smem_u32(&tempty[as]), 0));
             if (++as == 2) { as = 0; aph ^= 1; }
+            e2_s[as * TN + et] = e2_next;
         }
-        rbest[slot] = b1; rcnt[slot] = cnt | (ovf << 31);
-        (void)bi;
+        rbest[slot] = b1; rcnt[slot] = cnt;
         epi_sync();
 
-        // ---- decide / exact re-rank / finish: one warp per row ------------------------------------------------------------
+        // ---- decide (one thread per row): a single surviving candidate is the fp32 argmin; otherwise mark for the re-rank ----
+        if (et < TM) {
+            const float bound = fminf(rbest[et], rbest[TM + et]) + tie_threshold(zsq_s[et], emax);
+            const int ca = rcnt[et], cb2 = rcnt[TM + et];
+            int keep = 0, code = -1;
+            if (((ca | cb2) >> 31) == 0) {
+                for (int i = 0; i < ca; ++i) if (cand_d[i * 256 + et] <= bound) { ++keep; code = cand_c[i * 256 + et]; }
+                for (int i = 0; i < cb2; ++i) if (cand_d[i * 256 + TM + et] <= bound) { ++keep; code = cand_c[i * 256 + TM + et]; }
+            }
+            rcode[et] = (keep == 1) ? code : -1;
+        }
+        epi_sync();
+
+        // ---- exact re-rank of the near-tied rows (one warp per row): ONLY the surviving candidates are evaluated -----------
         float sse_local = 0.f;
         int undecided_local = 0;
         for (int rr = 0; rr < TM / 8; ++rr) {
             const int rw = ew * (TM / 8) + rr;
             const int64_t g = r0 + rw;
             if (g >= p.N) break;
-            const float* zrow = p.z + g * p.D;
-            const float ba = rbest[rw], bb = rbest[TM + rw];
-            const float best = fminf(ba, bb);
-            const float zr = zsq_s[rw];
-            const float bound = best + (4.8828125e-4f * sqrtf(zr * emax) + 1e-5f * (zr + emax));
-            const int na = rcnt[rw] & 0x7fffffff, nb = rcnt[TM + rw] & 0x7fffffff;
-            const bool overflow = ((rcnt[rw] | rcnt[TM + rw]) >> 31) != 0;
-            int code;
-            if (!overflow) {
-                float dme = INFINITY; int cme = 0x7fffffff;
-                if (lane < na) { dme = cand_d[lane * 256 + rw]; cme = cand_c[lane * 256 + rw]; }
-                else if (lane < na + nb) { dme = cand_d[(lane - na) * 256 + TM + rw]; cme = cand_c[(lane - na) * 256 + TM + rw]; }
-                const bool keep = dme <= bound;
-                const unsigned mask = __ballot_sync(0xffffffffu, keep);
-                if (__popc(mask) == 1) {
-                    code = __shfl_sync(0xffffffffu, cme, __ffs(mask) - 1);
-                } else {
-                    ++undecided_local;
-                    float dist = INFINITY;
-                    if (keep) dist = exact_distance(zrow, p.cb + (int64_t)cme * p.D, p.cb_sq[cme], p.D, p.order);
-                    int c2 = keep ? cme : 0x7fffffff;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        const float od = __shfl_xor_sync(0xffffffffu, dist, o);
-                        const int oc = __shfl_xor_sync(0xffffffffu, c2, o);
-                        if (od < dist || (od == dist && oc < c2)) { dist = od; c2 = oc; }
-                    }
-                    code = c2;
-                }
-            } else {
-                // more near-ties than the list holds (degenerate codebooks: duplicated codes): exact scan of every code
+            int code = rcode[rw];
+            if (code < 0) {
                 ++undecided_local;
+                const float* zrow = p.z + g * p.D;
+                const int ca = rcnt[rw], cb2 = rcnt[TM + rw];
                 float dist = INFINITY; int c2 = 0x7fffffff;
-                for (int k = lane; k < p.K; k += 32) {
-                    const float dk = exact_distance(zrow, p.cb + (int64_t)k * p.D, p.cb_sq[k], p.D, p.order);
-                    if (dk < dist || (dk == dist && k < c2)) { dist = dk; c2 = k; }
+                if (((ca | cb2) >> 31) == 0) {
+                    const float bound = fminf(rbest[rw], rbest[TM + rw]) + tie_threshold(zsq_s[rw], emax);
+                    float dme = INFINITY; int cme = 0x7fffffff;
+                    if (lane < ca) { dme = cand_d[lane * 256 + rw]; cme = cand_c[lane * 256 + rw]; }
+                    else if (lane < ca + cb2) { dme = cand_d[(lane - ca) * 256 + TM + rw]; cme = cand_c[(lane - ca) * 256 + TM + rw]; }
+                    if (dme <= bound) { dist = exact_distance(zrow, p.cb + (int64_t)cme * p.D, p.cb_sq[cme], p.D, p.order); c2 = cme; }
+                } else {
+                    // more near-ties than the list holds (degenerate codebooks: duplicated codes): exact scan of every code
+                    for (int k = lane; k < p.K; k += 32) {
+                        const float dk = exact_distance(zrow, p.cb + (int64_t)k * p.D, p.cb_sq[k], p.D, p.order);
+                        if (dk < dist || (dk == dist && k < c2)) { dist = dk; c2 = k; }
+                    }
                 }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
@@ -408,21 +457,22 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmEh, const __grid_constant_
                     if (od < dist || (od == dist && oc < c2)) { dist = od; c2 = oc; }
                 }
                 code = c2;
+                if (code < 0 || code >= p.K) code = 0;    // NaN rows: keep memory-safe (torch.argmin would return the NaN position)
+                if (lane == 0) rcode[rw] = code;
             }
-            if (code < 0 || code >= p.K) code = 0;        // NaN rows: keep memory-safe (torch.argmin would return the NaN position)
             if (lane == 0) {
-                rcode[rw] = code;
                 p.idx_out[g] = (int64_t)code;
                 if (p.counts) atomicAdd(p.counts + code, 1.0f);
             }
         }
         __syncwarp();
-        // finish, four rows in flight per warp: q = z + (e - z), sum (e - z)^2, EMA cluster sums
-        for (int rr = 0; rr < TM / 8; rr += 4) {
-            float4 zv[4][2], ev[4][2];
-            int codes[4];
+
+        // ---- finish, 8 rows in flight per warp: q = z + (e - z), sum (e - z)^2, EMA cluster sums (z re-read from L2) ----------
+        for (int rr = 0; rr < TM / 8; rr += 8) {
+            float4 zv[8][2], ev[8][2];
+            int codes[8];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 8; ++u) {
                 const int rw = ew * (TM / 8) + rr + u;
                 const int64_t g = r0 + rw;
                 codes[u] = (g < p.N) ? rcode[rw] : -1;
@@ -437,7 +487,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmEh, const __grid_constant_
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 8; ++u) {
                 const int64_t g = r0 + ew * (TM / 8) + rr + u;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
