@@ -223,22 +223,21 @@ int vqb_vq_assign_tc(const float* z, const float* codebook, int order, float* q_
                      float* counts, float* dw, int64_t N, int K, int D, void* workspace, size_t workspace_bytes,
                      int* undecided_rows_out, void* stream);
 /* ONE-launch form of the same contract (identical indices to vqb_vq_assign), the product path on sm_100: a cluster of two
- * CTAs owns 256 latent rows; z is read once from HBM and split to bf16 hi/lo in the prologue (resident in shared memory),
- * the PRE-SPLIT codebook streams through a TMA ring, tcgen05 cta_group::2 UMMAs (3 bf16 products per k-step) give the dot
- * products in TMEM, the scan warps keep a running minimum plus an online list of every code within a rigorous error bound of
- * it, near-tied rows re-evaluate ONLY their surviving candidates with the strict kernel's fp32 arithmetic, and the same
+ * CTAs owns 256 latent rows; z is read once from HBM and rounded to fp16 in the prologue (resident in shared memory), the
+ * fp16 copy of the codebook streams through a TMA ring, tcgen05 cta_group::2 UMMAs give the dot products in TMEM with a
+ * rigorously bounded error, the scan warps keep a running minimum plus an online list of every code within that error band
+ * of it, near-tied rows re-evaluate ONLY their surviving candidates with the strict kernel's fp32 arithmetic, and the same
  * launch writes idx, q, sum (e-z)^2, the histogram and the EMA cluster sums.  Replaces vector_quantizers.py:37-61, 142-166.
- *   cb_hi, cb_lo [K][D] bf16 and cb_sq [K] fp32: the codebook split, produced by vqb_vq_prep_codebook (any codebook) or by
- *   vqb_vq_ema_update_prep (the EMA path: the update kernel leaves the NEW codebook split for the next step).
+ *   cb_half [K][D] fp16 and cb_sq [K] fp32: produced by vqb_vq_prep_codebook (any codebook) or by vqb_vq_ema_update_prep
+ *   (the EMA path: the update kernel leaves them for the NEW codebook, so the next step needs no preparation launch).
  * Needs D % 64 == 0, D <= 256, K % 8 == 0, K <= 65528.  sse / counts / dw / undecided_rows_out: caller zero-fills. */
-int vqb_vq_prep_codebook(const float* codebook, void* cb_hi, void* cb_lo, float* cb_sq, int K, int D, void* stream);
-int vqb_vq_fused(const float* z, const float* codebook, const void* cb_hi, const void* cb_lo, const float* cb_sq, int order,
-                 float* q_out, int64_t* idx_out, double* sse, float* counts, float* dw, int64_t N, int K, int D,
-                 int* undecided_rows_out, void* stream);
-/* vqb_vq_ema_update (below) that additionally writes the split of the updated codebook (cb_hi, cb_lo, cb_sq). */
+int vqb_vq_prep_codebook(const float* codebook, void* cb_half, float* cb_sq, int K, int D, void* stream);
+int vqb_vq_fused(const float* z, const float* codebook, const void* cb_half, const float* cb_sq, int order, float* q_out,
+                 int64_t* idx_out, double* sse, float* counts, float* dw, int64_t N, int K, int D, int* undecided_rows_out,
+                 void* stream);
+/* vqb_vq_ema_update (below) that additionally writes cb_half / cb_sq of the updated codebook. */
 int vqb_vq_ema_update_prep(float* ema_count, float* ema_weight, float* codebook, const float* counts, const float* dw,
-                           void* cb_hi, void* cb_lo, float* cb_sq, int K, int D, float decay, float eps, float batch,
-                           void* stream);
+                           void* cb_half, float* cb_sq, int K, int D, float decay, float eps, float batch, void* stream);
 /* EMA codebook update (vector_quantizers.py:158-169), in place:
  *   c = decay*ema_count + (1-decay)*counts ; ema_count = (c+eps)/(b + K*eps)*b   (b = IMAGE batch: defect B7)
  *   ema_weight = decay*ema_weight + (1-decay)*dw ; codebook = ema_weight / ema_count[:,None] */

@@ -41,7 +41,7 @@ def test_tc_search_equals_exact_kernel(V, N, K, D, init, mode):
     assert abs(float(s0) - float(s1)) <= 1e-6 * abs(float(s0))
     assert torch.equal(c0, c1) and C.rel_err(w1, w0) < 1e-5
     if init == 'normal':
-        assert und <= N // 20, und                 # tie-free: almost every row is decided by the tensor-core pass
+        assert und <= (N // 20 if mode == 'legacy' else N // 8), und      # tie-free: most rows are decided by the tensor-core pass
     if init == 'uniform':
         assert und > 0                             # tie-heavy: the exact path takes over for the near-tied rows
     # and against the CPU oracle, tie-aware
@@ -78,6 +78,24 @@ def test_fused_duplicate_codes_take_first_index(V):
     assert torch.equal(i0, i1) and torch.equal(q0, q1) and torch.equal(c0, c1)
     assert int((i1 % 40 != 0).sum()) == 0                       # always the first of the 40 identical codes
     assert int(V.ops.vq_assign_raw.last_undecided) == N
+
+
+def test_fused_out_of_fp16_range_and_nan_rows(V):
+    """the fused search rounds z and the codebook to fp16 for the tensor cores: latents beyond the fp16 range, infinities and
+    NaN rows must fall back to the exact scan and still equal the strict kernel (NaN row -> index 0, as the strict kernel)"""
+    torch.manual_seed(6)
+    N, K, D = 512, 256, 64
+    z = torch.randn(N, D)
+    z[3, 5] = 1.0e5; z[7, 0] = -3.0e38; z[11, 63] = float('nan'); z[200] *= 7.0e4; z[300, 1] = 6.6e4
+    cb = torch.randn(K, D)
+    z, cb = z.cuda(), cb.cuda()
+    _, i0, _, c0, _ = V.ops.vq_assign_raw(z, cb, 0, True, True, use_tc=False)
+    _, i1, _, c1, _ = V.ops.vq_assign_raw(z, cb, 0, True, True, use_tc='fused')
+    assert torch.equal(i0, i1) and torch.equal(c0, c1)
+    cb2 = cb.clone(); cb2[17, 3] = 1.0e5                              # a codebook entry beyond fp16: every row takes the exact scan
+    _, i0, _, _, _ = V.ops.vq_assign_raw(z, cb2, 0, False, False, use_tc=False)
+    _, i1, _, _, _ = V.ops.vq_assign_raw(z, cb2, 0, False, False, use_tc='fused')
+    assert torch.equal(i0, i1)
 
 
 def test_fused_prep_cache_follows_the_codebook(V):

@@ -5,24 +5,25 @@
 //   reference's operation order, first-index ties).
 //
 // Structure (cluster of 2 CTAs = 256 latent rows, tcgen05 cta_group::2, 10 warps per CTA):
-//   prologue   warps 2-9 read this CTA's 128 z rows ONCE from HBM (fp32, coalesced), split every value into bf16 hi + lo
-//              (16 mantissa bits together) and write both straight into the UMMA K-major SWIZZLE_128B layout in shared
-//              memory, where they stay for the whole kernel (A operand, 2 x 64 KB at D = 256); |z|^2 comes from the same pass.
-//   warp 0     streams the pre-split codebook (hi / lo bf16, prepared once per codebook version by vq_prep_codebook or by the
-//              EMA update itself) through a 4-stage TMA ring; each CTA stages only HALF of every 256-code tile (16 KB).
-//   warp 1     (leader CTA) issues M = 256, N = 256 UMMAs: dot = zh.eh + zl.eh + zh.el in fp32 TMEM accumulators, double
-//              buffered (2 x 256 columns); three bf16 products give the dot products to ~2^-16 relative.
+//   prologue   warps 2-9 read this CTA's 128 z rows ONCE from HBM (fp32, coalesced), round them to fp16 and write them straight
+//              into the UMMA K-major SWIZZLE_128B layout in shared memory, where they stay for the whole kernel (A operand,
+//              64 KB at D = 256); |z|^2 comes from the same pass.
+//   warp 0     streams the fp16 copy of the codebook (prepared once per codebook version by vq_prep_codebook or by the EMA
+//              update itself) through a 6-stage TMA ring; each CTA stages only HALF of every 256-code tile (16 KB).
+//   warp 1     (leader CTA) issues M = 256, N = 256 UMMAs (kind::f16, fp32 accumulators in TMEM, double buffered).  ONE fp16
+//              product per k-step: the dot products carry a RIGOROUSLY bounded error of 2^-11 |z||e| (tie_threshold), a third
+//              of the tensor work of a bf16 hi/lo split that would give 2^-16.
 //   warps 2-9  scan each accumulator tile: d~ = |e|^2 - 2 dot, running minimum, and an online CANDIDATE LIST per row: every
-//              code whose d~ is within a rigorous error bound of the running minimum (a superset of the codes within the
-//              bound of the final minimum).  After the last tile a row with a single surviving candidate is decided; for the
-//              others (true fp32 near-ties, e.g. the reference's U(+-1/K) initial codebook) the survivors -- and only
-//              they -- are re-evaluated EXACTLY (sequential fp32 FMA chain, (|z|^2 + |e|^2) - 2 dot, the strict kernel's
-//              arithmetic bit for bit), so the indices equal the strict kernel's in every case.
+//              code whose d~ is within the error band of the running minimum (a superset of the codes within the band of the
+//              final minimum).  After the last tile a row with a single surviving candidate is decided -- no other code can
+//              have the smallest fp32 distance; for the others the survivors, and only they (typically two), are re-evaluated
+//              EXACTLY (sequential fp32 FMA chain, (|z|^2 + |e|^2) - 2 dot: the strict kernel's arithmetic bit for bit), so
+//              the indices equal the strict kernel's in every case.
 //   finish     same warps, same launch: idx (int64), q = z + (e - z), sum (e-z)^2, histogram and EMA cluster sums
 //              (vector red.global.add), z re-read from L2.
 //
-// Roofline: algorithmic bytes 4ND + 4KD + 4ND + 8N (+8K + 12KD); tensor work 3 x 2NKD FLOP.  At K = 1024 the
-// op sits at the bf16 ridge; the exact-index contract (three bf16 products) makes it tensor-bound, not HBM-bound.
+// Roofline: algorithmic bytes 4ND + 4KD + 4ND + 8N (+8K + 12KD); tensor work 2NKD FLOP.  At K = 1024 the op sits
+// at the fp16 ridge (215 FLOP/B): the search is tensor-bound, prologue and finish are HBM / L2-bound.
 #include "common.cuh"
 #include "ptx.cuh"
 #include <mutex>
@@ -33,7 +34,7 @@ constexpr int TM = 128;          // latent rows per CTA (256 per cluster)
 constexpr int TN = 256;          // codes per accumulator tile (128 staged per CTA)
 constexpr int TK = 64;           // k elements per shared-memory tile row (128 bytes)
 constexpr int NTH = 320;         // warp 0 TMA, warp 1 MMA, warps 2-9 prologue / scan / exact / finish
-constexpr int ESTAGES = 4;
+constexpr int ESTAGES = 6;
 constexpr int CAP = 16;          // candidate-list entries per (row, column half)
 constexpr int Z_TILE = TM * TK * 2;          // 16 KB
 constexpr int E_TILE = (TN / 2) * TK * 2;    // 16 KB (this CTA's half)
@@ -60,39 +61,33 @@ int make_code_map(CUtensorMap* m, const void* base, int64_t rows, int cols, int 
     cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
     cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
     cuuint32_t es[2] = {1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { vqb_set_error("cuTensorMapEncodeTiled(vq_fused) failed: %d", (int)r); return VQB_ERR_CUDA; }
     return VQB_OK;
 }
 
-// codebook fp32 [K][D] -> hi, lo bf16 [K][D] and sq[k] = |e_k|^2 with EXACTLY the summation of row_sqnorm_kernel (vq.cu):
+// codebook fp32 [K][D] -> fp16 copy [K][D] and sq[k] = |e_k|^2 with EXACTLY the summation of row_sqnorm_kernel (vq.cu):
 // lane-strided fp32 FMA chains, then the xor butterfly -- the strict kernel and the exact re-rank below read the same values.
-__device__ __forceinline__ void split_row(const float* __restrict__ x, bf16* __restrict__ hi, bf16* __restrict__ lo,
-                                          float* __restrict__ sq, int64_t row, int D, int lane) {
+__global__ void vq_prep_codebook_kernel(const float* __restrict__ cb, __half* __restrict__ hf, float* __restrict__ sq, int K, int D) {
+    const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= K) return;
     float s = 0.f;
     for (int d = lane; d < D; d += 32) {
-        const float v = x[row * D + d];
-        const bf16 h = __float2bfloat16_rn(v);
-        hi[row * D + d] = h;
-        lo[row * D + d] = __float2bfloat16_rn(v - __bfloat162float(h));
+        const float v = cb[row * D + d];
+        hf[row * D + d] = __float2half_rn(v);
         s = fmaf(v, v, s);
     }
     s = warp_sum(s);
     if (lane == 0) sq[row] = s;
 }
 
-__global__ void vq_prep_codebook_kernel(const float* __restrict__ cb, bf16* __restrict__ hi, bf16* __restrict__ lo,
-                                        float* __restrict__ sq, int K, int D) {
-    const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    if (row < K) split_row(cb, hi, lo, sq, row, D, threadIdx.x & 31);
-}
-
 // EMA state update (vector_quantizers.py:158-169, same arithmetic as vq_ema_update_kernel in vq.cu) that also leaves the
-// NEW codebook split for the next step's search: no separate preparation launch on the EMA path.
+// fp16 copy and the norms of the NEW codebook for the next step's search: no separate preparation launch on the EMA path.
 __global__ void vq_ema_update_prep_kernel(float* __restrict__ ema_count, float* __restrict__ ema_weight, float* __restrict__ cb,
-                                          const float* __restrict__ counts, const float* __restrict__ dw, bf16* __restrict__ hi,
-                                          bf16* __restrict__ lo, float* __restrict__ sq, int K, int D, float decay, float eps, float batch) {
+                                          const float* __restrict__ counts, const float* __restrict__ dw, __half* __restrict__ hf,
+                                          float* __restrict__ sq, int K, int D, float decay, float eps, float batch) {
     const int code = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (code >= K) return;
@@ -105,9 +100,7 @@ __global__ void vq_ema_update_prep_kernel(float* __restrict__ ema_count, float* 
         ema_weight[o] = w;
         const float v = w / cnt;
         cb[o] = v;
-        const bf16 h = __float2bfloat16_rn(v);
-        hi[o] = h;
-        lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
+        hf[o] = __float2half_rn(v);
         s = fmaf(v, v, s);
     }
     s = warp_sum(s);
@@ -140,6 +133,8 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
         "r"(parity)
         : "memory");
 }
+// instruction descriptor of kind::f16 with FP16 A / B (format 0), fp32 accumulate, both operands K-major
+__device__ __forceinline__ uint32_t umma_idesc_f16(int M, int N) { return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -147,17 +142,21 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 }
 
 // Width of the band around the smallest APPROXIMATE distance inside which a code may still be the fp32 argmin.  With
-// d~ = |e|^2 - 2 (zh.eh + zl.eh + zh.el) from the tensor cores and d = the strict kernel's fp32 value (same |z|^2 and |e|^2
-// operands for every code of a row, so they cancel in comparisons):
-//   * split error: z = zh + zl and e = eh + el hold 16 mantissa bits each, the zl.el product is dropped: <= 3 * 2^-18 |z||e|
-//     on the dot product; TMEM accumulation over 48 k-steps x 3 products (not round-to-nearest): <= 2^-16 |z||e|;
-//     on the distance (x2) and for two codes (x2): 2^-14 * 1.75 |z||e|  -> covered 4x by 2^-11 |z||e|;
+// d~ = |e|^2 - 2 (zh . eh) from the tensor cores (zh, eh = z, e rounded to fp16) and d = the strict kernel's fp32 value (same
+// |z|^2 and |e|^2 operands for every code of a row, so they cancel in comparisons):
+//   * operand rounding: |zh_i - z_i| <= 2^-12 |z_i| (11 significant bits, round to nearest) or <= 2^-25 below the fp16 normal
+//     range, likewise e: |zh.eh - z.e| <= (2^-11 + 2^-24) |z||e| + 2^-25 sqrt(D) (|z| + |e|)  (Cauchy-Schwarz);
+//     fp32 accumulation in TMEM over 16 k-steps (not round-to-nearest): <= 2^-17 |z||e|;
+//     on the distance (x2) and for the two codes being compared (x2):  2^-9 (1 + 2^-5) |z||e| + 2^-23 sqrt(D) (|z| + |e|);
 //   * the fp32 evaluation itself: one rounding of (|z|^2 + |e|^2) and one of the subtraction, each <= 1 ulp of a value
 //     <= (|z|+|e|)^2 <= 2 (|z|^2+|e|^2), i.e. <= 2^-22 (|z|^2+|e|^2) per code, and the sequential 256-term FMA chain of the
 //     dot product, <= 256 * 2^-24 |z||e| (x2 on the distance); for two codes: 2^-21 (|z|^2+|e|^2) + 2^-14 |z||e|.
 // A code outside the band cannot have the smallest fp32 distance, hence cannot be the strict kernel's first-index argmin.
-__device__ __forceinline__ float tie_threshold(float zs, float emax) {
-    return (4.8828125e-4f + 6.103515625e-5f) * sqrtf(zs * emax) + 4.76837158203125e-7f * (zs + emax);
+// (fp16 overflow -- |z_i| or |e_i| > 65504 -- gives inf / NaN dot products: such a row keeps no candidate and takes the exact
+// scan of the whole codebook.)
+__device__ __forceinline__ float tie_threshold(float zs, float emax, float sqrt_d) {
+    const float zn = sqrtf(zs), en = sqrtf(emax);
+    return (2.013916015625e-3f + 6.103515625e-5f) * zn * en + 4.76837158203125e-7f * (zs + emax) + 1.1920928955078125e-7f * sqrt_d * (zn + en);
 }
 
 // exact fp32 distance of one (row, code) pair with the strict kernel's arithmetic (vq.cu: vq_assign_tile): |z|^2 from four
@@ -196,18 +195,32 @@ __device__ __noinline__ int cand_push(float d, int code, float bound, int cnt, i
     return (int)0x80000000 | n;
 }
 
+// the same arithmetic on rows staged in shared memory (plain loads)
+__device__ __forceinline__ float exact_distance_smem(const float* zrow, const float* erow, float e2, int D, int order) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, acc = 0.f;
+    for (int d = 0; d < D; d += 4) {
+        const float4 zv = *reinterpret_cast<const float4*>(zrow + d);
+        const float4 ev = *reinterpret_cast<const float4*>(erow + d);
+        s0 = __fmaf_rn(zv.x, zv.x, s0); s1 = __fmaf_rn(zv.y, zv.y, s1); s2 = __fmaf_rn(zv.z, zv.z, s2); s3 = __fmaf_rn(zv.w, zv.w, s3);
+        acc = __fmaf_rn(zv.x, ev.x, acc); acc = __fmaf_rn(zv.y, ev.y, acc); acc = __fmaf_rn(zv.z, ev.z, acc); acc = __fmaf_rn(zv.w, ev.w, acc);
+    }
+    const float zsq = __fadd_rn(__fadd_rn(s0, s1), __fadd_rn(s2, s3));
+    const float two_dot = __fmul_rn(2.0f, acc);
+    return (order == 0) ? __fsub_rn(__fadd_rn(zsq, e2), two_dot) : __fadd_rn(__fsub_rn(zsq, two_dot), e2);
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTH, 1)
-vq_fused_kernel(const __grid_constant__ CUtensorMap tmEh, const __grid_constant__ CUtensorMap tmEl, const FusedParams p) {
+vq_fused_kernel(const __grid_constant__ CUtensorMap tmEh, const FusedParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* smemZ = smem;                                               // [2 (hi, lo)][kchunks] tiles of [128 rows][64 k] bf16
-    uint8_t* smemE = smemZ + (size_t)2 * p.kchunks * Z_TILE;             // [ESTAGES] tiles of [128 codes][64 k] bf16
+    uint8_t* smemZ = smem;                                               // [kchunks] tiles of [128 rows][64 k] fp16
+    uint8_t* smemE = smemZ + (size_t)p.kchunks * Z_TILE;                 // [ESTAGES] tiles of [128 codes][64 k] fp16
     float* cand_d = reinterpret_cast<float*>(smemE + (size_t)ESTAGES * E_TILE);      // [CAP][256]
     uint16_t* cand_c = reinterpret_cast<uint16_t*>(cand_d + CAP * 256);              // [CAP][256]
     float* e2_s = reinterpret_cast<float*>(cand_c + CAP * 256);                       // [2][256] code norms of the tile in flight
     float* zsq_s = e2_s + 2 * TN;                                        // [128] |z|^2 (approximate order; threshold only)
     float* rbest = zsq_s + TM;                                           // [2][128] running minimum per (half, row)
-    int* rcode = reinterpret_cast<int*>(rbest + 2 * TM);                 // [128] final code per row (second half unused)
+    int* rcode = reinterpret_cast<int*>(rbest + 2 * TM);                 // [128] final code per row, [128] fp16-overflow flag per row
     int* rcnt = rcode + 2 * TM;                                          // [2][128] list length, bit 31 = overflow
     float* red_s = reinterpret_cast<float*>(rcnt + 2 * TM);              // [8] per-warp partial sums, [8] emax
     uint64_t* zfull = reinterpret_cast<uint64_t*>(red_s + 16);
@@ -222,7 +235,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmEh, const __grid_constant_
     const int64_t r0 = (int64_t)blockIdx.x * TM;                          // blockIdx.x = 2 * cluster + rank
 
     if (warp == 0 && lane == 0) {
-        ptx::prefetch_tmap(&tmEh); ptx::prefetch_tmap(&tmEl);
+        ptx::prefetch_tmap(&tmEh);
         ptx::mbar_init(zfull, 2);                                          // one arrival per CTA of the pair
         for (int i = 0; i < ESTAGES; ++i) { ptx::mbar_init(&efull[i], 1); ptx::mbar_init(&eempty[i], 1); }
         for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull[i], 1); ptx::mbar_init(&tempty[i], 16); }      // 8 scan warps x 2 CTAs
@@ -240,19 +253,18 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmEh, const __grid_constant_
         if (lane == 0) {
             int s = 0; uint32_t ph = 0;
             for (int j = 0; j < p.ctiles; ++j)
-                for (int c = 0; c < p.kchunks; ++c)
-                    for (int hl = 0; hl < 2; ++hl) {
-                        ptx::mbar_wait(&eempty[s], ph ^ 1);
-                        if (rank == 0) ptx::mbar_expect_tx(&efull[s], 2u * (uint32_t)E_TILE);
-                        ptx::tma_load_2d_2sm(smemE + (size_t)s * E_TILE, hl ? &tmEl : &tmEh, ptx::mapa_rank(ptx::smem_u32(&efull[s]), 0),
-                                             c * TK, j * TN + (int)rank * (TN / 2));
-                        if (++s == ESTAGES) { s = 0; ph ^= 1; }
-                    }
+                for (int c = 0; c < p.kchunks; ++c) {
+                    ptx::mbar_wait(&eempty[s], ph ^ 1);
+                    if (rank == 0) ptx::mbar_expect_tx(&efull[s], 2u * (uint32_t)E_TILE);
+                    ptx::tma_load_2d_2sm(smemE + (size_t)s * E_TILE, &tmEh, ptx::mapa_rank(ptx::smem_u32(&efull[s]), 0), c * TK,
+                                         j * TN + (int)rank * (TN / 2));
+                    if (++s == ESTAGES) { s = 0; ph ^= 1; }
+                }
         }
     } else if (warp == 1) {
         // ---- MMA issue (leader CTA only): M = 256 rows (128 per CTA), N = 256 codes (128 staged per CTA) -----------------
         if (lane == 0 && rank == 0) {
-            const uint32_t idesc = ptx::umma_idesc_bf16(2 * TM, TN, 0, 0);
+            const uint32_t idesc = umma_idesc_f16(2 * TM, TN);
             mbar_wait_cluster(zfull, 0);
             ptx::tc_fence_after();
             int s = 0; uint32_t ph = 0;
@@ -261,23 +273,17 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmEh, const __grid_constant_
                 ptx::mbar_wait(&tempty[as], aph ^ 1);
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * TN);
-                uint32_t first = 1;
-                for (int c = 0; c < p.kchunks; ++c)
-                    for (int hl = 0; hl < 2; ++hl) {
-                        ptx::mbar_wait(&efull[s], ph);
-                        ptx::tc_fence_after();
-                        const uint64_t bdesc = ptx::umma_smem_desc(ptx::smem_u32(smemE + (size_t)s * E_TILE), 0, 1024);
-                        const uint64_t zh = ptx::umma_smem_desc(ptx::smem_u32(smemZ + (size_t)c * Z_TILE), 0, 1024);
-                        const uint64_t zl = ptx::umma_smem_desc(ptx::smem_u32(smemZ + (size_t)(p.kchunks + c) * Z_TILE), 0, 1024);
+                for (int c = 0; c < p.kchunks; ++c) {
+                    ptx::mbar_wait(&efull[s], ph);
+                    ptx::tc_fence_after();
+                    const uint64_t bdesc = ptx::umma_smem_desc(ptx::smem_u32(smemE + (size_t)s * E_TILE), 0, 1024);
+                    const uint64_t adesc = ptx::umma_smem_desc(ptx::smem_u32(smemZ + (size_t)c * Z_TILE), 0, 1024);
 #pragma unroll
-                        for (int k = 0; k < TK / 16; ++k) {
-                            ptx::umma2_bf16(d_tmem, zh + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, first ? 0u : 1u);   // zh.eh | zh.el
-                            first = 0;
-                            if (hl == 0) ptx::umma2_bf16(d_tmem, zl + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, 1u);    // zl.eh
-                        }
-                        ptx::umma2_commit(&eempty[s]);
-                        if (++s == ESTAGES) { s = 0; ph ^= 1; }
-                    }
+                    for (int k = 0; k < TK / 16; ++k)
+                        ptx::umma2_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (c | k) != 0 ? 1u : 0u);
+                    ptx::umma2_commit(&eempty[s]);
+                    if (++s == ESTAGES) { s = 0; ph ^= 1; }
+                }
                 ptx::umma2_commit(&tfull[as]);
                 if (++as == 2) { as = 0; aph ^= 1; }
             }
@@ -305,29 +311,28 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmEh, const __grid_constant_
                 for (int u = 0; u < 8; ++u) {
                     const int row = ew * (TM / 8) + rr + u;
                     const float f[8] = {v[u][0].x, v[u][0].y, v[u][0].z, v[u][0].w, v[u][1].x, v[u][1].y, v[u][1].z, v[u][1].w};
-                    uint32_t hw[4], lw[4];
+                    uint32_t hw[4];
                     float s = 0.f;
+                    int bad = 0;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        const bf16 h0 = __float2bfloat16_rn(f[2 * i]), h1 = __float2bfloat16_rn(f[2 * i + 1]);
-                        const bf16 l0 = __float2bfloat16_rn(f[2 * i] - __bfloat162float(h0));
-                        const bf16 l1 = __float2bfloat16_rn(f[2 * i + 1] - __bfloat162float(h1));
-                        hw[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                        lw[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                        const __half2 h2 = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+                        hw[i] = *reinterpret_cast<const uint32_t*>(&h2);
                         s = fmaf(f[2 * i], f[2 * i], s); s = fmaf(f[2 * i + 1], f[2 * i + 1], s);
+                        bad |= !(fabsf(f[2 * i]) < 65504.f) | !(fabsf(f[2 * i + 1]) < 65504.f);      // fp16 overflow, inf, NaN
                     }
                     if (lane * 8 < p.D) {
                         const uint32_t off = (uint32_t)row * 128u + (uint32_t)((j16 ^ (row & 7)) << 4);
                         *reinterpret_cast<uint4*>(smemZ + (size_t)cidx * Z_TILE + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                        *reinterpret_cast<uint4*>(smemZ + (size_t)(p.kchunks + cidx) * Z_TILE + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
                     }
                     s = warp_sum(s);
-                    if (lane == 0) zsq_s[row] = s;
+                    bad = __any_sync(0xffffffffu, bad != 0);
+                    if (lane == 0) { zsq_s[row] = s; rcode[TM + row] = bad; }
                 }
             }
             // largest code norm (threshold only): every CTA scans the K norms once (L2-resident, 4 KB at K = 1024)
             float m = 0.f;
-            for (int k = et; k < p.K; k += 256) m = fmaxf(m, p.cb_sq[k]);
+            for (int k = et; k < p.K; k += 256) { const float v = p.cb_sq[k]; m = (v < 4.29e9f) ? fmaxf(m, v) : INFINITY; }   // inf: fp16 overflow / NaN
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
             if (lane == 0) red_s[8 + ew] = m;
@@ -335,6 +340,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmEh, const __grid_constant_
             epi_sync();
             if (et == 0) ptx::mbar_arrive_cluster(ptx::mapa_rank(ptx::smem_u32(zfull), 0));
         }
+        const float sqrt_d = sqrtf((float)p.D);
         float emax = red_s[8];
 #pragma unroll
         for (int i = 1; i < 8; ++i) emax = fmaxf(emax, red_s[8 + i]);
@@ -343,7 +349,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmEh, const __grid_constant_
         const int quarter = warp & 3, half = ew >> 2;
         const int row = quarter * 32 + lane;
         const int slot = half * TM + row;
-        const float thr = tie_threshold(zsq_s[row], emax);
+        const float thr = tie_threshold(zsq_s[row], emax, sqrt_d);
         float b1 = INFINITY;
         int cnt = 0;                                                        // list length, bit 31 = overflow
         int as = 0; uint32_t aph = 0;
@@ -391,14 +397,15 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmEh, const __grid_constant_
                         else cnt = cand_push(mn, code, b1 + thr, cnt, slot, cand_d, cand_c);
                     } else {
 #pragma unroll 1
-                        for (int u = 0; u < 32; ++u)
-                            if ((near >> u) & 1u) {
-                                // the value of element u without a dynamically indexed register array: a select chain
-                                float du = d[0];
+                        while (near) {
+                            const int u = __ffs(near) - 1;
+                            near &= near - 1;
+                            // the value of element u without a dynamically indexed register array: a select chain
+                            float du = d[0];
 #pragma unroll
-                                for (int t = 1; t < 32; ++t) du = (u == t) ? d[t] : du;
-                                cnt = cand_push(du, j * TN + c + u, b1 + thr, cnt, slot, cand_d, cand_c);
-                            }
+                            for (int t = 1; t < 32; ++t) du = (u == t) ? d[t] : du;
+                            cnt = cand_push(du, j * TN + c + u, b1 + thr, cnt, slot, cand_d, cand_c);
+                        }
                     }
                 }
             }
@@ -408,12 +415,13 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmEh, const __grid_constant_
             if (++as == 2) { as = 0; aph ^= 1; }
             e2_s[as * TN + et] = e2_next;
         }
-        rbest[slot] = b1; rcnt[slot] = cnt;
+        // rows (or codebooks) that do not survive the fp16 rounding take the exact scan of the whole codebook
+        rbest[slot] = b1; rcnt[slot] = (rcode[TM + row] != 0 || !(emax < INFINITY)) ? (int)0x80000000 : cnt;
         epi_sync();
 
         // ---- decide (one thread per row): a single surviving candidate is the fp32 argmin; otherwise mark for the re-rank ----
         if (et < TM) {
-            const float bound = fminf(rbest[et], rbest[TM + et]) + tie_threshold(zsq_s[et], emax);
+            const float bound = fminf(rbest[et], rbest[TM + et]) + tie_threshold(zsq_s[et], emax, sqrt_d);
             const int ca = rcnt[et], cb2 = rcnt[TM + et];
             int keep = 0, code = -1;
             if (((ca | cb2) >> 31) == 0) {
@@ -425,6 +433,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmEh, const __grid_constant_
         epi_sync();
 
         // ---- exact re-rank of the near-tied rows (one warp per row): ONLY the surviving candidates are evaluated -----------
+        float* xbuf = reinterpret_cast<float*>(smemZ);          // staging: every MMA has completed (last tfull), the operand tiles are free
         float sse_local = 0.f;
         int undecided_local = 0;
         for (int rr = 0; rr < TM / 8; ++rr) {
@@ -437,13 +446,44 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmEh, const __grid_constant_
                 const float* zrow = p.z + g * p.D;
                 const int ca = rcnt[rw], cb2 = rcnt[TM + rw];
                 float dist = INFINITY; int c2 = 0x7fffffff;
+                bool have = false;
                 if (((ca | cb2) >> 31) == 0) {
-                    const float bound = fminf(rbest[rw], rbest[TM + rw]) + tie_threshold(zsq_s[rw], emax);
+                    const float bound = fminf(rbest[rw], rbest[TM + rw]) + tie_threshold(zsq_s[rw], emax, sqrt_d);
                     float dme = INFINITY; int cme = 0x7fffffff;
                     if (lane < ca) { dme = cand_d[lane * 256 + rw]; cme = cand_c[lane * 256 + rw]; }
                     else if (lane < ca + cb2) { dme = cand_d[(lane - ca) * 256 + TM + rw]; cme = cand_c[(lane - ca) * 256 + TM + rw]; }
-                    if (dme <= bound) { dist = exact_distance(zrow, p.cb + (int64_t)cme * p.D, p.cb_sq[cme], p.D, p.order); c2 = cme; }
-                } else {
+                    const bool keep = dme <= bound;
+                    const unsigned kmask = __ballot_sync(0xffffffffu, keep);
+                    const int nk = __popc(kmask);
+                    have = nk > 0;
+                    // The fp32 dot product is ONE sequential FMA chain (bit-exactness with the strict kernel), so a lane walking
+                    // global memory pays an L2 round trip every few steps (ncu: 5 us per row).  Instead the warp stages the z row
+                    // and up to four candidate rows in shared memory with coalesced loads (the operand tiles are dead by now),
+                    // and one lane per candidate runs its chain from there.
+                    float* xz = xbuf + ew * (5 * 256);
+                    int* xc = reinterpret_cast<int*>(xbuf + 8 * 5 * 256) + ew * 32;
+                    if (keep) xc[__popc(kmask & ((1u << lane) - 1u))] = cme;
+                    for (int d = lane * 4; d < p.D; d += 128) *reinterpret_cast<float4*>(xz + d) = *reinterpret_cast<const float4*>(zrow + d);
+                    __syncwarp();
+                    for (int g0 = 0; g0 < nk; g0 += 4) {
+                        const int ng = min(4, nk - g0);
+                        for (int cc = 0; cc < ng; ++cc) {
+                            const float* erow = p.cb + (int64_t)xc[g0 + cc] * p.D;
+                            for (int d = lane * 4; d < p.D; d += 128)
+                                *reinterpret_cast<float4*>(xz + 256 * (1 + cc) + d) = __ldg(reinterpret_cast<const float4*>(erow + d));
+                        }
+                        __syncwarp();
+                        if (lane < ng) {
+                            const int code_l = xc[g0 + lane];
+                            const float dl = exact_distance_smem(xz, xz + 256 * (1 + lane), p.cb_sq[code_l], p.D, p.order);
+                            if (dl < dist || (dl == dist && code_l < c2)) { dist = dl; c2 = code_l; }
+                        }
+                        __syncwarp();
+                    }
+                }
+                if (!have) {
+                    // list overflow (more near-ties than it holds: duplicated codes) or no finite approximate distance at all
+                    // (fp16 overflow, NaN): exact scan of every code
                     // more near-ties than the list holds (degenerate codebooks: duplicated codes): exact scan of every code
                     for (int k = lane; k < p.K; k += 32) {
                         const float dk = exact_distance(zrow, p.cb + (int64_t)k * p.D, p.cb_sq[k], p.D, p.order);
@@ -460,10 +500,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmEh, const __grid_constant_
                 if (code < 0 || code >= p.K) code = 0;    // NaN rows: keep memory-safe (torch.argmin would return the NaN position)
                 if (lane == 0) rcode[rw] = code;
             }
-            if (lane == 0) {
-                p.idx_out[g] = (int64_t)code;
-                if (p.counts) atomicAdd(p.counts + code, 1.0f);
-            }
+            if (lane == 0) p.idx_out[g] = (int64_t)code;
         }
         __syncwarp();
 
@@ -476,6 +513,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmEh, const __grid_constant_
                 const int rw = ew * (TM / 8) + rr + u;
                 const int64_t g = r0 + rw;
                 codes[u] = (g < p.N) ? rcode[rw] : -1;
+                if (lane == u && codes[u] >= 0 && p.counts) atomicAdd(p.counts + codes[u], 1.0f);
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int d = lane * 4 + h * 128;
@@ -526,43 +564,40 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmEh, const __grid_constant_
 
 size_t fused_smem_bytes(int D) {
     const int kchunks = D / TK;
-    return (size_t)2 * kchunks * Z_TILE + (size_t)ESTAGES * E_TILE + (size_t)CAP * 256 * 6 + (size_t)2 * TN * 4 + TM * 4 + 2 * TM * 4 * 3 +
+    return (size_t)kchunks * Z_TILE + (size_t)ESTAGES * E_TILE + (size_t)CAP * 256 * 6 + (size_t)2 * TN * 4 + TM * 4 + 2 * TM * 4 * 3 +
            16 * 4 + (1 + 2 * ESTAGES + 4) * 8 + 16 + 1024 + 64;
 }
 
 }  // namespace
 
-extern "C" int vqb_vq_prep_codebook(const float* codebook, void* cb_hi, void* cb_lo, float* cb_sq, int K, int D, void* stream) {
-    VQB_CHECK_ARG(codebook && cb_hi && cb_lo && cb_sq && K > 0 && D > 0, "vq_prep_codebook: bad arguments");
-    vq_prep_codebook_kernel<<<(unsigned)ceil_div64((int64_t)K * 32, 256), 256, 0, as_stream(stream)>>>(codebook, (bf16*)cb_hi, (bf16*)cb_lo,
-                                                                                                        cb_sq, K, D);
+extern "C" int vqb_vq_prep_codebook(const float* codebook, void* cb_half, float* cb_sq, int K, int D, void* stream) {
+    VQB_CHECK_ARG(codebook && cb_half && cb_sq && K > 0 && D > 0, "vq_prep_codebook: bad arguments");
+    vq_prep_codebook_kernel<<<(unsigned)ceil_div64((int64_t)K * 32, 256), 256, 0, as_stream(stream)>>>(codebook, (__half*)cb_half, cb_sq, K, D);
     VQB_CHECK_LAUNCH("vq_prep_codebook");
     return VQB_OK;
 }
 
 extern "C" int vqb_vq_ema_update_prep(float* ema_count, float* ema_weight, float* codebook, const float* counts, const float* dw,
-                                      void* cb_hi, void* cb_lo, float* cb_sq, int K, int D, float decay, float eps, float batch,
-                                      void* stream) {
-    VQB_CHECK_ARG(ema_count && ema_weight && codebook && counts && dw && cb_hi && cb_lo && cb_sq && K > 0 && D > 0,
+                                      void* cb_half, float* cb_sq, int K, int D, float decay, float eps, float batch, void* stream) {
+    VQB_CHECK_ARG(ema_count && ema_weight && codebook && counts && dw && cb_half && cb_sq && K > 0 && D > 0,
                   "vq_ema_update_prep: bad arguments");
     vq_ema_update_prep_kernel<<<(unsigned)ceil_div64((int64_t)K * 32, 256), 256, 0, as_stream(stream)>>>(
-        ema_count, ema_weight, codebook, counts, dw, (bf16*)cb_hi, (bf16*)cb_lo, cb_sq, K, D, decay, eps, batch);
+        ema_count, ema_weight, codebook, counts, dw, (__half*)cb_half, cb_sq, K, D, decay, eps, batch);
     VQB_CHECK_LAUNCH("vq_ema_update_prep");
     return VQB_OK;
 }
 
-extern "C" int vqb_vq_fused(const float* z, const float* codebook, const void* cb_hi, const void* cb_lo, const float* cb_sq,
-                            int order, float* q_out, int64_t* idx_out, double* sse, float* counts, float* dw, int64_t N, int K, int D,
-                            int* undecided_rows_out, void* stream) {
-    VQB_CHECK_ARG(z && codebook && cb_hi && cb_lo && cb_sq && idx_out, "vq_fused: null pointer");
+extern "C" int vqb_vq_fused(const float* z, const float* codebook, const void* cb_half, const float* cb_sq, int order, float* q_out,
+                            int64_t* idx_out, double* sse, float* counts, float* dw, int64_t N, int K, int D, int* undecided_rows_out,
+                            void* stream) {
+    VQB_CHECK_ARG(z && codebook && cb_half && cb_sq && idx_out, "vq_fused: null pointer");
     VQB_CHECK_ARG(N > 0 && K > 0 && D > 0 && (order == 0 || order == 1), "vq_fused: bad arguments");
     VQB_CHECK_ARG(D % 64 == 0 && D <= 256 && K % 8 == 0 && K <= 65528, "vq_fused: needs D %% 64 == 0, D <= 256, K %% 8 == 0, K <= 65528 (got D=%d K=%d)", D, K);
     VQB_CHECK_ARG(N < (int64_t)1 << 31, "vq_fused: N too large");
     cudaStream_t st = as_stream(stream);
-    CUtensorMap tmEh, tmEl;
+    CUtensorMap tmEh;
     int rc;
-    if ((rc = make_code_map(&tmEh, cb_hi, K, D, TN / 2))) return rc;
-    if ((rc = make_code_map(&tmEl, cb_lo, K, D, TN / 2))) return rc;
+    if ((rc = make_code_map(&tmEh, cb_half, K, D, TN / 2))) return rc;
     FusedParams fp;
     fp.N = N; fp.K = K; fp.D = D; fp.kchunks = D / TK; fp.ctiles = (K + TN - 1) / TN; fp.order = order;
     fp.z = z; fp.cb = codebook; fp.cb_sq = cb_sq; fp.q_out = q_out; fp.idx_out = idx_out; fp.sse = sse; fp.counts = counts; fp.dw = dw;
@@ -572,7 +607,7 @@ extern "C" int vqb_vq_fused(const float* z, const float* codebook, const void* c
     static std::once_flag attr_once;
     std::call_once(attr_once, [] { cudaFuncSetAttribute(vq_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
     const unsigned ctas = (unsigned)(2 * ceil_div64(N, 2 * TM));             // whole clusters (a cluster covers 256 rows)
-    vq_fused_kernel<<<ctas, NTH, smem, st>>>(tmEh, tmEl, fp);
+    vq_fused_kernel<<<ctas, NTH, smem, st>>>(tmEh, fp);
     VQB_CHECK_LAUNCH("vq_fused");
     return VQB_OK;
 }

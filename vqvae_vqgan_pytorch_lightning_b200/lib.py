@@ -65,9 +65,9 @@ SIGNATURES = {
     'vqb_vq_assign': (_i, [_p, _p, _i, _p, _p, _p, _p, _p, _i64, _i, _i, _p, _sz, _p]),
     'vqb_vq_tc_workspace_bytes': (_sz, [_i64, _i, _i]),
     'vqb_vq_assign_tc': (_i, [_p, _p, _i, _p, _p, _p, _p, _p, _i64, _i, _i, _p, _sz, _p, _p]),
-    'vqb_vq_prep_codebook': (_i, [_p, _p, _p, _p, _i, _i, _p]),
-    'vqb_vq_fused': (_i, [_p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _i64, _i, _i, _p, _p]),
-    'vqb_vq_ema_update_prep': (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _f, _f, _f, _p]),
+    'vqb_vq_prep_codebook': (_i, [_p, _p, _p, _i, _i, _p]),
+    'vqb_vq_fused': (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _i64, _i, _i, _p, _p]),
+    'vqb_vq_ema_update_prep': (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _f, _f, _f, _p]),
     'vqb_vq_ema_update': (_i, [_p, _p, _p, _p, _p, _i, _i, _f, _f, _f, _p]),
     'vqb_vq_backward': (_i, [_p, _p, _p, _p, _p, _f, _f, _p, _p, _i64, _i, _i, _p]),
     'vqb_vq_gather': (_i, [_p, _p, _p, _i64, _i, _i, _p]),

@@ -536,23 +536,22 @@ def mse_l1(a, b):
 # vector quantisation
 # ------------------------------------------------------------------------------------------------------
 class CodebookPrep:
-    """bf16 hi / lo split and row norms of a codebook for the fused search (vqb_vq_fused), owned by a quantizer module and
+    """fp16 copy and row norms of a codebook for the fused search (vqb_vq_fused), owned by a quantizer module and
     refreshed only when the codebook changed: the key holds the parameter's autograd version, its address and -- for codebooks
     an optimizer may rewrite behind autograd's back -- the global weights epoch.  The EMA update kernel refreshes the split
     itself (vq_ema_update), so the EMA path never runs a separate preparation launch."""
 
     def __init__(self):
         self.key = None
-        self.hi = self.lo = self.sq = None
+        self.hf = self.sq = None
 
     def _key(self, codebook: torch.Tensor):
         return (codebook._version, codebook.data_ptr(), tuple(codebook.shape), _weights_epoch if codebook.requires_grad else -1)
 
     def _alloc(self, codebook: torch.Tensor):
         k, d = codebook.shape
-        if self.hi is None or self.hi.shape != (k, d) or self.hi.device != codebook.device:
-            self.hi = torch.empty(k, d, dtype=torch.bfloat16, device=codebook.device)
-            self.lo = torch.empty(k, d, dtype=torch.bfloat16, device=codebook.device)
+        if self.hf is None or self.hf.shape != (k, d) or self.hf.device != codebook.device:
+            self.hf = torch.empty(k, d, dtype=torch.float16, device=codebook.device)
             self.sq = torch.empty(k, dtype=torch.float32, device=codebook.device)
 
     def get(self, codebook: torch.Tensor):
@@ -561,9 +560,9 @@ class CodebookPrep:
             self._alloc(codebook)
             cb = codebook.detach()
             k, d = cb.shape
-            call('vqb_vq_prep_codebook', ptr(cb), ptr(self.hi), ptr(self.lo), ptr(self.sq), k, d, stream())
+            call('vqb_vq_prep_codebook', ptr(cb), ptr(self.hf), ptr(self.sq), k, d, stream())
             self.key = key
-        return self.hi, self.lo, self.sq
+        return self.hf, self.sq
 
     def mark_fresh(self, codebook: torch.Tensor):
         self.key = self._key(codebook)
@@ -599,9 +598,9 @@ def vq_assign_raw(flat: torch.Tensor, codebook: torch.Tensor, order: int, want_q
     if use_tc and use_tc != 'legacy' and _fused_vq_ok(flat, k, d):
         scal = torch.zeros(2, dtype=torch.float64, device=dev)           # [sse | undecided-row counter (int32 in the low word)]
         sse, und = scal[:1], scal[1:].view(torch.int32)[:1]
-        hi, lo, sq = (prep or CodebookPrep()).get(codebook)
+        hf, sq = (prep or CodebookPrep()).get(codebook)
         cb = codebook.detach()
-        call('vqb_vq_fused', ptr(flat), ptr(cb), ptr(hi), ptr(lo), ptr(sq), order, ptr(q), ptr(idx), ptr(sse), ptr(counts), ptr(dw),
+        call('vqb_vq_fused', ptr(flat), ptr(cb), ptr(hf), ptr(sq), order, ptr(q), ptr(idx), ptr(sse), ptr(counts), ptr(dw),
              n, k, d, ptr(und), stream())
         vq_assign_raw.last_undecided = und
         return q, idx, sse, counts, dw
@@ -683,8 +682,8 @@ def vq_ema_update(ema_count, ema_weight, codebook, counts, dw, decay, eps, batch
     k, d = codebook.shape
     if prep is not None and get_precision().name == 'fast' and _fused_vq_ok(None, k, d):
         prep._alloc(codebook)
-        call('vqb_vq_ema_update_prep', ptr(ema_count), ptr(ema_weight), ptr(codebook), ptr(counts), ptr(dw), ptr(prep.hi), ptr(prep.lo),
-             ptr(prep.sq), k, d, decay, eps, float(batch), stream())
+        call('vqb_vq_ema_update_prep', ptr(ema_count), ptr(ema_weight), ptr(codebook), ptr(counts), ptr(dw), ptr(prep.hf), ptr(prep.sq),
+             k, d, decay, eps, float(batch), stream())
         prep.mark_fresh(codebook)
         return
     call('vqb_vq_ema_update', ptr(ema_count), ptr(ema_weight), ptr(codebook), ptr(counts), ptr(dw), k, d, decay, eps,
