@@ -419,90 +419,111 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmEh, const FusedParams p) {
         rbest[slot] = b1; rcnt[slot] = (rcode[TM + row] != 0 || !(emax < INFINITY)) ? (int)0x80000000 : cnt;
         epi_sync();
 
-        // ---- decide (one thread per row): a single surviving candidate is the fp32 argmin; otherwise mark for the re-rank ----
+        // ---- decide (one thread per row): a single surviving candidate is the fp32 argmin; the other rows are appended to the
+        //      CTA's re-rank work list (balanced over the eight warps afterwards)
+        int* und_n = reinterpret_cast<int*>(tmem_slot + 1);               // spare word next to the TMEM address slot
+        int* und_rows = rcode + TM;                                         // the fp16-overflow flags kept there were consumed above
+        if (et == 0) *und_n = 0;
+        epi_sync();
         if (et < TM) {
             const float bound = fminf(rbest[et], rbest[TM + et]) + tie_threshold(zsq_s[et], emax, sqrt_d);
-            const int ca = rcnt[et], cb2 = rcnt[TM + et];
+            const int my_ca = rcnt[et], my_cb = rcnt[TM + et];
             int keep = 0, code = -1;
-            if (((ca | cb2) >> 31) == 0) {
-                for (int i = 0; i < ca; ++i) if (cand_d[i * 256 + et] <= bound) { ++keep; code = cand_c[i * 256 + et]; }
-                for (int i = 0; i < cb2; ++i) if (cand_d[i * 256 + TM + et] <= bound) { ++keep; code = cand_c[i * 256 + TM + et]; }
+            if (((my_ca | my_cb) >> 31) == 0) {
+                for (int i = 0; i < my_ca; ++i) if (cand_d[i * 256 + et] <= bound) { ++keep; code = cand_c[i * 256 + et]; }
+                for (int i = 0; i < my_cb; ++i) if (cand_d[i * 256 + TM + et] <= bound) { ++keep; code = cand_c[i * 256 + TM + et]; }
             }
-            rcode[et] = (keep == 1) ? code : -1;
+            const int64_t g = r0 + et;
+            if (g < p.N) {
+                if (keep == 1) { rcode[et] = code; p.idx_out[g] = (int64_t)code; }
+                else { rcode[et] = -1; und_rows[atomicAdd(und_n, 1)] = et; }
+            } else rcode[et] = 0;
         }
         epi_sync();
 
-        // ---- exact re-rank of the near-tied rows (one warp per row): ONLY the surviving candidates are evaluated -----------
+        // ---- exact re-rank of the near-tied rows (one warp per row, round-robin over the work list): ONLY the surviving
+        //      candidates are evaluated -------------------------------------------------------------------------------------
         float* xbuf = reinterpret_cast<float*>(smemZ);          // staging: every MMA has completed (last tfull), the operand tiles are free
         float sse_local = 0.f;
-        int undecided_local = 0;
-        for (int rr = 0; rr < TM / 8; ++rr) {
-            const int rw = ew * (TM / 8) + rr;
+        const int n_und = *und_n;
+        for (int wi = ew; wi < n_und; wi += 8) {
+            const int rw = und_rows[wi];
             const int64_t g = r0 + rw;
-            if (g >= p.N) break;
-            int code = rcode[rw];
-            if (code < 0) {
-                ++undecided_local;
-                const float* zrow = p.z + g * p.D;
-                const int ca = rcnt[rw], cb2 = rcnt[TM + rw];
-                float dist = INFINITY; int c2 = 0x7fffffff;
-                bool have = false;
-                if (((ca | cb2) >> 31) == 0) {
-                    const float bound = fminf(rbest[rw], rbest[TM + rw]) + tie_threshold(zsq_s[rw], emax, sqrt_d);
-                    float dme = INFINITY; int cme = 0x7fffffff;
-                    if (lane < ca) { dme = cand_d[lane * 256 + rw]; cme = cand_c[lane * 256 + rw]; }
-                    else if (lane < ca + cb2) { dme = cand_d[(lane - ca) * 256 + TM + rw]; cme = cand_c[(lane - ca) * 256 + TM + rw]; }
-                    const bool keep = dme <= bound;
-                    const unsigned kmask = __ballot_sync(0xffffffffu, keep);
-                    const int nk = __popc(kmask);
-                    have = nk > 0;
-                    // The fp32 dot product is ONE sequential FMA chain (bit-exactness with the strict kernel), so a lane walking
-                    // global memory pays an L2 round trip every few steps (ncu: 5 us per row).  Instead the warp stages the z row
-                    // and up to four candidate rows in shared memory with coalesced loads (the operand tiles are dead by now),
-                    // and one lane per candidate runs its chain from there.
-                    float* xz = xbuf + ew * (5 * 256);
-                    int* xc = reinterpret_cast<int*>(xbuf + 8 * 5 * 256) + ew * 32;
-                    if (keep) xc[__popc(kmask & ((1u << lane) - 1u))] = cme;
-                    for (int d = lane * 4; d < p.D; d += 128) *reinterpret_cast<float4*>(xz + d) = *reinterpret_cast<const float4*>(zrow + d);
-                    __syncwarp();
-                    for (int g0 = 0; g0 < nk; g0 += 4) {
-                        const int ng = min(4, nk - g0);
-                        for (int cc = 0; cc < ng; ++cc) {
-                            const float* erow = p.cb + (int64_t)xc[g0 + cc] * p.D;
-                            for (int d = lane * 4; d < p.D; d += 128)
-                                *reinterpret_cast<float4*>(xz + 256 * (1 + cc) + d) = __ldg(reinterpret_cast<const float4*>(erow + d));
-                        }
-                        __syncwarp();
-                        if (lane < ng) {
-                            const int code_l = xc[g0 + lane];
-                            const float dl = exact_distance_smem(xz, xz + 256 * (1 + lane), p.cb_sq[code_l], p.D, p.order);
-                            if (dl < dist || (dl == dist && code_l < c2)) { dist = dl; c2 = code_l; }
-                        }
-                        __syncwarp();
-                    }
-                }
-                if (!have) {
-                    // list overflow (more near-ties than it holds: duplicated codes) or no finite approximate distance at all
-                    // (fp16 overflow, NaN): exact scan of every code
-                    // more near-ties than the list holds (degenerate codebooks: duplicated codes): exact scan of every code
-                    for (int k = lane; k < p.K; k += 32) {
-                        const float dk = exact_distance(zrow, p.cb + (int64_t)k * p.D, p.cb_sq[k], p.D, p.order);
-                        if (dk < dist || (dk == dist && k < c2)) { dist = dk; c2 = k; }
-                    }
-                }
+            const float* zrow = p.z + g * p.D;
+            const int ca = rcnt[rw], cb2 = rcnt[TM + rw];
+            float dist = INFINITY; int c2 = 0x7fffffff;
+            bool have = false;
+            if (((ca | cb2) >> 31) == 0) {
+                const float bound = fminf(rbest[rw], rbest[TM + rw]) + tie_threshold(zsq_s[rw], emax, sqrt_d);
+                float dme = INFINITY; int cme = 0x7fffffff;
+                if (lane < ca) { dme = cand_d[lane * 256 + rw]; cme = cand_c[lane * 256 + rw]; }
+                else if (lane < ca + cb2) { dme = cand_d[(lane - ca) * 256 + TM + rw]; cme = cand_c[(lane - ca) * 256 + TM + rw]; }
+                const bool keep = dme <= bound;
+                unsigned kmask = __ballot_sync(0xffffffffu, keep);
+                have = kmask != 0;
+                // The fp32 dot product is ONE sequential FMA chain (bit-exactness with the strict kernel), so a lane walking global
+                // memory pays an L2 round trip every few steps (ncu: 5 us per row).  Instead the warp stages the z row and up to
+                // four candidate rows in shared memory with coalesced loads issued back to back (the operand tiles are dead by
+                // now), and one lane per candidate runs its chain from there.
+                float* xz = xbuf + ew * (5 * 256);
+                while (kmask) {
+                    int codes4[4]; int ng = 0;
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const float od = __shfl_xor_sync(0xffffffffu, dist, o);
-                    const int oc = __shfl_xor_sync(0xffffffffu, c2, o);
-                    if (od < dist || (od == dist && oc < c2)) { dist = od; c2 = oc; }
+                    for (int cc = 0; cc < 4; ++cc) {
+                        codes4[cc] = -1;
+                        if (kmask) { codes4[cc] = __shfl_sync(0xffffffffu, cme, __ffs(kmask) - 1); kmask &= kmask - 1; ++ng; }
+                    }
+                    float4 zr[2], er[4][2];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int d = lane * 4 + h * 128;
+                        if (d < p.D) {
+                            zr[h] = *reinterpret_cast<const float4*>(zrow + d);
+#pragma unroll
+                            for (int cc = 0; cc < 4; ++cc)
+                                if (codes4[cc] >= 0) er[cc][h] = __ldg(reinterpret_cast<const float4*>(p.cb + (int64_t)codes4[cc] * p.D + d));
+                        }
+                    }
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int d = lane * 4 + h * 128;
+                        if (d < p.D) {
+                            *reinterpret_cast<float4*>(xz + d) = zr[h];
+#pragma unroll
+                            for (int cc = 0; cc < 4; ++cc)
+                                if (codes4[cc] >= 0) *reinterpret_cast<float4*>(xz + 256 * (1 + cc) + d) = er[cc][h];
+                        }
+                    }
+                    __syncwarp();
+                    if (lane < ng) {
+                        int code_l = codes4[0];
+#pragma unroll
+                        for (int cc = 1; cc < 4; ++cc) code_l = (lane == cc) ? codes4[cc] : code_l;
+                        const float dl = exact_distance_smem(xz, xz + 256 * (1 + lane), p.cb_sq[code_l], p.D, p.order);
+                        if (dl < dist || (dl == dist && code_l < c2)) { dist = dl; c2 = code_l; }
+                    }
+                    __syncwarp();
                 }
-                code = c2;
-                if (code < 0 || code >= p.K) code = 0;    // NaN rows: keep memory-safe (torch.argmin would return the NaN position)
-                if (lane == 0) rcode[rw] = code;
             }
-            if (lane == 0) p.idx_out[g] = (int64_t)code;
+            if (!have) {
+                // list overflow (more near-ties than it holds: duplicated codes) or no finite approximate distance at all
+                // (fp16 overflow, NaN): exact scan of every code
+                for (int k = lane; k < p.K; k += 32) {
+                    const float dk = exact_distance(zrow, p.cb + (int64_t)k * p.D, p.cb_sq[k], p.D, p.order);
+                    if (dk < dist || (dk == dist && k < c2)) { dist = dk; c2 = k; }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float od = __shfl_xor_sync(0xffffffffu, dist, o);
+                const int oc = __shfl_xor_sync(0xffffffffu, c2, o);
+                if (od < dist || (od == dist && oc < c2)) { dist = od; c2 = oc; }
+            }
+            int code = c2;
+            if (code < 0 || code >= p.K) code = 0;        // NaN rows: keep memory-safe (torch.argmin would return the NaN position)
+            if (lane == 0) { rcode[rw] = code; p.idx_out[g] = (int64_t)code; }
         }
-        __syncwarp();
+        epi_sync();                                                         // every row of the CTA has its code
 
         // ---- finish, 8 rows in flight per warp: q = z + (e - z), sum (e - z)^2, EMA cluster sums (z re-read from L2) ----------
         for (int rr = 0; rr < TM / 8; rr += 8) {
@@ -544,14 +565,13 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmEh, const FusedParams p) {
         }
         sse_local = warp_sum(sse_local);
         if (lane == 0) red_s[ew] = sse_local;
-        undecided_local = __shfl_sync(0xffffffffu, undecided_local, 0);
         epi_sync();
         if (et == 0 && p.sse) {
             double t = 0.0;
             for (int i = 0; i < 8; ++i) t += (double)red_s[i];
             atomicAdd(p.sse, t);
         }
-        if (lane == 0 && p.undecided && undecided_local) atomicAdd(p.undecided, undecided_local);
+        if (et == 0 && p.undecided && n_und) atomicAdd(p.undecided, n_und);
     }
     ptx::tc_fence_before();
     __syncthreads();
