@@ -230,7 +230,8 @@ int vqb_vq_assign_tc(const float* z, const float* codebook, int order, float* q_
  * launch writes idx, q, sum (e-z)^2, the histogram and the EMA cluster sums.  Replaces vector_quantizers.py:37-61, 142-166.
  *   cb_half [K][D] fp16 and cb_sq [K] fp32: produced by vqb_vq_prep_codebook (any codebook) or by vqb_vq_ema_update_prep
  *   (the EMA path: the update kernel leaves them for the NEW codebook, so the next step needs no preparation launch).
- * Needs D % 64 == 0, D <= 256, K % 8 == 0, K <= 65528.  sse / counts / dw / undecided_rows_out: caller zero-fills. */
+ * Needs D % 64 == 0, D <= 256, K % 8 == 0, K <= 65528.  sse / counts / dw / undecided_rows_out: caller zero-fills;
+ * undecided_rows_out (may be NULL) is int[2]: rows that took the exact re-rank, and those among them that scanned every code. */
 int vqb_vq_prep_codebook(const float* codebook, void* cb_half, float* cb_sq, int K, int D, void* stream);
 int vqb_vq_fused(const float* z, const float* codebook, const void* cb_half, const float* cb_sq, int order, float* q_out,
                  int64_t* idx_out, double* sse, float* counts, float* dw, int64_t N, int K, int D, int* undecided_rows_out,

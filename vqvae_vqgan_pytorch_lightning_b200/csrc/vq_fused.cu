@@ -119,7 +119,7 @@ struct FusedParams {
     double* sse;                 // [1] or NULL
     float* counts;               // [K] or NULL
     float* dw;                   // [K][D] or NULL
-    int* undecided;              // [1] or NULL: rows that took the exact path
+    int* undecided;              // [2] or NULL: rows that took the exact re-rank, rows among them that needed the full scan
 };
 
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
@@ -508,6 +508,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmEh, const FusedParams p) {
             if (!have) {
                 // list overflow (more near-ties than it holds: duplicated codes) or no finite approximate distance at all
                 // (fp16 overflow, NaN): exact scan of every code
+                if (lane == 0 && p.undecided) atomicAdd(p.undecided + 1, 1);
                 for (int k = lane; k < p.K; k += 32) {
                     const float dk = exact_distance(zrow, p.cb + (int64_t)k * p.D, p.cb_sq[k], p.D, p.order);
                     if (dk < dist || (dk == dist && k < c2)) { dist = dk; c2 = k; }

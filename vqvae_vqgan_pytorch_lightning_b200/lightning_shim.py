@@ -1,8 +1,9 @@
 """Minimal stand-in for the part of pytorch_lightning that the reference's VQVAE module touches
 (vqvae/model.py: self.log, self.optimizers(), self.manual_backward, self.trainer.{num_training_batches,optimizers},
 self.current_epoch, automatic_optimization and the fit-loop hooks), plus a one-process-per-GPU data-parallel
-Trainer.  pytorch_lightning is not installable in the build image; when it is importable the real
-`pl.LightningModule` is used as the base class instead and this Trainer remains available as the B200 fit loop.
+Trainer.  This class is ALWAYS the base of VQVAE, also when pytorch_lightning is importable: the fused optimizers, the EMA
+statistics all-reduce and the gradient scaling are wired up by Trainer.attach, which a stock pl.Trainer would not do
+(INTEGRATION.md shows how to drive the module from a Lightning-style loop).
 
 Data parallelism (reference: Lightning DDPStrategy, vqvae/train.py:128-131): the global batch is sharded across
 ranks; after backward the flat gradient buffer of each FusedAdamW is SUM-all-reduced with NCCL over NVLink in one
@@ -16,19 +17,13 @@ import torch
 import torch.distributed as dist
 from torch import nn
 
-try:                                    # pragma: no cover - not installed in the build image
-    import pytorch_lightning as _pl
-    _Base = _pl.LightningModule
-    HAVE_LIGHTNING = True
-except Exception:
-    _Base = nn.Module
-    HAVE_LIGHTNING = False
+HAVE_LIGHTNING = False            # kept for callers that branched on it: the shim never defers to pytorch_lightning
 
 
-class LightningModule(_Base):
+class LightningModule(nn.Module):
     """The subset of pl.LightningModule used by vqvae/model.py."""
 
-    if not HAVE_LIGHTNING:
+    if True:
         def __init__(self):
             super().__init__()
             self.trainer: Optional['Trainer'] = None

@@ -185,7 +185,9 @@ class VQVAE(BaseVQVAE, LightningModule):
     def on_train_epoch_end(self):
         if (self.reinit_every_n_epochs is not None and self.current_epoch % self.reinit_every_n_epochs == 0
                 and self.current_epoch > 0):
-            self.quantizer.reinit_unused_codes(self.quantizer.get_codebook_usage(self.train_epoch_usage_count.float())[0])
+            # under data parallelism the usage counts are summed over ranks and rank 0's draw is broadcast (base_quantizer.py)
+            self.quantizer.reinit_unused_codes(self.quantizer.get_codebook_usage(
+                self.quantizer.reduce_usage(self.train_epoch_usage_count.float()))[0])
         self.train_epoch_usage_count = None
 
     def on_train_end(self):
@@ -194,14 +196,33 @@ class VQVAE(BaseVQVAE, LightningModule):
 
     @torch.no_grad()
     def validation_step(self, batch: Any, batch_index: int):
-        """model.py:309-356 (MSE branch): returns the validation loss; usage counts kept for on_validation_epoch_end."""
+        """model.py:309-356: the three criterion branches of training_step without the optimizers -- VQGAN (forward_autoencoder +
+        forward_discriminator; no adaptive weight and no R1 outside training, loss.py:127,147), LPIPS only, plain MSE -- and the
+        seven validation/* scalars; usage counts are kept for on_validation_epoch_end (the reference's `else + used_indices`
+        keeps the LAST batch only, defect B3, replicated)."""
         images = self.preprocess_batch(batch[0] if isinstance(batch, tuple) else batch)
         x_recon, q_loss, used_indices = self.forward(images)
-        l2_loss = self.criterion(x_recon, images)
-        loss = q_loss + l2_loss
+        zero = torch.zeros(1, device=images.device)
+        if isinstance(self.criterion, VQLPIPSWithDiscriminator):
+            res = self.criterion.forward_autoencoder(q_loss, images, x_recon, self.current_epoch,
+                                                     last_layer=self.decoder.conv_out.weight)
+            loss, l1_loss, l2_loss, p_loss, g_loss, _ = res
+            step = (self.current_epoch * self.trainer.num_training_batches) + batch_index
+            _, d_loss, _ = self.criterion.forward_discriminator(images, x_recon, self.current_epoch, step)
+        elif isinstance(self.criterion, VQLPIPS):
+            loss, l1_loss, l2_loss, p_loss = self.criterion(q_loss, images, x_recon)
+            g_loss, d_loss = zero, zero
+        else:
+            l2_loss = self.criterion(x_recon, images)
+            l1_loss, g_loss, p_loss, d_loss = zero, zero, zero, zero
+            loss = q_loss + l2_loss
         self.log('validation/loss', loss)
+        self.log('validation/l1_loss', l1_loss)
         self.log('validation/l2_loss', l2_loss)
         self.log('validation/quant_loss', q_loss)
+        self.log('validation/perc_loss', p_loss)
+        self.log('validation/gen_loss', g_loss)
+        self.log('validation/disc_loss', d_loss)
         self.val_epoch_usage_count = torch.bincount(used_indices.view(-1), minlength=self.cb_size)
         return loss
 
@@ -222,8 +243,8 @@ class VQVAE(BaseVQVAE, LightningModule):
         dev = next(self.parameters()).device
         self._test_sse = torch.zeros((), dtype=torch.float64, device=dev)
         self._test_elems = 0
-        self._test_min = torch.full((), float('inf'), device=dev)
-        self._test_max = torch.full((), float('-inf'), device=dev)
+        self._test_min = torch.zeros((), device=dev)          # torchmetrics PeakSignalNoiseRatio(data_range=None) starts both at 0
+        self._test_max = torch.zeros((), device=dev)
         self.test_usage_count = None
         self.test_ssim = self.test_rfid = None
         try:
@@ -231,8 +252,10 @@ class VQVAE(BaseVQVAE, LightningModule):
             self.test_ssim = StructuralSimilarityIndexMeasure().to(dev)
             from torchmetrics.image.fid import FrechetInceptionDistance
             self.test_rfid = FrechetInceptionDistance().to(dev)
-        except Exception:                # not installed (or its Inception weights are not downloadable): MSE / PSNR / usage only
-            pass
+        except Exception as e:           # not installed (or its Inception weights are not downloadable): MSE / PSNR / usage only
+            import warnings
+            warnings.warn(f'torchmetrics SSIM / rFID unavailable ({type(e).__name__}: {e}); only MSE, PSNR and codebook usage are logged')
+            self.test_ssim = self.test_rfid = None
 
     @torch.no_grad()
     def test_step(self, images: Any, _: int = 0):
@@ -243,8 +266,7 @@ class VQVAE(BaseVQVAE, LightningModule):
         target = target.contiguous()
         counts = torch.bincount(used_indices.view(-1), minlength=self.cb_size)
         self.test_usage_count = counts if self.test_usage_count is None else self.test_usage_count + counts
-        mse, _l1 = ops.mse_l1(reconstructions, target)
-        self._test_sse += mse.double() * target.numel()
+        self._test_sse += ops.diff_sums(reconstructions, target)[0]                   # the kernel's fp64 sum of squared errors
         self._test_elems += target.numel()
         lo, hi = torch.aminmax(target)
         self._test_min = torch.minimum(self._test_min, lo)
@@ -252,7 +274,8 @@ class VQVAE(BaseVQVAE, LightningModule):
         if self.test_ssim is not None:
             self.test_ssim.update(reconstructions, target)
         if self.test_rfid is not None:
-            to_u8 = lambda t: (t.clamp(0, 1) * 255).to(torch.uint8)
+            # torchvision ConvertImageDtype(torch.uint8) on float images (model.py:543-545): x * (255 + 1 - 1e-3), truncated
+            to_u8 = lambda t: t.mul(255.999).to(torch.uint8)
             self.test_rfid.update(to_u8(reconstructions), real=False)
             self.test_rfid.update(to_u8(target), real=True)
 
@@ -309,6 +332,37 @@ class VQVAE(BaseVQVAE, LightningModule):
             self.automatic_optimization = False
             return [ae_optimizer, disc_optimizer], []
         return ae_optimizer
+
+    # ---- reference checkpoints (vqvae/train.py:106-111, vqvae/evaluate.py:48-49) ---------------------------------
+    @classmethod
+    def load_from_checkpoint(cls, checkpoint_path, map_location=None, strict: bool = True, **kwargs):
+        """pl.LightningModule.load_from_checkpoint for the reference's Lightning `.ckpt` files: a torch pickle holding
+        `state_dict` (keys `encoder.* / decoder.* / quantizer.* [/ criterion.*]`, the names and shapes this package keeps) and,
+        when the reference saved them, `hyper_parameters`.  Constructor arguments come from **kwargs exactly as in the reference
+        call sites (`strict=False, image_size=..., ae_conf=..., q_conf=..., l_conf=..., t_conf=..., init_cb=False,
+        load_loss=False`), falling back to the checkpoint's hyper_parameters.  With strict=False, keys of sub-modules that were
+        not built (e.g. `criterion.*` under load_loss=False) are ignored, as Lightning does."""
+        ckpt = torch.load(checkpoint_path, map_location=map_location or 'cpu', weights_only=False)
+        hp = dict(ckpt.get('hyper_parameters') or {})
+        hp.update(kwargs)
+        missing = [k for k in ('image_size', 'ae_conf', 'q_conf') if k not in hp]
+        if missing:
+            raise ValueError(f'load_from_checkpoint: missing constructor arguments {missing} (not in the checkpoint either)')
+        hp.setdefault('l_conf', None)
+        hp.setdefault('t_conf', None)
+        hp.setdefault('init_cb', False)
+        model = cls(**hp)
+        state = ckpt['state_dict'] if 'state_dict' in ckpt else ckpt
+        result = model.load_state_dict(state, strict=strict)
+        if not strict and result.missing_keys:
+            import warnings
+            warnings.warn(f'load_from_checkpoint: {len(result.missing_keys)} tensors keep their initial values '
+                          f'(first: {result.missing_keys[0]})')
+        model._checkpoint_extras = {k: ckpt[k] for k in ('epoch', 'global_step', 'optimizer_states') if k in ckpt}
+        if map_location is not None and map_location != 'cpu':
+            model = model.to(map_location)
+        ops.bump_weights_epoch()
+        return model
 
     # ---- two-stage-model API (model.py:458-489) -------------------------------------------------------------
     @torch.no_grad()

@@ -55,14 +55,33 @@ class BaseVectorQuantizer(ABC, nn.Module):
         return normalized, perplexity, used
 
     @torch.no_grad()
+    def reduce_usage(self, index_count: torch.Tensor) -> torch.Tensor:
+        """Sum the per-rank code-usage counts over the data-parallel group (no-op for one process).  The reference re-initialises
+        from each rank's own last batch, so its replicas diverge; here every rank sees the same global counts."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            index_count = index_count.clone()
+            dist.all_reduce(index_count, op=dist.ReduceOp.SUM)
+        return index_count
+
+    @torch.no_grad()
     def reinit_unused_codes(self, codebook_usage: torch.Tensor):
-        """Re-sample dead codes from live ones (base_quantizer.py:81-102); epoch-level, K-sized."""
+        """Re-sample dead codes from live ones (base_quantizer.py:81-102); epoch-level, K-sized.  Data parallel: the multinomial
+        draw happens on rank 0 only and is broadcast, so that all replicas keep identical codebooks (`codebook_usage` must be the
+        same on every rank: see reduce_usage)."""
+        import torch.distributed as dist
         unused = torch.nonzero(codebook_usage == 0.).squeeze(1)
         n_unused = unused.shape[0]
         if n_unused > 0:
-            det = torch.are_deterministic_algorithms_enabled()
-            torch.use_deterministic_algorithms(False)
-            sampled = torch.multinomial(codebook_usage, n_unused, replacement=True)
-            torch.use_deterministic_algorithms(det)
+            multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+            if not multi or dist.get_rank() == 0:
+                det = torch.are_deterministic_algorithms_enabled()
+                torch.use_deterministic_algorithms(False)
+                sampled = torch.multinomial(codebook_usage, n_unused, replacement=True)
+                torch.use_deterministic_algorithms(det)
+            else:
+                sampled = torch.empty(n_unused, dtype=torch.int64, device=codebook_usage.device)
+            if multi:
+                dist.broadcast(sampled, src=0)
             self.codebook.weight[unused] = self.codebook.weight[sampled].clone()
             ops.bump_weights_epoch()

@@ -532,6 +532,15 @@ def mse_l1(a, b):
     return DiffLossFn.apply(a, b)
 
 
+@torch.no_grad()
+def diff_sums(a, b) -> torch.Tensor:
+    """-> fp64 [sum (a-b)^2, sum |a-b|] (the raw accumulators of vqb_diff_sums; evaluation metrics, model.py:491-562)"""
+    a, b = as_nhwc(a), as_nhwc(b)
+    sums = torch.zeros(2, dtype=torch.float64, device=a.device)
+    call('vqb_diff_sums', ptr(a), dt(a), ptr(b), dt(b), ptr(sums), a.numel(), stream())
+    return sums
+
+
 # ------------------------------------------------------------------------------------------------------
 # vector quantisation
 # ------------------------------------------------------------------------------------------------------
@@ -596,8 +605,10 @@ def vq_assign_raw(flat: torch.Tensor, codebook: torch.Tensor, order: int, want_q
     if use_tc is None:
         use_tc = get_precision().name == 'fast'
     if use_tc and use_tc != 'legacy' and _fused_vq_ok(flat, k, d):
-        scal = torch.zeros(2, dtype=torch.float64, device=dev)           # [sse | undecided-row counter (int32 in the low word)]
-        sse, und = scal[:1], scal[1:].view(torch.int32)[:1]
+        scal = torch.zeros(2, dtype=torch.float64, device=dev)           # [sse | int32 x 2: re-ranked rows, full-scan rows]
+        sse, und2 = scal[:1], scal[1:].view(torch.int32)
+        und = und2[:1]
+        vq_assign_raw.last_fullscan = und2[1:]
         hf, sq = (prep or CodebookPrep()).get(codebook)
         cb = codebook.detach()
         call('vqb_vq_fused', ptr(flat), ptr(cb), ptr(hf), ptr(sq), order, ptr(q), ptr(idx), ptr(sse), ptr(counts), ptr(dw),

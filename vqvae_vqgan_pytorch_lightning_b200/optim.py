@@ -4,6 +4,14 @@ Replaces torch.optim.AdamW as configured by VQVAE.configure_optimizers (referenc
 update rule and param-group interface (`param_groups[i]['lr']` is what on_train_batch_start rewrites every step,
 model.py:216-218), but all tensors of a group live in ONE contiguous fp32 range so that the update is one kernel
 launch per group (vqb_adamw) and the data-parallel gradient all-reduce is one NCCL call on one buffer.
+
+Differences from torch.optim.AdamW, both invisible on the reference's path: (1) a parameter of a group that receives no
+gradient in a step is still decayed (its gradient view is zero), where torch skips `grad is None` tensors -- every tensor
+the reference hands to its optimizers gets a gradient in every step (frozen tensors are excluded at construction);
+(2) parameters become views of the flat buffer: moving or casting the module AFTER the optimizer was built (model.to(...))
+breaks the views, exactly as it invalidates a torch optimizer's state.
+state_dict() / load_state_dict() speak torch.optim.AdamW's per-parameter format (`state[i] = {step, exp_avg, exp_avg_sq}`),
+so the optimizer_states of a reference Lightning checkpoint resume the moments and the bias-correction step.
 """
 from __future__ import annotations
 
@@ -52,6 +60,56 @@ class FusedAdamW(torch.optim.Optimizer):
         self.step_count = 0
         self.grad_scale = 1.0       # set to 1/world_size by the data-parallel trainer (after a SUM all-reduce)
         ops.bump_weights_epoch()
+
+    # ---- checkpointing in torch.optim.AdamW's format ---------------------------------------------------------------------
+    def _flat_params(self):
+        return [p for ps in self._live for p in ps]
+
+    def state_dict(self):
+        index, packed_groups, live_ids = {}, [], {id(p) for p in self._flat_params()}
+        for g in self.param_groups:
+            pg = {k: v for k, v in g.items() if k != 'params'}
+            pg['params'] = []
+            for p in g['params']:
+                index.setdefault(id(p), len(index))
+                pg['params'].append(index[id(p)])
+            packed_groups.append(pg)
+        state, off = {}, 0
+        for p in self._flat_params():
+            n = p.numel()
+            if self.step_count > 0:
+                state[index[id(p)]] = {'step': torch.tensor(float(self.step_count)),
+                                       'exp_avg': self.exp_avg[off:off + n].view(p.shape).clone(),
+                                       'exp_avg_sq': self.exp_avg_sq[off:off + n].view(p.shape).clone()}
+            off += n
+        return {'state': state, 'param_groups': packed_groups}
+
+    @torch.no_grad()
+    def load_state_dict(self, state_dict) -> None:
+        groups = state_dict['param_groups']
+        if len(groups) != len(self.param_groups) or any(len(a['params']) != len(b['params']) for a, b in zip(groups, self.param_groups)):
+            raise ValueError('loaded state dict has different parameter groups')
+        index = {}
+        for saved, g in zip(groups, self.param_groups):
+            for k, v in saved.items():
+                if k != 'params':
+                    g[k] = v
+            for i, p in zip(saved['params'], g['params']):
+                index[id(p)] = i
+        steps, off = set(), 0
+        for p in self._flat_params():
+            n = p.numel()
+            st = state_dict['state'].get(index[id(p)])
+            if st is None:
+                self.exp_avg[off:off + n].zero_(); self.exp_avg_sq[off:off + n].zero_()
+            else:
+                self.exp_avg[off:off + n].copy_(st['exp_avg'].reshape(-1).to(self.exp_avg.device, torch.float32))
+                self.exp_avg_sq[off:off + n].copy_(st['exp_avg_sq'].reshape(-1).to(self.exp_avg.device, torch.float32))
+                steps.add(int(float(st['step'])))
+            off += n
+        if len(steps) > 1:
+            raise ValueError(f'FusedAdamW keeps ONE step counter; the loaded state has {sorted(steps)}')
+        self.step_count = steps.pop() if steps else 0
 
     def zero_grad(self, set_to_none: bool = False) -> None:      # grads must stay views of flat_grad
         self.flat_grad.zero_()
