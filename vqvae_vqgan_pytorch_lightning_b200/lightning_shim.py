@@ -6,8 +6,10 @@ statistics all-reduce and the gradient scaling are wired up by Trainer.attach, w
 (INTEGRATION.md shows how to drive the module from a Lightning-style loop).
 
 Data parallelism (reference: Lightning DDPStrategy, vqvae/train.py:128-131): the global batch is sharded across
-ranks; after backward the flat gradient buffer of each FusedAdamW is SUM-all-reduced with NCCL over NVLink in one
-call and scaled by 1/world inside the AdamW kernel; EMA cluster statistics are all-reduced by the quantizer.
+ranks; the flat gradient buffer of each FusedAdamW is cut into ~25 MB buckets laid out in the order the backward pass
+completes them, and every bucket is SUM-all-reduced with NCCL over NVLink (async, on NCCL's stream) as soon as its last
+gradient has been accumulated -- overlapped with the rest of backward, like DDP's bucketed reducer; the 1/world scaling
+happens inside the AdamW kernel; EMA cluster statistics are all-reduced by the quantizer in ONE [counts | dw] buffer.
 """
 from __future__ import annotations
 
@@ -55,7 +57,11 @@ class LightningModule(nn.Module):
 class Trainer:
     """One-process-per-GPU fit loop (rank / world from torch.distributed when initialised)."""
 
-    def __init__(self, max_epochs: int = 1, num_training_batches: Optional[int] = None):
+    def __init__(self, max_epochs: int = 1, num_training_batches: Optional[int] = None, overlap_grad_sync: bool = True,
+                 bucket_bytes: int = 25 << 20):
+        self.overlap_grad_sync = overlap_grad_sync
+        self.bucket_bytes = bucket_bytes
+        self._buckets: Dict[int, list] = {}          # id(optimizer) -> [bucket state]
         self.max_epochs = max_epochs
         self.num_training_batches = num_training_batches or 0
         self.optimizers: List[torch.optim.Optimizer] = []
@@ -78,6 +84,26 @@ class Trainer:
         if q is not None and self.world_size > 1:
             q.world_size = self.world_size
             q.stats_allreduce = self._allreduce_stats
+        if self.world_size > 1 and self.overlap_grad_sync:
+            for o in self.optimizers:
+                if hasattr(o, 'buckets'):
+                    self._install_bucket_hooks(o)
+
+    def _install_bucket_hooks(self, opt) -> None:
+        """One post-accumulate hook per parameter: when the last gradient of a bucket has landed in the flat buffer, its
+        all-reduce is enqueued (async_op: NCCL's stream waits for the kernels issued so far and runs beside backward)."""
+        states = []
+        for (a, b, params) in opt.buckets(self.bucket_bytes):
+            st = {'range': (a, b), 'n': len(params), 'pending': len(params), 'handle': None}
+            states.append(st)
+            for p in params:
+                def hook(_p, st=st, opt=opt):
+                    st['pending'] -= 1
+                    if st['pending'] == 0 and st['handle'] is None:
+                        a_, b_ = st['range']
+                        st['handle'] = dist.all_reduce(opt.flat_grad[a_:b_], op=dist.ReduceOp.SUM, async_op=True)
+                p.register_post_accumulate_grad_hook(hook)
+        self._buckets[id(opt)] = states
 
     def _allreduce_stats(self, *tensors: torch.Tensor) -> None:
         for t in tensors:
@@ -89,7 +115,17 @@ class Trainer:
             return
         for o in (self.optimizers if optimizer is None else [optimizer]):
             flat = getattr(o, 'flat_grad', None)
-            if flat is not None:
+            states = self._buckets.get(id(o))
+            if flat is not None and states is not None:
+                # buckets whose reduction is already in flight: wait; the others (a tensor received no gradient): reduce now
+                for st in states:
+                    if st['handle'] is None:
+                        a_, b_ = st['range']
+                        st['handle'] = dist.all_reduce(flat[a_:b_], op=dist.ReduceOp.SUM, async_op=True)
+                for st in states:
+                    st['handle'].wait()
+                    st['handle'], st['pending'] = None, st['n']
+            elif flat is not None:
                 dist.all_reduce(flat, op=dist.ReduceOp.SUM)       # one NCCL call per optimizer; averaged in vqb_adamw
             else:
                 for g in o.param_groups:

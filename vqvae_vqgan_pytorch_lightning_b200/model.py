@@ -324,11 +324,14 @@ class VQVAE(BaseVQVAE, LightningModule):
             {'params': [param_dict[pn] for pn in sorted(decay)], 'weight_decay': weight_decay},
             {'params': [param_dict[pn] for pn in sorted(no_decay)], 'weight_decay': 0.0},
         ]
-        ae_optimizer = FusedAdamW(groups, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        # flat-buffer layout = expected order of gradient completion (reverse of construction = reverse of the forward pass):
+        # decoder.conv_out first, encoder.conv_in last, so that gradient buckets can be all-reduced during backward
+        rank = {id(p): i for i, p in enumerate(reversed(list(self.parameters())))}
+        ae_optimizer = FusedAdamW(groups, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, layout_rank=rank)
         if isinstance(self.criterion, VQLPIPSWithDiscriminator):
             # every discriminator tensor decays (model.py:431-433); manual optimisation with two optimizers (:436-438)
             disc_optimizer = FusedAdamW(list(self.criterion.discriminator.parameters()), lr=lr, betas=betas, eps=eps,
-                                        weight_decay=weight_decay)
+                                        weight_decay=weight_decay, layout_rank=rank)
             self.automatic_optimization = False
             return [ae_optimizer, disc_optimizer], []
         return ae_optimizer

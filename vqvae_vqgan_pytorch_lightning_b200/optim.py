@@ -23,7 +23,11 @@ from . import ops
 
 
 class FusedAdamW(torch.optim.Optimizer):
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, layout_rank=None):
+        """`layout_rank` (optional dict id(param) -> int): order of the tensors INSIDE each group's range of the flat buffers
+        (ascending).  The data-parallel trainer passes the expected order of gradient completion in the backward pass, so that
+        contiguous buckets of the flat gradient become ready -- and are all-reduced -- while the rest of backward still runs.
+        The membership and order of `param_groups` (what state_dict() refers to) is unaffected."""
         defaults = dict(lr=float(lr), betas=tuple(float(b) for b in betas), eps=float(eps), weight_decay=float(weight_decay))
         super().__init__(params, defaults)
         self._ranges = []          # per group: (start, end) in the flat buffers
@@ -32,6 +36,8 @@ class FusedAdamW(torch.optim.Optimizer):
         device = None
         for g in self.param_groups:
             ps = [p for p in g['params'] if p.requires_grad]
+            if layout_rank is not None:
+                ps.sort(key=lambda p: layout_rank.get(id(p), 1 << 30))
             for p in ps:
                 if p.dtype != torch.float32:
                     raise TypeError('FusedAdamW keeps fp32 master parameters')
@@ -60,6 +66,19 @@ class FusedAdamW(torch.optim.Optimizer):
         self.step_count = 0
         self.grad_scale = 1.0       # set to 1/world_size by the data-parallel trainer (after a SUM all-reduce)
         ops.bump_weights_epoch()
+
+    def buckets(self, max_bytes: int = 25 << 20):
+        """Contiguous ranges [(start, end, [params])] of the flat buffers of at most ~max_bytes, cut at tensor boundaries (a single
+        larger tensor is its own bucket) -- the unit of the overlapped gradient all-reduce (reference: DDP's 25 MB buckets)."""
+        out, cur, start, off = [], [], 0, 0
+        for p in self._flat_params():
+            n = p.numel()
+            if cur and (off + n - start) * 4 > max_bytes:
+                out.append((start, off, cur)); cur, start = [], off
+            cur.append(p); off += n
+        if cur:
+            out.append((start, off, cur))
+        return out
 
     # ---- checkpointing in torch.optim.AdamW's format ---------------------------------------------------------------------
     def _flat_params(self):
