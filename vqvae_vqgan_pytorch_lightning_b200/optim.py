@@ -22,6 +22,14 @@ import torch
 from . import ops
 
 
+ALIGN = 64          # every tensor starts on a 256-byte boundary of the flat buffers: the kernels read parameters (e.g. the codebook,
+                    # a view of flat_param) with 16-byte vector loads and TMA, and a 3-element bias must not shift its successors
+
+
+def _padded(n: int) -> int:
+    return (n + ALIGN - 1) // ALIGN * ALIGN
+
+
 class FusedAdamW(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, layout_rank=None):
         """`layout_rank` (optional dict id(param) -> int): order of the tensors INSIDE each group's range of the flat buffers
@@ -43,12 +51,12 @@ class FusedAdamW(torch.optim.Optimizer):
                     raise TypeError('FusedAdamW keeps fp32 master parameters')
                 device = device or p.device
             live.append(ps)
-            n = sum(p.numel() for p in ps)
+            n = sum(_padded(p.numel()) for p in ps)
             self._ranges.append((total, total + n))
             total += n
         if device is None or device.type != 'cuda':
             raise RuntimeError('FusedAdamW needs CUDA parameters (no CPU fallback)')
-        self.flat_param = torch.empty(total, dtype=torch.float32, device=device)
+        self.flat_param = torch.zeros(total, dtype=torch.float32, device=device)      # padding elements stay exactly zero
         self.flat_grad = torch.zeros(total, dtype=torch.float32, device=device)
         self.exp_avg = torch.zeros(total, dtype=torch.float32, device=device)
         self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=device)
@@ -61,7 +69,7 @@ class FusedAdamW(torch.optim.Optimizer):
                     view.copy_(p.data)
                     p.data = view                                   # parameters become views of the flat buffer
                     p.grad = self.flat_grad[off:off + n].view(p.shape)   # autograd accumulates in place into these views
-                    off += n
+                    off += _padded(n)
         self._live = live
         self.step_count = 0
         self.grad_scale = 1.0       # set to 1/world_size by the data-parallel trainer (after a SUM all-reduce)
@@ -75,7 +83,7 @@ class FusedAdamW(torch.optim.Optimizer):
             n = p.numel()
             if cur and (off + n - start) * 4 > max_bytes:
                 out.append((start, off, cur)); cur, start = [], off
-            cur.append(p); off += n
+            cur.append(p); off += _padded(n)
         if cur:
             out.append((start, off, cur))
         return out
@@ -100,7 +108,7 @@ class FusedAdamW(torch.optim.Optimizer):
                 state[index[id(p)]] = {'step': torch.tensor(float(self.step_count)),
                                        'exp_avg': self.exp_avg[off:off + n].view(p.shape).clone(),
                                        'exp_avg_sq': self.exp_avg_sq[off:off + n].view(p.shape).clone()}
-            off += n
+            off += _padded(n)
         return {'state': state, 'param_groups': packed_groups}
 
     @torch.no_grad()
@@ -125,7 +133,7 @@ class FusedAdamW(torch.optim.Optimizer):
                 self.exp_avg[off:off + n].copy_(st['exp_avg'].reshape(-1).to(self.exp_avg.device, torch.float32))
                 self.exp_avg_sq[off:off + n].copy_(st['exp_avg_sq'].reshape(-1).to(self.exp_avg.device, torch.float32))
                 steps.add(int(float(st['step'])))
-            off += n
+            off += _padded(n)
         if len(steps) > 1:
             raise ValueError(f'FusedAdamW keeps ONE step counter; the loaded state has {sorted(steps)}')
         self.step_count = steps.pop() if steps else 0
@@ -138,7 +146,7 @@ class FusedAdamW(torch.optim.Optimizer):
                 n = p.numel()
                 if p.grad is None or p.grad.data_ptr() != self.flat_grad.data_ptr() + 4 * off:
                     p.grad = self.flat_grad[off:off + n].view(p.shape)
-                off += n
+                off += _padded(n)
 
     @torch.no_grad()
     def step(self, closure=None):
