@@ -60,6 +60,9 @@ int vqb_crop_flip_normalize(const void* images, int in_dtype, void* out, int out
 /* NHWC (dtype in) -> NCHW fp32, y = x*scale + shift, optional clamp (base_autoencoder.py:52-61). */
 int vqb_nhwc_to_nchw(const void* x, int in_dtype, float* y, int64_t N, int64_t C, int64_t H, int64_t W,
                      float scale, float shift, int do_clamp, float lo, float hi, void* stream);
+/* fp32 [rows][C] -> bf16 [rows][2C] = [hi | lo], x ~ hi + lo to 16 mantissa bits: the operand layout of the split-precision
+ * tensor-core convolutions (vqb_conv2d_fwd impl 2 / 3), which keep the strict numeric mode's 1e-4 parity on tcgen05. */
+int vqb_split_hi_lo(const float* x, void* y, int64_t rows, int C, void* stream);
 /* dtype conversion of a flat buffer */
 int vqb_convert(const void* x, int in_dtype, void* y, int out_dtype, int64_t n, void* stream);
 
@@ -85,8 +88,12 @@ int vqb_unpack_conv_wgrad(const float* dwp, float* dw, int Co, int Ci, int KH, i
  * Convolution as implicit GEMM (replaces F.conv2d behind nn.Conv2d: autoencoder.py:55-61,102,114,133,153,170)
  *   y[n,oh,ow,co] = act( sum_{kh,kw,ci} x[n, oh*stride-pad+kh, ow*stride-pad+kw, ci] * w[co,ci,kh,kw]
  *                        + bias[co] ) * gain + residual[n,oh,ow,co]
- * impl 0 = fp32 SIMT (strict parity path), impl 1 = tcgen05/TMA bf16 (fast path; x,y bf16; Ci%64==0, Co%64==0).
- * wp is the packed weight for that impl (mode 0 for impl 0, mode 2 for impl 1).  bias / residual may be NULL.
+ * impl 0 = fp32 SIMT (odd shapes of the strict path), impl 1 = tcgen05/TMA bf16 (fast path; x,y bf16; Ci%64==0, Co%64==0),
+ * impl 2 / 3 = the same tcgen05 kernels on SPLIT-PRECISION operands (strict path, 1e-4 parity): x holds [hi | lo] bf16 halves
+ *   of Ci fp32 channels (vqb_split_hi_lo: 2*Ci bf16 channels), wp is the K-major pack (mode 2) of the fp32 weight
+ *   [wh | wh | wl] (impl 2: xh.wh + xl.wh + xh.wl) or [wh | wh | wl | wl] (impl 3: + xl.wl) along the input-channel axis,
+ *   all terms accumulated in one fp32 TMEM accumulator; y is normally fp32.
+ * wp is the packed weight for that impl (mode 0 for impl 0, mode 2 for impl 1-3).  bias / residual may be NULL.
  * dgrad is the same call on dy with the dgrad-packed weight (stride 1 only).
  * ---------------------------------------------------------------------------------------------------- */
 int vqb_conv2d_fwd(int impl, const void* x, int x_dtype, const void* wp, const float* bias, const void* residual,

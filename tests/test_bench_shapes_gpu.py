@@ -60,6 +60,7 @@ def test_tcgen05_conv_equals_simt_at_bench_shapes(V, n, hw, ci, co, k, res):
     dx_tc = ops._dgrad_raw(dy16, w, hw, hw, pad, 1, 1.0, torch.float32)
     dw_tc = ops._wgrad_raw(x16, dy16, w.shape, pad, 1, 1.0)
     V.set_precision('strict')
+    ops.set_strict_conv('simt')                      # the fp32 SIMT kernels are the yardstick here (strict mode's default is split tcgen05)
     x32 = x16.float()
     y_s = ops.conv2d(x32, w, None, r, pad=pad, out_dtype=torch.float32)
     e = rel(y_tc, y_s)
@@ -76,6 +77,7 @@ def test_tcgen05_conv_equals_simt_at_bench_shapes(V, n, hw, ci, co, k, res):
     wsub = torch.zeros(8, 8, k, k, dtype=torch.float64, device=dev, requires_grad=True)
     torch.nn.functional.conv2d(xs, wsub, padding=pad).backward(dys)
     t_tc, t_s = rel(dw_tc[:8, :8], wsub.grad), rel(dw_s[:8, :8], wsub.grad)
+    ops.set_strict_conv('tc3')
     assert e < 1e-4 and e_dx < 1e-4, (e, e_dx)
     # measured: SIMT 2e-6, tcgen05 1.0e-4 at the 4.2 M-pixel reductions (the tensor core's fp32 accumulator does not round to
     # nearest; the error grows with the length of the reduction kept in TMEM) -- bar 2e-4 there, 1e-4 elsewhere
@@ -100,6 +102,42 @@ def test_vq_at_bench_shapes(V, N, K, init):
     assert bad == 0, (exact, ties, bad)
     if init == 'normal':
         assert ties == 0 and exact == N                          # tie-free: bit-exact against the reference arithmetic
+
+
+@pytest.mark.parametrize('n,hw,ci,co,k,res', [(16, 256, 128, 128, 3, True), (16, 128, 256, 256, 3, False), (16, 64, 256, 256, 1, False),
+                                              (16, 16, 512, 512, 3, True)])
+def test_split_precision_conv_at_bench_layer_shapes(V, n, hw, ci, co, k, res):
+    """strict mode's tensor-core convolutions (bf16 hi/lo split operands, three products per multiply in one fp32 accumulator)
+    on genuine fp32 operands at the bench's layer shapes (B=16 keeps the float64 yardstick affordable): forward, input and weight
+    gradient against the fp32 SIMT kernels and, on a channel sub-block, against float64."""
+    ops = V.ops
+    torch.manual_seed(7)
+    dev = 'cuda'
+    V.set_precision('strict')
+    x = torch.randn(n, ci, hw, hw, device=dev).contiguous(memory_format=torch.channels_last)
+    w = torch.randn(co, ci, k, k, device=dev) / (ci * k * k) ** 0.5
+    r = torch.randn(n, co, hw, hw, device=dev).contiguous(memory_format=torch.channels_last) if res else None
+    dy = torch.randn(n, co, hw, hw, device=dev).contiguous(memory_format=torch.channels_last)
+    pad = k // 2
+    out = {}
+    for mode in ('tc3', 'tc4', 'simt'):
+        ops.set_strict_conv(mode)
+        out[mode] = (ops.conv2d(x, w, None, r, pad=pad, out_dtype=torch.float32), ops._dgrad_raw(dy, w, hw, hw, pad, 1, 1.0, torch.float32),
+                     ops._wgrad_raw(x, dy, w.shape, pad, 1, 1.0))
+    ops.set_strict_conv('tc3')
+    # float64 truth on a sub-block: first 8 output channels (forward), first 8 input channels (dgrad), 8x8 block (wgrad)
+    xd, wd, dyd = x.double(), w.double(), dy.double()
+    y64 = torch.nn.functional.conv2d(xd, wd[:8], padding=pad) + (r[:, :8].double() if res else 0)
+    wsub = torch.zeros(8, 8, k, k, dtype=torch.float64, device=dev, requires_grad=True)
+    torch.nn.functional.conv2d(xd[:, :8].contiguous(), wsub, padding=pad).backward(dyd[:, :8].contiguous())
+    for mode in ('tc3', 'tc4', 'simt'):
+        y, dx, dw = out[mode]
+        e_y, e_dw = rel(y[:, :8], y64), rel(dw[:8, :8], wsub.grad)
+        e_dx = rel(dx, out['simt'][1])
+        print(f'{mode}: fwd {e_y:.2e} dx-vs-simt {e_dx:.2e} dw {e_dw:.2e}')
+        # three-term split: 2^-16 per product, random signs; the weight gradient also carries the TMEM accumulation of its long
+        # pixel reduction (see test_tcgen05_conv_equals_simt_at_bench_shapes)
+        assert e_y < 2e-5 and e_dx < 2e-5 and e_dw < (1e-4 if mode != 'simt' else 2e-5), (mode, e_y, e_dx, e_dw)
 
 
 def test_cfg2_fast_against_strict_at_256(V):

@@ -1,5 +1,5 @@
 // C-ABI entry points for convolution: dispatch between the fp32 SIMT implicit GEMM (impl 0, conv_simt.cu) and
-// the tcgen05/TMA bf16 implicit GEMM (impl 1, conv_tc.cu).
+// the tcgen05/TMA bf16 implicit GEMM (impl 1, conv_tc.cu; impl 2 / 3 = the same kernels on split-precision operands).
 #include "common.cuh"
 
 int vqb_conv2d_fwd_simt(const void* x, int x_dtype, const float* wp, const float* bias, const void* residual, void* y,
@@ -11,7 +11,7 @@ int vqb_conv2d_dgrad_simt(const void* dy, int dy_dtype, const float* wd, void* d
                           int Co, int KH, int KW, int pad, int stride, cudaStream_t stream);
 int vqb_conv2d_fwd_tc(const void* x, const void* wp, const float* bias, const void* residual, void* y, int y_dtype, int N,
                       int H, int W, int Ci, int Co, int KH, int KW, int pad, int act, float alpha, float gain,
-                      cudaStream_t stream);
+                      cudaStream_t stream, int Cx);
 int vqb_conv2d_wgrad_tc(const void* x, const void* dy, float* dwp, int N, int H, int W, int Ci, int Co, int KH, int KW,
                         int pad, cudaStream_t stream);
 
@@ -26,7 +26,15 @@ extern "C" int vqb_conv2d_fwd(int impl, const void* x, int x_dtype, const void* 
         VQB_CHECK_ARG(x_dtype == VQB_BF16, "conv2d_fwd(tcgen05): x must be bf16");
         VQB_CHECK_ARG(stride == 1, "conv2d_fwd(tcgen05): stride must be 1");
         return vqb_conv2d_fwd_tc(x, wp, bias, residual, y, y_dtype, N, H, W, Ci, Co, KH, KW, pad, act, act_alpha, gain,
-                                 as_stream(stream));
+                                 as_stream(stream), Ci);
+    }
+    if (impl == 2 || impl == 3) {
+        // split-precision tcgen05 (strict numeric mode): x = [hi | lo] bf16 halves of Ci fp32 channels (2 * Ci channels), wp packed
+        // K-major with 3 (impl 2) or 4 (impl 3) weight blocks per tap -- see vqb_conv2d_fwd_tc
+        VQB_CHECK_ARG(x_dtype == VQB_BF16, "conv2d_fwd(tcgen05 split): x must hold bf16 [hi | lo] halves");
+        VQB_CHECK_ARG(stride == 1 && Ci % 64 == 0, "conv2d_fwd(tcgen05 split): stride must be 1 and Ci a multiple of 64");
+        return vqb_conv2d_fwd_tc(x, wp, bias, residual, y, y_dtype, N, H, W, (impl + 1) * Ci, Co, KH, KW, pad, act, act_alpha, gain,
+                                 as_stream(stream), 2 * Ci);
     }
     vqb_set_error("conv2d_fwd: unknown impl %d", impl);
     return VQB_ERR_ARG;

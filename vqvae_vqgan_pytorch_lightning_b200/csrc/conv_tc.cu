@@ -103,6 +103,7 @@ __device__ __forceinline__ float act_f(float v, int act, float alpha) {
 
 struct FwdParams {
     int N, H, W, Ci, Co, KH, KW, pad;
+    int Cx;              // channels of the x TENSOR (== Ci, or 2*Ci/terms for split-precision operands: the k loop wraps over [hi | lo])
     int tw, th, nb, tiles_w, tiles_h, tiles_n, co_tiles, BN, stages, MT;
     int num_tiles, ksteps, cchunks;
     // halo kernel only
@@ -291,7 +292,7 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         uint8_t* sa = smem + (size_t)stage * stage_bytes;
                         ptx::mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
                         for (int m = 0; m < p.MT; ++m)
-                            ptx::tma_load_4d(sa + m * a_tile, &tmA, &full[stage], cc * BK, w0[m] + kw - p.pad, h0[m] + kh - p.pad, n0[m]);
+                            ptx::tma_load_4d(sa + m * a_tile, &tmA, &full[stage], (cc * BK) % p.Cx, w0[m] + kw - p.pad, h0[m] + kh - p.pad, n0[m]);
                         ptx::tma_load_2d(sa + a_bytes, &tmB, &full[stage], tap * p.Ci + cc * BK, co0);
                         if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     }
@@ -391,7 +392,7 @@ conv_fwd_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                     ptx::mbar_wait(&emptyA[sa], pa ^ 1);
                     ptx::mbar_expect_tx(&fullA[sa], a_box_bytes * (uint32_t)p.MT);
                     for (int m = 0; m < p.MT; ++m)
-                        ptx::tma_load_4d(smemA + (size_t)sa * a_stage + m * a_tile, &tmA, &fullA[sa], cc * BK, w0[m] - 1, h0[m] - 1, n0[m]);
+                        ptx::tma_load_4d(smemA + (size_t)sa * a_stage + m * a_tile, &tmA, &fullA[sa], (cc * BK) % p.Cx, w0[m] - 1, h0[m] - 1, n0[m]);
                     if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
                     for (int tap = 0; tap < 9; ++tap) {
                         ptx::mbar_wait(&emptyB[sb], pb ^ 1);
@@ -508,7 +509,7 @@ conv_fwd_tc_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 for (int cc = 0; cc < p.cchunks; ++cc) {
                     ptx::mbar_wait(&emptyA[sa], pa ^ 1);
                     if (rank == 0) ptx::mbar_expect_tx(&fullA[sa], 2u * a_box_bytes);
-                    ptx::tma_load_4d_2sm(smemA + (size_t)sa * a_stage, &tmA, ptx::mapa_rank(ptx::smem_u32(&fullA[sa]), 0), cc * BK, w0 - 1,
+                    ptx::tma_load_4d_2sm(smemA + (size_t)sa * a_stage, &tmA, ptx::mapa_rank(ptx::smem_u32(&fullA[sa]), 0), (cc * BK) % p.Cx, w0 - 1,
                                          h0 - 1, n0);
                     if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
                     for (int tap = 0; tap < 9; ++tap) {
@@ -661,7 +662,7 @@ conv_fwd_tc_halo_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
                 for (int cc = 0; cc < p.cchunks; ++cc) {
                     ptx::mbar_wait(&emptyX[sx], px ^ 1);
                     ptx::mbar_expect_tx(&fullX[sx], x_box_bytes);
-                    ptx::tma_load_4d(smemX + (size_t)sx * x_stage, &tmX, &fullX[sx], cc * BK, w0 - 1, h0 - 1, n);
+                    ptx::tma_load_4d(smemX + (size_t)sx * x_stage, &tmX, &fullX[sx], (cc * BK) % p.Cx, w0 - 1, h0 - 1, n);
                     if (++sx == p.a_stages) { sx = 0; px ^= 1; }
                     for (int tap = 0; tap < 9; ++tap) {
                         ptx::mbar_wait(&emptyW[sw], pw ^ 1);
@@ -1055,15 +1056,21 @@ extern "C" void vqb_set_halo_mode(int mode);
 static int g_halo_override = -1;
 extern "C" void vqb_set_halo_mode(int mode) { g_halo_override = mode; }
 
+// Cx: channels of the x tensor.  Cx == Ci is the plain bf16 convolution.  Split-precision operands (strict numeric mode): x holds
+// [hi | lo] bf16 halves of C fp32 channels (Cx = 2C) and the packed weight holds `terms` blocks per tap (Ci = terms * C):
+// [wh | wh | wl] (3 terms: xh.wh + xl.wh + xh.wl) or [wh | wh | wl | wl] (4 terms, + xl.wl); the k loop's channel coordinate
+// wraps modulo Cx, so the SAME kernels accumulate all terms in one fp32 TMEM accumulator.
 int vqb_conv2d_fwd_tc(const void* x, const void* wp, const float* bias, const void* residual, void* y, int y_dtype, int N,
                       int H, int W, int Ci, int Co, int KH, int KW, int pad, int act, float alpha, float gain,
-                      cudaStream_t stream) {
+                      cudaStream_t stream, int Cx) {
     VQB_CHECK_ARG(N > 0 && H > 0 && W > 0 && KH > 0 && KW > 0 && pad >= 0, "conv2d_fwd(tcgen05): bad geometry");
     VQB_CHECK_ARG(Ci % 64 == 0 && (Co % 64 == 0 || Co <= 16), "conv2d_fwd(tcgen05): need Ci %% 64 == 0 and (Co %% 64 == 0 or Co <= 16) (got %d, %d)", Ci, Co);
     VQB_CHECK_ARG(H + 2 * pad - KH + 1 == H && W + 2 * pad - KW + 1 == W, "conv2d_fwd(tcgen05): only 'same' convolutions");
     VQB_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)wp & 15) == 0 && ((uintptr_t)y & 15) == 0, "conv2d_fwd(tcgen05): unaligned pointer");
     FwdParams p;
-    p.N = N; p.H = H; p.W = W; p.Ci = Ci; p.Co = Co; p.KH = KH; p.KW = KW; p.pad = pad;
+    if (Cx <= 0) Cx = Ci;
+    VQB_CHECK_ARG(Cx % 64 == 0 && (2 * Ci) % Cx == 0, "conv2d_fwd(tcgen05): bad split-operand channel count %d for Ci %d", Cx, Ci);
+    p.N = N; p.H = H; p.W = W; p.Ci = Ci; p.Co = Co; p.KH = KH; p.KW = KW; p.pad = pad; p.Cx = Cx;
     p.narrow = (Co % 64 != 0);
     // narrow heads: UMMA N = 16, the weight box rows beyond Co are zero-filled by TMA
     p.BN = p.narrow ? 16 : ((Co % 256 == 0) ? 256 : ((Co % 128 == 0) ? 128 : 64));
@@ -1092,7 +1099,7 @@ int vqb_conv2d_fwd_tc(const void* x, const void* wp, const float* bias, const vo
         p.a_stages = 3;
         p.b_stages = (SMEM_LIMIT - 2048 - p.a_stages * p.a_tile_bytes) / b_stage; if (p.b_stages > 12) p.b_stages = 12;
         rc = make_weight_map(&tmB, wp, Co, KH * KW * Ci, p.BN / 2); if (rc) return rc;
-        rc = make_act_map(&tmA, x, N, H, W, Ci, p.pitch, p.th + 2, 1); if (rc) return rc;
+        rc = make_act_map(&tmA, x, N, H, W, Cx, p.pitch, p.th + 2, 1); if (rc) return rc;
         size_t smem = (size_t)p.a_stages * p.a_tile_bytes + (size_t)p.b_stages * b_stage + 1024 + 512;
         VQB_CUDA(cudaFuncSetAttribute(conv_fwd_tc_halo2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int clusters = p.num_tiles < sm_count() / 2 ? p.num_tiles : sm_count() / 2;
@@ -1111,7 +1118,7 @@ int vqb_conv2d_fwd_tc(const void* x, const void* wp, const float* bias, const vo
         p.a_stages = 2;
         const int tr_bytes = 8 * 32 * 36 * 4;                       // epilogue transpose tiles (8 warps)
         p.b_stages = (SMEM_LIMIT - 2048 - tr_bytes - p.a_stages * p.a_tile_bytes) / w_stage; if (p.b_stages > 12) p.b_stages = 12;
-        rc = make_act_map(&tmA, x, N, H, W, Ci, 10, 34, 1); if (rc) return rc;
+        rc = make_act_map(&tmA, x, N, H, W, Cx, 10, 34, 1); if (rc) return rc;
         size_t smem = (size_t)p.a_stages * p.a_tile_bytes + (size_t)p.b_stages * w_stage + 1024 + 512 + tr_bytes;
         VQB_CUDA(cudaFuncSetAttribute(conv_fwd_tc_halo_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
@@ -1133,7 +1140,7 @@ int vqb_conv2d_fwd_tc(const void* x, const void* wp, const float* bias, const vo
         p.b_stages = (SMEM_LIMIT - 2048 - p.a_stages * a_stage) / b_stage; if (p.b_stages > 12) p.b_stages = 12;
         VQB_CHECK_ARG(p.b_stages >= 2, "conv2d_fwd(tcgen05 halo): shared memory budget");
         p.stages = 0;
-        rc = make_act_map(&tmA, x, N, H, W, Ci, p.pitch, p.th + 2, 1); if (rc) return rc;
+        rc = make_act_map(&tmA, x, N, H, W, Cx, p.pitch, p.th + 2, 1); if (rc) return rc;
         size_t smem = (size_t)p.a_stages * a_stage + (size_t)p.b_stages * b_stage + 1024 + 512;
         VQB_CUDA(cudaFuncSetAttribute(conv_fwd_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
@@ -1148,7 +1155,7 @@ int vqb_conv2d_fwd_tc(const void* x, const void* wp, const float* bias, const vo
     p.num_tiles = ((ptiles + p.MT - 1) / p.MT) * p.co_tiles;
     const int stage_bytes = p.MT * BM * BK * 2 + p.BN * BK * 2;
     p.stages = (SMEM_LIMIT - 2048) / stage_bytes; if (p.stages > 8) p.stages = 8;
-    rc = make_act_map(&tmA, x, N, H, W, Ci, p.tw, p.th, p.nb); if (rc) return rc;
+    rc = make_act_map(&tmA, x, N, H, W, Cx, p.tw, p.th, p.nb); if (rc) return rc;
     size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256;
     VQB_CUDA(cudaFuncSetAttribute(conv_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();

@@ -131,6 +131,36 @@ __global__ void convert_kernel(const TI* __restrict__ x, TO* __restrict__ y, int
         st1(y + i, ld1(x + i));
 }
 
+// fp32 [rows][C] -> bf16 [rows][2C] = [hi | lo] with x ~ hi + lo (16 mantissa bits): the split-precision operand layout of the
+// strict numeric mode's tensor-core convolutions (conv_tc.cu: the k loop wraps over the two halves)
+__global__ void split_hi_lo_kernel(const float* __restrict__ x, bf16* __restrict__ y, int64_t rows, int C) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;          // one float4 per thread
+    const int c4 = C >> 2;
+    if (i >= rows * c4) return;
+    const int64_t r = i / c4;
+    const int c = (int)(i - r * c4) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(x + r * C + c);
+    const float f[4] = {v.x, v.y, v.z, v.w};
+    uint32_t hw[2], lw[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const bf16 h0 = __float2bfloat16_rn(f[2 * k]), h1 = __float2bfloat16_rn(f[2 * k + 1]);
+        const bf16 l0 = __float2bfloat16_rn(f[2 * k] - __bfloat162float(h0)), l1 = __float2bfloat16_rn(f[2 * k + 1] - __bfloat162float(h1));
+        hw[k] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        lw[k] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+    *reinterpret_cast<uint2*>(y + r * 2 * C + c) = make_uint2(hw[0], hw[1]);
+    *reinterpret_cast<uint2*>(y + r * 2 * C + C + c) = make_uint2(lw[0], lw[1]);
+}
+
+extern "C" int vqb_split_hi_lo(const float* x, void* y, int64_t rows, int C, void* stream) {
+    VQB_CHECK_ARG(x && y && rows > 0 && C > 0 && C % 4 == 0, "split_hi_lo: bad arguments");
+    const int64_t n = rows * (C / 4);
+    split_hi_lo_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, as_stream(stream)>>>(x, (bf16*)y, rows, C);
+    VQB_CHECK_LAUNCH("split_hi_lo");
+    return VQB_OK;
+}
+
 extern "C" int vqb_convert(const void* x, int in_dtype, void* y, int out_dtype, int64_t n, void* stream) {
     VQB_CHECK_ARG(x && y && n >= 0, "convert: bad arguments");
     if (n == 0) return VQB_OK;

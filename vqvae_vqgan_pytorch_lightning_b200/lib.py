@@ -27,6 +27,7 @@ SIGNATURES = {
     'vqb_nchw_to_nhwc': (_i, [_p, _p, _i, _i64, _i64, _i64, _i64, _i, _f, _f, _f, _f, _p]),
     'vqb_crop_flip_normalize': (_i, [_p, _i, _p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _f, _f, _p]),
     'vqb_nhwc_to_nchw': (_i, [_p, _i, _p, _i64, _i64, _i64, _i64, _f, _f, _i, _f, _f, _p]),
+    'vqb_split_hi_lo': (_i, [_p, _p, _i64, _i, _p]),
     'vqb_convert': (_i, [_p, _i, _p, _i, _i64, _p]),
     'vqb_pack_conv_weight': (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _f, _p]),
     'vqb_im2col3x3_narrow': (_i, [_p, _i, _p, _i, _i, _i, _i, _i, _i, _p]),

@@ -23,7 +23,12 @@ CL = torch.channels_last
 class Precision:
     """Numeric mode of the convolution stacks.
 
-    strict: fp32 storage + fp32 SIMT implicit GEMM -- the parity path (<= 1e-4 rel. vs the fp32 oracle).
+    strict: fp32 storage; convolutions on the tensor cores with SPLIT-PRECISION operands -- every fp32 value is split into bf16
+            hi + lo (16 mantissa bits), three (or four) bf16 products per multiply accumulate in ONE fp32 TMEM accumulator,
+            by the same tcgen05 kernels as the fast mode (their k loop wraps over the [hi | lo] halves) -- the parity path
+            (<= 1e-4 rel. vs the fp32 oracle); shapes the tensor-core kernels do not take (RGB heads, strided or odd-channel
+            discriminator layers) run on the fp32 SIMT implicit GEMM.  VQB_STRICT_CONV=simt forces the SIMT kernels everywhere,
+            =tc4 adds the lo.lo product.
     fast  : bf16 storage, tcgen05 bf16 x bf16 -> fp32 implicit GEMM wherever Ci and Co are multiples of 64
             (the reference itself trains with precision='16-mixed', vqvae/train.py:129); fp32 master weights,
             fp32 GroupNorm statistics, fp32 VQ, fp32 weight gradients.
@@ -35,15 +40,43 @@ class Precision:
         return torch.float32 if self.name == 'strict' else torch.bfloat16
 
     def conv_impl(self, ci: int, co: int, stride: int = 1) -> int:
-        """1 = tcgen05 implicit GEMM (forward, and dgrad with ci/co swapped), 0 = fp32 SIMT."""
+        """1 = tcgen05 implicit GEMM on bf16 operands (forward, and dgrad with ci/co swapped), 2 / 3 = the same kernels on
+        split-precision operands (3 / 4 bf16 products per multiply), 0 = fp32 SIMT."""
         if self.name == 'fast' and ci % 64 == 0 and (co % 64 == 0 or co <= 16) and stride == 1:
             return 1
+        if self.name == 'strict' and _strict_conv() and ci % 64 == 0 and co % 64 == 0 and stride == 1:
+            return _strict_conv()
         return 0
 
     def wgrad_impl(self, ci: int, co: int, stride: int = 1) -> int:
         if self.name == 'fast' and ci % 64 == 0 and co % 128 == 0 and stride == 1:
             return 1
+        if self.name == 'strict' and _strict_conv() and ci % 64 == 0 and co % 64 == 0 and stride == 1:
+            return _strict_conv()
         return 0
+
+
+_strict_conv_mode = None
+
+
+def _strict_conv() -> int:
+    """conv impl of the strict mode: 2 (three-term split, default), 3 (four-term), 0 (fp32 SIMT: VQB_STRICT_CONV=simt or no
+    sm_100 device)"""
+    global _strict_conv_mode
+    if _strict_conv_mode is None:
+        import os
+        v = os.environ.get('VQB_STRICT_CONV', 'tc3').lower()
+        mode = {'simt': 0, 'tc3': 2, 'tc4': 3}.get(v, 2)
+        if mode and not lib.load().vqb_device_supports_tcgen05():
+            mode = 0
+        _strict_conv_mode = mode
+    return _strict_conv_mode
+
+
+def set_strict_conv(mode: str) -> None:
+    """'tc3' | 'tc4' | 'simt' (A/B measurements and tests)"""
+    global _strict_conv_mode
+    _strict_conv_mode = {'simt': 0, 'tc3': 2, 'tc4': 3}[mode]
 
 
 _precision = Precision('strict')
@@ -128,6 +161,51 @@ def _packed_weight(weight: torch.Tensor, mode: int, dtype: torch.dtype, scale: f
         if not src.is_contiguous() or src.dtype != torch.float32:
             src = src.float().contiguous()            # e.g. the transposed-codebook view used by the Gumbel einsum
         call('vqb_pack_conv_weight', ptr(src), ptr(wp), dt(wp), mode, co, ci, kh, kw, scale, stream())
+        cache[tag] = wp
+    return cache[tag]
+
+
+def split_hi_lo(x: torch.Tensor) -> torch.Tensor:
+    """fp32 channels-last [N,C,H,W] -> bf16 channels-last [N,2C,H,W] = [hi | lo] per pixel (vqb_split_hi_lo)"""
+    x = as_nhwc(x, torch.float32)
+    n, c, h, w = x.shape
+    out = empty_nhwc(n, 2 * c, h, w, torch.bfloat16, x.device)
+    call('vqb_split_hi_lo', ptr(x), ptr(out), n * h * w, c, stream())
+    return out
+
+
+def _is_split(x: torch.Tensor, c: int) -> bool:
+    return x.dtype == torch.bfloat16 and x.shape[1] == 2 * c
+
+
+def _packed_split_weight(weight: torch.Tensor, terms: int, dgrad: bool, scale: float = 1.0) -> torch.Tensor:
+    """K-major bf16 pack of the split weight for impl 2 / 3: [wh | wh | wl (| wl)] along the contraction axis (input channels for
+    the forward convolution, output channels -- with flipped taps -- for dgrad).  Cached per weight version like _packed_weight."""
+    key = (weight._version, _weights_epoch, weight.data_ptr(), scale)
+    cache = getattr(weight, '_vqb_pack', None)
+    if cache is None or cache.get('key') != key:
+        cache = {'key': key}
+        try:
+            weight._vqb_pack = cache
+        except Exception:
+            pass
+    tag = ('split', terms, dgrad)
+    if tag not in cache:
+        w = weight.detach().float()
+        if scale != 1.0:
+            w = w * scale                        # equalised-lr gain folded in BEFORE the split (the product must split the scaled value)
+        wh = w.bfloat16().float()
+        wl = w - wh
+        blocks = [wh, wh, wl] + ([wl] if terms == 4 else [])
+        co, ci, kh, kw = w.shape
+        if dgrad:
+            w2 = torch.cat(blocks, dim=0).contiguous()                 # [terms*co, ci, kh, kw]
+            wp = torch.empty(w2.numel(), dtype=torch.bfloat16, device=w.device)
+            call('vqb_pack_conv_weight', ptr(w2), ptr(wp), BF16, 3, terms * co, ci, kh, kw, 1.0, stream())
+        else:
+            w2 = torch.cat(blocks, dim=1).contiguous()                 # [co, terms*ci, kh, kw]
+            wp = torch.empty(w2.numel(), dtype=torch.bfloat16, device=w.device)
+            call('vqb_pack_conv_weight', ptr(w2), ptr(wp), BF16, 2, co, terms * ci, kh, kw, 1.0, stream())
         cache[tag] = wp
     return cache[tag]
 
@@ -220,6 +298,8 @@ class Conv2dFn(torch.autograd.Function):
         in_dtype = x.dtype
         if impl == 1:
             cdt = torch.bfloat16
+        elif impl in (2, 3):
+            cdt = torch.float32
         else:
             cdt = x.dtype if x.dtype in (torch.float32, torch.bfloat16) else prec.act_dtype
         x = as_nhwc(x, cdt)
@@ -234,6 +314,11 @@ class Conv2dFn(torch.autograd.Function):
         if route == 'in':
             wp = _packed_weight(weight, 4, torch.bfloat16, w_scale)                  # [co][64], K zero-padded
             y = _conv_fwd_raw(1, _im2col64(x), wp, b, residual, out_dtype, 64, co, 1, 1, 0, 1, act, alpha, gain)
+        elif impl in (2, 3):
+            # strict mode on the tensor cores: [hi | lo] operand halves, 3 / 4 bf16 products per multiply in one fp32 accumulator
+            x = split_hi_lo(x)                                                        # saved in this form for the weight gradient
+            wp = _packed_split_weight(weight, impl + 1, False, w_scale)
+            y = _conv_fwd_raw(impl, x, wp, b, residual, out_dtype, ci, co, kh, kw, pad, stride, act, alpha, gain)
         else:
             wp = _packed_weight(weight, 2 if impl == 1 else 0, torch.bfloat16 if impl == 1 else torch.float32, w_scale)
             y = _conv_fwd_raw(impl, x, wp, b, residual, out_dtype, ci, co, kh, kw, pad, stride, act, alpha, gain)
@@ -304,10 +389,13 @@ class Conv2dFn(torch.autograd.Function):
                 ddt = in_dtype if in_dtype in (torch.float32, torch.bfloat16) else gdt
                 dx = ConvDgradFn.apply(dy, weight, h, w, pad, stride, w_scale, ddt)
             return dx, None, None, dres, None, None, None, None, None, None, None
+        dy_ops = dy
+        if impl in (2, 3) and dy.dtype == torch.float32 and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]):
+            dy_ops = split_hi_lo(dy)                     # one [hi | lo] split of dy serves the input AND the weight gradient
         if ctx.needs_input_grad[0]:
-            dx = _dgrad_raw(dy, weight, h, w, pad, stride, w_scale, in_dtype if in_dtype in (torch.float32, torch.bfloat16) else gdt)
+            dx = _dgrad_raw(dy_ops, weight, h, w, pad, stride, w_scale, in_dtype if in_dtype in (torch.float32, torch.bfloat16) else gdt)
         if ctx.needs_input_grad[1] and not _no_weight_grad:
-            dw = _wgrad_raw(x, dy, weight.shape, pad, stride, w_scale)
+            dw = _wgrad_raw(x, dy_ops, weight.shape, pad, stride, w_scale)
         if has_bias and ctx.needs_input_grad[2] and not _no_weight_grad:
             db = db_fused if db_fused is not None else _colsum(dy, n * oh * ow, co)
         return dx, dw, db, dres, None, None, None, None, None, None, None
@@ -331,6 +419,13 @@ def _dgrad_raw(dy: torch.Tensor, weight: torch.Tensor, h: int, w: int, pad: int,
         call('vqb_conv2d_dgrad', ptr(dy), dt(dy), ptr(wd), ptr(dx), dt(dx), n, h, w, ci, co, kh, kw, pad, stride, stream())
         return dx
     dimpl = prec.conv_impl(co, ci, 1) if kh - 1 - pad == kh // 2 else 0       # tcgen05 path needs a 'same' dgrad
+    if _is_split(dy, co) and dimpl not in (2, 3):
+        raise lib.VQBError('conv2d dgrad: split-precision gradient but no tensor-core kernel for this shape')
+    if dimpl in (2, 3):
+        dys = dy if _is_split(dy, co) else split_hi_lo(dy)
+        wd = _packed_split_weight(weight, dimpl + 1, True, w_scale)
+        return _conv_fwd_raw(dimpl, dys, wd, None, None, torch.float32 if out_dtype is None else out_dtype, co, ci, kh, kw,
+                             kh - 1 - pad, 1, ACT_NONE, 0.0, 1.0)
     dyd = as_nhwc(dy, torch.bfloat16) if dimpl == 1 else dy
     wd = _packed_weight(weight, 3 if dimpl == 1 else 1, torch.bfloat16 if dimpl == 1 else torch.float32, w_scale)
     # dgrad = correlation of dy with the tap-flipped, channel-swapped weight; padding k-1-pad
@@ -343,7 +438,21 @@ def _wgrad_raw(x: torch.Tensor, dy: torch.Tensor, wshape, pad: int, stride: int,
     prec = get_precision()
     co, ci, kh, kw = wshape
     n, _, h, w = x.shape
+    simpl = prec.wgrad_impl(ci, co, stride)
+    if simpl in (2, 3) and pad == kh // 2 and kh == kw and (_is_split(x, ci) or x.dtype == torch.float32):
+        # split-precision operands: the bf16 kernel on [xh | xl] x [dyh | dyl] gives the four partial gradients hh, hl, lh, ll as
+        # the four (co, ci) blocks of a (2co) x (2ci) problem; their sum is dW to ~2^-17 relative
+        xs = x if _is_split(x, ci) else split_hi_lo(x)
+        dys = dy if _is_split(dy, co) else split_hi_lo(dy)
+        dwp = torch.zeros(kh * kw * 4 * ci * co, dtype=torch.float32, device=x.device)
+        call('vqb_conv2d_wgrad', 1, ptr(xs), BF16, ptr(dys), BF16, ptr(dwp), n, h, w, 2 * ci, 2 * co, kh, kw, pad, stride, stream())
+        dw4 = torch.empty((2 * co, 2 * ci, kh, kw), dtype=torch.float32, device=x.device)
+        call('vqb_unpack_conv_wgrad', ptr(dwp), ptr(dw4), 2 * co, 2 * ci, kh, kw, w_scale, stream())
+        return (dw4[:co, :ci] + dw4[:co, ci:]) + (dw4[co:, :ci] + dw4[co:, ci:])
+    if _is_split(x, ci) and x.shape[1] != ci:
+        raise lib.VQBError('conv2d wgrad: split-precision input but no tensor-core weight-gradient kernel for this shape')
     wimpl = prec.wgrad_impl(ci, co, stride) if x.dtype == torch.bfloat16 else 0
+    wimpl = 1 if wimpl == 1 else 0
     dyw = as_nhwc(dy, torch.bfloat16) if wimpl == 1 else dy
     dwp = torch.zeros(kh * kw * ci * co, dtype=torch.float32, device=x.device)
     call('vqb_conv2d_wgrad', wimpl, ptr(x), dt(x), ptr(dyw), dt(dyw), ptr(dwp), n, h, w, ci, co, kh, kw, pad, stride, stream())
