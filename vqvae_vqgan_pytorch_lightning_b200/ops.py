@@ -27,8 +27,9 @@ class Precision:
             hi + lo (16 mantissa bits), three (or four) bf16 products per multiply accumulate in ONE fp32 TMEM accumulator,
             by the same tcgen05 kernels as the fast mode (their k loop wraps over the [hi | lo] halves) -- the parity path
             (<= 1e-4 rel. vs the fp32 oracle); shapes the tensor-core kernels do not take (RGB heads, strided or odd-channel
-            discriminator layers) run on the fp32 SIMT implicit GEMM.  VQB_STRICT_CONV=simt forces the SIMT kernels everywhere,
-            =tc4 adds the lo.lo product.
+            discriminator layers, problems of fewer than 1024 output pixels) run on the fp32 SIMT implicit GEMM.  Default:
+            four products (hi.hi + lo.hi + hi.lo + lo.lo, ~4e-6 per convolution: measured in
+            tests/test_bench_shapes_gpu.py); VQB_STRICT_CONV=tc3 drops lo.lo (~1.2e-5, 4/3 faster), =simt forces the SIMT kernels.
     fast  : bf16 storage, tcgen05 bf16 x bf16 -> fp32 implicit GEMM wherever Ci and Co are multiples of 64
             (the reference itself trains with precision='16-mixed', vqvae/train.py:129); fp32 master weights,
             fp32 GroupNorm statistics, fp32 VQ, fp32 weight gradients.
@@ -39,19 +40,19 @@ class Precision:
     def act_dtype(self) -> torch.dtype:
         return torch.float32 if self.name == 'strict' else torch.bfloat16
 
-    def conv_impl(self, ci: int, co: int, stride: int = 1) -> int:
+    def conv_impl(self, ci: int, co: int, stride: int = 1, pixels: int = 1 << 30) -> int:
         """1 = tcgen05 implicit GEMM on bf16 operands (forward, and dgrad with ci/co swapped), 2 / 3 = the same kernels on
-        split-precision operands (3 / 4 bf16 products per multiply), 0 = fp32 SIMT."""
+        split-precision operands (3 / 4 bf16 products per multiply), 0 = fp32 SIMT.  `pixels` = N*OH*OW of the problem."""
         if self.name == 'fast' and ci % 64 == 0 and (co % 64 == 0 or co <= 16) and stride == 1:
             return 1
-        if self.name == 'strict' and _strict_conv() and ci % 64 == 0 and co % 64 == 0 and stride == 1:
+        if self.name == 'strict' and _strict_conv() and ci % 64 == 0 and co % 64 == 0 and stride == 1 and pixels >= 1024:
             return _strict_conv()
         return 0
 
-    def wgrad_impl(self, ci: int, co: int, stride: int = 1) -> int:
+    def wgrad_impl(self, ci: int, co: int, stride: int = 1, pixels: int = 1 << 30) -> int:
         if self.name == 'fast' and ci % 64 == 0 and co % 128 == 0 and stride == 1:
             return 1
-        if self.name == 'strict' and _strict_conv() and ci % 64 == 0 and co % 64 == 0 and stride == 1:
+        if self.name == 'strict' and _strict_conv() and ci % 64 == 0 and co % 64 == 0 and stride == 1 and pixels >= 1024:
             return _strict_conv()
         return 0
 
@@ -60,13 +61,13 @@ _strict_conv_mode = None
 
 
 def _strict_conv() -> int:
-    """conv impl of the strict mode: 2 (three-term split, default), 3 (four-term), 0 (fp32 SIMT: VQB_STRICT_CONV=simt or no
+    """conv impl of the strict mode: 3 (four-term split, default), 2 (three-term), 0 (fp32 SIMT: VQB_STRICT_CONV=simt or no
     sm_100 device)"""
     global _strict_conv_mode
     if _strict_conv_mode is None:
         import os
-        v = os.environ.get('VQB_STRICT_CONV', 'tc3').lower()
-        mode = {'simt': 0, 'tc3': 2, 'tc4': 3}.get(v, 2)
+        v = os.environ.get('VQB_STRICT_CONV', 'tc4').lower()
+        mode = {'simt': 0, 'tc3': 2, 'tc4': 3}.get(v, 3)
         if mode and not lib.load().vqb_device_supports_tcgen05():
             mode = 0
         _strict_conv_mode = mode
@@ -294,7 +295,7 @@ class Conv2dFn(torch.autograd.Function):
     def forward(ctx, x, weight, bias, residual, pad, stride, act, alpha, gain, out_dtype, w_scale):
         prec = get_precision()
         co, ci, kh, kw = weight.shape
-        impl = prec.conv_impl(ci, co, stride) if (pad == kh // 2 and kh == kw) else 0
+        impl = prec.conv_impl(ci, co, stride, x.shape[0] * x.shape[2] * x.shape[3]) if (pad == kh // 2 and kh == kw) else 0
         in_dtype = x.dtype
         if impl == 1:
             cdt = torch.bfloat16
@@ -418,7 +419,7 @@ def _dgrad_raw(dy: torch.Tensor, weight: torch.Tensor, h: int, w: int, pad: int,
         dx = empty_nhwc(n, ci, h, w, out_dtype, dy.device)
         call('vqb_conv2d_dgrad', ptr(dy), dt(dy), ptr(wd), ptr(dx), dt(dx), n, h, w, ci, co, kh, kw, pad, stride, stream())
         return dx
-    dimpl = prec.conv_impl(co, ci, 1) if kh - 1 - pad == kh // 2 else 0       # tcgen05 path needs a 'same' dgrad
+    dimpl = prec.conv_impl(co, ci, 1, n * h * w) if kh - 1 - pad == kh // 2 else 0       # tcgen05 path needs a 'same' dgrad
     if _is_split(dy, co) and dimpl not in (2, 3):
         raise lib.VQBError('conv2d dgrad: split-precision gradient but no tensor-core kernel for this shape')
     if dimpl in (2, 3):
@@ -438,7 +439,7 @@ def _wgrad_raw(x: torch.Tensor, dy: torch.Tensor, wshape, pad: int, stride: int,
     prec = get_precision()
     co, ci, kh, kw = wshape
     n, _, h, w = x.shape
-    simpl = prec.wgrad_impl(ci, co, stride)
+    simpl = prec.wgrad_impl(ci, co, stride, n * h * w)
     if simpl in (2, 3) and pad == kh // 2 and kh == kw and (_is_split(x, ci) or x.dtype == torch.float32):
         # split-precision operands: the bf16 kernel on [xh | xl] x [dyh | dyl] gives the four partial gradients hh, hl, lh, ll as
         # the four (co, ci) blocks of a (2co) x (2ci) problem; their sum is dW to ~2^-17 relative
