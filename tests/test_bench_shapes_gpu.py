@@ -135,10 +135,11 @@ def test_split_precision_conv_at_bench_layer_shapes(V, n, hw, ci, co, k, res):
         e_y, e_dw = rel(y[:, :8], y64), rel(dw[:8, :8], wsub.grad)
         e_dx = rel(dx, out['simt'][1])
         print(f'{mode}: fwd {e_y:.2e} dx-vs-simt {e_dx:.2e} dw {e_dw:.2e}')
-        # measured on B200: tc3 5e-6 .. 2.3e-5 (the dropped lo.lo term and the rounding of lo itself, 2^-17 per operand), tc4
-        # 4e-6, SIMT 3e-7; the weight gradient also carries the TMEM accumulation of its long pixel reduction, 1e-4 at 1 M pixels
-        # (see test_tcgen05_conv_equals_simt_at_bench_shapes)
-        bar = {'tc3': 4e-5, 'tc4': 1e-5, 'simt': 2e-6}[mode]
+        # measured on B200: SIMT 3e-7; tc4 4e-6 (1x1, 256 products per output) .. 2e-5 (3x3 x 512 channels: 18 k products), tc3
+        # ~1.3x that.  The floor is not the split (2^-17 per operand) but the tensor core's fp32 accumulator, which does not round
+        # to nearest: the error grows with the number of k-steps accumulated in TMEM; the weight gradient's pixel reduction
+        # (1 M pixels here) reaches 1e-4 (see test_tcgen05_conv_equals_simt_at_bench_shapes)
+        bar = {'tc3': 6e-5, 'tc4': 5e-5, 'simt': 2e-6}[mode]
         assert e_y < bar and e_dx < bar and e_dw < (2e-4 if mode != 'simt' else 2e-5), (mode, e_y, e_dx, e_dw)
 
 
