@@ -237,13 +237,16 @@ def run_reference(args, rank, world, out=sys.stdout):
 # ------------------------------------------------------------------------------------------------------
 def run_workload(name, args, pkg, dev, rank, world, precision, steps, warmup, stamp, sample_clocks=False, ncu_step=False):
     """Build workload `name`, run `warmup` + `steps` device-resident steps and `steps` end-to-end steps through
-    Trainer.run_step; returns the record (rank 0; other ranks return None)."""
+    Trainer.run_step; returns the record (rank 0; other ranks return None).  With --graph (default) the trainer replays one
+    captured CUDA graph per step; a third, EAGER timed region of the same length then times the convolution entry points with
+    CUDA events (per-kernel events cannot be recorded inside a graph replay) for the roofline object."""
     from vqvae_vqgan_pytorch_lightning_b200.lightning_shim import Trainer
     pkg.set_precision(precision)
     image_size, ae_conf, q_conf, l_conf, t_conf, bs, codebook = model_confs(name, args, world)
     torch.manual_seed(1234)                       # same weights on every rank (reference construction order)
     model = pkg.VQVAE(image_size, ae_conf, q_conf, l_conf, t_conf, pretrained_lpips=False).to(dev).train()
-    trainer = Trainer(max_epochs=1, num_training_batches=steps * 2 + warmup)
+    use_graph = bool(args.graph) and not ncu_step
+    trainer = Trainer(max_epochs=1, num_training_batches=steps * 3 + warmup + 4, cuda_graph=use_graph)
     trainer.attach(model)
     model.on_train_start()
     model.training_augmentations = None           # SURVEY.md 8d: the metric is quoted with augmentation off
@@ -263,17 +266,20 @@ def run_workload(name, args, pkg, dev, rank, world, precision, steps, warmup, st
 
     def step_resident(i):
         loss = trainer.run_step(resident[i % nbuf], step_idx[0]); step_idx[0] += 1
-        l2_log.append((loss.detach(), torch.as_tensor(model.logged['train/l2_loss']).detach()))
+        # (clones: under graph replay the step's outputs live in static tensors that the next replay overwrites)
+        l2_log.append((loss.detach().clone(), torch.as_tensor(model.logged['train/l2_loss']).detach().clone()))
         return loss
 
     def step_e2e(i):
         x = host[i % nbuf].to(dev, non_blocking=True)                            # H2D from pinned memory, every step
         loss = trainer.run_step(x, step_idx[0]); step_idx[0] += 1
-        l2_log.append((loss.detach(), torch.as_tensor(model.logged['train/l2_loss']).detach()))
+        l2_log.append((loss.detach().clone(), torch.as_tensor(model.logged['train/l2_loss']).detach().clone()))
         return float(loss.detach().cpu())                                        # D2H read of the step's loss
 
     stamp(f'{name}/{precision}: model and inputs ready')
-    for i in range(warmup):
+    # warm-up: W steps, plus -- with graphs -- enough steps for every step variant met in the timed regions to be captured
+    # (2 eager steps + the capture step per variant; the R1 variant of the VQGAN configs comes every 16th step)
+    for i in range(warmup + ((3 + (33 if WORKLOADS[name]['gan'] else 0)) if use_graph else 0)):
         step_resident(i)
     barrier()
     if ncu_step:
@@ -283,11 +289,12 @@ def run_workload(name, args, pkg, dev, rank, world, precision, steps, warmup, st
         torch.cuda.profiler.stop()
         return None
 
-    # ---- timed region 1: inputs resident in HBM (value, ms_per_step, roofline) ---------------------------------
+    # ---- timed region 1: inputs resident in HBM (value, ms_per_step) ---------------------------------------------
     clocks = ClockSampler(dev.index or 0)
     if rank == 0 and sample_clocks:
         clocks.start()
-    pkg.lib.timer = pkg.lib.KernelTimer(['vqb_conv2d_fwd', 'vqb_conv2d_wgrad', 'vqb_vq_assign', 'vqb_vq_assign_tc', 'vqb_vq_fused'])
+    if not use_graph:
+        pkg.lib.timer = pkg.lib.KernelTimer(['vqb_conv2d_fwd', 'vqb_conv2d_wgrad', 'vqb_vq_assign', 'vqb_vq_assign_tc', 'vqb_vq_fused'])
     launches0 = pkg.lib.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -298,7 +305,7 @@ def run_workload(name, args, pkg, dev, rank, world, precision, steps, warmup, st
     barrier()
     ms = e0.elapsed_time(e1)
     launches = pkg.lib.launch_count - launches0
-    ksum = pkg.lib.timer.summary()
+    ksum = pkg.lib.timer.summary() if pkg.lib.timer is not None else {}
     pkg.lib.timer = None
 
     # ---- timed region 2: end to end through the public API with host buffers ---------------------------------------
@@ -311,12 +318,31 @@ def run_workload(name, args, pkg, dev, rank, world, precision, steps, warmup, st
     barrier()
     ms_e2e = f0.elapsed_time(f1)
     clk = clocks.stop() if (rank == 0 and sample_clocks) else None
+    ms_eager = None
+    if use_graph:
+        # ---- timed region 3 (graphs only): the same steps EAGERLY, every convolution entry point bracketed by CUDA events ------
+        trainer.cuda_graph = False
+        step_resident(0)
+        pkg.lib.timer = pkg.lib.KernelTimer(['vqb_conv2d_fwd', 'vqb_conv2d_wgrad', 'vqb_vq_assign', 'vqb_vq_assign_tc', 'vqb_vq_fused'])
+        launches0 = pkg.lib.launch_count
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        h0.record()
+        for i in range(steps):
+            step_resident(i)
+        h1.record()
+        barrier()
+        ms_eager = h0.elapsed_time(h1)
+        launches = pkg.lib.launch_count - launches0
+        ksum = pkg.lib.timer.summary()
+        pkg.lib.timer = None
     stamp(f'{name}/{precision}: timed regions done')
 
-    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, ms_e2e, ms_eager or 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(t[0]), float(t[1])
+    ms_eager = float(t[2]) if ms_eager is not None else None
 
     # ---- the step must be a real optimisation step: every loss finite, reconstruction error not increasing ----------
     losses = torch.stack([a.float().reshape(()) for a, _ in l2_log]).cpu().tolist()
@@ -347,7 +373,11 @@ def run_workload(name, args, pkg, dev, rank, world, precision, steps, warmup, st
                 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
                 'traffic': tr['dram_bytes_per_launch'] if tr else None, 'traffic_source': tr.get('source') if tr else None,
                 'traffic_algorithmic_bytes': tr.get('algorithmic_bytes') if tr else None,
-                'peak_source': f'{pk_kind} (sustained bf16)', 'launches_timed': conv_calls, 'share_of_step': conv_ms / ms,
+                'peak_source': f'{pk_kind} (sustained bf16)', 'launches_timed': conv_calls,
+                'share_of_step': conv_ms / (ms_eager if ms_eager is not None else ms),
+                'measured_in': (f'eager timed region of {steps} steps ({ms_eager / steps:.2f} ms/step): CUDA events around every conv entry '
+                                f'point; the headline value replays a CUDA graph of the same step') if ms_eager is not None else
+                               'the headline timed region (CUDA events around every conv entry point)',
                 'flop_per_step': conv_fl / steps, 'whole_step_tflops': conv_fl / (ms / 1e3) / 1e12,
                 'whole_step_frac': conv_fl / (ms / 1e3) / 1e12 / peak}
     rec = {
@@ -358,7 +388,8 @@ def run_workload(name, args, pkg, dev, rank, world, precision, steps, warmup, st
                    'l2_policy': 'working set per step (inputs + activations > 5 GB) exceeds the 126 MB L2'},
         'e2e': {'value': total_images / (ms_e2e / 1e3), 'unit': UNIT, 'h2d_bytes_per_step': bs * 3 * image_size * image_size * 4,
                 'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e / steps},
-        'gpu_launches': launches, 'roofline': roofline,
+        'gpu_launches': launches, 'cuda_graph': use_graph, 'ms_per_step_eager': (ms_eager / steps) if ms_eager is not None else None,
+        'roofline': roofline,
         'loss': {'first': losses[0], 'last': losses[-1], 'l2_first': head, 'l2_last': tail, 'all_finite': True,
                  'steps_observed': len(losses)},
         'peak_mem_gib': peak_mem,
@@ -386,6 +417,7 @@ def main():
     ap.add_argument('--cpu-batch', type=int, default=2)
     ap.add_argument('--cpu-steps', type=int, default=2)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--graph', type=int, default=1, help='1 (default): replay one captured CUDA graph per step; 0: eager launches')
     ap.add_argument('--ncu-step', action='store_true', help='after the warm-up run ONE step between cudaProfilerStart/Stop and exit '
                     '(for `ncu --profile-from-start off`; prints no bench line)')
     args = ap.parse_args()
@@ -447,7 +479,9 @@ def main():
             'metric': head['metric'], 'value': head['value'], 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': head['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': head['dtype'], 'data': 'synthetic', 'config': head['config'], 'e2e': head['e2e'],
-            'gpu_launches': head['gpu_launches'], 'clocks': head.get('clocks'), 'roofline': head['roofline'], 'loss': head['loss'],
+            'gpu_launches': head['gpu_launches'], 'gpu_launches_note': 'kernel entry points per timed region (the graph replays the same launches)',
+            'cuda_graph': head.get('cuda_graph'), 'ms_per_step_eager': head.get('ms_per_step_eager'),
+            'clocks': head.get('clocks'), 'roofline': head['roofline'], 'loss': head['loss'],
         }
         if world == 1:
             vq = {}

@@ -289,6 +289,12 @@ int vqb_gumbel_rows_fwd(const float* logits, const float* exp_noise, float tau, 
                         double* kl_sum, int64_t N, int K, void* stream);
 int vqb_gumbel_rows_bwd(const float* logits, const float* exp_noise, float tau, const float* dy, const float* g_kl,
                         float kl_scale, float* dlogits, int64_t N, int K, void* stream);
+/* vqb_gumbel_rows_fwd / _bwd with the temperature read from device memory (tau_dev[0]): CUDA-graph replay under the
+ * temperature schedule of model.py:219-225. */
+int vqb_gumbel_rows_fwd_dev(const float* logits, const float* exp_noise, const float* tau_dev, int hard, float* y,
+                            int64_t* idx_out, double* kl_sum, int64_t N, int K, void* stream);
+int vqb_gumbel_rows_bwd_dev(const float* logits, const float* exp_noise, const float* tau_dev, const float* dy,
+                            const float* g_kl, float kl_scale, float* dlogits, int64_t N, int K, void* stream);
 
 /* gather rows: out[i] = codebook[idx[i]] (BaseVectorQuantizer.codes_to_vec base_quantizer.py:53-61) */
 int vqb_vq_gather(const float* codebook, const int64_t* idx, float* out, int64_t N, int K, int D, void* stream);
@@ -300,6 +306,11 @@ int vqb_vq_gather(const float* codebook, const int64_t* idx, float* out, int64_t
  * the gradient first (1/world_size after a sum all-reduce). */
 int vqb_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
               float weight_decay, int step, float grad_scale, void* stream);
+/* The same update with the per-step scalars in DEVICE memory: hyper = {lr, 1 - beta1^step, sqrt(1 - beta2^step)}.  The launch
+ * holds no step-dependent host value, so a whole training step can be captured in a CUDA graph and replayed while the host
+ * rewrites three floats per optimizer group (lr schedule of on_train_batch_start, model.py:202-218). */
+int vqb_adamw_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper, float beta1, float beta2,
+                  float eps, float weight_decay, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -651,6 +651,35 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
     }
 }
 
+// the same update with the per-step scalars read from DEVICE memory (hyper = {lr, bc1, sqrt(bc2)}), so that the launch can be
+// captured in a CUDA graph and replayed while the host only rewrites three floats in a pinned buffer (lr schedule, step count)
+__global__ void adamw_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                 int64_t n, const float* __restrict__ hyper, float beta1, float beta2, float eps, float wd,
+                                 float grad_scale) {
+    const float lr = hyper[0], bc2_sqrt = hyper[2];
+    const float step_size = lr / hyper[1];
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float gi = g[i] * grad_scale;
+        float pi = p[i] * (1.0f - lr * wd);
+        float mi = m[i] * beta1 + (1.0f - beta1) * gi;
+        float vi = v[i] * beta2 + (1.0f - beta2) * gi * gi;
+        float denom = sqrtf(vi) / bc2_sqrt + eps;
+        p[i] = pi - step_size * (mi / denom);
+        m[i] = mi;
+        v[i] = vi;
+    }
+}
+
+extern "C" int vqb_adamw_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper, float beta1, float beta2,
+                             float eps, float weight_decay, float grad_scale, void* stream) {
+    VQB_CHECK_ARG(p && g && m && v && hyper && n >= 0, "adamw_dev: bad arguments");
+    if (n == 0) return VQB_OK;
+    int gsz = grid_for(n, 256);
+    adamw_dev_kernel<<<gsz, 256, 0, as_stream(stream)>>>(p, g, m, v, n, hyper, beta1, beta2, eps, weight_decay, grad_scale);
+    VQB_CHECK_LAUNCH("adamw_dev");
+    return VQB_OK;
+}
+
 extern "C" int vqb_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                          float eps, float weight_decay, int step, float grad_scale, void* stream) {
     VQB_CHECK_ARG(p && g && m && v && n >= 0 && step >= 1, "adamw: bad arguments");

@@ -138,7 +138,9 @@ __global__ void entropy_combine_dcb_kernel(float* __restrict__ dcb, const float*
 // ---- Gumbel-softmax rows ----------------------------------------------------------------------------------
 // y = softmax((logits - log(E)) / tau)  [hard: one-hot(argmax)], idx = argmax y, kl_sum += sum_n qy log(qy K + 1e-10), qy = softmax(logits)
 __global__ void gumbel_rows_fwd_kernel(const float* __restrict__ logits, const float* __restrict__ expo, float inv_tau, int hard,
-                                       float* __restrict__ y, int64_t* __restrict__ idx_out, double* __restrict__ kl_sum, int64_t N, int K) {
+                                       float* __restrict__ y, int64_t* __restrict__ idx_out, double* __restrict__ kl_sum, int64_t N, int K,
+                                       const float* __restrict__ tau_dev) {
+    if (tau_dev) inv_tau = 1.0f / tau_dev[0];           // temperature from device memory (CUDA-graph replay with a schedule)
     int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (row >= N) return;
@@ -188,7 +190,8 @@ __global__ void gumbel_rows_fwd_kernel(const float* __restrict__ logits, const f
 // dlogits = (1/tau) soft (dy - sum soft dy) + ckl * qy (f - sum qy f),  f = log(qy K + eps) + qy K / (qy K + eps)
 __global__ void gumbel_rows_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ expo, float inv_tau,
                                        const float* __restrict__ dy, const float* __restrict__ g_kl, float kl_scale,
-                                       float* __restrict__ dlogits, int64_t N, int K) {
+                                       float* __restrict__ dlogits, int64_t N, int K, const float* __restrict__ tau_dev) {
+    if (tau_dev) inv_tau = 1.0f / tau_dev[0];
     int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (row >= N) return;
@@ -293,8 +296,17 @@ extern "C" int vqb_gumbel_rows_fwd(const float* logits, const float* exp_noise, 
                                    double* kl_sum, int64_t N, int K, void* stream) {
     VQB_CHECK_ARG(logits && y && idx_out && kl_sum && N > 0 && K > 0 && tau > 0.f, "gumbel_rows_fwd: bad arguments");
     gumbel_rows_fwd_kernel<<<(unsigned)ceil_div64(N * 32, 256), 256, 0, as_stream(stream)>>>(logits, exp_noise, 1.0f / tau, hard, y,
-                                                                                              idx_out, kl_sum, N, K);
+                                                                                              idx_out, kl_sum, N, K, nullptr);
     VQB_CHECK_LAUNCH("gumbel_rows_fwd");
+    return VQB_OK;
+}
+
+extern "C" int vqb_gumbel_rows_fwd_dev(const float* logits, const float* exp_noise, const float* tau_dev, int hard, float* y,
+                                       int64_t* idx_out, double* kl_sum, int64_t N, int K, void* stream) {
+    VQB_CHECK_ARG(logits && y && idx_out && kl_sum && tau_dev && N > 0 && K > 0, "gumbel_rows_fwd_dev: bad arguments");
+    gumbel_rows_fwd_kernel<<<(unsigned)ceil_div64(N * 32, 256), 256, 0, as_stream(stream)>>>(logits, exp_noise, 1.0f, hard, y, idx_out,
+                                                                                              kl_sum, N, K, tau_dev);
+    VQB_CHECK_LAUNCH("gumbel_rows_fwd_dev");
     return VQB_OK;
 }
 
@@ -302,7 +314,16 @@ extern "C" int vqb_gumbel_rows_bwd(const float* logits, const float* exp_noise, 
                                    float kl_scale, float* dlogits, int64_t N, int K, void* stream) {
     VQB_CHECK_ARG(logits && dlogits && N > 0 && K > 0 && tau > 0.f, "gumbel_rows_bwd: bad arguments");
     gumbel_rows_bwd_kernel<<<(unsigned)ceil_div64(N * 32, 256), 256, 0, as_stream(stream)>>>(logits, exp_noise, 1.0f / tau, dy, g_kl,
-                                                                                              kl_scale, dlogits, N, K);
+                                                                                              kl_scale, dlogits, N, K, nullptr);
     VQB_CHECK_LAUNCH("gumbel_rows_bwd");
+    return VQB_OK;
+}
+
+extern "C" int vqb_gumbel_rows_bwd_dev(const float* logits, const float* exp_noise, const float* tau_dev, const float* dy,
+                                       const float* g_kl, float kl_scale, float* dlogits, int64_t N, int K, void* stream) {
+    VQB_CHECK_ARG(logits && dlogits && tau_dev && N > 0 && K > 0, "gumbel_rows_bwd_dev: bad arguments");
+    gumbel_rows_bwd_kernel<<<(unsigned)ceil_div64(N * 32, 256), 256, 0, as_stream(stream)>>>(logits, exp_noise, 1.0f, dy, g_kl, kl_scale,
+                                                                                              dlogits, N, K, tau_dev);
+    VQB_CHECK_LAUNCH("gumbel_rows_bwd_dev");
     return VQB_OK;
 }

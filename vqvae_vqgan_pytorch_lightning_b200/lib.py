@@ -80,7 +80,10 @@ SIGNATURES = {
     'vqb_vq_entropy_combine_dcb': (_i, [_p, _p, _p, _p, _i, _i, _p]),
     'vqb_gumbel_rows_fwd': (_i, [_p, _p, _f, _i, _p, _p, _p, _i64, _i, _p]),
     'vqb_gumbel_rows_bwd': (_i, [_p, _p, _f, _p, _p, _f, _p, _i64, _i, _p]),
+    'vqb_gumbel_rows_fwd_dev': (_i, [_p, _p, _p, _i, _p, _p, _p, _i64, _i, _p]),
+    'vqb_gumbel_rows_bwd_dev': (_i, [_p, _p, _p, _p, _p, _f, _p, _i64, _i, _p]),
     'vqb_adamw': (_i, [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _f, _i, _f, _p]),
+    'vqb_adamw_dev': (_i, [_p, _p, _p, _p, _i64, _p, _f, _f, _f, _f, _f, _p]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -58,7 +58,16 @@ class Trainer:
     """One-process-per-GPU fit loop (rank / world from torch.distributed when initialised)."""
 
     def __init__(self, max_epochs: int = 1, num_training_batches: Optional[int] = None, overlap_grad_sync: bool = True,
-                 bucket_bytes: int = 25 << 20):
+                 bucket_bytes: int = 25 << 20, cuda_graph: bool = False, graph_warmup: int = 2):
+        """cuda_graph: capture one whole optimisation step (forward, backward, gradient reduction, optimizer) per step VARIANT
+        (model.graph_variant) after `graph_warmup` eager steps of that variant and replay it afterwards: ~600 kernel launches
+        become one graph launch, which removes the host-side launch gaps between the small kernels of the low-resolution
+        levels.  Everything that changes from step to step reaches the kernels through device memory (learning rate and Adam
+        bias corrections: FusedAdamW's pinned hyper buffer; Gumbel temperature / KL weight: the quantizer's; the batch: a
+        static input tensor), so a replay computes exactly what the eager step would."""
+        self.cuda_graph = cuda_graph
+        self.graph_warmup = graph_warmup
+        self._graphs: Dict[Any, dict] = {}
         self.overlap_grad_sync = overlap_grad_sync
         self.bucket_bytes = bucket_bytes
         self._buckets: Dict[int, list] = {}          # id(optimizer) -> [bucket state]
@@ -136,8 +145,59 @@ class Trainer:
 
     # ---- one optimisation step (what Lightning's fit loop does around training_step) -------------------
     def run_step(self, batch, batch_index: int):
+        if self.cuda_graph and torch.is_tensor(batch) and batch.is_cuda:
+            return self._run_step_graphed(batch, batch_index)
+        return self._run_step_eager(batch, batch_index)
+
+    def _run_step_graphed(self, batch, batch_index: int):
+        m = self.model
+        q = getattr(m, 'quantizer', None)
+        if q is not None and hasattr(q, 'device_consts'):
+            q.device_consts = True
+        key = (tuple(batch.shape), batch.dtype, m.graph_variant(batch_index) if hasattr(m, 'graph_variant') else ())
+        st = self._graphs.setdefault(key, {'calls': 0, 'graph': None})
+        st['calls'] += 1
+        if st['graph'] is None and st['calls'] <= self.graph_warmup:
+            return self._run_step_eager(batch, batch_index)
+        from . import ops
+        if st['graph'] is None:
+            # capture: the step runs once more under stream capture (nothing executes), on a static copy of the batch
+            st['input'] = batch.clone()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            m.on_train_batch_start(st['input'], batch_index)              # host scalars of THIS step (pinned buffers are read at replay)
+            counts0 = [o.step_count for o in self.optimizers if hasattr(o, 'host_step_update')]
+            with torch.cuda.graph(g):
+                st['loss'] = self._step_body(st['input'], batch_index)
+            # the capture ran the host-side bookkeeping of one step without executing it: undo, the replay below performs it
+            for o, c in zip([o for o in self.optimizers if hasattr(o, 'host_step_update')], counts0):
+                o.step_count = c
+            st['graph'] = g
+            st['logged'] = dict(m.logged)
+        else:
+            st['input'].copy_(batch, non_blocking=True)
+            m.on_train_batch_start(st['input'], batch_index)
+        for o in self._optimizers_stepped(key):
+            o.host_step_update()
+        st['graph'].replay()
+        ops.bump_weights_epoch()                  # weights changed behind the Python-side caches (packed layouts, codebook copies)
+        m.logged.update(st['logged'])
+        return st['loss']
+
+    def _optimizers_stepped(self, key):
+        """optimizers whose step() is part of this variant's graph (the discriminator's is absent before its start epoch)"""
+        variant = key[2]
+        if len(self.optimizers) > 1 and len(variant) == 2 and not variant[0]:
+            return [o for o in self.optimizers[:1] if hasattr(o, 'host_step_update')]
+        return [o for o in self.optimizers if hasattr(o, 'host_step_update')]
+
+    def _run_step_eager(self, batch, batch_index: int):
         m = self.model
         m.on_train_batch_start(batch, batch_index)
+        return self._step_body(batch, batch_index)
+
+    def _step_body(self, batch, batch_index: int):
+        m = self.model
         if m.automatic_optimization:
             opt = self.optimizers[0]
             opt.zero_grad()

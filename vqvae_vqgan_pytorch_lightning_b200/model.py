@@ -179,8 +179,19 @@ class VQVAE(BaseVQVAE, LightningModule):
         self.log('train/gen_loss', g_loss.detach())
         self.log('train/disc_loss', d_loss.detach())
         # per-batch code usage (model.py:289-293; defect B3 -- only the last batch is kept -- replicated)
-        self.train_epoch_usage_count = torch.bincount(used_indices.view(-1), minlength=self.cb_size)
+        self.train_epoch_usage_count = ops.code_histogram(used_indices, self.cb_size)
         return ae_loss
+
+    def graph_variant(self, batch_index: int):
+        """What makes two training steps DIFFERENT sequences of kernel launches (the CUDA-graph trainer keeps one captured graph
+        per value): whether the discriminator has started and whether this step carries the R1 penalty (loss.py:144-150)."""
+        c = self.criterion
+        if isinstance(c, VQLPIPSWithDiscriminator):
+            started = self.current_epoch >= c.adversarial_start_epoch
+            step = (self.current_epoch * self.trainer.num_training_batches) + batch_index
+            r1 = started and c.r1_regularization_cost is not None and step % c.r1_regularization_every == 0
+            return (started, r1)
+        return ()
 
     def on_train_epoch_end(self):
         if (self.reinit_every_n_epochs is not None and self.current_epoch % self.reinit_every_n_epochs == 0

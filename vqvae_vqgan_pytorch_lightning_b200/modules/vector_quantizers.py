@@ -78,17 +78,32 @@ class GumbelVectorQuantizer(BaseVectorQuantizer):
         self.straight_through = straight_through
         self.temp = temp
         self.kl_cost = kl_cost
+        # device mirror of (temp, kl_cost) for CUDA-graph replay: refreshed through a pinned buffer by a copy INSIDE forward
+        self._consts_host = None
+        self._consts_dev = None
+        self.device_consts = False
 
     def forward(self, x: torch.Tensor, exp_noise: torch.Tensor = None):
         hard = self.straight_through if self.training else True
         logits = self.x_to_logits(x, out_dtype=torch.float32)
         if exp_noise is None:
             exp_noise = torch.empty_like(logits, memory_format=torch.preserve_format).exponential_()     # RNG plumbing
-        y, idx, kl_mean = ops.gumbel_rows(logits, exp_noise, float(self.temp), hard)
+        if self.device_consts:
+            # (temp, kl_cost) travel through a pinned host buffer -> device copy: under CUDA-graph replay the copy node re-reads the
+            # values set_consts() wrote for this step (schedules of model.py:219-225)
+            if self._consts_dev is None or self._consts_dev.device != logits.device:
+                self._consts_host = torch.tensor([float(self.temp), float(self.kl_cost)], dtype=torch.float32).pin_memory()
+                self._consts_dev = torch.empty(2, dtype=torch.float32, device=logits.device)
+            self._consts_dev.copy_(self._consts_host, non_blocking=True)
+            y, idx, kl_mean = ops.gumbel_rows(logits, exp_noise, self._consts_dev[:1], hard)
+            kl = self._consts_dev[1] * kl_mean
+        else:
+            y, idx, kl_mean = ops.gumbel_rows(logits, exp_noise, float(self.temp), hard)
+            kl = self.kl_cost * kl_mean
         w = self.codebook.weight.t().reshape(self.embedding_dim, self.num_embeddings, 1, 1)
         quantized = ops.conv2d(y, w, out_dtype=torch.float32)
         self.last_counts = None
-        return quantized, idx, self.kl_cost * kl_mean
+        return quantized, idx, kl
 
     def get_consts(self):
         return self.temp, self.kl_cost
@@ -98,6 +113,9 @@ class GumbelVectorQuantizer(BaseVectorQuantizer):
             self.temp = temp
         if kl_cost is not None:
             self.kl_cost = kl_cost
+        if self._consts_host is not None:
+            self._consts_host[0] = float(self.temp)
+            self._consts_host[1] = float(self.kl_cost)
 
     @torch.no_grad()
     def vec_to_codes(self, x: torch.Tensor, exp_noise: torch.Tensor = None) -> torch.Tensor:

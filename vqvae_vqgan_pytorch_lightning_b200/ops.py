@@ -789,6 +789,14 @@ def vq_quantize(z, codebook, order=0, beta=0.25, cb_scale=1.0, want_stats=False,
     return VQFn.apply(z, codebook, order, beta, cb_scale, want_stats, prep)
 
 
+def code_histogram(idx: torch.Tensor, k: int) -> torch.Tensor:
+    """int64 histogram of code indices WITHOUT a host synchronisation (torch.bincount reads the maximum back to size its
+    output, which also forbids CUDA-graph capture): the per-batch usage counts of model.py:289-293."""
+    out = torch.zeros(k, dtype=torch.int64, device=idx.device)
+    flat = idx.reshape(-1)
+    return out.scatter_add_(0, flat, torch.ones_like(flat))
+
+
 def vq_codes(z, codebook, order=0, prep=None):
     """argmin only (vec_to_codes, vector_quantizers.py:63-84,182-203,358-381) -> idx [B, h*w] int64."""
     z = as_nhwc(z.detach(), torch.float32)
@@ -913,7 +921,10 @@ class GumbelRowsFn(torch.autograd.Function):
         y = torch.empty_like(logits, memory_format=torch.preserve_format)
         idx = torch.empty(n, dtype=torch.int64, device=logits.device)
         kl = torch.zeros(1, dtype=torch.float64, device=logits.device)
-        call('vqb_gumbel_rows_fwd', ptr(logits), ptr(noise), tau, int(hard), ptr(y), ptr(idx), ptr(kl), n, k, stream())
+        if torch.is_tensor(tau):                 # temperature in device memory (CUDA-graph replay under a schedule)
+            call('vqb_gumbel_rows_fwd_dev', ptr(logits), ptr(noise), ptr(tau), int(hard), ptr(y), ptr(idx), ptr(kl), n, k, stream())
+        else:
+            call('vqb_gumbel_rows_fwd', ptr(logits), ptr(noise), tau, int(hard), ptr(y), ptr(idx), ptr(kl), n, k, stream())
         ctx.save_for_backward(logits, noise)
         ctx.cfg = (tau, n, k)
         ctx.mark_non_differentiable(idx)
@@ -926,7 +937,10 @@ class GumbelRowsFn(torch.autograd.Function):
         dyc = as_nhwc(dy, torch.float32) if dy is not None else None
         gk = g_kl.reshape(1).float().contiguous() if g_kl is not None else None
         dl = torch.empty_like(logits, memory_format=torch.preserve_format)
-        call('vqb_gumbel_rows_bwd', ptr(logits), ptr(noise), tau, ptr(dyc), ptr(gk), 1.0 / n, ptr(dl), n, k, stream())
+        if torch.is_tensor(tau):
+            call('vqb_gumbel_rows_bwd_dev', ptr(logits), ptr(noise), ptr(tau), ptr(dyc), ptr(gk), 1.0 / n, ptr(dl), n, k, stream())
+        else:
+            call('vqb_gumbel_rows_bwd', ptr(logits), ptr(noise), tau, ptr(dyc), ptr(gk), 1.0 / n, ptr(dl), n, k, stream())
         return dl, None, None, None
 
 
@@ -937,6 +951,11 @@ def gumbel_rows(logits, exp_noise, tau, hard):
 # ------------------------------------------------------------------------------------------------------
 # optimizer
 # ------------------------------------------------------------------------------------------------------
+def adamw_flat_dev(p, g, m, v, hyper, beta1, beta2, eps, weight_decay, grad_scale=1.0):
+    """AdamW over a flat range with {lr, bias corrections} in device memory (hyper: fp32 [>=3]); the caller bumps the weights epoch"""
+    call('vqb_adamw_dev', ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), ptr(hyper), beta1, beta2, eps, weight_decay, grad_scale, stream())
+
+
 def adamw_flat(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
     call('vqb_adamw', ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), lr, beta1, beta2, eps, weight_decay, step, grad_scale, stream())
     bump_weights_epoch()
