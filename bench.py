@@ -397,6 +397,11 @@ def run_workload(name, args, pkg, dev, rank, world, precision, steps, warmup, st
     vq_step = ksum.get('vqb_vq_fused') or ksum.get('vqb_vq_assign_tc') or ksum.get('vqb_vq_assign')
     if vq_step:
         rec['vq_in_step_us_per_launch'] = vq_step['ms'] / vq_step['calls'] * 1e3
+        und, full = getattr(pkg.ops.vq_assign_raw, 'last_undecided', None), getattr(pkg.ops.vq_assign_raw, 'last_fullscan', None)
+        if und is not None and full is not None and ksum.get('vqb_vq_fused'):
+            # the first steps after initialisation are the search's worst case: the reference's U(+-1/K) codebook against
+            # large-norm latents puts hundreds of codes within fp32 rounding of each other (rows that need the full exact scan)
+            rec['vq_in_step_rows'] = {'re_ranked': int(und), 'full_scan': int(full), 'of': bs * (image_size // 16) ** 2}
     if clk is not None:
         rec['clocks'] = clk
     return rec
