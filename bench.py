@@ -116,10 +116,17 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(',')])
 
+    def mark(self):
+        """index of the next sample: the sampler is started BEFORE the warm-up (nvidia-smi takes ~1 s to come up and holds a
+        driver lock meanwhile -- inside a timed region that showed up as one 1000 ms step) and only the samples taken between
+        mark() at the start of the timed regions and stop() are reported"""
+        self.first = len(self.rows)
+
     def stop(self):
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         self.proc.terminate()
+        self.rows = self.rows[getattr(self, 'first', 0):]
         sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
         mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
@@ -277,6 +284,9 @@ def run_workload(name, args, pkg, dev, rank, world, precision, steps, warmup, st
         return float(loss.detach().cpu())                                        # D2H read of the step's loss
 
     stamp(f'{name}/{precision}: model and inputs ready')
+    clocks = ClockSampler(dev.index or 0)
+    if rank == 0 and sample_clocks:
+        clocks.start()
     # warm-up: W steps, plus -- with graphs -- enough steps for every step variant met in the timed regions to be captured
     # (2 eager steps + the capture step per variant; the R1 variant of the VQGAN configs comes every 16th step)
     for i in range(warmup + ((3 + (33 if WORKLOADS[name]['gan'] else 0)) if use_graph else 0)):
@@ -290,9 +300,8 @@ def run_workload(name, args, pkg, dev, rank, world, precision, steps, warmup, st
         return None
 
     # ---- timed region 1: inputs resident in HBM (value, ms_per_step) ---------------------------------------------
-    clocks = ClockSampler(dev.index or 0)
     if rank == 0 and sample_clocks:
-        clocks.start()
+        clocks.mark()
     if not use_graph:
         pkg.lib.timer = pkg.lib.KernelTimer(['vqb_conv2d_fwd', 'vqb_conv2d_wgrad', 'vqb_vq_assign', 'vqb_vq_assign_tc', 'vqb_vq_fused'])
     launches0 = pkg.lib.launch_count
@@ -310,11 +319,16 @@ def run_workload(name, args, pkg, dev, rank, world, precision, steps, warmup, st
 
     # ---- timed region 2: end to end through the public API with host buffers ---------------------------------------
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    step_e2e(0)                                    # untimed: first use of the pinned H2D / D2H staging path
     barrier()
     f0.record()
+    t_dbg = []
     for i in range(steps):
+        t_a = time.perf_counter()
         step_e2e(i)
+        t_dbg.append((time.perf_counter() - t_a) * 1e3)
     f1.record()
+    stamp(f'{name}/{precision}: e2e per-step wall ms ' + ' '.join(f'{v:.1f}' for v in t_dbg))
     barrier()
     ms_e2e = f0.elapsed_time(f1)
     clk = clocks.stop() if (rank == 0 and sample_clocks) else None
