@@ -99,6 +99,16 @@ int vqb_unpack_conv_wgrad(const float* dwp, float* dw, int Co, int Ci, int KH, i
 int vqb_conv2d_fwd(int impl, const void* x, int x_dtype, const void* wp, const float* bias, const void* residual,
                    void* y, int y_dtype, int N, int H, int W, int Ci, int Co, int KH, int KW, int pad, int stride,
                    int act, float act_alpha, float gain, void* stream);
+/* vqb_conv2d_fwd that ALSO accumulates the GroupNorm statistics of its output (the consumer is GroupNorm(gn_groups, Co),
+ * autoencoder.py:25-39, 66-73): gn_sums [N][gn_groups][2] double, caller zero-fills, += (sum, sum of squares) of the final
+ * output values per (image, group) from the epilogue registers -- the separate statistics pass over the activation
+ * (vqb_gn_stats) disappears.  Tensor-core impls only; vqb_conv2d_fwd_gn_supported tells whether a problem qualifies
+ * (>= 128 pixels per image, 4 / 8 / 16 channels per group); gn_sums == NULL is plain vqb_conv2d_fwd. */
+int vqb_conv2d_fwd_gn(int impl, const void* x, int x_dtype, const void* wp, const float* bias, const void* residual,
+                      void* y, int y_dtype, int N, int H, int W, int Ci, int Co, int KH, int KW, int pad, int stride,
+                      int act, float act_alpha, float gain, double* gn_sums, int gn_groups, void* stream);
+int vqb_conv2d_fwd_gn_supported(int impl, int N, int H, int W, int Ci, int Co, int KH, int KW, int pad, int stride,
+                                int gn_groups);
 /* weight gradient: dwp[(kh*KW+kw)*Ci+ci][co] (fp32, mode-0 packed layout) = sum_pix x_shift * dy.
  * dwp must be zero-filled by the caller (split-K partial sums are accumulated with atomics). */
 int vqb_conv2d_wgrad(int impl, const void* x, int x_dtype, const void* dy, int dy_dtype, float* dwp,

@@ -107,3 +107,41 @@ def test_rgb_heads_on_tensor_cores(V):
     assert C.rel_err(yg, yo) < 1e-4
     assert C.rel_err(xg.grad.float(), xo.grad) < 8e-3              # dpre and dx are stored as bf16
     assert C.rel_err(wg.grad, wo.grad) < 5e-3 and C.rel_err(bg.grad, bo.grad) < 5e-3
+
+
+@pytest.mark.parametrize('n,h,w,ci,co,k,bias,res,f32out', [
+    (2, 64, 64, 128, 128, 3, True, True, False),     # swapped-operand kernel (conv_fwd_tc_halo_t), 4 channels per group, bf16 out
+    (3, 40, 24, 128, 128, 3, False, False, True),    # same kernel, ragged tiles, fp32 out
+    (2, 32, 32, 256, 256, 3, False, True, False),    # CTA-pair kernel (halo2), 8 channels per group
+    (3, 16, 16, 256, 512, 3, True, False, False),    # CTA-pair kernel, 16 channels per group, odd number of pixel tiles
+    (2, 16, 16, 128, 128, 3, False, True, False),    # one-CTA halo kernel (H < 32), 4 channels per group
+    (2, 32, 16, 256, 256, 1, True, False, False),    # generic kernel (1x1)
+])
+def test_conv_epilogue_groupnorm_statistics(V, n, h, w, ci, co, k, bias, res, f32out):
+    """vqb_conv2d_fwd_gn: the per-(image, group) sum / sum of squares of the convolution OUTPUT from the epilogue registers equal
+    those of the stored tensor (fp32 output: to accumulation order; bf16 output: the statistics see the values before the
+    bf16 rounding, 2^-9 relative per element with random sign), and GroupNorm fed with them equals GroupNorm on its own pass."""
+    torch.manual_seed(11)
+    x = r16(torch.randn(n, ci, h, w))
+    wt = r16(torch.randn(co, ci, k, k) / (ci * k * k) ** 0.5)
+    b = torch.randn(co) if bias else None
+    r = torch.randn(n, co, h, w) if res else None
+    out_dtype = torch.float32 if f32out else torch.bfloat16
+    rg = cl(r).to(out_dtype) if res else None
+    y = V.ops.conv2d(cl(x).bfloat16(), wt.cuda(), b.cuda() if bias else None, rg, pad=k // 2, out_dtype=out_dtype, gn_groups=32)
+    assert hasattr(y, '_gn_sums'), 'the convolution did not fuse the statistics'
+    sums, groups = y._gn_sums
+    assert groups == 32 and sums.numel() == n * 32 * 2
+    yf = y.float().reshape(n, 32, co // 32, h, w).double()
+    ref = torch.stack([yf.sum(dim=(2, 3, 4)), (yf * yf).sum(dim=(2, 3, 4))], dim=-1).reshape(-1)
+    tol = 1e-5 if f32out else 2e-3
+    scale = ref.reshape(n, 32, 2)[..., 1].sqrt().reshape(n, 32, 1).expand(n, 32, 2).reshape(-1) * (co // 32 * h * w) ** 0.5   # |x|_2 * sqrt(count)
+    got = sums.reshape(n, 32, 2)
+    assert float(((got[..., 0].reshape(-1) - ref.reshape(n, 32, 2)[..., 0].reshape(-1).cuda()).abs() / scale.reshape(n, 32, 2)[..., 0].reshape(-1).cuda()).max()) < tol
+    assert C.rel_err(got[..., 1], ref.reshape(n, 32, 2)[..., 1]) < tol
+    # GroupNorm + SiLU with the fused statistics vs its own statistics pass on the same tensor
+    gamma, beta = torch.randn(1, co, 1, 1).cuda(), torch.randn(1, co, 1, 1).cuda()
+    o1 = V.ops.group_norm_act(y, gamma, beta)
+    y2 = y.detach().clone()
+    o2 = V.ops.group_norm_act(y2, gamma, beta)
+    assert C.rel_err(o1.float(), o2.float()) < (1e-5 if f32out else 6e-3)

@@ -11,14 +11,41 @@ int vqb_conv2d_dgrad_simt(const void* dy, int dy_dtype, const float* wd, void* d
                           int Co, int KH, int KW, int pad, int stride, cudaStream_t stream);
 int vqb_conv2d_fwd_tc(const void* x, const void* wp, const float* bias, const void* residual, void* y, int y_dtype, int N,
                       int H, int W, int Ci, int Co, int KH, int KW, int pad, int act, float alpha, float gain,
-                      cudaStream_t stream, int Cx);
+                      cudaStream_t stream, int Cx, double* gn_sums, int gn_groups);
 int vqb_conv2d_wgrad_tc(const void* x, const void* dy, float* dwp, int N, int H, int W, int Ci, int Co, int KH, int KW,
                         int pad, cudaStream_t stream);
+
+extern "C" int vqb_conv2d_fwd_gn(int impl, const void* x, int x_dtype, const void* wp, const float* bias, const void* residual,
+                                 void* y, int y_dtype, int N, int H, int W, int Ci, int Co, int KH, int KW, int pad, int stride,
+                                 int act, float act_alpha, float gain, double* gn_sums, int gn_groups, void* stream);
 
 extern "C" int vqb_conv2d_fwd(int impl, const void* x, int x_dtype, const void* wp, const float* bias, const void* residual,
                               void* y, int y_dtype, int N, int H, int W, int Ci, int Co, int KH, int KW, int pad, int stride,
                               int act, float act_alpha, float gain, void* stream) {
+    return vqb_conv2d_fwd_gn(impl, x, x_dtype, wp, bias, residual, y, y_dtype, N, H, W, Ci, Co, KH, KW, pad, stride, act, act_alpha,
+                             gain, nullptr, 0, stream);
+}
+
+// 1 when vqb_conv2d_fwd_gn can fuse the GroupNorm statistics for this problem (tensor-core impl, >= 128 pixels per image, 4 / 8 / 16
+// channels per group), else 0: the caller then runs vqb_gn_stats on the output as before
+extern "C" int vqb_conv2d_fwd_gn_supported(int impl, int N, int H, int W, int Ci, int Co, int KH, int KW, int pad, int stride,
+                                           int gn_groups) {
+    if (impl < 1 || impl > 3 || stride != 1 || gn_groups <= 0 || Co % gn_groups != 0 || Co % 64 != 0 || Ci % 64 != 0) return 0;
+    const int cpg = Co / gn_groups;
+    if (!(cpg == 4 || cpg == 8 || cpg == 16)) return 0;
+    if (H + 2 * pad - KH + 1 != H || W + 2 * pad - KW + 1 != W) return 0;
+    const bool halo = KH == 3 && KW == 3 && pad == 1 && H >= 16 && W >= 8;
+    if (halo) return 1;                              // the halo kernels tile inside one image
+    int tw = 1; while (tw * 2 <= W) tw *= 2; if (tw > 16) tw = 16; if (tw > 128) tw = 128;
+    int th = 1; while (th * 2 <= H) th *= 2; if (th > 128 / tw) th = 128 / tw;
+    return tw * th == 128 ? 1 : 0;                   // generic kernel: one image per 128-pixel tile (pick_tile's nb == 1)
+}
+
+extern "C" int vqb_conv2d_fwd_gn(int impl, const void* x, int x_dtype, const void* wp, const float* bias, const void* residual,
+                                 void* y, int y_dtype, int N, int H, int W, int Ci, int Co, int KH, int KW, int pad, int stride,
+                                 int act, float act_alpha, float gain, double* gn_sums, int gn_groups, void* stream) {
     VQB_CHECK_ARG(x && wp && y, "conv2d_fwd: null pointer");
+    VQB_CHECK_ARG(!gn_sums || impl >= 1, "conv2d_fwd: fused GroupNorm statistics need a tensor-core impl");
     if (impl == 0)
         return vqb_conv2d_fwd_simt(x, x_dtype, (const float*)wp, bias, residual, y, y_dtype, N, H, W, Ci, Co, KH, KW, pad,
                                    stride, act, act_alpha, gain, as_stream(stream));
@@ -26,7 +53,7 @@ extern "C" int vqb_conv2d_fwd(int impl, const void* x, int x_dtype, const void* 
         VQB_CHECK_ARG(x_dtype == VQB_BF16, "conv2d_fwd(tcgen05): x must be bf16");
         VQB_CHECK_ARG(stride == 1, "conv2d_fwd(tcgen05): stride must be 1");
         return vqb_conv2d_fwd_tc(x, wp, bias, residual, y, y_dtype, N, H, W, Ci, Co, KH, KW, pad, act, act_alpha, gain,
-                                 as_stream(stream), Ci);
+                                 as_stream(stream), Ci, gn_sums, gn_groups);
     }
     if (impl == 2 || impl == 3) {
         // split-precision tcgen05 (strict numeric mode): x = [hi | lo] bf16 halves of Ci fp32 channels (2 * Ci channels), wp packed
@@ -34,7 +61,7 @@ extern "C" int vqb_conv2d_fwd(int impl, const void* x, int x_dtype, const void* 
         VQB_CHECK_ARG(x_dtype == VQB_BF16, "conv2d_fwd(tcgen05 split): x must hold bf16 [hi | lo] halves");
         VQB_CHECK_ARG(stride == 1 && Ci % 64 == 0, "conv2d_fwd(tcgen05 split): stride must be 1 and Ci a multiple of 64");
         return vqb_conv2d_fwd_tc(x, wp, bias, residual, y, y_dtype, N, H, W, (impl + 1) * Ci, Co, KH, KW, pad, act, act_alpha, gain,
-                                 as_stream(stream), 2 * Ci);
+                                 as_stream(stream), 2 * Ci, gn_sums, gn_groups);
     }
     vqb_set_error("conv2d_fwd: unknown impl %d", impl);
     return VQB_ERR_ARG;

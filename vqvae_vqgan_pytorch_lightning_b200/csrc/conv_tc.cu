@@ -113,11 +113,52 @@ struct FwdParams {
     void* y;
     int y_f32, act, narrow, res_prefetch;
     float alpha, gain;
+    // GroupNorm statistics of the OUTPUT fused into the epilogue (the consumer is a GroupNorm with Co / gn_cpg groups): per (image,
+    // group) sum and sum of squares of the final values, fp32 partials per tile, double atomics -- replaces the gn_stats pass
+    double* gn_sums;     // [N][Co / gn_cpg][2] or NULL
+    int gn_cpg;          // channels per group: 4, 8 or 16
 };
 
 // ---- shared epilogue: 32 accumulator columns of one pixel row -> bias / act / residual -> NHWC store ---------------
+// warp-level flush of per-thread GroupNorm partial sums of one 32-channel chunk: gs[2*g], gs[2*g+1] = (sum, sum of squares) of
+// group g of the chunk for THIS thread's pixel; the 32 lanes (pixels of one image) are reduced by shuffles, lane 0 adds to global
+__device__ __forceinline__ void gn_flush_chunk(const FwdParams& p, float (&gs)[16], int n, int c_abs, int lane) {
+    const int ngr = 32 / p.gn_cpg;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        if (i < 2 * ngr) {
+            float v = gs[i];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            gs[i] = v;
+        }
+    }
+    if (lane == 0) {
+        const int G = p.Co / p.gn_cpg;
+        double* dst = p.gn_sums + ((int64_t)n * G + c_abs / p.gn_cpg) * 2;
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (i < 2 * ngr) atomicAdd(dst + i, (double)gs[i]);
+    }
+}
+
+template <int SHIFT>
+__device__ __forceinline__ void gn_accumulate32_t(const float (&v)[32], float (&gs)[16]) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {                       // static register indices: g = j >> SHIFT
+        gs[2 * (j >> SHIFT)] += v[j];
+        gs[2 * (j >> SHIFT) + 1] = fmaf(v[j], v[j], gs[2 * (j >> SHIFT) + 1]);
+    }
+}
+__device__ __forceinline__ void gn_accumulate32(const FwdParams& p, const float (&v)[32], float (&gs)[16]) {
+    // cpg = 4 / 8 / 16 channels per group -> 8 / 4 / 2 groups in a 32-channel chunk
+    if (p.gn_cpg == 4) gn_accumulate32_t<2>(v, gs);
+    else if (p.gn_cpg == 8) gn_accumulate32_t<3>(v, gs);
+    else gn_accumulate32_t<4>(v, gs);
+}
+
 __device__ __forceinline__ void epilogue_chunk(const FwdParams& p, const uint32_t (&r)[32], bool valid, int64_t pix, int co0, int c,
-                                               const uint4* qpre = nullptr) {
+                                               const uint4* qpre = nullptr, float* gsums = nullptr) {
     if (!valid) return;
     if (p.narrow) {
         // Co < BN (e.g. the 3-channel image head): scalar, masked stores; static register indices
@@ -157,9 +198,8 @@ __device__ __forceinline__ void epilogue_chunk(const FwdParams& p, const uint32_
         const float* ro = p.residual ? reinterpret_cast<const float*>(p.residual) + off : nullptr;
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            if (ro) { float4 q = *reinterpret_cast<const float4*>(ro + j); o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w; }
-            *reinterpret_cast<float4*>(yo + j) = o;
+            if (ro) { float4 q = *reinterpret_cast<const float4*>(ro + j); v[j] += q.x; v[j + 1] += q.y; v[j + 2] += q.z; v[j + 3] += q.w; }
+            *reinterpret_cast<float4*>(yo + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         }
     } else {
         bf16* yo = reinterpret_cast<bf16*>(p.y) + off;
@@ -180,6 +220,7 @@ __device__ __forceinline__ void epilogue_chunk(const FwdParams& p, const uint32_
             *reinterpret_cast<uint4*>(yo + j) = o;
         }
     }
+    if (gsums) gn_accumulate32(p, v, *reinterpret_cast<float (*)[16]>(gsums));
 }
 
 // epilogue warps of both forward kernels: drain the MT sub-tile accumulators of every tile this CTA owns.
@@ -231,7 +272,16 @@ __device__ __forceinline__ void epilogue_loop(const FwdParams& p, uint32_t tmem_
             uint32_t r[32];
             ptx::tmem_ld32(t_addr + (uint32_t)c, r);
             ptx::tmem_ld_wait();
-            epilogue_chunk(p, r, valid, pix, co0, c, pre ? qc : nullptr);
+            if (p.gn_sums) {
+                float gs[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) gs[i] = 0.f;
+                epilogue_chunk(p, r, valid, pix, co0, c, pre ? qc : nullptr, gs);
+                const int nimg = (pt * p.MT + m) / (p.tiles_w * p.tiles_h);   // all 128 rows of a sub-tile lie in ONE image (nb == 1)
+                if (nimg < p.N) gn_flush_chunk(p, gs, nimg, co0 + c, lane);
+            } else {
+                epilogue_chunk(p, r, valid, pix, co0, c, pre ? qc : nullptr);
+            }
         }
         ptx::tc_fence_before();
         __syncwarp();
@@ -593,7 +643,15 @@ conv_fwd_tc_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 uint32_t r[32];
                 ptx::tmem_ld32(t_addr + (uint32_t)c, r);
                 ptx::tmem_ld_wait();
-                epilogue_chunk(p, r, valid, pix, co0, c, pre ? qc : nullptr);
+                if (p.gn_sums) {
+                    float gs[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) gs[i] = 0.f;
+                    epilogue_chunk(p, r, valid, pix, co0, c, pre ? qc : nullptr, gs);
+                    if (q < ptiles) gn_flush_chunk(p, gs, n, co0 + c, lane);         // (warp-uniform: q, n do not depend on the lane)
+                } else {
+                    epilogue_chunk(p, r, valid, pix, co0, c, pre ? qc : nullptr);
+                }
             }
             ptx::tc_fence_before();
             __syncwarp();
@@ -718,6 +776,7 @@ conv_fwd_tc_halo_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
             const int twi = pt % p.tiles_w, t2 = pt / p.tiles_w, thi = t2 % p.tiles_h, n = t2 / p.tiles_h;
             const int w0 = twi * TW, h0 = thi * TH;
             const int co8 = ct * BM + quarter * 32 + grp * 8;
+            float gsa = 0.f, gqa = 0.f, gsb = 0.f, gqb = 0.f;   // GroupNorm partial sums of channels co8..co8+3 / co8+4..co8+7 over this tile
             float bv[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) bv[u] = p.bias ? __ldg(p.bias + co8 + u) : 0.f;
@@ -785,6 +844,13 @@ conv_fwd_tc_halo_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
                             for (int u = 0; u < 4; ++u) ob[u] = __floats2bfloat162_rn(v[2 * u], v[2 * u + 1]);
                             *reinterpret_cast<uint4*>(yo) = o;
                         }
+                        if (p.gn_sums) {
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                gsa += v[u]; gqa = fmaf(v[u], v[u], gqa);
+                                gsb += v[4 + u]; gqb = fmaf(v[4 + u], v[4 + u], gqb);
+                            }
+                        }
                     }
                 }
                 __syncwarp();
@@ -793,6 +859,28 @@ conv_fwd_tc_halo_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tempty[as]);
             if (++as == 2) { as = 0; aphase ^= 1; }
+            if (p.gn_sums) {
+                // the eight lanes that share `grp` hold partial sums of the same eight channels (different pixel rows)
+#pragma unroll
+                for (int o = 4; o < 32; o <<= 1) {
+                    gsa += __shfl_xor_sync(0xffffffffu, gsa, o); gqa += __shfl_xor_sync(0xffffffffu, gqa, o);
+                    gsb += __shfl_xor_sync(0xffffffffu, gsb, o); gqb += __shfl_xor_sync(0xffffffffu, gqb, o);
+                }
+                if (prow == 0) {
+                    const int G = p.Co / p.gn_cpg;
+                    if (p.gn_cpg == 4) {
+                        double* dst = p.gn_sums + ((int64_t)n * G + co8 / 4) * 2;
+                        atomicAdd(dst, (double)gsa); atomicAdd(dst + 1, (double)gqa);
+                        atomicAdd(dst + 2, (double)gsb); atomicAdd(dst + 3, (double)gqb);
+                    } else if (p.gn_cpg == 8) {
+                        double* dst = p.gn_sums + ((int64_t)n * G + co8 / 8) * 2;
+                        atomicAdd(dst, (double)(gsa + gsb)); atomicAdd(dst + 1, (double)(gqa + gqb));
+                    } else {                                   // 16 channels per group: two neighbouring lanes, distinct atomics
+                        double* dst = p.gn_sums + ((int64_t)n * G + co8 / 16) * 2;
+                        atomicAdd(dst, (double)(gsa + gsb)); atomicAdd(dst + 1, (double)(gqa + gqb));
+                    }
+                }
+            }
         }
     }
     ptx::tc_fence_before();
@@ -1062,7 +1150,7 @@ extern "C" void vqb_set_halo_mode(int mode) { g_halo_override = mode; }
 // wraps modulo Cx, so the SAME kernels accumulate all terms in one fp32 TMEM accumulator.
 int vqb_conv2d_fwd_tc(const void* x, const void* wp, const float* bias, const void* residual, void* y, int y_dtype, int N,
                       int H, int W, int Ci, int Co, int KH, int KW, int pad, int act, float alpha, float gain,
-                      cudaStream_t stream, int Cx) {
+                      cudaStream_t stream, int Cx, double* gn_sums, int gn_groups) {
     VQB_CHECK_ARG(N > 0 && H > 0 && W > 0 && KH > 0 && KW > 0 && pad >= 0, "conv2d_fwd(tcgen05): bad geometry");
     VQB_CHECK_ARG(Ci % 64 == 0 && (Co % 64 == 0 || Co <= 16), "conv2d_fwd(tcgen05): need Ci %% 64 == 0 and (Co %% 64 == 0 or Co <= 16) (got %d, %d)", Ci, Co);
     VQB_CHECK_ARG(H + 2 * pad - KH + 1 == H && W + 2 * pad - KW + 1 == W, "conv2d_fwd(tcgen05): only 'same' convolutions");
@@ -1072,6 +1160,15 @@ int vqb_conv2d_fwd_tc(const void* x, const void* wp, const float* bias, const vo
     VQB_CHECK_ARG(Cx % 64 == 0 && (2 * Ci) % Cx == 0, "conv2d_fwd(tcgen05): bad split-operand channel count %d for Ci %d", Cx, Ci);
     p.N = N; p.H = H; p.W = W; p.Ci = Ci; p.Co = Co; p.KH = KH; p.KW = KW; p.pad = pad; p.Cx = Cx;
     p.narrow = (Co % 64 != 0);
+    p.gn_sums = nullptr; p.gn_cpg = 0;
+    if (gn_sums) {
+        const int cpg = (gn_groups > 0 && Co % gn_groups == 0) ? Co / gn_groups : 0;
+        if (p.narrow || !(cpg == 4 || cpg == 8 || cpg == 16)) {
+            vqb_set_error("conv2d_fwd(tcgen05): fused GroupNorm statistics need 4, 8 or 16 channels per group (Co=%d, groups=%d)", Co, gn_groups);
+            return VQB_ERR_UNSUPPORTED;
+        }
+        p.gn_sums = gn_sums; p.gn_cpg = cpg;
+    }
     // narrow heads: UMMA N = 16, the weight box rows beyond Co are zero-filled by TMA
     p.BN = p.narrow ? 16 : ((Co % 256 == 0) ? 256 : ((Co % 128 == 0) ? 128 : 64));
     p.co_tiles = p.narrow ? 1 : Co / p.BN;
@@ -1149,6 +1246,10 @@ int vqb_conv2d_fwd_tc(const void* x, const void* wp, const float* bias, const vo
         return VQB_OK;
     }
     pick_tile(BM, H, W, p.tw, p.th, p.nb);
+    if (p.gn_sums && p.nb != 1) {
+        vqb_set_error("conv2d_fwd(tcgen05): fused GroupNorm statistics need images of at least 128 pixels (tile spans %d images)", p.nb);
+        return VQB_ERR_UNSUPPORTED;
+    }
     p.tiles_w = (W + p.tw - 1) / p.tw; p.tiles_h = (H + p.th - 1) / p.th; p.tiles_n = (N + p.nb - 1) / p.nb;
     const int ptiles = p.tiles_w * p.tiles_h * p.tiles_n;
     p.MT = (p.BN <= 128 && ptiles >= 2 * sm_count()) ? 2 : 1;     // 2 x 128 pixels per CTA tile when the accumulators fit TMEM

@@ -33,6 +33,8 @@ SIGNATURES = {
     'vqb_im2col3x3_narrow': (_i, [_p, _i, _p, _i, _i, _i, _i, _i, _i, _p]),
     'vqb_unpack_conv_wgrad': (_i, [_p, _p, _i, _i, _i, _i, _f, _p]),
     'vqb_conv2d_fwd': (_i, [_i, _p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, _p]),
+    'vqb_conv2d_fwd_gn': (_i, [_i, _p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, _p, _i, _p]),
+    'vqb_conv2d_fwd_gn_supported': (_i, [_i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i]),
     'vqb_conv2d_wgrad': (_i, [_i, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     'vqb_set_halo_mode': (None, [_i]),
     'vqb_conv2d_dgrad': (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),

@@ -14,7 +14,9 @@ from ..lib import ACT_NONE, ACT_SILU, ACT_TANH
 class Conv2d(nn.Conv2d):
     """nn.Conv2d parameters (same init, same state_dict keys); forward = vqb_conv2d_fwd with fused epilogue."""
 
-    def forward(self, x, residual=None, act=ACT_NONE, out_dtype=None):
+    def forward(self, x, residual=None, act=ACT_NONE, out_dtype=None, gn_groups=0):
+        """gn_groups: number of groups of the GroupNorm that consumes this output (its statistics then come out of the
+        convolution's epilogue, ops.conv2d)"""
         pad = self.padding
         if isinstance(pad, str):
             if pad != 'same':
@@ -22,7 +24,8 @@ class Conv2d(nn.Conv2d):
             pad = self.kernel_size[0] // 2
         else:
             pad = pad[0]
-        return ops.conv2d(x, self.weight, self.bias, residual, pad=pad, stride=self.stride[0], act=act, out_dtype=out_dtype)
+        return ops.conv2d(x, self.weight, self.bias, residual, pad=pad, stride=self.stride[0], act=act, out_dtype=out_dtype,
+                          gn_groups=gn_groups)
 
 
 class GroupNorm(nn.Module):
@@ -63,9 +66,10 @@ class ResBlock(nn.Module):
         else:
             # the skip connection goes through norm1's identity output: its gradient is added inside the GN backward kernel
             h, x = self.norm1(x, act=ACT_SILU, want_skip=True)
-        h = self.conv1(h)
+        h = self.conv1(h, gn_groups=self.norm2.num_groups)          # norm2's statistics come out of conv1's epilogue
         h = self.norm2(h, act=ACT_SILU)
-        return self.conv2(h, residual=x)
+        # the block output is (almost always) the input of the next GroupNorm: next block's norm1 or the final norm
+        return self.conv2(h, residual=x, gn_groups=self.norm2.num_groups)
 
 
 class Downsample(nn.Module):
@@ -90,7 +94,7 @@ class Upsample(nn.Module):
         self.conv = Conv2d(channels, channels, kernel_size=3, padding='same')
 
     def forward(self, x):
-        return self.conv(ops.upsample2(x))
+        return self.conv(ops.upsample2(x), gn_groups=32)            # feeds the next ResBlock's norm1 / the decoder's final norm
 
 
 class Encoder(nn.Module):
@@ -116,7 +120,7 @@ class Encoder(nn.Module):
         """x: [B,3,H,W] in [-1,1] (NCHW or channels-last) -> z [B,embedding_dim,H/2^L,W/2^L] fp32, channels-last."""
         if x.dtype not in (torch.float32, torch.bfloat16):
             x = x.float()
-        x = self.conv_in(ops.as_nhwc(x))
+        x = self.conv_in(ops.as_nhwc(x), gn_groups=32)
         x = self.blocks(x)
         x = self.final_residual(x)
         x = self.norm(x, act=ACT_SILU)
@@ -144,7 +148,7 @@ class Decoder(nn.Module):
 
     def forward(self, x):
         """x: [B,embedding_dim,h,w] -> reconstruction [B,3,H,W] fp32 in [-1,1] (tanh fused in conv_out's epilogue)."""
-        x = self.conv_in(ops.as_nhwc(x))
+        x = self.conv_in(ops.as_nhwc(x), gn_groups=32)
         x = self.initial_residual(x)
         x = self.blocks(x)
         x = self.norm(x, act=ACT_SILU)

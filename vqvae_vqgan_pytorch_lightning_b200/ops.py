@@ -212,14 +212,30 @@ def _packed_split_weight(weight: torch.Tensor, terms: int, dgrad: bool, scale: f
 
 
 def _conv_fwd_raw(impl: int, x: torch.Tensor, wp: torch.Tensor, bias, residual, out_dtype, ci, co, kh, kw, pad, stride, act,
-                  alpha, gain) -> torch.Tensor:
+                  alpha, gain, gn_sums: Optional[torch.Tensor] = None, gn_groups: int = 0) -> torch.Tensor:
     n, _, h, w = x.shape
     oh = (h + 2 * pad - kh) // stride + 1
     ow = (w + 2 * pad - kw) // stride + 1
     y = empty_nhwc(n, co, oh, ow, out_dtype, x.device)
-    call('vqb_conv2d_fwd', impl, ptr(x), dt(x), ptr(wp), ptr(bias), ptr(residual), ptr(y), dt(y), n, h, w, ci, co, kh, kw,
-         pad, stride, act, alpha, gain, stream())
+    if gn_sums is not None:
+        call('vqb_conv2d_fwd_gn', impl, ptr(x), dt(x), ptr(wp), ptr(bias), ptr(residual), ptr(y), dt(y), n, h, w, ci, co, kh, kw,
+             pad, stride, act, alpha, gain, ptr(gn_sums), gn_groups, stream())
+    else:
+        call('vqb_conv2d_fwd', impl, ptr(x), dt(x), ptr(wp), ptr(bias), ptr(residual), ptr(y), dt(y), n, h, w, ci, co, kh, kw,
+             pad, stride, act, alpha, gain, stream())
     return y
+
+
+_gn_fusion = None
+
+
+def gn_fusion_enabled() -> bool:
+    """VQB_GN_FUSE=0 switches the fused GroupNorm statistics of the convolution epilogues off (A/B measurements)"""
+    global _gn_fusion
+    if _gn_fusion is None:
+        import os
+        _gn_fusion = os.environ.get('VQB_GN_FUSE', '1') != '0'
+    return _gn_fusion
 
 
 def _narrow_route(prec: Precision, ci: int, co: int, kh: int, kw: int, pad: int, stride: int, frozen: bool = False) -> Optional[str]:
@@ -292,7 +308,10 @@ class Conv2dFn(torch.autograd.Function):
     102,114,133,153,170; fused epilogues replace the separate `x + h` of ResBlock.forward :77 and torch.tanh :180)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, residual, pad, stride, act, alpha, gain, out_dtype, w_scale):
+    def forward(ctx, x, weight, bias, residual, pad, stride, act, alpha, gain, out_dtype, w_scale, gn_groups=0):
+        """gn_groups > 0: the output feeds GroupNorm(gn_groups, co); when the kernel can, its epilogue also accumulates the
+        per-(image, group) sums of the output, returned as a second (non-differentiable) output [N * gn_groups * 2] float64
+        (an empty tensor otherwise) that GroupNormActFn consumes instead of running its statistics pass."""
         prec = get_precision()
         co, ci, kh, kw = weight.shape
         impl = prec.conv_impl(ci, co, stride, x.shape[0] * x.shape[2] * x.shape[3]) if (pad == kh // 2 and kh == kw) else 0
@@ -312,24 +331,41 @@ class Conv2dFn(torch.autograd.Function):
             residual = as_nhwc(residual, out_dtype)
         b = bias.detach().reshape(-1).float().contiguous() if bias is not None else None
         route = _narrow_route(prec, ci, co, kh, kw, pad, stride, frozen=not weight.requires_grad)
+        n_, _, h_, w_ = x.shape
+        sums = None
+
+        def gn_buffer(eff_impl, eci, ekh, ekw, epad):
+            if gn_groups and act == ACT_NONE and gn_fusion_enabled() and lib.load().vqb_conv2d_fwd_gn_supported(
+                    eff_impl, n_, h_, w_, eci, co, ekh, ekw, epad, stride, gn_groups):
+                return torch.zeros(n_ * gn_groups * 2, dtype=torch.float64, device=x.device)
+            return None
+
         if route == 'in':
             wp = _packed_weight(weight, 4, torch.bfloat16, w_scale)                  # [co][64], K zero-padded
-            y = _conv_fwd_raw(1, _im2col64(x), wp, b, residual, out_dtype, 64, co, 1, 1, 0, 1, act, alpha, gain)
+            sums = gn_buffer(1, 64, 1, 1, 0)
+            y = _conv_fwd_raw(1, _im2col64(x), wp, b, residual, out_dtype, 64, co, 1, 1, 0, 1, act, alpha, gain, sums, gn_groups)
         elif impl in (2, 3):
             # strict mode on the tensor cores: [hi | lo] operand halves, 3 / 4 bf16 products per multiply in one fp32 accumulator
             x = split_hi_lo(x)                                                        # saved in this form for the weight gradient
             wp = _packed_split_weight(weight, impl + 1, False, w_scale)
-            y = _conv_fwd_raw(impl, x, wp, b, residual, out_dtype, ci, co, kh, kw, pad, stride, act, alpha, gain)
+            sums = gn_buffer(impl, ci, kh, kw, pad)
+            y = _conv_fwd_raw(impl, x, wp, b, residual, out_dtype, ci, co, kh, kw, pad, stride, act, alpha, gain, sums, gn_groups)
         else:
             wp = _packed_weight(weight, 2 if impl == 1 else 0, torch.bfloat16 if impl == 1 else torch.float32, w_scale)
-            y = _conv_fwd_raw(impl, x, wp, b, residual, out_dtype, ci, co, kh, kw, pad, stride, act, alpha, gain)
+            sums = gn_buffer(impl, ci, kh, kw, pad) if impl == 1 else None
+            y = _conv_fwd_raw(impl, x, wp, b, residual, out_dtype, ci, co, kh, kw, pad, stride, act, alpha, gain, sums, gn_groups)
         ctx.save_for_backward(x, weight, y if act != ACT_NONE else None)
         ctx.cfg = (impl, pad, stride, act, alpha, gain, w_scale, bias is not None, residual is not None,
                    residual.dtype if residual is not None else None, in_dtype)
+        if gn_groups:
+            if sums is None:
+                sums = torch.empty(0, dtype=torch.float64, device=y.device)
+            ctx.mark_non_differentiable(sums)
+            return y, sums
         return y
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, _g_sums=None):
         x, weight, y = ctx.saved_tensors
         impl, pad, stride, act, alpha, gain, w_scale, has_bias, has_res, res_dtype, in_dtype = ctx.cfg
         prec = get_precision()
@@ -363,7 +399,7 @@ class Conv2dFn(torch.autograd.Function):
             call('vqb_unpack_conv_wgrad', ptr(dwp), ptr(dw), co, ci, kh, kw, w_scale, stream())
             if has_bias and ctx.needs_input_grad[2]:
                 db = db_fused if db_fused is not None else _colsum(dy, n * oh * ow, co)
-            return None, dw, db, dres, None, None, None, None, None, None, None
+            return None, dw, db, dres, None, None, None, None, None, None, None, None
         if route == 'out' and x.dtype == torch.bfloat16:
             pd = _im2col64(dy)                                                        # im2col of the 3-channel gradient
             if ctx.needs_input_grad[0]:
@@ -379,7 +415,7 @@ class Conv2dFn(torch.autograd.Function):
                     dw = dw * w_scale
             if has_bias and ctx.needs_input_grad[2]:
                 db = db_fused if db_fused is not None else _colsum(dy, n * oh * ow, co)
-            return dx, dw, db, dres, None, None, None, None, None, None, None
+            return dx, dw, db, dres, None, None, None, None, None, None, None, None
         if torch.is_grad_enabled():
             # the graph of this backward pass is being recorded (autograd.grad(..., create_graph=True): the R1 penalty,
             # loss.py:98-112): produce dx through ConvDgradFn, itself differentiable in dy and in the weight
@@ -389,7 +425,7 @@ class Conv2dFn(torch.autograd.Function):
             if ctx.needs_input_grad[0]:
                 ddt = in_dtype if in_dtype in (torch.float32, torch.bfloat16) else gdt
                 dx = ConvDgradFn.apply(dy, weight, h, w, pad, stride, w_scale, ddt)
-            return dx, None, None, dres, None, None, None, None, None, None, None
+            return dx, None, None, dres, None, None, None, None, None, None, None, None
         dy_ops = dy
         if impl in (2, 3) and dy.dtype == torch.float32 and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]):
             dy_ops = split_hi_lo(dy)                     # one [hi | lo] split of dy serves the input AND the weight gradient
@@ -399,7 +435,7 @@ class Conv2dFn(torch.autograd.Function):
             dw = _wgrad_raw(x, dy_ops, weight.shape, pad, stride, w_scale)
         if has_bias and ctx.needs_input_grad[2] and not _no_weight_grad:
             db = db_fused if db_fused is not None else _colsum(dy, n * oh * ow, co)
-        return dx, dw, db, dres, None, None, None, None, None, None, None
+        return dx, dw, db, dres, None, None, None, None, None, None, None, None
 
 
 def _colsum(dy: torch.Tensor, rows: int, co: int) -> torch.Tensor:
@@ -503,8 +539,15 @@ class ConvDgradFn(torch.autograd.Function):
 
 
 def conv2d(x, weight, bias=None, residual=None, pad=0, stride=1, act=ACT_NONE, alpha=0.0, gain=1.0, out_dtype=None,
-           w_scale=1.0):
-    return Conv2dFn.apply(x, weight, bias, residual, pad, stride, act, alpha, gain, out_dtype, w_scale)
+           w_scale=1.0, gn_groups=0):
+    """gn_groups > 0 (the output feeds GroupNorm(gn_groups, co)): the returned tensor carries `_gn_sums` = (sums, groups) when the
+    convolution's epilogue produced the statistics, which group_norm_act() then uses instead of its own pass over the tensor."""
+    if not gn_groups:
+        return Conv2dFn.apply(x, weight, bias, residual, pad, stride, act, alpha, gain, out_dtype, w_scale)
+    y, sums = Conv2dFn.apply(x, weight, bias, residual, pad, stride, act, alpha, gain, out_dtype, w_scale, gn_groups)
+    if sums.numel():
+        y._gn_sums = (sums, gn_groups)
+    return y
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -518,14 +561,16 @@ class GroupNormActFn(torch.autograd.Function):
     a separate elementwise pass over the activation."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, groups, eps, act, want_skip):
+    def forward(ctx, x, gamma, beta, groups, eps, act, want_skip, sums=None):
         x = as_nhwc(x)
         n, c, h, w = x.shape
         ga = gamma.detach().reshape(-1).float().contiguous()
         be = beta.detach().reshape(-1).float().contiguous()
-        sums = torch.zeros(n * groups * 2, dtype=torch.float64, device=x.device)
         stats = torch.empty(n * groups * 2, dtype=torch.float32, device=x.device)
-        call('vqb_gn_stats', ptr(x), dt(x), ptr(sums), n, h * w, c, groups, stream())
+        if sums is None or sums.numel() != n * groups * 2:
+            sums = torch.zeros(n * groups * 2, dtype=torch.float64, device=x.device)
+            call('vqb_gn_stats', ptr(x), dt(x), ptr(sums), n, h * w, c, groups, stream())
+        # else: the producing convolution's epilogue already accumulated them (vqb_conv2d_fwd_gn)
         call('vqb_gn_finalize', ptr(sums), ptr(stats), n, h * w, c, groups, eps, stream())
         y = torch.empty_like(x, memory_format=torch.preserve_format)
         call('vqb_gn_apply', ptr(x), dt(x), ptr(stats), ptr(ga), ptr(be), ptr(y), dt(y), n, h * w, c, groups, act, stream())
@@ -554,11 +599,13 @@ class GroupNormActFn(torch.autograd.Function):
             add = as_nhwc(dskip, dx.dtype) if dskip is not None else None
             call('vqb_gn_bwd_apply', ptr(x), dt(x), ptr(dy), dt(dy), ptr(stats), ptr(ga), ptr(be), ptr(coef), ptr(add), ptr(dx),
                  dt(dx), n, h * w, c, groups, act, stream())
-        return dx, dgamma.reshape(gshape), dbeta.reshape(bshape), None, None, None, None
+        return dx, dgamma.reshape(gshape), dbeta.reshape(bshape), None, None, None, None, None
 
 
 def group_norm_act(x, gamma, beta, groups=32, eps=1e-6, act=ACT_SILU, want_skip=False):
-    return GroupNormActFn.apply(x, gamma, beta, groups, eps, act, want_skip)
+    pre = getattr(x, '_gn_sums', None)
+    sums = pre[0] if (pre is not None and pre[1] == groups) else None
+    return GroupNormActFn.apply(x, gamma, beta, groups, eps, act, want_skip, sums)
 
 
 # ------------------------------------------------------------------------------------------------------
