@@ -114,8 +114,9 @@ def test_rgb_heads_on_tensor_cores(V):
     (3, 40, 24, 128, 128, 3, False, False, True),    # same kernel, ragged tiles, fp32 out
     (2, 32, 32, 256, 256, 3, False, True, False),    # CTA-pair kernel (halo2), 8 channels per group
     (3, 16, 16, 256, 512, 3, True, False, False),    # CTA-pair kernel, 16 channels per group, odd number of pixel tiles
-    (2, 16, 16, 128, 128, 3, False, True, False),    # one-CTA halo kernel (H < 32), 4 channels per group
-    (2, 32, 16, 256, 256, 1, True, False, False),    # generic kernel (1x1)
+    (5, 64, 64, 256, 512, 3, False, False, False),   # two channel tiles per pixel tile, many images per CTA (flush on image change)
+    (2, 16, 16, 128, 128, 3, False, True, False),    # one-CTA halo kernel (H < 32): NOT fused -> GroupNorm runs its own pass
+    (2, 32, 16, 256, 256, 1, True, False, False),    # generic kernel (1x1): not fused either
 ])
 def test_conv_epilogue_groupnorm_statistics(V, n, h, w, ci, co, k, bias, res, f32out):
     """vqb_conv2d_fwd_gn: the per-(image, group) sum / sum of squares of the convolution OUTPUT from the epilogue registers equal
@@ -129,7 +130,11 @@ def test_conv_epilogue_groupnorm_statistics(V, n, h, w, ci, co, k, bias, res, f3
     out_dtype = torch.float32 if f32out else torch.bfloat16
     rg = cl(r).to(out_dtype) if res else None
     y = V.ops.conv2d(cl(x).bfloat16(), wt.cuda(), b.cuda() if bias else None, rg, pad=k // 2, out_dtype=out_dtype, gn_groups=32)
-    assert hasattr(y, '_gn_sums'), 'the convolution did not fuse the statistics'
+    import os
+    fused = k == 3 and ((co % 256 == 0 and os.environ.get('VQB_GN_FUSE') == '2') or (co % 256 != 0 and h >= 32))
+    assert hasattr(y, '_gn_sums') == fused, 'by default only the swapped-operand 3x3 kernel fuses the statistics (VQB_GN_FUSE=2: CTA pairs too)'
+    if not fused:
+        return
     sums, groups = y._gn_sums
     assert groups == 32 and sums.numel() == n * 32 * 2
     yf = y.float().reshape(n, 32, co // 32, h, w).double()

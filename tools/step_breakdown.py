@@ -33,9 +33,9 @@ agg = collections.defaultdict(lambda: [0, 0.0, 0.0])
 for name, args, s, e in pkg.lib.timer.records:
     ms = s.elapsed_time(e)
     key = name; fl = 0.0
-    if name == 'vqb_conv2d_fwd':
+    if name in ('vqb_conv2d_fwd', 'vqb_conv2d_fwd_gn'):
         impl = args[0]; n, h, w, ci, co, kh, kw, pad, st = args[8:17]
-        key = f'conv_fwd impl{impl} {ci}->{co} k{kh} @{h}x{w}'; fl = 2.0 * n * h * w * ci * co * kh * kw
+        key = f'conv_fwd{"+gn" if name.endswith("gn") else ""} impl{impl} {ci}->{co} k{kh} @{h}x{w}'; fl = 2.0 * n * h * w * ci * co * kh * kw
     elif name == 'vqb_conv2d_wgrad':
         impl = args[0]; n, h, w, ci, co, kh, kw, pad, st = args[6:15]
         key = f'conv_wgrad impl{impl} {ci}->{co} k{kh} @{h}x{w}'; fl = 2.0 * n * h * w * ci * co * kh * kw

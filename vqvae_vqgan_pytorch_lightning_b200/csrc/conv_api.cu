@@ -1,6 +1,7 @@
 // C-ABI entry points for convolution: dispatch between the fp32 SIMT implicit GEMM (impl 0, conv_simt.cu) and
 // the tcgen05/TMA bf16 implicit GEMM (impl 1, conv_tc.cu; impl 2 / 3 = the same kernels on split-precision operands).
 #include "common.cuh"
+#include <stdlib.h>
 
 int vqb_conv2d_fwd_simt(const void* x, int x_dtype, const float* wp, const float* bias, const void* residual, void* y,
                         int y_dtype, int N, int H, int W, int Ci, int Co, int KH, int KW, int pad, int stride, int act,
@@ -34,11 +35,16 @@ extern "C" int vqb_conv2d_fwd_gn_supported(int impl, int N, int H, int W, int Ci
     const int cpg = Co / gn_groups;
     if (!(cpg == 4 || cpg == 8 || cpg == 16)) return 0;
     if (H + 2 * pad - KH + 1 != H || W + 2 * pad - KW + 1 != W) return 0;
+    // Measured on B200 (tools/step_breakdown.py, B = 64): the swapped-operand kernel (128-channel tiles, H >= 32: the 256^2 and 128^2
+    // levels, i.e. the largest tensors) pays +0.11 ms per 128->128 @256^2 launch for a 0.17 ms statistics pass saved: fused.  The
+    // CTA-pair kernel (256-channel tiles) pays +0.09 .. +0.2 ms per launch (40 shuffles per 32-channel chunk in an epilogue that
+    // has to keep pace with 94 %-busy tensor pipes) for passes of 0.02 .. 0.08 ms, and the epilogue-bound generic kernel tripled
+    // on the 64 -> 128 1x1 head: NOT fused unless VQB_GN_FUSE=2 asks for the CTA-pair kernel too (kept for A/B measurements).
     const bool halo = KH == 3 && KW == 3 && pad == 1 && H >= 16 && W >= 8;
-    if (halo) return 1;                              // the halo kernels tile inside one image
-    int tw = 1; while (tw * 2 <= W) tw *= 2; if (tw > 16) tw = 16; if (tw > 128) tw = 128;
-    int th = 1; while (th * 2 <= H) th *= 2; if (th > 128 / tw) th = 128 / tw;
-    return tw * th == 128 ? 1 : 0;                   // generic kernel: one image per 128-pixel tile (pick_tile's nb == 1)
+    if (!halo) return 0;
+    static const int level = getenv("VQB_GN_FUSE") ? atoi(getenv("VQB_GN_FUSE")) : 1;
+    if (Co % 256 == 0) return (level >= 2 && Co / 256 <= 2) ? 1 : 0;
+    return (Co % 128 == 0 && H >= 32) ? 1 : 0;
 }
 
 extern "C" int vqb_conv2d_fwd_gn(int impl, const void* x, int x_dtype, const void* wp, const float* bias, const void* residual,

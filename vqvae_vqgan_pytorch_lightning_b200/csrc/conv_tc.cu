@@ -120,25 +120,21 @@ struct FwdParams {
 };
 
 // ---- shared epilogue: 32 accumulator columns of one pixel row -> bias / act / residual -> NHWC store ---------------
-// warp-level flush of per-thread GroupNorm partial sums of one 32-channel chunk: gs[2*g], gs[2*g+1] = (sum, sum of squares) of
-// group g of the chunk for THIS thread's pixel; the 32 lanes (pixels of one image) are reduced by shuffles, lane 0 adds to global
-__device__ __forceinline__ void gn_flush_chunk(const FwdParams& p, float (&gs)[16], int n, int c_abs, int lane) {
-    const int ngr = 32 / p.gn_cpg;
+// GroupNorm statistics in the pixel-major epilogue (thread = pixel, 32 channels per chunk): gs[2g], gs[2g+1] = (sum, sum of
+// squares) of group g of the chunk for THIS thread's pixel.  The 32 lanes (pixels of one image) are reduced by xor butterflies
+// -- every lane ends with every total -- and lane i keeps total i in `acc`, which lives across tiles: global double atomics are
+// issued only when the CTA moves on to another image.  (One atomic per chunk and tile from every warp of every CTA hammered the
+// 64 addresses of the image in flight: measured +30 % on the convolution, more than the statistics pass it replaced.)
+__device__ __forceinline__ void gn_reduce_chunk(const FwdParams& p, float (&gs)[16], float& acc, int lane) {
+    const int nv = 64 / p.gn_cpg;                        // 2 * groups per chunk: 16 / 8 / 4
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-        if (i < 2 * ngr) {
+        if (i < nv) {
             float v = gs[i];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            gs[i] = v;
+            if (lane == i) acc += v;
         }
-    }
-    if (lane == 0) {
-        const int G = p.Co / p.gn_cpg;
-        double* dst = p.gn_sums + ((int64_t)n * G + c_abs / p.gn_cpg) * 2;
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-            if (i < 2 * ngr) atomicAdd(dst + i, (double)gs[i]);
     }
 }
 
@@ -272,16 +268,7 @@ __device__ __forceinline__ void epilogue_loop(const FwdParams& p, uint32_t tmem_
             uint32_t r[32];
             ptx::tmem_ld32(t_addr + (uint32_t)c, r);
             ptx::tmem_ld_wait();
-            if (p.gn_sums) {
-                float gs[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) gs[i] = 0.f;
-                epilogue_chunk(p, r, valid, pix, co0, c, pre ? qc : nullptr, gs);
-                const int nimg = (pt * p.MT + m) / (p.tiles_w * p.tiles_h);   // all 128 rows of a sub-tile lie in ONE image (nb == 1)
-                if (nimg < p.N) gn_flush_chunk(p, gs, nimg, co0 + c, lane);
-            } else {
-                epilogue_chunk(p, r, valid, pix, co0, c, pre ? qc : nullptr);
-            }
+            epilogue_chunk(p, r, valid, pix, co0, c, pre ? qc : nullptr);
         }
         ptx::tc_fence_before();
         __syncwarp();
@@ -531,6 +518,10 @@ conv_fwd_tc_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
     const uint32_t a_box_bytes = (uint32_t)((p.th + 2) * p.pitch * 128);
     const int ptiles = p.tiles_w * p.tiles_h * p.tiles_n;
+    // a CONTIGUOUS range of cluster tiles per cluster (neighbouring tiles share halo rows in L2, and the fused GroupNorm statistics
+    // are flushed only when the image changes)
+    const int tile_begin = (int)((int64_t)cluster_id * p.num_tiles / num_clusters);
+    const int tile_end = (int)((int64_t)(cluster_id + 1) * p.num_tiles / num_clusters);
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmA);
@@ -550,7 +541,7 @@ conv_fwd_tc_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     if (warp == 0) {
         if (lane == 0) {
             int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
-            for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
+            for (int tile = tile_begin; tile < tile_end; ++tile) {
                 const int ct = tile % p.co_tiles, pt = tile / p.co_tiles;
                 const int q = pt * 2 + (int)rank;                   // this CTA's pixel tile (may be one past the end)
                 const int twi = q % p.tiles_w, t2 = q / p.tiles_w, thi = t2 % p.tiles_h;
@@ -578,7 +569,7 @@ conv_fwd_tc_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             const uint32_t sbo = (uint32_t)p.pitch * 128u;
             int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
             int as = 0; uint32_t aphase = 0;
-            for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
+            for (int tile = tile_begin; tile < tile_end; ++tile) {
                 ptx::mbar_wait(&tempty[as], aphase ^ 1);
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.BN);
@@ -612,8 +603,28 @@ conv_fwd_tc_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const int wi = row % p.tw, hi = row / p.tw;
         const bool pre = p.residual && !p.y_f32 && p.res_prefetch;
         const int nch = (p.BN - half * 32 + 63) / 64;
+        // fused GroupNorm statistics: acc[ct][s] = this lane's total (see gn_reduce_chunk) of chunk s of channel tile ct, image gn_n
+        float gacc[2][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) gacc[i >> 2][i & 3] = 0.f;
+        int gn_n = -1;
+        auto gn_flush = [&]() {
+            if (gn_n >= 0 && lane < 64 / p.gn_cpg) {
+                const int G = p.Co / p.gn_cpg;
+#pragma unroll
+                for (int ctl = 0; ctl < 2; ++ctl)
+#pragma unroll
+                    for (int s_ = 0; s_ < 4; ++s_)
+                        if (ctl < p.co_tiles && s_ < nch) {
+                            const int c_abs = ctl * p.BN + half * 32 + s_ * 64;
+                            atomicAdd(p.gn_sums + ((int64_t)gn_n * G + c_abs / p.gn_cpg) * 2 + lane, (double)gacc[ctl][s_]);
+                        }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) gacc[i >> 2][i & 3] = 0.f;
+        };
         int as = 0; uint32_t aphase = 0;
-        for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
+        for (int tile = tile_begin; tile < tile_end; ++tile) {
             const int ct = tile % p.co_tiles, pt = tile / p.co_tiles;
             const int co0 = ct * p.BN;
             const int q = pt * 2 + (int)rank;
@@ -631,6 +642,7 @@ conv_fwd_tc_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             };
             uint4 qn[4] = {};
             if (pre) fetch(0, qn);
+            if (p.gn_sums && q < ptiles && n != gn_n) { gn_flush(); gn_n = n; }
             ptx::mbar_wait(&tfull[as], aphase);
             ptx::tc_fence_after();
             const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * p.BN);
@@ -648,7 +660,12 @@ conv_fwd_tc_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
                     for (int i = 0; i < 16; ++i) gs[i] = 0.f;
                     epilogue_chunk(p, r, valid, pix, co0, c, pre ? qc : nullptr, gs);
-                    if (q < ptiles) gn_flush_chunk(p, gs, n, co0 + c, lane);         // (warp-uniform: q, n do not depend on the lane)
+                    // static accumulator indices: (ct, s_) enumerated
+#pragma unroll
+                    for (int ctl = 0; ctl < 2; ++ctl)
+#pragma unroll
+                        for (int sl = 0; sl < 4; ++sl)
+                            if (ctl == ct && sl == s_) gn_reduce_chunk(p, gs, gacc[ctl][sl], lane);
                 } else {
                     epilogue_chunk(p, r, valid, pix, co0, c, pre ? qc : nullptr);
                 }
@@ -658,6 +675,7 @@ conv_fwd_tc_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa_rank(ptx::smem_u32(&tempty[as]), 0));
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
+        if (p.gn_sums) gn_flush();
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -695,6 +713,9 @@ conv_fwd_tc_halo_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t x_box_bytes = (uint32_t)((TH + 2) * PITCH * 128);
+    // a CONTIGUOUS range of tiles per CTA (see conv_fwd_tc_halo2_kernel)
+    const int tile_begin = (int)((int64_t)blockIdx.x * p.num_tiles / gridDim.x);
+    const int tile_end = (int)((int64_t)(blockIdx.x + 1) * p.num_tiles / gridDim.x);
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmX);
@@ -713,7 +734,7 @@ conv_fwd_tc_halo_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
     if (warp == 0) {
         if (lane == 0) {
             int sx = 0, sw = 0; uint32_t px = 0, pw = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            for (int tile = tile_begin; tile < tile_end; ++tile) {
                 const int ct = tile % p.co_tiles, pt = tile / p.co_tiles;
                 const int twi = pt % p.tiles_w, t2 = pt / p.tiles_w, thi = t2 % p.tiles_h, n = t2 / p.tiles_h;
                 const int w0 = twi * TW, h0 = thi * TH, co0 = ct * BM;
@@ -736,7 +757,7 @@ conv_fwd_tc_halo_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
             const uint32_t idesc = ptx::umma_idesc_bf16(BM, NPIX, 0, 0);
             int sx = 0, sw = 0; uint32_t px = 0, pw = 0;
             int as = 0; uint32_t aphase = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            for (int tile = tile_begin; tile < tile_end; ++tile) {
                 ptx::mbar_wait(&tempty[as], aphase ^ 1);
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * NPIX);
@@ -770,13 +791,39 @@ conv_fwd_tc_halo_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
         const int half = (warp - 2) >> 2;                    // two warps per quarter take alternating 32-column chunks
         float* tsm = reinterpret_cast<float*>(tmem_slot + 4) + (size_t)(warp - 2) * (32 * 36);   // [32 pixels][36] fp32
         const int grp = lane & 3, prow = lane >> 2;          // phase 2: lane -> (pixel row within 8, group of 8 channels)
+        // fused GroupNorm statistics: partial sums of channels co8..co8+3 / co8+4..co8+7 over this lane's pixels, kept ACROSS tiles
+        // and flushed (shuffle reduction over the eight lanes that share `grp`, then double atomics) when the image or the
+        // channel tile changes -- one atomic per tile from every warp of every CTA hammered the 64 addresses of the image in flight
+        float gsa = 0.f, gqa = 0.f, gsb = 0.f, gqb = 0.f;
+        int gn_n = -1, gn_co8 = 0;
+        auto gn_flush = [&]() {
+            if (gn_n >= 0) {
+#pragma unroll
+                for (int o = 4; o < 32; o <<= 1) {
+                    gsa += __shfl_xor_sync(0xffffffffu, gsa, o); gqa += __shfl_xor_sync(0xffffffffu, gqa, o);
+                    gsb += __shfl_xor_sync(0xffffffffu, gsb, o); gqb += __shfl_xor_sync(0xffffffffu, gqb, o);
+                }
+                if (prow == 0) {
+                    const int G = p.Co / p.gn_cpg;
+                    if (p.gn_cpg == 4) {
+                        double* dst = p.gn_sums + ((int64_t)gn_n * G + gn_co8 / 4) * 2;
+                        atomicAdd(dst, (double)gsa); atomicAdd(dst + 1, (double)gqa);
+                        atomicAdd(dst + 2, (double)gsb); atomicAdd(dst + 3, (double)gqb);
+                    } else {                                   // 8 channels per group; 16: two neighbouring lanes add to the same group
+                        double* dst = p.gn_sums + ((int64_t)gn_n * G + gn_co8 / p.gn_cpg) * 2;
+                        atomicAdd(dst, (double)(gsa + gsb)); atomicAdd(dst + 1, (double)(gqa + gqb));
+                    }
+                }
+            }
+            gsa = gqa = gsb = gqb = 0.f;
+        };
         int as = 0; uint32_t aphase = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        for (int tile = tile_begin; tile < tile_end; ++tile) {
             const int ct = tile % p.co_tiles, pt = tile / p.co_tiles;
             const int twi = pt % p.tiles_w, t2 = pt / p.tiles_w, thi = t2 % p.tiles_h, n = t2 / p.tiles_h;
             const int w0 = twi * TW, h0 = thi * TH;
             const int co8 = ct * BM + quarter * 32 + grp * 8;
-            float gsa = 0.f, gqa = 0.f, gsb = 0.f, gqb = 0.f;   // GroupNorm partial sums of channels co8..co8+3 / co8+4..co8+7 over this tile
+            if (p.gn_sums && (n != gn_n || co8 != gn_co8)) { gn_flush(); gn_n = n; gn_co8 = co8; }
             float bv[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) bv[u] = p.bias ? __ldg(p.bias + co8 + u) : 0.f;
@@ -859,29 +906,8 @@ conv_fwd_tc_halo_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tempty[as]);
             if (++as == 2) { as = 0; aphase ^= 1; }
-            if (p.gn_sums) {
-                // the eight lanes that share `grp` hold partial sums of the same eight channels (different pixel rows)
-#pragma unroll
-                for (int o = 4; o < 32; o <<= 1) {
-                    gsa += __shfl_xor_sync(0xffffffffu, gsa, o); gqa += __shfl_xor_sync(0xffffffffu, gqa, o);
-                    gsb += __shfl_xor_sync(0xffffffffu, gsb, o); gqb += __shfl_xor_sync(0xffffffffu, gqb, o);
-                }
-                if (prow == 0) {
-                    const int G = p.Co / p.gn_cpg;
-                    if (p.gn_cpg == 4) {
-                        double* dst = p.gn_sums + ((int64_t)n * G + co8 / 4) * 2;
-                        atomicAdd(dst, (double)gsa); atomicAdd(dst + 1, (double)gqa);
-                        atomicAdd(dst + 2, (double)gsb); atomicAdd(dst + 3, (double)gqb);
-                    } else if (p.gn_cpg == 8) {
-                        double* dst = p.gn_sums + ((int64_t)n * G + co8 / 8) * 2;
-                        atomicAdd(dst, (double)(gsa + gsb)); atomicAdd(dst + 1, (double)(gqa + gqb));
-                    } else {                                   // 16 channels per group: two neighbouring lanes, distinct atomics
-                        double* dst = p.gn_sums + ((int64_t)n * G + co8 / 16) * 2;
-                        atomicAdd(dst, (double)(gsa + gsb)); atomicAdd(dst + 1, (double)(gqa + gqb));
-                    }
-                }
-            }
         }
+        if (p.gn_sums) gn_flush();
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -1167,6 +1193,12 @@ int vqb_conv2d_fwd_tc(const void* x, const void* wp, const float* bias, const vo
             vqb_set_error("conv2d_fwd(tcgen05): fused GroupNorm statistics need 4, 8 or 16 channels per group (Co=%d, groups=%d)", Co, gn_groups);
             return VQB_ERR_UNSUPPORTED;
         }
+        const bool halo_ok = KH == 3 && KW == 3 && pad == 1 && H >= 16 && W >= 8 &&
+                             ((Co % 256 == 0 && Co / 256 <= 2) || (Co % 256 != 0 && Co % 128 == 0 && H >= 32));
+        if (!halo_ok) {
+            vqb_set_error("conv2d_fwd(tcgen05): fused GroupNorm statistics are built into the CTA-pair and swapped-operand 3x3 kernels only");
+            return VQB_ERR_UNSUPPORTED;
+        }
         p.gn_sums = gn_sums; p.gn_cpg = cpg;
     }
     // narrow heads: UMMA N = 16, the weight box rows beyond Co are zero-filled by TMA
@@ -1246,10 +1278,6 @@ int vqb_conv2d_fwd_tc(const void* x, const void* wp, const float* bias, const vo
         return VQB_OK;
     }
     pick_tile(BM, H, W, p.tw, p.th, p.nb);
-    if (p.gn_sums && p.nb != 1) {
-        vqb_set_error("conv2d_fwd(tcgen05): fused GroupNorm statistics need images of at least 128 pixels (tile spans %d images)", p.nb);
-        return VQB_ERR_UNSUPPORTED;
-    }
     p.tiles_w = (W + p.tw - 1) / p.tw; p.tiles_h = (H + p.th - 1) / p.th; p.tiles_n = (N + p.nb - 1) / p.nb;
     const int ptiles = p.tiles_w * p.tiles_h * p.tiles_n;
     p.MT = (p.BN <= 128 && ptiles >= 2 * sm_count()) ? 2 : 1;     // 2 x 128 pixels per CTA tile when the accumulators fit TMEM
