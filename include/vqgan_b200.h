@@ -75,6 +75,13 @@ int vqb_convert(const void* x, int in_dtype, void* y, int out_dtype, int64_t n, 
  * scale multiplies every weight (StyleGAN2 equalised-lr gain, discriminator.py:148,165). */
 int vqb_pack_conv_weight(const float* w, void* wp, int out_dtype, int mode, int Co, int Ci, int KH, int KW,
                          float scale, void* stream);
+/* Every kernel-layout weight copy of a model in ONE launch (they are all stale after an optimizer step).  desc_table: device
+ * array of n_desc records of vqb_pack_desc_bytes() bytes each --
+ *   { const float* w; void* wp; int mode, out_is_bf16, Co, Ci, KH, KW; float scale; int pad; long long start; }
+ * (modes as in vqb_pack_conv_weight; `start` = first element of the record in the concatenated output index space, ascending);
+ * total_elems = sum of the output element counts. */
+size_t vqb_pack_desc_bytes(void);
+int vqb_pack_conv_weights_batched(const void* desc_table, int n_desc, int64_t total_elems, void* stream);
 /* Narrow-input 3x3 / pad-1 convolutions (the RGB heads: encoder.conv_in 3->128, and everything that touches the 3-channel
  * side of decoder.conv_out) run on tensor cores as a 64-channel 1x1 implicit GEMM over this im2col tensor:
  * P[n,h,w,j] = x[n,h+kh-1,w+kw-1,c] for j = (kh*3+kw)*C+c < 9*C, zero otherwise (C <= 7).  write_all = 0 writes only the

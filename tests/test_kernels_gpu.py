@@ -328,3 +328,33 @@ def test_test_step_metrics_match_definitions(V):
     usage = sum(torch.bincount(model.get_tokens(b).view(-1), minlength=32) for b in batches)
     assert torch.equal(model.test_usage_count, usage) and int(usage.sum()) == 12 * 64
     assert 0 < float(model.logged['perplexity']) <= 32
+
+
+def test_batched_weight_pack_equals_single_packs(V):
+    """vqb_pack_conv_weights_batched (one launch for every kernel-layout weight copy of a model) against vqb_pack_conv_weight, all
+    six layouts, bf16 and fp32 outputs, through the registry the convolutions use (re-pack on a weights-epoch bump)."""
+    from vqvae_vqgan_pytorch_lightning_b200 import ops
+    from vqvae_vqgan_pytorch_lightning_b200.lib import call, ptr, dt, stream
+    torch.manual_seed(12)
+    shapes = [(128, 64, 3, 3), (256, 128, 1, 1), (64, 64, 3, 3), (128, 3, 3, 3), (3, 128, 3, 3), (70, 130, 3, 3)]
+    ws = [torch.nn.Parameter(torch.randn(*s).cuda()) for s in shapes]
+    combos = []
+    for w in ws:
+        co, ci, kh, kw = w.shape
+        for mode, dtype in ((0, torch.float32), (1, torch.float32), (2, torch.bfloat16), (3, torch.bfloat16)):
+            combos.append((w, mode, dtype, 1.0 if mode != 2 else 0.5))
+        if kh * kw * ci <= 64:
+            combos.append((w, 4, torch.bfloat16, 1.0))
+        if kh * kw * co <= 64:
+            combos.append((w, 5, torch.bfloat16, 1.0))
+    for rnd in range(3):
+        got = [ops._packed_weight(w, m, d, sc) for (w, m, d, sc) in combos]      # round 0 registers, rounds 1-2 use the batched launch
+        for (w, m, d, sc), g in zip(combos, got):
+            co, ci, kh, kw = w.shape
+            ref = torch.empty_like(g)
+            call('vqb_pack_conv_weight', ptr(w.detach()), ptr(ref), dt(ref), m, co, ci, kh, kw, sc, stream())
+            assert torch.equal(g, ref), (rnd, tuple(w.shape), m)
+        with torch.no_grad():
+            for w in ws:
+                w.data.mul_(1.01)                    # parameters rewritten behind autograd's back, as the optimizer kernel does
+        ops.bump_weights_epoch()

@@ -230,6 +230,59 @@ extern "C" int vqb_pack_conv_weight(const float* w, void* wp, int out_dtype, int
     return VQB_OK;
 }
 
+// ---- all kernel-layout weight copies of a model in ONE launch -------------------------------------------------------------
+// After every optimizer step each convolution weight is re-packed into the layouts its kernels read (K-major bf16 for the
+// forward, flipped / transposed for dgrad, ...): ~100 launches of a few microseconds each per step.  The batched form walks a
+// descriptor table; element i of the concatenated outputs finds its descriptor by binary search on the start offsets.
+struct PackDesc {
+    const float* w;      // source [Co][Ci][KH][KW] fp32
+    void* wp;            // destination
+    int mode, bf16, co, ci, kh, kw;
+    float scale;
+    int pad_;
+    long long start;     // first element of this entry in the concatenated index space
+};
+
+__global__ void pack_weights_batched_kernel(const PackDesc* __restrict__ d, int n, long long total) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int lo = 0, hi = n - 1;
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (d[mid].start <= i) lo = mid; else hi = mid - 1; }
+        const PackDesc e = d[lo];
+        const long long j = i - e.start;
+        const int Co = e.co, Ci = e.ci, KH = e.kh, KW = e.kw;
+        float v = 0.f;
+        if (e.mode < 4) {
+            int co, ci, kh, kw;
+            if (e.mode == 0) { co = (int)(j % Co); long long r = j / Co; ci = (int)(r % Ci); r /= Ci; kw = (int)(r % KW); kh = (int)(r / KW); }
+            else if (e.mode == 1) { ci = (int)(j % Ci); long long r = j / Ci; co = (int)(r % Co); r /= Co; kw = KW - 1 - (int)(r % KW); kh = KH - 1 - (int)(r / KW); }
+            else if (e.mode == 2) { ci = (int)(j % Ci); long long r = j / Ci; kw = (int)(r % KW); r /= KW; kh = (int)(r % KH); co = (int)(r / KH); }
+            else { co = (int)(j % Co); long long r = j / Co; kw = KW - 1 - (int)(r % KW); r /= KW; kh = KH - 1 - (int)(r % KH); ci = (int)(r / KH); }
+            v = e.w[(((long long)co * Ci + ci) * KH + kh) * KW + kw];
+        } else {
+            const int inner = (e.mode == 4) ? Ci : Co, kreal = KH * KW * inner;
+            const int jj = (int)(j % 64), r = (int)(j / 64);
+            if (jj < kreal) {
+                const int c = jj % inner, tap = jj / inner, kw = tap % KW, kh = tap / KW;
+                v = (e.mode == 4) ? e.w[(((long long)r * Ci + c) * KH + kh) * KW + kw]
+                                  : e.w[(((long long)c * Ci + r) * KH + (KH - 1 - kh)) * KW + (KW - 1 - kw)];
+            }
+        }
+        v *= e.scale;
+        if (e.bf16) reinterpret_cast<bf16*>(e.wp)[j] = __float2bfloat16_rn(v);
+        else reinterpret_cast<float*>(e.wp)[j] = v;
+    }
+}
+
+extern "C" size_t vqb_pack_desc_bytes(void) { return sizeof(PackDesc); }
+
+extern "C" int vqb_pack_conv_weights_batched(const void* desc_table, int n_desc, int64_t total_elems, void* stream) {
+    VQB_CHECK_ARG(desc_table && n_desc > 0 && total_elems > 0, "pack_conv_weights_batched: bad arguments");
+    int g = grid_for(total_elems, 256);
+    pack_weights_batched_kernel<<<g, 256, 0, as_stream(stream)>>>((const PackDesc*)desc_table, n_desc, (long long)total_elems);
+    VQB_CHECK_LAUNCH("pack_conv_weights_batched");
+    return VQB_OK;
+}
+
 // 16-byte vector access: 8 bf16 or 4 fp32 per thread
 template <typename T> struct V16 { static constexpr int N = 16 / sizeof(T); };
 template <typename T>

@@ -30,6 +30,8 @@ SIGNATURES = {
     'vqb_split_hi_lo': (_i, [_p, _p, _i64, _i, _p]),
     'vqb_convert': (_i, [_p, _i, _p, _i, _i64, _p]),
     'vqb_pack_conv_weight': (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _f, _p]),
+    'vqb_pack_desc_bytes': (_sz, []),
+    'vqb_pack_conv_weights_batched': (_i, [_p, _i, _i64, _p]),
     'vqb_im2col3x3_narrow': (_i, [_p, _i, _p, _i, _i, _i, _i, _i, _i, _p]),
     'vqb_unpack_conv_wgrad': (_i, [_p, _p, _i, _i, _i, _i, _f, _p]),
     'vqb_conv2d_fwd': (_i, [_i, _p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, _p]),

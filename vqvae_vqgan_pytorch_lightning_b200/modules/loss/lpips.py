@@ -136,6 +136,8 @@ class LPIPS(nn.Module):
         self.lin = LinLayers(self.net.n_channels_list)
         if pretrained:
             self._load_pretrained(net_type, version)
+        for p_ in self.net.parameters():          # frozen trunk: its kernel-layout weight copies are packed once, not every step
+            p_._vqb_static = True
 
     def _load_pretrained(self, net_type: str, version: str) -> None:
         from torchvision import models

@@ -143,27 +143,114 @@ def nhwc_to_images(x: torch.Tensor, scale: float = 1.0, shift: float = 0.0, clam
 # ------------------------------------------------------------------------------------------------------
 # convolution
 # ------------------------------------------------------------------------------------------------------
-def _packed_weight(weight: torch.Tensor, mode: int, dtype: torch.dtype, scale: float = 1.0) -> torch.Tensor:
-    """Cached kernel-layout copy of an nn.Conv2d weight (see vqb_pack_conv_weight for the modes)."""
-    key = (weight._version, _weights_epoch, weight.data_ptr(), scale)
-    cache = getattr(weight, '_vqb_pack', None)
-    if cache is None or cache.get('key') != key:
-        cache = {'key': key}
-        try:
-            weight._vqb_pack = cache
-        except Exception:
-            pass
-    tag = (mode, dtype)
-    if tag not in cache:
+class _PackRegistry:
+    """Every (weight, layout) pair the kernels asked for, with a PERSISTENT packed buffer.  When the weights epoch moves (an
+    optimizer step rewrote the parameters), the first request re-packs ALL registered trainable entries in ONE launch
+    (vqb_pack_conv_weights_batched) instead of ~100 single launches spread over the step; weights marked `_vqb_static` (frozen
+    trunks: LPIPS) are packed once.  Entries hold weak references; a table is rebuilt when an entry is added or has died."""
+
+    def __init__(self):
+        self.entries = {}            # (id(weight), mode, dtype, scale) -> dict(ref, wp, shape, ...)
+        self.table = None            # device uint8 tensor of PackDesc records
+        self.table_keys = None
+        self.total = 0
+        self.epoch = -1              # weights epoch at which all table entries were last packed
+        self.dirty = True
+
+    def _alive(self):
+        return {k: e for k, e in self.entries.items() if e['ref']() is not None}
+
+    def lookup(self, weight, mode, dtype, scale):
+        import weakref
+        k = (id(weight), mode, dtype, scale)
+        e = self.entries.get(k)
+        w = e['ref']() if e is not None else None
+        if e is None or w is not weight or e['ptr'] != weight.data_ptr() or e['shape'] != tuple(weight.shape) or e['version'] != weight._version:
+            co, ci, kh, kw = weight.shape
+            numel = co * ci * kh * kw if mode < 4 else 64 * (co if mode == 4 else ci)      # modes 4/5 pad K to 64
+            wp = e['wp'] if (e is not None and e['wp'].numel() == numel and e['wp'].device == weight.device) else \
+                torch.empty(numel, dtype=dtype, device=weight.device)
+            e = {'ref': weakref.ref(weight), 'wp': wp, 'ptr': weight.data_ptr(), 'shape': tuple(weight.shape), 'mode': mode, 'dtype': dtype,
+                 'scale': scale, 'numel': numel, 'version': weight._version, 'fresh_epoch': None,
+                 'static': bool(getattr(weight, '_vqb_static', False))}
+            self.entries[k] = e
+            if not e['static']:
+                self.dirty = True
+        return e
+
+    def _pack_one(self, e, weight):
         co, ci, kh, kw = weight.shape
-        numel = co * ci * kh * kw if mode < 4 else 64 * (co if mode == 4 else ci)      # modes 4/5 pad K to 64
-        wp = torch.empty(numel, dtype=dtype, device=weight.device)
         src = weight.detach()
         if not src.is_contiguous() or src.dtype != torch.float32:
             src = src.float().contiguous()            # e.g. the transposed-codebook view used by the Gumbel einsum
-        call('vqb_pack_conv_weight', ptr(src), ptr(wp), dt(wp), mode, co, ci, kh, kw, scale, stream())
-        cache[tag] = wp
-    return cache[tag]
+        call('vqb_pack_conv_weight', ptr(src), ptr(e['wp']), dt(e['wp']), e['mode'], co, ci, kh, kw, e['scale'], stream())
+
+    def _rebuild(self):
+        import struct
+        self.entries = self._alive()
+        recs, start, keys = [], 0, []
+        for k, e in self.entries.items():
+            w = e['ref']()
+            if e['static'] or not (w.is_contiguous() and w.dtype == torch.float32):
+                continue                              # packed individually (once / through a temporary)
+            co, ci, kh, kw = e['shape']
+            recs.append(struct.pack('<QQiiiiiifiq', e['ptr'], e['wp'].data_ptr(), e['mode'], int(e['dtype'] == torch.bfloat16), co, ci, kh, kw,
+                                    float(e['scale']), 0, start))
+            keys.append(k)
+            start += e['numel']
+        assert not recs or len(recs[0]) == lib.load().vqb_pack_desc_bytes()
+        self.table_keys, self.total = keys, start
+        dev = next(iter(self.entries.values()))['wp'].device if self.entries else None
+        self.table = torch.frombuffer(bytearray(b''.join(recs)), dtype=torch.uint8).to(dev) if recs else None
+        self.dirty = False
+
+    def get(self, weight, mode, dtype, scale):
+        if not (weight.is_contiguous() and weight.dtype == torch.float32):
+            # a temporary view (the transposed codebook of the Gumbel einsum): packed on the spot, never registered
+            co, ci, kh, kw = weight.shape
+            numel = co * ci * kh * kw if mode < 4 else 64 * (co if mode == 4 else ci)
+            wp = torch.empty(numel, dtype=dtype, device=weight.device)
+            src = weight.detach().float().contiguous()
+            call('vqb_pack_conv_weight', ptr(src), ptr(wp), dt(wp), mode, co, ci, kh, kw, scale, stream())
+            return wp
+        e = self.lookup(weight, mode, dtype, scale)
+        if e['static']:
+            if e['fresh_epoch'] is None:
+                self._pack_one(e, weight); e['fresh_epoch'] = -1
+            return e['wp']
+        if e['fresh_epoch'] == _weights_epoch:
+            return e['wp']
+        if not batched_pack_enabled():
+            self._pack_one(e, weight); e['fresh_epoch'] = _weights_epoch
+            return e['wp']
+        if self.dirty:
+            self._rebuild()
+        if self.table is not None and self.epoch != _weights_epoch:
+            call('vqb_pack_conv_weights_batched', ptr(self.table), len(self.table_keys), self.total, stream())
+            self.epoch = _weights_epoch
+            for k in self.table_keys:
+                self.entries[k]['fresh_epoch'] = _weights_epoch
+        if e['fresh_epoch'] != _weights_epoch:        # registered after the batched launch of this epoch
+            self._pack_one(e, weight); e['fresh_epoch'] = _weights_epoch
+        return e['wp']
+
+
+_pack_registry = _PackRegistry()
+_batched_pack = None
+
+
+def batched_pack_enabled() -> bool:
+    """VQB_BATCHED_PACK=0: one pack launch per weight and layout, as in round 1 (A/B measurements)"""
+    global _batched_pack
+    if _batched_pack is None:
+        import os
+        _batched_pack = os.environ.get('VQB_BATCHED_PACK', '1') != '0'
+    return _batched_pack
+
+
+def _packed_weight(weight: torch.Tensor, mode: int, dtype: torch.dtype, scale: float = 1.0) -> torch.Tensor:
+    """Kernel-layout copy of an nn.Conv2d weight (see vqb_pack_conv_weight for the modes), refreshed when the weights changed."""
+    return _pack_registry.get(weight, mode, dtype, scale)
 
 
 def split_hi_lo(x: torch.Tensor) -> torch.Tensor:
