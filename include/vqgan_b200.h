@@ -78,8 +78,9 @@ int vqb_pack_conv_weight(const float* w, void* wp, int out_dtype, int mode, int 
 /* Every kernel-layout weight copy of a model in ONE launch (they are all stale after an optimizer step).  desc_table: device
  * array of n_desc records of vqb_pack_desc_bytes() bytes each --
  *   { const float* w; void* wp; int mode, out_is_bf16, Co, Ci, KH, KW; float scale; int pad; long long start; }
- * (modes as in vqb_pack_conv_weight; `start` = first element of the record in the concatenated output index space, ascending);
- * total_elems = sum of the output element counts. */
+ * (modes as in vqb_pack_conv_weight; `start` = first element of the record in the concatenated output index space, ascending,
+ * each record padded to a multiple of 4096 elements: one CTA serves 4096 elements of ONE record);
+ * total_elems = end of the last padded record. */
 size_t vqb_pack_desc_bytes(void);
 int vqb_pack_conv_weights_batched(const void* desc_table, int n_desc, int64_t total_elems, void* stream);
 /* Narrow-input 3x3 / pad-1 convolutions (the RGB heads: encoder.conv_in 3->128, and everything that touches the 3-channel

@@ -243,13 +243,24 @@ struct PackDesc {
     long long start;     // first element of this entry in the concatenated index space
 };
 
+constexpr int PACK_CHUNK = 4096;     // output elements per CTA; a descriptor's `start` is a multiple of it (the host pads)
+
 __global__ void pack_weights_batched_kernel(const PackDesc* __restrict__ d, int n, long long total) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    // one descriptor per CTA: found once by thread 0 (binary search on the chunk-aligned start offsets)
+    __shared__ int which;
+    const long long base = (long long)blockIdx.x * PACK_CHUNK;
+    if (threadIdx.x == 0) {
         int lo = 0, hi = n - 1;
-        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (d[mid].start <= i) lo = mid; else hi = mid - 1; }
-        const PackDesc e = d[lo];
-        const long long j = i - e.start;
-        const int Co = e.co, Ci = e.ci, KH = e.kh, KW = e.kw;
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (d[mid].start <= base) lo = mid; else hi = mid - 1; }
+        which = lo;
+    }
+    __syncthreads();
+    const PackDesc e = d[which];
+    const int Co = e.co, Ci = e.ci, KH = e.kh, KW = e.kw;
+    const long long count = (e.mode < 4) ? (long long)Co * Ci * KH * KW : 64ll * ((e.mode == 4) ? Co : Ci);
+    for (int t = threadIdx.x; t < PACK_CHUNK; t += blockDim.x) {
+        const long long j = base - e.start + t;
+        if (j >= count) break;
         float v = 0.f;
         if (e.mode < 4) {
             int co, ci, kh, kw;
@@ -276,9 +287,10 @@ __global__ void pack_weights_batched_kernel(const PackDesc* __restrict__ d, int 
 extern "C" size_t vqb_pack_desc_bytes(void) { return sizeof(PackDesc); }
 
 extern "C" int vqb_pack_conv_weights_batched(const void* desc_table, int n_desc, int64_t total_elems, void* stream) {
-    VQB_CHECK_ARG(desc_table && n_desc > 0 && total_elems > 0, "pack_conv_weights_batched: bad arguments");
-    int g = grid_for(total_elems, 256);
-    pack_weights_batched_kernel<<<g, 256, 0, as_stream(stream)>>>((const PackDesc*)desc_table, n_desc, (long long)total_elems);
+    VQB_CHECK_ARG(desc_table && n_desc > 0 && total_elems > 0 && total_elems % PACK_CHUNK == 0,
+                  "pack_conv_weights_batched: bad arguments (total_elems and every start must be multiples of %d)", PACK_CHUNK);
+    pack_weights_batched_kernel<<<(unsigned)(total_elems / PACK_CHUNK), 256, 0, as_stream(stream)>>>((const PackDesc*)desc_table, n_desc,
+                                                                                                    (long long)total_elems);
     VQB_CHECK_LAUNCH("pack_conv_weights_batched");
     return VQB_OK;
 }

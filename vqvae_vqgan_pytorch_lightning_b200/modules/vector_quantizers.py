@@ -55,7 +55,7 @@ class EMAVectorQuantizer(BaseVectorQuantizer):
                 counts, dw = stats[:k], stats[k:].view(k, self.embedding_dim)
                 ops.vq_ema_update(self.ema_count, self.ema_weight.data, self.codebook.weight.data, counts, dw, self.decay,
                                   self.epsilon, batch, prep=self._prep)
-                ops.bump_weights_epoch()
+                self._prep.invalidate_unless_fresh(self.codebook.weight)       # (no global weights-epoch bump: only the codebook moved)
         return q, idx, loss
 
     @torch.no_grad()

@@ -156,6 +156,7 @@ class _PackRegistry:
         self.total = 0
         self.epoch = -1              # weights epoch at which all table entries were last packed
         self.dirty = True
+        self.keepalive = []
 
     def _alive(self):
         return {k: e for k, e in self.entries.items() if e['ref']() is not None}
@@ -197,11 +198,19 @@ class _PackRegistry:
             recs.append(struct.pack('<QQiiiiiifiq', e['ptr'], e['wp'].data_ptr(), e['mode'], int(e['dtype'] == torch.bfloat16), co, ci, kh, kw,
                                     float(e['scale']), 0, start))
             keys.append(k)
-            start += e['numel']
+            start += (e['numel'] + 4095) // 4096 * 4096          # one CTA serves 4096 elements of ONE record
         assert not recs or len(recs[0]) == lib.load().vqb_pack_desc_bytes()
         self.table_keys, self.total = keys, start
         dev = next(iter(self.entries.values()))['wp'].device if self.entries else None
-        self.table = torch.frombuffer(bytearray(b''.join(recs)), dtype=torch.uint8).to(dev) if recs else None
+        if recs:
+            # pinned staging + async copy: legal under CUDA-graph capture; every table ever built stays alive, a captured graph
+            # keeps launching on the table (and the pinned source of its copy node) it was captured with
+            host = torch.frombuffer(bytearray(b''.join(recs)), dtype=torch.uint8).pin_memory()
+            self.table = torch.empty(host.numel(), dtype=torch.uint8, device=dev)
+            self.table.copy_(host, non_blocking=True)
+            self.keepalive.append((host, self.table))
+        else:
+            self.table = None
         self.dirty = False
 
     def get(self, weight, mode, dtype, scale):
@@ -819,6 +828,13 @@ class CodebookPrep:
 
     def mark_fresh(self, codebook: torch.Tensor):
         self.key = self._key(codebook)
+        self._fresh_tag = True
+
+    def invalidate_unless_fresh(self, codebook: torch.Tensor):
+        """after a kernel rewrote the codebook behind autograd's back: keep the cached copy only if that kernel refreshed it too"""
+        if not getattr(self, '_fresh_tag', False):
+            self.key = None
+        self._fresh_tag = False
 
 
 def _fused_vq_ok(flat: torch.Tensor, k: int, d: int) -> bool:
