@@ -65,4 +65,5 @@ def test_graph_replay_equals_eager(V, name, mode):
         if k in C.DEGENERATE or not eager[k].dtype.is_floating_point:
             continue
         num += float((graph[k].double() - eager[k].double()).pow(2).sum()); den += float(eager[k].double().pow(2).sum())
-    assert (num / den) ** 0.5 < (2e-4 if mode == 'strict' else 5e-2), (num / den) ** 0.5
+    # strict: 1e-4 .. 2.5e-4 measured between two runs of the 10-step GAN case (state dominated by the frozen trunk + initial weights)
+    assert (num / den) ** 0.5 < (1e-3 if mode == 'strict' else 5e-2), (num / den) ** 0.5

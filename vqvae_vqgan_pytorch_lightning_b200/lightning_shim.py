@@ -167,8 +167,10 @@ class Trainer:
             g = torch.cuda.CUDAGraph()
             m.on_train_batch_start(st['input'], batch_index)              # host scalars of THIS step (pinned buffers are read at replay)
             counts0 = [o.step_count for o in self.optimizers if hasattr(o, 'host_step_update')]
+            ops.take_capture_refs()
             with torch.cuda.graph(g):
                 st['loss'] = self._step_body(st['input'], batch_index)
+            st['refs'] = ops.take_capture_refs()          # cached tensors the graph addresses (packed-weight table, sources, ...)
             # the capture ran the host-side bookkeeping of one step without executing it: undo, the replay below performs it
             for o, c in zip([o for o in self.optimizers if hasattr(o, 'host_step_update')], counts0):
                 o.step_count = c

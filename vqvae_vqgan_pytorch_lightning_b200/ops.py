@@ -156,7 +156,8 @@ class _PackRegistry:
         self.total = 0
         self.epoch = -1              # weights epoch at which all table entries were last packed
         self.dirty = True
-        self.keepalive = []
+        self.table_host = None
+        self.capture_refs = []       # what a stream capture baked into its graph by address (handed to the graph's owner)
 
     def _alive(self):
         return {k: e for k, e in self.entries.items() if e['ref']() is not None}
@@ -203,14 +204,15 @@ class _PackRegistry:
         self.table_keys, self.total = keys, start
         dev = next(iter(self.entries.values()))['wp'].device if self.entries else None
         if recs:
-            # pinned staging + async copy: legal under CUDA-graph capture; every table ever built stays alive, a captured graph
-            # keeps launching on the table (and the pinned source of its copy node) it was captured with
+            # pinned staging + async copy: legal under CUDA-graph capture (the copy becomes a node that re-reads `host` at replay)
             host = torch.frombuffer(bytearray(b''.join(recs)), dtype=torch.uint8).pin_memory()
             self.table = torch.empty(host.numel(), dtype=torch.uint8, device=dev)
             self.table.copy_(host, non_blocking=True)
-            self.keepalive.append((host, self.table))
+            self.table_host = host
+            if torch.cuda.is_current_stream_capturing():
+                self.capture_refs.append((host, self.table))
         else:
-            self.table = None
+            self.table = self.table_host = None
         self.dirty = False
 
     def get(self, weight, mode, dtype, scale):
@@ -232,10 +234,17 @@ class _PackRegistry:
         if not batched_pack_enabled():
             self._pack_one(e, weight); e['fresh_epoch'] = _weights_epoch
             return e['wp']
+        if self.epoch != _weights_epoch and not self.dirty and self.table is not None and \
+                any(self.entries[k]['ref']() is None for k in self.table_keys):
+            self.dirty = True                         # a registered weight died: its storage may be unmapped by now, never launch on it
         if self.dirty:
             self._rebuild()
         if self.table is not None and self.epoch != _weights_epoch:
             call('vqb_pack_conv_weights_batched', ptr(self.table), len(self.table_keys), self.total, stream())
+            if torch.cuda.is_current_stream_capturing():
+                # the graph replays this launch: table, sources and destinations must outlive it (take_capture_refs)
+                ents = [self.entries[k] for k in self.table_keys]
+                self.capture_refs.append((self.table, self.table_host, [e['wp'] for e in ents], [e['ref']() for e in ents]))
             self.epoch = _weights_epoch
             for k in self.table_keys:
                 self.entries[k]['fresh_epoch'] = _weights_epoch
@@ -245,6 +254,13 @@ class _PackRegistry:
 
 
 _pack_registry = _PackRegistry()
+
+
+def take_capture_refs() -> list:
+    """Tensors whose addresses the stream capture that just ended baked into its graph through this module's caches; the
+    owner of the CUDA graph keeps the returned list for as long as the graph may be replayed."""
+    refs, _pack_registry.capture_refs = _pack_registry.capture_refs, []
+    return refs
 _batched_pack = None
 
 
