@@ -135,8 +135,11 @@ class ClockSampler:
                 'samples': len(sm)}
 
 
+CONV_ENTRY_POINTS = ('vqb_conv2d_fwd', 'vqb_conv2d_fwd_gn', 'vqb_conv2d_wgrad')     # fwd_gn = fwd + fused GroupNorm statistics
+
+
 def conv_flops(name, a):
-    if name == 'vqb_conv2d_fwd':
+    if name in ('vqb_conv2d_fwd', 'vqb_conv2d_fwd_gn'):
         n, h, w, ci, co, kh, kw, pad, stride = a[8:17]
     else:
         n, h, w, ci, co, kh, kw, pad, stride = a[6:15]
@@ -303,7 +306,7 @@ def run_workload(name, args, pkg, dev, rank, world, precision, steps, warmup, st
     if rank == 0 and sample_clocks:
         clocks.mark()
     if not use_graph:
-        pkg.lib.timer = pkg.lib.KernelTimer(['vqb_conv2d_fwd', 'vqb_conv2d_wgrad', 'vqb_vq_assign', 'vqb_vq_assign_tc', 'vqb_vq_fused'])
+        pkg.lib.timer = pkg.lib.KernelTimer(list(CONV_ENTRY_POINTS) + ['vqb_vq_assign', 'vqb_vq_assign_tc', 'vqb_vq_fused'])
     launches0 = pkg.lib.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -337,7 +340,7 @@ def run_workload(name, args, pkg, dev, rank, world, precision, steps, warmup, st
         # ---- timed region 3 (graphs only): the same steps EAGERLY, every convolution entry point bracketed by CUDA events ------
         trainer.cuda_graph = False
         step_resident(0)
-        pkg.lib.timer = pkg.lib.KernelTimer(['vqb_conv2d_fwd', 'vqb_conv2d_wgrad', 'vqb_vq_assign', 'vqb_vq_assign_tc', 'vqb_vq_fused'])
+        pkg.lib.timer = pkg.lib.KernelTimer(list(CONV_ENTRY_POINTS) + ['vqb_vq_assign', 'vqb_vq_assign_tc', 'vqb_vq_fused'])
         launches0 = pkg.lib.launch_count
         h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
@@ -376,9 +379,9 @@ def run_workload(name, args, pkg, dev, rank, world, precision, steps, warmup, st
 
     pk, pk_kind = peaks()
     total_images = bs * world * steps
-    conv_ms = sum(ksum[k]['ms'] for k in ('vqb_conv2d_fwd', 'vqb_conv2d_wgrad') if k in ksum)
-    conv_fl = sum(conv_flops(k, a) for k in ('vqb_conv2d_fwd', 'vqb_conv2d_wgrad') if k in ksum for a in ksum[k]['args'])
-    conv_calls = sum(ksum[k]['calls'] for k in ('vqb_conv2d_fwd', 'vqb_conv2d_wgrad') if k in ksum)
+    conv_ms = sum(ksum[k]['ms'] for k in CONV_ENTRY_POINTS if k in ksum)
+    conv_fl = sum(conv_flops(k, a) for k in CONV_ENTRY_POINTS if k in ksum for a in ksum[k]['args'])
+    conv_calls = sum(ksum[k]['calls'] for k in CONV_ENTRY_POINTS if k in ksum)
     achieved = conv_fl / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
     fast = precision != 'strict'
     peak = pk['bf16_tflops_sustained']
