@@ -135,16 +135,36 @@ class ClockSampler:
                 'samples': len(sm)}
 
 
-CONV_ENTRY_POINTS = ('vqb_conv2d_fwd', 'vqb_conv2d_fwd_gn', 'vqb_conv2d_wgrad')     # fwd_gn = fwd + fused GroupNorm statistics
+CONV_ENTRY_POINTS = ('vqb_conv2d_fwd', 'vqb_conv2d_fwd_gn', 'vqb_conv2d_wgrad', 'vqb_conv2d_fwd_sub', 'vqb_conv2d_wgrad_sub')
+
+
+def conv_shape(name, a):
+    """(kind, impl, N, H, W, Ci, Co, k, stride, residual, ALGORITHMIC flop) of one convolution entry-point call.  fwd_gn = fwd + fused
+    GroupNorm statistics.  The *_sub calls carry the discriminator's stride-2 3x3 convolution as a 2x2-tap convolution over the 4C
+    channels of the space-to-depth input (16C MACs per output issued): they are counted with the 9C MACs per output of the
+    strided convolution they implement (conv2d_resample.py:119-122), not with what the kernel issues."""
+    if name in ('vqb_conv2d_fwd', 'vqb_conv2d_fwd_gn'):
+        n, h, w, ci, co, kh, kw, pad, stride = a[8:17]
+        oh, ow = (h + 2 * pad - kh) // stride + 1, (w + 2 * pad - kw) // stride + 1
+        return ('fwd/dgrad' + ('+gn' if name.endswith('_gn') else ''), a[0], n, h, w, ci, co, kh, stride, bool(a[5]),
+                2.0 * n * oh * ow * co * ci * kh * kw)
+    if name == 'vqb_conv2d_wgrad':
+        n, h, w, ci, co, kh, kw, pad, stride = a[6:15]
+        oh, ow = (h + 2 * pad - kh) // stride + 1, (w + 2 * pad - kw) // stride + 1
+        return ('wgrad', a[0], n, h, w, ci, co, kh, stride, False, 2.0 * n * oh * ow * co * ci * kh * kw)
+    if name == 'vqb_conv2d_fwd_sub':
+        n, hx, wx, h, w, ci, co, t, off = a[6:15]
+        if off == 0:      # forward: [N, H, W, Co] from the 4C-channel space-to-depth input
+            return ('s2d fwd', 1, n, h, w, ci, co, 3, 2, bool(a[3]), 2.0 * n * h * w * co * (ci // 4) * 9)
+        return ('s2d dgrad', 1, n, h, w, ci, co, 3, 2, False, 2.0 * n * (h - 1) * (w - 1) * ci * (co // 4) * 9)
+    if name == 'vqb_conv2d_wgrad_sub':
+        n, hx, wx, h, w, ci, co, t, off = a[3:12]
+        return ('s2d wgrad', 1, n, h, w, ci, co, 3, 2, False, 2.0 * n * h * w * co * (ci // 4) * 9)
+    raise KeyError(name)
 
 
 def conv_flops(name, a):
-    if name in ('vqb_conv2d_fwd', 'vqb_conv2d_fwd_gn'):
-        n, h, w, ci, co, kh, kw, pad, stride = a[8:17]
-    else:
-        n, h, w, ci, co, kh, kw, pad, stride = a[6:15]
-    oh, ow = (h + 2 * pad - kh) // stride + 1, (w + 2 * pad - kw) // stride + 1
-    return 2.0 * n * oh * ow * co * ci * kh * kw
+    return conv_shape(name, a)[-1]
 
 
 # ------------------------------------------------------------------------------------------------------

@@ -91,6 +91,11 @@ int vqb_im2col3x3_narrow(const void* x, int x_dtype, void* P, int p_dtype, int N
                          void* stream);
 /* inverse of mode 0 for gradients: dw[co][ci][kh][kw] = scale * dwp[(kh*KW+kw)*Ci+ci][co] */
 int vqb_unpack_conv_wgrad(const float* dwp, float* dw, int Co, int Ci, int KH, int KW, float scale, void* stream);
+/* the same with accumulate != 0: dw += (dw = the parameter's .grad inside the optimizer's flat gradient buffer: replaces autograd's
+ * AccumulateGrad pass, model.py:244-264 manual_backward) and rezero != 0: dwp is cleared behind the read (a persistent per-weight
+ * partial-sum buffer then never needs a fill launch) */
+int vqb_unpack_conv_wgrad_acc(float* dwp, float* dw, int Co, int Ci, int KH, int KW, float scale, int accumulate, int rezero,
+                              void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * Convolution as implicit GEMM (replaces F.conv2d behind nn.Conv2d: autoencoder.py:55-61,102,114,133,153,170)
@@ -117,6 +122,19 @@ int vqb_conv2d_fwd_gn(int impl, const void* x, int x_dtype, const void* wp, cons
                       int act, float act_alpha, float gain, double* gn_sums, int gn_groups, void* stream);
 int vqb_conv2d_fwd_gn_supported(int impl, int N, int H, int W, int Ci, int Co, int KH, int KW, int pad, int stride,
                                 int gn_groups);
+/* T x T-tap sub-convolution on the 3x3 halo kernels (tcgen05, bf16 operands):
+ *     y[n,h,w,co] = act(bias + sum_{a,b<T} sum_ci x[n, h+off+a, w+off+b, ci] * wp[co][(a*T+b)*Ci + ci]),  x zero outside its Hx x Wx pixels,
+ * H x W = output size (may differ from the input's), T in {2,3}, -1 <= off, off + T <= 2.  It carries the discriminator's stride-2
+ * 3x3 convolution (stylegan2_discriminator/ops/conv2d_resample.py:119-122) without the 4x surplus of a full-resolution evaluation:
+ * on the 2x2 space-to-depth form z' [N, H/2+1, W/2+1, 4C] of the FIR-filtered input (written in that layout by vqb_fir4_s2d) the
+ * strided convolution is a 2x2-tap stride-1 convolution over 4C channels (T = 2, off = 0: 16C instead of 36C MACs per output); its
+ * input gradient is the same call on dy with the tap-flipped, channel-swapped weight (T = 2, off = -1, output (H/2+1) x (W/2+1)).
+ * vqb_conv2d_wgrad_sub: dwp[(a*T+b)*Ci + ci][co] (fp32, caller zero-fills) += sum_pix x[n,h+off+a,w+off+b,ci] * dy[n,h,w,co]. */
+int vqb_conv2d_sub_supported(int N, int Hx, int Wx, int H, int W, int Ci, int Co, int T, int off);
+int vqb_conv2d_fwd_sub(const void* x, const void* wp, const float* bias, const void* residual, void* y, int y_dtype, int N, int Hx,
+                       int Wx, int H, int W, int Ci, int Co, int T, int off, int act, float act_alpha, float gain, void* stream);
+int vqb_conv2d_wgrad_sub(const void* x, const void* dy, float* dwp, int N, int Hx, int Wx, int H, int W, int Ci, int Co, int T, int off,
+                         void* stream);
 /* weight gradient: dwp[(kh*KW+kw)*Ci+ci][co] (fp32, mode-0 packed layout) = sum_pix x_shift * dy.
  * dwp must be zero-filled by the caller (split-K partial sums are accumulated with atomics). */
 int vqb_conv2d_wgrad(int impl, const void* x, int x_dtype, const void* dy, int dy_dtype, float* dwp,
@@ -155,6 +173,18 @@ int vqb_gn_bwd_finalize(const double* part, const float* gamma, float* coef, flo
 int vqb_gn_bwd_apply(const void* x, int x_dtype, const void* dy, int dy_dtype, const float* stats,
                      const float* gamma, const float* beta, const float* coef, const void* add, void* dx, int dx_dtype,
                      int N, int HW, int C, int G, int act, void* stream);
+/* Two-launch forms of the same arithmetic (the finalize kernels folded into their consumers: 4 -> 2 launches per GroupNorm in
+ * each direction of autoencoder.py:25-39):
+ *   vqb_gn_apply_sums      = vqb_gn_finalize + vqb_gn_apply: mean / rstd are evaluated (in double) from sums[b][g][2] by every
+ *                            block for its own channels; stats_out[b][g][2] (may be NULL) receives them for the backward pass.
+ *   vqb_gn_bwd_apply_part  = vqb_gn_bwd_finalize + vqb_gn_bwd_apply: coef[b][g] is evaluated from part[b][c][2] by every block;
+ *                            block (0,0) also reduces dgamma[c] / dbeta[c] over the batch -- overwritten, or += when
+ *                            accumulate_param_grads != 0 (the destinations are then the parameters' .grad views). */
+int vqb_gn_apply_sums(const void* x, int x_dtype, const double* sums, const float* gamma, const float* beta, void* y, int y_dtype,
+                      float* stats_out, int N, int HW, int C, int G, float eps, int act, void* stream);
+int vqb_gn_bwd_apply_part(const void* x, int x_dtype, const void* dy, int dy_dtype, const float* stats, const float* gamma,
+                          const float* beta, const double* part, const void* add, void* dx, int dx_dtype, float* dgamma,
+                          float* dbeta, int accumulate_param_grads, int N, int HW, int C, int G, int act, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * Resampling (Downsample = avg_pool2d(2,2) autoencoder.py:89-91; Upsample = nearest-exact x2 :103-106)
@@ -192,6 +222,12 @@ int vqb_act_bwd_bias(const void* y, const void* dy, void* dx, int dtype, int act
  * (upfirdn2d with up=1: ops/upfirdn2d.py:120-208, kernels upfirdn2d.cu:97-341).  bwd = its adjoint (dx is [N,H,W,C]). */
 int vqb_fir4_fwd(const void* x, void* y, int dtype, int N, int H, int W, int C, int pad, int down, void* stream);
 int vqb_fir4_bwd(const void* dy, void* dx, int dtype, int N, int H, int W, int C, int pad, int down, void* stream);
+/* The down = 1 filter between a plain NHWC tensor and the 2x2 space-to-depth layout [N][ceil(H/2)][ceil(W/2)][(dy,dx,c)]:
+ *   out_s2d: y = s2d(FIR(x, pad)), x [N,H,W,C], OH = H + 2 pad - 3 (OW alike; padding slots of odd sizes are zero-filled);
+ *   in_s2d : y [N,OH,OW,C] = FIR(x, pad) of the logical [N,H,W,C] tensor stored in that layout -- with pad' = 3 - pad and
+ *            OH = the forward input height this is the adjoint of the first form (upfirdn2d.py:120-208 backward). */
+int vqb_fir4_s2d(const void* x, void* y, int dtype, int N, int H, int W, int C, int OH, int OW, int pad, int in_s2d, int out_s2d,
+                 void* stream);
 /* y[n,oh,ow,:] = x[n,2*oh+off,2*ow+off,:] and its adjoint (zero_upsample2 writes all of x).  A stride-2 3x3 convolution of the
  * discriminator (conv2d_resample.py:119-122) runs in the bf16 fast mode as the stride-1 tcgen05 convolution at full
  * resolution + decimate2(off=1); its backward is zero_upsample2 + the stride-1 dgrad / wgrad kernels. */
@@ -261,6 +297,9 @@ int vqb_vq_prep_codebook(const float* codebook, void* cb_half, float* cb_sq, int
 int vqb_vq_fused(const float* z, const float* codebook, const void* cb_half, const float* cb_sq, int order, float* q_out,
                  int64_t* idx_out, double* sse, float* counts, float* dw, int64_t N, int K, int D, int* undecided_rows_out,
                  void* stream);
+/* Tuning hook: device buffer [ctas][8] int64 that subsequent vqb_vq_fused launches fill with globaltimer stamps of their phase
+ * boundaries (start, prologue, scan, decide, re-rank, finish); NULL (default) = off. */
+void vqb_vq_fused_set_trace(void* dev_buf);
 /* vqb_vq_ema_update (below) that additionally writes cb_half / cb_sq of the updated codebook. */
 int vqb_vq_ema_update_prep(float* ema_count, float* ema_weight, float* codebook, const float* counts, const float* dw,
                            void* cb_half, float* cb_sq, int K, int D, float decay, float eps, float batch, void* stream);

@@ -35,11 +35,8 @@ conv, other = {}, {}
 for name, args, s, e in recs:
     dt = s.elapsed_time(e)
     if name in bench.CONV_ENTRY_POINTS:
-        fwd = name != 'vqb_conv2d_wgrad'
-        n, h, w, ci, co, kh, kw, pad, stride = args[8:17] if fwd else args[6:15]
-        key = ('fwd/dgrad' + ('+gn' if name.endswith('_gn') else '') if fwd else 'wgrad', args[0], n, h, w, ci, co, kh, stride,
-               bool(args[5]) if fwd else False)
-        d = conv.setdefault(key, [0, 0.0, 0.0]); d[0] += 1; d[1] += dt; d[2] += bench.conv_flops(name, args)
+        sh = bench.conv_shape(name, args)
+        d = conv.setdefault(sh[:-1], [0, 0.0, 0.0]); d[0] += 1; d[1] += dt; d[2] += sh[-1]
     else:
         d = other.setdefault(name, [0, 0.0]); d[0] += 1; d[1] += dt
 tot_ms = sum(v[1] for v in conv.values()) / a.steps

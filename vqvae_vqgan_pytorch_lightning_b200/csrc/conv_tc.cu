@@ -117,6 +117,10 @@ struct FwdParams {
     // group) sum and sum of squares of the final values, fp32 partials per tile, double atomics -- replaces the gn_stats pass
     double* gn_sums;     // [N][Co / gn_cpg][2] or NULL
     int gn_cpg;          // channels per group: 4, 8 or 16
+    // halo kernels: the taps actually multiplied, as a sub-rectangle of the 3x3 frame the halo box serves -- tap t reads the frame
+    // position (kh0 + t / ktw, kw0 + t % ktw) and the weight block t of the packed weight.  3x3: ntaps 9, ktw 3, kh0 = kw0 = 0.
+    // A 2x2-tap convolution (the space-to-depth form of the discriminator's stride-2 3x3 convolution and its dgrad) uses 4.
+    int ntaps, ktw, kh0, kw0;
 };
 
 // ---- shared epilogue: 32 accumulator columns of one pixel row -> bias / act / residual -> NHWC store ---------------
@@ -178,11 +182,31 @@ __device__ __forceinline__ void epilogue_chunk(const FwdParams& p, const uint32_
     }
     float v[32];
     if (p.bias || p.act != VQB_ACT_NONE || p.gain != 1.0f) {
+        // the 32 bias values of the chunk are the same for every pixel (thread): eight broadcast 16-byte loads, and the activation
+        // is selected ONCE per chunk -- a per-element __ldg + act_f() chain made the bias + lrelu / relu layers of the loss heads
+        // epilogue-bound (discriminator 128->256 @257^2: 422 TFLOP/s against 1.6 PFLOP/s for the same kernel without bias)
+        float bb[32];
+        if (p.bias) {
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + co0 + c);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            float t = __uint_as_float(r[j]);
-            if (p.bias) t += __ldg(p.bias + co0 + c + j);
-            v[j] = act_f(t, p.act, p.alpha) * p.gain;
+            for (int j = 0; j < 8; ++j) { const float4 q = __ldg(bp + j); bb[4 * j] = q.x; bb[4 * j + 1] = q.y; bb[4 * j + 2] = q.z; bb[4 * j + 3] = q.w; }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) bb[j] = 0.f;
+        }
+        const float gain = p.gain, alpha = p.alpha;
+        if (p.act == VQB_ACT_LRELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { const float t = __uint_as_float(r[j]) + bb[j]; v[j] = (t > 0.f ? t : t * alpha) * gain; }
+        } else if (p.act == VQB_ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(__uint_as_float(r[j]) + bb[j], 0.f) * gain;
+        } else if (p.act == VQB_ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = (__uint_as_float(r[j]) + bb[j]) * gain;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = act_f(__uint_as_float(r[j]) + bb[j], p.act, alpha) * gain;
         }
     } else {
 #pragma unroll
@@ -431,7 +455,7 @@ conv_fwd_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                     for (int m = 0; m < p.MT; ++m)
                         ptx::tma_load_4d(smemA + (size_t)sa * a_stage + m * a_tile, &tmA, &fullA[sa], (cc * BK) % p.Cx, w0[m] - 1, h0[m] - 1, n0[m]);
                     if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
-                    for (int tap = 0; tap < 9; ++tap) {
+                    for (int tap = 0; tap < p.ntaps; ++tap) {
                         ptx::mbar_wait(&emptyB[sb], pb ^ 1);
                         ptx::mbar_expect_tx(&fullB[sb], (uint32_t)b_stage);
                         ptx::tma_load_2d(smemB + (size_t)sb * b_stage, &tmB, &fullB[sb], tap * p.Ci + cc * BK, co0);
@@ -453,8 +477,8 @@ conv_fwd_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                 for (int cc = 0; cc < p.cchunks; ++cc) {
                     ptx::mbar_wait(&fullA[sa], pa);
                     const uint32_t a_addr = ptx::smem_u32(smemA + (size_t)sa * a_stage);
-                    for (int tap = 0; tap < 9; ++tap) {
-                        const int kh = tap / 3, kw = tap - kh * 3;
+                    for (int tap = 0; tap < p.ntaps; ++tap) {
+                        const int kh = p.kh0 + tap / p.ktw, kw = p.kw0 + tap % p.ktw;
                         ptx::mbar_wait(&fullB[sb], pb);
                         ptx::tc_fence_after();
                         const uint64_t bdesc = ptx::umma_smem_desc(ptx::smem_u32(smemB + (size_t)sb * b_stage), 0, 1024);
@@ -553,7 +577,7 @@ conv_fwd_tc_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                     ptx::tma_load_4d_2sm(smemA + (size_t)sa * a_stage, &tmA, ptx::mapa_rank(ptx::smem_u32(&fullA[sa]), 0), (cc * BK) % p.Cx, w0 - 1,
                                          h0 - 1, n0);
                     if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
-                    for (int tap = 0; tap < 9; ++tap) {
+                    for (int tap = 0; tap < p.ntaps; ++tap) {
                         ptx::mbar_wait(&emptyB[sb], pb ^ 1);
                         if (rank == 0) ptx::mbar_expect_tx(&fullB[sb], 2u * (uint32_t)b_stage);
                         ptx::tma_load_2d_2sm(smemB + (size_t)sb * b_stage, &tmB, ptx::mapa_rank(ptx::smem_u32(&fullB[sb]), 0),
@@ -576,8 +600,8 @@ conv_fwd_tc_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 for (int cc = 0; cc < p.cchunks; ++cc) {
                     ptx::mbar_wait(&fullA[sa], pa);
                     const uint32_t a_addr = ptx::smem_u32(smemA + (size_t)sa * a_stage);
-                    for (int tap = 0; tap < 9; ++tap) {
-                        const int kh = tap / 3, kw = tap - kh * 3;
+                    for (int tap = 0; tap < p.ntaps; ++tap) {
+                        const int kh = p.kh0 + tap / p.ktw, kw = p.kw0 + tap % p.ktw;
                         ptx::mbar_wait(&fullB[sb], pb);
                         ptx::tc_fence_after();
                         const uint64_t bdesc = ptx::umma_smem_desc(ptx::smem_u32(smemB + (size_t)sb * b_stage), 0, 1024);
@@ -743,7 +767,7 @@ conv_fwd_tc_halo_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
                     ptx::mbar_expect_tx(&fullX[sx], x_box_bytes);
                     ptx::tma_load_4d(smemX + (size_t)sx * x_stage, &tmX, &fullX[sx], (cc * BK) % p.Cx, w0 - 1, h0 - 1, n);
                     if (++sx == p.a_stages) { sx = 0; px ^= 1; }
-                    for (int tap = 0; tap < 9; ++tap) {
+                    for (int tap = 0; tap < p.ntaps; ++tap) {
                         ptx::mbar_wait(&emptyW[sw], pw ^ 1);
                         ptx::mbar_expect_tx(&fullW[sw], (uint32_t)w_stage);
                         ptx::tma_load_2d(smemW + (size_t)sw * w_stage, &tmW, &fullW[sw], tap * p.Ci + cc * BK, co0);
@@ -764,8 +788,8 @@ conv_fwd_tc_halo_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
                 for (int cc = 0; cc < p.cchunks; ++cc) {
                     ptx::mbar_wait(&fullX[sx], px);
                     const uint32_t x_addr = ptx::smem_u32(smemX + (size_t)sx * x_stage);
-                    for (int tap = 0; tap < 9; ++tap) {
-                        const int kh = tap / 3, kw = tap - kh * 3;
+                    for (int tap = 0; tap < p.ntaps; ++tap) {
+                        const int kh = p.kh0 + tap / p.ktw, kw = p.kw0 + tap % p.ktw;
                         ptx::mbar_wait(&fullW[sw], pw);
                         ptx::tc_fence_after();
                         const uint64_t adesc = ptx::umma_smem_desc(ptx::smem_u32(smemW + (size_t)sw * w_stage), 0, 1024);
@@ -1034,6 +1058,7 @@ struct WgradHaloParams {
     int tiles_w, tiles_h, CN, co_tiles, ci_tiles, stages;
     int ptiles_total, ptiles_per_split;
     float* dwp;
+    int ktw, kh0, kw0;   // taps per kernel row and first frame row / column (3, 0, 0 for a 3x3 kernel; see FwdParams)
 };
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -1086,7 +1111,7 @@ conv_wgrad_tc_halo_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid
                     for (int j = 0; j < BM / 64; ++j)
                         ptx::tma_load_4d(sa + j * DY_BLK, &tmDy, &full[stage], co0 + j * 64, w0, h0, n);
                     for (int j = 0; j < p.CN / 64; ++j)
-                        ptx::tma_load_4d(sa + a_bytes + j * X_BLK, &tmX, &full[stage], ci0 + j * 64, w0 - 1, h0 + kh - 1, n);
+                        ptx::tma_load_4d(sa + a_bytes + j * X_BLK, &tmX, &full[stage], ci0 + j * 64, w0 - 1, h0 + p.kh0 + kh - 1, n);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -1103,7 +1128,8 @@ conv_wgrad_tc_halo_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid
                     for (int j = 0; j < 4; ++j) {              // UMMA j: pixel rows 2j, 2j+1 of the 8x8 tile (16 K-rows)
 #pragma unroll
                         for (int kw = 0; kw < 3; ++kw) {
-                            const uint64_t bdesc = ptx::umma_smem_desc(sa + a_bytes + (uint32_t)((2 * j * PITCH + kw) * 128),
+                            if (kw >= p.ktw) break;
+                            const uint64_t bdesc = ptx::umma_smem_desc(sa + a_bytes + (uint32_t)((2 * j * PITCH + p.kw0 + kw) * 128),
                                                                        (uint32_t)X_BLK, (uint32_t)(PITCH * 128));
                             ptx::umma_bf16(tmem_base + (uint32_t)(kw * p.CN), adesc + (uint64_t)(j * 2048 / 16), bdesc, idesc,
                                            (s | j) != 0 ? 1u : 0u);
@@ -1119,9 +1145,9 @@ conv_wgrad_tc_halo_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid
             const int co = co0 + quarter * 32 + lane;
             ptx::mbar_wait(tfull, 0);
             ptx::tc_fence_after();
-            for (int kw = 0; kw < 3; ++kw) {
+            for (int kw = 0; kw < p.ktw; ++kw) {
                 const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(kw * p.CN);
-                float* out = p.dwp + ((int64_t)(kh * 3 + kw) * p.Ci + ci0) * p.Co + co;
+                float* out = p.dwp + ((int64_t)(kh * p.ktw + kw) * p.Ci + ci0) * p.Co + co;
                 for (int c = 0; c < p.CN; c += 32) {
                     uint32_t r[32];
                     ptx::tmem_ld32(t_addr + (uint32_t)c, r);
@@ -1174,10 +1200,16 @@ extern "C" void vqb_set_halo_mode(int mode) { g_halo_override = mode; }
 // [hi | lo] bf16 halves of C fp32 channels (Cx = 2C) and the packed weight holds `terms` blocks per tap (Ci = terms * C):
 // [wh | wh | wl] (3 terms: xh.wh + xl.wh + xh.wl) or [wh | wh | wl | wl] (4 terms, + xl.wl); the k loop's channel coordinate
 // wraps modulo Cx, so the SAME kernels accumulate all terms in one fp32 TMEM accumulator.
-int vqb_conv2d_fwd_tc(const void* x, const void* wp, const float* bias, const void* residual, void* y, int y_dtype, int N,
-                      int H, int W, int Ci, int Co, int KH, int KW, int pad, int act, float alpha, float gain,
-                      cudaStream_t stream, int Cx, double* gn_sums, int gn_groups) {
+// `sub` (optional): a T x T-tap sub-convolution y[n,h,w,:] = sum_{a,b<T} x[n, h+off+a, w+off+b, :] . wp[:, (a*T+b)*Ci ...] over an input of
+// Hx x Wx pixels (zero outside), executed by the 3x3 halo kernels on the tap sub-rectangle [off+1, off+1+T)^2 of their frame.
+struct SubConv { int Hx, Wx, T, off; };
+
+static int conv_fwd_tc_impl(const void* x, const void* wp, const float* bias, const void* residual, void* y, int y_dtype, int N,
+                            int H, int W, int Ci, int Co, int KH, int KW, int pad, int act, float alpha, float gain,
+                            cudaStream_t stream, int Cx, double* gn_sums, int gn_groups, const SubConv* sub) {
     VQB_CHECK_ARG(N > 0 && H > 0 && W > 0 && KH > 0 && KW > 0 && pad >= 0, "conv2d_fwd(tcgen05): bad geometry");
+    const int Hx = sub ? sub->Hx : H, Wx = sub ? sub->Wx : W;
+    const int wk = sub ? sub->T * sub->T * Ci : KH * KW * Ci;            // reduction length of the packed weight
     VQB_CHECK_ARG(Ci % 64 == 0 && (Co % 64 == 0 || Co <= 16), "conv2d_fwd(tcgen05): need Ci %% 64 == 0 and (Co %% 64 == 0 or Co <= 16) (got %d, %d)", Ci, Co);
     VQB_CHECK_ARG(H + 2 * pad - KH + 1 == H && W + 2 * pad - KW + 1 == W, "conv2d_fwd(tcgen05): only 'same' convolutions");
     VQB_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)wp & 15) == 0 && ((uintptr_t)y & 15) == 0, "conv2d_fwd(tcgen05): unaligned pointer");
@@ -1187,6 +1219,8 @@ int vqb_conv2d_fwd_tc(const void* x, const void* wp, const float* bias, const vo
     p.N = N; p.H = H; p.W = W; p.Ci = Ci; p.Co = Co; p.KH = KH; p.KW = KW; p.pad = pad; p.Cx = Cx;
     p.narrow = (Co % 64 != 0);
     p.gn_sums = nullptr; p.gn_cpg = 0;
+    p.ntaps = 9; p.ktw = 3; p.kh0 = 0; p.kw0 = 0;
+    if (sub) { p.ntaps = sub->T * sub->T; p.ktw = sub->T; p.kh0 = p.kw0 = sub->off + 1; }
     if (gn_sums) {
         const int cpg = (gn_groups > 0 && Co % gn_groups == 0) ? Co / gn_groups : 0;
         if (p.narrow || !(cpg == 4 || cpg == 8 || cpg == 16)) {
@@ -1213,7 +1247,7 @@ int vqb_conv2d_fwd_tc(const void* x, const void* wp, const float* bias, const vo
     const int mode = g_halo_override >= 0 ? g_halo_override : halo_mode();
     const bool halo = mode != 0 && KH == 3 && KW == 3 && pad == 1 && H >= 16 && W >= 8;
     CUtensorMap tmA, tmB;
-    int rc = make_weight_map(&tmB, wp, Co, KH * KW * Ci, p.BN); if (rc) return rc;
+    int rc = make_weight_map(&tmB, wp, Co, wk, p.BN); if (rc) return rc;
     // VQB_CONV_2CTA: 0 = never, 1 (default) = 256-channel output tiles, 2 = also 128-channel tiles (slower than the swapped-operand
     // kernel below: with N = 128 a CTA pair still feeds 128 x 16 of A per 64 cycles -- measured 1.08 vs 1.42 PFLOP/s)
     static const int use_2cta = getenv("VQB_CONV_2CTA") ? atoi(getenv("VQB_CONV_2CTA")) : 1;
@@ -1227,8 +1261,8 @@ int vqb_conv2d_fwd_tc(const void* x, const void* wp, const float* bias, const vo
         const int b_stage = (p.BN / 2) * BK * 2;
         p.a_stages = 3;
         p.b_stages = (SMEM_LIMIT - 2048 - p.a_stages * p.a_tile_bytes) / b_stage; if (p.b_stages > 12) p.b_stages = 12;
-        rc = make_weight_map(&tmB, wp, Co, KH * KW * Ci, p.BN / 2); if (rc) return rc;
-        rc = make_act_map(&tmA, x, N, H, W, Cx, p.pitch, p.th + 2, 1); if (rc) return rc;
+        rc = make_weight_map(&tmB, wp, Co, wk, p.BN / 2); if (rc) return rc;
+        rc = make_act_map(&tmA, x, N, Hx, Wx, Cx, p.pitch, p.th + 2, 1); if (rc) return rc;
         size_t smem = (size_t)p.a_stages * p.a_tile_bytes + (size_t)p.b_stages * b_stage + 1024 + 512;
         VQB_CUDA(cudaFuncSetAttribute(conv_fwd_tc_halo2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int clusters = p.num_tiles < sm_count() / 2 ? p.num_tiles : sm_count() / 2;
@@ -1247,7 +1281,7 @@ int vqb_conv2d_fwd_tc(const void* x, const void* wp, const float* bias, const vo
         p.a_stages = 2;
         const int tr_bytes = 8 * 32 * 36 * 4;                       // epilogue transpose tiles (8 warps)
         p.b_stages = (SMEM_LIMIT - 2048 - tr_bytes - p.a_stages * p.a_tile_bytes) / w_stage; if (p.b_stages > 12) p.b_stages = 12;
-        rc = make_act_map(&tmA, x, N, H, W, Cx, 10, 34, 1); if (rc) return rc;
+        rc = make_act_map(&tmA, x, N, Hx, Wx, Cx, 10, 34, 1); if (rc) return rc;
         size_t smem = (size_t)p.a_stages * p.a_tile_bytes + (size_t)p.b_stages * w_stage + 1024 + 512 + tr_bytes;
         VQB_CUDA(cudaFuncSetAttribute(conv_fwd_tc_halo_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
@@ -1259,6 +1293,7 @@ int vqb_conv2d_fwd_tc(const void* x, const void* wp, const float* bias, const vo
         p.tw = 8; p.th = 16; p.nb = 1;
         p.tiles_w = (W + 7) / 8; p.tiles_h = (H + 15) / 16; p.tiles_n = N;
         p.pitch = (mode == 2 || mode == 3) ? 16 : 10;
+        if (sub) { p.pitch = 10; }
         p.bo_mode = (mode == 3 || mode == 4) ? 1 : 0;
         p.a_tile_bytes = (((p.th + 2) * p.pitch * 128) + 1023) / 1024 * 1024;
         const int ptiles = p.tiles_w * p.tiles_h * p.tiles_n;
@@ -1269,7 +1304,7 @@ int vqb_conv2d_fwd_tc(const void* x, const void* wp, const float* bias, const vo
         p.b_stages = (SMEM_LIMIT - 2048 - p.a_stages * a_stage) / b_stage; if (p.b_stages > 12) p.b_stages = 12;
         VQB_CHECK_ARG(p.b_stages >= 2, "conv2d_fwd(tcgen05 halo): shared memory budget");
         p.stages = 0;
-        rc = make_act_map(&tmA, x, N, H, W, Cx, p.pitch, p.th + 2, 1); if (rc) return rc;
+        rc = make_act_map(&tmA, x, N, Hx, Wx, Cx, p.pitch, p.th + 2, 1); if (rc) return rc;
         size_t smem = (size_t)p.a_stages * a_stage + (size_t)p.b_stages * b_stage + 1024 + 512;
         VQB_CUDA(cudaFuncSetAttribute(conv_fwd_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
@@ -1277,6 +1312,7 @@ int vqb_conv2d_fwd_tc(const void* x, const void* wp, const float* bias, const vo
         VQB_CHECK_LAUNCH("conv2d_fwd_tc_halo");
         return VQB_OK;
     }
+    if (sub) { vqb_set_error("conv2d_fwd_sub(tcgen05): needs the 3x3 halo kernels (output of at least 16 x 8 pixels)"); return VQB_ERR_UNSUPPORTED; }
     pick_tile(BM, H, W, p.tw, p.th, p.nb);
     p.tiles_w = (W + p.tw - 1) / p.tw; p.tiles_h = (H + p.th - 1) / p.th; p.tiles_n = (N + p.nb - 1) / p.nb;
     const int ptiles = p.tiles_w * p.tiles_h * p.tiles_n;
@@ -1284,7 +1320,7 @@ int vqb_conv2d_fwd_tc(const void* x, const void* wp, const float* bias, const vo
     p.num_tiles = ((ptiles + p.MT - 1) / p.MT) * p.co_tiles;
     const int stage_bytes = p.MT * BM * BK * 2 + p.BN * BK * 2;
     p.stages = (SMEM_LIMIT - 2048) / stage_bytes; if (p.stages > 8) p.stages = 8;
-    rc = make_act_map(&tmA, x, N, H, W, Cx, p.tw, p.th, p.nb); if (rc) return rc;
+    rc = make_act_map(&tmA, x, N, Hx, Wx, Cx, p.tw, p.th, p.nb); if (rc) return rc;
     size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256;
     VQB_CUDA(cudaFuncSetAttribute(conv_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
@@ -1293,22 +1329,55 @@ int vqb_conv2d_fwd_tc(const void* x, const void* wp, const float* bias, const vo
     return VQB_OK;
 }
 
-int vqb_conv2d_wgrad_tc(const void* x, const void* dy, float* dwp, int N, int H, int W, int Ci, int Co, int KH, int KW,
-                        int pad, cudaStream_t stream) {
+int vqb_conv2d_fwd_tc(const void* x, const void* wp, const float* bias, const void* residual, void* y, int y_dtype, int N,
+                      int H, int W, int Ci, int Co, int KH, int KW, int pad, int act, float alpha, float gain,
+                      cudaStream_t stream, int Cx, double* gn_sums, int gn_groups) {
+    return conv_fwd_tc_impl(x, wp, bias, residual, y, y_dtype, N, H, W, Ci, Co, KH, KW, pad, act, alpha, gain, stream, Cx, gn_sums, gn_groups,
+                            nullptr);
+}
+
+static int sub_check(const char* who, int N, int Hx, int Wx, int H, int W, int Ci, int Co, int T, int off) {
+    if (!(N > 0 && Hx > 0 && Wx > 0 && H >= 16 && W >= 8 && Ci % 64 == 0 && Co % 64 == 0 && (T == 2 || T == 3) && off >= -1 && off + T <= 2)) {
+        vqb_set_error("%s: unsupported sub-convolution (N=%d in %dx%d out %dx%d Ci=%d Co=%d T=%d off=%d): needs an output of >= 16 x 8 pixels, "
+                      "64-multiple channels, T in {2,3}, the taps inside the 3x3 frame", who, N, Hx, Wx, H, W, Ci, Co, T, off);
+        return VQB_ERR_UNSUPPORTED;
+    }
+    return VQB_OK;
+}
+
+extern "C" int vqb_conv2d_sub_supported(int N, int Hx, int Wx, int H, int W, int Ci, int Co, int T, int off) {
+    const int mode = g_halo_override >= 0 ? g_halo_override : halo_mode();
+    return mode == 1 && N > 0 && Hx > 0 && Wx > 0 && H >= 16 && W >= 8 && Ci % 64 == 0 && Co % 64 == 0 && (T == 2 || T == 3) && off >= -1 &&
+           off + T <= 2;
+}
+
+extern "C" int vqb_conv2d_fwd_sub(const void* x, const void* wp, const float* bias, const void* residual, void* y, int y_dtype, int N, int Hx,
+                                  int Wx, int H, int W, int Ci, int Co, int T, int off, int act, float act_alpha, float gain, void* stream) {
+    VQB_CHECK_ARG(x && wp && y, "conv2d_fwd_sub: null pointer");
+    int rc = sub_check("conv2d_fwd_sub", N, Hx, Wx, H, W, Ci, Co, T, off); if (rc) return rc;
+    SubConv sc{Hx, Wx, T, off};
+    return conv_fwd_tc_impl(x, wp, bias, residual, y, y_dtype, N, H, W, Ci, Co, 3, 3, 1, act, act_alpha, gain, as_stream(stream), Ci, nullptr, 0, &sc);
+}
+
+static int conv_wgrad_tc_impl(const void* x, const void* dy, float* dwp, int N, int H, int W, int Ci, int Co, int KH, int KW,
+                              int pad, cudaStream_t stream, const SubConv* sub) {
     VQB_CHECK_ARG(N > 0 && H > 0 && W > 0 && KH > 0 && KW > 0 && pad >= 0, "conv2d_wgrad(tcgen05): bad geometry");
     VQB_CHECK_ARG(Ci % 64 == 0 && Co % 128 == 0, "conv2d_wgrad(tcgen05): need Ci %% 64 == 0 and Co %% 128 == 0 (got %d, %d)", Ci, Co);
     VQB_CHECK_ARG(H + 2 * pad - KH + 1 == H && W + 2 * pad - KW + 1 == W, "conv2d_wgrad(tcgen05): only 'same' convolutions");
     const int mode = g_halo_override >= 0 ? g_halo_override : halo_mode();
+    if (sub && !(mode != 0 && H >= 8 && W >= 8)) { vqb_set_error("conv2d_wgrad_sub(tcgen05): needs the halo kernel"); return VQB_ERR_UNSUPPORTED; }
     if (mode != 0 && KH == 3 && KW == 3 && pad == 1 && H >= 8 && W >= 8) {
         WgradHaloParams h;
         h.N = N; h.H = H; h.W = W; h.Ci = Ci; h.Co = Co;
+        h.ktw = 3; h.kh0 = 0; h.kw0 = 0;
+        if (sub) { h.ktw = sub->T; h.kh0 = h.kw0 = sub->off + 1; }
         h.tiles_w = (W + 7) / 8; h.tiles_h = (H + 7) / 8;
         h.CN = (Ci % 128 == 0) ? 128 : 64;
         h.co_tiles = Co / BM; h.ci_tiles = Ci / h.CN;
         const int stage_bytes = (BM / 64) * 64 * 128 + (h.CN / 64) * 8 * 10 * 128;
         h.stages = (SMEM_LIMIT - 2048) / stage_bytes; if (h.stages > 8) h.stages = 8;
         h.ptiles_total = h.tiles_w * h.tiles_h * N;
-        const int out_tiles = 3 * h.ci_tiles * h.co_tiles;
+        const int out_tiles = h.ktw * h.ci_tiles * h.co_tiles;           // one CTA per (kernel row, ci tile, co tile)
         // ONE wave: TMEM (3 x 128 accumulator columns) admits one CTA per SM, so out_tiles * splits must not exceed the SM count
         // -- ceil(2 * SMs / out_tiles) gave 297 CTAs for the 128-channel layers: two waves plus ONE straggler CTA (ncu: SMs
         // active 57 % of the launch) and twice the atomic-combine traffic.
@@ -1322,7 +1391,7 @@ int vqb_conv2d_wgrad_tc(const void* x, const void* dy, float* dwp, int N, int H,
         h.dwp = dwp;
         CUtensorMap tmDy, tmX;
         int rc = make_act_map(&tmDy, dy, N, H, W, Co, 8, 8, 1); if (rc) return rc;
-        rc = make_act_map(&tmX, x, N, H, W, Ci, 10, 8, 1); if (rc) return rc;
+        rc = make_act_map(&tmX, x, N, sub ? sub->Hx : H, sub ? sub->Wx : W, Ci, 10, 8, 1); if (rc) return rc;
         size_t smem = (size_t)h.stages * stage_bytes + 1024 + 256;
         VQB_CUDA(cudaFuncSetAttribute(conv_wgrad_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid(out_tiles, splits);
@@ -1356,4 +1425,19 @@ int vqb_conv2d_wgrad_tc(const void* x, const void* dy, float* dwp, int N, int H,
     conv_wgrad_tc_kernel<<<grid, NTHREADS, smem, stream>>>(tmDy, tmX, p);
     VQB_CHECK_LAUNCH("conv2d_wgrad_tc");
     return VQB_OK;
+}
+
+int vqb_conv2d_wgrad_tc(const void* x, const void* dy, float* dwp, int N, int H, int W, int Ci, int Co, int KH, int KW,
+                        int pad, cudaStream_t stream) {
+    return conv_wgrad_tc_impl(x, dy, dwp, N, H, W, Ci, Co, KH, KW, pad, stream, nullptr);
+}
+
+// weight gradient of vqb_conv2d_fwd_sub: dwp[(a*T+b)*Ci + ci][co] (fp32, caller zero-fills) += sum_pix x[n, h+off+a, w+off+b, ci] dy[n,h,w,co]
+extern "C" int vqb_conv2d_wgrad_sub(const void* x, const void* dy, float* dwp, int N, int Hx, int Wx, int H, int W, int Ci, int Co, int T, int off,
+                                    void* stream) {
+    VQB_CHECK_ARG(x && dy && dwp, "conv2d_wgrad_sub: null pointer");
+    int rc = sub_check("conv2d_wgrad_sub", N, Hx, Wx, H, W, Ci, Co, T, off); if (rc) return rc;
+    VQB_CHECK_ARG(Co % 128 == 0, "conv2d_wgrad_sub: Co must be a multiple of 128");
+    SubConv sc{Hx, Wx, T, off};
+    return conv_wgrad_tc_impl(x, dy, dwp, N, H, W, Ci, Co, 3, 3, 1, as_stream(stream), &sc);
 }

@@ -368,8 +368,11 @@ extern "C" int vqb_im2col3x3_narrow(const void* x, int x_dtype, void* P, int p_d
     return VQB_OK;
 }
 
-__global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int Co, int Ci, int KH, int KW,
-                                    float scale) {
+// ACC: dw += (the destination is the parameter's gradient view inside the optimizer's flat buffer -- no separate autograd
+// accumulation pass); REZERO: the packed partial-sum buffer is cleared behind the read, so that the persistent per-weight buffer is
+// ready for the next weight-gradient launch without a fill kernel.
+template <bool ACC, bool REZERO>
+__global__ void unpack_wgrad_kernel(float* __restrict__ dwp, float* __restrict__ dw, int Co, int Ci, int KH, int KW, float scale) {
     // tile-transpose between [(tap,ci)][co] and [co][ci][tap]: handle per tap a [Ci][Co] -> [Co][Ci] transpose
     __shared__ float tile[32][33];
     int tap = blockIdx.z;
@@ -377,20 +380,41 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, float* __rest
     int ci0 = blockIdx.y * 32, co0 = blockIdx.x * 32;
     for (int j = threadIdx.y; j < 32; j += blockDim.y) {
         int ci = ci0 + j, co = co0 + threadIdx.x;
-        if (ci < Ci && co < Co) tile[j][threadIdx.x] = dwp[((int64_t)tap * Ci + ci) * Co + co];
+        if (ci < Ci && co < Co) {
+            const int64_t o = ((int64_t)tap * Ci + ci) * Co + co;
+            tile[j][threadIdx.x] = dwp[o];
+            if constexpr (REZERO) dwp[o] = 0.f;
+        }
     }
     __syncthreads();
     for (int j = threadIdx.y; j < 32; j += blockDim.y) {
         int co = co0 + j, ci = ci0 + threadIdx.x;
-        if (ci < Ci && co < Co) dw[((int64_t)co * Ci + ci) * T + tap] = tile[threadIdx.x][j] * scale;
+        if (ci < Ci && co < Co) {
+            const int64_t o = ((int64_t)co * Ci + ci) * T + tap;
+            const float v = tile[threadIdx.x][j] * scale;
+            if constexpr (ACC) dw[o] += v; else dw[o] = v;
+        }
     }
 }
 
 extern "C" int vqb_unpack_conv_wgrad(const float* dwp, float* dw, int Co, int Ci, int KH, int KW, float scale, void* stream) {
     VQB_CHECK_ARG(dwp && dw && Co > 0 && Ci > 0 && KH > 0 && KW > 0, "unpack_conv_wgrad: bad arguments");
     dim3 grid((Co + 31) / 32, (Ci + 31) / 32, KH * KW), block(32, 8);
-    unpack_wgrad_kernel<<<grid, block, 0, as_stream(stream)>>>(dwp, dw, Co, Ci, KH, KW, scale);
+    unpack_wgrad_kernel<false, false><<<grid, block, 0, as_stream(stream)>>>(const_cast<float*>(dwp), dw, Co, Ci, KH, KW, scale);
     VQB_CHECK_LAUNCH("unpack_conv_wgrad");
+    return VQB_OK;
+}
+
+extern "C" int vqb_unpack_conv_wgrad_acc(float* dwp, float* dw, int Co, int Ci, int KH, int KW, float scale, int accumulate, int rezero,
+                                         void* stream) {
+    VQB_CHECK_ARG(dwp && dw && Co > 0 && Ci > 0 && KH > 0 && KW > 0, "unpack_conv_wgrad_acc: bad arguments");
+    dim3 grid((Co + 31) / 32, (Ci + 31) / 32, KH * KW), block(32, 8);
+    cudaStream_t st = as_stream(stream);
+    if (accumulate && rezero) unpack_wgrad_kernel<true, true><<<grid, block, 0, st>>>(dwp, dw, Co, Ci, KH, KW, scale);
+    else if (accumulate) unpack_wgrad_kernel<true, false><<<grid, block, 0, st>>>(dwp, dw, Co, Ci, KH, KW, scale);
+    else if (rezero) unpack_wgrad_kernel<false, true><<<grid, block, 0, st>>>(dwp, dw, Co, Ci, KH, KW, scale);
+    else unpack_wgrad_kernel<false, false><<<grid, block, 0, st>>>(dwp, dw, Co, Ci, KH, KW, scale);
+    VQB_CHECK_LAUNCH("unpack_conv_wgrad_acc");
     return VQB_OK;
 }
 

@@ -170,6 +170,114 @@ int launch_fir4_patch(const void* x, void* y, int N, int H, int W, int C, int OH
     return 0;
 }
 
+
+// Sliding-window form of the down = 1 filter: one thread owns V channels x CW = 4 output columns and walks DOWN a strip of RH
+// output rows.  Per input row it loads CW + 3 = 7 vectors (1.75 16-byte loads per output instead of the patch kernel's 6.25:
+// ncu had the patch kernel LSU-bound at ~22 % of the HBM roof), forms the 4 horizontal sums and feeds them into the four
+// output rows in flight (a ring of accumulators with static indices: the row loop is unrolled by 4).
+// Layout flags: IN_S2D / OUT_S2D address the tensor as its 2x2 space-to-depth form [N][ceil(H/2)][ceil(W/2)][(dy, dx, c)]
+// (physical dims given by the *_h2 / *_w2 arguments) -- the discriminator's stride-2 3x3 convolution then runs as a 2x2-tap
+// stride-1 convolution over 4C channels of the filtered tensor (vqb_conv2d_fwd_sub), with no decimation pass.  OUT_S2D also
+// zero-fills the padding row / column of the physical tensor (logical index OH / OW when they are odd).
+template <typename T, bool IN_S2D, bool OUT_S2D>
+__global__ void __launch_bounds__(128) fir4_strip_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int OH, int OW,
+                                                         int pad, int RH, int in_h2, int in_w2, int out_h2, int out_w2) {
+    constexpr int V = Vec<T>::N, CW = 4, NC = CW + 3;
+    const int Cv = C / V;
+    const int OHp = OUT_S2D ? 2 * out_h2 : OH, OWp = OUT_S2D ? 2 * out_w2 : OW;     // rows / columns that must be WRITTEN
+    const int nstrips = (OHp + RH - 1) / RH, ncb = (OWp + CW - 1) / CW;
+    const int64_t total = (int64_t)N * nstrips * ncb * Cv;
+    auto in_off = [&](int n, int ih, int iw) -> int64_t {
+        if constexpr (IN_S2D) return ((((int64_t)n * in_h2 + (ih >> 1)) * in_w2 + (iw >> 1)) * 4 + ((ih & 1) * 2 + (iw & 1))) * C;
+        else return (((int64_t)n * H + ih) * W + iw) * C;
+    };
+    auto out_off = [&](int n, int oh, int ow) -> int64_t {
+        if constexpr (OUT_S2D) return ((((int64_t)n * out_h2 + (oh >> 1)) * out_w2 + (ow >> 1)) * 4 + ((oh & 1) * 2 + (ow & 1))) * C;
+        else return (((int64_t)n * OH + oh) * OW + ow) * C;
+    };
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int cv = (int)(i % Cv); int64_t r_ = i / Cv;
+        const int cb = (int)(r_ % ncb); r_ /= ncb;
+        const int strip = (int)(r_ % nstrips); const int n = (int)(r_ / nstrips);
+        const int oh0 = strip * RH, ow0 = cb * CW;
+        int rows = OHp - oh0; if (rows > RH) rows = RH;
+        float acc[4][CW][V];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int j = 0; j < CW; ++j)
+#pragma unroll
+                for (int u = 0; u < V; ++u) acc[a][j][u] = 0.f;
+        const int nin = rows + 3;                                  // input rows oh0 - pad .. oh0 - pad + rows + 2
+        for (int r4 = 0; r4 < nin; r4 += 4) {
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+                const int r = r4 + rr;
+                if (r < nin) {
+                    const int ih = oh0 - pad + r;
+                    if (ih >= 0 && ih < H) {
+                        float v[NC][V];
+#pragma unroll
+                        for (int c = 0; c < NC; ++c) {
+                            const int iw = ow0 - pad + c;
+                            if (iw >= 0 && iw < W) ldvec<T>(x + in_off(n, ih, iw) + cv * V, v[c]);
+                            else {
+#pragma unroll
+                                for (int u = 0; u < V; ++u) v[c][u] = 0.f;
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < CW; ++j)
+#pragma unroll
+                            for (int u = 0; u < V; ++u) {
+                                const float hs = fmaf(0.375f, v[j + 1][u] + v[j + 2][u], 0.125f * (v[j][u] + v[j + 3][u]));
+                                // vertical tap a of this input row belongs to output row r - a (ring slot (rr - a) & 3)
+                                acc[(rr + 4 - 0) & 3][j][u] = fmaf(0.125f, hs, acc[(rr + 4 - 0) & 3][j][u]);
+                                acc[(rr + 4 - 1) & 3][j][u] = fmaf(0.375f, hs, acc[(rr + 4 - 1) & 3][j][u]);
+                                acc[(rr + 4 - 2) & 3][j][u] = fmaf(0.375f, hs, acc[(rr + 4 - 2) & 3][j][u]);
+                                acc[(rr + 4 - 3) & 3][j][u] = fmaf(0.125f, hs, acc[(rr + 4 - 3) & 3][j][u]);
+                            }
+                    }
+                    {                                               // output row r - 3 has received its last tap (rows < 0: only the reset)
+                        const int oh = oh0 + r - 3;
+#pragma unroll
+                        for (int j = 0; j < CW; ++j) {
+                            const int ow = ow0 + j;
+                            if (r >= 3 && ow < OWp) {
+                                if (OUT_S2D && (oh >= OH || ow >= OW)) {
+#pragma unroll
+                                    for (int u = 0; u < V; ++u) acc[(rr + 1) & 3][j][u] = 0.f;
+                                }
+                                stvec<T>(y + out_off(n, oh, ow) + cv * V, acc[(rr + 1) & 3][j]);
+                            }
+#pragma unroll
+                            for (int u = 0; u < V; ++u) acc[(rr + 1) & 3][j][u] = 0.f;
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <typename T>
+int launch_fir4_strip(const void* x, void* y, int N, int H, int W, int C, int OH, int OW, int pad, int in_s2d, int out_s2d, cudaStream_t st) {
+    const int in_h2 = (H + 1) / 2, in_w2 = (W + 1) / 2, out_h2 = (OH + 1) / 2, out_w2 = (OW + 1) / 2;
+    const int OHp = out_s2d ? 2 * out_h2 : OH, OWp = out_s2d ? 2 * out_w2 : OW;
+    // strip height: enough threads to fill the machine (>= ~8 warps per SM scheduler), but long strips amortise the 3-row prologue
+    const int64_t per_row_strip = (int64_t)N * ((OWp + 3) / 4) * (C / Vec<T>::N);
+    int RH = 32;
+    while (RH > 8 && per_row_strip * ((OHp + RH - 1) / RH) < (int64_t)148 * 2048) RH >>= 1;
+    const int64_t total = per_row_strip * ((OHp + RH - 1) / RH);
+    int64_t blocks = (total + 127) / 128; if (blocks > 148 * 64) blocks = 148 * 64; if (blocks < 1) blocks = 1;
+    const unsigned grid = (unsigned)blocks;
+    if (in_s2d && out_s2d) return -1;
+    if (in_s2d) fir4_strip_kernel<T, true, false><<<grid, 128, 0, st>>>((const T*)x, (T*)y, N, H, W, C, OH, OW, pad, RH, in_h2, in_w2, out_h2, out_w2);
+    else if (out_s2d) fir4_strip_kernel<T, false, true><<<grid, 128, 0, st>>>((const T*)x, (T*)y, N, H, W, C, OH, OW, pad, RH, in_h2, in_w2, out_h2, out_w2);
+    else fir4_strip_kernel<T, false, false><<<grid, 128, 0, st>>>((const T*)x, (T*)y, N, H, W, C, OH, OW, pad, RH, in_h2, in_w2, out_h2, out_w2);
+    return 0;
+}
+
 // y[n,oh,ow,:] = x[n, 2*oh+off, 2*ow+off, :]
 template <typename T>
 __global__ void decimate2_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int OH, int OW, int off) {
@@ -208,6 +316,13 @@ inline int ew_grid(int64_t n) { int64_t b = (n + 255) / 256; if (b > 148 * 32) b
 
 // vectorised entry points used by vqb_fir4_fwd / vqb_fir4_bwd when C is a multiple of the vector width
 int vqb_fir4_fwd_vec(const void* x, void* y, int dtype, int N, int H, int W, int C, int OH, int OW, int pad, int down, cudaStream_t st) {
+    static const int use_strip = getenv("VQB_FIR_STRIP") ? atoi(getenv("VQB_FIR_STRIP")) : 1;
+    if (use_strip && down == 1) {
+        if (dtype == VQB_BF16) launch_fir4_strip<bf16>(x, y, N, H, W, C, OH, OW, pad, 0, 0, st);
+        else launch_fir4_strip<float>(x, y, N, H, W, C, OH, OW, pad, 0, 0, st);
+        VQB_CHECK_LAUNCH("fir4_strip");
+        return VQB_OK;
+    }
     static const int use_patch = getenv("VQB_FIR_PATCH") ? atoi(getenv("VQB_FIR_PATCH")) : 1;
     if (use_patch && (down == 1 || down == 2)) {
         if (dtype == VQB_BF16) launch_fir4_patch<bf16>(x, y, N, H, W, C, OH, OW, pad, down, st);
@@ -221,6 +336,14 @@ int vqb_fir4_fwd_vec(const void* x, void* y, int dtype, int N, int H, int W, int
     return VQB_OK;
 }
 int vqb_fir4_bwd_vec(const void* dy, void* dx, int dtype, int N, int H, int W, int C, int OH, int OW, int pad, int down, cudaStream_t st) {
+    static const int use_strip = getenv("VQB_FIR_STRIP") ? atoi(getenv("VQB_FIR_STRIP")) : 1;
+    if (use_strip && down == 1 && pad <= 3) {
+        // adjoint of the symmetric down = 1 filter = the same filter with pad' = 3 - pad, applied to dy [OH, OW] -> dx [H, W]
+        if (dtype == VQB_BF16) launch_fir4_strip<bf16>(dy, dx, N, OH, OW, C, H, W, 3 - pad, 0, 0, st);
+        else launch_fir4_strip<float>(dy, dx, N, OH, OW, C, H, W, 3 - pad, 0, 0, st);
+        VQB_CHECK_LAUNCH("fir4_strip(adjoint)");
+        return VQB_OK;
+    }
     static const int use_patch = getenv("VQB_FIR_PATCH") ? atoi(getenv("VQB_FIR_PATCH")) : 1;
     if (use_patch && down == 1 && pad <= 3) {
         // adjoint of the symmetric down = 1 filter = the same filter with pad' = 3 - pad, applied to dy [OH, OW] -> dx [H, W]
@@ -251,5 +374,21 @@ extern "C" int vqb_zero_upsample2(const void* y, void* x, int dtype, int N, int 
     if (dtype == VQB_BF16) zero_upsample2_kernel<bf16><<<ew_grid((int64_t)N * H * W * C / 8), 256, 0, as_stream(stream)>>>((const bf16*)y, (bf16*)x, N, H, W, C, OH, OW, off);
     else zero_upsample2_kernel<float><<<ew_grid((int64_t)N * H * W * C / 4), 256, 0, as_stream(stream)>>>((const float*)y, (float*)x, N, H, W, C, OH, OW, off);
     VQB_CHECK_LAUNCH("zero_upsample2");
+    return VQB_OK;
+}
+
+// FIR [1,3,3,1]^2/64 (down = 1) between a plain NHWC tensor and a 2x2 space-to-depth tensor (see fir4_strip_kernel):
+//   out_s2d: y = s2d(FIR(x, pad)),   x [N,H,W,C] -> y physical [N, ceil(OH/2), ceil(OW/2), 4C], OH = H + 2 pad - 3 (padding slots zeroed)
+//   in_s2d : y = FIR(unS2D(x), pad), x physical [N, ceil(H/2), ceil(W/2), 4C] holding a logical [N,H,W,C] -> y [N,OH,OW,C] (OH, OW given:
+//            the adjoint of the first form is this one with pad' = 3 - pad and OH = the original input height)
+extern "C" int vqb_fir4_s2d(const void* x, void* y, int dtype, int N, int H, int W, int C, int OH, int OW, int pad, int in_s2d, int out_s2d,
+                            void* stream) {
+    VQB_CHECK_ARG(x && y && N > 0 && H > 0 && W > 0 && C > 0 && OH > 0 && OW > 0 && pad >= 0 && pad <= 3, "fir4_s2d: bad arguments");
+    VQB_CHECK_ARG(!(in_s2d && out_s2d), "fir4_s2d: only one side may be in space-to-depth layout");
+    VQB_CHECK_ARG(dtype == VQB_BF16 || dtype == VQB_F32, "fir4_s2d: dtype");
+    VQB_CHECK_ARG(C % ((dtype == VQB_BF16) ? 8 : 4) == 0, "fir4_s2d: C must be a multiple of the 16-byte vector width");
+    if (dtype == VQB_BF16) launch_fir4_strip<bf16>(x, y, N, H, W, C, OH, OW, pad, in_s2d, out_s2d, as_stream(stream));
+    else launch_fir4_strip<float>(x, y, N, H, W, C, OH, OW, pad, in_s2d, out_s2d, as_stream(stream));
+    VQB_CHECK_LAUNCH("fir4_s2d");
     return VQB_OK;
 }

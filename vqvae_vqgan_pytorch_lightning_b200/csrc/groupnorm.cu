@@ -155,21 +155,91 @@ __global__ void gn_finalize_kernel(const double* __restrict__ sums, float* __res
     stats[2 * i + 1] = (float)(1.0 / sqrt(var + eps));
 }
 
+
+// mean / rstd of group g of image b: from the finalized stats, or (sums != NULL) evaluated here from the raw double sums with
+// gn_finalize_kernel's arithmetic -- bit-identical, so the folded two-launch forms equal the four-launch ones
+__device__ __forceinline__ void gn_group_stats(const float* __restrict__ stats, const double* __restrict__ sums, int64_t bg, double n,
+                                               double eps, float& mean, float& rstd) {
+    if (sums) {
+        const double s = sums[2 * bg], q = sums[2 * bg + 1];
+        const double m = s / n;
+        double var = (q - s * m) / (n - 1.0);
+        if (var < 0.0) var = 0.0;
+        mean = (float)m;
+        rstd = (float)(1.0 / sqrt(var + eps));
+    } else {
+        mean = stats[2 * bg];
+        rstd = stats[2 * bg + 1];
+    }
+}
+// per-channel mean / rstd of a thread's VEC consecutive channels (at most VEC / 4 + 1 distinct groups: evaluated once per group)
+template <int VEC>
+__device__ __forceinline__ void gn_thread_stats(const float* __restrict__ stats, const double* __restrict__ sums, float* __restrict__ stats_out,
+                                                bool writer, int b, int c0, int cg, int G, double n, double eps, float (&mean)[VEC],
+                                                float (&rstd)[VEC]) {
+    int gprev = -1;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+        const int g = (c0 + j) / cg;
+        if (g != gprev) {
+            gn_group_stats(stats, sums, (int64_t)b * G + g, n, eps, mean[j], rstd[j]);
+            if (stats_out && writer && (c0 + j) % cg == 0) {
+                stats_out[((int64_t)b * G + g) * 2] = mean[j];
+                stats_out[((int64_t)b * G + g) * 2 + 1] = rstd[j];
+            }
+            gprev = g;
+        } else { mean[j] = mean[j - (j > 0)]; rstd[j] = rstd[j - (j > 0)]; }
+    }
+}
+// coef[b][g] = (sum_c gamma ds / n, sum_c gamma ds xhat / (n - 1)): from the finalized buffer or (part != NULL) from the raw
+// per-channel double sums with gn_bwd_finalize_kernel's arithmetic
+__device__ __forceinline__ void gn_group_coef(const float* __restrict__ coef, const double* __restrict__ part, const float* __restrict__ gamma,
+                                              int b, int g, int cg, int C, int G, double n, float& k1, float& k2) {
+    if (part) {
+        double s1 = 0.0, s2 = 0.0;
+        for (int c = g * cg; c < (g + 1) * cg; ++c) {
+            const double ga = (double)gamma[c];
+            s1 += ga * part[((int64_t)b * C + c) * 2];
+            s2 += ga * part[((int64_t)b * C + c) * 2 + 1];
+        }
+        k1 = (float)(s1 / n);
+        k2 = (float)(s2 / (n - 1.0));
+    } else {
+        k1 = coef[((int64_t)b * G + g) * 2];
+        k2 = coef[((int64_t)b * G + g) * 2 + 1];
+    }
+}
+// dgamma[c] / dbeta[c] = sums of part over the batch (gn_bwd_finalize_kernel's second half), by ONE block of the apply kernel
+__device__ __forceinline__ void gn_param_grads(const double* __restrict__ part, float* __restrict__ dgamma, float* __restrict__ dbeta, int acc,
+                                               int N, int C, int tid, int nthr) {
+    for (int c = tid; c < C; c += nthr) {
+        double db = 0.0, dg = 0.0;
+        for (int b = 0; b < N; ++b) {
+            db += part[((int64_t)b * C + c) * 2];
+            dg += part[((int64_t)b * C + c) * 2 + 1];
+        }
+        if (acc) { dbeta[c] += (float)db; dgamma[c] += (float)dg; }
+        else { dbeta[c] = (float)db; dgamma[c] = (float)dg; }
+    }
+}
+
 // ---- forward apply -----------------------------------------------------------------------------------
 template <typename TI, typename TO, int VEC>
 __global__ void gn_apply_kernel(const TI* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
-                                const float* __restrict__ beta, TO* __restrict__ y, int HW, int C, int G, int ppb, int act) {
+                                const float* __restrict__ beta, TO* __restrict__ y, int HW, int C, int G, int ppb, int act,
+                                const double* __restrict__ sums, float* __restrict__ stats_out, double nel, double eps) {
     const int b = blockIdx.y;
     const int c0 = threadIdx.x * VEC;
     const int cg = C / G;
     float sc[VEC], sh_[VEC];          // y = x * sc + sh_  with sc = rstd*gamma, sh_ = beta - mean*rstd*gamma
+    {
+        float mean[VEC], rstd[VEC];
+        gn_thread_stats<VEC>(stats, sums, stats_out, blockIdx.x == 0 && threadIdx.y == 0, b, c0, cg, G, nel, eps, mean, rstd);
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-        int g = (c0 + j) / cg;
-        float mean = stats[((int64_t)b * G + g) * 2];
-        float rstd = stats[((int64_t)b * G + g) * 2 + 1];
-        sc[j] = rstd * gamma[c0 + j];
-        sh_[j] = beta[c0 + j] - mean * sc[j];
+        for (int j = 0; j < VEC; ++j) {
+            sc[j] = rstd[j] * gamma[c0 + j];
+            sh_[j] = beta[c0 + j] - mean[j] * sc[j];
+        }
     }
     constexpr bool APPROX = (sizeof(TI) == 2 && sizeof(TO) == 2);      // bf16 in and out: single-MUFU SiLU on u = t/2
     const bool half_arg = APPROX && act == VQB_ACT_SILU;
@@ -433,7 +503,8 @@ __global__ void gn_stats_async_kernel(const bf16* __restrict__ x, double* __rest
 // forward apply, bf16 -> bf16, VEC = 8: x through the cp.async ring, y stored directly (stores are fire-and-forget)
 template <int D>
 __global__ void gn_apply_async_kernel(const bf16* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
-                                      const float* __restrict__ beta, bf16* __restrict__ y, int HW, int C, int G, int ppb, int act) {
+                                      const float* __restrict__ beta, bf16* __restrict__ y, int HW, int C, int G, int ppb, int act,
+                                      const double* __restrict__ sums, float* __restrict__ stats_out, double nel, double eps) {
     constexpr int VEC = 8;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint4* ring = reinterpret_cast<uint4*>(smem_raw);            // [D][nthreads]
@@ -444,14 +515,15 @@ __global__ void gn_apply_async_kernel(const bf16* __restrict__ x, const float* _
     const int tid = threadIdx.y * tx + threadIdx.x;
     const bool silu = (act == VQB_ACT_SILU);
     float sc[VEC], sh_[VEC];
+    {
+        float mean[VEC], rstd[VEC];
+        gn_thread_stats<VEC>(stats, sums, stats_out, blockIdx.x == 0 && threadIdx.y == 0, b, c0, cg, G, nel, eps, mean, rstd);
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-        int g = (c0 + j) / cg;
-        float mean = stats[((int64_t)b * G + g) * 2];
-        float rstd = stats[((int64_t)b * G + g) * 2 + 1];
-        sc[j] = rstd * gamma[c0 + j];
-        sh_[j] = beta[c0 + j] - mean * sc[j];
-        if (silu) { sc[j] *= 0.5f; sh_[j] *= 0.5f; }
+        for (int j = 0; j < VEC; ++j) {
+            sc[j] = rstd[j] * gamma[c0 + j];
+            sh_[j] = beta[c0 + j] - mean[j] * sc[j];
+            if (silu) { sc[j] *= 0.5f; sh_[j] *= 0.5f; }
+        }
     }
     const int p0 = blockIdx.x * ppb;
     int p1 = p0 + ppb; if (p1 > HW) p1 = HW;
@@ -487,7 +559,8 @@ template <int D, bool HAS_ADD>
 __global__ void gn_bwd_apply_async_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, const float* __restrict__ stats,
                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                           const float* __restrict__ coef, const bf16* __restrict__ add, bf16* __restrict__ dx,
-                                          int HW, int C, int G, int ppb, int act) {
+                                          int HW, int C, int G, int ppb, int act, const double* __restrict__ part,
+                                          float* __restrict__ dgamma, float* __restrict__ dbeta, int acc, int N, double nel) {
     constexpr int VEC = 8, NT = HAS_ADD ? 3 : 2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint4* ring = reinterpret_cast<uint4*>(smem_raw);            // [D][NT][nthreads]
@@ -498,19 +571,23 @@ __global__ void gn_bwd_apply_async_kernel(const bf16* __restrict__ x, const bf16
     const int tid = threadIdx.y * tx + threadIdx.x;
     const bool silu = (act == VQB_ACT_SILU);
     float sc[VEC], sf[VEC], ca[VEC], cb[VEC], cc[VEC];       // dx = ds*ca + x*cb + cc
+    if (part && dgamma && blockIdx.x == 0 && blockIdx.y == 0) gn_param_grads(part, dgamma, dbeta, acc, N, C, tid, nthr);
+    {
+        float k1 = 0.f, k2 = 0.f;
+        int gprev = -1;
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-        int g = (c0 + j) / cg;
-        const float mean = stats[((int64_t)b * G + g) * 2];
-        const float rstd = stats[((int64_t)b * G + g) * 2 + 1];
-        const float k1 = coef[((int64_t)b * G + g) * 2];
-        const float k2 = coef[((int64_t)b * G + g) * 2 + 1];
-        sc[j] = rstd * gamma[c0 + j];
-        sf[j] = beta[c0 + j] - mean * sc[j];
-        ca[j] = sc[j];
-        cb[j] = -rstd * rstd * k2;
-        cc[j] = -rstd * k1 - mean * cb[j];
-        if (silu) { sc[j] *= 0.5f; sf[j] *= 0.5f; ca[j] *= 0.5f; }
+        for (int j = 0; j < VEC; ++j) {
+            int g = (c0 + j) / cg;
+            const float mean = stats[((int64_t)b * G + g) * 2];
+            const float rstd = stats[((int64_t)b * G + g) * 2 + 1];
+            if (g != gprev) { gn_group_coef(coef, part, gamma, b, g, cg, C, G, nel, k1, k2); gprev = g; }
+            sc[j] = rstd * gamma[c0 + j];
+            sf[j] = beta[c0 + j] - mean * sc[j];
+            ca[j] = sc[j];
+            cb[j] = -rstd * rstd * k2;
+            cc[j] = -rstd * k1 - mean * cb[j];
+            if (silu) { sc[j] *= 0.5f; sf[j] *= 0.5f; ca[j] *= 0.5f; }
+        }
     }
     const int p0 = blockIdx.x * ppb;
     int p1 = p0 + ppb; if (p1 > HW) p1 = HW;
@@ -586,18 +663,22 @@ template <typename TI, typename TG, typename TO, int VEC>
 __global__ void gn_bwd_apply_kernel(const TI* __restrict__ x, const TG* __restrict__ dy, const float* __restrict__ stats,
                                     const float* __restrict__ gamma, const float* __restrict__ beta,
                                     const float* __restrict__ coef, const TO* __restrict__ add, TO* __restrict__ dx, int HW,
-                                    int C, int G, int ppb, int act) {
+                                    int C, int G, int ppb, int act, const double* __restrict__ part, float* __restrict__ dgamma,
+                                    float* __restrict__ dbeta, int acc, int N, double nel) {
     const int b = blockIdx.y;
     const int c0 = threadIdx.x * VEC;
     const int cg = C / G;
     float sc[VEC], sf[VEC], ca[VEC], cb[VEC], cc[VEC];       // dx = ds*ca + x*cb + cc
+    if (part && dgamma && blockIdx.x == 0 && blockIdx.y == 0)
+        gn_param_grads(part, dgamma, dbeta, acc, N, C, threadIdx.y * blockDim.x + threadIdx.x, blockDim.x * blockDim.y);
+    float k1 = 0.f, k2 = 0.f;
+    int gprev = -1;
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
         int g = (c0 + j) / cg;
         const float mean = stats[((int64_t)b * G + g) * 2];
         const float rstd = stats[((int64_t)b * G + g) * 2 + 1];
-        const float k1 = coef[((int64_t)b * G + g) * 2];
-        const float k2 = coef[((int64_t)b * G + g) * 2 + 1];
+        if (g != gprev) { gn_group_coef(coef, part, gamma, b, g, cg, C, G, nel, k1, k2); gprev = g; }
         sc[j] = rstd * gamma[c0 + j];
         sf[j] = beta[c0 + j] - mean * sc[j];
         ca[j] = sc[j];                                    // rstd * gamma
@@ -682,25 +763,40 @@ extern "C" int vqb_gn_finalize(const double* sums, float* stats, int N, int HW, 
     return VQB_OK;
 }
 
-extern "C" int vqb_gn_apply(const void* x, int x_dtype, const float* stats, const float* gamma, const float* beta, void* y,
-                            int y_dtype, int N, int HW, int C, int G, int act, void* stream) {
+static int gn_apply_impl(const void* x, int x_dtype, const float* stats, const double* sums, float* stats_out, float eps,
+                         const float* gamma, const float* beta, void* y, int y_dtype, int N, int HW, int C, int G, int act, void* stream) {
     int rc = gn_check("gn_apply", N, HW, C, G); if (rc) return rc;
-    VQB_CHECK_ARG(x && stats && gamma && beta && y, "gn_apply: null pointer");
+    VQB_CHECK_ARG(x && (stats || sums) && gamma && beta && y, "gn_apply: null pointer");
     VQB_CHECK_ARG(act == VQB_ACT_NONE || act == VQB_ACT_SILU, "gn_apply: act must be NONE or SILU");
+    const double nel = (double)(C / G) * HW;
     static int use_async = getenv("VQB_GN_ASYNC") ? atoi(getenv("VQB_GN_ASYNC")) : 1;
     if (use_async && x_dtype == VQB_BF16 && y_dtype == VQB_BF16 && gn_vec(C, G) == 8) {
         const int ppt = 32;
         GnLaunch La = gn_launch(N, HW, C, G, ppt, 8);
         const size_t nthr = (size_t)La.block.x * La.block.y;
-        gn_apply_async_kernel<8><<<La.grid, La.block, (size_t)8 * nthr * 16, as_stream(stream)>>>((const bf16*)x, stats, gamma, beta, (bf16*)y, HW, C, G, La.ppb, act);
+        gn_apply_async_kernel<8><<<La.grid, La.block, (size_t)8 * nthr * 16, as_stream(stream)>>>((const bf16*)x, stats, gamma, beta, (bf16*)y, HW, C, G, La.ppb, act,
+                                                                                                 sums, stats_out, nel, (double)eps);
         VQB_CHECK_LAUNCH("gn_apply_async");
         return VQB_OK;
     }
     GnLaunch L = gn_launch(N, HW, C, G);
     GN_VEC_DISPATCH(L, VQB_DISPATCH_1(x_dtype, TI, VQB_DISPATCH_1(y_dtype, TO,
-        (gn_apply_kernel<TI, TO, VEC><<<L.grid, L.block, 0, as_stream(stream)>>>((const TI*)x, stats, gamma, beta, (TO*)y, HW, C, G, L.ppb, act));)))
+        (gn_apply_kernel<TI, TO, VEC><<<L.grid, L.block, 0, as_stream(stream)>>>((const TI*)x, stats, gamma, beta, (TO*)y, HW, C, G, L.ppb, act,
+                                                                                  sums, stats_out, nel, (double)eps));)))
     VQB_CHECK_LAUNCH("gn_apply");
     return VQB_OK;
+}
+
+extern "C" int vqb_gn_apply(const void* x, int x_dtype, const float* stats, const float* gamma, const float* beta, void* y,
+                            int y_dtype, int N, int HW, int C, int G, int act, void* stream) {
+    VQB_CHECK_ARG(stats, "gn_apply: null pointer");
+    return gn_apply_impl(x, x_dtype, stats, nullptr, nullptr, 0.f, gamma, beta, y, y_dtype, N, HW, C, G, act, stream);
+}
+
+extern "C" int vqb_gn_apply_sums(const void* x, int x_dtype, const double* sums, const float* gamma, const float* beta, void* y, int y_dtype,
+                                 float* stats_out, int N, int HW, int C, int G, float eps, int act, void* stream) {
+    VQB_CHECK_ARG(sums, "gn_apply_sums: null pointer");
+    return gn_apply_impl(x, x_dtype, nullptr, sums, stats_out, eps, gamma, beta, y, y_dtype, N, HW, C, G, act, stream);
 }
 
 extern "C" int vqb_gn_bwd_reduce(const void* x, int x_dtype, const void* dy, int dy_dtype, const float* stats,
@@ -745,11 +841,13 @@ extern "C" int vqb_gn_bwd_finalize(const double* part, const float* gamma, float
     return VQB_OK;
 }
 
-extern "C" int vqb_gn_bwd_apply(const void* x, int x_dtype, const void* dy, int dy_dtype, const float* stats,
-                                const float* gamma, const float* beta, const float* coef, const void* add, void* dx,
-                                int dx_dtype, int N, int HW, int C, int G, int act, void* stream) {
+static int gn_bwd_apply_impl(const void* x, int x_dtype, const void* dy, int dy_dtype, const float* stats, const float* gamma,
+                             const float* beta, const float* coef, const double* part, const void* add, void* dx, int dx_dtype,
+                             float* dgamma, float* dbeta, int acc, int N, int HW, int C, int G, int act, void* stream) {
     int rc = gn_check("gn_bwd_apply", N, HW, C, G); if (rc) return rc;
-    VQB_CHECK_ARG(x && dy && stats && gamma && beta && coef && dx, "gn_bwd_apply: null pointer");
+    VQB_CHECK_ARG(x && dy && stats && gamma && beta && (coef || part) && dx, "gn_bwd_apply: null pointer");
+    VQB_CHECK_ARG(!part || (dgamma && dbeta), "gn_bwd_apply_part: null parameter-gradient pointer");
+    const double nel = (double)(C / G) * HW;
     static int use_async = getenv("VQB_GN_ASYNC") ? atoi(getenv("VQB_GN_ASYNC")) : 1;
     if (use_async && x_dtype == VQB_BF16 && dy_dtype == VQB_BF16 && dx_dtype == VQB_BF16 && gn_vec(C, G) == 8 &&
         (act == VQB_ACT_NONE || act == VQB_ACT_SILU)) {
@@ -765,16 +863,32 @@ extern "C" int vqb_gn_bwd_apply(const void* x, int x_dtype, const void* dy, int 
         }
         if (add)
             gn_bwd_apply_async_kernel<DB, true><<<La.grid, La.block, (size_t)DB * 3 * nthr * 16, as_stream(stream)>>>(
-                (const bf16*)x, (const bf16*)dy, stats, gamma, beta, coef, (const bf16*)add, (bf16*)dx, HW, C, G, La.ppb, act);
+                (const bf16*)x, (const bf16*)dy, stats, gamma, beta, coef, (const bf16*)add, (bf16*)dx, HW, C, G, La.ppb, act, part, dgamma, dbeta, acc, N, nel);
         else
             gn_bwd_apply_async_kernel<DB, false><<<La.grid, La.block, (size_t)DB * 2 * nthr * 16, as_stream(stream)>>>(
-                (const bf16*)x, (const bf16*)dy, stats, gamma, beta, coef, nullptr, (bf16*)dx, HW, C, G, La.ppb, act);
+                (const bf16*)x, (const bf16*)dy, stats, gamma, beta, coef, nullptr, (bf16*)dx, HW, C, G, La.ppb, act, part, dgamma, dbeta, acc, N, nel);
         VQB_CHECK_LAUNCH("gn_bwd_apply_async");
         return VQB_OK;
     }
     GnLaunch L = gn_launch(N, HW, C, G);
     GN_VEC_DISPATCH(L, VQB_DISPATCH_1(x_dtype, TI, VQB_DISPATCH_1(dy_dtype, TG, VQB_DISPATCH_1(dx_dtype, TO,
-        (gn_bwd_apply_kernel<TI, TG, TO, VEC><<<L.grid, L.block, 0, as_stream(stream)>>>((const TI*)x, (const TG*)dy, stats, gamma, beta, coef, (const TO*)add, (TO*)dx, HW, C, G, L.ppb, act));))))
+        (gn_bwd_apply_kernel<TI, TG, TO, VEC><<<L.grid, L.block, 0, as_stream(stream)>>>((const TI*)x, (const TG*)dy, stats, gamma, beta, coef, (const TO*)add, (TO*)dx, HW, C, G, L.ppb, act,
+                                                                                          part, dgamma, dbeta, acc, N, nel));))))
     VQB_CHECK_LAUNCH("gn_bwd_apply");
     return VQB_OK;
+}
+
+extern "C" int vqb_gn_bwd_apply(const void* x, int x_dtype, const void* dy, int dy_dtype, const float* stats,
+                                const float* gamma, const float* beta, const float* coef, const void* add, void* dx,
+                                int dx_dtype, int N, int HW, int C, int G, int act, void* stream) {
+    VQB_CHECK_ARG(coef, "gn_bwd_apply: null pointer");
+    return gn_bwd_apply_impl(x, x_dtype, dy, dy_dtype, stats, gamma, beta, coef, nullptr, add, dx, dx_dtype, nullptr, nullptr, 0, N, HW, C, G, act, stream);
+}
+
+extern "C" int vqb_gn_bwd_apply_part(const void* x, int x_dtype, const void* dy, int dy_dtype, const float* stats, const float* gamma,
+                                     const float* beta, const double* part, const void* add, void* dx, int dx_dtype, float* dgamma,
+                                     float* dbeta, int accumulate_param_grads, int N, int HW, int C, int G, int act, void* stream) {
+    VQB_CHECK_ARG(part, "gn_bwd_apply_part: null pointer");
+    return gn_bwd_apply_impl(x, x_dtype, dy, dy_dtype, stats, gamma, beta, nullptr, part, add, dx, dx_dtype, dgamma, dbeta, accumulate_param_grads,
+                             N, HW, C, G, act, stream);
 }

@@ -120,7 +120,11 @@ struct FusedParams {
     float* counts;               // [K] or NULL
     float* dw;                   // [K][D] or NULL
     int* undecided;              // [2] or NULL: rows that took the exact re-rank, rows among them that needed the full scan
+    long long* trace;            // [ctas][8] or NULL: globaltimer stamps of the phase boundaries (tools/vq_phases.py)
 };
+
+__device__ __forceinline__ long long gtimer() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define VQ_TRACE(slot) do { if (p.trace && et == 0) p.trace[(size_t)blockIdx.x * 8 + (slot)] = gtimer(); } while (0)
 
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
     asm volatile(
@@ -291,6 +295,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmEh, const FusedParams p) {
     } else {
         const int ew = warp - 2;                                            // 0..7
         const int et = ew * 32 + lane;                                      // 0..255
+        VQ_TRACE(0);
         // ---- prologue: z rows -> bf16 hi / lo in the UMMA K-major SWIZZLE_128B layout (resident), |z|^2 ------------------
         // one warp per row and iteration: lane L owns k = 8L .. 8L+7 (one 16-byte chunk of the hi and of the lo tile)
         {
@@ -340,6 +345,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmEh, const FusedParams p) {
             epi_sync();
             if (et == 0) ptx::mbar_arrive_cluster(ptx::mapa_rank(ptx::smem_u32(zfull), 0));
         }
+        VQ_TRACE(1);                                                        // prologue done (z staged, |z|^2)
         const float sqrt_d = sqrtf((float)p.D);
         float emax = red_s[8];
 #pragma unroll
@@ -418,6 +424,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmEh, const FusedParams p) {
         // rows (or codebooks) that do not survive the fp16 rounding take the exact scan of the whole codebook
         rbest[slot] = b1; rcnt[slot] = (rcode[TM + row] != 0 || !(emax < INFINITY)) ? (int)0x80000000 : cnt;
         epi_sync();
+        VQ_TRACE(2);                                                        // scan of every code tile done
 
         // ---- decide (one thread per row): a single surviving candidate is the fp32 argmin; the other rows are appended to the
         //      CTA's re-rank work list (balanced over the eight warps afterwards)
@@ -443,6 +450,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmEh, const FusedParams p) {
 
         // ---- exact re-rank of the near-tied rows (one warp per row, round-robin over the work list): ONLY the surviving
         //      candidates are evaluated -------------------------------------------------------------------------------------
+        VQ_TRACE(3);                                                        // decided rows written, re-rank work list built
         float* xbuf = reinterpret_cast<float*>(smemZ);          // staging: every MMA has completed (last tfull), the operand tiles are free
         float sse_local = 0.f;
         const int n_und = *und_n;
@@ -525,6 +533,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmEh, const FusedParams p) {
             if (lane == 0) { rcode[rw] = code; p.idx_out[g] = (int64_t)code; }
         }
         epi_sync();                                                         // every row of the CTA has its code
+        VQ_TRACE(4);                                                        // exact re-rank done
 
         // ---- finish, 8 rows in flight per warp: q = z + (e - z), sum (e - z)^2, EMA cluster sums (z re-read from L2) ----------
         for (int rr = 0; rr < TM / 8; rr += 8) {
@@ -573,6 +582,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmEh, const FusedParams p) {
             atomicAdd(p.sse, t);
         }
         if (et == 0 && p.undecided && n_und) atomicAdd(p.undecided, n_und);
+        VQ_TRACE(5);                                                        // finish (gather / STE / statistics) done
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -608,6 +618,11 @@ extern "C" int vqb_vq_ema_update_prep(float* ema_count, float* ema_weight, float
     return VQB_OK;
 }
 
+static long long* g_vq_trace = nullptr;
+// tuning hook (tools/vq_phases.py): device buffer of [ctas][8] int64 that the next vqb_vq_fused launches fill with globaltimer
+// stamps of their phase boundaries; NULL (default) switches the stamps off
+extern "C" void vqb_vq_fused_set_trace(void* dev_buf) { g_vq_trace = (long long*)dev_buf; }
+
 extern "C" int vqb_vq_fused(const float* z, const float* codebook, const void* cb_half, const float* cb_sq, int order, float* q_out,
                             int64_t* idx_out, double* sse, float* counts, float* dw, int64_t N, int K, int D, int* undecided_rows_out,
                             void* stream) {
@@ -623,6 +638,7 @@ extern "C" int vqb_vq_fused(const float* z, const float* codebook, const void* c
     fp.N = N; fp.K = K; fp.D = D; fp.kchunks = D / TK; fp.ctiles = (K + TN - 1) / TN; fp.order = order;
     fp.z = z; fp.cb = codebook; fp.cb_sq = cb_sq; fp.q_out = q_out; fp.idx_out = idx_out; fp.sse = sse; fp.counts = counts; fp.dw = dw;
     fp.undecided = undecided_rows_out;
+    fp.trace = g_vq_trace;
     const size_t smem = fused_smem_bytes(D);
     if (smem > 227 * 1024) { vqb_set_error("vq_fused: D=%d does not fit the shared-memory budget (%zu B)", D, smem); return VQB_ERR_UNSUPPORTED; }
     static std::once_flag attr_once;

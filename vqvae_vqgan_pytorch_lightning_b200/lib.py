@@ -34,6 +34,7 @@ SIGNATURES = {
     'vqb_pack_conv_weights_batched': (_i, [_p, _i, _i64, _p]),
     'vqb_im2col3x3_narrow': (_i, [_p, _i, _p, _i, _i, _i, _i, _i, _i, _p]),
     'vqb_unpack_conv_wgrad': (_i, [_p, _p, _i, _i, _i, _i, _f, _p]),
+    'vqb_unpack_conv_wgrad_acc': (_i, [_p, _p, _i, _i, _i, _i, _f, _i, _i, _p]),
     'vqb_conv2d_fwd': (_i, [_i, _p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, _p]),
     'vqb_conv2d_fwd_gn': (_i, [_i, _p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, _p, _i, _p]),
     'vqb_conv2d_fwd_gn_supported': (_i, [_i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i]),
@@ -60,6 +61,16 @@ SIGNATURES = {
     'vqb_gn_bwd_reduce': (_i, [_p, _i, _p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     'vqb_gn_bwd_finalize': (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     'vqb_gn_bwd_apply': (_i, [_p, _i, _p, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    # x, xdt, sums, gamma, beta, y, ydt, stats_out, N, HW, C, G, eps, act, stream
+    'vqb_gn_apply_sums': (_i, [_p, _i, _p, _p, _p, _p, _i, _p, _i, _i, _i, _i, _f, _i, _p]),
+    # x, xdt, dy, dydt, stats, gamma, beta, part, add, dx, dxdt, dgamma, dbeta, acc, N, HW, C, G, act, stream
+    'vqb_gn_bwd_apply_part': (_i, [_p, _i, _p, _i, _p, _p, _p, _p, _p, _p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    # x, wp, bias, residual, y, ydt, N, Hx, Wx, H, W, Ci, Co, T, off, act, alpha, gain, stream
+    'vqb_conv2d_fwd_sub': (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, _p]),
+    'vqb_conv2d_wgrad_sub': (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    'vqb_conv2d_sub_supported': (_i, [_i, _i, _i, _i, _i, _i, _i, _i, _i]),
+    # x, y, dtype, N, H, W, C, OH, OW, pad, in_s2d, out_s2d, stream
+    'vqb_fir4_s2d': (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     'vqb_down2': (_i, [_p, _p, _i, _i, _i, _i, _i, _f, _p]),
     'vqb_up2': (_i, [_p, _p, _i, _i, _i, _i, _i, _f, _p]),
     'vqb_diff_sums': (_i, [_p, _i, _p, _i, _p, _i64, _p]),
@@ -72,6 +83,7 @@ SIGNATURES = {
     'vqb_vq_assign_tc': (_i, [_p, _p, _i, _p, _p, _p, _p, _p, _i64, _i, _i, _p, _sz, _p, _p]),
     'vqb_vq_prep_codebook': (_i, [_p, _p, _p, _i, _i, _p]),
     'vqb_vq_fused': (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _i64, _i, _i, _p, _p]),
+    'vqb_vq_fused_set_trace': (None, [_p]),
     'vqb_vq_ema_update_prep': (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _f, _f, _f, _p]),
     'vqb_vq_ema_update': (_i, [_p, _p, _p, _p, _p, _i, _i, _f, _f, _f, _p]),
     'vqb_vq_backward': (_i, [_p, _p, _p, _p, _p, _f, _f, _p, _p, _i64, _i, _i, _p]),

@@ -97,6 +97,15 @@ class Trainer:
             for o in self.optimizers:
                 if hasattr(o, 'buckets'):
                     self._install_bucket_hooks(o)
+        # Single process: the backward kernels accumulate parameter gradients straight into the flat gradient buffers
+        # (ops.grad_sink) -- no AccumulateGrad `add` launch per parameter.  With bucket hooks (post-accumulate hooks) installed the
+        # gradients keep going through autograd.
+        direct = not (self.world_size > 1 and self.overlap_grad_sync)
+        for o in self.optimizers:
+            if hasattr(o, 'flat_grad'):
+                for g in o.param_groups:
+                    for p in g['params']:
+                        p._vqb_direct_grad = direct
 
     def _install_bucket_hooks(self, opt) -> None:
         """One post-accumulate hook per parameter: when the last gradient of a bucket has landed in the flat buffer, its
@@ -199,6 +208,14 @@ class Trainer:
         return self._step_body(batch, batch_index)
 
     def _step_body(self, batch, batch_index: int):
+        from . import ops
+        dev = batch.device if torch.is_tensor(batch) and batch.is_cuda else None
+        if dev is None:
+            return self._step_body_inner(batch, batch_index)
+        with ops.zero_arena.step(dev):                  # one memset instead of ~150 small zero fills per step
+            return self._step_body_inner(batch, batch_index)
+
+    def _step_body_inner(self, batch, batch_index: int):
         m = self.model
         if m.automatic_optimization:
             opt = self.optimizers[0]

@@ -95,6 +95,11 @@ class Conv2dLayer(nn.Module):
             x = ops_gan.fir4(x, 1, 2)
             return ops.conv2d(x, self.weight, self.bias, residual, pad=0, w_scale=w_scale, **kw)
         # conv2d_resample.py:119-122: pad k//2 + 1 each side, FIR, then a stride-2 conv without padding
+        if (self.kernel_size == 3 and residual is None and not ops_gan.in_second_order() and _S2D_ROUTE
+                and ops_gan.down2_conv3x3_supported(x, self.weight)):
+            # space-to-depth route: FIR written in 2x2 space-to-depth layout, then a 2x2-tap tensor-core convolution over 4C channels
+            act = kw['act']
+            return ops_gan.down2_conv3x3(x, self.weight, self.bias, act, kw.get('alpha', 0.0), kw.get('gain', 1.0), w_scale)
         x = ops_gan.fir4(x, self.padding + 1, 1)
         co, ci = self.weight.shape[0], self.weight.shape[1]
         if (ops.get_precision().name == 'fast' and self.kernel_size == 3 and residual is None and ci % 64 == 0 and co % 128 == 0
@@ -104,6 +109,10 @@ class Conv2dLayer(nn.Module):
             full = ops.conv2d(x, self.weight, self.bias, None, pad=1, stride=1, w_scale=w_scale, **kw)
             return ops_gan.decimate2(full, (x.shape[2] - 3) // 2 + 1, (x.shape[3] - 3) // 2 + 1, 1)
         return ops.conv2d(x, self.weight, self.bias, residual, pad=0, stride=2, w_scale=w_scale, **kw)
+
+
+import os as _os
+_S2D_ROUTE = _os.environ.get('VQB_D_S2D', '1') != '0'      # A/B switch: 0 = full-resolution stride-1 conv + decimation
 
 
 class DiscriminatorBlock(nn.Module):

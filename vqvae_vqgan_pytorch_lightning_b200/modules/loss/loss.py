@@ -8,7 +8,7 @@ import torch.nn as nn
 import torch.nn.functional as functional
 from torch.autograd import grad
 
-from ... import ops
+from ... import ops, ops_gan
 from .discriminator import Discriminator
 from .lpips import LPIPS
 
@@ -55,8 +55,9 @@ class VQLPIPSWithDiscriminator(nn.Module):
 
     def calculate_adaptive_weight(self, nll_loss, g_loss, last_layer):
         """loss.py:80-96 (the caller passes the perceptual loss as `nll_loss`, :131)"""
-        nll_grads = grad(nll_loss, last_layer, grad_outputs=torch.ones_like(nll_loss), retain_graph=True)[0].detach()
-        g_grads = grad(g_loss, last_layer, grad_outputs=torch.ones_like(g_loss), retain_graph=True)[0].detach()
+        with ops.no_grad_sink():           # these parameter gradients are RETURNED, not accumulated into last_layer.grad
+            nll_grads = grad(nll_loss, last_layer, grad_outputs=torch.ones_like(nll_loss), retain_graph=True)[0].detach()
+            g_grads = grad(g_loss, last_layer, grad_outputs=torch.ones_like(g_loss), retain_graph=True)[0].detach()
         adaptive_weight = torch.norm(nll_grads, p=2) / (torch.norm(g_grads, p=2) + 1e-8)
         adaptive_weight = torch.clamp(adaptive_weight, 0.0, 1e4).detach()
         return adaptive_weight * self.generator_weight
@@ -104,7 +105,11 @@ class VQLPIPSWithDiscriminator(nn.Module):
                           self.r1_regularization_cost is not None)
             if compute_r1:
                 images = images.detach().requires_grad_(True)
-            logits_real = self.discriminator(images)
+            if compute_r1:
+                with ops_gan.second_order():            # this pass is differentiated twice (R1): twice-differentiable layer routes
+                    logits_real = self.discriminator(images)
+            else:
+                logits_real = self.discriminator(images)
             logits_fake = self.discriminator(reconstructions.detach())
             d_loss = discriminator_loss(logits_real, logits_fake, loss_type=self.adversarial_loss_type)
             r1_term = self.calculate_r1_regularization_term(logits_real, images, compute_r1)

@@ -99,6 +99,72 @@ def bump_weights_epoch() -> None:
     _weights_epoch += 1
 
 
+class ZeroArena:
+    """Per-step pool of zero-initialised scratch (GroupNorm sum buffers, bias-gradient accumulators ...): the ~150 small
+    torch.zeros fills of a training step become ONE memset at the start of the step (Trainer._step_body brackets the step with
+    `zero_arena.step()`); outside a step, or when the pool is exhausted, zeros() is plain torch.zeros.  Buffers handed out are
+    valid until the next step begins -- every user consumes them inside the forward / backward pass that took them."""
+
+    def __init__(self, nbytes: int = 64 << 20):
+        self.nbytes, self.buf, self.off, self.high, self.active = nbytes, None, 0, 0, False
+
+    @contextlib.contextmanager
+    def step(self, device):
+        if self.active:                               # nested steps (a trainer driving another): the outer one owns the pool
+            yield
+            return
+        if self.buf is None or self.buf.device != device:
+            self.buf = torch.zeros(self.nbytes, dtype=torch.uint8, device=device)
+            self.high = 0
+        elif self.high:
+            # everything ANY earlier step dirtied (monotone high-water mark: replayed CUDA graphs of other step variants write
+            # the pool without passing through here)
+            self.buf[:self.high].zero_()
+        self.off, self.active = 0, True
+        try:
+            yield
+        finally:
+            self.active = False
+
+    def zeros(self, n: int, dtype: torch.dtype, device) -> torch.Tensor:
+        nb = n * torch.empty((), dtype=dtype).element_size()
+        if not self.active or self.buf is None or self.buf.device != device or self.off + nb > self.nbytes:
+            return torch.zeros(n, dtype=dtype, device=device)
+        t = self.buf[self.off:self.off + nb].view(dtype)
+        self.off = (self.off + nb + 255) & ~255
+        self.high = max(self.high, min(self.off, self.nbytes))
+        return t
+
+
+zero_arena = ZeroArena()
+
+
+_sink_off = 0
+
+
+@contextlib.contextmanager
+def no_grad_sink():
+    """Around torch.autograd.grad(...) calls that ask for PARAMETER gradients (the adaptive generator weight, loss.py:80-96):
+    inside, backward kernels return their parameter gradients to autograd instead of accumulating them into .grad."""
+    global _sink_off
+    _sink_off += 1
+    try:
+        yield
+    finally:
+        _sink_off -= 1
+
+
+def grad_sink(p) -> Optional[torch.Tensor]:
+    """The tensor a backward kernel may accumulate parameter `p`'s gradient into DIRECTLY (its .grad view inside FusedAdamW's
+    flat gradient buffer) instead of returning it to autograd (whose AccumulateGrad is one `add` launch per parameter per step).
+    Only when the optimizer opted the parameter in (`_vqb_direct_grad`, set by the single-process Trainer: the data-parallel
+    bucket hooks are post-accumulate hooks and need autograd's accumulation) and no graph of the backward pass is recorded."""
+    if p is None or _sink_off or not getattr(p, '_vqb_direct_grad', False) or torch.is_grad_enabled():
+        return None
+    g = p.grad
+    return g if (g is not None and g.is_contiguous() and g.dtype == torch.float32) else None
+
+
 def empty_nhwc(n: int, c: int, h: int, w: int, dtype: torch.dtype, device) -> torch.Tensor:
     return torch.empty((n, c, h, w), dtype=dtype, device=device, memory_format=CL)
 
@@ -449,7 +515,7 @@ class Conv2dFn(torch.autograd.Function):
         def gn_buffer(eff_impl, eci, ekh, ekw, epad):
             if gn_groups and act == ACT_NONE and gn_fusion_enabled() and lib.load().vqb_conv2d_fwd_gn_supported(
                     eff_impl, n_, h_, w_, eci, co, ekh, ekw, epad, stride, gn_groups):
-                return torch.zeros(n_ * gn_groups * 2, dtype=torch.float64, device=x.device)
+                return zero_arena.zeros(n_ * gn_groups * 2, torch.float64, x.device)
             return None
 
         if route == 'in':
@@ -491,7 +557,7 @@ class Conv2dFn(torch.autograd.Function):
         db_fused = None
         if act != ACT_NONE:
             want_db = has_bias and ctx.needs_input_grad[2] and not _no_weight_grad and not torch.is_grad_enabled()
-            db_buf = torch.zeros(co, dtype=torch.float32, device=x.device) if want_db else None
+            db_buf = zero_arena.zeros(co, torch.float32, x.device) if want_db else None
             dy = ActBwdFn.apply(dy, y.detach(), act, alpha, gain, gdt, db_buf)
             if want_db and ActBwdFn.last_db_done:
                 db_fused = db_buf                        # bias gradient produced by the same pass
@@ -544,7 +610,7 @@ class Conv2dFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = _dgrad_raw(dy_ops, weight, h, w, pad, stride, w_scale, in_dtype if in_dtype in (torch.float32, torch.bfloat16) else gdt)
         if ctx.needs_input_grad[1] and not _no_weight_grad:
-            dw = _wgrad_raw(x, dy_ops, weight.shape, pad, stride, w_scale)
+            dw = _wgrad_raw(x, dy_ops, weight.shape, pad, stride, w_scale, weight)
         if has_bias and ctx.needs_input_grad[2] and not _no_weight_grad:
             db = db_fused if db_fused is not None else _colsum(dy, n * oh * ow, co)
         return dx, dw, db, dres, None, None, None, None, None, None, None, None
@@ -582,8 +648,21 @@ def _dgrad_raw(dy: torch.Tensor, weight: torch.Tensor, h: int, w: int, pad: int,
     return _conv_fwd_raw(dimpl, dyd, wd, None, None, ddt, co, ci, kh, kw, kh - 1 - pad, 1, ACT_NONE, 0.0, 1.0)
 
 
-def _wgrad_raw(x: torch.Tensor, dy: torch.Tensor, wshape, pad: int, stride: int, w_scale: float) -> torch.Tensor:
-    """dW [co, ci, kh, kw] fp32 of y = conv2d(x, W * w_scale, pad, stride) given x and dy (channels-last)."""
+def _persistent_dwp(weight, numel: int) -> torch.Tensor:
+    """The packed partial-sum buffer of `weight`'s gradient kernel, kept on the parameter: zero-filled ONCE -- the unpack kernel
+    clears it behind its read (vqb_unpack_conv_wgrad_acc rezero), so no fill launch precedes a weight-gradient launch."""
+    buf = getattr(weight, '_vqb_dwp', None)
+    if buf is None or buf.numel() != numel or buf.device != weight.device or getattr(weight, '_vqb_dwp_dirty', False):
+        buf = torch.zeros(numel, dtype=torch.float32, device=weight.device)
+        weight._vqb_dwp = buf
+    weight._vqb_dwp_dirty = True                       # cleared by the caller once the unpack (which re-zeroes) has been enqueued
+    return buf
+
+
+def _wgrad_raw(x: torch.Tensor, dy: torch.Tensor, wshape, pad: int, stride: int, w_scale: float, weight=None) -> Optional[torch.Tensor]:
+    """dW [co, ci, kh, kw] fp32 of y = conv2d(x, W * w_scale, pad, stride) given x and dy (channels-last).  With `weight` (the
+    parameter) the partial sums go through its persistent packed buffer, and -- when grad_sink(weight) allows -- the result is
+    accumulated straight into weight.grad and None is returned."""
     prec = get_precision()
     co, ci, kh, kw = wshape
     n, _, h, w = x.shape
@@ -603,10 +682,18 @@ def _wgrad_raw(x: torch.Tensor, dy: torch.Tensor, wshape, pad: int, stride: int,
     wimpl = prec.wgrad_impl(ci, co, stride) if x.dtype == torch.bfloat16 else 0
     wimpl = 1 if wimpl == 1 else 0
     dyw = as_nhwc(dy, torch.bfloat16) if wimpl == 1 else dy
-    dwp = torch.zeros(kh * kw * ci * co, dtype=torch.float32, device=x.device)
+    persistent = weight is not None and isinstance(weight, torch.nn.Parameter)
+    dwp = _persistent_dwp(weight, kh * kw * ci * co) if persistent else torch.zeros(kh * kw * ci * co, dtype=torch.float32, device=x.device)
     call('vqb_conv2d_wgrad', wimpl, ptr(x), dt(x), ptr(dyw), dt(dyw), ptr(dwp), n, h, w, ci, co, kh, kw, pad, stride, stream())
+    sink = grad_sink(weight) if persistent else None
+    if sink is not None and tuple(sink.shape) == tuple(wshape):
+        call('vqb_unpack_conv_wgrad_acc', ptr(dwp), ptr(sink), co, ci, kh, kw, w_scale, 1, 1, stream())
+        weight._vqb_dwp_dirty = False
+        return None
     dw = torch.empty(tuple(wshape), dtype=torch.float32, device=x.device)         # contiguous even if the weight is a view
-    call('vqb_unpack_conv_wgrad', ptr(dwp), ptr(dw), co, ci, kh, kw, w_scale, stream())
+    call('vqb_unpack_conv_wgrad_acc', ptr(dwp), ptr(dw), co, ci, kh, kw, w_scale, 0, int(persistent), stream())
+    if persistent:
+        weight._vqb_dwp_dirty = False
     return dw
 
 
@@ -680,13 +767,15 @@ class GroupNormActFn(torch.autograd.Function):
         be = beta.detach().reshape(-1).float().contiguous()
         stats = torch.empty(n * groups * 2, dtype=torch.float32, device=x.device)
         if sums is None or sums.numel() != n * groups * 2:
-            sums = torch.zeros(n * groups * 2, dtype=torch.float64, device=x.device)
+            sums = zero_arena.zeros(n * groups * 2, torch.float64, x.device)
             call('vqb_gn_stats', ptr(x), dt(x), ptr(sums), n, h * w, c, groups, stream())
         # else: the producing convolution's epilogue already accumulated them (vqb_conv2d_fwd_gn)
-        call('vqb_gn_finalize', ptr(sums), ptr(stats), n, h * w, c, groups, eps, stream())
         y = torch.empty_like(x, memory_format=torch.preserve_format)
-        call('vqb_gn_apply', ptr(x), dt(x), ptr(stats), ptr(ga), ptr(be), ptr(y), dt(y), n, h * w, c, groups, act, stream())
+        # mean / rstd are evaluated from the sums inside the apply kernel (and left in `stats` for the backward pass)
+        call('vqb_gn_apply_sums', ptr(x), dt(x), ptr(sums), ptr(ga), ptr(be), ptr(y), dt(y), ptr(stats), n, h * w, c, groups, eps, act,
+             stream())
         ctx.save_for_backward(x, stats, ga, be)
+        ctx.params = (gamma, beta)
         ctx.cfg = (groups, act, gamma.shape, beta.shape)
         if want_skip:
             return y, x.view_as(x)
@@ -698,19 +787,31 @@ class GroupNormActFn(torch.autograd.Function):
         groups, act, gshape, bshape = ctx.cfg
         n, c, h, w = x.shape
         dy = as_nhwc(dy)
-        part = torch.zeros(n * c * 2, dtype=torch.float64, device=x.device)
+        part = zero_arena.zeros(n * c * 2, torch.float64, x.device)
         call('vqb_gn_bwd_reduce', ptr(x), dt(x), ptr(dy), dt(dy), ptr(stats), ptr(ga), ptr(be), ptr(part), n, h * w, c, groups,
              act, stream())
-        coef = torch.empty(n * groups * 2, dtype=torch.float32, device=x.device)
-        dgamma = torch.empty(c, dtype=torch.float32, device=x.device)
-        dbeta = torch.empty(c, dtype=torch.float32, device=x.device)
-        call('vqb_gn_bwd_finalize', ptr(part), ptr(ga), ptr(coef), ptr(dgamma), ptr(dbeta), n, h * w, c, groups, stream())
-        dx = None
-        if ctx.needs_input_grad[0]:
-            dx = torch.empty_like(x, memory_format=torch.preserve_format)
-            add = as_nhwc(dskip, dx.dtype) if dskip is not None else None
-            call('vqb_gn_bwd_apply', ptr(x), dt(x), ptr(dy), dt(dy), ptr(stats), ptr(ga), ptr(be), ptr(coef), ptr(add), ptr(dx),
-                 dt(dx), n, h * w, c, groups, act, stream())
+        if not ctx.needs_input_grad[0]:
+            coef = torch.empty(n * groups * 2, dtype=torch.float32, device=x.device)
+            dgamma = torch.empty(c, dtype=torch.float32, device=x.device)
+            dbeta = torch.empty(c, dtype=torch.float32, device=x.device)
+            call('vqb_gn_bwd_finalize', ptr(part), ptr(ga), ptr(coef), ptr(dgamma), ptr(dbeta), n, h * w, c, groups, stream())
+            return None, dgamma.reshape(gshape), dbeta.reshape(bshape), None, None, None, None, None
+        # the finalize arithmetic (per-group coefficients, dgamma / dbeta) runs inside the apply kernel; with a gradient sink the
+        # parameter gradients are accumulated straight into the optimizer's flat buffer
+        gamma_p, beta_p = ctx.params
+        sg, sb = grad_sink(gamma_p), grad_sink(beta_p)
+        direct = sg is not None and sb is not None and ctx.needs_input_grad[1] and ctx.needs_input_grad[2]
+        if direct:
+            dgamma, dbeta = sg.view(-1), sb.view(-1)
+        else:
+            dgamma = torch.empty(c, dtype=torch.float32, device=x.device)
+            dbeta = torch.empty(c, dtype=torch.float32, device=x.device)
+        dx = torch.empty_like(x, memory_format=torch.preserve_format)
+        add = as_nhwc(dskip, dx.dtype) if dskip is not None else None
+        call('vqb_gn_bwd_apply_part', ptr(x), dt(x), ptr(dy), dt(dy), ptr(stats), ptr(ga), ptr(be), ptr(part), ptr(add), ptr(dx),
+             dt(dx), ptr(dgamma), ptr(dbeta), int(direct), n, h * w, c, groups, act, stream())
+        if direct:
+            return dx, None, None, None, None, None, None, None
         return dx, dgamma.reshape(gshape), dbeta.reshape(bshape), None, None, None, None, None
 
 

@@ -288,3 +288,131 @@ class ZeroUpsample2Fn(torch.autograd.Function):
 
 def decimate2(x, oh, ow, off):
     return Decimate2Fn.apply(x, oh, ow, off)
+
+
+# ------------------------------------------------------------------------------------------------------
+# the discriminator's down-sampling 3x3 convolution (conv2d_resample.py:119-122) in space-to-depth form
+# ------------------------------------------------------------------------------------------------------
+def _s2d_packed(weight: torch.Tensor, w_scale: float):
+    """Kernel layouts of a [co, c, 3, 3] weight for the 2x2-tap form: with t = 2a + dy (row) and u = 2b + dx (column) of the kernel
+    zero-padded to 4x4, W2[co][a][b][(dy,dx,c)] = w[co][c][t][u].  Returns (forward K-major [co][(a,b),(dy,dx,c)], dgrad K-major
+    [(dy,dx,c)][(1-a,1-b),co]) as persistent bf16 buffers, refreshed once per weights epoch."""
+    from . import ops
+    cache = getattr(weight, '_vqb_s2d', None)
+    if cache is not None and cache['epoch'] == ops._weights_epoch and cache['scale'] == w_scale and cache['ptr'] == weight.data_ptr():
+        return cache['fwd'], cache['dgrad']
+    co, c = weight.shape[0], weight.shape[1]
+    w4 = torch.nn.functional.pad(weight.detach().float() * w_scale, (0, 1, 0, 1)).view(co, c, 2, 2, 2, 2)      # [co, c, a, dy, b, dx]
+    w2 = w4.permute(0, 2, 4, 3, 5, 1)                                                                         # [co, a, b, dy, dx, c]
+    fwd = w2.reshape(co, 16 * c)
+    dgr = w2.flip(1, 2).permute(3, 4, 5, 1, 2, 0).reshape(4 * c, 4 * co)
+    if cache is None or cache['fwd'].numel() != fwd.numel() or cache['fwd'].device != weight.device:
+        cache = {'fwd': torch.empty(fwd.shape, dtype=torch.bfloat16, device=weight.device),
+                 'dgrad': torch.empty(dgr.shape, dtype=torch.bfloat16, device=weight.device)}
+        weight._vqb_s2d = cache
+    cache['fwd'].copy_(fwd); cache['dgrad'].copy_(dgr)
+    cache.update(epoch=ops._weights_epoch, scale=w_scale, ptr=weight.data_ptr())
+    return cache['fwd'], cache['dgrad']
+
+
+def down2_conv3x3_supported(x: torch.Tensor, weight: torch.Tensor) -> bool:
+    from . import ops
+    n, c, h, w = x.shape
+    co = weight.shape[0]
+    if ops.get_precision().name != 'fast' or tuple(weight.shape[2:]) != (3, 3) or h % 2 or w % 2 or c % 16 or co % 128:
+        return False
+    L = lib.load()
+    h2, w2 = h // 2 + 1, w // 2 + 1
+    return bool(L.vqb_conv2d_sub_supported(n, h2, w2, h // 2, w // 2, 4 * c, co, 2, 0) and
+                L.vqb_conv2d_sub_supported(n, h // 2, w // 2, h2, w2, co, 4 * c, 2, -1))
+
+
+class Down2Conv3x3Fn(torch.autograd.Function):
+    """act(conv2d(FIR(x, pad 2), w * w_scale, stride 2) + bias) * gain -- conv2d_resample(down=2, padding=1) with the [1,3,3,1]
+    filter (conv2d_resample.py:119-122) followed by bias_act -- without the full-resolution detour:
+      z' = s2d(FIR(x))  [N, H/2+1, W/2+1, 4C]   one pass (vqb_fir4_s2d), then
+      y[o] = sum_{a,b<2} W2[a][b] z'[o+a, o+b]  a 2x2-tap stride-1 tensor-core convolution over 4C channels (vqb_conv2d_fwd_sub):
+    16C MACs per output instead of the 36C of a stride-1 3x3 evaluation at full resolution that is then decimated.  First order
+    only: while the graph of a backward pass is recorded (R1) the layer takes the twice-differentiable route."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, act, alpha, gain, w_scale):
+        from . import ops
+        x = as_nhwc(x, torch.bfloat16)
+        n, c, h, w = x.shape
+        co = weight.shape[0]
+        hz, wz, h2, w2, oh, ow = h + 1, w + 1, h // 2 + 1, w // 2 + 1, h // 2, w // 2
+        zs = empty_nhwc(n, 4 * c, h2, w2, torch.bfloat16, x.device)
+        call('vqb_fir4_s2d', ptr(x), ptr(zs), lib.BF16, n, h, w, c, hz, wz, 2, 0, 1, stream())
+        wf, _ = _s2d_packed(weight, w_scale)
+        b = bias.detach().reshape(-1).float().contiguous() if bias is not None else None
+        y = empty_nhwc(n, co, oh, ow, torch.bfloat16, x.device)
+        call('vqb_conv2d_fwd_sub', ptr(zs), ptr(wf), ptr(b), None, ptr(y), lib.BF16, n, h2, w2, oh, ow, 4 * c, co, 2, 0, act, alpha, gain,
+             stream())
+        ctx.save_for_backward(zs, weight, y if act != lib.ACT_NONE else None)
+        ctx.cfg = (n, c, h, w, co, act, alpha, gain, w_scale, bias is not None)
+        ctx.params = (weight, bias)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        from . import ops
+        if torch.is_grad_enabled():
+            raise lib.VQBError('Down2Conv3x3Fn is first-order only: run the discriminator under ops_gan.second_order() when the graph of '
+                               'a backward pass is recorded (R1 penalty)')
+        zs, weight, y = ctx.saved_tensors
+        n, c, h, w, co, act, alpha, gain, w_scale, has_bias = ctx.cfg
+        hz, wz, h2, w2, oh, ow = h + 1, w + 1, h // 2 + 1, w // 2 + 1, h // 2, w // 2
+        dy = as_nhwc(dy)
+        db = None
+        want_db = has_bias and ctx.needs_input_grad[2]
+        if act != lib.ACT_NONE:
+            db_buf = ops.zero_arena.zeros(co, torch.float32, dy.device) if want_db else None
+            dy = ops.ActBwdFn.apply(dy, y.detach(), act, alpha, gain, torch.bfloat16, db_buf)
+            if want_db and ops.ActBwdFn.last_db_done:
+                db = db_buf
+        elif gain != 1.0:
+            raise lib.VQBError('gain != 1 requires an activation epilogue')
+        dy = as_nhwc(dy, torch.bfloat16)
+        if want_db and db is None:
+            db = ops._colsum(dy, n * oh * ow, co)
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            _, wd = _s2d_packed(weight, w_scale)
+            dzs = empty_nhwc(n, 4 * c, h2, w2, torch.bfloat16, dy.device)
+            call('vqb_conv2d_fwd_sub', ptr(dy), ptr(wd), None, None, ptr(dzs), lib.BF16, n, oh, ow, h2, w2, co, 4 * c, 2, -1, lib.ACT_NONE, 0.0,
+                 1.0, stream())
+            dx = empty_nhwc(n, c, h, w, torch.bfloat16, dy.device)
+            # adjoint of FIR(pad 2): the same filter with pad 1 on the (H+1) x (W+1) gradient, read from its space-to-depth layout
+            call('vqb_fir4_s2d', ptr(dzs), ptr(dx), lib.BF16, n, hz, wz, c, h, w, 1, 1, 0, stream())
+        if ctx.needs_input_grad[1] and not ops._no_weight_grad:
+            dwp = torch.zeros(16 * c * co, dtype=torch.float32, device=dy.device)
+            call('vqb_conv2d_wgrad_sub', ptr(zs), ptr(dy), ptr(dwp), n, h2, w2, oh, ow, 4 * c, co, 2, 0, stream())
+            # dwp [(a,b)][(dy,dx,c)][co] -> dw [co][c][2a+dy][2b+dx] (the zero-padding row / column of the 4x4 frame is dropped)
+            dw = dwp.view(2, 2, 2, 2, c, co).permute(5, 4, 0, 2, 1, 3).reshape(co, c, 4, 4)[:, :, :3, :3]
+            dw = (dw * w_scale) if w_scale != 1.0 else dw.contiguous()
+        return dx, dw, db, None, None, None, None
+
+
+_second_order = 0
+
+
+class second_order:
+    """Context: the forward passes inside will be differentiated TWICE (R1: autograd.grad(..., create_graph=True), loss.py:98-112),
+    so layers with a first-order-only fast route take their twice-differentiable one."""
+
+    def __enter__(self):
+        global _second_order
+        _second_order += 1
+
+    def __exit__(self, *a):
+        global _second_order
+        _second_order -= 1
+
+
+def in_second_order() -> bool:
+    return _second_order > 0
+
+
+def down2_conv3x3(x, weight, bias, act, alpha, gain, w_scale):
+    return Down2Conv3x3Fn.apply(x, weight, bias, act, alpha, gain, w_scale)
