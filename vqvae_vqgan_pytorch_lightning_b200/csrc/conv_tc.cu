@@ -121,6 +121,10 @@ struct FwdParams {
     // position (kh0 + t / ktw, kw0 + t % ktw) and the weight block t of the packed weight.  3x3: ntaps 9, ktw 3, kh0 = kw0 = 0.
     // A 2x2-tap convolution (the space-to-depth form of the discriminator's stride-2 3x3 convolution and its dgrad) uses 4.
     int ntaps, ktw, kh0, kw0;
+    // one-CTA halo kernel: the WHOLE packed weight (ntaps x cchunks tiles of BN x 64) stays resident in shared memory -- loaded once
+    // per CTA instead of once per pixel tile (narrow output heads: Co <= 16, one channel tile, 2 KB weight tiles whose per-tap TMA
+    // round trips, not the tensor pipe, paced the kernel)
+    int b_resident;
 };
 
 // ---- shared epilogue: 32 accumulator columns of one pixel row -> bias / act / residual -> NHWC store ---------------
@@ -440,6 +444,13 @@ conv_fwd_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     if (warp == 0) {
         if (lane == 0) {
             int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+            if (p.b_resident && blockIdx.x < p.num_tiles) {
+                // all weight tiles once, on ONE barrier: slot cc * ntaps + tap
+                ptx::mbar_expect_tx(&fullB[0], (uint32_t)(p.cchunks * p.ntaps * b_stage));
+                for (int cc = 0; cc < p.cchunks; ++cc)
+                    for (int tap = 0; tap < p.ntaps; ++tap)
+                        ptx::tma_load_2d(smemB + (size_t)(cc * p.ntaps + tap) * b_stage, &tmB, &fullB[0], tap * p.Ci + cc * BK, 0);
+            }
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 int ct = tile % p.co_tiles; int pt = tile / p.co_tiles;
                 int w0[2], h0[2], n0[2];
@@ -455,6 +466,7 @@ conv_fwd_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                     for (int m = 0; m < p.MT; ++m)
                         ptx::tma_load_4d(smemA + (size_t)sa * a_stage + m * a_tile, &tmA, &fullA[sa], (cc * BK) % p.Cx, w0[m] - 1, h0[m] - 1, n0[m]);
                     if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
+                    if (p.b_resident) continue;
                     for (int tap = 0; tap < p.ntaps; ++tap) {
                         ptx::mbar_wait(&emptyB[sb], pb ^ 1);
                         ptx::mbar_expect_tx(&fullB[sb], (uint32_t)b_stage);
@@ -470,6 +482,7 @@ conv_fwd_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             const uint32_t sbo = (uint32_t)p.pitch * 128u;           // stride between 8-pixel row groups = one halo row
             int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
             int as = 0; uint32_t aphase = 0;
+            if (p.b_resident && blockIdx.x < p.num_tiles) ptx::mbar_wait(&fullB[0], 0);
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 ptx::mbar_wait(&tempty[as], aphase ^ 1);
                 ptx::tc_fence_after();
@@ -479,7 +492,8 @@ conv_fwd_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                     const uint32_t a_addr = ptx::smem_u32(smemA + (size_t)sa * a_stage);
                     for (int tap = 0; tap < p.ntaps; ++tap) {
                         const int kh = p.kh0 + tap / p.ktw, kw = p.kw0 + tap % p.ktw;
-                        ptx::mbar_wait(&fullB[sb], pb);
+                        if (p.b_resident) sb = cc * p.ntaps + tap;
+                        else ptx::mbar_wait(&fullB[sb], pb);
                         ptx::tc_fence_after();
                         const uint64_t bdesc = ptx::umma_smem_desc(ptx::smem_u32(smemB + (size_t)sb * b_stage), 0, 1024);
                         const uint32_t row_off = (uint32_t)(kh * p.pitch + kw);
@@ -491,8 +505,10 @@ conv_fwd_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                                 ptx::umma_bf16(d_tmem + (uint32_t)(m * p.BN), adesc + (uint64_t)(k * UMMA_K * 2 / 16),
                                                bdesc + (uint64_t)(k * UMMA_K * 2 / 16), idesc, (cc | tap | k) != 0 ? 1u : 0u);
                         }
-                        ptx::umma_commit(&emptyB[sb]);
-                        if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
+                        if (!p.b_resident) {
+                            ptx::umma_commit(&emptyB[sb]);
+                            if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
+                        }
                     }
                     ptx::umma_commit(&emptyA[sa]);
                     if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
@@ -1219,7 +1235,7 @@ static int conv_fwd_tc_impl(const void* x, const void* wp, const float* bias, co
     p.N = N; p.H = H; p.W = W; p.Ci = Ci; p.Co = Co; p.KH = KH; p.KW = KW; p.pad = pad; p.Cx = Cx;
     p.narrow = (Co % 64 != 0);
     p.gn_sums = nullptr; p.gn_cpg = 0;
-    p.ntaps = 9; p.ktw = 3; p.kh0 = 0; p.kw0 = 0;
+    p.ntaps = 9; p.ktw = 3; p.kh0 = 0; p.kw0 = 0; p.b_resident = 0;
     if (sub) { p.ntaps = sub->T * sub->T; p.ktw = sub->T; p.kh0 = p.kw0 = sub->off + 1; }
     if (gn_sums) {
         const int cpg = (gn_groups > 0 && Co % gn_groups == 0) ? Co / gn_groups : 0;
@@ -1301,7 +1317,14 @@ static int conv_fwd_tc_impl(const void* x, const void* wp, const float* bias, co
         p.num_tiles = ((ptiles + p.MT - 1) / p.MT) * p.co_tiles;
         const int a_stage = p.MT * p.a_tile_bytes, b_stage = p.BN * BK * 2;
         p.a_stages = 2;
-        p.b_stages = (SMEM_LIMIT - 2048 - p.a_stages * a_stage) / b_stage; if (p.b_stages > 12) p.b_stages = 12;
+        static const int allow_resident = getenv("VQB_CONV_BRES") ? atoi(getenv("VQB_CONV_BRES")) : 1;
+        if (allow_resident && p.co_tiles == 1 && p.ntaps * p.cchunks * b_stage <= 72 * 1024) {
+            p.b_resident = 1;
+            p.b_stages = p.ntaps * p.cchunks;
+            p.a_stages = (SMEM_LIMIT - 2048 - p.b_stages * b_stage) / a_stage; if (p.a_stages > 4) p.a_stages = 4;
+        } else {
+            p.b_stages = (SMEM_LIMIT - 2048 - p.a_stages * a_stage) / b_stage; if (p.b_stages > 12) p.b_stages = 12;
+        }
         VQB_CHECK_ARG(p.b_stages >= 2, "conv2d_fwd(tcgen05 halo): shared memory budget");
         p.stages = 0;
         rc = make_act_map(&tmA, x, N, Hx, Wx, Cx, p.pitch, p.th + 2, 1); if (rc) return rc;

@@ -172,17 +172,43 @@ int launch_fir4_patch(const void* x, void* y, int N, int H, int W, int C, int OH
 
 
 // Sliding-window form of the down = 1 filter: one thread owns V channels x CW = 4 output columns and walks DOWN a strip of RH
-// output rows.  Per input row it loads CW + 3 = 7 vectors (1.75 16-byte loads per output instead of the patch kernel's 6.25:
-// ncu had the patch kernel LSU-bound at ~22 % of the HBM roof), forms the 4 horizontal sums and feeds them into the four
-// output rows in flight (a ring of accumulators with static indices: the row loop is unrolled by 4).
+// output rows.  Per input row it needs CW + 3 = 7 vectors (1.75 16-byte loads per output instead of the patch kernel's 6.25, which
+// ncu had LSU-bound at ~22 % of the HBM roof); the 4 horizontal sums feed the four output rows in flight (a ring of accumulators
+// with static indices: the row loop is unrolled by 4).  The 128 accumulator registers leave ~8 warps per SM, too few to cover
+// HBM latency with plain loads (first version: 1 TB/s) -- so every thread streams ITS OWN input rows through a private
+// DEPTH-deep ring in shared memory with cp.async (no registers held in flight, no inter-thread synchronisation), the scheme of the
+// GroupNorm kernels.
 // Layout flags: IN_S2D / OUT_S2D address the tensor as its 2x2 space-to-depth form [N][ceil(H/2)][ceil(W/2)][(dy, dx, c)]
 // (physical dims given by the *_h2 / *_w2 arguments) -- the discriminator's stride-2 3x3 convolution then runs as a 2x2-tap
 // stride-1 convolution over 4C channels of the filtered tensor (vqb_conv2d_fwd_sub), with no decimation pass.  OUT_S2D also
 // zero-fills the padding row / column of the physical tensor (logical index OH / OW when they are odd).
+constexpr int FIR_DEPTH = 4;          // input rows in flight per thread
+constexpr int FIR_THREADS = 128;
+
+__device__ __forceinline__ void fir_cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void fir_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void fir_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <typename T>
+__device__ __forceinline__ void unpack_vec(const uint4& u, float* v) {
+    if constexpr (sizeof(T) == 2) {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+    } else {
+        v[0] = __uint_as_float(u.x); v[1] = __uint_as_float(u.y); v[2] = __uint_as_float(u.z); v[3] = __uint_as_float(u.w);
+    }
+}
+
 template <typename T, bool IN_S2D, bool OUT_S2D>
-__global__ void __launch_bounds__(128) fir4_strip_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int OH, int OW,
-                                                         int pad, int RH, int in_h2, int in_w2, int out_h2, int out_w2) {
-    constexpr int V = Vec<T>::N, CW = 4, NC = CW + 3;
+__global__ void __launch_bounds__(FIR_THREADS) fir4_strip_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int OH, int OW,
+                                                                 int pad, int RH, int in_h2, int in_w2, int out_h2, int out_w2) {
+    constexpr int V = Vec<T>::N, CW = 4, NC = CW + 3, D = FIR_DEPTH;
+    extern __shared__ uint4 fir_ring_raw[];                         // 56 KB: slot [row mod D][column][thread]
+    uint4 (*ring)[NC][FIR_THREADS] = reinterpret_cast<uint4 (*)[NC][FIR_THREADS]>(fir_ring_raw);
+    const int tid = threadIdx.x;
     const int Cv = C / V;
     const int OHp = OUT_S2D ? 2 * out_h2 : OH, OWp = OUT_S2D ? 2 * out_w2 : OW;     // rows / columns that must be WRITTEN
     const int nstrips = (OHp + RH - 1) / RH, ncb = (OWp + CW - 1) / CW;
@@ -195,12 +221,28 @@ __global__ void __launch_bounds__(128) fir4_strip_kernel(const T* __restrict__ x
         if constexpr (OUT_S2D) return ((((int64_t)n * out_h2 + (oh >> 1)) * out_w2 + (ow >> 1)) * 4 + ((oh & 1) * 2 + (ow & 1))) * C;
         else return (((int64_t)n * OH + oh) * OW + ow) * C;
     };
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + tid; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int cv = (int)(i % Cv); int64_t r_ = i / Cv;
         const int cb = (int)(r_ % ncb); r_ /= ncb;
         const int strip = (int)(r_ % nstrips); const int n = (int)(r_ / nstrips);
         const int oh0 = strip * RH, ow0 = cb * CW;
         int rows = OHp - oh0; if (rows > RH) rows = RH;
+        const int nin = rows + 3;                                  // input rows oh0 - pad .. oh0 - pad + rows + 2
+        // request input row r into ring slot r mod D (one commit group per row, empty when the row lies outside the image)
+        auto request = [&](int r) {
+            const int ih = oh0 - pad + r;
+            if (r < nin && ih >= 0 && ih < H) {
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    const int iw = ow0 - pad + c;
+                    if (iw >= 0 && iw < W) fir_cp_async16(&ring[r % D][c][tid], x + in_off(n, ih, iw) + cv * V);
+                    else ring[r % D][c][tid] = make_uint4(0u, 0u, 0u, 0u);
+                }
+            }
+            fir_cp_commit();
+        };
+#pragma unroll
+        for (int r = 0; r < D; ++r) request(r);
         float acc[4][CW][V];
 #pragma unroll
         for (int a = 0; a < 4; ++a)
@@ -208,36 +250,33 @@ __global__ void __launch_bounds__(128) fir4_strip_kernel(const T* __restrict__ x
             for (int j = 0; j < CW; ++j)
 #pragma unroll
                 for (int u = 0; u < V; ++u) acc[a][j][u] = 0.f;
-        const int nin = rows + 3;                                  // input rows oh0 - pad .. oh0 - pad + rows + 2
         for (int r4 = 0; r4 < nin; r4 += 4) {
 #pragma unroll
             for (int rr = 0; rr < 4; ++rr) {
                 const int r = r4 + rr;
                 if (r < nin) {
+                    fir_cp_wait<D - 1>();                           // the group of row r has landed (rows r+1 .. r+D-1 may be in flight)
                     const int ih = oh0 - pad + r;
                     if (ih >= 0 && ih < H) {
-                        float v[NC][V];
+                        // horizontal sums with a 4-wide register window over the 7 columns
+                        float w0[V], w1[V], w2[V], w3[V];
+                        unpack_vec<T>(ring[r % D][0][tid], w0); unpack_vec<T>(ring[r % D][1][tid], w1); unpack_vec<T>(ring[r % D][2][tid], w2);
 #pragma unroll
-                        for (int c = 0; c < NC; ++c) {
-                            const int iw = ow0 - pad + c;
-                            if (iw >= 0 && iw < W) ldvec<T>(x + in_off(n, ih, iw) + cv * V, v[c]);
-                            else {
-#pragma unroll
-                                for (int u = 0; u < V; ++u) v[c][u] = 0.f;
-                            }
-                        }
-#pragma unroll
-                        for (int j = 0; j < CW; ++j)
+                        for (int j = 0; j < CW; ++j) {
+                            unpack_vec<T>(ring[r % D][j + 3][tid], w3);
 #pragma unroll
                             for (int u = 0; u < V; ++u) {
-                                const float hs = fmaf(0.375f, v[j + 1][u] + v[j + 2][u], 0.125f * (v[j][u] + v[j + 3][u]));
+                                const float hs = fmaf(0.375f, w1[u] + w2[u], 0.125f * (w0[u] + w3[u]));
                                 // vertical tap a of this input row belongs to output row r - a (ring slot (rr - a) & 3)
                                 acc[(rr + 4 - 0) & 3][j][u] = fmaf(0.125f, hs, acc[(rr + 4 - 0) & 3][j][u]);
                                 acc[(rr + 4 - 1) & 3][j][u] = fmaf(0.375f, hs, acc[(rr + 4 - 1) & 3][j][u]);
                                 acc[(rr + 4 - 2) & 3][j][u] = fmaf(0.375f, hs, acc[(rr + 4 - 2) & 3][j][u]);
                                 acc[(rr + 4 - 3) & 3][j][u] = fmaf(0.125f, hs, acc[(rr + 4 - 3) & 3][j][u]);
+                                w0[u] = w1[u]; w1[u] = w2[u]; w2[u] = w3[u];
                             }
+                        }
                     }
+                    request(r + D);                                 // refill the slot just consumed (D == 4: slot rr)
                     {                                               // output row r - 3 has received its last tap (rows < 0: only the reset)
                         const int oh = oh0 + r - 3;
 #pragma unroll
@@ -257,6 +296,7 @@ __global__ void __launch_bounds__(128) fir4_strip_kernel(const T* __restrict__ x
                 }
             }
         }
+        fir_cp_wait<0>();                                           // nothing of this item is in flight when the ring is reused
     }
 }
 
@@ -269,12 +309,20 @@ int launch_fir4_strip(const void* x, void* y, int N, int H, int W, int C, int OH
     int RH = 32;
     while (RH > 8 && per_row_strip * ((OHp + RH - 1) / RH) < (int64_t)148 * 2048) RH >>= 1;
     const int64_t total = per_row_strip * ((OHp + RH - 1) / RH);
-    int64_t blocks = (total + 127) / 128; if (blocks > 148 * 64) blocks = 148 * 64; if (blocks < 1) blocks = 1;
+    int64_t blocks = (total + FIR_THREADS - 1) / FIR_THREADS; if (blocks > 148 * 64) blocks = 148 * 64; if (blocks < 1) blocks = 1;
     const unsigned grid = (unsigned)blocks;
     if (in_s2d && out_s2d) return -1;
-    if (in_s2d) fir4_strip_kernel<T, true, false><<<grid, 128, 0, st>>>((const T*)x, (T*)y, N, H, W, C, OH, OW, pad, RH, in_h2, in_w2, out_h2, out_w2);
-    else if (out_s2d) fir4_strip_kernel<T, false, true><<<grid, 128, 0, st>>>((const T*)x, (T*)y, N, H, W, C, OH, OW, pad, RH, in_h2, in_w2, out_h2, out_w2);
-    else fir4_strip_kernel<T, false, false><<<grid, 128, 0, st>>>((const T*)x, (T*)y, N, H, W, C, OH, OW, pad, RH, in_h2, in_w2, out_h2, out_w2);
+    const size_t smem = (size_t)FIR_DEPTH * 7 * FIR_THREADS * sizeof(uint4);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(fir4_strip_kernel<T, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(fir4_strip_kernel<T, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(fir4_strip_kernel<T, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+    }
+    if (in_s2d) fir4_strip_kernel<T, true, false><<<grid, FIR_THREADS, smem, st>>>((const T*)x, (T*)y, N, H, W, C, OH, OW, pad, RH, in_h2, in_w2, out_h2, out_w2);
+    else if (out_s2d) fir4_strip_kernel<T, false, true><<<grid, FIR_THREADS, smem, st>>>((const T*)x, (T*)y, N, H, W, C, OH, OW, pad, RH, in_h2, in_w2, out_h2, out_w2);
+    else fir4_strip_kernel<T, false, false><<<grid, FIR_THREADS, smem, st>>>((const T*)x, (T*)y, N, H, W, C, OH, OW, pad, RH, in_h2, in_w2, out_h2, out_w2);
     return 0;
 }
 

@@ -370,10 +370,10 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmEh, const FusedParams p) {
             ptx::mbar_wait(&tfull[as], aph);
             ptx::tc_fence_after();
             const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * TN);
-            for (int c = half * 32; c < TN; c += 64) {
-                uint32_t r[32];
-                ptx::tmem_ld32(t_addr + (uint32_t)c, r);
-                ptx::tmem_ld_wait();
+            // The accumulator chunks are read one AHEAD: tcgen05.ld of chunk i+1 is issued before chunk i is scanned, so the TMEM read
+            // latency overlaps the ~100 instructions of a chunk (read -> wait -> scan in sequence left the eight scan warps, two per
+            // scheduler, latency-bound: 3.2 us per 256-code tile against 1.1 us of tensor work -- tools/vq_phases.py).
+            auto scan_chunk = [&](const uint32_t (&r)[32], const int c) {
                 const float* e2c = e2_s + as * TN + c;
                 // all 32 distances first (independent FMAs) and their minimum by a tree.  Only if the chunk minimum m lies within
                 // the band of the running minimum does the chunk hold candidates at all; then m itself is appended, and -- rare,
@@ -381,7 +381,11 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmEh, const FusedParams p) {
                 // FINAL minimum is either its chunk's minimum, appended because final <= running, or within the band of it.)
                 float d[32];
 #pragma unroll
-                for (int u = 0; u < 32; ++u) d[u] = fmaf(-2.0f, __uint_as_float(r[u]), e2c[u]);
+                for (int u = 0; u < 32; u += 4) {
+                    const float4 e4 = *reinterpret_cast<const float4*>(e2c + u);
+                    d[u] = fmaf(-2.0f, __uint_as_float(r[u]), e4.x); d[u + 1] = fmaf(-2.0f, __uint_as_float(r[u + 1]), e4.y);
+                    d[u + 2] = fmaf(-2.0f, __uint_as_float(r[u + 2]), e4.z); d[u + 3] = fmaf(-2.0f, __uint_as_float(r[u + 3]), e4.w);
+                }
                 float m[16];
 #pragma unroll
                 for (int u = 0; u < 16; ++u) m[u] = fminf(d[u], d[u + 16]);
@@ -413,6 +417,20 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmEh, const FusedParams p) {
                             cnt = cand_push(du, j * TN + c + u, b1 + thr, cnt, slot, cand_d, cand_c);
                         }
                     }
+                }
+            };
+            {
+                uint32_t ra[32], rb[32];
+                const int c0 = half * 32;
+                ptx::tmem_ld32(t_addr + (uint32_t)c0, ra);
+#pragma unroll 1
+                for (int it = 0; it < TN / 64; it += 2) {
+                    ptx::tmem_ld_wait();
+                    ptx::tmem_ld32(t_addr + (uint32_t)(c0 + (it + 1) * 64), rb);
+                    scan_chunk(ra, c0 + it * 64);
+                    ptx::tmem_ld_wait();
+                    if (it + 2 < TN / 64) ptx::tmem_ld32(t_addr + (uint32_t)(c0 + (it + 2) * 64), ra);
+                    scan_chunk(rb, c0 + (it + 1) * 64);
                 }
             }
             ptx::tc_fence_before();
