@@ -180,6 +180,16 @@ int vqb_gn_bwd_apply(const void* x, int x_dtype, const void* dy, int dy_dtype, c
  *   vqb_gn_bwd_apply_part  = vqb_gn_bwd_finalize + vqb_gn_bwd_apply: coef[b][g] is evaluated from part[b][c][2] by every block;
  *                            block (0,0) also reduces dgamma[c] / dbeta[c] over the batch -- overwritten, or += when
  *                            accumulate_param_grads != 0 (the destinations are then the parameters' .grad views). */
+/* The whole backward in ONE cooperative launch (bf16 tensors, VQB_ACT_NONE / SILU): a persistent grid walks the batch image by image,
+ * reduces image b, signals a per-image counter and applies image b-1 while its x / dy are still in L2 -- x and dy are read from HBM
+ * once instead of twice.  part [N][C][2] double and counters [N] int32 are zero-filled by the caller; dgamma / dbeta overwritten or
+ * += (accumulate_param_grads).  max_ctas > 0 caps the grid (data-parallel steps leave SMs to the overlapped NCCL kernels; a
+ * cooperative grid waits until all of its CTAs fit).  vqb_gn_bwd_fused_supported: 1 when the problem qualifies (one image's x + dy
+ * between 12 and 40 MB, 8-channel vectors), else the caller uses vqb_gn_bwd_reduce + vqb_gn_bwd_apply_part. */
+int vqb_gn_bwd_fused_supported(int x_dtype, int dy_dtype, int dx_dtype, int N, int HW, int C, int G, int act);
+int vqb_gn_bwd_fused(const void* x, const void* dy, const float* stats, const float* gamma, const float* beta, double* part,
+                     int* counters, const void* add, void* dx, float* dgamma, float* dbeta, int accumulate_param_grads, int N,
+                     int HW, int C, int G, int act, int max_ctas, void* stream);
 int vqb_gn_apply_sums(const void* x, int x_dtype, const double* sums, const float* gamma, const float* beta, void* y, int y_dtype,
                       float* stats_out, int N, int HW, int C, int G, float eps, int act, void* stream);
 int vqb_gn_bwd_apply_part(const void* x, int x_dtype, const void* dy, int dy_dtype, const float* stats, const float* gamma,

@@ -139,17 +139,17 @@ def test_maxpool3s2_matches_torch(V):
         assert torch.equal(yg.cpu(), y) and C.rel_err(xg.grad, xo.grad) < 1e-6
 
 
-@pytest.mark.parametrize('conv', ['tc4', 'simt'])
+@pytest.mark.parametrize('conv', ['tc3', 'tc4', 'simt'])
 def test_discriminator_matches_reference_fixture(V, conv):
     """strict numeric mode, both convolution back ends: split-precision tcgen05 (the default) and the fp32 SIMT kernels"""
     from vqvae_vqgan_pytorch_lightning_b200.modules.loss.discriminator import Discriminator
-    if conv == 'tc4' and not V.lib.load().vqb_device_supports_tcgen05():
+    if conv != 'simt' and not V.lib.load().vqb_device_supports_tcgen05():
         pytest.skip('needs sm_100')
     V.ops.set_strict_conv(conv)
     try:
         _discriminator_fixture_case(V, 5e-3 if conv == 'simt' else 2e-2, 2e-3 if conv == 'simt' else 5e-3)
     finally:
-        V.ops.set_strict_conv('tc4' if V.lib.load().vqb_device_supports_tcgen05() else 'simt')
+        V.ops.set_strict_conv('tc3' if V.lib.load().vqb_device_supports_tcgen05() else 'simt')
 
 
 def _discriminator_fixture_case(V, flip_bar, norm_bar):

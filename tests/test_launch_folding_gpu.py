@@ -140,3 +140,42 @@ def test_direct_gradient_accumulation_equals_autograd(V, name, mode):
         d = float((a.double() - b.double()).norm() / b.double().norm())
         print(f'{name}/{mode}: |g| {float(b.norm()):.3e} relative difference {d:.2e}')
         assert d < 1e-4, d
+
+
+@pytest.mark.parametrize('n,c,h,w,with_add', [(3, 128, 128, 192, True), (5, 128, 256, 256, False), (2, 256, 128, 128, True)])
+def test_gn_backward_cooperative_equals_two_launches(V, n, c, h, w, with_add):
+    """vqb_gn_bwd_fused (one cooperative launch, image b-1 applied out of L2 while image b is reduced) == vqb_gn_bwd_reduce +
+    vqb_gn_bwd_apply_part: same per-element arithmetic; the double-precision sums are combined in a different order."""
+    from vqvae_vqgan_pytorch_lightning_b200.lib import ACT_SILU, BF16, call, dt, ptr, stream
+    L = V.lib.load()
+    G, eps = 32, 1e-6
+    torch.manual_seed(9)
+    mk = lambda: torch.randn(n, c, h, w, device='cuda').bfloat16().contiguous(memory_format=torch.channels_last)
+    x, dy, skip = mk() * 2 + 0.5, mk(), mk()
+    ga, be = torch.rand(c, device='cuda') + 0.5, torch.randn(c, device='cuda') * 0.1
+    sums = torch.zeros(n * G * 2, dtype=torch.float64, device='cuda')
+    call('vqb_gn_stats', ptr(x), dt(x), ptr(sums), n, h * w, c, G, stream())
+    stats = torch.empty(n * G * 2, device='cuda')
+    call('vqb_gn_finalize', ptr(sums), ptr(stats), n, h * w, c, G, eps, stream())
+    add = skip if with_add else None
+    part = torch.zeros(n * c * 2, dtype=torch.float64, device='cuda')
+    call('vqb_gn_bwd_reduce', ptr(x), dt(x), ptr(dy), dt(dy), ptr(stats), ptr(ga), ptr(be), ptr(part), n, h * w, c, G, ACT_SILU, stream())
+    dx = torch.empty_like(x); dga = torch.empty(c, device='cuda'); dbe = torch.empty(c, device='cuda')
+    call('vqb_gn_bwd_apply_part', ptr(x), dt(x), ptr(dy), dt(dy), ptr(stats), ptr(ga), ptr(be), ptr(part), ptr(add), ptr(dx), dt(dx),
+         ptr(dga), ptr(dbe), 0, n, h * w, c, G, ACT_SILU, stream())
+    for max_ctas in (0, 64):
+        for acc in (0, 1):
+            part2 = torch.zeros(n * c * 2, dtype=torch.float64, device='cuda')
+            counters = torch.zeros(n, dtype=torch.int32, device='cuda')
+            dx2 = torch.full_like(x, float('nan'))
+            dga2 = torch.full((c,), 1.5, device='cuda'); dbe2 = torch.full((c,), -0.5, device='cuda')
+            call('vqb_gn_bwd_fused', ptr(x), ptr(dy), ptr(stats), ptr(ga), ptr(be), ptr(part2), ptr(counters), ptr(add), ptr(dx2),
+                 ptr(dga2), ptr(dbe2), acc, n, h * w, c, G, ACT_SILU, max_ctas, stream())
+            torch.cuda.synchronize()
+            assert torch.isfinite(dx2.float()).all()
+            # per-thread partial sums are fp32 over DIFFERENT pixel subsets in the two forms (only the cross-CTA combine is double)
+            assert float((part2 - part).norm() / part.norm()) < 1e-5
+            assert float((dx2.float() - dx.float()).abs().max()) <= 2e-2 * float(dx.float().abs().max())       # a bf16 ulp where a coefficient moved by one fp32 ulp
+            assert float((dx2.float() - dx.float()).norm() / dx.float().norm()) < 1e-3
+            ref_g, ref_b = (dga + 1.5, dbe - 0.5) if acc else (dga, dbe)
+            assert torch.allclose(dga2, ref_g, rtol=1e-4, atol=1e-3) and torch.allclose(dbe2, ref_b, rtol=1e-4, atol=1e-3)

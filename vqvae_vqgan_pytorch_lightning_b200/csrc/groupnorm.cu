@@ -631,6 +631,180 @@ __global__ void gn_bwd_apply_async_kernel(const bf16* __restrict__ x, const bf16
     cp_async_wait<0>();
 }
 
+
+// ---- backward, ONE cooperative launch: reduce + apply with the second read of x / dy served by L2 ------------------------------
+// The two-launch backward reads x and dy twice from HBM (reduce: 2T, apply: 2T + skip gradient + dx) because a whole batch
+// (2 x 1 GB at 256^2 x 128 channels x 64 images) passes between the two uses of an image.  Here a persistent grid walks the batch
+// image by image: every CTA reduces ITS pixel range of image b (fp32 partials -> double atomics into part[b][c]), signals a
+// per-image counter, then applies image b - 1 -- whose x / dy (33 MB) it streamed one phase earlier and are still resident in the
+// 126 MB L2 (the apply phase walks its range in REVERSE order, most recently used lines first).  The grid-wide dependency is a
+// counter per image (release: __threadfence + atomicAdd; acquire: one thread spins, then __syncthreads); the launch is cooperative
+// (all CTAs co-resident by contract).  Same arithmetic as gn_bwd_reduce_async_kernel + gn_bwd_apply_async_kernel with the finalize
+// folded in (gn_group_coef, gn_param_grads).
+template <int D, bool HAS_ADD>
+__global__ void __launch_bounds__(256) gn_bwd_fused_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, const float* __restrict__ stats,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           double* __restrict__ part, int* __restrict__ counters, const bf16* __restrict__ add,
+                                                           bf16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, int acc,
+                                                           int N, int HW, int C, int G, int act, double nel) {
+    constexpr int VEC = 8, NT = HAS_ADD ? 3 : 2;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint4* ring = reinterpret_cast<uint4*>(smem_raw);            // [D][NT][nthreads]
+    double* sh = reinterpret_cast<double*>(smem_raw);            // block reduction (the ring is drained at that point): [2][ty][tx*VEC]
+    const int tx = blockDim.x, ty = blockDim.y, nthr = tx * ty;
+    const int tid = threadIdx.y * tx + threadIdx.x;
+    const int c0 = threadIdx.x * VEC;
+    const int cg = C / G;
+    const bool silu = (act == VQB_ACT_SILU);
+    // this CTA's pixel range of EVERY image
+    const int per = (HW + gridDim.x - 1) / gridDim.x;
+    const int p0 = blockIdx.x * per;
+    int p1 = p0 + per; if (p1 > HW) p1 = HW;
+    const int first = p0 + threadIdx.y;
+    const int niter = first < p1 ? (p1 - first + ty - 1) / ty : 0;
+    float gam[VEC], bet[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) { gam[j] = gamma[c0 + j]; bet[j] = beta[c0 + j]; }
+
+    for (int b = 0; b <= N; ++b) {
+        if (b < N) {
+            // ================= reduce image b =================
+            float sc[VEC], sf[VEC], a[VEC], q[VEC], mean[VEC], rstd[VEC];
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                const int g = (c0 + j) / cg;
+                mean[j] = stats[((int64_t)b * G + g) * 2];
+                rstd[j] = stats[((int64_t)b * G + g) * 2 + 1];
+                sc[j] = rstd[j] * gam[j];
+                sf[j] = bet[j] - mean[j] * sc[j];
+                if (silu) { sc[j] *= 0.5f; sf[j] *= 0.5f; }
+                a[j] = 0.f; q[j] = 0.f;
+            }
+            const int64_t base = (int64_t)b * HW * C + c0;
+#pragma unroll
+            for (int s = 0; s < D; ++s) {
+                if (s < niter) {
+                    const int64_t off = base + (int64_t)(first + s * ty) * C;
+                    cp_async16(&ring[(s * NT + 0) * nthr + tid], x + off);
+                    cp_async16(&ring[(s * NT + 1) * nthr + tid], dy + off);
+                }
+                cp_async_commit();
+            }
+            int slot = 0;
+            for (int it = 0; it < niter; ++it) {
+                cp_async_wait<D - 1>();
+                float v[VEC], g[VEC];
+                unpack8(ring[(slot * NT + 0) * nthr + tid], v);
+                unpack8(ring[(slot * NT + 1) * nthr + tid], g);
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+                    float ds = g[j];
+                    if (silu) ds *= silu_grad2_of_half(fmaf(v[j], sc[j], sf[j]));
+                    a[j] += ds;
+                    q[j] = fmaf(ds, v[j], q[j]);
+                }
+                if (it + D < niter) {
+                    const int64_t off = base + (int64_t)(first + (it + D) * ty) * C;
+                    cp_async16(&ring[(slot * NT + 0) * nthr + tid], x + off);
+                    cp_async16(&ring[(slot * NT + 1) * nthr + tid], dy + off);
+                }
+                cp_async_commit();
+                slot = (slot + 1 == D) ? 0 : slot + 1;
+            }
+            cp_async_wait<0>();
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                if (silu) { a[j] *= 0.5f; q[j] *= 0.5f; }
+                q[j] = rstd[j] * (q[j] - mean[j] * a[j]);
+            }
+            __syncthreads();                                      // every thread is done with its ring before the reuse
+            const int row = tx * VEC;
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                sh[threadIdx.y * row + c0 + j] = (double)a[j];
+                sh[(ty + threadIdx.y) * row + c0 + j] = (double)q[j];
+            }
+            __syncthreads();
+            for (int c = tid; c < C; c += nthr) {
+                double sa = 0.0, sq = 0.0;
+                for (int y = 0; y < ty; ++y) { sa += sh[y * row + c]; sq += sh[(ty + y) * row + c]; }
+                atomicAdd(&part[((int64_t)b * C + c) * 2 + 0], sa);
+                atomicAdd(&part[((int64_t)b * C + c) * 2 + 1], sq);
+            }
+            __threadfence();                                      // the sums are visible device-wide before the counter moves
+            __syncthreads();
+            if (tid == 0) atomicAdd(&counters[b], 1);
+        }
+        if (b >= 1) {
+            // ================= apply image b - 1 =================
+            const int ib = b - 1;
+            if (tid == 0) {
+                const volatile int* cnt = counters + ib;
+                while (*cnt < (int)gridDim.x) { __nanosleep(64); }
+                __threadfence();
+            }
+            __syncthreads();
+            if (ib == N - 1 && blockIdx.x == 0 && dgamma) gn_param_grads(part, dgamma, dbeta, acc, N, C, tid, nthr);
+            float sc[VEC], sf[VEC], ca[VEC], cb[VEC], cc[VEC];       // dx = ds*ca + x*cb + cc
+            {
+                float k1 = 0.f, k2 = 0.f;
+                int gprev = -1;
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+                    const int g = (c0 + j) / cg;
+                    const float mean = stats[((int64_t)ib * G + g) * 2];
+                    const float rstd = stats[((int64_t)ib * G + g) * 2 + 1];
+                    if (g != gprev) { gn_group_coef(nullptr, part, gamma, ib, g, cg, C, G, nel, k1, k2); gprev = g; }
+                    sc[j] = rstd * gam[j];
+                    sf[j] = bet[j] - mean * sc[j];
+                    ca[j] = sc[j];
+                    cb[j] = -rstd * rstd * k2;
+                    cc[j] = -rstd * k1 - mean * cb[j];
+                    if (silu) { sc[j] *= 0.5f; sf[j] *= 0.5f; ca[j] *= 0.5f; }
+                }
+            }
+            const int64_t base = (int64_t)ib * HW * C + c0;
+            // iteration `it` handles pixel first + (niter - 1 - it) * ty: the range is walked backwards
+            auto issue = [&](int slot, int it) {
+                const int64_t off = base + (int64_t)(first + (niter - 1 - it) * ty) * C;
+                cp_async16(&ring[(slot * NT + 0) * nthr + tid], x + off);
+                cp_async16(&ring[(slot * NT + 1) * nthr + tid], dy + off);
+                if constexpr (HAS_ADD) cp_async16(&ring[(slot * NT + 2) * nthr + tid], add + off);
+            };
+#pragma unroll
+            for (int st = 0; st < D; ++st) {
+                if (st < niter) issue(st, st);
+                cp_async_commit();
+            }
+            int slot = 0;
+            for (int it = 0; it < niter; ++it) {
+                cp_async_wait<D - 1>();
+                float v[VEC], g[VEC], o[VEC];
+                unpack8(ring[(slot * NT + 0) * nthr + tid], v);
+                unpack8(ring[(slot * NT + 1) * nthr + tid], g);
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+                    float ds = g[j];
+                    if (silu) ds *= silu_grad2_of_half(fmaf(v[j], sc[j], sf[j]));
+                    o[j] = fmaf(ds, ca[j], fmaf(v[j], cb[j], cc[j]));
+                }
+                if constexpr (HAS_ADD) {
+                    float r[VEC];
+                    unpack8(ring[(slot * NT + 2) * nthr + tid], r);
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) o[j] += r[j];
+                }
+                stv<bf16, VEC>(dx + base + (int64_t)(first + (niter - 1 - it) * ty) * C, o);
+                if (it + D < niter) issue(slot, it + D);
+                cp_async_commit();
+                slot = (slot + 1 == D) ? 0 : slot + 1;
+            }
+            cp_async_wait<0>();
+            __syncthreads();                                      // ring / sh are reused by the next reduce phase
+        }
+    }
+}
+
 // coef[b][g] and parameter grads
 __global__ void gn_bwd_finalize_kernel(const double* __restrict__ part, const float* __restrict__ gamma,
                                        float* __restrict__ coef, float* __restrict__ dgamma, float* __restrict__ dbeta,
@@ -891,4 +1065,65 @@ extern "C" int vqb_gn_bwd_apply_part(const void* x, int x_dtype, const void* dy,
     VQB_CHECK_ARG(part, "gn_bwd_apply_part: null pointer");
     return gn_bwd_apply_impl(x, x_dtype, dy, dy_dtype, stats, gamma, beta, nullptr, part, add, dx, dx_dtype, dgamma, dbeta, accumulate_param_grads,
                              N, HW, C, G, act, stream);
+}
+
+// One cooperative launch for the whole backward (see gn_bwd_fused_kernel).  part [N][C][2] doubles and counters [N] ints are
+// zero-filled by the caller.  Returns VQB_ERR_UNSUPPORTED (nothing launched) when the problem does not qualify -- the caller then
+// uses vqb_gn_bwd_reduce + vqb_gn_bwd_apply_part.
+extern "C" int vqb_gn_bwd_fused_supported(int x_dtype, int dy_dtype, int dx_dtype, int N, int HW, int C, int G, int act) {
+    // OFF by default -- a measured negative result (profiles/r02_ncu_full_gn_bwd_fused_raw.csv): the L2 reuse works for 17 MB images
+    // (DRAM reads = x + dy exactly once) but not for the 33.5 MB images that carry most of the bytes (3.8 T read: the effective L2
+    // capacity for this streaming pattern is < 45 MB), and the per-image phase switch (ring drain, block reduction, counter) leaves
+    // DRAM 17-23 % busy: 1.16 ms per launch against 0.35 + 0.45 ms for the two-launch form.  VQB_GN_BWD_FUSED=1 enables it.
+    static const int enabled = getenv("VQB_GN_BWD_FUSED") ? atoi(getenv("VQB_GN_BWD_FUSED")) : 0;
+    if (!enabled || x_dtype != VQB_BF16 || dy_dtype != VQB_BF16 || dx_dtype != VQB_BF16) return 0;
+    if (!(N > 1 && HW > 0 && C > 0 && G > 0 && C % G == 0) || gn_vec(C, G) != 8 || C / 8 > 256 || 256 % (C / 8) != 0) return 0;
+    if (!(act == VQB_ACT_NONE || act == VQB_ACT_SILU)) return 0;
+    // worth it when one image's x + dy is a sizeable piece of L2 (>= 12 MB) yet two of them fit comfortably (<= 40 MB each)
+    const double img = 4.0 * HW * C;
+    return img >= 12e6 && img <= 40e6;
+}
+
+extern "C" int vqb_gn_bwd_fused(const void* x, const void* dy, const float* stats, const float* gamma, const float* beta, double* part,
+                                int* counters, const void* add, void* dx, float* dgamma, float* dbeta, int accumulate_param_grads, int N,
+                                int HW, int C, int G, int act, int max_ctas, void* stream) {
+    int rc = gn_check("gn_bwd_fused", N, HW, C, G); if (rc) return rc;
+    VQB_CHECK_ARG(x && dy && stats && gamma && beta && part && counters && dx && dgamma && dbeta, "gn_bwd_fused: null pointer");
+    if (!(N > 1 && gn_vec(C, G) == 8 && C / 8 <= 256 && 256 % (C / 8) == 0 && (act == VQB_ACT_NONE || act == VQB_ACT_SILU))) {
+        vqb_set_error("gn_bwd_fused: unsupported problem (N=%d HW=%d C=%d G=%d)", N, HW, C, G);
+        return VQB_ERR_UNSUPPORTED;
+    }
+    constexpr int DB = 6;
+    const int tx = C / 8, ty = 256 / tx;
+    dim3 block(tx, ty);
+    const size_t nthr = 256;
+    size_t ring = (size_t)DB * (add ? 3 : 2) * nthr * 16, red = 2 * sizeof(double) * nthr * 8;
+    size_t smem = ring > red ? ring : red;
+    static bool attr_set = false;
+    if (!attr_set) {
+        VQB_CUDA(cudaFuncSetAttribute(gn_bwd_fused_kernel<DB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        VQB_CUDA(cudaFuncSetAttribute(gn_bwd_fused_kernel<DB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        attr_set = true;
+    }
+    int dev = 0, sms = 0, occ = 0;
+    VQB_CUDA(cudaGetDevice(&dev));
+    VQB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (add) { VQB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gn_bwd_fused_kernel<DB, true>, 256, smem)); }
+    else { VQB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gn_bwd_fused_kernel<DB, false>, 256, smem)); }
+    if (occ < 1) { vqb_set_error("gn_bwd_fused: kernel does not fit an SM"); return VQB_ERR_UNSUPPORTED; }
+    if (occ > 2) occ = 2;
+    int grid = sms * occ;
+    // max_ctas > 0: leave SMs free for kernels that run BESIDE this one (the overlapped NCCL gradient all-reduce of a data-parallel
+    // step): a cooperative grid starts only when all its CTAs fit at once, so a full-machine grid would wait for those to drain
+    if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+    const int max_grid = (HW + ty - 1) / ty;                      // at least one pixel row of threads per CTA
+    if (grid > max_grid) grid = max_grid;
+    const double nel = (double)(C / G) * HW;
+    const bf16* xp = (const bf16*)x; const bf16* dyp = (const bf16*)dy; const bf16* addp = (const bf16*)add; bf16* dxp = (bf16*)dx;
+    void* args[] = {&xp, &dyp, &stats, &gamma, &beta, &part, &counters, &addp, &dxp, &dgamma, &dbeta, &accumulate_param_grads,
+                    &N, &HW, &C, &G, &act, (void*)&nel};
+    const void* fn = add ? (const void*)gn_bwd_fused_kernel<DB, true> : (const void*)gn_bwd_fused_kernel<DB, false>;
+    VQB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), block, args, smem, as_stream(stream)));
+    VQB_CHECK_LAUNCH("gn_bwd_fused");
+    return VQB_OK;
 }

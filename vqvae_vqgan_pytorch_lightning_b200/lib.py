@@ -71,6 +71,9 @@ SIGNATURES = {
     'vqb_conv2d_sub_supported': (_i, [_i, _i, _i, _i, _i, _i, _i, _i, _i]),
     # x, y, dtype, N, H, W, C, OH, OW, pad, in_s2d, out_s2d, stream
     'vqb_fir4_s2d': (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    'vqb_gn_bwd_fused_supported': (_i, [_i, _i, _i, _i, _i, _i, _i, _i]),
+    # x, dy, stats, gamma, beta, part, counters, add, dx, dgamma, dbeta, acc, N, HW, C, G, act, max_ctas, stream
+    'vqb_gn_bwd_fused': (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     'vqb_down2': (_i, [_p, _p, _i, _i, _i, _i, _i, _f, _p]),
     'vqb_up2': (_i, [_p, _p, _i, _i, _i, _i, _i, _f, _p]),
     'vqb_diff_sums': (_i, [_p, _i, _p, _i, _p, _i64, _p]),

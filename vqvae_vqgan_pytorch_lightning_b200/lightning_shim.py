@@ -100,6 +100,10 @@ class Trainer:
         # Single process: the backward kernels accumulate parameter gradients straight into the flat gradient buffers
         # (ops.grad_sink) -- no AccumulateGrad `add` launch per parameter.  With bucket hooks (post-accumulate hooks) installed the
         # gradients keep going through autograd.
+        if self.world_size > 1 and torch.cuda.is_available():
+            from . import ops
+            # cooperative kernels start only when all their CTAs fit: leave 32 SMs to the NCCL kernels that run beside backward
+            ops.coop_cta_limit = max(32, torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count - 32)
         direct = not (self.world_size > 1 and self.overlap_grad_sync)
         for o in self.optimizers:
             if hasattr(o, 'flat_grad'):
