@@ -66,6 +66,26 @@ def test_fir_strip_kernel(V, dtype, n, c, h, w, pad):
     assert C.rel_err(yg.float(), y) < tol and C.rel_err(xg.grad.float(), xo.grad) < tol
 
 
+@pytest.mark.parametrize('dtype,n,c,h,w', [(torch.float32, 2, 8, 18, 22), (torch.float32, 1, 4, 70, 10), (torch.bfloat16, 2, 64, 40, 36),
+                                           (torch.bfloat16, 1, 128, 34, 16), (torch.float32, 2, 16, 6, 4), (torch.bfloat16, 3, 8, 64, 64)])
+def test_fir_down2_strip_kernels(V, dtype, n, c, h, w):
+    """the discriminator's skip path: upfirdn2d(x, f, down=2, padding=1) forward and adjoint on the strip / cp.async-ring kernels"""
+    from vqvae_vqgan_pytorch_lightning_b200 import ops_gan
+    torch.manual_seed(7)
+    x = torch.randn(n, c, h, w)
+    x = r16(x) if dtype == torch.bfloat16 else x
+    xo = x.clone().requires_grad_()
+    y = fir_ref(xo, 1)[:, :, ::2, ::2]
+    go = torch.randn_like(y); go = r16(go) if dtype == torch.bfloat16 else go
+    y.backward(go)
+    xg = cl(x).to(dtype).requires_grad_()
+    yg = ops_gan.fir4(xg, 1, 2)
+    yg.backward(cl(go).to(dtype))
+    tol = 4e-3 if dtype == torch.bfloat16 else 1e-6
+    assert yg.shape == y.shape
+    assert C.rel_err(yg.float(), y) < tol and C.rel_err(xg.grad.float(), xo.grad) < tol
+
+
 @pytest.mark.parametrize('n,c,h,w', [(2, 16, 16, 16), (1, 64, 34, 20), (2, 8, 6, 10)])
 def test_fir_s2d_forms(V, n, c, h, w):
     from vqvae_vqgan_pytorch_lightning_b200.lib import BF16, call, ptr, stream

@@ -326,6 +326,213 @@ int launch_fir4_strip(const void* x, void* y, int N, int H, int W, int C, int OH
     return 0;
 }
 
+
+// ---- down = 2 (the discriminator's skip path: upfirdn2d(x, f, down=2, padding=1)), the same strip / cp.async-ring scheme ---------
+// Forward: y[oh][ow] = sum_{a,b} f[a] f[b] x[2 oh - pad + a][2 ow - pad + b].  One thread = V channels x 2 output columns (6 input
+// columns) walking down a strip; input row r feeds output row r >> 1 (tap r & 1) and the one before it (tap (r & 1) + 2): two
+// output rows in flight.
+template <typename T>
+__global__ void __launch_bounds__(FIR_THREADS) fir4_down2_strip_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C,
+                                                                       int OH, int OW, int pad, int RH) {
+    constexpr int V = Vec<T>::N, CW = 2, NC = 2 * CW + 2, D = FIR_DEPTH;
+    extern __shared__ uint4 fir_ring_raw[];
+    uint4 (*ring)[NC][FIR_THREADS] = reinterpret_cast<uint4 (*)[NC][FIR_THREADS]>(fir_ring_raw);
+    const int tid = threadIdx.x;
+    const int Cv = C / V;
+    const int nstrips = (OH + RH - 1) / RH, ncb = (OW + CW - 1) / CW;
+    const int64_t total = (int64_t)N * nstrips * ncb * Cv;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + tid; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int cv = (int)(i % Cv); int64_t r_ = i / Cv;
+        const int cb = (int)(r_ % ncb); r_ /= ncb;
+        const int strip = (int)(r_ % nstrips); const int n = (int)(r_ / nstrips);
+        const int oh0 = strip * RH, ow0 = cb * CW;
+        int rows = OH - oh0; if (rows > RH) rows = RH;
+        const int nin = 2 * rows + 2;                               // input rows 2 oh0 - pad .. + 2 rows + 1
+        auto request = [&](int r) {
+            const int ih = 2 * oh0 - pad + r;
+            if (r < nin && ih >= 0 && ih < H) {
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    const int iw = 2 * ow0 - pad + c;
+                    if (iw >= 0 && iw < W) fir_cp_async16(&ring[r % D][c][tid], x + (((int64_t)n * H + ih) * W + iw) * C + cv * V);
+                    else ring[r % D][c][tid] = make_uint4(0u, 0u, 0u, 0u);
+                }
+            }
+            fir_cp_commit();
+        };
+#pragma unroll
+        for (int r = 0; r < D; ++r) request(r);
+        float acc[2][CW][V];
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int j = 0; j < CW; ++j)
+#pragma unroll
+                for (int u = 0; u < V; ++u) acc[a][j][u] = 0.f;
+        for (int r4 = 0; r4 < nin; r4 += 4) {
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+                const int r = r4 + rr;
+                if (r < nin) {
+                    fir_cp_wait<D - 1>();
+                    const int ih = 2 * oh0 - pad + r;
+                    // taps: output (r >> 1) gets f[r & 1] (slot (rr >> 1) & 1), output (r >> 1) - 1 gets f[(r & 1) + 2] (the other slot)
+                    constexpr float F[4] = {0.125f, 0.375f, 0.375f, 0.125f};
+                    const float fa = F[rr & 1], fb = F[(rr & 1) + 2];
+                    if (ih >= 0 && ih < H) {
+                        float v[NC][V];
+#pragma unroll
+                        for (int c = 0; c < NC; ++c) unpack_vec<T>(ring[r % D][c][tid], v[c]);
+#pragma unroll
+                        for (int j = 0; j < CW; ++j)
+#pragma unroll
+                            for (int u = 0; u < V; ++u) {
+                                const float hs = fmaf(0.375f, v[2 * j + 1][u] + v[2 * j + 2][u], 0.125f * (v[2 * j][u] + v[2 * j + 3][u]));
+                                acc[(rr >> 1) & 1][j][u] = fmaf(fa, hs, acc[(rr >> 1) & 1][j][u]);
+                                acc[((rr >> 1) + 1) & 1][j][u] = fmaf(fb, hs, acc[((rr >> 1) + 1) & 1][j][u]);
+                            }
+                    }
+                    request(r + D);
+                    if (rr & 1) {                                   // odd input row r = 2 o + 3 completes output o = (r - 3) / 2 (other slot)
+                        const int oh = oh0 + ((r - 3) >> 1);
+#pragma unroll
+                        for (int j = 0; j < CW; ++j) {
+                            const int ow = ow0 + j;
+                            if (r >= 3 && ow < OW) stvec<T>(y + (((int64_t)n * OH + oh) * OW + ow) * C + cv * V, acc[((rr >> 1) + 1) & 1][j]);
+#pragma unroll
+                            for (int u = 0; u < V; ++u) acc[((rr >> 1) + 1) & 1][j][u] = 0.f;
+                        }
+                    }
+                }
+            }
+        }
+        fir_cp_wait<0>();
+    }
+}
+
+// Adjoint for pad = 1: dx[h][w] = sum over the taps of matching parity of f[a] f[b] dy[(h + 1 - a) / 2][(w + 1 - b) / 2].  Per axis:
+//   D[2k] = f1 dy[k] + f3 dy[k-1],   D[2k+1] = f0 dy[k+1] + f2 dy[k].
+// One thread = V channels x 4 output columns 4q .. 4q+3 (dy columns 2q-1 .. 2q+2) walking down the dy rows of a strip: dy row m
+// feeds output rows 2m-1 (f0), 2m (f1), 2m+1 (f2), 2m+2 (f3) -- four output rows in flight -- and completes 2m-1 and 2m.
+template <typename T>
+__global__ void __launch_bounds__(FIR_THREADS) fir4_up2_adjoint_strip_kernel(const T* __restrict__ dy, T* __restrict__ dx, int N, int H, int W, int C,
+                                                                             int OH, int OW, int RM) {
+    constexpr int V = Vec<T>::N, NC = 4, D = FIR_DEPTH;
+    extern __shared__ uint4 fir_ring_raw[];
+    uint4 (*ring)[NC][FIR_THREADS] = reinterpret_cast<uint4 (*)[NC][FIR_THREADS]>(fir_ring_raw);
+    const int tid = threadIdx.x;
+    const int Cv = C / V;
+    const int MH = (H + 1) / 2;                                      // dy rows m = 0 .. MH cover the output rows (row m completes 2m-1, 2m)
+    const int nstrips = (MH + RM) / RM, ncb = (W + 3) / 4;           // strips of RM input rows over m in [0, MH]
+    const int64_t total = (int64_t)N * nstrips * ncb * Cv;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + tid; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int cv = (int)(i % Cv); int64_t r_ = i / Cv;
+        const int cb = (int)(r_ % ncb); r_ /= ncb;
+        const int strip = (int)(r_ % nstrips); const int n = (int)(r_ / nstrips);
+        const int m_lo = strip * RM;                                 // this strip OWNS output rows 2 m_lo - 1 .. 2 (m_lo + cnt - 1)
+        int cnt = MH + 1 - m_lo; if (cnt > RM) cnt = RM;
+        const int w0 = cb * 4, q2 = cb * 2;
+        // input rows m_lo - 1 .. m_lo + cnt - 1 (the first one only contributes its f2 / f3 taps to the first owned rows)
+        const int nin = cnt + 1;
+        auto request = [&](int r) {
+            const int m = m_lo - 1 + r;
+            if (r < nin && m >= 0 && m < OH) {
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    const int k = q2 - 1 + c;
+                    if (k >= 0 && k < OW) fir_cp_async16(&ring[r % D][c][tid], dy + (((int64_t)n * OH + m) * OW + k) * C + cv * V);
+                    else ring[r % D][c][tid] = make_uint4(0u, 0u, 0u, 0u);
+                }
+            }
+            fir_cp_commit();
+        };
+#pragma unroll
+        for (int r = 0; r < D; ++r) request(r);
+        // slot s holds output row h with (h - (2 m_lo - 1)) & 3 == s ; relative row t = h - (2 m_lo - 1)
+        float acc[4][4][V];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int u = 0; u < V; ++u) acc[a][j][u] = 0.f;
+        for (int r2 = 0; r2 < nin; r2 += 2) {
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                const int r = r2 + rr;
+                if (r < nin) {
+                    fir_cp_wait<D - 1>();
+                    const int m = m_lo - 1 + r;
+                    // relative output rows fed by input row r: 2r-2 (f0), 2r-1 (f1), 2r (f2), 2r+1 (f3); with r = r2 + rr and r2 even the
+                    // slots are static: (2rr-2)&3, (2rr-1)&3, (2rr)&3, (2rr+1)&3
+                    if (m >= 0 && m < OH) {
+                        float v[NC][V];
+#pragma unroll
+                        for (int c = 0; c < NC; ++c) unpack_vec<T>(ring[r % D][c][tid], v[c]);
+#pragma unroll
+                        for (int u = 0; u < V; ++u) {
+                            float hsv[4];
+                            hsv[0] = fmaf(0.375f, v[1][u], 0.125f * v[0][u]);        // D[4q]   = f1 dy[2q]   + f3 dy[2q-1]
+                            hsv[1] = fmaf(0.125f, v[2][u], 0.375f * v[1][u]);        // D[4q+1] = f0 dy[2q+1] + f2 dy[2q]
+                            hsv[2] = fmaf(0.375f, v[2][u], 0.125f * v[1][u]);        // D[4q+2] = f1 dy[2q+1] + f3 dy[2q]
+                            hsv[3] = fmaf(0.125f, v[3][u], 0.375f * v[2][u]);        // D[4q+3] = f0 dy[2q+2] + f2 dy[2q+1]
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                acc[(2 * rr + 2) & 3][j][u] = fmaf(0.125f, hsv[j], acc[(2 * rr + 2) & 3][j][u]);   // row 2r-2: f0
+                                acc[(2 * rr + 3) & 3][j][u] = fmaf(0.375f, hsv[j], acc[(2 * rr + 3) & 3][j][u]);   // row 2r-1: f1
+                                acc[(2 * rr + 0) & 3][j][u] = fmaf(0.375f, hsv[j], acc[(2 * rr + 0) & 3][j][u]);   // row 2r  : f2
+                                acc[(2 * rr + 1) & 3][j][u] = fmaf(0.125f, hsv[j], acc[(2 * rr + 1) & 3][j][u]);   // row 2r+1: f3
+                            }
+                        }
+                    }
+                    request(r + D);
+                    // rows 2r-2 and 2r-1 (relative) are complete; absolute h = 2 m_lo - 1 + t.  Owned rows: t in [0, 2 cnt - 1]
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int t = 2 * r - 2 + e;
+                        const int h = 2 * m_lo - 1 + t;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int w = w0 + j;
+                            if (t >= 0 && h >= 0 && h < H && w < W) stvec<T>(dx + (((int64_t)n * H + h) * W + w) * C + cv * V, acc[(2 * rr + 2 + e) & 3][j]);
+#pragma unroll
+                            for (int u = 0; u < V; ++u) acc[(2 * rr + 2 + e) & 3][j][u] = 0.f;
+                        }
+                    }
+                }
+            }
+        }
+        fir_cp_wait<0>();
+    }
+}
+
+template <typename T>
+int launch_fir4_down2_strip(const void* x, void* y, int N, int H, int W, int C, int OH, int OW, int pad, cudaStream_t st) {
+    const int64_t per_row_strip = (int64_t)N * ((OW + 1) / 2) * (C / Vec<T>::N);
+    int RH = 16;
+    while (RH > 4 && per_row_strip * ((OH + RH - 1) / RH) < (int64_t)148 * 2048) RH >>= 1;
+    const int64_t total = per_row_strip * ((OH + RH - 1) / RH);
+    int64_t blocks = (total + FIR_THREADS - 1) / FIR_THREADS; if (blocks > 148 * 64) blocks = 148 * 64; if (blocks < 1) blocks = 1;
+    const size_t smem = (size_t)FIR_DEPTH * 6 * FIR_THREADS * sizeof(uint4);
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(fir4_down2_strip_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+    fir4_down2_strip_kernel<T><<<(unsigned)blocks, FIR_THREADS, smem, st>>>((const T*)x, (T*)y, N, H, W, C, OH, OW, pad, RH);
+    return 0;
+}
+
+template <typename T>
+int launch_fir4_up2_adjoint_strip(const void* dy, void* dx, int N, int H, int W, int C, int OH, int OW, cudaStream_t st) {
+    const int MH = (H + 1) / 2;
+    const int64_t per_row_strip = (int64_t)N * ((W + 3) / 4) * (C / Vec<T>::N);
+    int RM = 16;
+    while (RM > 4 && per_row_strip * ((MH + RM) / RM) < (int64_t)148 * 2048) RM >>= 1;
+    const int64_t total = per_row_strip * ((MH + RM) / RM);
+    int64_t blocks = (total + FIR_THREADS - 1) / FIR_THREADS; if (blocks > 148 * 64) blocks = 148 * 64; if (blocks < 1) blocks = 1;
+    const size_t smem = (size_t)FIR_DEPTH * 4 * FIR_THREADS * sizeof(uint4);
+    fir4_up2_adjoint_strip_kernel<T><<<(unsigned)blocks, FIR_THREADS, smem, st>>>((const T*)dy, (T*)dx, N, H, W, C, OH, OW, RM);
+    return 0;
+}
+
 // y[n,oh,ow,:] = x[n, 2*oh+off, 2*ow+off, :]
 template <typename T>
 __global__ void decimate2_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int OH, int OW, int off) {
@@ -371,6 +578,12 @@ int vqb_fir4_fwd_vec(const void* x, void* y, int dtype, int N, int H, int W, int
         VQB_CHECK_LAUNCH("fir4_strip");
         return VQB_OK;
     }
+    if (use_strip && down == 2) {
+        if (dtype == VQB_BF16) launch_fir4_down2_strip<bf16>(x, y, N, H, W, C, OH, OW, pad, st);
+        else launch_fir4_down2_strip<float>(x, y, N, H, W, C, OH, OW, pad, st);
+        VQB_CHECK_LAUNCH("fir4_down2_strip");
+        return VQB_OK;
+    }
     static const int use_patch = getenv("VQB_FIR_PATCH") ? atoi(getenv("VQB_FIR_PATCH")) : 1;
     if (use_patch && (down == 1 || down == 2)) {
         if (dtype == VQB_BF16) launch_fir4_patch<bf16>(x, y, N, H, W, C, OH, OW, pad, down, st);
@@ -390,6 +603,12 @@ int vqb_fir4_bwd_vec(const void* dy, void* dx, int dtype, int N, int H, int W, i
         if (dtype == VQB_BF16) launch_fir4_strip<bf16>(dy, dx, N, OH, OW, C, H, W, 3 - pad, 0, 0, st);
         else launch_fir4_strip<float>(dy, dx, N, OH, OW, C, H, W, 3 - pad, 0, 0, st);
         VQB_CHECK_LAUNCH("fir4_strip(adjoint)");
+        return VQB_OK;
+    }
+    if (use_strip && down == 2 && pad == 1) {
+        if (dtype == VQB_BF16) launch_fir4_up2_adjoint_strip<bf16>(dy, dx, N, H, W, C, OH, OW, st);
+        else launch_fir4_up2_adjoint_strip<float>(dy, dx, N, H, W, C, OH, OW, st);
+        VQB_CHECK_LAUNCH("fir4_up2_adjoint_strip");
         return VQB_OK;
     }
     static const int use_patch = getenv("VQB_FIR_PATCH") ? atoi(getenv("VQB_FIR_PATCH")) : 1;
