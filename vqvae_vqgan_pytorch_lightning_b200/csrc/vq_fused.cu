@@ -35,7 +35,9 @@ constexpr int TN = 256;          // codes per accumulator tile (128 staged per C
 constexpr int TK = 64;           // k elements per shared-memory tile row (128 bytes)
 constexpr int NTH = 320;         // warp 0 TMA, warp 1 MMA, warps 2-9 prologue / scan / exact / finish
 constexpr int ESTAGES = 6;
-constexpr int CAP = 16;          // candidate-list entries per (row, column half)
+constexpr int CAP = 32;          // candidate-list entries per (row, column half): 16 overflowed on the reference's INITIAL codebook
+                                 // (U(+-1/K) codes against O(1) latents: dozens of codes within the error band at K = 8192 -- 200
+                                 // of 8192 rows took the exact full scan, 1.7 ms in the first steps of the K = 8192 configuration)
 constexpr int Z_TILE = TM * TK * 2;          // 16 KB
 constexpr int E_TILE = (TN / 2) * TK * 2;    // 16 KB (this CTA's half)
 
@@ -481,12 +483,14 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmEh, const FusedParams p) {
             bool have = false;
             if (((ca | cb2) >> 31) == 0) {
                 const float bound = fminf(rbest[rw], rbest[TM + rw]) + tie_threshold(zsq_s[rw], emax, sqrt_d);
+              for (int cbase = 0; cbase < ca + cb2; cbase += 32) {       // the concatenated list of both halves, 32 entries per pass
                 float dme = INFINITY; int cme = 0x7fffffff;
-                if (lane < ca) { dme = cand_d[lane * 256 + rw]; cme = cand_c[lane * 256 + rw]; }
-                else if (lane < ca + cb2) { dme = cand_d[(lane - ca) * 256 + TM + rw]; cme = cand_c[(lane - ca) * 256 + TM + rw]; }
+                const int li = cbase + lane;
+                if (li < ca) { dme = cand_d[li * 256 + rw]; cme = cand_c[li * 256 + rw]; }
+                else if (li < ca + cb2) { dme = cand_d[(li - ca) * 256 + TM + rw]; cme = cand_c[(li - ca) * 256 + TM + rw]; }
                 const bool keep = dme <= bound;
                 unsigned kmask = __ballot_sync(0xffffffffu, keep);
-                have = kmask != 0;
+                have = have || kmask != 0;
                 // The fp32 dot product is ONE sequential FMA chain (bit-exactness with the strict kernel), so a lane walking global
                 // memory pays an L2 round trip every few steps (ncu: 5 us per row).  Instead the warp stages the z row and up to
                 // four candidate rows in shared memory with coalesced loads issued back to back (the operand tiles are dead by
@@ -530,6 +534,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmEh, const FusedParams p) {
                     }
                     __syncwarp();
                 }
+              }
             }
             if (!have) {
                 // list overflow (more near-ties than it holds: duplicated codes) or no finite approximate distance at all
