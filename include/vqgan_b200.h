@@ -122,6 +122,12 @@ int vqb_conv2d_fwd_gn(int impl, const void* x, int x_dtype, const void* wp, cons
                       int act, float act_alpha, float gain, double* gn_sums, int gn_groups, void* stream);
 int vqb_conv2d_fwd_gn_supported(int impl, int N, int H, int W, int Ci, int Co, int KH, int KW, int pad, int stride,
                                 int gn_groups);
+/* Narrow-OUTPUT 3x3 'same' convolution, Co <= 3 (decoder.conv_out 128 -> 3 + tanh, autoencoder.py:170,178), bf16 x:
+ * one [128 halo pixels] x [32 >= 9 Co] x [Ci] tensor-core GEMM per 16 x 8 halo tile gives the per-tap partial products, the epilogue
+ * shift-adds them over the 3x3 neighbourhood for the 14 x 6 interior (+ bias, activation, gain).  wp = [32][Ci] bf16 with row
+ * (tap * Co + co) = w[co][:, tap], tap = kh * 3 + kw, remaining rows zero.  y fp32 or bf16 NHWC [N,H,W,Co]. */
+int vqb_conv2d_fwd_narrowout(const void* x, const void* wp, const float* bias, void* y, int y_dtype, int N, int H, int W, int Ci,
+                             int Co, int act, float act_alpha, float gain, void* stream);
 /* T x T-tap sub-convolution on the 3x3 halo kernels (tcgen05, bf16 operands):
  *     y[n,h,w,co] = act(bias + sum_{a,b<T} sum_ci x[n, h+off+a, w+off+b, ci] * wp[co][(a*T+b)*Ci + ci]),  x zero outside its Hx x Wx pixels,
  * H x W = output size (may differ from the input's), T in {2,3}, -1 <= off, off + T <= 2.  It carries the discriminator's stride-2

@@ -150,3 +150,43 @@ def test_conv_epilogue_groupnorm_statistics(V, n, h, w, ci, co, k, bias, res, f3
     y2 = y.detach().clone()
     o2 = V.ops.group_norm_act(y2, gamma, beta)
     assert C.rel_err(o1.float(), o2.float()) < (1e-5 if f32out else 6e-3)
+
+
+@pytest.mark.parametrize('n,ci,h,w,co,act', [(2, 128, 32, 32, 3, 'tanh'), (1, 128, 19, 21, 3, 'none'), (2, 128, 16, 16, 1, 'tanh'),
+                                              (1, 256, 40, 28, 3, 'tanh'), (3, 128, 64, 64, 2, 'none')])
+def test_narrow_output_head_partial_products(n, ci, h, w, co, act):
+    """decoder.conv_out-like heads (Co <= 3, autoencoder.py:170,178) on the per-tap-partials kernel (vqb_conv2d_fwd_narrowout): forward
+    against fp32 torch on bf16-rounded operands (fp32 output: accumulation order only), and the module path with its backward against
+    the N = 16 halo kernel it replaces"""
+    import torch.nn.functional as F
+    import vqvae_vqgan_pytorch_lightning_b200 as pkg
+    from vqvae_vqgan_pytorch_lightning_b200 import ops
+    from vqvae_vqgan_pytorch_lightning_b200.lib import ACT_NONE, ACT_TANH
+    pkg.lib.load()
+    if not pkg.lib.load().vqb_device_supports_tcgen05():
+        pytest.skip('needs sm_100')
+    pkg.set_precision('fast')
+    try:
+        torch.manual_seed(11)
+        x = torch.randn(n, ci, h, w).bfloat16().float()
+        wt = (torch.randn(co, ci, 3, 3) / (3 * ci ** 0.5)).bfloat16().float()
+        b = torch.randn(co) * 0.1
+        ref = F.conv2d(x, wt, b, padding=1)
+        ref = torch.tanh(ref) if act == 'tanh' else ref
+        outs = {}
+        for flag in (True, False):
+            ops._narrowout = flag
+            xg = x.cuda().contiguous(memory_format=torch.channels_last).bfloat16().requires_grad_()
+            wg = torch.nn.Parameter(wt.cuda().clone())
+            bg = torch.nn.Parameter(b.cuda().clone())
+            y = ops.conv2d(xg, wg, bg, None, pad=1, act=ACT_TANH if act == 'tanh' else ACT_NONE, out_dtype=torch.float32)
+            y.backward(torch.ones_like(y))
+            outs[flag] = (y.detach().float().cpu(), xg.grad.float().cpu(), wg.grad.cpu().clone())
+        err = float((outs[True][0] - ref).norm() / ref.norm())
+        assert err < 1e-4, err
+        assert float((outs[True][0] - outs[False][0]).norm() / ref.norm()) < 1e-4
+        assert torch.equal(outs[True][1], outs[False][1]) or float((outs[True][1] - outs[False][1]).norm() / outs[False][1].norm()) < 1e-2
+        assert float((outs[True][2] - outs[False][2]).norm() / outs[False][2].norm()) < 1e-2
+    finally:
+        ops._narrowout = None
+        pkg.set_precision('strict')

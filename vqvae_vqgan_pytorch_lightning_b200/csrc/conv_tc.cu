@@ -957,6 +957,158 @@ conv_fwd_tc_halo_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Narrow-OUTPUT 3x3 convolution (Co <= 3: the decoder's 128 -> 3 image head with tanh, autoencoder.py:170,178): per-tap partial
+// products + shift-add.  With N = 16 the halo kernel issued 72 UMMAs per 128-pixel tile and a UMMA costs the same ~128 cycles at
+// N = 16 as at N = 256 (1.2-1.4 ms for 29 GFLOP).  Here ONE small GEMM per tile computes, for every pixel q of a 16 x 8 HALO
+// tile, P[q][(tap, co)] = sum_ci x[q][ci] w[co][ci][tap] (M = 128 pixels, N = 32 >= 9 Co, K = Ci: Ci / 16 UMMAs), and the
+// epilogue forms y[h][w][co] = act(bias + sum_tap P[(h + kh - 1, w + kw - 1)][(tap, co)]) for the 14 x 6 interior from a
+// shared-memory copy of P.  The packed weight ([32][Ci], rows (tap * Co + co), zero-padded) stays resident in shared memory.
+// ---------------------------------------------------------------------------------------------------
+struct NarrowOutParams {
+    int N, H, W, Ci, Co;
+    int tiles_w, tiles_h, num_tiles, cchunks, stages;
+    const float* bias;
+    void* y;
+    int y_f32, act;
+    float alpha, gain;
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+conv_fwd_tc_narrowout_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const NarrowOutParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    constexpr int TWH = 16, THH = 8;                       // halo tile: 16 x 8 pixels = 128 rows of the A operand
+    constexpr int OW_T = TWH - 2, OH_T = THH - 2;          // interior: 14 x 6 outputs
+    constexpr int PN = 32, PP = 33;                        // P columns (UMMA N) and the padded shared-memory pitch
+    const int a_tile = BM * BK * 2;                        // 16 KB per (tile, 64-channel chunk)
+    const int w_tile = PN * BK * 2;                        // 4 KB per chunk of the resident weight
+    uint8_t* smemW = smem;
+    uint8_t* smemA = smem + (size_t)p.cchunks * 4096;      // (4 KB tiles keep the 1024-byte alignment)
+    float* ptile = reinterpret_cast<float*>(smemA + (size_t)p.stages * a_tile);        // [2][128][PP]
+    uint64_t* full = reinterpret_cast<uint64_t*>(ptile + 2 * BM * PP);
+    uint64_t* empty = full + p.stages;
+    uint64_t* wfull = empty + p.stages;
+    uint64_t* tfull = wfull + 1;                           // [2]
+    uint64_t* tempty = tfull + 2;                          // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmA);
+        ptx::prefetch_tmap(&tmB);
+        for (int i = 0; i < p.stages; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 1); }
+        ptx::mbar_init(wfull, 1);
+        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull[i], 1); ptx::mbar_init(&tempty[i], 4); }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) ptx::tmem_alloc(tmem_slot, 64);         // two accumulators of 32 columns
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            if (blockIdx.x < p.num_tiles) {
+                ptx::mbar_expect_tx(wfull, (uint32_t)(p.cchunks * w_tile));
+                for (int cc = 0; cc < p.cchunks; ++cc) ptx::tma_load_2d(smemW + (size_t)cc * w_tile, &tmB, wfull, cc * BK, 0);
+            }
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int twi = tile % p.tiles_w, t2 = tile / p.tiles_w, thi = t2 % p.tiles_h, n = t2 / p.tiles_h;
+                for (int cc = 0; cc < p.cchunks; ++cc) {
+                    ptx::mbar_wait(&empty[stage], phase ^ 1);
+                    ptx::mbar_expect_tx(&full[stage], (uint32_t)a_tile);
+                    ptx::tma_load_4d(smemA + (size_t)stage * a_tile, &tmA, &full[stage], cc * BK, twi * OW_T - 1, thi * OH_T - 1, n);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = ptx::umma_idesc_bf16(BM, PN, 0, 0);
+            int stage = 0; uint32_t phase = 0;
+            int as = 0; uint32_t aphase = 0;
+            if (blockIdx.x < p.num_tiles) ptx::mbar_wait(wfull, 0);
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                ptx::mbar_wait(&tempty[as], aphase ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * PN);
+                for (int cc = 0; cc < p.cchunks; ++cc) {
+                    ptx::mbar_wait(&full[stage], phase);
+                    ptx::tc_fence_after();
+                    const uint64_t adesc = ptx::umma_smem_desc(ptx::smem_u32(smemA + (size_t)stage * a_tile), 0, 1024);
+                    const uint64_t bdesc = ptx::umma_smem_desc(ptx::smem_u32(smemW + (size_t)cc * w_tile), 0, 1024);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k)
+                        ptx::umma_bf16(d_tmem, adesc + (uint64_t)(k * UMMA_K * 2 / 16), bdesc + (uint64_t)(k * UMMA_K * 2 / 16), idesc,
+                                       (cc | k) != 0 ? 1u : 0u);
+                    ptx::umma_commit(&empty[stage]);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+                ptx::umma_commit(&tfull[as]);
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+        }
+    } else {
+        // epilogue warps 2..5: TMEM lane = halo pixel (row-major 8 x 16)
+        const int quarter = warp & 3;
+        const int q = quarter * 32 + lane;                 // halo pixel of this thread
+        const int et = (warp - 2) * 32 + lane;             // 0..127: thread index among the epilogue warps
+        int as = 0; uint32_t aphase = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const int twi = tile % p.tiles_w, t2 = tile / p.tiles_w, thi = t2 % p.tiles_h, n = t2 / p.tiles_h;
+            ptx::mbar_wait(&tfull[as], aphase);
+            ptx::tc_fence_after();
+            uint32_t r[32];
+            ptx::tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * PN), r);
+            ptx::tmem_ld_wait();
+            ptx::tc_fence_before();
+            float* pt = ptile + (size_t)as * BM * PP;
+#pragma unroll
+            for (int j = 0; j < 27; ++j) pt[q * PP + j] = __uint_as_float(r[j]);
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tempty[as]);   // the accumulator is free for the tile after next
+            asm volatile("bar.sync 1, 128;" ::: "memory");  // P of the whole halo tile is in shared memory
+            for (int o = et; o < OW_T * OH_T; o += 128) {
+                const int orow = o / OW_T, ocol = o - orow * OW_T;
+                const int h = thi * OH_T + orow, w = twi * OW_T + ocol;
+                if (h < p.H && w < p.W) {
+                    float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                        for (int kw = 0; kw < 3; ++kw) {
+                            const float* src = pt + ((orow + kh) * TWH + (ocol + kw)) * PP + (kh * 3 + kw) * p.Co;
+#pragma unroll
+                            for (int co = 0; co < 3; ++co)
+                                if (co < p.Co) acc[co] += src[co];
+                        }
+                    const int64_t off = (((int64_t)n * p.H + h) * p.W + w) * p.Co;
+#pragma unroll
+                    for (int co = 0; co < 3; ++co)
+                        if (co < p.Co) {
+                            float t = acc[co] + (p.bias ? __ldg(p.bias + co) : 0.f);
+                            t = act_f(t, p.act, p.alpha) * p.gain;
+                            if (p.y_f32) reinterpret_cast<float*>(p.y)[off + co] = t;
+                            else reinterpret_cast<bf16*>(p.y)[off + co] = __float2bfloat16_rn(t);
+                        }
+                }
+            }
+            // (the P buffer `as` is rewritten two tiles later, after another bar.sync of these warps: no second barrier needed)
+            if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, 64);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 struct WgradParams {
     int N, H, W, Ci, Co, KH, KW, pad;
@@ -1463,4 +1615,33 @@ extern "C" int vqb_conv2d_wgrad_sub(const void* x, const void* dy, float* dwp, i
     VQB_CHECK_ARG(Co % 128 == 0, "conv2d_wgrad_sub: Co must be a multiple of 128");
     SubConv sc{Hx, Wx, T, off};
     return conv_wgrad_tc_impl(x, dy, dwp, N, H, W, Ci, Co, 3, 3, 1, as_stream(stream), &sc);
+}
+
+// y = act(conv3x3(x, w) + bias) * gain for Co <= 3 (see conv_fwd_tc_narrowout_kernel); wp = [32][Ci] bf16, row (tap * Co + co) =
+// w[co][:, tap] (tap = kh * 3 + kw), rows >= 9 Co zero
+extern "C" int vqb_conv2d_fwd_narrowout(const void* x, const void* wp, const float* bias, void* y, int y_dtype, int N, int H, int W, int Ci,
+                                        int Co, int act, float act_alpha, float gain, void* stream) {
+    VQB_CHECK_ARG(x && wp && y && N > 0 && H > 0 && W > 0, "conv2d_fwd_narrowout: bad arguments");
+    VQB_CHECK_ARG(Ci % 64 == 0 && Ci <= 512 && Co >= 1 && Co <= 3, "conv2d_fwd_narrowout: needs Ci %% 64 == 0, Ci <= 512, Co <= 3 (got %d, %d)", Ci, Co);
+    VQB_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)wp & 15) == 0, "conv2d_fwd_narrowout: unaligned pointer");
+    NarrowOutParams p;
+    p.N = N; p.H = H; p.W = W; p.Ci = Ci; p.Co = Co;
+    p.tiles_w = (W + 13) / 14; p.tiles_h = (H + 5) / 6;
+    p.num_tiles = p.tiles_w * p.tiles_h * N;
+    p.cchunks = Ci / BK;
+    static const int stages_env = getenv("VQB_NARROW_OUT_STAGES") ? atoi(getenv("VQB_NARROW_OUT_STAGES")) : 0;
+    const size_t fixed = (size_t)p.cchunks * 4096 + (size_t)2 * BM * 33 * 4 + 256 + 1024;
+    p.stages = (int)((SMEM_LIMIT - fixed) / (BM * BK * 2));             // as many 16 KB input boxes in flight as fit (11 at Ci = 128)
+    if (stages_env > 0 && stages_env < p.stages) p.stages = stages_env;
+    if (p.stages > 12) p.stages = 12;
+    p.bias = bias; p.y = y; p.y_f32 = (y_dtype == VQB_F32); p.act = act; p.alpha = act_alpha; p.gain = gain;
+    CUtensorMap tmA, tmB;
+    int rc = make_act_map(&tmA, x, N, H, W, Ci, 16, 8, 1); if (rc) return rc;
+    rc = make_weight_map(&tmB, wp, 32, Ci, 32); if (rc) return rc;
+    size_t smem = fixed + (size_t)p.stages * BM * BK * 2;
+    VQB_CUDA(cudaFuncSetAttribute(conv_fwd_tc_narrowout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+    conv_fwd_tc_narrowout_kernel<<<grid, NTHREADS, smem, as_stream(stream)>>>(tmA, tmB, p);
+    VQB_CHECK_LAUNCH("conv2d_fwd_narrowout");
+    return VQB_OK;
 }

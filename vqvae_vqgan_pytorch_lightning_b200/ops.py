@@ -418,6 +418,34 @@ def gn_fusion_enabled() -> bool:
     return _gn_fusion
 
 
+_narrowout = None
+
+
+def _narrowout_enabled() -> bool:
+    """VQB_NARROW_OUT=0: the 128 -> 3 head on the N = 16 halo kernel (A/B measurements)"""
+    global _narrowout
+    if _narrowout is None:
+        import os
+        _narrowout = os.environ.get('VQB_NARROW_OUT', '1') != '0'
+    return _narrowout
+
+
+def _packed_narrowout_weight(weight: torch.Tensor, w_scale: float) -> torch.Tensor:
+    """[co <= 3, ci, 3, 3] -> [32][ci] bf16, row (tap * co + c) = w[c][:, tap] (vqb_conv2d_fwd_narrowout); persistent buffer,
+    refreshed once per weights epoch"""
+    cache = getattr(weight, '_vqb_narrowout', None)
+    if cache is not None and cache['epoch'] == _weights_epoch and cache['scale'] == w_scale and cache['ptr'] == weight.data_ptr():
+        return cache['wp']
+    co, ci = weight.shape[0], weight.shape[1]
+    rows = (weight.detach().float() * w_scale).permute(2, 3, 0, 1).reshape(9 * co, ci)
+    if cache is None or cache['wp'].shape != (32, ci) or cache['wp'].device != weight.device:
+        cache = {'wp': torch.zeros(32, ci, dtype=torch.bfloat16, device=weight.device)}
+        weight._vqb_narrowout = cache
+    cache['wp'][:9 * co].copy_(rows)
+    cache.update(epoch=_weights_epoch, scale=w_scale, ptr=weight.data_ptr())
+    return cache['wp']
+
+
 def _narrow_route(prec: Precision, ci: int, co: int, kh: int, kw: int, pad: int, stride: int, frozen: bool = False) -> Optional[str]:
     """fast mode: the RGB heads (3x3, pad 1) ride the tensor cores as a 64-channel 1x1 implicit GEMM over an im2col tensor
     ('in': narrow input, e.g. encoder.conv_in 3->128; 'out': narrow output, e.g. decoder.conv_out 128->3, whose dgrad and
@@ -520,7 +548,14 @@ class Conv2dFn(torch.autograd.Function):
                 return zero_arena.zeros(n_ * gn_groups * 2, torch.float64, x.device)
             return None
 
-        if route == 'in':
+        if (route == 'out' and impl == 1 and x.dtype == torch.bfloat16 and residual is None and ci <= 512 and co <= 3 and
+                (kh, kw, pad, stride) == (3, 3, 1, 1) and _narrowout_enabled()):
+            # the 3-channel image head: per-tap partial products on the tensor cores + shift-add epilogue (one small GEMM per tile
+            # instead of 72 N = 16 UMMAs)
+            wp = _packed_narrowout_weight(weight, w_scale)
+            y = empty_nhwc(n_, co, h_, w_, out_dtype, x.device)
+            call('vqb_conv2d_fwd_narrowout', ptr(x), ptr(wp), ptr(b), ptr(y), dt(y), n_, h_, w_, ci, co, act, alpha, gain, stream())
+        elif route == 'in':
             wp = _packed_weight(weight, 4, torch.bfloat16, w_scale)                  # [co][64], K zero-padded
             sums = gn_buffer(1, 64, 1, 1, 0)
             y = _conv_fwd_raw(1, _im2col64(x), wp, b, residual, out_dtype, 64, co, 1, 1, 0, 1, act, alpha, gain, sums, gn_groups)
