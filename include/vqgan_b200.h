@@ -128,6 +128,12 @@ int vqb_conv2d_fwd_gn_supported(int impl, int N, int H, int W, int Ci, int Co, i
  * (tap * Co + co) = w[co][:, tap], tap = kh * 3 + kw, remaining rows zero.  y fp32 or bf16 NHWC [N,H,W,Co]. */
 int vqb_conv2d_fwd_narrowout(const void* x, const void* wp, const float* bias, void* y, int y_dtype, int N, int H, int W, int Ci,
                              int Co, int act, float act_alpha, float gain, void* stream);
+/* Narrow-INPUT 3x3 'same' convolution, Ci == 3 (encoder.conv_in 3 -> 128, autoencoder.py:114; LPIPS-VGG conv1_1 3 -> 64): the A operand
+ * [128 pixels][K = 27 -> 64] is built in shared memory by producer warps straight from the NHWC image (fp32 or bf16, rounded to bf16) --
+ * no 64-channel im2col tensor in HBM.  wp = mode-4 packed weight [Co][64] of vqb_pack_conv_weight; common bias / activation /
+ * residual epilogue; Co a multiple of 64. */
+int vqb_conv2d_fwd_narrowin(const void* x, int x_dtype, const void* wp, const float* bias, const void* residual, void* y, int y_dtype,
+                            int N, int H, int W, int Ci, int Co, int act, float act_alpha, float gain, void* stream);
 /* T x T-tap sub-convolution on the 3x3 halo kernels (tcgen05, bf16 operands):
  *     y[n,h,w,co] = act(bias + sum_{a,b<T} sum_ci x[n, h+off+a, w+off+b, ci] * wp[co][(a*T+b)*Ci + ci]),  x zero outside its Hx x Wx pixels,
  * H x W = output size (may differ from the input's), T in {2,3}, -1 <= off, off + T <= 2.  It carries the discriminator's stride-2

@@ -190,3 +190,42 @@ def test_narrow_output_head_partial_products(n, ci, h, w, co, act):
     finally:
         ops._narrowout = None
         pkg.set_precision('strict')
+
+
+@pytest.mark.parametrize('n,h,w,co,dtype,act', [(2, 32, 32, 128, torch.float32, 'none'), (1, 19, 21, 128, torch.bfloat16, 'none'),
+                                                 (2, 16, 16, 64, torch.bfloat16, 'relu'), (3, 64, 48, 128, torch.float32, 'none'),
+                                                 (1, 8, 8, 256, torch.float32, 'none')])
+def test_narrow_input_head_in_kernel_im2col(n, h, w, co, dtype, act):
+    """encoder.conv_in / VGG conv1_1-like heads (Ci = 3) with the A operand built inside the kernel (vqb_conv2d_fwd_narrowin) against
+    fp32 torch on bf16-rounded operands, and against the im2col route it replaces (same rounding points: fp32 outputs equal to
+    accumulation order)"""
+    import torch.nn.functional as F
+    import vqvae_vqgan_pytorch_lightning_b200 as pkg
+    from vqvae_vqgan_pytorch_lightning_b200 import ops
+    from vqvae_vqgan_pytorch_lightning_b200.lib import ACT_NONE, ACT_RELU
+    pkg.lib.load()
+    if not pkg.lib.load().vqb_device_supports_tcgen05():
+        pytest.skip('needs sm_100')
+    pkg.set_precision('fast')
+    try:
+        torch.manual_seed(12)
+        x = torch.randn(n, 3, h, w)
+        x16 = x.bfloat16().float()
+        wt = (torch.randn(co, 3, 3, 3) / 27 ** 0.5).bfloat16().float()
+        b = torch.randn(co) * 0.1
+        ref = F.conv2d(x16, wt, b, padding=1)
+        ref = torch.relu(ref) if act == 'relu' else ref
+        outs = {}
+        for flag in (True, False):
+            ops._narrowin = flag
+            xg = (x16 if dtype == torch.bfloat16 else x).cuda().contiguous(memory_format=torch.channels_last).to(dtype)
+            wg = torch.nn.Parameter(wt.cuda().clone(), requires_grad=(co % 128 == 0))     # (64-wide heads ride this route only when frozen)
+            bg = torch.nn.Parameter(b.cuda().clone())
+            y = ops.conv2d(xg, wg, bg, None, pad=1, act=ACT_RELU if act == 'relu' else ACT_NONE, out_dtype=torch.float32)
+            outs[flag] = y.detach().float().cpu()
+        err = float((outs[True] - ref).norm() / ref.norm())
+        assert err < 1e-4, err
+        assert float((outs[True] - outs[False]).norm() / ref.norm()) < 1e-4
+    finally:
+        ops._narrowin = None
+        pkg.set_precision('strict')

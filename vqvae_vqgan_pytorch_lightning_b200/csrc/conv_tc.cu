@@ -1109,6 +1109,128 @@ conv_fwd_tc_narrowout_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Narrow-INPUT 3x3 convolution (Ci <= 3: encoder.conv_in 3 -> 128, VGG conv1_1 3 -> 64; autoencoder.py:114, lpips.py): the A
+// operand [128 pixels][K = 9 Ci <= 27, zero-padded to 64] is BUILT in shared memory by four producer warps straight from the
+// image (one pixel row per thread, written in the UMMA K-major SWIZZLE_128B layout), instead of materialising a 64-channel im2col
+// tensor in HBM (537 MB written and read back per call at B = 64) and running a 1x1 convolution over it.  Two UMMA k-steps
+// (K = 32) per tile; the packed weight [Co][64] (mode 4) is resident; the epilogue is the common one.
+// ---------------------------------------------------------------------------------------------------
+constexpr int NTHREADS_NIN = 448;      // TMA / MMA / 8 epilogue warps / 4 producer warps
+
+template <typename TI>
+__global__ void __launch_bounds__(NTHREADS_NIN, 1)
+conv_fwd_tc_narrowin_kernel(const __grid_constant__ CUtensorMap tmB, const FwdParams p, const TI* __restrict__ x, int Cin, int a_stages) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int a_tile = BM * BK * 2;                        // 16 KB
+    const int w_tile = p.BN * BK * 2;                      // one channel tile of the resident weight
+    uint8_t* smemW = smem;
+    uint8_t* smemA = smem + (size_t)p.co_tiles * w_tile;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smemA + (size_t)a_stages * a_tile);
+    uint64_t* empty = full + a_stages;
+    uint64_t* wfull = empty + a_stages;
+    uint64_t* tfull = wfull + 1;                           // [2]
+    uint64_t* tempty = tfull + 2;                          // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // the K columns 9 Cin .. 63 of every A tile are zero and never rewritten: clear the stages once
+    for (int i = threadIdx.x; i < a_stages * a_tile / 16; i += NTHREADS_NIN) reinterpret_cast<uint4*>(smemA)[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmB);
+        for (int i = 0; i < a_stages; ++i) { ptx::mbar_init(&full[i], 4); ptx::mbar_init(&empty[i], 1); }
+        ptx::mbar_init(wfull, 1);
+        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull[i], 1); ptx::mbar_init(&tempty[i], 8); }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) ptx::tmem_alloc(tmem_slot, 256);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the zero fill is visible to the async proxy (UMMA reads)
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0 && blockIdx.x < p.num_tiles) {
+            ptx::mbar_expect_tx(wfull, (uint32_t)(p.co_tiles * w_tile));
+            for (int ct = 0; ct < p.co_tiles; ++ct) ptx::tma_load_2d(smemW + (size_t)ct * w_tile, &tmB, wfull, 0, ct * p.BN);
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = ptx::umma_idesc_bf16(BM, p.BN, 0, 0);
+            int stage = 0; uint32_t phase = 0;
+            int as = 0; uint32_t aphase = 0;
+            if (blockIdx.x < p.num_tiles) ptx::mbar_wait(wfull, 0);
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int ct = tile % p.co_tiles;
+                ptx::mbar_wait(&tempty[as], aphase ^ 1);
+                ptx::mbar_wait(&full[stage], phase);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.BN);
+                const uint64_t adesc = ptx::umma_smem_desc(ptx::smem_u32(smemA + (size_t)stage * a_tile), 0, 1024);
+                const uint64_t bdesc = ptx::umma_smem_desc(ptx::smem_u32(smemW + (size_t)ct * w_tile), 0, 1024);
+#pragma unroll
+                for (int k = 0; k < 2; ++k)                  // K = 32 of the 64 columns (the rest is zero on both sides)
+                    ptx::umma_bf16(d_tmem, adesc + (uint64_t)(k * UMMA_K * 2 / 16), bdesc + (uint64_t)(k * UMMA_K * 2 / 16), idesc, k != 0 ? 1u : 0u);
+                ptx::umma_commit(&empty[stage]);
+                ptx::umma_commit(&tfull[as]);
+                if (++stage == a_stages) { stage = 0; phase ^= 1; }
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+        }
+    } else if (warp < 10) {
+        epilogue_loop(p, tmem_base, tfull, tempty, warp, lane);
+    } else {
+        // ================= A-tile producers: thread = pixel row of the 16 x 8 tile =================
+        const int row = (warp - 10) * 32 + lane;
+        const int wi = row % p.tw, hi = row / p.tw;
+        int stage = 0; uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const int pt = tile / p.co_tiles;
+            const int twi = pt % p.tiles_w, t2 = pt / p.tiles_w, thi = t2 % p.tiles_h, n = t2 / p.tiles_h;
+            const int h = thi * p.th + hi, w = twi * p.tw + wi;
+            // 32 K values: (tap, c) for tap < 9, c < Cin (9 Cin <= 27), zero beyond
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+            if (h < p.H && w < p.W) {
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) {
+                    const int ih = h + tap / 3 - 1, iw = w + tap % 3 - 1;
+                    if (ih >= 0 && ih < p.H && iw >= 0 && iw < p.W) {
+                        const TI* src = x + (((int64_t)n * p.H + ih) * p.W + iw) * Cin;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c)
+                            if (c < Cin) v[tap * 3 + c] = (float)src[c];
+                    }
+                }
+            }
+            ptx::mbar_wait(&empty[stage], phase ^ 1);
+            uint8_t* dst = smemA + (size_t)stage * a_tile + (size_t)row * 128;
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+                uint4 u;
+                __nv_bfloat162* hb = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) hb[e] = __floats2bfloat162_rn(v[ch * 8 + 2 * e], v[ch * 8 + 2 * e + 1]);
+                *reinterpret_cast<uint4*>(dst + ((ch ^ (row & 7)) << 4)) = u;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&full[stage]);
+            if (++stage == a_stages) { stage = 0; phase ^= 1; }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, 256);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 struct WgradParams {
     int N, H, W, Ci, Co, KH, KW, pad;
@@ -1643,5 +1765,43 @@ extern "C" int vqb_conv2d_fwd_narrowout(const void* x, const void* wp, const flo
     int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
     conv_fwd_tc_narrowout_kernel<<<grid, NTHREADS, smem, as_stream(stream)>>>(tmA, tmB, p);
     VQB_CHECK_LAUNCH("conv2d_fwd_narrowout");
+    return VQB_OK;
+}
+
+// y = act(conv3x3(x, w) + bias [+ residual]) * gain for Ci == 3 packed as K index (tap * 3 + c) (see conv_fwd_tc_narrowin_kernel);
+// x NHWC [N,H,W,3] fp32 or bf16 (rounded to bf16 for the tensor cores, as the im2col route does); wp = mode-4 packed weight [Co][64]
+extern "C" int vqb_conv2d_fwd_narrowin(const void* x, int x_dtype, const void* wp, const float* bias, const void* residual, void* y,
+                                       int y_dtype, int N, int H, int W, int Ci, int Co, int act, float act_alpha, float gain, void* stream) {
+    VQB_CHECK_ARG(x && wp && y && N > 0 && H > 0 && W > 0, "conv2d_fwd_narrowin: bad arguments");
+    VQB_CHECK_ARG(Ci == 3 && Co % 64 == 0 && Co <= 512, "conv2d_fwd_narrowin: needs Ci == 3, Co %% 64 == 0, Co <= 512 (got %d, %d)", Ci, Co);
+    VQB_CHECK_ARG(x_dtype == VQB_F32 || x_dtype == VQB_BF16, "conv2d_fwd_narrowin: x must be fp32 or bf16");
+    FwdParams p;
+    p.N = N; p.H = H; p.W = W; p.Ci = 64; p.Co = Co; p.KH = 1; p.KW = 1; p.pad = 0; p.Cx = 64;
+    p.tw = 16; p.th = 8; p.nb = 1; p.MT = 1;
+    p.tiles_w = (W + 15) / 16; p.tiles_h = (H + 7) / 8; p.tiles_n = N;
+    p.BN = (Co % 128 == 0) ? 128 : 64;
+    p.co_tiles = Co / p.BN;
+    p.num_tiles = p.tiles_w * p.tiles_h * N * p.co_tiles;
+    p.stages = 0; p.ksteps = 0; p.cchunks = 1;
+    p.pitch = 0; p.bo_mode = 0; p.a_tile_bytes = 0; p.a_stages = 0; p.b_stages = 0;
+    p.bias = bias; p.residual = residual; p.y = y; p.y_f32 = (y_dtype == VQB_F32); p.act = act; p.narrow = 0;
+    static const int res_prefetch = getenv("VQB_RES_PREFETCH") ? atoi(getenv("VQB_RES_PREFETCH")) : 1;
+    p.res_prefetch = res_prefetch;
+    p.alpha = act_alpha; p.gain = gain; p.gn_sums = nullptr; p.gn_cpg = 0;
+    p.ntaps = 1; p.ktw = 1; p.kh0 = 0; p.kw0 = 0; p.b_resident = 1;
+    CUtensorMap tmB;
+    int rc = make_weight_map(&tmB, wp, Co, 64, p.BN); if (rc) return rc;
+    const int a_stages = 4;
+    size_t smem = (size_t)Co * 128 + (size_t)a_stages * BM * BK * 2 + 256 + 1024;
+    cudaStream_t st = as_stream(stream);
+    int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+    if (x_dtype == VQB_F32) {
+        VQB_CUDA(cudaFuncSetAttribute(conv_fwd_tc_narrowin_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        conv_fwd_tc_narrowin_kernel<float><<<grid, NTHREADS_NIN, smem, st>>>(tmB, p, (const float*)x, Ci, a_stages);
+    } else {
+        VQB_CUDA(cudaFuncSetAttribute(conv_fwd_tc_narrowin_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        conv_fwd_tc_narrowin_kernel<bf16><<<grid, NTHREADS_NIN, smem, st>>>(tmB, p, (const bf16*)x, Ci, a_stages);
+    }
+    VQB_CHECK_LAUNCH("conv2d_fwd_narrowin");
     return VQB_OK;
 }

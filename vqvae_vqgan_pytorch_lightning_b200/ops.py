@@ -430,6 +430,18 @@ def _narrowout_enabled() -> bool:
     return _narrowout
 
 
+_narrowin = None
+
+
+def _narrowin_enabled() -> bool:
+    """VQB_NARROW_IN=0: 3-channel inputs through the im2col tensor + 1x1 convolution (A/B measurements)"""
+    global _narrowin
+    if _narrowin is None:
+        import os
+        _narrowin = os.environ.get('VQB_NARROW_IN', '1') != '0'
+    return _narrowin
+
+
 def _packed_narrowout_weight(weight: torch.Tensor, w_scale: float) -> torch.Tensor:
     """[co <= 3, ci, 3, 3] -> [32][ci] bf16, row (tap * co + c) = w[c][:, tap] (vqb_conv2d_fwd_narrowout); persistent buffer,
     refreshed once per weights epoch"""
@@ -555,6 +567,12 @@ class Conv2dFn(torch.autograd.Function):
             wp = _packed_narrowout_weight(weight, w_scale)
             y = empty_nhwc(n_, co, h_, w_, out_dtype, x.device)
             call('vqb_conv2d_fwd_narrowout', ptr(x), ptr(wp), ptr(b), ptr(y), dt(y), n_, h_, w_, ci, co, act, alpha, gain, stream())
+        elif route == 'in' and ci == 3 and co <= 512 and x.dtype in (torch.float32, torch.bfloat16) and _narrowin_enabled():
+            # the A operand (27 -> 64 im2col columns) is built in shared memory inside the kernel: no im2col tensor in HBM
+            wp = _packed_weight(weight, 4, torch.bfloat16, w_scale)                  # [co][64], K zero-padded
+            y = empty_nhwc(n_, co, h_, w_, out_dtype, x.device)
+            call('vqb_conv2d_fwd_narrowin', ptr(x), dt(x), ptr(wp), ptr(b), ptr(residual), ptr(y), dt(y), n_, h_, w_, ci, co, act, alpha,
+                 gain, stream())
         elif route == 'in':
             wp = _packed_weight(weight, 4, torch.bfloat16, w_scale)                  # [co][64], K zero-padded
             sums = gn_buffer(1, 64, 1, 1, 0)
