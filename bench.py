@@ -135,7 +135,8 @@ class ClockSampler:
                 'samples': len(sm)}
 
 
-CONV_ENTRY_POINTS = ('vqb_conv2d_fwd', 'vqb_conv2d_fwd_gn', 'vqb_conv2d_wgrad', 'vqb_conv2d_fwd_sub', 'vqb_conv2d_wgrad_sub')
+CONV_ENTRY_POINTS = ('vqb_conv2d_fwd', 'vqb_conv2d_fwd_gn', 'vqb_conv2d_wgrad', 'vqb_conv2d_fwd_sub', 'vqb_conv2d_wgrad_sub',
+                     'vqb_conv2d_fwd_narrowin', 'vqb_conv2d_fwd_narrowout')
 
 
 def conv_shape(name, a):
@@ -157,6 +158,12 @@ def conv_shape(name, a):
         if off == 0:      # forward: [N, H, W, Co] from the 4C-channel space-to-depth input
             return ('s2d fwd', 1, n, h, w, ci, co, 3, 2, bool(a[3]), 2.0 * n * h * w * co * (ci // 4) * 9)
         return ('s2d dgrad', 1, n, h, w, ci, co, 3, 2, False, 2.0 * n * (h - 1) * (w - 1) * ci * (co // 4) * 9)
+    if name == 'vqb_conv2d_fwd_narrowin':        # 3 -> Co image head, im2col operand built in the kernel
+        n, h, w, ci, co = a[7:12]
+        return ('fwd narrow-in', 1, n, h, w, ci, co, 3, 1, bool(a[4]), 2.0 * n * h * w * co * ci * 9)
+    if name == 'vqb_conv2d_fwd_narrowout':       # Ci -> 3 image head, per-tap partial products + shift-add
+        n, h, w, ci, co = a[5:10]
+        return ('fwd narrow-out', 1, n, h, w, ci, co, 3, 1, False, 2.0 * n * h * w * co * ci * 9)
     if name == 'vqb_conv2d_wgrad_sub':
         n, hx, wx, h, w, ci, co, t, off = a[3:12]
         return ('s2d wgrad', 1, n, h, w, ci, co, 3, 2, False, 2.0 * n * h * w * co * (ci // 4) * 9)
