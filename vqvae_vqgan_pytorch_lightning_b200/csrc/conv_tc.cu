@@ -1121,14 +1121,17 @@ constexpr int NTHREADS_NIN = 448;      // TMA / MMA / 8 epilogue warps / 4 produ
 
 template <typename TI>
 __global__ void __launch_bounds__(NTHREADS_NIN, 1)
-conv_fwd_tc_narrowin_kernel(const __grid_constant__ CUtensorMap tmB, const FwdParams p, const TI* __restrict__ x, int Cin, int a_stages) {
+conv_fwd_tc_narrowin_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmY, const FwdParams p,
+                            const TI* __restrict__ x, int Cin, int a_stages, int out_tma) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int a_tile = BM * BK * 2;                        // 16 KB
     const int w_tile = p.BN * BK * 2;                      // one channel tile of the resident weight
     uint8_t* smemW = smem;
     uint8_t* smemA = smem + (size_t)p.co_tiles * w_tile;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smemA + (size_t)a_stages * a_tile);
+    uint8_t* smemO = smemA + (size_t)a_stages * a_tile;    // out_tma: [2 buffers][BN / 64 halves][128 pixels][128 B] output staging (SWIZZLE_128B)
+    const int o_half = BM * 128, o_buf = (p.BN / 64) * o_half;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smemO + (out_tma ? 2 * (size_t)o_buf : 0));
     uint64_t* empty = full + a_stages;
     uint64_t* wfull = empty + a_stages;
     uint64_t* tfull = wfull + 1;                           // [2]
@@ -1180,8 +1183,85 @@ conv_fwd_tc_narrowin_kernel(const __grid_constant__ CUtensorMap tmB, const FwdPa
                 if (++as == 2) { as = 0; aphase ^= 1; }
             }
         }
-    } else if (warp < 10) {
+    } else if (warp < 10 && !out_tma) {
         epilogue_loop(p, tmem_base, tfull, tempty, warp, lane);
+    } else if (warp < 10) {
+        // ================= epilogue through shared memory + TMA store (bf16 output, no residual) =================
+        // thread = pixel row: a 32-channel chunk is 64 B per pixel at a pixel stride of 2 Co bytes -- stored straight to global
+        // memory every lane of a warp store hits a different 128-byte line (2048 LSU transactions per 32 KB tile: the kernel was
+        // bound by that, 2.8 us per tile).  Staged in the TMA SWIZZLE_128B layout instead and written by two bulk tensor stores per
+        // tile (which also clip partial tiles at the image border).
+        if (warp == 2 && lane == 0) ptx::prefetch_tmap(&tmY);
+        const int quarter = warp & 3, half = (warp - 2) >> 2;
+        const int row = quarter * 32 + lane;
+        const int nch = (p.BN - half * 32 + 63) / 64;
+        int as = 0; uint32_t aphase = 0;
+        int buf = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const int ct = tile % p.co_tiles, pt = tile / p.co_tiles;
+            const int twi = pt % p.tiles_w, t2 = pt / p.tiles_w, thi = t2 % p.tiles_h, n = t2 / p.tiles_h;
+            const int co0 = ct * p.BN;
+            // the bulk store that read this staging buffer two tiles ago has finished reading it
+            if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+            ptx::mbar_wait(&tfull[as], aphase);
+            ptx::tc_fence_after();
+            uint8_t* ob = smemO + (size_t)buf * o_buf;
+            for (int s_ = 0; s_ < nch; ++s_) {
+                const int c = half * 32 + s_ * 64;
+                uint32_t r[32];
+                ptx::tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * p.BN + c), r);
+                ptx::tmem_ld_wait();
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                if (p.bias || p.act != VQB_ACT_NONE || p.gain != 1.0f) {
+                    const float4* bp = reinterpret_cast<const float4*>(p.bias ? p.bias + co0 + c : nullptr);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (p.bias) q4 = __ldg(bp + j);
+                        v[4 * j] += q4.x; v[4 * j + 1] += q4.y; v[4 * j + 2] += q4.z; v[4 * j + 3] += q4.w;
+                    }
+                    if (p.act == VQB_ACT_RELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f) * p.gain;
+                    } else if (p.act == VQB_ACT_LRELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = (v[j] > 0.f ? v[j] : v[j] * p.alpha) * p.gain;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = act_f(v[j], p.act, p.alpha) * p.gain;
+                    }
+                }
+                uint8_t* orow = ob + (size_t)(c >> 6) * o_half + (size_t)row * 128;
+                const int jb = (c & 63) >> 3;                       // first 16-byte chunk of this 32-channel piece inside the 128-byte row
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    uint4 u;
+                    __nv_bfloat162* hb = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) hb[e] = __floats2bfloat162_rn(v[i * 8 + 2 * e], v[i * 8 + 2 * e + 1]);
+                    *reinterpret_cast<uint4*>(orow + (((jb + i) ^ (row & 7)) << 4)) = u;
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tempty[as]);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the bulk store
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+            if (warp == 2 && lane == 0) {
+                for (int hf = 0; hf < p.BN / 64; ++hf)
+                    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                                     reinterpret_cast<uint64_t>(&tmY)),
+                                 "r"(ptx::smem_u32(ob + (size_t)hf * o_half)), "r"(co0 + hf * 64), "r"(twi * p.tw), "r"(thi * p.th), "r"(n)
+                                 : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            buf ^= 1;
+            if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+        if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");    // all output bytes written before exit
     } else {
         // ================= A-tile producers: thread = pixel row of the 16 x 8 tile =================
         const int row = (warp - 10) * 32 + lane;
@@ -1191,6 +1271,16 @@ conv_fwd_tc_narrowin_kernel(const __grid_constant__ CUtensorMap tmB, const FwdPa
             const int pt = tile / p.co_tiles;
             const int twi = pt % p.tiles_w, t2 = pt / p.tiles_w, thi = t2 % p.tiles_h, n = t2 / p.tiles_h;
             const int h = thi * p.th + hi, w = twi * p.tw + wi;
+            {   // this thread's pixel of the tile two iterations ahead -> L2 (the image is streamed: every tile is a first touch)
+                const int tile2 = tile + 2 * (int)gridDim.x;
+                if (tile2 < p.num_tiles) {
+                    const int pt2 = tile2 / p.co_tiles;
+                    const int twi2 = pt2 % p.tiles_w, t22 = pt2 / p.tiles_w, thi2 = t22 % p.tiles_h, n2 = t22 / p.tiles_h;
+                    const int h2 = thi2 * p.th + hi, w2 = twi2 * p.tw + wi;
+                    if (h2 < p.H && w2 < p.W)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(x + (((int64_t)n2 * p.H + h2) * p.W + w2) * Cin) : "memory");
+                }
+            }
             // 32 K values: (tap, c) for tap < 9, c < Cin (9 Cin <= 27), zero beyond
             float v[32];
 #pragma unroll
@@ -1789,18 +1879,23 @@ extern "C" int vqb_conv2d_fwd_narrowin(const void* x, int x_dtype, const void* w
     p.res_prefetch = res_prefetch;
     p.alpha = act_alpha; p.gain = gain; p.gn_sums = nullptr; p.gn_cpg = 0;
     p.ntaps = 1; p.ktw = 1; p.kh0 = 0; p.kw0 = 0; p.b_resident = 1;
-    CUtensorMap tmB;
+    CUtensorMap tmB, tmY;
     int rc = make_weight_map(&tmB, wp, Co, 64, p.BN); if (rc) return rc;
     const int a_stages = 4;
-    size_t smem = (size_t)Co * 128 + (size_t)a_stages * BM * BK * 2 + 256 + 1024;
+    // bf16 output without a residual leaves through shared memory + TMA bulk stores (VQB_NARROW_IN_TMA=0: the common pixel-major epilogue)
+    static const int tma_out = getenv("VQB_NARROW_IN_TMA") ? atoi(getenv("VQB_NARROW_IN_TMA")) : 1;
+    const int out_tma = (tma_out && y_dtype == VQB_BF16 && !residual && ((uintptr_t)y & 15) == 0) ? 1 : 0;
+    if (out_tma) { rc = make_act_map(&tmY, y, N, H, W, Co, 16, 8, 1); if (rc) return rc; }
+    else tmY = tmB;
+    size_t smem = (size_t)Co * 128 + (size_t)a_stages * BM * BK * 2 + (out_tma ? (size_t)2 * (p.BN / 64) * BM * 128 : 0) + 256 + 1024;
     cudaStream_t st = as_stream(stream);
     int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
     if (x_dtype == VQB_F32) {
         VQB_CUDA(cudaFuncSetAttribute(conv_fwd_tc_narrowin_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        conv_fwd_tc_narrowin_kernel<float><<<grid, NTHREADS_NIN, smem, st>>>(tmB, p, (const float*)x, Ci, a_stages);
+        conv_fwd_tc_narrowin_kernel<float><<<grid, NTHREADS_NIN, smem, st>>>(tmB, tmY, p, (const float*)x, Ci, a_stages, out_tma);
     } else {
         VQB_CUDA(cudaFuncSetAttribute(conv_fwd_tc_narrowin_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        conv_fwd_tc_narrowin_kernel<bf16><<<grid, NTHREADS_NIN, smem, st>>>(tmB, p, (const bf16*)x, Ci, a_stages);
+        conv_fwd_tc_narrowin_kernel<bf16><<<grid, NTHREADS_NIN, smem, st>>>(tmB, tmY, p, (const bf16*)x, Ci, a_stages, out_tma);
     }
     VQB_CHECK_LAUNCH("conv2d_fwd_narrowin");
     return VQB_OK;

@@ -634,12 +634,21 @@ class Conv2dFn(torch.autograd.Function):
                 db = db_fused if db_fused is not None else _colsum(dy, n * oh * ow, co)
             return None, dw, db, dres, None, None, None, None, None, None, None, None
         if route == 'out' and x.dtype == torch.bfloat16:
-            pd = _im2col64(dy)                                                        # im2col of the 3-channel gradient
+            pd = None
             if ctx.needs_input_grad[0]:
                 wd = _packed_weight(weight, 5, torch.bfloat16, w_scale)               # [ci][64]: flipped taps, K zero-padded
                 ddt = in_dtype if in_dtype in (torch.float32, torch.bfloat16) else gdt
-                dx = _conv_fwd_raw(1, pd, wd, None, None, ddt, 64, ci, 1, 1, 0, 1, ACT_NONE, 0.0, 1.0)
+                if co == 3 and ci <= 512 and dy.dtype in (torch.float32, torch.bfloat16) and _narrowin_enabled():
+                    # the input gradient of a Ci -> 3 head is a 3 -> Ci narrow-input convolution of dy: operand built inside the kernel
+                    dx = empty_nhwc(n, ci, h, w, ddt, dy.device)
+                    call('vqb_conv2d_fwd_narrowin', ptr(dy), dt(dy), ptr(wd), None, None, ptr(dx), dt(dx), n, h, w, co, ci, ACT_NONE, 0.0, 1.0,
+                         stream())
+                else:
+                    pd = _im2col64(dy)                                                # im2col of the 3-channel gradient
+                    dx = _conv_fwd_raw(1, pd, wd, None, None, ddt, 64, ci, 1, 1, 0, 1, ACT_NONE, 0.0, 1.0)
             if ctx.needs_input_grad[1]:
+                if pd is None:
+                    pd = _im2col64(dy)
                 # R[(kh',kw',co)][ci] = im2col(dy)^T x ; dW[co][ci][kh][kw] = R[(2-kh, 2-kw, co)][ci]
                 r = torch.zeros(64 * ci, dtype=torch.float32, device=x.device)
                 call('vqb_conv2d_wgrad', 1, ptr(pd), BF16, ptr(x), BF16, ptr(r), n, h, w, 64, ci, 1, 1, 0, 1, stream())
