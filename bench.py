@@ -136,7 +136,7 @@ class ClockSampler:
 
 
 CONV_ENTRY_POINTS = ('vqb_conv2d_fwd', 'vqb_conv2d_fwd_gn', 'vqb_conv2d_wgrad', 'vqb_conv2d_fwd_sub', 'vqb_conv2d_wgrad_sub',
-                     'vqb_conv2d_fwd_narrowin', 'vqb_conv2d_fwd_narrowout')
+                     'vqb_conv2d_fwd_narrowin', 'vqb_conv2d_fwd_narrowout', 'vqb_conv2d_wgrad_narrow')
 
 
 def conv_shape(name, a):
@@ -164,6 +164,9 @@ def conv_shape(name, a):
     if name == 'vqb_conv2d_fwd_narrowout':       # Ci -> 3 image head, per-tap partial products + shift-add
         n, h, w, ci, co = a[5:10]
         return ('fwd narrow-out', 1, n, h, w, ci, co, 3, 1, False, 2.0 * n * h * w * co * ci * 9)
+    if name == 'vqb_conv2d_wgrad_narrow':        # weight gradient of a 3-channel-sided head, im2col operand built in the kernel
+        n, h, w, cn, cw = a[4:9]
+        return ('wgrad narrow', 1, n, h, w, cn, cw, 3, 1, False, 2.0 * n * h * w * cn * cw * 9)
     if name == 'vqb_conv2d_wgrad_sub':
         n, hx, wx, h, w, ci, co, t, off = a[3:12]
         return ('s2d wgrad', 1, n, h, w, ci, co, 3, 2, False, 2.0 * n * h * w * co * (ci // 4) * 9)

@@ -134,6 +134,12 @@ int vqb_conv2d_fwd_narrowout(const void* x, const void* wp, const float* bias, v
  * residual epilogue; Co a multiple of 64. */
 int vqb_conv2d_fwd_narrowin(const void* x, int x_dtype, const void* wp, const float* bias, const void* residual, void* y, int y_dtype,
                             int N, int H, int W, int Ci, int Co, int act, float act_alpha, float gain, void* stream);
+/* Weight gradient of a 3x3 'same' convolution one side of which has 3 channels (encoder.conv_in: narrow = the image, wide = dy;
+ * decoder.conv_out: narrow = dy, wide = the layer input): dwp [64][Cw] fp32 (caller zero-fills), row (tap * 3 + c) with tap = kh * 3 + kw,
+ * += sum_pix narrow[n, h + kh - 1, w + kw - 1, c] * wide[n, h, w, cw].  The im2col operand is built in shared memory (no HBM tensor);
+ * narrow fp32 or bf16, wide bf16 with Cw a multiple of 128. */
+int vqb_conv2d_wgrad_narrow(const void* narrow, int n_dtype, const void* wide, float* dwp, int N, int H, int W, int Cn, int Cw,
+                            void* stream);
 /* T x T-tap sub-convolution on the 3x3 halo kernels (tcgen05, bf16 operands):
  *     y[n,h,w,co] = act(bias + sum_{a,b<T} sum_ci x[n, h+off+a, w+off+b, ci] * wp[co][(a*T+b)*Ci + ci]),  x zero outside its Hx x Wx pixels,
  * H x W = output size (may differ from the input's), T in {2,3}, -1 <= off, off + T <= 2.  It carries the discriminator's stride-2

@@ -222,10 +222,23 @@ def test_narrow_input_head_in_kernel_im2col(n, h, w, co, dtype, act):
             wg = torch.nn.Parameter(wt.cuda().clone(), requires_grad=(co % 128 == 0))     # (64-wide heads ride this route only when frozen)
             bg = torch.nn.Parameter(b.cuda().clone())
             y = ops.conv2d(xg, wg, bg, None, pad=1, act=ACT_RELU if act == 'relu' else ACT_NONE, out_dtype=torch.float32)
-            outs[flag] = y.detach().float().cpu()
-        err = float((outs[True] - ref).norm() / ref.norm())
+            gw = None
+            if wg.requires_grad:                      # weight gradient: vqb_conv2d_wgrad_narrow vs im2col + the generic 1x1 kernel
+                torch.manual_seed(13)
+                go = torch.randn(n, co, h, w).bfloat16().float()
+                y.backward(go.cuda().contiguous(memory_format=torch.channels_last))
+                gw = wg.grad.cpu().clone()
+            outs[flag] = (y.detach().float().cpu(), gw)
+        err = float((outs[True][0] - ref).norm() / ref.norm())
         assert err < 1e-4, err
-        assert float((outs[True] - outs[False]).norm() / ref.norm()) < 1e-4
+        assert float((outs[True][0] - outs[False][0]).norm() / ref.norm()) < 1e-4
+        if outs[True][1] is not None:
+            wr = wt.clone().requires_grad_()
+            out = F.conv2d(x16, wr, b, padding=1)
+            torch.manual_seed(13)
+            out.backward(torch.randn(n, co, h, w).bfloat16().float())
+            assert float((outs[True][1] - wr.grad).norm() / wr.grad.norm()) < 2e-4, 'narrow weight gradient vs fp32 torch'
+            assert float((outs[True][1] - outs[False][1]).norm() / wr.grad.norm()) < 2e-4
     finally:
         ops._narrowin = None
         pkg.set_precision('strict')

@@ -1427,6 +1427,146 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_cons
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Weight gradient with a NARROW operand (3 channels: the image side of encoder.conv_in, or dy of the 128 -> 3 head):
+//   dwp[(tap * 3 + c)][cw] += sum_pix nar[pix + tap][c] * wide[pix][cw],   dwp = [64][Cw] fp32 (rows >= 27 stay zero).
+// The [64 pixels][64 im2col columns] operand of every reduction step is built in shared memory by producer warps (the layout of
+// conv_fwd_tc_narrowin_kernel's A tile, read here as an MN-major operand: rows = pixels = the reduction index); the wide
+// operand arrives by TMA.  Replaces im2col-to-HBM + the generic 1x1 weight-gradient kernel.
+// ---------------------------------------------------------------------------------------------------
+constexpr int NTHREADS_NWG = 320;      // TMA / MMA / 4 epilogue warps / 4 producer warps (two groups alternating steps)
+
+template <typename TI>
+__global__ void __launch_bounds__(NTHREADS_NWG, 1)
+conv_wgrad_tc_narrow_kernel(const __grid_constant__ CUtensorMap tmWide, const WgradParams p, const TI* __restrict__ nar, int Cn) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int blk_bytes = BK * 128;                     // one [64 pixels][64 channels] bf16 block = 8 KB
+    const int a_bytes = (BM / 64) * blk_bytes;          // wide operand: 128 channels
+    const int stage_bytes = a_bytes + blk_bytes;        // + the built [64 pixels][64 columns] block
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+    uint64_t* empty = full + p.stages;
+    uint64_t* tfull = empty + p.stages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cot = blockIdx.x;                          // 128-channel tile of the wide operand
+    const int co0 = cot * BM;
+    const int pt_begin = blockIdx.y * p.ptiles_per_split;
+    int pt_end = pt_begin + p.ptiles_per_split; if (pt_end > p.ptiles_total) pt_end = p.ptiles_total;
+    const int nsteps = pt_end - pt_begin;
+
+    // columns 27 .. 63 of every built block are zero and never rewritten
+    for (int st = 0; st < p.stages; ++st)
+        for (int i = threadIdx.x; i < blk_bytes / 16; i += NTHREADS_NWG)
+            reinterpret_cast<uint4*>(smem + (size_t)st * stage_bytes + a_bytes)[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmWide);
+        for (int i = 0; i < p.stages; ++i) { ptx::mbar_init(&full[i], 3); ptx::mbar_init(&empty[i], 1); }   // TMA expect_tx + 2 producer warps
+        ptx::mbar_init(tfull, 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) ptx::tmem_alloc(tmem_slot, 64);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (nsteps > 0) {
+        if (warp == 0) {
+            if (lane == 0) {
+                int stage = 0; uint32_t phase = 0;
+                for (int pt = pt_begin; pt < pt_end; ++pt) {
+                    const int twi = pt % p.tiles_w, t2 = pt / p.tiles_w, thi = t2 % p.tiles_h, tni = t2 / p.tiles_h;
+                    ptx::mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                    ptx::mbar_expect_tx(&full[stage], (uint32_t)a_bytes);
+                    for (int j = 0; j < BM / 64; ++j)
+                        ptx::tma_load_4d(sa + j * blk_bytes, &tmWide, &full[stage], co0 + j * 64, twi * p.tw, thi * p.th, tni * p.nb);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        } else if (warp == 1) {
+            if (lane == 0) {
+                const uint32_t idesc = ptx::umma_idesc_bf16(BM, 64, 1, 1);
+                int stage = 0; uint32_t phase = 0;
+                for (int s_ = 0; s_ < nsteps; ++s_) {
+                    ptx::mbar_wait(&full[stage], phase);
+                    ptx::tc_fence_after();
+                    const uint32_t sa = ptx::smem_u32(smem + (size_t)stage * stage_bytes);
+                    const uint64_t adesc = ptx::umma_smem_desc(sa, (uint32_t)blk_bytes, 1024);
+                    const uint64_t bdesc = ptx::umma_smem_desc(sa + a_bytes, (uint32_t)blk_bytes, 1024);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k)
+                        ptx::umma_bf16(tmem_base, adesc + (uint64_t)(k * UMMA_K * 128 / 16), bdesc + (uint64_t)(k * UMMA_K * 128 / 16), idesc,
+                                       (s_ | k) != 0 ? 1u : 0u);
+                    ptx::umma_commit(&empty[stage]);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+                ptx::umma_commit(tfull);
+            }
+        } else if (warp < 6) {
+            const int quarter = warp & 3;
+            const int co = co0 + quarter * 32 + lane;
+            ptx::mbar_wait(tfull, 0);
+            ptx::tc_fence_after();
+            uint32_t r[32];
+            ptx::tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16), r);
+            ptx::tmem_ld_wait();
+            // D[cw lane][j column]: only the 27 real rows of dwp
+#pragma unroll
+            for (int j = 0; j < 27; ++j) atomicAdd(p.dwp + (int64_t)j * p.Co + co, __uint_as_float(r[j]));
+        } else {
+            // producers: group g = (warp - 6) / 2 builds the blocks of steps s with (s & 1) == g; thread = pixel row of the block
+            const int g = (warp - 6) >> 1;
+            const int row = ((warp - 6) & 1) * 32 + lane;                  // 0..63
+            const int wi = row % p.tw, r2 = row / p.tw, hi = r2 % p.th, ni = r2 / p.th;
+            for (int s_ = g; s_ < nsteps; s_ += 2) {
+                const int pt = pt_begin + s_;
+                const int stage = s_ % p.stages;
+                const uint32_t phase = (uint32_t)((s_ / p.stages) & 1);
+                const int twi = pt % p.tiles_w, t2 = pt / p.tiles_w, thi = t2 % p.tiles_h, tni = t2 / p.tiles_h;
+                const int w = twi * p.tw + wi, h = thi * p.th + hi, n = tni * p.nb + ni;
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0.f;
+                if (h < p.H && w < p.W && n < p.N) {
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const int ih = h + tap / 3 - 1, iw = w + tap % 3 - 1;
+                        if (ih >= 0 && ih < p.H && iw >= 0 && iw < p.W) {
+                            const TI* src = nar + (((int64_t)n * p.H + ih) * p.W + iw) * Cn;
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) v[tap * 3 + c] = (float)src[c];
+                        }
+                    }
+                }
+                ptx::mbar_wait(&empty[stage], phase ^ 1);
+                uint8_t* dst = smem + (size_t)stage * stage_bytes + a_bytes + (size_t)row * 128;
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) {
+                    uint4 u;
+                    __nv_bfloat162* hb = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) hb[e] = __floats2bfloat162_rn(v[ch * 8 + 2 * e], v[ch * 8 + 2 * e + 1]);
+                    *reinterpret_cast<uint4*>(dst + ((ch ^ (row & 7)) << 4)) = u;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&full[stage]);
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, 64);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // 3x3 weight gradient with halo reuse: a CTA owns (128 co) x (CN ci) x (one kernel row kh = three taps) and a range
 // of 8x8-pixel tiles.  Per tile it loads dy [64 px][128 co] once and ONE x halo box {64 ch, 10, 8} per channel block;
@@ -1898,5 +2038,44 @@ extern "C" int vqb_conv2d_fwd_narrowin(const void* x, int x_dtype, const void* w
         conv_fwd_tc_narrowin_kernel<bf16><<<grid, NTHREADS_NIN, smem, st>>>(tmB, tmY, p, (const bf16*)x, Ci, a_stages, out_tma);
     }
     VQB_CHECK_LAUNCH("conv2d_fwd_narrowin");
+    return VQB_OK;
+}
+
+// dwp [64][Cw] fp32 (caller zero-fills; rows (tap * 3 + c), tap = kh * 3 + kw) += sum_pix narrow[pix + tap - (1,1)][c] * wide[pix][cw]:
+// the weight gradient of a 3x3 'same' convolution whose one side has 3 channels (see conv_wgrad_tc_narrow_kernel).  narrow: NHWC
+// [N,H,W,3] fp32 or bf16; wide: NHWC [N,H,W,Cw] bf16, Cw a multiple of 128.
+extern "C" int vqb_conv2d_wgrad_narrow(const void* narrow, int n_dtype, const void* wide, float* dwp, int N, int H, int W, int Cn, int Cw,
+                                       void* stream) {
+    VQB_CHECK_ARG(narrow && wide && dwp && N > 0 && H > 0 && W > 0, "conv2d_wgrad_narrow: bad arguments");
+    VQB_CHECK_ARG(Cn == 3 && Cw % 128 == 0, "conv2d_wgrad_narrow: needs 3 narrow channels and Cw %% 128 == 0 (got %d, %d)", Cn, Cw);
+    VQB_CHECK_ARG(n_dtype == VQB_F32 || n_dtype == VQB_BF16, "conv2d_wgrad_narrow: narrow operand must be fp32 or bf16");
+    WgradParams p;
+    p.N = N; p.H = H; p.W = W; p.Ci = 64; p.Co = Cw; p.KH = 1; p.KW = 1; p.pad = 0;
+    pick_tile(BK, H, W, p.tw, p.th, p.nb);
+    p.tiles_w = (W + p.tw - 1) / p.tw; p.tiles_h = (H + p.th - 1) / p.th; p.tiles_n = (N + p.nb - 1) / p.nb;
+    p.CN = 64; p.co_tiles = Cw / BM; p.ci_tiles = 1;
+    const int stage_bytes = (BM / 64 + 1) * BK * 128;
+    p.stages = 8;
+    p.ptiles_total = p.tiles_w * p.tiles_h * p.tiles_n;
+    int splits = p.co_tiles <= sm_count() ? sm_count() / p.co_tiles : 1;
+    int max_splits = (p.ptiles_total + 7) / 8; if (max_splits < 1) max_splits = 1;
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    p.ptiles_per_split = (p.ptiles_total + splits - 1) / splits;
+    splits = (p.ptiles_total + p.ptiles_per_split - 1) / p.ptiles_per_split;
+    p.dwp = dwp;
+    CUtensorMap tmWide;
+    int rc = make_act_map(&tmWide, wide, N, H, W, Cw, p.tw, p.th, p.nb); if (rc) return rc;
+    size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256;
+    cudaStream_t st = as_stream(stream);
+    dim3 grid(p.co_tiles, splits);
+    if (n_dtype == VQB_F32) {
+        VQB_CUDA(cudaFuncSetAttribute(conv_wgrad_tc_narrow_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        conv_wgrad_tc_narrow_kernel<float><<<grid, NTHREADS_NWG, smem, st>>>(tmWide, p, (const float*)narrow, Cn);
+    } else {
+        VQB_CUDA(cudaFuncSetAttribute(conv_wgrad_tc_narrow_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        conv_wgrad_tc_narrow_kernel<bf16><<<grid, NTHREADS_NWG, smem, st>>>(tmWide, p, (const bf16*)narrow, Cn);
+    }
+    VQB_CHECK_LAUNCH("conv2d_wgrad_narrow");
     return VQB_OK;
 }

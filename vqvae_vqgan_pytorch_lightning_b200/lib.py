@@ -72,6 +72,7 @@ SIGNATURES = {
     'vqb_conv2d_fwd_narrowout': (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _f, _p]),
     # x, xdt, wp, bias, residual, y, ydt, N, H, W, Ci, Co, act, alpha, gain, stream
     'vqb_conv2d_fwd_narrowin': (_i, [_p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _f, _p]),
+    'vqb_conv2d_wgrad_narrow': (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _i, _p]),
     'vqb_conv2d_sub_supported': (_i, [_i, _i, _i, _i, _i, _i, _i, _i, _i]),
     # x, y, dtype, N, H, W, C, OH, OW, pad, in_s2d, out_s2d, stream
     'vqb_fir4_s2d': (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),

@@ -627,7 +627,10 @@ class Conv2dFn(torch.autograd.Function):
             # dW[(tap,ci)][co] = im2col(x)^T dy : 1x1 tcgen05 wgrad with 64 (zero-padded) input channels
             dwp = torch.zeros(64 * co, dtype=torch.float32, device=x.device)
             dyw = as_nhwc(dy, torch.bfloat16)
-            call('vqb_conv2d_wgrad', 1, ptr(_im2col64(x)), BF16, ptr(dyw), BF16, ptr(dwp), n, h, w, 64, co, 1, 1, 0, 1, stream())
+            if ci == 3 and co % 128 == 0 and x.dtype in (torch.float32, torch.bfloat16) and _narrowin_enabled():
+                call('vqb_conv2d_wgrad_narrow', ptr(x), dt(x), ptr(dyw), ptr(dwp), n, h, w, ci, co, stream())     # im2col operand built in the kernel
+            else:
+                call('vqb_conv2d_wgrad', 1, ptr(_im2col64(x)), BF16, ptr(dyw), BF16, ptr(dwp), n, h, w, 64, co, 1, 1, 0, 1, stream())
             dw = torch.empty(weight.shape, dtype=torch.float32, device=x.device)
             call('vqb_unpack_conv_wgrad', ptr(dwp), ptr(dw), co, ci, kh, kw, w_scale, stream())
             if has_bias and ctx.needs_input_grad[2]:
@@ -647,11 +650,14 @@ class Conv2dFn(torch.autograd.Function):
                     pd = _im2col64(dy)                                                # im2col of the 3-channel gradient
                     dx = _conv_fwd_raw(1, pd, wd, None, None, ddt, 64, ci, 1, 1, 0, 1, ACT_NONE, 0.0, 1.0)
             if ctx.needs_input_grad[1]:
-                if pd is None:
-                    pd = _im2col64(dy)
                 # R[(kh',kw',co)][ci] = im2col(dy)^T x ; dW[co][ci][kh][kw] = R[(2-kh, 2-kw, co)][ci]
                 r = torch.zeros(64 * ci, dtype=torch.float32, device=x.device)
-                call('vqb_conv2d_wgrad', 1, ptr(pd), BF16, ptr(x), BF16, ptr(r), n, h, w, 64, ci, 1, 1, 0, 1, stream())
+                if co == 3 and ci % 128 == 0 and dy.dtype in (torch.float32, torch.bfloat16) and _narrowin_enabled():
+                    call('vqb_conv2d_wgrad_narrow', ptr(dy), dt(dy), ptr(x), ptr(r), n, h, w, co, ci, stream())   # im2col(dy) built in the kernel
+                else:
+                    if pd is None:
+                        pd = _im2col64(dy)
+                    call('vqb_conv2d_wgrad', 1, ptr(pd), BF16, ptr(x), BF16, ptr(r), n, h, w, 64, ci, 1, 1, 0, 1, stream())
                 dw = r[:9 * co * ci].view(3, 3, co, ci).flip(0, 1).permute(2, 3, 0, 1).contiguous()      # 10 KB reorder
                 if w_scale != 1.0:
                     dw = dw * w_scale
