@@ -314,11 +314,13 @@ int vqb_vq_assign_tc(const float* z, const float* codebook, int order, float* q_
 /* ONE-launch form of the same contract (identical indices to vqb_vq_assign), the product path on sm_100: a cluster of two
  * CTAs owns 256 latent rows; z is read once from HBM and rounded to fp16 in the prologue (resident in shared memory), the
  * fp16 copy of the codebook streams through a TMA ring, tcgen05 cta_group::2 UMMAs give the dot products in TMEM with a
- * rigorously bounded error, the scan warps keep a running minimum plus an online list of every code within that error band
- * of it, near-tied rows re-evaluate ONLY their surviving candidates with the strict kernel's fp32 arithmetic, and the same
- * launch writes idx, q, sum (e-z)^2, the histogram and the EMA cluster sums.  Replaces vector_quantizers.py:37-61, 142-166.
- *   cb_half [K][D] fp16 and cb_sq [K] fp32: produced by vqb_vq_prep_codebook (any codebook) or by vqb_vq_ema_update_prep
- *   (the EMA path: the update kernel leaves them for the NEW codebook, so the next step needs no preparation launch).
+ * rigorously bounded error PER CODE (it grows with the code's norm), the scan warps keep a running upper bound of the smallest
+ * distance plus an online list of every code whose lower bound does not exceed it, near-tied rows re-evaluate ONLY their
+ * surviving candidates with the strict kernel's fp32 arithmetic, and the same launch writes idx, q, sum (e-z)^2, the histogram
+ * and the EMA cluster sums.  Replaces vector_quantizers.py:37-61, 142-166.
+ *   cb_half [K][D] fp16 and cb_sq [4 K] fp32 (|e_k|^2, then the per-code and per-32-code-chunk coefficients of the error
+ *   bound): produced by vqb_vq_prep_codebook (any codebook) or by vqb_vq_ema_update_prep (the EMA path: the update kernel
+ *   leaves them for the NEW codebook, so the next step needs no preparation launch).
  * Needs D % 64 == 0, D <= 256, K % 8 == 0, K <= 65528.  sse / counts / dw / undecided_rows_out: caller zero-fills;
  * undecided_rows_out (may be NULL) is int[2]: rows that took the exact re-rank, and those among them that scanned every code. */
 int vqb_vq_prep_codebook(const float* codebook, void* cb_half, float* cb_sq, int K, int D, void* stream);

@@ -80,6 +80,31 @@ def test_fused_duplicate_codes_take_first_index(V):
     assert int(V.ops.vq_assign_raw.last_undecided) == N
 
 
+@pytest.mark.parametrize('K,n_used', [(8192, 300), (1024, 40), (8192, 8000)])
+def test_fused_trained_ema_codebook_large_and_decayed_codes(V, K, n_used):
+    """the codebook an EMA run produces (vector_quantizers.py:158-169): a few used codes of the latents' norm among thousands of
+    unused ones that have decayed towards the origin.  With one error band for the whole codebook (the largest norm) all decayed
+    codes lie within a band of each other and every row overflowed its candidate list (exact scan of all K codes: 30 ms per
+    launch in the K = 8192 training step); with per-code bounds the rows are decided from short lists -- and the indices stay
+    those of the exact fp32 kernel, for rows next to a used code as for rows next to the origin."""
+    torch.manual_seed(12)
+    N, D = 4096, 256
+    used = torch.randperm(K)[:n_used]
+    cb = torch.empty(K, D).uniform_(-1, 1) * 0.027                       # |e| ~ 0.25
+    cb[used] = torch.randn(n_used, D)                                    # |e| ~ 16
+    z = cb[used[torch.randint(0, n_used, (N,))]] + 0.3 * torch.randn(N, D)
+    z[: N // 8] = 0.02 * torch.randn(N // 8, D)                          # latents whose nearest code is one of the decayed ones
+    z[N // 8: N // 4] *= 0.05                                            # and latents in between
+    z, cb = z.cuda(), cb.cuda()
+    q0, i0, s0, c0, w0 = V.ops.vq_assign_raw(z, cb, 0, True, True, use_tc=False)
+    q1, i1, s1, c1, w1 = V.ops.vq_assign_raw(z, cb, 0, True, True, use_tc='fused')
+    und, full = int(V.ops.vq_assign_raw.last_undecided), int(V.ops.vq_assign_raw.last_fullscan)
+    assert torch.equal(i0, i1), (int((i0 != i1).sum()), und, full)
+    assert torch.equal(q0, q1) and torch.equal(c0, c1)
+    assert full <= 4, (und, full)                                         # no row falls back to the scan of the whole codebook
+    assert und <= N // 4, (und, full)
+
+
 def test_fused_out_of_fp16_range_and_nan_rows(V):
     """the fused search rounds z and the codebook to fp16 for the tensor cores: latents beyond the fp16 range, infinities and
     NaN rows must fall back to the exact scan and still equal the strict kernel (NaN row -> index 0, as the strict kernel)"""

@@ -35,7 +35,7 @@ for (N, K) in ((16384, 1024), (8192, 8192)):
         cb = (torch.empty(K, D).uniform_(-1 / K, 1 / K) if init == 'uniform' else torch.randn(K, D)).cuda()
         nbytes = 4 * N * D * 2 + 4 * K * D + 8 * N + 8 * K + 12 * K * D
         prep = pkg.ops.CodebookPrep(); prep.get(cb)                        # cached split, as the quantizer modules hold it
-        for tc in (False, 'legacy', 'fused', 'fused+prep'):
+        for tc in (('fused',) if '--fused-only' in sys.argv else (False, 'legacy', 'fused', 'fused+prep')):
             if tc == 'fused+prep':
                 us, kus = timeit(lambda: pkg.ops.vq_assign_raw(z, cb, 0, True, True, use_tc='fused'))          # split launch included
             else:

@@ -11,14 +11,16 @@
 //   warp 0     streams the fp16 copy of the codebook (prepared once per codebook version by vq_prep_codebook or by the EMA
 //              update itself) through a 6-stage TMA ring; each CTA stages only HALF of every 256-code tile (16 KB).
 //   warp 1     (leader CTA) issues M = 256, N = 256 UMMAs (kind::f16, fp32 accumulators in TMEM, double buffered).  ONE fp16
-//              product per k-step: the dot products carry a RIGOROUSLY bounded error of 2^-11 |z||e| (tie_threshold), a third
-//              of the tensor work of a bf16 hi/lo split that would give 2^-16.
-//   warps 2-9  scan each accumulator tile: d~ = |e|^2 - 2 dot, running minimum, and an online CANDIDATE LIST per row: every
-//              code whose d~ is within the error band of the running minimum (a superset of the codes within the band of the
-//              final minimum).  After the last tile a row with a single surviving candidate is decided -- no other code can
-//              have the smallest fp32 distance; for the others the survivors, and only they (typically two), are re-evaluated
-//              EXACTLY (sequential fp32 FMA chain, (|z|^2 + |e|^2) - 2 dot: the strict kernel's arithmetic bit for bit), so
-//              the indices equal the strict kernel's in every case.
+//              product per k-step: the dot products carry a RIGOROUSLY bounded error of ~2^-10 |z||e_k| per code (eps_k below), a
+//              third of the tensor work of a bf16 hi/lo split that would give 2^-16.
+//   warps 2-9  scan each accumulator tile: d~ = |e|^2 - 2 dot, a running UPPER bound ub = min_k (d~_k + eps_k) of the smallest
+//              fp32 distance, and an online CANDIDATE LIST per row: every code whose lower bound d~_k - eps_k does not exceed the
+//              running ub (a superset of the codes that can still be the fp32 argmin at the end).  The bounds are per code
+//              (eps_k grows with |e_k|): a trained codebook mixes large used codes with decayed unused ones.  After the last tile
+//              a row with a single surviving candidate is decided -- no other code can have the smallest fp32 distance; for the
+//              others the survivors, and only they (typically two), are re-evaluated EXACTLY (sequential fp32 FMA chain,
+//              (|z|^2 + |e|^2) - 2 dot: the strict kernel's arithmetic bit for bit), so the indices equal the strict kernel's in
+//              every case.
 //   finish     same warps, same launch: idx (int64), q = z + (e - z), sum (e-z)^2, histogram and EMA cluster sums
 //              (vector red.global.add), z re-read from L2.
 //
@@ -69,45 +71,105 @@ int make_code_map(CUtensorMap* m, const void* base, int64_t rows, int cols, int 
     return VQB_OK;
 }
 
-// codebook fp32 [K][D] -> fp16 copy [K][D] and sq[k] = |e_k|^2 with EXACTLY the summation of row_sqnorm_kernel (vq.cu):
-// lane-strided fp32 FMA chains, then the xor butterfly -- the strict kernel and the exact re-rank below read the same values.
-__global__ void vq_prep_codebook_kernel(const float* __restrict__ cb, __half* __restrict__ hf, float* __restrict__ sq, int K, int D) {
-    const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (row >= K) return;
-    float s = 0.f;
-    for (int d = lane; d < D; d += 32) {
-        const float v = cb[row * D + d];
-        hf[row * D + d] = __float2half_rn(v);
-        s = fmaf(v, v, s);
+// How far the APPROXIMATE distance d~_k = |e_k|^2 - 2 (zh . eh_k) from the tensor cores (zh, eh = z, e rounded to fp16) may lie
+// from the strict kernel's fp32 value d_k (both without the row's |z|^2, which is the same operand for every code of a row
+// and cancels in comparisons):  |d~_k - d_k| <= eps_k = EPS_A |z||e_k| + EPS_B (|z|^2 + |e_k|^2) + EPS_R |e_k|^2 + EPS_G sqrt(D) (|z| + |e_k|)
+//   * operand rounding: |zh_i - z_i| <= 2^-12 |z_i| (11 significant bits, round to nearest) or <= 2^-25 below the fp16 normal
+//     range, likewise e: |zh.eh - z.e| <= (2^-11 + 2^-24) |z||e| + 2^-25 sqrt(D) (|z| + |e|)  (Cauchy-Schwarz);
+//     fp32 accumulation in TMEM over 16 k-steps (not round-to-nearest): <= 2^-17 |z||e|;
+//     on the distance (x2):  (2^-10 + 2^-16 + 2^-23) |z||e| + 2^-24 sqrt(D) (|z| + |e|);
+//   * the fp32 evaluation itself: one rounding of (|z|^2 + |e|^2) and one of the subtraction, each <= 1 ulp of a value
+//     <= (|z|+|e|)^2 <= 2 (|z|^2+|e|^2), i.e. <= 2^-22 (|z|^2+|e|^2), and the sequential 256-term FMA chain of the dot product,
+//     <= 256 * 2^-24 |z||e| (x2 on the distance) = 2^-15 |z||e|.
+//   * the bookkeeping of the scan itself (d~ = fma(-2, dot, |e|^2), d~ - eps, d~ + eps, ub + eps: at most four roundings, per pair of
+//     codes compared, of values <= |e|^2 + 2|z||e| + eps): <= 2^-22 |e|^2 + 2^-21 |z||e| (+ a 2^-22 fraction of eps) per code.
+//   EPS_A = 1.04e-3 >= 2^-10 + 2^-15 + 2^-16 + 2^-21 + 2^-23 (= 1.0231e-3: the 1.6 % slack covers the roundings of evaluating eps
+//   itself, the approximate square roots and the approximate |z|^2 of the prologue), EPS_B = 2.4e-7 >= 2^-22 on |z|^2 + |e|^2,
+//   EPS_R = 2.4e-7 >= 2^-22 on |e|^2 alone, EPS_G = 6.0e-8 >= 2^-24.
+// The bound is PER CODE (round 2 used the largest code norm of the whole codebook for every code: a trained EMA codebook holds a
+// few large used codes next to thousands of unused ones that have decayed towards the origin; with the global norm all of those
+// lie within one band of each other, every row overflowed its candidate list before it met its real neighbour and took the exact
+// scan of the whole codebook -- 30.8 ms per launch at K = 8192 after ~100 training steps, profiles/r02_bench_final_1gpu.json cfg5).
+// Code k can be the fp32 argmin only if  lo_k = d~_k - eps_k  <=  min_j (d~_j + eps_j) = ub.
+// (fp16 overflow -- |z_i| or |e_i| > 65504 -- gives inf / NaN dot products: such a row keeps no candidate and takes the exact
+// scan of the whole codebook.)
+constexpr float EPS_A = 1.04e-3f, EPS_B = 2.4e-7f, EPS_R = 2.4e-7f, EPS_G = 6.0e-8f;
+
+// The auxiliary buffer `cb_sq` of a codebook (4 K floats), written by the two preparation kernels below and read by the search:
+//   [0, K)        |e_k|^2 with EXACTLY the summation of row_sqnorm_kernel (vq.cu): lane-strided fp32 FMA chains, then the xor
+//                 butterfly -- the strict kernel and the exact re-rank read the same values;
+//   [K, 2K)       pa_k = EPS_A |e_k|                                       } the code-dependent part of the error bound eps_k
+//   [2K, 3K)      qa_k = (EPS_B + EPS_R) |e_k|^2 + EPS_G sqrt(D) |e_k|     } (see below): eps_k = |z| pa_k + qa_k + row term
+//   [3K, 3K + 2 ceil(K/32))   the same pair for the LARGEST norm of every 32-code chunk (the scan's chunk-wide test); the second
+//                 value carries a minus sign when the chunk mixes large and small norms.
+// One block = 32 warps = the 32 codes of one chunk.
+__device__ __forceinline__ void prep_aux(float* __restrict__ sq, int K, int D, int code, bool valid, float s, int warp, int lane) {
+    __shared__ float en_s[32], en_lo_s[32];
+    const float fin = (valid && s < INFINITY) ? s : 0.f;                   // non-finite norms: the search takes the exact scan anyway
+    const float en = sqrtf(fin);
+    const float gd = EPS_G * sqrtf((float)D);
+    if (lane == 0) {
+        en_s[warp] = en;
+        en_lo_s[warp] = valid ? en : INFINITY;
+        if (valid) { sq[code] = s; sq[K + code] = EPS_A * en; sq[2 * K + code] = fmaf((EPS_B + EPS_R) * en, en, gd * en); }
     }
+    __syncthreads();
+    if (warp == 0) {
+        float mx = en_s[lane], mi = en_lo_s[lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            mi = fminf(mi, __shfl_xor_sync(0xffffffffu, mi, o));
+        }
+        // a NEGATIVE second coefficient marks a chunk of mixed norms (largest > 1.5 x smallest): there the scan evaluates the
+        // per-code bounds even for a single candidate; in a homogeneous chunk the chunk-wide bound is at most 1.5 x too wide
+        const float qc = fmaf((EPS_B + EPS_R) * mx, mx, gd * mx);
+        if (lane == 0) { sq[3 * K + 2 * blockIdx.x] = EPS_A * mx; sq[3 * K + 2 * blockIdx.x + 1] = (mx > 1.5f * mi) ? -qc : qc; }
+    }
+}
+
+// codebook fp32 [K][D] -> fp16 copy [K][D] and the auxiliary buffer
+__global__ void __launch_bounds__(1024) vq_prep_codebook_kernel(const float* __restrict__ cb, __half* __restrict__ hf, float* __restrict__ sq, int K, int D) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 32 + warp;
+    const bool valid = row < K;
+    float s = 0.f;
+    if (valid)
+        for (int d = lane; d < D; d += 32) {
+            const float v = cb[row * D + d];
+            hf[row * D + d] = __float2half_rn(v);
+            s = fmaf(v, v, s);
+        }
     s = warp_sum(s);
-    if (lane == 0) sq[row] = s;
+    prep_aux(sq, K, D, (int)row, valid, s, warp, lane);
 }
 
 // EMA state update (vector_quantizers.py:158-169, same arithmetic as vq_ema_update_kernel in vq.cu) that also leaves the
-// fp16 copy and the norms of the NEW codebook for the next step's search: no separate preparation launch on the EMA path.
-__global__ void vq_ema_update_prep_kernel(float* __restrict__ ema_count, float* __restrict__ ema_weight, float* __restrict__ cb,
-                                          const float* __restrict__ counts, const float* __restrict__ dw, __half* __restrict__ hf,
-                                          float* __restrict__ sq, int K, int D, float decay, float eps, float batch) {
-    const int code = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (code >= K) return;
-    const float c = ema_count[code] * decay + (1.0f - decay) * counts[code];
-    const float cnt = (c + eps) / (batch + (float)K * eps) * batch;
-    float s = 0.f;
-    for (int d = lane; d < D; d += 32) {
-        const int64_t o = (int64_t)code * D + d;
-        const float w = ema_weight[o] * decay + (1.0f - decay) * dw[o];
-        ema_weight[o] = w;
-        const float v = w / cnt;
-        cb[o] = v;
-        hf[o] = __float2half_rn(v);
-        s = fmaf(v, v, s);
+// fp16 copy and the auxiliary buffer of the NEW codebook for the next step's search: no separate preparation launch on the EMA path.
+__global__ void __launch_bounds__(1024) vq_ema_update_prep_kernel(float* __restrict__ ema_count, float* __restrict__ ema_weight, float* __restrict__ cb,
+                                                                  const float* __restrict__ counts, const float* __restrict__ dw, __half* __restrict__ hf,
+                                                                  float* __restrict__ sq, int K, int D, float decay, float eps, float batch) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int code = blockIdx.x * 32 + warp;
+    const bool valid = code < K;
+    float s = 0.f, cnt = 0.f;
+    if (valid) {
+        const float c = ema_count[code] * decay + (1.0f - decay) * counts[code];
+        cnt = (c + eps) / (batch + (float)K * eps) * batch;
+        for (int d = lane; d < D; d += 32) {
+            const int64_t o = (int64_t)code * D + d;
+            const float w = ema_weight[o] * decay + (1.0f - decay) * dw[o];
+            ema_weight[o] = w;
+            const float v = w / cnt;
+            cb[o] = v;
+            hf[o] = __float2half_rn(v);
+            s = fmaf(v, v, s);
+        }
     }
     s = warp_sum(s);
     __syncwarp();
-    if (lane == 0) { ema_count[code] = cnt; sq[code] = s; }
+    if (valid && lane == 0) ema_count[code] = cnt;
+    prep_aux(sq, K, D, code, valid, s, warp, lane);
 }
 
 struct FusedParams {
@@ -147,23 +209,6 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-// Width of the band around the smallest APPROXIMATE distance inside which a code may still be the fp32 argmin.  With
-// d~ = |e|^2 - 2 (zh . eh) from the tensor cores (zh, eh = z, e rounded to fp16) and d = the strict kernel's fp32 value (same
-// |z|^2 and |e|^2 operands for every code of a row, so they cancel in comparisons):
-//   * operand rounding: |zh_i - z_i| <= 2^-12 |z_i| (11 significant bits, round to nearest) or <= 2^-25 below the fp16 normal
-//     range, likewise e: |zh.eh - z.e| <= (2^-11 + 2^-24) |z||e| + 2^-25 sqrt(D) (|z| + |e|)  (Cauchy-Schwarz);
-//     fp32 accumulation in TMEM over 16 k-steps (not round-to-nearest): <= 2^-17 |z||e|;
-//     on the distance (x2) and for the two codes being compared (x2):  2^-9 (1 + 2^-5) |z||e| + 2^-23 sqrt(D) (|z| + |e|);
-//   * the fp32 evaluation itself: one rounding of (|z|^2 + |e|^2) and one of the subtraction, each <= 1 ulp of a value
-//     <= (|z|+|e|)^2 <= 2 (|z|^2+|e|^2), i.e. <= 2^-22 (|z|^2+|e|^2) per code, and the sequential 256-term FMA chain of the
-//     dot product, <= 256 * 2^-24 |z||e| (x2 on the distance); for two codes: 2^-21 (|z|^2+|e|^2) + 2^-14 |z||e|.
-// A code outside the band cannot have the smallest fp32 distance, hence cannot be the strict kernel's first-index argmin.
-// (fp16 overflow -- |z_i| or |e_i| > 65504 -- gives inf / NaN dot products: such a row keeps no candidate and takes the exact
-// scan of the whole codebook.)
-__device__ __forceinline__ float tie_threshold(float zs, float emax, float sqrt_d) {
-    const float zn = sqrtf(zs), en = sqrtf(emax);
-    return (2.013916015625e-3f + 6.103515625e-5f) * zn * en + 4.76837158203125e-7f * (zs + emax) + 1.1920928955078125e-7f * sqrt_d * (zn + en);
-}
 
 // exact fp32 distance of one (row, code) pair with the strict kernel's arithmetic (vq.cu: vq_assign_tile): |z|^2 from four
 // interleaved FMA chains combined as (s0+s1)+(s2+s3), the dot product as ONE sequential FMA chain over d, then the
@@ -181,14 +226,16 @@ __device__ __forceinline__ float exact_distance(const float* __restrict__ zrow, 
     return (order == 0) ? __fsub_rn(__fadd_rn(zsq, e2), two_dot) : __fadd_rn(__fsub_rn(zsq, two_dot), e2);
 }
 
-// Append (d, code) to the candidate list of `slot` (shared memory, [CAP][256]).  `cnt` = length | overflow << 31.  When the list
-// is full it is first compacted against the current bound (entries that fell out of the band of the running minimum are
-// dropped); only if CAP genuine near-ties remain does the row fall back to the exact scan of the whole codebook.
+// Append (lo, code) to the candidate list of `slot` (shared memory, [CAP][256]); `cnt` = its length.  When the list is full it
+// is first compacted against the current bound (entries whose lower bound rose above the running upper bound are dropped).  If
+// CAP entries remain, the list keeps the CAP SMALLEST lower bounds and drop[slot] remembers the smallest one that was turned away:
+// at the end the list is complete iff that value lies above the final bound (otherwise: more than CAP genuine near-ties --
+// duplicated codes -- and the row takes the exact scan of the whole codebook).
 // Deliberately NOT inlined: the scan loop is unrolled 32x and an inlined copy per element made the loop body ~100 KB of
 // code (ncu: the scan warps stalled on instruction fetch); a thread gets here ~ln K times per row half.
-__device__ __noinline__ int cand_push(float d, int code, float bound, int cnt, int slot, float* cand_d, uint16_t* cand_c) {
+__device__ __noinline__ int cand_push(float d, int code, float bound, int cnt, int slot, float* cand_d, uint16_t* cand_c, float* drop) {
     if (!(d < INFINITY)) return cnt;                                        // padding codes (|e|^2 = inf) and NaN never qualify
-    int n = cnt & 0x7fffffff;
+    int n = cnt;
     if (n == CAP) {
         int m = 0;
         for (int i = 0; i < CAP; ++i) {
@@ -197,8 +244,14 @@ __device__ __noinline__ int cand_push(float d, int code, float bound, int cnt, i
         }
         n = m;
     }
-    if (n < CAP) { cand_d[n * 256 + slot] = d; cand_c[n * 256 + slot] = (uint16_t)code; return (cnt & 0x80000000) | (n + 1); }
-    return (int)0x80000000 | n;
+    if (n < CAP) { cand_d[n * 256 + slot] = d; cand_c[n * 256 + slot] = (uint16_t)code; return n + 1; }
+    int im = 0;
+    float dm = cand_d[slot];
+    for (int i = 1; i < CAP; ++i) { const float di = cand_d[i * 256 + slot]; if (di > dm) { dm = di; im = i; } }
+    float out = d;
+    if (d < dm) { out = dm; cand_d[im * 256 + slot] = d; cand_c[im * 256 + slot] = (uint16_t)code; }
+    drop[slot] = fminf(drop[slot], out);
+    return n;
 }
 
 // the same arithmetic on rows staged in shared memory (plain loads)
@@ -224,10 +277,14 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmEh, const FusedParams p) {
     float* cand_d = reinterpret_cast<float*>(smemE + (size_t)ESTAGES * E_TILE);      // [CAP][256]
     uint16_t* cand_c = reinterpret_cast<uint16_t*>(cand_d + CAP * 256);              // [CAP][256]
     float* e2_s = reinterpret_cast<float*>(cand_c + CAP * 256);                       // [2][256] code norms of the tile in flight
-    float* zsq_s = e2_s + 2 * TN;                                        // [128] |z|^2 (approximate order; threshold only)
-    float* rbest = zsq_s + TM;                                           // [2][128] running minimum per (half, row)
+    float* pa_s = e2_s + 2 * TN;                                         // [2][256] EPS_A |e_k|                       } eps_k = |z| pa_k + qa_k
+    float* qa_s = pa_s + 2 * TN;                                         // [2][256] EPS_B |e_k|^2 + EPS_G sqrt(D) |e_k| }         + row term
+    float* ck_s = qa_s + 2 * TN;                                         // [2][8][2] the same pair for the largest norm of each 32-code chunk
+    float* drop_s = ck_s + 32;                                           // [256] smallest lower bound turned away from a full list
+    float* zsq_s = drop_s + 256;                                         // [128] |z|^2 (approximate order; bounds only)
+    float* rbest = zsq_s + TM;                                           // [2][128] running upper bound of the minimum per (half, row)
     int* rcode = reinterpret_cast<int*>(rbest + 2 * TM);                 // [128] final code per row, [128] fp16-overflow flag per row
-    int* rcnt = rcode + 2 * TM;                                          // [2][128] list length, bit 31 = overflow
+    int* rcnt = rcode + 2 * TM;                                          // [2][128] list length, bit 31 = take the exact full scan
     float* red_s = reinterpret_cast<float*>(rcnt + 2 * TM);              // [8] per-warp partial sums, [8] emax
     uint64_t* zfull = reinterpret_cast<uint64_t*>(red_s + 16);
     uint64_t* efull = zfull + 1;                                          // [ESTAGES] (the leader's are used)
@@ -357,18 +414,38 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmEh, const FusedParams p) {
         const int quarter = warp & 3, half = ew >> 2;
         const int row = quarter * 32 + lane;
         const int slot = half * TM + row;
-        const float thr = tie_threshold(zsq_s[row], emax, sqrt_d);
-        float b1 = INFINITY;
-        int cnt = 0;                                                        // list length, bit 31 = overflow
+        const float gd = EPS_G * sqrt_d;
+        const float zn = sqrtf(zsq_s[row]);
+        const float rterm = fmaf(EPS_B, zsq_s[row], gd * zn);              // the part of eps that depends on the row only
+        float ub = INFINITY;                                                // running min of the upper bounds d~ + eps
+        int cnt = 0;                                                        // list length
         int as = 0; uint32_t aph = 0;
+        drop_s[et] = INFINITY;
+        // code norms of a tile and the coefficients of their error bounds (prepared with the codebook, see prep_aux): thread et
+        // owns code et of the tile, threads 0-15 the eight chunk-wide pairs
+        const int nchunk2 = 2 * ((p.K + 31) / 32);
+        auto load_norms = [&](const int tile, float& e2v, float& pav, float& qav, float& ckv) {
+            const int code = tile * TN + et;
+            const bool in = tile < p.ctiles && code < p.K;
+            e2v = in ? p.cb_sq[code] : INFINITY;                            // padding codes never qualify (d~ = inf)
+            pav = in ? p.cb_sq[p.K + code] : 0.f;
+            qav = in ? p.cb_sq[2 * p.K + code] : 0.f;
+            ckv = (et < 16 && tile < p.ctiles && tile * 16 + et < nchunk2) ? p.cb_sq[3 * p.K + tile * 16 + et] : 0.f;
+        };
+        auto stage_norms = [&](const int buf, const float e2v, const float pav, const float qav, const float ckv) {
+            e2_s[buf * TN + et] = e2v; pa_s[buf * TN + et] = pav; qa_s[buf * TN + et] = qav;
+            if (et < 16) ck_s[buf * 16 + et] = ckv;
+        };
         {
-            e2_s[et] = (et < p.K) ? p.cb_sq[et] : INFINITY;                // code norms of tile 0
+            float e2v, pav, qav, ckv;
+            load_norms(0, e2v, pav, qav, ckv);
+            stage_norms(0, e2v, pav, qav, ckv);                             // tile 0
         }
         for (int j = 0; j < p.ctiles; ++j) {
             epi_sync();                                                     // e2_s[as] written; every warp has left tile j-1
             // norms of the NEXT tile: loaded now, stored after this tile's scan (buffer as^1 was tile j-1's, free since the sync)
-            const int ncode = (j + 1) * TN + et;
-            const float e2_next = (j + 1 < p.ctiles && ncode < p.K) ? p.cb_sq[ncode] : INFINITY;
+            float e2_next, pa_next, qa_next, ck_next;
+            load_norms(j + 1, e2_next, pa_next, qa_next, ck_next);
             ptx::mbar_wait(&tfull[as], aph);
             ptx::tc_fence_after();
             const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * TN);
@@ -377,10 +454,11 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmEh, const FusedParams p) {
             // scheduler, latency-bound: 3.2 us per 256-code tile against 1.1 us of tensor work -- tools/vq_phases.py).
             auto scan_chunk = [&](const uint32_t (&r)[32], const int c) {
                 const float* e2c = e2_s + as * TN + c;
-                // all 32 distances first (independent FMAs) and their minimum by a tree.  Only if the chunk minimum m lies within
-                // the band of the running minimum does the chunk hold candidates at all; then m itself is appended, and -- rare,
-                // genuine near-ties inside one chunk -- every other code within the band of m.  (A code within the band of the
-                // FINAL minimum is either its chunk's minimum, appended because final <= running, or within the band of it.)
+                // all 32 distances first (independent FMAs) and their minimum by a tree.  Only if the chunk minimum, lowered by the
+                // error bound of the chunk's LARGEST code norm, reaches the running upper bound can the chunk hold candidates at
+                // all; only then are the per-code bounds evaluated: lo_k = d~_k - eps_k, the upper bound tightened by
+                // min_k (d~_k + eps_k), and every code with lo_k <= ub appended (usually one).  ub only decreases, so a code that
+                // is not appended here lies above the final bound as well.
                 float d[32];
 #pragma unroll
                 for (int u = 0; u < 32; u += 4) {
@@ -396,18 +474,34 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmEh, const FusedParams p) {
 #pragma unroll
                     for (int u = 0; u < w2; ++u) m[u] = fminf(m[u], m[u + w2]);
                 const float mn = m[0];
-                if (mn <= b1 + thr && mn < INFINITY) {
-                    b1 = fminf(b1, mn);
-                    const float band = mn + thr;
+                const float2 ck = *reinterpret_cast<const float2*>(ck_s + (as * 8 + (c >> 5)) * 2);
+                const float epsc = fmaf(zn, ck.x, fabsf(ck.y)) + rterm;
+                if (mn - epsc <= ub && mn < INFINITY) {
+                    // (at warp level this branch is the COMMON case -- some lane of 32 improves its running bound in most chunks --
+                    // so its usual form stays as light as the comparison against one band: the codes that pass the chunk-wide bound
+                    // first, the per-code bound only for those)
+                    ub = fminf(ub, mn + epsc);                              // the chunk minimum's own upper bound (eps_k <= epsc)
+                    const float band = ub + epsc;                           // = min(old ub, mn + epsc) + epsc: at most mn + 2 epsc
                     unsigned near = 0;
 #pragma unroll
                     for (int u = 0; u < 32; ++u) near |= (d[u] <= band) ? (1u << u) : 0u;
-                    if (__popc(near) == 1) {                                 // the usual case: the chunk minimum alone
-                        const int code = j * TN + c + (__ffs(near) - 1);
-                        const int n = cnt & 0x7fffffff;
-                        if (n < CAP) { cand_d[n * 256 + slot] = mn; cand_c[n * 256 + slot] = (uint16_t)code; ++cnt; }
-                        else cnt = cand_push(mn, code, b1 + thr, cnt, slot, cand_d, cand_c);
-                    } else {
+                    const float* pac = pa_s + as * TN + c;
+                    const float* qac = qa_s + as * TN + c;
+                    const int nn = __popc(near);
+                    if (nn == 1) {                                            // the usual case: the chunk minimum alone
+                        const int u = __ffs(near) - 1;
+                        float lo = mn - epsc;                                 // homogeneous chunk: the chunk-wide bound is the code's
+                        if (ck.y < 0.f) {                                     // mixed norms (warp-uniform): the code's own bound
+                            const float eu = fmaf(zn, pac[u], qac[u]) + rterm;
+                            ub = fminf(ub, mn + eu);
+                            lo = mn - eu;
+                        }
+                        if (lo <= ub) {
+                            const int code = j * TN + c + u;
+                            if (cnt < CAP) { cand_d[cnt * 256 + slot] = lo; cand_c[cnt * 256 + slot] = (uint16_t)code; ++cnt; }
+                            else cnt = cand_push(lo, code, ub, cnt, slot, cand_d, cand_c, drop_s);
+                        }
+                    } else if (nn <= 4) {
 #pragma unroll 1
                         while (near) {
                             const int u = __ffs(near) - 1;
@@ -416,7 +510,35 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmEh, const FusedParams p) {
                             float du = d[0];
 #pragma unroll
                             for (int t = 1; t < 32; ++t) du = (u == t) ? d[t] : du;
-                            cnt = cand_push(du, j * TN + c + u, b1 + thr, cnt, slot, cand_d, cand_c);
+                            const float eu = fmaf(zn, pac[u], qac[u]) + rterm;
+                            ub = fminf(ub, du + eu);
+                            if (du - eu <= ub) cnt = cand_push(du - eu, j * TN + c + u, ub, cnt, slot, cand_d, cand_c, drop_s);
+                        }
+                    } else {
+                        // many codes inside the chunk-wide band (a chunk that mixes one large-norm code with decayed ones): all
+                        // 32 per-code bounds at once, then the few that remain
+                        float hmin = INFINITY;
+#pragma unroll
+                        for (int u = 0; u < 32; u += 4) {
+                            const float4 p4 = *reinterpret_cast<const float4*>(pac + u);
+                            const float4 q4 = *reinterpret_cast<const float4*>(qac + u);
+                            const float e0 = fmaf(zn, p4.x, q4.x) + rterm, e1 = fmaf(zn, p4.y, q4.y) + rterm;
+                            const float e2 = fmaf(zn, p4.z, q4.z) + rterm, e3 = fmaf(zn, p4.w, q4.w) + rterm;
+                            hmin = fminf(fminf(hmin, d[u] + e0), fminf(d[u + 1] + e1, fminf(d[u + 2] + e2, d[u + 3] + e3)));
+                            d[u] -= e0; d[u + 1] -= e1; d[u + 2] -= e2; d[u + 3] -= e3;
+                        }
+                        ub = fminf(ub, hmin);
+                        near = 0;
+#pragma unroll
+                        for (int u = 0; u < 32; ++u) near |= (d[u] <= ub) ? (1u << u) : 0u;
+#pragma unroll 1
+                        while (near) {
+                            const int u = __ffs(near) - 1;
+                            near &= near - 1;
+                            float du = d[0];
+#pragma unroll
+                            for (int t = 1; t < 32; ++t) du = (u == t) ? d[t] : du;
+                            cnt = cand_push(du, j * TN + c + u, ub, cnt, slot, cand_d, cand_c, drop_s);
                         }
                     }
                 }
@@ -439,10 +561,10 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmEh, const FusedParams p) {
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa_rank(ptx::smem_u32(&tempty[as]), 0));
             if (++as == 2) { as = 0; aph ^= 1; }
-            e2_s[as * TN + et] = e2_next;
+            stage_norms(as, e2_next, pa_next, qa_next, ck_next);
         }
         // rows (or codebooks) that do not survive the fp16 rounding take the exact scan of the whole codebook
-        rbest[slot] = b1; rcnt[slot] = (rcode[TM + row] != 0 || !(emax < INFINITY)) ? (int)0x80000000 : cnt;
+        rbest[slot] = ub; rcnt[slot] = (rcode[TM + row] != 0 || !(emax < INFINITY)) ? (int)0x80000000 : cnt;
         epi_sync();
         VQ_TRACE(2);                                                        // scan of every code tile done
 
@@ -453,8 +575,9 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmEh, const FusedParams p) {
         if (et == 0) *und_n = 0;
         epi_sync();
         if (et < TM) {
-            const float bound = fminf(rbest[et], rbest[TM + et]) + tie_threshold(zsq_s[et], emax, sqrt_d);
-            const int my_ca = rcnt[et], my_cb = rcnt[TM + et];
+            const float bound = fminf(rbest[et], rbest[TM + et]);
+            int my_ca = rcnt[et], my_cb = rcnt[TM + et];
+            if (drop_s[et] <= bound || drop_s[TM + et] <= bound) { my_ca |= (int)0x80000000; rcnt[et] = my_ca; }   // the lists are incomplete
             int keep = 0, code = -1;
             if (((my_ca | my_cb) >> 31) == 0) {
                 for (int i = 0; i < my_ca; ++i) if (cand_d[i * 256 + et] <= bound) { ++keep; code = cand_c[i * 256 + et]; }
@@ -482,7 +605,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmEh, const FusedParams p) {
             float dist = INFINITY; int c2 = 0x7fffffff;
             bool have = false;
             if (((ca | cb2) >> 31) == 0) {
-                const float bound = fminf(rbest[rw], rbest[TM + rw]) + tie_threshold(zsq_s[rw], emax, sqrt_d);
+                const float bound = fminf(rbest[rw], rbest[TM + rw]);
               for (int cbase = 0; cbase < ca + cb2; cbase += 32) {       // the concatenated list of both halves, 32 entries per pass
                 float dme = INFINITY; int cme = 0x7fffffff;
                 const int li = cbase + lane;
@@ -618,7 +741,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmEh, const FusedParams p) {
 
 size_t fused_smem_bytes(int D) {
     const int kchunks = D / TK;
-    return (size_t)kchunks * Z_TILE + (size_t)ESTAGES * E_TILE + (size_t)CAP * 256 * 6 + (size_t)2 * TN * 4 + TM * 4 + 2 * TM * 4 * 3 +
+    return (size_t)kchunks * Z_TILE + (size_t)ESTAGES * E_TILE + (size_t)CAP * 256 * 6 + (size_t)3 * 2 * TN * 4 + (32 + 256) * 4 + TM * 4 + 2 * TM * 4 * 3 +
            16 * 4 + (1 + 2 * ESTAGES + 4) * 8 + 16 + 1024 + 64;
 }
 
@@ -626,7 +749,7 @@ size_t fused_smem_bytes(int D) {
 
 extern "C" int vqb_vq_prep_codebook(const float* codebook, void* cb_half, float* cb_sq, int K, int D, void* stream) {
     VQB_CHECK_ARG(codebook && cb_half && cb_sq && K > 0 && D > 0, "vq_prep_codebook: bad arguments");
-    vq_prep_codebook_kernel<<<(unsigned)ceil_div64((int64_t)K * 32, 256), 256, 0, as_stream(stream)>>>(codebook, (__half*)cb_half, cb_sq, K, D);
+    vq_prep_codebook_kernel<<<(unsigned)((K + 31) / 32), 1024, 0, as_stream(stream)>>>(codebook, (__half*)cb_half, cb_sq, K, D);
     VQB_CHECK_LAUNCH("vq_prep_codebook");
     return VQB_OK;
 }
@@ -635,7 +758,7 @@ extern "C" int vqb_vq_ema_update_prep(float* ema_count, float* ema_weight, float
                                       void* cb_half, float* cb_sq, int K, int D, float decay, float eps, float batch, void* stream) {
     VQB_CHECK_ARG(ema_count && ema_weight && codebook && counts && dw && cb_half && cb_sq && K > 0 && D > 0,
                   "vq_ema_update_prep: bad arguments");
-    vq_ema_update_prep_kernel<<<(unsigned)ceil_div64((int64_t)K * 32, 256), 256, 0, as_stream(stream)>>>(
+    vq_ema_update_prep_kernel<<<(unsigned)((K + 31) / 32), 1024, 0, as_stream(stream)>>>(
         ema_count, ema_weight, codebook, counts, dw, (__half*)cb_half, cb_sq, K, D, decay, eps, batch);
     VQB_CHECK_LAUNCH("vq_ema_update_prep");
     return VQB_OK;

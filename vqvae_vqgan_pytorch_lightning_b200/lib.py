@@ -12,7 +12,8 @@ from typing import Optional
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libvqgan_b200.so')
+# VQB_LIB: another build of the same library (A/B measurements of one kernel on one box, tools/); default: the in-tree build
+LIB_PATH = os.environ.get('VQB_LIB') or os.path.join(HERE, 'libvqgan_b200.so')
 
 F32, BF16 = 0, 1
 ACT_NONE, ACT_TANH, ACT_SILU, ACT_LRELU, ACT_RELU = 0, 1, 2, 3, 4

@@ -1020,7 +1020,7 @@ class CodebookPrep:
         k, d = codebook.shape
         if self.hf is None or self.hf.shape != (k, d) or self.hf.device != codebook.device:
             self.hf = torch.empty(k, d, dtype=torch.float16, device=codebook.device)
-            self.sq = torch.empty(k, dtype=torch.float32, device=codebook.device)
+            self.sq = torch.empty(4 * k, dtype=torch.float32, device=codebook.device)     # norms + error-bound coefficients (vq_fused.cu)
 
     def get(self, codebook: torch.Tensor):
         key = self._key(codebook)
@@ -1194,6 +1194,23 @@ def _gemm_nk(x2d: torch.Tensor, wp: torch.Tensor, k_in: int, k_out: int, residua
     return y
 
 
+def _entropy_tc_ok(codebook: torch.Tensor, n: int, k: int, d: int) -> bool:
+    """VQB_ENTROPY_TC=0: the entropy quantizer's GEMMs on the fp32 SIMT kernels in fast mode too (A/B measurements)"""
+    import os
+    return (get_precision().name == 'fast' and d % 64 == 0 and k % 128 == 0 and n >= 1024 and codebook.dtype == torch.float32 and
+            codebook.is_contiguous() and os.environ.get('VQB_ENTROPY_TC', '1') != '0' and bool(lib.load().vqb_device_supports_tcgen05()))
+
+
+def _codebook_as_conv_weight(codebook: torch.Tensor) -> torch.Tensor:
+    """[K,D] codebook as the weight [K,D,1,1] of a 1x1 convolution over the latent grid.  ONE view object per codebook storage, kept
+    on the parameter: the packed-weight caches are keyed by the weight object."""
+    v = getattr(codebook, '_vqb_view4', None)
+    if v is None or v.data_ptr() != codebook.data_ptr() or v.shape[:2] != codebook.shape:
+        v = codebook.detach().view(codebook.shape[0], codebook.shape[1], 1, 1)
+        codebook._vqb_view4 = v
+    return v
+
+
 class VQEntropyFn(torch.autograd.Function):
     """EntropyVectorQuantizer.forward (vector_quantizers.py:290-356): nearest code on d = (|z|^2 - 2 z.e) + |e|^2, straight-through
     output, (1+beta)-weighted MSE terms and the entropy regulariser ratio * (mean_i H(p_i) - H(mean_i p_i)), p = softmax(-d/T).
@@ -1207,9 +1224,20 @@ class VQEntropyFn(torch.autograd.Function):
         cb = codebook.detach().float().contiguous()
         n, k = flat.shape[0], cb.shape[0]
         dev = flat.device
-        cbt = torch.empty(d * k, dtype=torch.float32, device=dev)                       # E^T as a packed 1x1 weight [D][K]
-        call('vqb_pack_conv_weight', ptr(cb), ptr(cbt), F32, 0, k, d, 1, 1, 1.0, stream())
-        m = _gemm_nk(flat, cbt, d, k)                                                    # dot products [N,K]
+        use_tc = _entropy_tc_ok(codebook, n, k, d)
+        if use_tc:
+            # fast mode: the three GEMMs of this quantizer ride the tcgen05 1x1 convolution kernels.  The dot products feed a
+            # softmax at T = 0.01 (a 100x gain on every distance error), so the forward product runs on SPLIT-PRECISION operands
+            # (bf16 hi / lo halves, three products per multiply in one fp32 accumulator, ~2^-16 relative -- the strict mode's
+            # convolution arithmetic); the two gradient products run on plain bf16 operands like every other gradient of this mode.
+            w4 = _codebook_as_conv_weight(codebook)
+            m4 = _conv_fwd_raw(2, split_hi_lo(z), _packed_split_weight(w4, 3, False), None, None, torch.float32, d, k, 1, 1, 0, 1,
+                               ACT_NONE, 0.0, 1.0)                                       # [B,K,h,w] channels-last = [N,K]
+            m = m4.permute(0, 2, 3, 1).reshape(n, k)
+        else:
+            cbt = torch.empty(d * k, dtype=torch.float32, device=dev)                   # E^T as a packed 1x1 weight [D][K]
+            call('vqb_pack_conv_weight', ptr(cb), ptr(cbt), F32, 0, k, d, 1, 1, 1.0, stream())
+            m = _gemm_nk(flat, cbt, d, k)                                                # dot products [N,K]
         cb_sq = torch.empty(k, dtype=torch.float32, device=dev)
         call('vqb_row_sqnorm', ptr(cb), ptr(cb_sq), k, d, stream())
         idx = torch.empty(n, dtype=torch.int64, device=dev)
@@ -1231,6 +1259,7 @@ class VQEntropyFn(torch.autograd.Function):
         loss = (sums[0] * ((1.0 + beta) / flat.numel())).float() + ent[0]
         ctx.save_for_backward(flat, q, idx, m, colsum_p, cb)
         ctx.cfg = (beta, ratio, temperature, z.shape, bool(argmax_target))
+        ctx.w4 = w4 if use_tc else None
         qz = q.reshape(b, h, w, d).permute(0, 3, 1, 2)
         ctx.mark_non_differentiable(idx)
         return qz, idx.reshape(b, h * w), loss
@@ -1250,13 +1279,20 @@ class VQEntropyFn(torch.autograd.Function):
         g = m.clone()                                                                    # keep logp intact for a second backward call
         call('vqb_vq_entropy_bwd_rows', ptr(g), ptr(colsum_p), ptr(gl), ratio, temperature, n, k, ptr(idx) if argmax_target else None,
              stream())
-        dz = _gemm_nk(g, cb, k, d, residual=dz, gain=-2.0)                               # dz += -2 G E   (wp[(k)][d] = E itself)
-        gtz = torch.zeros(k * d, dtype=torch.float32, device=dev)
-        call('vqb_conv2d_wgrad', 0, ptr(g), F32, ptr(flat), F32, ptr(gtz), n, 1, 1, k, d, 1, 1, 0, 1, stream())   # G^T Z
+        b, _, h, w = zshape
+        if ctx.w4 is not None:
+            gb = as_nhwc(g.view(b, h, w, k).permute(0, 3, 1, 2), torch.bfloat16)         # [B,K,h,w] channels-last
+            ge = _dgrad_raw(gb, ctx.w4, h, w, 0, 1, 1.0, torch.float32)                  # G E  [B,D,h,w]
+            dz.add_(ge.permute(0, 2, 3, 1).reshape(n, d), alpha=-2.0)
+            zb = as_nhwc(flat.view(b, h, w, d).permute(0, 3, 1, 2), torch.bfloat16)
+            gtz = _wgrad_raw(zb, gb, (k, d, 1, 1), 0, 1, 1.0).reshape(k * d)              # G^T Z  [K][D]
+        else:
+            dz = _gemm_nk(g, cb, k, d, residual=dz, gain=-2.0)                           # dz += -2 G E   (wp[(k)][d] = E itself)
+            gtz = torch.zeros(k * d, dtype=torch.float32, device=dev)
+            call('vqb_conv2d_wgrad', 0, ptr(g), F32, ptr(flat), F32, ptr(gtz), n, 1, 1, k, d, 1, 1, 0, 1, stream())   # G^T Z
         colsum_g = torch.zeros(k, dtype=torch.float32, device=dev)
         call('vqb_colsum', ptr(g), F32, ptr(colsum_g), n, k, stream())
         call('vqb_vq_entropy_combine_dcb', ptr(dcb), ptr(cb), ptr(colsum_g), ptr(gtz), k, d, stream())
-        b, _, h, w = zshape
         return dz.reshape(b, h, w, d).permute(0, 3, 1, 2), dcb, None, None, None, None
 
 
