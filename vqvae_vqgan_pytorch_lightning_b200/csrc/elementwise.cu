@@ -273,29 +273,34 @@ __global__ void pack_weights_batched_kernel(const PackDesc* __restrict__ d, int 
         for (int tl = t0; tl < ntiles; tl += nch) {
             const int co0 = (tl / tci) * PACK_T, ci0 = (tl % tci) * PACK_T;
             const int nco = min(PACK_T, Co - co0), nci = min(PACK_T, Ci - ci0);
-            const int run = nci * T, cnt = nco * run;
+            const int run = nci * T;
             __syncthreads();                                               // the previous tile has been written out
-            for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
-                const int r = i / run, k = i - r * run;
-                tile[r][k] = e.w[((long long)(co0 + r) * Ci + ci0) * T + k];
+            // (loop nests instead of a flat index: no integer division by run-time extents anywhere -- the element-wise form spent
+            // more time on its five div / mod pairs per element than on memory)
+            const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+            for (int r = warp; r < nco; r += nw) {
+                const float* src = e.w + ((long long)(co0 + r) * Ci + ci0) * T;
+                for (int k = lane; k < run; k += 32) tile[r][k] = src[k];
             }
             __syncthreads();
-            for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
-                int col, cil, tp;                                          // tp: tap position in the DESTINATION
-                if (e.mode == 0) { col = i % nco; const int r = i / nco; cil = r % nci; tp = r / nci; }
-                else if (e.mode == 1) { cil = i % nci; const int r = i / nci; col = r % nco; tp = r / nco; }
-                else if (e.mode == 2) { cil = i % nci; const int r = i / nci; tp = r % T; col = r / T; }
-                else { col = i % nco; const int r = i / nco; tp = r % T; cil = r / T; }
-                const float v = tile[col][cil * T + (flip ? T - 1 - tp : tp)] * e.scale;
-                const int co = co0 + col, ci = ci0 + cil;
-                long long j;
-                if (e.mode == 0) j = ((long long)tp * Ci + ci) * Co + co;
-                else if (e.mode == 1) j = ((long long)tp * Co + co) * Ci + ci;
-                else if (e.mode == 2) j = ((long long)co * T + tp) * Ci + ci;
-                else j = ((long long)ci * T + tp) * Co + co;
-                if (e.bf16) reinterpret_cast<bf16*>(e.wp)[j] = __float2bfloat16_rn(v);
-                else reinterpret_cast<float*>(e.wp)[j] = v;
-            }
+            const bool inner_co = (e.mode == 0 || e.mode == 3);            // which of co / ci is innermost in the destination
+            const int n_in = inner_co ? nco : nci, n_out = inner_co ? nci : nco;
+            if (lane < n_in)
+                for (int tp = 0; tp < T; ++tp) {                           // tp: tap position in the DESTINATION
+                    const int ts = flip ? T - 1 - tp : tp;
+                    for (int o = warp; o < n_out; o += nw) {
+                        const int col = inner_co ? lane : o, cil = inner_co ? o : lane;
+                        const float v = tile[col][cil * T + ts] * e.scale;
+                        const int co = co0 + col, ci = ci0 + cil;
+                        long long j;
+                        if (e.mode == 0) j = ((long long)tp * Ci + ci) * Co + co;
+                        else if (e.mode == 1) j = ((long long)tp * Co + co) * Ci + ci;
+                        else if (e.mode == 2) j = ((long long)co * T + tp) * Ci + ci;
+                        else j = ((long long)ci * T + tp) * Co + co;
+                        if (e.bf16) reinterpret_cast<bf16*>(e.wp)[j] = __float2bfloat16_rn(v);
+                        else reinterpret_cast<float*>(e.wp)[j] = v;
+                    }
+                }
         }
         return;
     }
