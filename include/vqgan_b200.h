@@ -227,6 +227,12 @@ int vqb_up2(const void* x, void* y, int dtype, int N, int H, int W, int C, float
  * ---------------------------------------------------------------------------------------------------- */
 /* out[0] += sum (a-b)^2 ; out[1] += sum |a-b|   (double[2], caller zero-fills) */
 int vqb_diff_sums(const void* a, int a_dtype, const void* b, int b_dtype, double* out, int64_t n, void* stream);
+/* SSIM of the test-time evaluation (vqvae/model.py:495, 529-530, 549: torchmetrics StructuralSimilarityIndexMeasure() defaults --
+ * 11 x 11 Gaussian window, sigma 1.5, k1 0.01, k2 0.03, valid windows of the un-padded image): per_image_sum[n] += sum over
+ * (C, H-10, W-10) of the SSIM map of image n (double[N], caller zero-fills; the image's SSIM is that sum / (C (H-10) (W-10))).
+ * preds / target: NCHW fp32; data_range: ONE float in device memory (max(preds.max - preds.min, target.max - target.min)). */
+int vqb_ssim_sums(const float* preds, const float* target, const float* data_range, double* per_image_sum, int N, int C, int H,
+                  int W, float k1, float k2, void* stream);
 /* da = c2 * 2*(a-b) * up2 + c1 * sign(a-b) * up1, (up2, up1) = upstream ? (upstream[0], upstream[1]) : (1, 1)
  * (device scalars: the upstream gradients of the L2 and L1 means); when y_tanh!=0 `a` is a tanh output and the
  * result is additionally multiplied by (1-a^2) (grad wrt the pre-activation) */

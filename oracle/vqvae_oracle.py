@@ -304,6 +304,34 @@ def linear_cosine_schedule(step: int, start_step: int, stop_step: int, start_val
 # --------------------------------------------------------------------------------------
 # one training step, plain VQ-VAE branch (vqvae/model.py:232-295 branch C, + optimizer)
 # --------------------------------------------------------------------------------------
+def ssim_torchmetrics(preds: Tensor, target: Tensor, kernel_size: int = 11, sigma: float = 1.5, k1: float = 0.01,
+                      k2: float = 0.03) -> Tensor:
+    """Per-image SSIM as the reference's evaluation computes it (vqvae/model.py:495, 529-530: torchmetrics
+    StructuralSimilarityIndexMeasure() with its defaults).  PARITY UNPINNED: torchmetrics is a third-party dependency that is
+    absent from this image; this restates its published algorithm (functional/image/ssim.py, v1.x): reflect-pad by
+    (kernel_size - 1) / 2, depth-wise Gaussian filtering of (x, y, x^2, y^2, xy), variances clamped at 0, the padded border
+    cropped again, mean over (C, H', W') per image; data_range=None -> max of the two batch ranges."""
+    c = preds.shape[1]
+    data_range = torch.maximum(preds.max() - preds.min(), target.max() - target.min())
+    c1, c2 = (k1 * data_range) ** 2, (k2 * data_range) ** 2
+    dist = torch.arange((1 - kernel_size) / 2, (1 + kernel_size) / 2, 1, dtype=preds.dtype)
+    g = torch.exp(-((dist / sigma) ** 2) / 2)
+    g = (g / g.sum()).unsqueeze(0)
+    kernel = (g.t() @ g).expand(c, 1, kernel_size, kernel_size)
+    pad = (kernel_size - 1) // 2
+    p = F.pad(preds, (pad, pad, pad, pad), mode='reflect')
+    t = F.pad(target, (pad, pad, pad, pad), mode='reflect')
+    stack = torch.cat((p, t, p * p, t * t, p * t))
+    out = F.conv2d(stack, kernel, groups=c).split(preds.shape[0])
+    mu_p2, mu_t2, mu_pt = out[0] ** 2, out[1] ** 2, out[0] * out[1]
+    s_p = torch.clamp(out[2] - mu_p2, min=0.0)
+    s_t = torch.clamp(out[3] - mu_t2, min=0.0)
+    s_pt = out[4] - mu_pt
+    upper, lower = 2 * s_pt + c2, s_p + s_t + c2
+    full = ((2 * mu_pt + c1) * upper) / ((mu_p2 + mu_t2 + c1) * lower)
+    return full[..., pad:-pad, pad:-pad].reshape(preds.shape[0], -1).mean(-1)
+
+
 def normalize_images(images01: Tensor) -> Tensor:
     """abstract_modules/base_autoencoder.py:41-50 without the kornia augmentation: clamp to [0,1], (x-.5)/.5."""
     return (torch.clamp(images01, 0.0, 1.0) - 0.5) / 0.5

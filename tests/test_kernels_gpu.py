@@ -328,6 +328,26 @@ def test_test_step_metrics_match_definitions(V):
     usage = sum(torch.bincount(model.get_tokens(b).view(-1), minlength=32) for b in batches)
     assert torch.equal(model.test_usage_count, usage) and int(usage.sum()) == 12 * 64
     assert 0 < float(model.logged['perplexity']) <= 32
+    # SSIM: mean over all images of the per-image values, each batch with its own data range (torchmetrics' update / compute)
+    ssim = torch.cat([orc.ssim_torchmetrics(model.reconstruct(b).cpu(), b.cpu()) for b in batches]).mean()
+    assert abs(float(model.logged['ssim']) - float(ssim)) < 2e-5
+
+
+@pytest.mark.parametrize('shape', [(2, 3, 32, 32), (3, 3, 64, 48), (1, 1, 11, 11), (2, 3, 256, 256), (5, 2, 27, 45)])
+def test_ssim_kernel_matches_published_definition(V, shape):
+    """vqb_ssim_sums against the restated torchmetrics algorithm (oracle.ssim_torchmetrics: reflect pad + depth-wise Gaussian
+    conv + crop), close image pairs and unrelated ones, ragged tile edges, the smallest legal image (one window)."""
+    from vqvae_vqgan_pytorch_lightning_b200 import ops
+    torch.manual_seed(3)
+    tgt = torch.rand(*shape)
+    for noise in (0.0, 0.05, 1.0):
+        rec = (tgt + noise * torch.randn(*shape)).clamp(0, 1) if noise < 1.0 else torch.rand(*shape)
+        got = ops.ssim_per_image(rec.cuda(), tgt.cuda()).cpu()
+        ref = orc.ssim_torchmetrics(rec.double(), tgt.double())
+        assert got.shape == ref.shape
+        assert float((got - ref).abs().max()) < 2e-5, (shape, noise, got, ref)
+        if noise == 0.0:
+            assert float((got - 1.0).abs().max()) < 1e-6
 
 
 def test_batched_weight_pack_equals_single_packs(V):

@@ -115,3 +115,28 @@ def test_oracle_entropy_quantizer_matches_reference_module(loss_type):
     assert abs(float(loss) - float(g['loss'])) < 1e-6
     assert np.allclose(z.grad.numpy(), g['dz'], atol=2e-5 * np.abs(g['dz']).max())
     assert np.allclose(cb.grad.numpy(), g['dcb'], atol=2e-5 * np.abs(g['dcb']).max())
+
+
+def test_oracle_ssim_properties():
+    """oracle.ssim_torchmetrics (restated published algorithm; torchmetrics is absent, parity unpinned): identity, symmetry,
+    invariance under a common scaling (data_range=None follows the images), and the reflect-pad + crop form equals VALID
+    Gaussian windows of the un-padded image -- the form the CUDA kernel evaluates."""
+    import torch.nn.functional as F
+    torch.manual_seed(0)
+    x = torch.rand(2, 3, 40, 36, dtype=torch.float64)
+    y = (x + 0.1 * torch.randn_like(x)).clamp(0, 1)
+    s = orc.ssim_torchmetrics(x, y)
+    assert s.shape == (2,) and bool((s < 1).all()) and bool((s > 0).all())
+    assert float((orc.ssim_torchmetrics(x, x) - 1).abs().max()) < 1e-12
+    assert float((orc.ssim_torchmetrics(y, x) - s).abs().max()) < 1e-12
+    assert float((orc.ssim_torchmetrics(3 * x, 3 * y) - s).abs().max()) < 1e-10
+    dist = torch.arange(-5, 6, dtype=torch.float64)
+    g = torch.exp(-((dist / 1.5) ** 2) / 2); g = g / g.sum()
+    k = torch.outer(g, g).expand(3, 1, 11, 11)
+    R = torch.maximum(x.max() - x.min(), y.max() - y.min())
+    c1, c2 = (0.01 * R) ** 2, (0.03 * R) ** 2
+    f = lambda t: F.conv2d(t, k, groups=3)
+    mx, my = f(x), f(y)
+    sx, sy, sxy = (f(x * x) - mx * mx).clamp(min=0), (f(y * y) - my * my).clamp(min=0), f(x * y) - mx * my
+    direct = (((2 * mx * my + c1) * (2 * sxy + c2)) / ((mx * mx + my * my + c1) * (sx + sy + c2))).reshape(2, -1).mean(-1)
+    assert float((direct - s).abs().max()) < 1e-12

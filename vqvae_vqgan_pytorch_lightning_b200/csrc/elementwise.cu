@@ -618,6 +618,86 @@ __global__ void diff_sums_kernel(const TA* __restrict__ a, const TB* __restrict_
     }
 }
 
+// ---- SSIM (evaluation, vqvae/model.py:495, 529-530, 549: torchmetrics StructuralSimilarityIndexMeasure with its defaults) -----------
+// Published definition (torchmetrics functional/image/ssim.py, gaussian_kernel = True, kernel_size 11, sigma 1.5, k1 0.01,
+// k2 0.03): both images are reflect-padded by 5, filtered with the separable Gaussian window, and the border the padding
+// touched is cropped again -- i.e. the windows are the VALID 11 x 11 windows of the un-padded image.  Per window:
+//   c1 = (k1 R)^2, c2 = (k2 R)^2, R = data range;  mu = E[x], mu' = E[y], s = max(E[x^2] - mu^2, 0), s' likewise, sxy = E[xy] - mu mu'
+//   ssim = ((2 mu mu' + c1)(2 sxy + c2)) / ((mu^2 + mu'^2 + c1)(s + s' + c2))
+// and an image's value is the mean over (C, H-10, W-10).  One CTA = one 16 x 16 tile of windows of one (image, channel) plane:
+// the 26 x 26 input patches in shared memory, a horizontal pass into shared memory (five moments), a vertical pass in registers,
+// fp64 sum per image.  NCHW fp32 inputs (the test-time images).
+constexpr int SSIM_T = 16, SSIM_K = 11, SSIM_P = SSIM_T + SSIM_K - 1;
+__global__ void __launch_bounds__(256) ssim_sums_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ range,
+                                                         double* __restrict__ out, int C, int H, int W, float k1, float k2) {
+    __shared__ float pa[SSIM_P][SSIM_P + 1], pb[SSIM_P][SSIM_P + 1];
+    __shared__ float hz[5][SSIM_P][SSIM_T + 1];
+    __shared__ float g[SSIM_K];
+    __shared__ double red[8];
+    const int plane = blockIdx.z, n = plane / C;
+    const int x0 = blockIdx.x * SSIM_T, y0 = blockIdx.y * SSIM_T;
+    const int OW = W - SSIM_K + 1, OH = H - SSIM_K + 1;
+    const float* pa_g = a + (int64_t)plane * H * W;
+    const float* pb_g = b + (int64_t)plane * H * W;
+    if (threadIdx.x == 0) {
+        float w[SSIM_K], sum = 0.f;
+        for (int i = 0; i < SSIM_K; ++i) { const float d = (float)(i - SSIM_K / 2) / 1.5f; w[i] = expf(-0.5f * d * d); sum += w[i]; }
+        for (int i = 0; i < SSIM_K; ++i) g[i] = w[i] / sum;
+    }
+    for (int i = threadIdx.x; i < SSIM_P * SSIM_P; i += 256) {
+        const int r = i / SSIM_P, c = i - r * SSIM_P;
+        const int y = y0 + r, x = x0 + c;
+        const bool in = y < H && x < W;
+        pa[r][c] = in ? pa_g[(int64_t)y * W + x] : 0.f;
+        pb[r][c] = in ? pb_g[(int64_t)y * W + x] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < SSIM_P * SSIM_T; i += 256) {                    // horizontal pass: rows 0..25, window columns 0..15
+        const int r = i / SSIM_T, c = i - r * SSIM_T;
+        float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f, m4 = 0.f;
+#pragma unroll
+        for (int t = 0; t < SSIM_K; ++t) {
+            const float u = pa[r][c + t], v = pb[r][c + t], w = g[t];
+            m0 = fmaf(w, u, m0); m1 = fmaf(w, v, m1); m2 = fmaf(w, u * u, m2); m3 = fmaf(w, v * v, m3); m4 = fmaf(w, u * v, m4);
+        }
+        hz[0][r][c] = m0; hz[1][r][c] = m1; hz[2][r][c] = m2; hz[3][r][c] = m3; hz[4][r][c] = m4;
+    }
+    __syncthreads();
+    const int ty = threadIdx.x / SSIM_T, tx = threadIdx.x % SSIM_T;
+    double val = 0.0;
+    if (y0 + ty < OH && x0 + tx < OW) {
+        float m[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int t = 0; t < SSIM_K; ++t)
+#pragma unroll
+            for (int q = 0; q < 5; ++q) m[q] = fmaf(g[t], hz[q][ty + t][tx], m[q]);
+        const float R = range[0], c1 = (k1 * R) * (k1 * R), c2 = (k2 * R) * (k2 * R);
+        const float mua2 = m[0] * m[0], mub2 = m[1] * m[1], muab = m[0] * m[1];
+        const float sa = fmaxf(m[2] - mua2, 0.f), sb = fmaxf(m[3] - mub2, 0.f), sab = m[4] - muab;
+        const float upper = 2.f * sab + c2, lower = sa + sb + c2;
+        val = (double)(((2.f * muab + c1) * upper) / ((mua2 + mub2 + c1) * lower));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = val;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < 8; ++i) t += red[i];
+        atomicAdd(out + n, t);
+    }
+}
+
+extern "C" int vqb_ssim_sums(const float* preds, const float* target, const float* data_range, double* per_image_sum, int N, int C, int H,
+                             int W, float k1, float k2, void* stream) {
+    VQB_CHECK_ARG(preds && target && data_range && per_image_sum && N > 0 && C > 0, "ssim_sums: bad arguments");
+    VQB_CHECK_ARG(H >= SSIM_K && W >= SSIM_K && (int64_t)N * C <= 65535, "ssim_sums: needs H, W >= 11 and N * C <= 65535 (got %d x %d, %d planes)", H, W, N * C);
+    dim3 grid((unsigned)ceil_div64(W - SSIM_K + 1, SSIM_T), (unsigned)ceil_div64(H - SSIM_K + 1, SSIM_T), (unsigned)(N * C));
+    ssim_sums_kernel<<<grid, 256, 0, as_stream(stream)>>>(preds, target, data_range, per_image_sum, C, H, W, k1, k2);
+    VQB_CHECK_LAUNCH("ssim_sums");
+    return VQB_OK;
+}
+
 extern "C" int vqb_diff_sums(const void* a, int a_dtype, const void* b, int b_dtype, double* out, int64_t n, void* stream) {
     VQB_CHECK_ARG(a && b && out && n > 0, "diff_sums: bad arguments");
     int g = grid_for(n, 256, 4);

@@ -56,6 +56,7 @@ SIGNATURES = {
     'vqb_mbstd_fwd': (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p]),
     'vqb_mbstd_bwd': (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _i, _p]),
     'vqb_colsum': (_i, [_p, _i, _p, _i64, _i, _p]),
+    'vqb_ssim_sums': (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _f, _f, _p]),
     'vqb_gn_stats': (_i, [_p, _i, _p, _i, _i, _i, _i, _p]),
     'vqb_gn_finalize': (_i, [_p, _p, _i, _i, _i, _i, _f, _p]),
     'vqb_gn_apply': (_i, [_p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),

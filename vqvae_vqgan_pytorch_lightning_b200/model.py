@@ -248,25 +248,27 @@ class VQVAE(BaseVQVAE, LightningModule):
     def on_test_epoch_start(self):
         """MSE and PSNR are accumulated with the library's own reduction kernel (vqb_diff_sums, fp64 sums), following
         torchmetrics' definitions (MeanSquaredError: sum of squared errors / elements; PeakSignalNoiseRatio with
-        data_range=None: 10 log10((max - min of all targets)^2 / MSE)).  SSIM and rFID are delegated to torchmetrics exactly as
-        in the reference when that package is installed (un-pinned third-party arithmetic, off the hot path); otherwise they are
-        not logged.  Codebook usage ACCUMULATES over the epoch (the reference's `else + used_indices` keeps the last batch only)."""
+        data_range=None: 10 log10((max - min of all targets)^2 / MSE)).  SSIM is the library's own kernel (vqb_ssim_sums:
+        StructuralSimilarityIndexMeasure() defaults -- Gaussian 11 x 11 window, sigma 1.5, per-batch data range, mean over images;
+        torchmetrics' published algorithm, un-pinned: the package is absent here).  rFID needs torchmetrics AND its pretrained
+        Inception weights: it is delegated exactly as in the reference when both are available, otherwise not logged.
+        Codebook usage ACCUMULATES over the epoch (the reference's `else + used_indices` keeps the last batch only)."""
         dev = next(self.parameters()).device
         self._test_sse = torch.zeros((), dtype=torch.float64, device=dev)
         self._test_elems = 0
         self._test_min = torch.zeros((), device=dev)          # torchmetrics PeakSignalNoiseRatio(data_range=None) starts both at 0
         self._test_max = torch.zeros((), device=dev)
         self.test_usage_count = None
-        self.test_ssim = self.test_rfid = None
+        self._test_ssim_sum = torch.zeros((), dtype=torch.float64, device=dev)
+        self._test_images = 0
+        self.test_rfid = None
         try:
-            from torchmetrics.image import StructuralSimilarityIndexMeasure
-            self.test_ssim = StructuralSimilarityIndexMeasure().to(dev)
             from torchmetrics.image.fid import FrechetInceptionDistance
             self.test_rfid = FrechetInceptionDistance().to(dev)
-        except Exception as e:           # not installed (or its Inception weights are not downloadable): MSE / PSNR / usage only
+        except Exception as e:           # not installed (or its Inception weights are not downloadable)
             import warnings
-            warnings.warn(f'torchmetrics SSIM / rFID unavailable ({type(e).__name__}: {e}); only MSE, PSNR and codebook usage are logged')
-            self.test_ssim = self.test_rfid = None
+            warnings.warn(f'torchmetrics rFID unavailable ({type(e).__name__}: {e}); MSE, PSNR, SSIM and codebook usage are logged')
+            self.test_rfid = None
 
     @torch.no_grad()
     def test_step(self, images: Any, _: int = 0):
@@ -282,8 +284,8 @@ class VQVAE(BaseVQVAE, LightningModule):
         lo, hi = torch.aminmax(target)
         self._test_min = torch.minimum(self._test_min, lo)
         self._test_max = torch.maximum(self._test_max, hi)
-        if self.test_ssim is not None:
-            self.test_ssim.update(reconstructions, target)
+        self._test_ssim_sum += ops.ssim_per_image(reconstructions, target).sum()
+        self._test_images += target.shape[0]
         if self.test_rfid is not None:
             # torchvision ConvertImageDtype(torch.uint8) on float images (model.py:543-545): x * (255 + 1 - 1e-3), truncated
             to_u8 = lambda t: t.mul(255.999).to(torch.uint8)
@@ -295,8 +297,7 @@ class VQVAE(BaseVQVAE, LightningModule):
         self.log('mse', mse)
         data_range = (self._test_max - self._test_min).double()
         self.log('psnr', (10.0 * torch.log10(data_range * data_range / self._test_sse * max(self._test_elems, 1))).float())
-        if self.test_ssim is not None:
-            self.log('ssim', self.test_ssim.compute())
+        self.log('ssim', (self._test_ssim_sum / max(self._test_images, 1)).float())
         if self.test_rfid is not None:
             self.log('rfid', self.test_rfid.compute())
         if self.test_usage_count is not None:

@@ -1000,6 +1000,20 @@ def diff_sums(a, b) -> torch.Tensor:
     return sums
 
 
+def ssim_per_image(preds: torch.Tensor, target: torch.Tensor, k1: float = 0.01, k2: float = 0.03) -> torch.Tensor:
+    """SSIM of every image of an NCHW fp32 batch, fp64 [N] (vqb_ssim_sums: torchmetrics' StructuralSimilarityIndexMeasure() with
+    its defaults -- Gaussian 11 x 11 window, sigma 1.5, data_range=None = the larger of the two batch ranges; model.py:495, 529)."""
+    preds, target = preds.float().contiguous(), target.float().contiguous()
+    n, c, h, w = preds.shape
+    if target.shape != preds.shape:
+        raise lib.VQBError('ssim: shapes differ')
+    (plo, phi), (tlo, thi) = torch.aminmax(preds), torch.aminmax(target)
+    rng = torch.maximum(phi - plo, thi - tlo).reshape(1).float()
+    sums = torch.zeros(n, dtype=torch.float64, device=preds.device)
+    call('vqb_ssim_sums', ptr(preds), ptr(target), ptr(rng), ptr(sums), n, c, h, w, k1, k2, stream())
+    return sums / float(c * (h - 10) * (w - 10))
+
+
 # ------------------------------------------------------------------------------------------------------
 # vector quantisation
 # ------------------------------------------------------------------------------------------------------
