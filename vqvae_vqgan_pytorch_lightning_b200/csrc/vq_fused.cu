@@ -421,31 +421,39 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmEh, const FusedParams p) {
         int cnt = 0;                                                        // list length
         int as = 0; uint32_t aph = 0;
         drop_s[et] = INFINITY;
-        // code norms of a tile and the coefficients of their error bounds (prepared with the codebook, see prep_aux): thread et
-        // owns code et of the tile, threads 0-15 the eight chunk-wide pairs
+        // code norms of a tile and the coefficients of their error bounds (prepared with the codebook, see prep_aux) go from the
+        // auxiliary buffer to shared memory by cp.async, 16 bytes per thread (64 + 64 + 64 granules of four codes, 4 of two chunk
+        // pairs): nothing is held in registers across the scan of a tile (holding the four values of the next tile there spilled:
+        // 46 K local loads per launch that missed the 28 KB L1 a third of the time, right before the per-tile barrier)
         const int nchunk2 = 2 * ((p.K + 31) / 32);
-        auto load_norms = [&](const int tile, float& e2v, float& pav, float& qav, float& ckv) {
-            const int code = tile * TN + et;
-            const bool in = tile < p.ctiles && code < p.K;
-            e2v = in ? p.cb_sq[code] : INFINITY;                            // padding codes never qualify (d~ = inf)
-            pav = in ? p.cb_sq[p.K + code] : 0.f;
-            qav = in ? p.cb_sq[2 * p.K + code] : 0.f;
-            ckv = (et < 16 && tile < p.ctiles && tile * 16 + et < nchunk2) ? p.cb_sq[3 * p.K + tile * 16 + et] : 0.f;
+        auto fetch_norms = [&](const int tile, const int buf) {
+            if (et < 196) {
+                const int which = et >> 6, gq = (et & 63) * 4;
+                float* dst; const float* src; bool in;
+                if (which < 3) {
+                    const int code = tile * TN + gq;
+                    in = tile < p.ctiles && code < p.K;                     // K % 8 == 0: a granule is entirely in or out
+                    dst = (which == 0 ? e2_s : which == 1 ? pa_s : qa_s) + buf * TN + gq;
+                    src = p.cb_sq + (size_t)which * p.K + code;
+                } else {
+                    in = tile < p.ctiles && tile * 16 + gq < nchunk2;
+                    dst = ck_s + buf * 16 + gq;
+                    src = p.cb_sq + (size_t)3 * p.K + tile * 16 + gq;
+                }
+                if (in) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ptx::smem_u32(dst)), "l"(src) : "memory");
+                else {
+                    const float f = (which == 0) ? INFINITY : 0.f;          // padding codes never qualify (d~ = inf)
+                    *reinterpret_cast<float4*>(dst) = make_float4(f, f, f, f);
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
         };
-        auto stage_norms = [&](const int buf, const float e2v, const float pav, const float qav, const float ckv) {
-            e2_s[buf * TN + et] = e2v; pa_s[buf * TN + et] = pav; qa_s[buf * TN + et] = qav;
-            if (et < 16) ck_s[buf * 16 + et] = ckv;
-        };
-        {
-            float e2v, pav, qav, ckv;
-            load_norms(0, e2v, pav, qav, ckv);
-            stage_norms(0, e2v, pav, qav, ckv);                             // tile 0
-        }
+        fetch_norms(0, 0);                                                  // tile 0
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         for (int j = 0; j < p.ctiles; ++j) {
             epi_sync();                                                     // e2_s[as] written; every warp has left tile j-1
             // norms of the NEXT tile: loaded now, stored after this tile's scan (buffer as^1 was tile j-1's, free since the sync)
-            float e2_next, pa_next, qa_next, ck_next;
-            load_norms(j + 1, e2_next, pa_next, qa_next, ck_next);
+            fetch_norms(j + 1, as ^ 1);                                     // buffer as^1 was tile j-1's: free since the sync
             ptx::mbar_wait(&tfull[as], aph);
             ptx::tc_fence_after();
             const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * TN);
@@ -561,7 +569,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmEh, const FusedParams p) {
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa_rank(ptx::smem_u32(&tempty[as]), 0));
             if (++as == 2) { as = 0; aph ^= 1; }
-            stage_norms(as, e2_next, pa_next, qa_next, ck_next);
+            asm volatile("cp.async.wait_group 0;" ::: "memory");            // the next tile's norms have landed (visible after the sync)
         }
         // rows (or codebooks) that do not survive the fp16 rounding take the exact scan of the whole codebook
         rbest[slot] = ub; rcnt[slot] = (rcode[TM + row] != 0 || !(emax < INFINITY)) ? (int)0x80000000 : cnt;
