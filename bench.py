@@ -216,7 +216,7 @@ def vq_microbench(pkg, dev, n_lat, k, use_tc, pk, iters=15):
                       'tensor_tflops_algorithmic': flop / us / 1e6, 'tensor_frac_algorithmic': flop / us / 1e6 / pk['bf16_tflops'],
                       'rows_on_exact_path': und})
     c0 = cases[0]
-    return {'bound': 'hbm', 'kernel': 'vq_assign_tc' if use_tc else 'vq_assign (fp32 SIMT)', 'achieved': c0['gbs'], 'peak': pk['hbm_gbs'],
+    return {'bound': 'hbm', 'kernel': 'vq_fused_kernel (vqb_vq_fused: one launch, tcgen05 search + exact re-rank + gather / STE / SSE / EMA sums)' if use_tc else 'vq_assign (fp32 SIMT)', 'achieved': c0['gbs'], 'peak': pk['hbm_gbs'],
             'unit': 'GB/s', 'frac': c0['frac'], 'traffic': None, 'algorithmic_bytes': nbytes, 'algorithmic_flop': flop,
             'shape': {'N': n_lat, 'K': k, 'D': d}, 'cases': cases}
 
@@ -257,6 +257,93 @@ def cpu_reference_step(name: str, batch: int, image_size: int, codebook: int, st
             times.append(dt)
     sec = sum(times) / len(times)
     return batch / sec, sec
+
+
+class _TorchAdamW:
+    """torch.optim.AdamW (foreach) behind the three calls gan_oracle.train_step makes on its optimizers -- what the reference's
+    configure_optimizers returns (vqvae/model.py:424-440); the oracle's own per-tensor AdamW would be launch-bound on a GPU."""
+
+    def __init__(self, sd, oracle_opt):
+        self.lr = oracle_opt.lr
+        self.opt = torch.optim.AdamW([{'params': [sd[n] for n in names], 'weight_decay': wd} for names, wd in oracle_opt.groups],
+                                     lr=oracle_opt.lr, betas=oracle_opt.betas, eps=oracle_opt.eps, foreach=True)
+
+    def zero_grad(self):
+        self.opt.zero_grad(set_to_none=True)
+
+    def step(self):
+        for g in self.opt.param_groups:
+            g['lr'] = self.lr
+        self.opt.step()
+
+
+def torch_eager_gpu_step(name: str, batch: int, image_size: int, codebook: int, steps: int, warmup: int, dev, autocast: bool):
+    """Secondary baseline of SURVEY.md 8(d): the reference's arithmetic as stock torch EAGER ops on THIS GPU -- the oracle port of
+    the reference modules with its tensors on the device (cuDNN convolutions, ATen element-wise kernels, cuBLAS distances),
+    torch.optim.AdamW over the reference's parameter groups, inputs resident on the device.  autocast=True wraps the step in
+    torch.autocast(bfloat16), the counterpart of the reference's Trainer(precision='16-mixed') (vqvae/train.py:129).  None of this
+    repository's kernels run here.  Returns (images_per_sec, ms_per_step, peak GiB)."""
+    from oracle import gan_oracle as G
+    from oracle import init_state as oinit
+
+    class A:
+        pass
+    a = A(); a.batch, a.codebook, a.image_size = batch, codebook, image_size
+    image_size, ae_conf, q_conf, l_conf, t_conf, bs, codebook = model_confs(name, a, 1)
+    qtype = q_conf['type']
+    crit = None if l_conf is None else 'gan'
+    sd = oinit.init_state(qtype, codebook, q_conf['embedding_dim'], ae_conf['channels'], ae_conf['num_res_blocks'],
+                          tuple(ae_conf['channel_multipliers']), seed=1234, criterion=crit, image_size=image_size)
+    sd = oinit.make_leaf({k: v.to(dev) for k, v in sd.items()}, qtype)
+
+    def num(v):
+        try:
+            return float(v) if isinstance(v, str) else v
+        except ValueError:
+            return v
+    cfg = {'num_res_blocks': ae_conf['num_res_blocks'], 'channel_multipliers': tuple(ae_conf['channel_multipliers']),
+           'quantizer': dict({k: num(v) for k, v in (q_conf.get('params') or {}).items()}, type=qtype)}
+    opts = [_TorchAdamW(sd, o) for o in G.configure_optimizers(sd, t_conf, gan=(crit == 'gan'))]
+    x = torch.rand(batch, 3, image_size, image_size, device=dev)
+    torch.cuda.reset_peak_memory_stats(dev)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    for it in range(warmup + steps):
+        if it == warmup:
+            torch.cuda.synchronize(dev)
+            ev[0].record()
+        noise = (torch.empty(batch, codebook, image_size // 16, image_size // 16, device=dev).exponential_()
+                 if qtype == 'gumbel' else None)
+        with torch.autocast('cuda', dtype=torch.bfloat16, enabled=autocast):
+            G.train_step(sd, opts, x, cfg, l_conf, t_conf, 0, it, warmup + steps, exp_noise=noise)
+    ev[1].record()
+    torch.cuda.synchronize(dev)
+    ms = ev[0].elapsed_time(ev[1]) / steps
+    return batch / ms * 1e3, ms, torch.cuda.max_memory_allocated(dev) / 2 ** 30
+
+
+def torch_eager_gpu_baseline(name: str, image_size: int, codebook: int, dev, batch: int = 32, steps: int = 3, warmup: int = 2):
+    import gc
+    rec = {'unit': UNIT, 'kind': 'oracle port of the reference modules as stock torch eager ops on the same GPU (cuDNN / ATen / cuBLAS, '
+                                  'torch.optim.AdamW foreach); none of this repository\'s kernels; inputs resident on the device',
+           'micro_batch': batch, 'steps': steps, 'warmup': warmup}
+    for tag, autocast in (('fp32_tf32_convs', False), ('bf16_autocast', True)):
+        b = batch
+        while True:
+            gc.collect(); torch.cuda.empty_cache()
+            try:
+                ips, ms, gib = torch_eager_gpu_step(name, b, image_size, codebook, steps, warmup, dev, autocast)
+                rec[tag] = {'value': ips, 'ms_per_step': ms, 'micro_batch': b, 'peak_mem_gib': gib}
+                break
+            except torch.OutOfMemoryError:
+                if b <= 8:
+                    rec[tag] = {'error': 'out of memory at micro-batch 8'}
+                    break
+                b //= 2
+            except Exception as e:
+                rec[tag] = {'error': f'{type(e).__name__}: {e}'[:300]}
+                break
+    gc.collect(); torch.cuda.empty_cache()
+    return rec
 
 
 def run_reference(args, rank, world, out=sys.stdout):
@@ -432,7 +519,7 @@ def run_workload(name, args, pkg, dev, rank, world, precision, steps, warmup, st
     achieved = conv_fl / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
     peak = pk['bf16_tflops_sustained']
     tr = measured_traffic() if (name == 'cfg2' and fast and (image_size, bs) == (256, 64)) else None
-    roofline = {'bound': 'tensor', 'kernel': 'implicit-GEMM conv (fwd+dgrad+wgrad launches)' + ('' if fast else ' -- fp32 SIMT kernels against the bf16 roof'),
+    roofline = {'bound': 'tensor', 'kernel': 'implicit-GEMM conv (fwd+dgrad+wgrad launches)' + ('' if fast else ' -- split-precision bf16 hi/lo operands through the same tcgen05 kernels (3 tensor-core passes per algorithmic FLOP, fp32 storage), ALGORITHMIC FLOPs against the bf16 roof'),
                 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
                 'traffic': tr['dram_bytes_per_launch'] if tr else None, 'traffic_source': tr.get('source') if tr else None,
                 'traffic_algorithmic_bytes': tr.get('algorithmic_bytes') if tr else None,
@@ -485,6 +572,8 @@ def main():
     ap.add_argument('--cpu-batch', type=int, default=2)
     ap.add_argument('--cpu-steps', type=int, default=2)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-gpu-eager-baseline', action='store_true',
+                    help='skip the secondary baseline (the oracle port of the reference modules as torch eager ops on the same GPU)')
     ap.add_argument('--graph', type=int, default=1, help='1 (default): replay one captured CUDA graph per step; 0: eager launches')
     ap.add_argument('--ncu-step', action='store_true', help='after the warm-up run ONE step between cudaProfilerStart/Stop and exit '
                     '(for `ncu --profile-from-start off`; prints no bench line)')
@@ -580,6 +669,20 @@ def main():
                                                   f'reference modules, fp32 torch CPU'}
             except Exception as e:
                 line['cpu_baseline'] = {'value': None, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'error': str(e)[:300]}
+        if world == 1 and not args.no_gpu_eager_baseline:
+            codebook = args.codebook or WORKLOADS[args.config]['codebook']
+            try:
+                line['torch_eager_gpu_baseline'] = torch_eager_gpu_baseline(args.config, args.image_size, codebook, dev)
+            except BaseException as e:
+                line['torch_eager_gpu_baseline'] = {'error': f'{type(e).__name__}: {e}'[:300]}
+            if isinstance(subs.get('cfg4'), dict) and 'error' not in subs['cfg4']:      # the VQGAN step (no R1 step in the timed region)
+                try:
+                    subs['cfg4']['torch_eager_gpu_baseline'] = torch_eager_gpu_baseline('cfg4', args.image_size, WORKLOADS['cfg4']['codebook'], dev)
+                    subs['cfg4']['torch_eager_gpu_baseline']['note'] = (
+                        'the discriminator\'s FIR resampling / bias-act run as the reference\'s pure-torch fallbacks (depthwise F.conv2d; '
+                        'upfirdn2d.py:162-208, bias_act.py:55-97), not its CUDA plugin: pessimistic for the reference there; no R1 step timed')
+                except BaseException as e:
+                    subs['cfg4']['torch_eager_gpu_baseline'] = {'error': f'{type(e).__name__}: {e}'[:300]}
         out.write(json.dumps(line) + '\n'); out.flush()
     if world > 1:
         dist.destroy_process_group()

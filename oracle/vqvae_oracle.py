@@ -153,10 +153,10 @@ def vq_ema(z: Tensor, codebook: Tensor, ema_count: Tensor, ema_weight: Tensor, b
     new_cb, new_cnt, new_w = codebook, ema_count, ema_weight
     if training:
         with torch.no_grad():
-            counts = torch.bincount(idx, minlength=K).to(flat.dtype)
+            counts = torch.bincount(idx, minlength=K).to(ema_count.dtype)
             cnt = ema_count * decay + (1 - decay) * counts
             new_cnt = (cnt + epsilon) / (b + K * epsilon) * b
-            dw = torch.zeros_like(codebook).index_add_(0, idx, flat.detach())
+            dw = torch.zeros_like(codebook).index_add_(0, idx, flat.detach().to(codebook.dtype))   # no-op in fp32 (bench: autocast leg)
             new_w = ema_weight * decay + (1 - decay) * dw
             new_cb = new_w / new_cnt.unsqueeze(1)
     e_loss = beta * F.mse_loss(q.detach(), flat)

@@ -25,33 +25,32 @@ HAVE_LIGHTNING = False            # kept for callers that branched on it: the sh
 class LightningModule(nn.Module):
     """The subset of pl.LightningModule used by vqvae/model.py."""
 
-    if True:
-        def __init__(self):
-            super().__init__()
-            self.trainer: Optional['Trainer'] = None
-            self.current_epoch = 0
-            self.automatic_optimization = True
-            self.logged: Dict[str, Any] = {}
+    def __init__(self):
+        super().__init__()
+        self.trainer: Optional['Trainer'] = None
+        self.current_epoch = 0
+        self.automatic_optimization = True
+        self.logged: Dict[str, Any] = {}
 
-        def log(self, name: str, value, **kwargs) -> None:
-            # values may be device tensors; nothing is synchronised here (the reference does 7 .item() syncs per step)
-            self.logged[name] = value
+    def log(self, name: str, value, **kwargs) -> None:
+        # values may be device tensors; nothing is synchronised here (the reference does 7 .item() syncs per step)
+        self.logged[name] = value
 
-        def optimizers(self):
-            opts = self.trainer.optimizers
-            return opts if len(opts) > 1 else opts[0]
+    def optimizers(self):
+        opts = self.trainer.optimizers
+        return opts if len(opts) > 1 else opts[0]
 
-        def manual_backward(self, loss: torch.Tensor, optimizer=None) -> None:
-            """backward + data-parallel all-reduce of `optimizer`'s gradients (all optimizers when None)"""
-            loss.backward()
-            if self.trainer is not None:
-                self.trainer.sync_gradients(optimizer)
+    def manual_backward(self, loss: torch.Tensor, optimizer=None) -> None:
+        """backward + data-parallel all-reduce of `optimizer`'s gradients (all optimizers when None)"""
+        loss.backward()
+        if self.trainer is not None:
+            self.trainer.sync_gradients(optimizer)
 
-        # hooks (overridden by the model)
-        def on_train_start(self): ...
-        def on_train_batch_start(self, batch, batch_index): ...
-        def on_train_epoch_end(self): ...
-        def on_train_end(self): ...
+    # hooks (overridden by the model)
+    def on_train_start(self): ...
+    def on_train_batch_start(self, batch, batch_index): ...
+    def on_train_epoch_end(self): ...
+    def on_train_end(self): ...
 
 
 class DevicePrefetcher:
