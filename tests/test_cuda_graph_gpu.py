@@ -19,7 +19,7 @@ def V():
     pkg.set_precision('strict')
 
 
-def run(V, name, graph, steps, mode):
+def run(V, name, graph, steps, mode, sync=True):
     from vqvae_vqgan_pytorch_lightning_b200.lightning_shim import Trainer
     V.set_precision(mode)
     case = dict(STEP_CASES[name])
@@ -43,11 +43,14 @@ def run(V, name, graph, steps, mode):
         if case['qtype'] == 'gumbel':
             torch.manual_seed(500 + i)               # the Gumbel noise comes from torch's CUDA generator in both runs
             torch.cuda.manual_seed(500 + i)
-        losses.append(float(tr.run_step(xs[i % 2], i)))
+        loss = tr.run_step(xs[i % 2], i)
+        if sync:
+            losses.append(float(loss))              # a device -> host read: the host never runs ahead of the device
     return {k: v.detach().clone() for k, v in model.state_dict().items()}, losses, tr
 
 
 @pytest.mark.parametrize('name,mode', [('mse_ema', 'strict'), ('mse_ema', 'fast'), ('mse_standard', 'strict'), ('mse_entropy', 'strict'),
+                                       ('mse_gumbel', 'strict'),
                                        ('gan_hinge_adaptive_r1', 'strict'), ('gan_nonsat_fixed', 'fast')])
 def test_graph_replay_equals_eager(V, name, mode):
     if mode == 'fast' and not V.lib.load().vqb_device_supports_tcgen05():
@@ -67,3 +70,22 @@ def test_graph_replay_equals_eager(V, name, mode):
         num += float((graph[k].double() - eager[k].double()).pow(2).sum()); den += float(eager[k].double().pow(2).sum())
     # strict: 1e-4 .. 2.5e-4 measured between two runs of the 10-step GAN case (state dominated by the frozen trunk + initial weights)
     assert (num / den) ** 0.5 < (1e-3 if mode == 'strict' else 5e-2), (num / den) ** 0.5
+
+
+@pytest.mark.parametrize('name', ['mse_ema', 'mse_gumbel'])
+def test_graph_replay_with_the_host_running_ahead(V, name):
+    """No synchronisation between steps: the host queues every replay while the device is still on the first ones.  The per-step
+    scalars (learning-rate schedule + Adam bias corrections; Gumbel temperature / KL weight) must still be the ones of THEIR
+    step -- they reach the device through ops.StepScalars' ring of pinned slots, not through one pinned buffer that the host
+    would have re-written before the device read it."""
+    steps = 12
+    synced, _, _ = run(V, name, True, steps, 'strict', sync=True)
+    ahead, _, tr = run(V, name, True, steps, 'strict', sync=False)
+    torch.cuda.synchronize()
+    assert any(st['graph'] is not None for st in tr._graphs.values()), 'no graph was captured'
+    num = den = 0.0
+    for k in synced:
+        if k in C.DEGENERATE or not synced[k].dtype.is_floating_point:
+            continue
+        num += float((ahead[k].double() - synced[k].double()).pow(2).sum()); den += float(synced[k].double().pow(2).sum())
+    assert (num / den) ** 0.5 < 1e-3, (num / den) ** 0.5

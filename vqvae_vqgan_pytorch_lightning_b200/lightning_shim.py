@@ -231,8 +231,8 @@ class Trainer:
     def _run_step_graphed(self, batch, batch_index: int):
         m = self.model
         q = getattr(m, 'quantizer', None)
-        if q is not None and hasattr(q, 'device_consts'):
-            q.device_consts = True
+        if q is not None and hasattr(q, 'enable_device_consts') and not q.device_consts:
+            q.enable_device_consts(batch.device)
         key = (tuple(batch.shape), batch.dtype, m.graph_variant(batch_index) if hasattr(m, 'graph_variant') else ())
         st = self._graphs.setdefault(key, {'calls': 0, 'graph': None})
         st['calls'] += 1

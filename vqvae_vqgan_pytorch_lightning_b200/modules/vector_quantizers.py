@@ -78,10 +78,20 @@ class GumbelVectorQuantizer(BaseVectorQuantizer):
         self.straight_through = straight_through
         self.temp = temp
         self.kl_cost = kl_cost
-        # device mirror of (temp, kl_cost) for CUDA-graph replay: refreshed through a pinned buffer by a copy INSIDE forward
-        self._consts_host = None
-        self._consts_dev = None
+        # device mirror of (temp, kl_cost) for CUDA-graph replay: uploaded by set_consts() (ops.StepScalars), read by the kernels
+        self._consts = None
         self.device_consts = False
+
+    def enable_device_consts(self, device) -> None:
+        """(temp, kl_cost) reach the kernels through device memory from now on (the CUDA-graph trainer calls this BEFORE a step is
+        captured: the captured kernels keep reading the buffer that set_consts() refreshes before every replay)."""
+        if self._consts is None or self._consts.dev.device != torch.device(device):
+            self._consts = ops.StepScalars((2,), device)
+        self.device_consts = True
+        self._upload_consts()
+
+    def _upload_consts(self) -> None:
+        self._consts.upload(torch.tensor([float(self.temp), float(self.kl_cost)], dtype=torch.float32))
 
     def forward(self, x: torch.Tensor, exp_noise: torch.Tensor = None):
         hard = self.straight_through if self.training else True
@@ -89,14 +99,11 @@ class GumbelVectorQuantizer(BaseVectorQuantizer):
         if exp_noise is None:
             exp_noise = torch.empty_like(logits, memory_format=torch.preserve_format).exponential_()     # RNG plumbing
         if self.device_consts:
-            # (temp, kl_cost) travel through a pinned host buffer -> device copy: under CUDA-graph replay the copy node re-reads the
-            # values set_consts() wrote for this step (schedules of model.py:219-225)
-            if self._consts_dev is None or self._consts_dev.device != logits.device:
-                self._consts_host = torch.tensor([float(self.temp), float(self.kl_cost)], dtype=torch.float32).pin_memory()
-                self._consts_dev = torch.empty(2, dtype=torch.float32, device=logits.device)
-            self._consts_dev.copy_(self._consts_host, non_blocking=True)
-            y, idx, kl_mean = ops.gumbel_rows(logits, exp_noise, self._consts_dev[:1], hard)
-            kl = self._consts_dev[1] * kl_mean
+            # (temp, kl_cost) from device memory: the values set_consts() uploaded for this step (schedules of model.py:219-225)
+            if self._consts is None or self._consts.dev.device != logits.device:
+                raise RuntimeError('GumbelVectorQuantizer: enable_device_consts(device) was not called for this device')
+            y, idx, kl_mean = ops.gumbel_rows(logits, exp_noise, self._consts.dev[:1], hard)
+            kl = self._consts.dev[1] * kl_mean
         else:
             y, idx, kl_mean = ops.gumbel_rows(logits, exp_noise, float(self.temp), hard)
             kl = self.kl_cost * kl_mean
@@ -113,9 +120,8 @@ class GumbelVectorQuantizer(BaseVectorQuantizer):
             self.temp = temp
         if kl_cost is not None:
             self.kl_cost = kl_cost
-        if self._consts_host is not None:
-            self._consts_host[0] = float(self.temp)
-            self._consts_host[1] = float(self.kl_cost)
+        if self._consts is not None:
+            self._upload_consts()
 
     @torch.no_grad()
     def vec_to_codes(self, x: torch.Tensor, exp_noise: torch.Tensor = None) -> torch.Tensor:

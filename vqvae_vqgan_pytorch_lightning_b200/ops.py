@@ -138,6 +138,37 @@ class ZeroArena:
 
 
 zero_arena = ZeroArena()
+
+
+class StepScalars:
+    """A few fp32 scalars that change from step to step (learning rate, Adam bias corrections, Gumbel temperature / KL weight) and
+    reach the kernels through DEVICE memory, so that a captured CUDA graph of the step reads this step's values.  upload() copies
+    them host -> device on the current stream -- ordered before the step's kernels or its graph replay -- through a small ring of
+    pinned slots, each guarded by an event: the host may run several steps ahead of the device without re-writing a slot whose
+    queued copy has not executed yet (ONE pinned buffer read by a copy at execution time would hand a step the values of a later
+    step whenever the host runs ahead, i.e. whenever the caller does not synchronise every step)."""
+    SLOTS = 4
+
+    def __init__(self, shape, device):
+        self.dev = torch.zeros(shape, dtype=torch.float32, device=device)
+        self._slots = [torch.zeros(shape, dtype=torch.float32).pin_memory() for _ in range(self.SLOTS)]
+        self._done = [None] * self.SLOTS
+        self._n = 0
+
+    def upload(self, values: torch.Tensor) -> None:
+        """values: CPU tensor of the buffer's shape.  A no-op under stream capture: the caller uploads before every replay."""
+        if torch.cuda.is_current_stream_capturing():
+            return
+        s = self._n % self.SLOTS
+        self._n += 1
+        if self._done[s] is None:
+            self._done[s] = torch.cuda.Event()
+        else:
+            self._done[s].synchronize()                    # the copy issued SLOTS uploads ago has read this slot
+        self._slots[s].copy_(values)
+        with torch.cuda.device(self.dev.device):
+            self.dev.copy_(self._slots[s], non_blocking=True)
+            self._done[s].record()
 coop_cta_limit = 0          # cap on the grid of cooperative kernels (vqb_gn_bwd_fused); the data-parallel Trainer sets it to leave SMs to NCCL
 
 

@@ -72,10 +72,9 @@ class FusedAdamW(torch.optim.Optimizer):
                     off += _padded(n)
         self._live = live
         self.step_count = 0
-        # per-step scalars of every group {lr, 1 - beta1^t, sqrt(1 - beta2^t)}: written by the host into a pinned buffer and copied
-        # to the device INSIDE step() -- a copy node that a captured CUDA graph re-executes on every replay
-        self._hyper_host = torch.zeros(len(self.param_groups), 4, dtype=torch.float32).pin_memory()
-        self._hyper_dev = torch.zeros(len(self.param_groups), 4, dtype=torch.float32, device=device)
+        # per-step scalars of every group {lr, 1 - beta1^t, sqrt(1 - beta2^t)}: uploaded to device memory by host_step_update() on
+        # the current stream (before the step's kernels, or before the replay of a captured graph of the step)
+        self._hyper = ops.StepScalars((len(self.param_groups), 4), device)
         self.grad_scale = 1.0       # set to 1/world_size by the data-parallel trainer (after a SUM all-reduce)
         ops.bump_weights_epoch()
 
@@ -153,23 +152,25 @@ class FusedAdamW(torch.optim.Optimizer):
                 off += _padded(n)
 
     def host_step_update(self) -> None:
-        """Advance the step counter and refresh the pinned scalars from param_groups.  step() calls it; a trainer replaying a
-        captured CUDA graph of the step calls it INSTEAD of step() (the graph's copy node then picks the new values up)."""
+        """Advance the step counter and upload this step's scalars from param_groups.  step() calls it; a trainer replaying a
+        captured CUDA graph of the step calls it INSTEAD of step(), before the replay (under capture the upload is skipped: the
+        graph holds only the kernels, which read the device copy)."""
         self.step_count += 1
+        vals = torch.zeros(len(self.param_groups), 4, dtype=torch.float32)
         for i, g in enumerate(self.param_groups):
             b1, b2 = g['betas']
-            self._hyper_host[i, 0] = float(g['lr'])
-            self._hyper_host[i, 1] = 1.0 - b1 ** self.step_count
-            self._hyper_host[i, 2] = (1.0 - b2 ** self.step_count) ** 0.5
+            vals[i, 0] = float(g['lr'])
+            vals[i, 1] = 1.0 - b1 ** self.step_count
+            vals[i, 2] = (1.0 - b2 ** self.step_count) ** 0.5
+        self._hyper.upload(vals)
 
     @torch.no_grad()
     def step(self, closure=None):
         loss = closure() if closure is not None else None
         self.host_step_update()
-        self._hyper_dev.copy_(self._hyper_host, non_blocking=True)
         for i, (g, (a, b)) in enumerate(zip(self.param_groups, self._ranges)):
             if b > a:
                 ops.adamw_flat_dev(self.flat_param[a:b], self.flat_grad[a:b], self.exp_avg[a:b], self.exp_avg_sq[a:b],
-                                   self._hyper_dev[i], g['betas'][0], g['betas'][1], g['eps'], g['weight_decay'], self.grad_scale)
+                                   self._hyper.dev[i], g['betas'][0], g['betas'][1], g['eps'], g['weight_decay'], self.grad_scale)
         ops.bump_weights_epoch()
         return loss
