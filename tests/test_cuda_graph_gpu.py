@@ -89,3 +89,23 @@ def test_graph_replay_with_the_host_running_ahead(V, name):
             continue
         num += float((ahead[k].double() - synced[k].double()).pow(2).sum()); den += float(synced[k].double().pow(2).sum())
     assert (num / den) ** 0.5 < 1e-3, (num / den) ** 0.5
+
+
+def test_fit_loop_with_graphs(V):
+    """Trainer.fit (which keeps the previous step's loss while the next step runs) captures and replays graphs"""
+    from vqvae_vqgan_pytorch_lightning_b200.lightning_shim import Trainer
+    V.set_precision('strict')
+    case = STEP_CASES['mse_ema']
+    sd = oinit.init_state(case['qtype'], case['K'], case['D'], case['ch'], case['nrb'], case['mult'], seed=case['seed'],
+                          criterion=None, image_size=case['S'])
+    model = V.VQVAE(case['S'], dict(channels=case['ch'], num_res_blocks=case['nrb'], channel_multipliers=list(case['mult'])),
+                    q_conf_of(case), None, dict(case['t_conf']), pretrained_lpips=False)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().train()
+    model.training_augmentations = None
+    torch.manual_seed(3)
+    batches = [torch.rand(case['B'], 3, case['S'], case['S']).cuda() for _ in range(6)]
+    tr = Trainer(max_epochs=2, cuda_graph=True, graph_warmup=2)
+    loss = tr.fit(model, batches)
+    assert any(st['graph'] is not None for st in tr._graphs.values()), 'no graph was captured'
+    assert loss.grad_fn is None and torch.isfinite(loss).all()

@@ -296,7 +296,10 @@ class Trainer:
             opt.step()
         else:
             loss = m.training_step(batch, batch_index)
-        return loss
+        # detached, as Lightning's loop hands losses on: a caller that keeps the returned loss (fit() below does, across the next
+        # step) must not keep this step's autograd graph -- and its AccumulateGrad nodes, bound to the stream they were created
+        # on -- alive into the next step, which may run under stream capture
+        return loss.detach()
 
     def fit(self, model: LightningModule, batches: Iterable, steps_per_epoch: Optional[int] = None):
         if self.model is not model:
