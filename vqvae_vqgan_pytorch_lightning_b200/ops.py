@@ -169,6 +169,8 @@ class StepScalars:
         with torch.cuda.device(self.dev.device):
             self.dev.copy_(self._slots[s], non_blocking=True)
             self._done[s].record()
+
+
 coop_cta_limit = 0          # cap on the grid of cooperative kernels (vqb_gn_bwd_fused); the data-parallel Trainer sets it to leave SMs to NCCL
 
 
@@ -360,6 +362,8 @@ def take_capture_refs() -> list:
     owner of the CUDA graph keeps the returned list for as long as the graph may be replayed."""
     refs, _pack_registry.capture_refs = _pack_registry.capture_refs, []
     return refs
+
+
 _batched_pack = None
 
 
