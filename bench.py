@@ -653,6 +653,9 @@ def main():
                     t = json.load(open(tr))
                     line['vq_roofline']['traffic'] = t.get('dram_bytes_per_launch')
                     line['vq_roofline']['traffic_source'] = t.get('source')
+                    if isinstance(t.get('k8192'), dict):
+                        line['vq_roofline_k8192']['traffic'] = t['k8192'].get('dram_bytes_per_launch')
+                        line['vq_roofline_k8192']['traffic_source'] = t['k8192'].get('source')
                 except Exception:
                     pass
         if subs:
