@@ -224,6 +224,8 @@ class Trainer:
 
     # ---- one optimisation step (what Lightning's fit loop does around training_step) -------------------
     def run_step(self, batch, batch_index: int):
+        if isinstance(batch, tuple):              # (images, labels) of the FFCV loaders: the step reads the images only (model.py:237)
+            batch = batch[0]
         if self.cuda_graph and torch.is_tensor(batch) and batch.is_cuda:
             return self._run_step_graphed(batch, batch_index)
         return self._run_step_eager(batch, batch_index)
@@ -301,6 +303,22 @@ class Trainer:
         # on -- alive into the next step, which may run under stream capture
         return loss.detach()
 
+    @staticmethod
+    def _device_batches(batches: Iterable, model: nn.Module):
+        """Lightning's batch transfer (the reference feeds host batches from a DataLoader(pin_memory=True), vqvae/train.py:121-142):
+        host batches reach the model's device through the DevicePrefetcher, one step ahead; device batches pass through."""
+        import itertools
+        p = next(model.parameters(), None)
+        it = iter(batches)
+        first = next(it, None)
+        if first is None:
+            return iter(())
+        rest = itertools.chain([first], it)
+        ts = DevicePrefetcher._tensors(first)
+        if p is not None and p.is_cuda and ts and not ts[0].is_cuda:
+            return DevicePrefetcher(rest, p.device)
+        return rest
+
     def fit(self, model: LightningModule, batches: Iterable, steps_per_epoch: Optional[int] = None):
         if self.model is not model:
             self.attach(model)
@@ -312,7 +330,7 @@ class Trainer:
         loss = None
         for epoch in range(self.max_epochs):
             model.current_epoch = epoch
-            for i, batch in enumerate(batches):
+            for i, batch in enumerate(self._device_batches(batches, model)):
                 if i >= steps_per_epoch:
                     break
                 loss = self.run_step(batch, i)
