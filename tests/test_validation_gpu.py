@@ -117,3 +117,34 @@ def test_fused_adamw_state_dict_resumes_identically(V):
     got = model2.state_dict()
     for k in want:                         # (weight gradients are combined with floating-point atomics: not bit-reproducible)
         assert C.rel_err(got[k], want[k]) < 1e-5, k
+
+
+def test_trainer_validate_and_test_loops(V):
+    """Trainer.validate / Trainer.test (pl.Trainer.validate / .test around the module's hooks) on HOST batches -- (images, labels)
+    tuples as the reference's loaders yield -- log what the hooks log when called by hand on device batches."""
+    from vqvae_vqgan_pytorch_lightning_b200.lightning_shim import Trainer
+    case, crit, sd, model, tr, x = build(V, 'lpips_ema')
+    torch.manual_seed(21)
+    host = [(torch.rand(case['B'], 3, case['S'], case['S']), torch.tensor(i)) for i in range(3)]
+    # by hand
+    for i, (xb, _) in enumerate(host):
+        model.validation_step(xb.cuda(), i)
+    want_val = {k: float(torch.as_tensor(v).reshape(-1)[0]) for k, v in model.logged.items() if k.startswith('validation/')}
+    model.on_validation_epoch_end()
+    want_ppl = float(model.logged['val_metrics/perplexity'])
+    model.on_test_epoch_start()
+    for xb, _ in host:
+        model.test_step(xb.cuda(), 0)
+    model.on_test_epoch_end()
+    want_test = {k: float(model.logged[k]) for k in ('mse', 'psnr', 'ssim', 'perplexity', 'used_codebook')}
+    # through the loops
+    model.train()
+    model.logged.clear()
+    logged = Trainer().validate(model, host)
+    assert model.training                                          # the loop restores the mode it found
+    for k, v in want_val.items():
+        assert abs(float(torch.as_tensor(logged[k]).reshape(-1)[0]) - v) <= 1e-5 * max(abs(v), 0.1), k
+    assert abs(float(logged['val_metrics/perplexity']) - want_ppl) <= 1e-5 * want_ppl
+    logged = Trainer().test(model, host)
+    for k, v in want_test.items():
+        assert abs(float(logged[k]) - v) <= 1e-5 * max(abs(v), 0.1), k

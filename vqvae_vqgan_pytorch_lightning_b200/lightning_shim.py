@@ -337,3 +337,31 @@ class Trainer:
             model.on_train_epoch_end()
         model.on_train_end()
         return loss
+
+    # ---- evaluation loops (what pl.Trainer.validate / .test do around the module's hooks) -----------------------
+    def _eval_loop(self, model: LightningModule, batches: Iterable, step, begin, end) -> Dict[str, Any]:
+        if model.trainer is None:
+            model.trainer = self                      # validation_step reads trainer.num_training_batches (model.py:341)
+        was_training = model.training
+        model.eval()
+        try:
+            if begin is not None:
+                begin()
+            with torch.no_grad():
+                for i, batch in enumerate(self._device_batches(batches, model)):
+                    step(batch, i)
+            if end is not None:
+                end()
+        finally:
+            model.train(was_training)
+        return dict(model.logged)
+
+    def validate(self, model: LightningModule, batches: Iterable) -> Dict[str, Any]:
+        """validation_step over `batches` + on_validation_epoch_end (model.py:309-370); returns the logged validation/* scalars"""
+        return self._eval_loop(model, batches, model.validation_step, None, getattr(model, 'on_validation_epoch_end', None))
+
+    def test(self, model: LightningModule, batches: Iterable) -> Dict[str, Any]:
+        """on_test_epoch_start / test_step / on_test_epoch_end (model.py:491-562, driven by vqvae/evaluate.py); returns the
+        logged metrics (mse, psnr, ssim, used_codebook, perplexity [, rfid])"""
+        return self._eval_loop(model, batches, model.test_step, getattr(model, 'on_test_epoch_start', None),
+                               getattr(model, 'on_test_epoch_end', None))
