@@ -102,3 +102,15 @@ def test_reinit_unused_codes_keeps_replicas_identical():
         assert any(torch.equal(cb0[i], ref.codebook.weight[j]) for j in live.tolist())
     for j in live.tolist():
         assert torch.equal(cb0[j], ref.codebook.weight[j])
+
+
+def test_trainer_batch_transfer_passes_through_without_a_device():
+    """Trainer._device_batches: only HOST batches of a model that lives on a GPU go through the DevicePrefetcher; anything else
+    (here: a CPU module) is handed on unchanged and in order, tuples included, and an empty loader stays empty."""
+    from vqvae_vqgan_pytorch_lightning_b200.lightning_shim import Trainer
+    m = torch.nn.Linear(2, 2)
+    batches = [(torch.full((1, 2), float(i)), torch.tensor(i)) for i in range(4)]
+    got = list(Trainer._device_batches(batches, m))
+    assert len(got) == 4 and all(a is b for a, b in zip(got, batches))
+    assert list(Trainer._device_batches([], m)) == []
+    assert list(Trainer._device_batches(iter(batches), m))[3][1].item() == 3          # one-shot iterators work too
