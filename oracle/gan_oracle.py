@@ -7,7 +7,8 @@ Functional (state-dict driven) fp32 restatement of
   * the loss heads (vqvae/modules/loss/loss.py:11-199),
   * one whole optimisation step of every branch of VQVAE.training_step incl. the schedules and AdamW with the reference's
     parameter grouping (vqvae/model.py:202-295, 372-440).
-Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference arm may import this file.
+Only tests/, __graft_entry__.smoke() and bench.py's baseline legs (cpu_baseline, --impl reference, torch_eager_gpu_baseline) may
+import this file.
 
 Pinning: tests/golden/step_*.npz are produced by oracle/make_golden_step.py, which executes the reference's OWN VQVAE class
 (oracle/ref_harness.py); tests/test_oracle_step.py checks this file against them on the CPU.  The schedule classes come

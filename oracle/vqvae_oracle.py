@@ -2,8 +2,9 @@
 
 This file is a functional (state-dict driven) restatement, in plain fp32 PyTorch on the
 CPU, of the arithmetic of the reference's hot path.  It is *not* part of the product:
-only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / reference
-arm may import it.  The product path (``vqvae_vqgan_pytorch_lightning_b200``) never does
+only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s baseline legs (cpu_baseline,
+``--impl reference`` and ``torch_eager_gpu_baseline`` -- the same port timed as stock torch eager ops
+with its tensors on the GPU; reported baselines, never the thing shipped) may import it.  The product path (``vqvae_vqgan_pytorch_lightning_b200``) never does
 and fails loudly when its CUDA library is missing.
 
 Pinning: the reference ships no tests or golden vectors, so this
