@@ -35,6 +35,20 @@ def seeded_inputs(case_name, qtype):
     return sd, x
 
 
+# BASELINE configs[1]'s architecture and image size at batch 2 (oracle/make_golden_256.py: tests/golden/cfg2_256_ema.npz)
+CASES['cfg2_256'] = dict(S=256, B=2, ch=128, nrb=2, mult=(1, 2, 2, 4), K=1024, D=256, seed=2468)
+
+
+def seeded_inputs_256():
+    """(state dict, images in [-1,1]) exactly as oracle/make_golden_256.py made them: the cfg1 recipe, then a tie-free codebook"""
+    sd, x = seeded_inputs('cfg2_256', 'ema')
+    c = CASES['cfg2_256']
+    torch.manual_seed(c['seed'] + 1)
+    sd['quantizer.codebook.weight'] = torch.randn(c['K'], c['D']) * 0.05
+    sd['quantizer.ema_weight'] = sd['quantizer.codebook.weight'].clone()
+    return sd, x
+
+
 def oracle_cfg(case_name, qtype):
     c = CASES[case_name]
     return {'num_res_blocks': c['nrb'], 'channel_multipliers': c['mult'], 'quantizer': dict(Q_PARAMS[qtype])}

@@ -181,3 +181,57 @@ def test_cfg2_fast_against_strict_at_256(V):
     assert abs(f['l2'] - s['l2']) <= 2e-2 * s['l2'] and abs(f['q'] - s['q']) <= 5e-2 * abs(s['q']) + 1e-4
     assert float((f['idx'] == s['idx']).float().mean()) >= 0.90
     assert (num / den) ** 0.5 < 5e-2 and worst < 0.10
+
+
+@pytest.mark.parametrize('mode', ['strict', 'fast'])
+def test_cfg2_architecture_at_256_against_reference_fixture(V, mode):
+    """The benchmark's architecture at the benchmark's image size (ema_vqvae.yaml: 256 x 256, 128 channels, (1,2,2,4), K = 1024;
+    batch 2) against a fixture produced by EXECUTING THE REFERENCE'S MODULES (oracle/make_golden_256.py; the CPU oracle is held to
+    the same fixture in tests/test_oracle_golden.py).  strict (split-precision tcgen05 convolutions, fp32 storage): the
+    north_star's 1e-4 on floats, indices bit-exact up to the reference's own fp32 near-ties; fast (bf16): the stated bf16 bars."""
+    g = C.golden('cfg2_256_ema')
+    sd, x = C.seeded_inputs_256()
+    c = C.CASES['cfg2_256']
+    V.set_precision(mode)
+    qp = {k: v for k, v in C.Q_PARAMS['ema'].items() if k != 'type'}
+    model = V.VQVAE(c['S'], dict(channels=c['ch'], num_res_blocks=c['nrb'], channel_multipliers=list(c['mult'])),
+                    dict(num_embeddings=c['K'], embedding_dim=c['D'], type='ema', params=qp, reinit_every_n_epochs=None),
+                    None, dict(lr=1e-4, betas=[0.0, 0.99], eps=1e-8, weight_decay=1e-4, warmup_epochs=None, decay_epochs=None))
+    model.load_state_dict(sd)
+    model.training_augmentations = None
+    model = model.cuda().train()
+    xg = x.cuda().contiguous(memory_format=torch.channels_last)
+    recon, q_loss, idx = model(xg)
+    l2 = model.criterion(recon, xg)
+    (q_loss + l2).backward()
+    z = model.encoder(xg).detach().float()
+    recon = recon.detach().float()
+    tol = 1e-4 if mode == 'strict' else 3e-2
+    ez = C.rel_err(z, g['z'])
+    flat = torch.from_numpy(g['z']).permute(0, 2, 3, 1).reshape(-1, c['D'])
+    exact, ties, bad = C.tie_aware_index_check(idx, g['idx'], flat, sd['quantizer.codebook.weight'])
+    e_pool = C.rel_err(torch.nn.functional.avg_pool2d(recon, 8), g['recon_pool8'])
+    e_head = C.rel_err(recon.reshape(-1)[:4096], g['recon_head'])
+    ref_norm = dict(zip(g['grad_names'].tolist(), g['grad_norms'].tolist()))
+    worst = max(abs(float(p.grad.double().norm()) - ref_norm[n]) / ref_norm[n]
+                for n, p in model.named_parameters() if p.grad is not None and ref_norm.get(n, 0) > 1e-7)
+    print(f'cfg2 architecture @256 vs reference fixture [{mode}]: z {ez:.2e} idx exact/tie/bad {exact}/{ties}/{bad} recon pooled {e_pool:.2e} '
+          f'head {e_head:.2e} l2 {float(l2):.6f} vs {float(g["l2"]):.6f} q {float(q_loss):.6f} vs {float(g["q_loss"]):.6f} worst grad norm {worst:.2e}')
+    assert ez < tol
+    if mode == 'strict':
+        assert bad == 0 and ties <= max(1, idx.numel() // 100), (exact, ties, bad)
+        if ties == 0:
+            assert e_pool < tol and e_head < tol
+            assert abs(float(l2) - float(g['l2'])) <= tol and abs(float(q_loss) - float(g['q_loss'])) <= tol
+            assert C.rel_err(model.decoder.conv_out.weight.grad, g['grad_dec_conv_out']) < tol
+            assert C.rel_err(model.encoder.conv_in.weight.grad, g['grad_enc_conv_in']) < 5 * tol
+            assert worst < 5 * tol
+            assert C.rel_err(model.quantizer.ema_count, g['new_ema_count']) < 2e-5
+            assert C.rel_err(model.quantizer.ema_weight.double().sum(1), g['new_ema_weight_rowsum']) < 1e-4
+    else:
+        # bf16 activation storage through 48 convolutions and 42 GroupNorms (the bars of test_cfg2_fast_against_strict_at_256)
+        assert exact >= 0.90 * idx.numel()
+        assert e_pool < 1e-1
+        assert abs(float(l2) - float(g['l2'])) <= 2e-2 * float(g['l2'])
+        assert abs(float(q_loss) - float(g['q_loss'])) <= 5e-2 * abs(float(g['q_loss'])) + 1e-4
+        assert worst < 0.10

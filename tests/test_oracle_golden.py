@@ -43,6 +43,37 @@ def test_oracle_matches_reference_fixture(case, qtype):
         assert C.rel_err(sd['quantizer.codebook.weight'].grad, g['grad_codebook']) < 1e-4
 
 
+def test_oracle_matches_reference_fixture_at_256():
+    """The benchmark's architecture and image size (ema_vqvae.yaml: 256 x 256, channels 128, K = 1024; batch 2) against the
+    fixture made by executing the reference's modules (oracle/make_golden_256.py)."""
+    g = C.golden('cfg2_256_ema')
+    sd, x = C.seeded_inputs_256()
+    ref_init = dict(zip(g['init_names'].tolist(), g['init_abs_sums'].tolist()))
+    assert set(ref_init) == set(sd)
+    for n, t in sd.items():
+        assert abs(float(t.double().abs().sum()) - ref_init[n]) <= 1e-9 * max(1.0, ref_init[n]), n
+    sd = oinit.make_leaf(sd, 'ema')
+    torch.set_num_threads(8)
+    out = orc.train_step_mse(sd, x, C.oracle_cfg('cfg2_256', 'ema'))
+    assert np.array_equal(out['idx'].numpy(), g['idx']), 'codebook indices must be bit-exact'
+    assert C.rel_err(out['z'], g['z']) < 1e-5
+    recon = out['recon'].detach()
+    assert C.rel_err(torch.nn.functional.avg_pool2d(recon, 8), g['recon_pool8']) < 2e-5
+    assert C.rel_err(recon.reshape(-1)[:4096], g['recon_head']) < 2e-5
+    assert abs(float(recon.double().abs().sum()) - float(g['recon_abs_sum'])) <= 1e-6 * float(g['recon_abs_sum'])
+    assert abs(out['q_loss'].item() - float(g['q_loss'])) <= 2e-6
+    assert abs(out['l2_loss'].item() - float(g['l2'])) <= 1e-6
+    assert C.rel_err(sd['encoder.conv_in.weight'].grad, g['grad_enc_conv_in']) < 1e-4
+    assert C.rel_err(sd['decoder.conv_out.weight'].grad, g['grad_dec_conv_out']) < 1e-4
+    ref_norm = dict(zip(g['grad_names'].tolist(), g['grad_norms'].tolist()))
+    for n, t in sd.items():
+        if t.grad is not None and n in ref_norm:
+            assert abs(float(t.grad.double().norm()) - ref_norm[n]) <= 1e-4 * ref_norm[n] + 1e-7, n
+    assert C.rel_err(out['new_ema_count'], g['new_ema_count']) < 1e-6
+    assert C.rel_err(out['new_ema_weight'].double().sum(1), g['new_ema_weight_rowsum']) < 1e-6
+    assert C.rel_err(out['new_codebook'].double().sum(1), g['new_codebook_rowsum']) < 1e-5
+
+
 def test_survey_known_answers():
     """The SURVEY.md 8(c) known-answer values, which were produced independently of make_golden.py."""
     g = C.golden('cfg1_standard')
