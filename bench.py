@@ -12,7 +12,9 @@ way: device-resident value, end-to-end e2e, conv roofline, loss check):
     cfg4  gumbel_vqgan.yaml (Gumbel K=1024 + LPIPS-VGG16 + StyleGAN2 discriminator ACTIVE, R1 every 16th step), B=32/GPU
     cfg5  EMA VQGAN: gumbel_vqgan.yaml's loss / autoencoder with the EMA quantizer at K=8192, B=32/GPU
 and "strict" = cfg2 in the fp32-parity numeric mode.  `--config X` makes X the headline and skips the sub-records;
-`--only-headline` skips them for cfg2.  Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+`--only-headline` skips them for cfg2.  At N=1 the line also carries `cpu_baseline` (the oracle port on the host cores) and
+`torch_eager_gpu_baseline` (the same port as stock torch eager ops on this GPU: fp32 / TF32 convolutions and bf16 autocast; none
+of this repository's kernels).  Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
 """
 from __future__ import annotations
 
